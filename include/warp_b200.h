@@ -1,0 +1,219 @@
+/*
+ * warp_b200.h -- C ABI of libwarp_b200.so, the B200-native (sm_100a) replacement for the
+ * mesh / BVH spatial-query path of NVIDIA/warp's native library (warp.so).
+ *
+ * Part 1 re-exports, with identical names, argument order and meaning, the entry points that the
+ * reference's Python layer binds for this path (warp/_src/context.py:7000-7070 binding
+ * warp/native/warp.h:93-140).  A maintainer can point `warp._src.context.runtime.core` at this
+ * library for these symbols and `wp.Mesh(...)` / `wp.Bvh(...)` / `.refit()` / `.rebuild()` keep
+ * working (INTEGRATION.md shows the stub).
+ *
+ * Part 2 is the small slice of the runtime API (allocation, copies, streams, events) this path
+ * needs, again under the reference's names (warp/native/warp.h:38-84, 682-764).
+ *
+ * Part 3 is new: the reference has no C entry point for queries (they are header code inlined
+ * into NVRTC-compiled user kernels, warp/native/mesh.h); here they are batched calls returning
+ * the fields of MeshQueryPoint / MeshQueryRay (warp/_src/types.py:7786-7848) as SoA arrays.
+ *
+ * Conventions (same as the reference): an object id is the address of a device-resident
+ * descriptor (layout below, identical to wp::BVH / wp::Mesh so kernels that dereference the id keep
+ * working once wp_b200_bvh_sync_reference_layout() has been called); id 0 means failure and
+ * wp_get_error_string() says why; points / indices / lowers / uppers / groups are BORROWED -- the
+ * caller keeps them alive and may modify them in place before refit(); all work is enqueued on the
+ * current stream of the calling thread's device (wp_cuda_context_set_stream) and is asynchronous.
+ * `context` arguments accept NULL (= current device) or a handle from
+ * wp_cuda_device_get_primary_context().  No entry point falls back to the CPU.
+ */
+#ifndef WARP_B200_H
+#define WARP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WP_B200_API __attribute__((visibility("default")))
+
+/* wp::vec3 -- three packed floats (warp/native/vec.h) */
+typedef struct {
+    float c[3];
+} wp_vec3;
+
+/* wp::array_t<T>, passed BY VALUE (warp/native/array.h:173-277, warp/_src/types.py:2417-2425) */
+typedef struct {
+    uint64_t data;
+    uint64_t grad;
+    int32_t shape[4];
+    int32_t strides[4];
+    uint16_t ndim;
+    uint16_t flags;
+} wp_array_t;
+
+/* BVH_CONSTRUCTOR_* (warp/native/bvh.h:21-24) */
+#define WP_BVH_CONSTRUCTOR_SAH 0
+#define WP_BVH_CONSTRUCTOR_MEDIAN 1
+#define WP_BVH_CONSTRUCTOR_LBVH 2
+#define WP_BVH_CONSTRUCTOR_CUBQL (-1)
+
+/* device-resident descriptors at `id`; field-for-field wp::BVH (bvh.h:176-207, 112 bytes) and
+ * wp::Mesh (mesh.h:18-35, 328 bytes) */
+typedef struct {
+    void* node_lowers;  /* BVHPackedNodeHalf[max_nodes]; valid after wp_b200_bvh_sync_reference_layout */
+    void* node_uppers;
+    int* node_parents;
+    int* node_counts;
+    int* primitive_indices;
+    int max_depth, max_nodes, num_nodes, num_leaf_nodes;
+    int* root;
+    wp_vec3* item_lowers;
+    wp_vec3* item_uppers;
+    int* item_groups;
+    int num_items, leaf_size, constructor_type;
+    void* context;
+} wp_b200_bvh_desc;
+
+typedef struct {
+    wp_array_t points, velocities, indices;
+    wp_vec3* lowers;
+    wp_vec3* uppers;
+    void* solid_angle_props;
+    int num_points, num_tris;
+    wp_b200_bvh_desc bvh;
+    void* context;
+    float average_edge_length;
+} wp_b200_mesh_desc;
+
+/* ---------------------------------------------------------------------------------------------
+ * Part 1 -- drop-in entry points (same symbols as warp.so)
+ * ------------------------------------------------------------------------------------------- */
+
+/* replaces warp/native/bvh.cu:852-875 (decl. warp.h:99-101).  Only constructor_type LBVH builds on
+ * the GPU; SAH / MEDIAN / CUBQL return 0 with an error string (this library has no CPU builder). */
+WP_B200_API uint64_t wp_bvh_create_device(void* context, wp_vec3* lowers, wp_vec3* uppers, int num_items,
+                                          int constructor_type, int* groups, int leaf_size);
+/* replaces bvh.cu:878-888 (warp.h:102) */
+WP_B200_API void wp_bvh_destroy_device(uint64_t id);
+/* replaces bvh.cu:809-817 (warp.h:103) */
+WP_B200_API void wp_bvh_refit_device(uint64_t id);
+/* replaces bvh.cu:819-843 (warp.h:104): in-place LBVH rebuild, no allocation, capture safe */
+WP_B200_API void wp_bvh_rebuild_device(uint64_t id);
+
+/* replaces warp/native/mesh.cu:258-345 (warp.h:123-134) */
+WP_B200_API uint64_t wp_mesh_create_device(void* context, wp_array_t points, wp_array_t velocities, wp_array_t tris,
+                                           int num_points, int num_tris, int support_winding_number,
+                                           int constructor_type, int* groups, int bvh_leaf_size);
+/* replaces mesh.cu:347-364 (warp.h:135) */
+WP_B200_API void wp_mesh_destroy_device(uint64_t id);
+/* replaces mesh.cu:368-407 (warp.h:136): 1 ok, 0 error */
+WP_B200_API int wp_mesh_refit_device(uint64_t id);
+/* replaces mesh.cu:409-433 (warp.h:139): shape must match; triggers a refit */
+WP_B200_API int wp_mesh_set_points_device(uint64_t id, wp_array_t points);
+/* replaces mesh.cu:435-456 (warp.h:142) */
+WP_B200_API void wp_mesh_set_velocities_device(uint64_t id, wp_array_t velocities);
+/* replaces warp/native/error.cpp:8-27 (warp.h:38) */
+WP_B200_API const char* wp_get_error_string(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Part 2 -- runtime slice (names of warp.h:60-84, 682-764)
+ * ------------------------------------------------------------------------------------------- */
+WP_B200_API int wp_init(const char* expected_version);
+WP_B200_API int wp_is_cuda_enabled(void);
+WP_B200_API int wp_cuda_device_get_count(void);
+WP_B200_API void* wp_cuda_device_get_primary_context(int ordinal);
+WP_B200_API void* wp_cuda_context_get_current(void);
+WP_B200_API void wp_cuda_context_set_current(void* context);
+WP_B200_API void wp_cuda_context_synchronize(void* context);
+WP_B200_API void* wp_cuda_context_get_stream(void* context);
+WP_B200_API void wp_cuda_context_set_stream(void* context, void* stream, int sync);
+WP_B200_API void* wp_cuda_stream_create(void* context, int priority);
+WP_B200_API void wp_cuda_stream_destroy(void* context, void* stream);
+WP_B200_API void wp_cuda_stream_synchronize(void* stream);
+WP_B200_API void* wp_cuda_event_create(void* context, unsigned flags); /* flags: 1 = disable timing */
+WP_B200_API void wp_cuda_event_destroy(void* event);
+WP_B200_API void wp_cuda_event_record(void* event, void* stream, int external);
+WP_B200_API void wp_cuda_event_synchronize(void* event);
+WP_B200_API float wp_cuda_event_elapsed_time(void* start_event, void* end_event);
+WP_B200_API void* wp_alloc_device(void* context, size_t s, const char* tag);
+WP_B200_API void wp_free_device(void* context, void* ptr);
+WP_B200_API void* wp_alloc_pinned(size_t s, const char* tag);
+WP_B200_API void wp_free_pinned(void* ptr);
+WP_B200_API int wp_memcpy_h2d(void* context, void* dest, void* src, size_t n, void* stream);
+WP_B200_API int wp_memcpy_d2h(void* context, void* dest, void* src, size_t n, void* stream);
+WP_B200_API int wp_memcpy_d2d(void* context, void* dest, void* src, size_t n, void* stream);
+WP_B200_API int wp_memset_device(void* context, void* dest, int value, size_t n, void* stream);
+/* device-wide query used by bench.py (L2 size, SM count, clocks, free memory) */
+WP_B200_API int wp_b200_device_attr(int ordinal, const char* name, long long* value);
+WP_B200_API int wp_b200_device_name(int ordinal, char* buf, int len);
+
+/* ---------------------------------------------------------------------------------------------
+ * Part 3 -- batched queries (new; semantics of warp/native/mesh.h)
+ * All pointers are DEVICE pointers unless the name ends in _host.  Points / starts / dirs are n x 3
+ * packed floats.  Outputs follow the struct-returning overloads (mesh.h:1514-1540, 1583-1608,
+ * 2216-2257): on a miss result = 0 and every other field is 0.  Return 1 ok, 0 error.
+ * ------------------------------------------------------------------------------------------- */
+
+/* wp.mesh_query_point_no_sign (mesh.h:501-676) */
+WP_B200_API int wp_b200_mesh_query_point_no_sign(uint64_t id, const float* points, int64_t n, float max_dist,
+                                                 uint8_t* result, int32_t* face, float* u, float* v);
+/* wp.mesh_query_point (mesh.h:128-307 + 2286-2359): sign = -1 inside / +1 outside */
+WP_B200_API int wp_b200_mesh_query_point(uint64_t id, const float* points, int64_t n, float max_dist, uint8_t* result,
+                                         float* sign, int32_t* face, float* u, float* v);
+/* wp.mesh_query_ray (mesh.h:1768-1891): normal is n x 3 */
+WP_B200_API int wp_b200_mesh_query_ray(uint64_t id, const float* starts, const float* dirs, int64_t n, float max_t,
+                                       uint8_t* result, float* sign, int32_t* face, float* t, float* u, float* v,
+                                       float* normal);
+
+/* same three calls with HOST buffers: inputs are copied to the device, the query runs, results are
+ * copied back, and the call returns after the results are valid (synchronous).  Work is chunked and
+ * double-buffered through pinned staging so copies overlap traversal. */
+WP_B200_API int wp_b200_mesh_query_point_no_sign_host(uint64_t id, const float* points, int64_t n, float max_dist,
+                                                      uint8_t* result, int32_t* face, float* u, float* v);
+WP_B200_API int wp_b200_mesh_query_point_host(uint64_t id, const float* points, int64_t n, float max_dist,
+                                              uint8_t* result, float* sign, int32_t* face, float* u, float* v);
+WP_B200_API int wp_b200_mesh_query_ray_host(uint64_t id, const float* starts, const float* dirs, int64_t n,
+                                            float max_t, uint8_t* result, float* sign, int32_t* face, float* t,
+                                            float* u, float* v, float* normal);
+
+/* traversal counters of the NEXT query call on this thread: when `enable` is non-zero the next
+ * query also counts 64-byte sibling-pair fetches and 48-byte triangle fetches (slower, used for the
+ * bytes-fetched / nodes-per-second report); read them back with wp_b200_query_stats_read. */
+WP_B200_API void wp_b200_query_stats_enable(int enable);
+WP_B200_API void wp_b200_query_stats_read(unsigned long long* pair_fetches, unsigned long long* tri_fetches);
+
+/* in-place LBVH rebuild of a mesh's tree from the current vertices (the reference only offers this
+ * for wp.Bvh, bvh.cu:819-843; here a Mesh gets it too): no allocation, same buffers. 1 ok / 0 error */
+WP_B200_API int wp_b200_mesh_rebuild_device(uint64_t id);
+
+/* introspection for parity checks / drop-in kernels */
+typedef struct {
+    int num_items, leaf_size, max_nodes, root, height, deep;
+    float total_lower[3], total_upper[3], inv_edges[3];
+} wp_b200_bvh_info_t;
+WP_B200_API int wp_b200_bvh_info(uint64_t id, wp_b200_bvh_info_t* info); /* synchronises the stream */
+/* (re)materialise node_lowers / node_uppers / node_parents / root of the descriptor at `id` in the
+ * reference's layout (bvh.h:161-207) from the native pair layout.  Works for Bvh and Mesh ids. */
+WP_B200_API int wp_b200_bvh_sync_reference_layout(uint64_t id);
+/* host copies of the tree products (any pointer may be NULL): sorted 32-bit Morton keys [n],
+ * primitive_indices [n], node_lowers / node_uppers [2n-1] x 16 bytes, node_parents [2n-1], root [1].
+ * Calls wp_b200_bvh_sync_reference_layout first and synchronises. */
+WP_B200_API int wp_b200_bvh_download(uint64_t id, uint32_t* keys, int32_t* primitive_indices, void* node_lowers,
+                                     void* node_uppers, int32_t* node_parents, int32_t* root);
+
+/* ---------------------------------------------------------------------------------------------
+ * multi-GPU: query batches are sharded by the host, results gathered with NCCL over NVLink.
+ * One communicator per process (one process per GPU).  libnccl.so.2 is dlopen()ed on first use.
+ * ------------------------------------------------------------------------------------------- */
+WP_B200_API int wp_b200_nccl_load(const char* libnccl_path);       /* NULL = default search */
+WP_B200_API int wp_b200_nccl_unique_id(void* id128);               /* rank 0: fills 128 bytes */
+WP_B200_API int wp_b200_nccl_init(const void* id128, int world_size, int rank);
+WP_B200_API int wp_b200_nccl_allgather(const void* send, void* recv, size_t bytes_per_rank); /* device ptrs */
+WP_B200_API int wp_b200_nccl_allreduce_max_f32(float* inout_device, size_t count);
+WP_B200_API int wp_b200_nccl_barrier(void);
+WP_B200_API void wp_b200_nccl_destroy(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WARP_B200_H */

@@ -1,0 +1,183 @@
+"""GPU parity tests of LBVH build / refit / rebuild: the CUDA path (through the C ABI) against the
+oracle restatement of warp/native/bvh.cu on the same inputs.  Bit-exact: Morton keys, sorted
+primitive order, hierarchy topology (children, parents, root, packed-leaf ranges) and node boxes."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_tree_equal, random_boxes, visible_nodes
+from warp_b200 import meshgen as mg
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_mesh(wp, P, I, leaf=None, **kw):
+    pts = wp.array(P, dtype=wp.vec3, device="cuda:0")
+    idx = wp.array(I, dtype=wp.int32, device="cuda:0")
+    return wp.Mesh(pts, idx, bvh_constructor="lbvh", bvh_leaf_size=leaf, **kw)
+
+
+MESHES = {
+    "cube": lambda: (mg.CUBE_POINTS, mg.CUBE_INDICES_RH),
+    "ico2_noisy": lambda: mg.noisy_sphere(2, 0.05, 11),
+    "ico5_noisy": lambda: mg.noisy_sphere(5, 0.02, 1),
+    "height65": lambda: mg.heightfield(65),
+    "cloth130": lambda: mg.cloth(130, frame=3),
+}
+
+
+@pytest.mark.parametrize("name", list(MESHES))
+@pytest.mark.parametrize("leaf", [1, 2, 4, 8])
+def test_mesh_build_bit_exact(wp, oracle_mod, name, leaf):
+    P, I = MESHES[name]()
+    m = gpu_mesh(wp, P, I, leaf)
+    got = m.download_tree()
+    want = oracle_mod.mesh_lbvh_build(P, I, leaf)
+    assert_tree_equal(got, want)
+    for k in ("total_lower", "total_upper", "inv_edges"):
+        assert np.array_equal(got[k], want[k]), k
+
+
+def test_default_leaf_size_is_4(wp, oracle_mod):
+    P, I = mg.noisy_sphere(3)
+    m = gpu_mesh(wp, P, I)  # bvh_leaf_size=None -> 4 (types.py:6181-6182)
+    assert m.bvh_leaf_size == 4
+    assert_tree_equal(m.download_tree(), oracle_mod.mesh_lbvh_build(P, I, 4))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 33, 255, 256, 257, 4095, 4096, 4097, 10000, 70001])
+def test_bvh_build_sizes(wp, oracle_mod, n):
+    """Edge sizes around the sort tile (4096) and block (256) boundaries; wp.Bvh default leaf_size 1."""
+    lo, hi = random_boxes(n, seed=n)
+    b = wp.Bvh(wp.array(lo, dtype=wp.vec3), wp.array(hi, dtype=wp.vec3))
+    assert_tree_equal(b.download_tree(), oracle_mod.lbvh_build(lo, hi, 1))
+
+
+@pytest.mark.parametrize("n,leaf", [(1, 1), (1, 4), (2, 2), (3, 4), (4, 8)])
+def test_root_is_a_packed_leaf(wp, oracle_mod, n, leaf):
+    """warp/tests/geometry/test_bvh.py:423-511: single-item trees and leaf_size >= N."""
+    lo, hi = random_boxes(n, seed=7)
+    lo_d, hi_d = wp.array(lo, dtype=wp.vec3), wp.array(hi, dtype=wp.vec3)
+    b = wp.Bvh(lo_d, hi_d, leaf_size=leaf)
+    want = oracle_mod.lbvh_build(lo, hi, leaf)
+    assert_tree_equal(b.download_tree(), want)
+    lo2, hi2 = lo + 3.0, hi + 4.0
+    lo_d.assign(lo2), hi_d.assign(hi2)
+    b.refit()
+    got = b.download_tree()
+    oracle_mod.lbvh_refit(want, lo2, hi2)
+    r = want["root"]
+    for f in "xyz":
+        assert got["node_lowers"][f][r] == want["node_lowers"][f][r]
+        assert got["node_uppers"][f][r] == want["node_uppers"][f][r]
+
+
+def test_duplicate_keys_depth_rule(wp, oracle_mod):
+    """Thousands of coincident boxes: equal keys, parity tie-breaks, depth >= 32 packed leaves."""
+    for n, leaf in ((600, 1), (5000, 4)):
+        lo = np.zeros((n, 3), np.float32)
+        lo[: n // 2] += 1.0
+        lo[n // 3 : n // 2, 1] += 2.0
+        hi = lo + 0.5
+        b = wp.Bvh(wp.array(lo, dtype=wp.vec3), wp.array(hi, dtype=wp.vec3), leaf_size=leaf)
+        got = b.download_tree()
+        assert got["deep"] == 1
+        assert_tree_equal(got, oracle_mod.lbvh_build(lo, hi, leaf))
+
+
+def test_sort_cross_check_against_cub(wp, oracle_mod):
+    """The hand-written onesweep and the library sort (WARP_B200_SORT=cub) give the same tree."""
+    P, I = mg.noisy_sphere(6, 0.02, 3)  # 81 920 triangles = 20 sort tiles
+    a = gpu_mesh(wp, P, I, 4).download_tree()
+    os.environ["WARP_B200_SORT"] = "cub"
+    try:
+        b = gpu_mesh(wp, P, I, 4).download_tree()
+    finally:
+        del os.environ["WARP_B200_SORT"]
+    assert_tree_equal(a, b)
+    assert_tree_equal(a, oracle_mod.mesh_lbvh_build(P, I, 4))
+
+
+def test_large_mesh_build_properties(wp, oracle_mod):
+    """1.3 M triangles (config C2 size): full diff against the oracle + permutation / order properties."""
+    P, I = mg.noisy_sphere(8, 0.02, 1)
+    m = gpu_mesh(wp, P, I, 4)
+    got = m.download_tree()
+    assert np.all(np.diff(got["keys"].astype(np.int64)) >= 0)
+    assert np.array_equal(np.sort(got["primitive_indices"]), np.arange(len(I) // 3))
+    assert_tree_equal(got, oracle_mod.mesh_lbvh_build(P, I, 4))
+
+
+def _refit_and_compare(wp, oracle_mod, m, pts_dev, P2, I, want):
+    pts_dev.assign(P2)
+    m.refit()
+    got = m.download_tree()
+    lo2, hi2 = oracle_mod.triangle_bounds(P2, I)
+    oracle_mod.lbvh_refit(want, lo2, hi2)
+    vis = visible_nodes(want)
+    assert np.array_equal(got["parents"], want["parents"])
+    for name in ("node_lowers", "node_uppers"):
+        assert np.array_equal(got[name]["ib"], want[name]["ib"])
+        for f in "xyz":
+            assert np.array_equal(got[name][f][vis], want[name][f][vis]), (name, f)
+
+
+@pytest.mark.parametrize("leaf", [1, 4])
+def test_mesh_refit_bit_exact_on_visible_nodes(wp, oracle_mod, leaf):
+    """Refit after deformation: every node a query can reach has the oracle's box (muted nodes under
+    packed leaves keep stale boxes in the reference too, bvh.cu:100-118, and are never read)."""
+    P, I = mg.noisy_sphere(5, 0.02, 1)
+    pts = wp.array(P, dtype=wp.vec3)
+    m = wp.Mesh(pts, wp.array(I, dtype=wp.int32), bvh_leaf_size=leaf)
+    want = oracle_mod.mesh_lbvh_build(P, I, leaf)
+    _refit_and_compare(wp, oracle_mod, m, pts, mg.renoise_sphere(P, 0.05, 3), I, want)
+    _refit_and_compare(wp, oracle_mod, m, pts, mg.renoise_sphere(P, 0.01, 4), I, want)  # second refit: counter parity
+
+
+def test_points_setter_triggers_refit(wp, oracle_mod):
+    """warp/tests/geometry/test_mesh_query_point.py:891-972: assigning mesh.points refits."""
+    P, I = mg.noisy_sphere(4)
+    m = gpu_mesh(wp, P, I, 4)
+    want = oracle_mod.mesh_lbvh_build(P, I, 4)
+    P2 = (P + np.array([10, 0, 0], np.float32)).astype(np.float32)
+    m.points = wp.array(P2, dtype=wp.vec3)
+    got = m.download_tree()
+    lo2, hi2 = oracle_mod.triangle_bounds(P2, I)
+    oracle_mod.lbvh_refit(want, lo2, hi2)
+    r = want["root"]
+    assert got["node_lowers"]["x"][r] == want["node_lowers"]["x"][r]
+    with pytest.raises(RuntimeError, match="same shape"):
+        m.points = wp.array(P2[:-1], dtype=wp.vec3)
+
+
+def test_bvh_refit_then_rebuild(wp, oracle_mod):
+    """warp/tests/geometry/test_bvh.py:186-262 procedure (100 boxes, rng 123) on the build products."""
+    lo, hi = random_boxes(100, seed=123)
+    lo_d, hi_d = wp.array(lo, dtype=wp.vec3), wp.array(hi, dtype=wp.vec3)
+    b = wp.Bvh(lo_d, hi_d, constructor="lbvh", leaf_size=2)
+    want = oracle_mod.lbvh_build(lo, hi, 2)
+    assert_tree_equal(b.download_tree(), want)
+    lo2, hi2 = random_boxes(100, seed=124)
+    lo_d.assign(lo2), hi_d.assign(hi2)
+    b.refit()
+    got = b.download_tree()
+    oracle_mod.lbvh_refit(want, lo2, hi2)
+    vis = visible_nodes(want)
+    for f in "xyz":
+        assert np.array_equal(got["node_lowers"][f][vis], want["node_lowers"][f][vis])
+        assert np.array_equal(got["node_uppers"][f][vis], want["node_uppers"][f][vis])
+    b.rebuild()
+    assert_tree_equal(b.download_tree(), oracle_mod.lbvh_build(lo2, hi2, 2))
+    b.rebuild()  # twice: buffers and counters are reused
+    assert_tree_equal(b.download_tree(), oracle_mod.lbvh_build(lo2, hi2, 2))
+
+
+def test_native_failure_raises_with_error_string(wp):
+    """warp/tests/geometry/test_mesh.py:443-485: id 0 -> RuntimeError carrying wp_get_error_string()."""
+    P, I = mg.CUBE_POINTS, mg.CUBE_INDICES_RH
+    with pytest.raises(RuntimeError, match="Failed to create mesh: .*constructor"):
+        gpu_mesh_sah = wp.Mesh(wp.array(P, dtype=wp.vec3), wp.array(I, dtype=wp.int32), bvh_constructor="sah")  # noqa: F841
+    lo, hi = random_boxes(4)
+    with pytest.raises(RuntimeError, match="Failed to create BVH"):
+        wp.Bvh(wp.array(lo, dtype=wp.vec3), wp.array(hi, dtype=wp.vec3), constructor="median")

@@ -1,0 +1,215 @@
+"""GPU parity tests of the batched queries: CUDA (through the C ABI) vs the oracle on the same
+tree.  Every field is compared for exact equality (the library is built with -fmad=false and
+visits nodes in the reference's order, so even exact distance ties resolve identically); the
+tolerance form of the bar (1e-5 relative on u, v, t; ties counted) is asserted as well so the test
+documents the contract BASELINE.json states."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_results_equal
+from warp_b200 import meshgen as mg
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "golden_cpu.npz")
+POINT_FIELDS = ("result", "sign", "face", "u", "v")
+RAY_FIELDS = ("result", "sign", "face", "t", "u", "v", "normal")
+
+
+def gpu_mesh(wp, P, I, leaf=4):
+    return wp.Mesh(wp.array(P, dtype=wp.vec3), wp.array(I, dtype=wp.int32), bvh_constructor="lbvh", bvh_leaf_size=leaf)
+
+
+def test_cube_golden_vectors(wp):
+    """warp/tests/geometry/test_mesh.py:111-187 through the CUDA path, leaf sizes 1, 2, 4."""
+    d = np.array([-1.2, 2.3, -3.4], np.float32)
+    d /= np.linalg.norm(d)
+    for idx, sgn in ((mg.CUBE_INDICES_RH, -1.0), (mg.CUBE_INDICES_LH, 1.0)):
+        for leaf in (1, 2, 4):
+            m = gpu_mesh(wp, mg.CUBE_POINTS, idx, leaf)
+            p = wp.mesh_query_point(m, np.array([[0.1, 0.2, 0.3]], np.float32), 1e6)
+            assert p.result[0] == 1 and p.face[0] == 1 and p.sign[0] == sgn
+            tri = mg.CUBE_POINTS[idx.reshape(-1, 3)[1]]
+            pos = p.u[0] * tri[0] + p.v[0] * tri[1] + (1 - p.u[0] - p.v[0]) * tri[2]
+            assert np.allclose(pos, (0.1, 0.2, 0.5), atol=1e-6)
+            r = wp.mesh_query_ray(m, np.array([[0.1, 0.2, 0.3]], np.float32), d[None], 1e6)
+            assert r.result[0] == 1 and r.face[0] == 4 and abs(r.t[0] - 0.557828) < 1e-6
+            assert np.sign(r.sign[0]) == sgn
+
+
+def test_reference_fixture_answers(wp):
+    """Answers recorded from the reference C++ on an LBVH tree (tests/golden/golden_cpu.npz)."""
+    g = np.load(GOLD)
+    P, I, Q, S, D = (g[k] for k in ("mesh_points", "mesh_indices", "queries", "ray_starts", "ray_dirs"))
+    for leaf in (1, 4):
+        m = gpu_mesh(wp, P, I, leaf)
+        assert_results_equal(wp.mesh_query_point(m, Q, 1e6).numpy(), {f: g[f"lbvh{leaf}_point_{f}"] for f in POINT_FIELDS}, POINT_FIELDS)
+        assert_results_equal(wp.mesh_query_point(m, Q, 0.5).numpy(), {f: g[f"lbvh{leaf}_point05_{f}"] for f in POINT_FIELDS}, POINT_FIELDS)
+        assert_results_equal(wp.mesh_query_ray(m, S, D, 1e6).numpy(), {f: g[f"lbvh{leaf}_ray_{f}"] for f in RAY_FIELDS}, RAY_FIELDS)
+
+
+@pytest.mark.parametrize("leaf", [1, 4, 8])
+def test_point_queries_bit_exact(wp, oracle_mod, leaf):
+    P, I = mg.noisy_sphere(5, 0.05, 1)
+    m = gpu_mesh(wp, P, I, leaf)
+    tree = oracle_mod.mesh_lbvh_build(P, I, leaf)
+    Q = mg.box_queries(P, 20000, seed=2)
+    for max_dist in (1e6, 0.1):
+        want = oracle_mod.query_point(P, I, tree, Q, max_dist)
+        got = wp.mesh_query_point(m, Q, max_dist).numpy()  # host buffers -> *_host entry point
+        assert_results_equal(got, want, POINT_FIELDS)
+        got_ns = wp.mesh_query_point_no_sign(m, wp.array(Q, dtype=wp.vec3), max_dist).numpy()  # device buffers
+        assert_results_equal(got_ns, dict(want, sign=np.zeros_like(want["sign"])), POINT_FIELDS)
+    # the contract as BASELINE.json words it: faces equal except exact ties (counted), u/v within 1e-5
+    want = oracle_mod.query_point(P, I, tree, Q, 1e6)
+    got = wp.mesh_query_point(m, Q, 1e6).numpy()
+    ties = int((got["face"] != want["face"]).sum())
+    assert ties == 0
+    assert np.allclose(got["u"], want["u"], rtol=1e-5, atol=1e-7) and np.allclose(got["v"], want["v"], rtol=1e-5, atol=1e-7)
+
+
+def test_point_queries_on_surface_points_have_many_ties(wp, oracle_mod):
+    """Queries AT mesh vertices: distance 0 to every incident face -> exact ties; same winner as the reference order."""
+    P, I = mg.icosphere(4)
+    m = gpu_mesh(wp, P, I, 4)
+    tree = oracle_mod.mesh_lbvh_build(P, I, 4)
+    Q = P[:2000].copy()
+    assert_results_equal(wp.mesh_query_point_no_sign(m, Q, 1e6).numpy(), oracle_mod.query_point_no_sign(P, I, tree, Q, 1e6), ("result", "face", "u", "v"))
+
+
+@pytest.mark.parametrize("leaf", [1, 4])
+def test_ray_queries_bit_exact(wp, oracle_mod, leaf):
+    P, I = mg.heightfield(129)
+    m = gpu_mesh(wp, P, I, leaf)
+    tree = oracle_mod.mesh_lbvh_build(P, I, leaf)
+    S, D = mg.pinhole_rays(160, 120)
+    want = oracle_mod.query_ray(P, I, tree, S, D, 1e6)
+    assert want["result"].mean() > 0.3
+    assert_results_equal(wp.mesh_query_ray(m, S, D, 1e6).numpy(), want, RAY_FIELDS)
+    got = wp.mesh_query_ray(m, wp.array(S, dtype=wp.vec3), wp.array(D, dtype=wp.vec3), 1.0).numpy()
+    assert_results_equal(got, oracle_mod.query_ray(P, I, tree, S, D, 1.0), RAY_FIELDS)
+    # grid-aligned vertical rays hit edges / vertices exactly: exercises the fp64 edge fallback (intersect.h:394-404)
+    xs = np.linspace(0, 1, 129, dtype=np.float32)
+    gx, gy = np.meshgrid(xs[::4], xs[::4], indexing="ij")
+    S2 = np.stack([gx.ravel(), gy.ravel(), np.full(gx.size, 2.0, np.float32)], 1).astype(np.float32)
+    D2 = np.tile(np.array([[0, 0, -1]], np.float32), (S2.shape[0], 1))
+    want2 = oracle_mod.query_ray(P, I, tree, S2, D2, 1e6)
+    assert want2["result"].all()
+    assert_results_equal(wp.mesh_query_ray(m, S2, D2, 1e6).numpy(), want2, RAY_FIELDS)
+
+
+def test_ray_on_shared_edge_never_leaks(wp):
+    """warp/tests/geometry/test_mesh_query_ray.py:678-722: 900 rays at a 2-triangle quad all hit."""
+    P = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], np.float32) - np.array([0.5, 0.5, 0], np.float32)
+    I = np.array([0, 1, 2, 0, 2, 3], np.int32)
+    g = np.arange(0.1, 0.4, 0.01, dtype=np.float32)
+    gx, gy = np.meshgrid(g, g, indexing="ij")
+    S = np.stack([gx.ravel(), gy.ravel(), np.ones(gx.size, np.float32)], 1).astype(np.float32)
+    D = np.tile(np.array([[0, 0, -1]], np.float32), (S.shape[0], 1))
+    S[:, :2] = S[:, [0, 0]]  # along the diagonal x == y: exactly on the shared edge
+    for leaf in (1, 2, 4):
+        r = wp.mesh_query_ray(gpu_mesh(wp, P, I, leaf), S, D, 1e6)
+        assert r.result.all(), f"leaf {leaf}: {int((r.result == 0).sum())} rays leaked"
+
+
+def test_ray_parallel_to_slab_boundaries(wp, oracle_mod):
+    """warp/tests/geometry/test_mesh_query_ray.py:725-842: axis-aligned rays whose origin lies on AABB faces."""
+    P, I = mg.CUBE_POINTS, mg.CUBE_INDICES_RH
+    S = np.array([[0.5, 0.0, 2.0], [-0.5, 0.25, 2.0], [0.0, 0.5, -2.0], [2.0, 0.5, 0.0], [0.0, -2.0, 0.5]], np.float32)
+    D = np.array([[0, 0, -1], [0, 0, -1], [0, 0, 1], [-1, 0, 0], [0, 1, 0]], np.float32)
+    for leaf in (1, 2, 4):
+        tree = oracle_mod.mesh_lbvh_build(P, I, leaf)
+        want = oracle_mod.query_ray(P, I, tree, S, D, 1e6)
+        got = wp.mesh_query_ray(gpu_mesh(wp, P, I, leaf), S, D, 1e6).numpy()
+        assert got["result"].all()
+        assert_results_equal(got, want, RAY_FIELDS)
+
+
+def test_queries_after_refit(wp, oracle_mod):
+    """warp/tests/geometry/test_mesh.py:319-357: translate +10 x, refit, hit new / miss old; then full parity."""
+    P, I = mg.noisy_sphere(4, 0.02, 9)
+    pts = wp.array(P, dtype=wp.vec3)
+    m = wp.Mesh(pts, wp.array(I, dtype=wp.int32))
+    P2 = (P + np.array([10, 0, 0], np.float32)).astype(np.float32)
+    pts.assign(P2)
+    m.refit()
+    d = np.array([[0.0, 0.0, -1.0]], np.float32)
+    assert wp.mesh_query_ray(m, np.array([[0.0, 0.0, 5.0]], np.float32), d, 1e6).result[0] == 0
+    assert wp.mesh_query_ray(m, np.array([[10.0, 0.0, 5.0]], np.float32), d, 1e6).result[0] == 1
+    tree = oracle_mod.mesh_lbvh_build(P, I, 4)
+    lo2, hi2 = oracle_mod.triangle_bounds(P2, I)
+    oracle_mod.lbvh_refit(tree, lo2, hi2)
+    Q = mg.box_queries(P2, 5000, seed=4)
+    assert_results_equal(wp.mesh_query_point(m, Q, 1e6).numpy(), oracle_mod.query_point(P2, I, tree, Q, 1e6), POINT_FIELDS)
+    S, D = mg.random_rays(P2, 5000, seed=5)
+    assert_results_equal(wp.mesh_query_ray(m, S, D, 1e6).numpy(), oracle_mod.query_ray(P2, I, tree, S, D, 1e6), RAY_FIELDS)
+
+
+def test_empty_and_ragged_batches(wp, oracle_mod):
+    P, I = mg.noisy_sphere(2)
+    m = gpu_mesh(wp, P, I)
+    r = wp.mesh_query_point_no_sign(m, np.zeros((0, 3), np.float32), 1.0)
+    assert r.result.shape == (0,)
+    tree = oracle_mod.mesh_lbvh_build(P, I, 4)
+    for n in (1, 31, 33, 129, 1000):
+        Q = mg.box_queries(P, n, seed=n)
+        assert_results_equal(wp.mesh_query_point(m, Q, 1e6).numpy(), oracle_mod.query_point(P, I, tree, Q, 1e6), POINT_FIELDS)
+    # max_dist so small nothing is found: all fields keep their zero defaults (mesh.h:1514-1521)
+    far = np.full((5, 3), 100.0, np.float32)
+    r = wp.mesh_query_point(m, far, 1.0).numpy()
+    assert not r["result"].any() and not r["face"].any() and not r["u"].any() and not r["sign"].any()
+    rr = wp.mesh_query_ray(m, far, np.tile(np.array([[1, 0, 0]], np.float32), (5, 1)), 1e6).numpy()
+    assert not rr["result"].any() and not rr["normal"].any() and not rr["t"].any()
+
+
+def test_sliver_triangles_are_skipped(wp, oracle_mod):
+    """mesh.h:563: near-degenerate faces never win a closest-point query."""
+    P = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [1e-9, 0, 1], [5e-10, 1e-12, 1]], np.float32)
+    I = np.array([0, 1, 2, 3, 4, 5], np.int32)
+    m = gpu_mesh(wp, P, I, 1)
+    tree = oracle_mod.mesh_lbvh_build(P, I, 1)
+    Q = np.array([[0, 0, 1.0], [0.2, 0.2, 0.4], [0, 0, 0.9]], np.float32)
+    want = oracle_mod.query_point_no_sign(P, I, tree, Q, 1e6)
+    got = wp.mesh_query_point_no_sign(m, Q, 1e6).numpy()
+    assert (got["face"] == 0).all()
+    assert_results_equal(got, want, ("result", "face", "u", "v"))
+
+
+def test_large_batch_properties_c2_shape(wp, oracle_mod):
+    """Config C2 shapes (1.3 M triangles, 4 M of the 16 M queries): sampled oracle diff + size-independent
+    properties: found everywhere (max_dist 1e6), barycentrics in range, reported point is no farther than
+    any of 64 random faces, host and device entry points agree exactly."""
+    P, I = mg.noisy_sphere(8, 0.02, 1)
+    m = gpu_mesh(wp, P, I, 4)
+    Q = mg.box_queries(P, 1 << 22, seed=2)
+    got = wp.mesh_query_point_no_sign(m, Q, 1e6).numpy()
+    assert got["result"].all()
+    u, v = got["u"], got["v"]
+    assert (u >= 0).all() and (v >= 0).all() and (u + v <= 1 + 1e-6).all()
+    tri = P[I.reshape(-1, 3)[got["face"]]]
+    c = u[:, None] * tri[:, 0] + v[:, None] * tri[:, 1] + (1 - u - v)[:, None] * tri[:, 2]
+    d = np.linalg.norm(c - Q, axis=1)
+    rng = np.random.default_rng(0)
+    others = P[I.reshape(-1, 3)[rng.integers(0, len(I) // 3, 64)]].mean(axis=1)  # centroids of 64 random faces
+    assert (d[:, None] <= np.linalg.norm(Q[:, None, :] - others[None], axis=2) + 1e-5).all()
+    dev = wp.mesh_query_point_no_sign(m, wp.array(Q, dtype=wp.vec3), 1e6).numpy()
+    assert_results_equal(dev, got, ("result", "face", "u", "v"))
+    tree = oracle_mod.mesh_lbvh_build(P, I, 4)
+    sel = rng.integers(0, Q.shape[0], 20000)
+    want = oracle_mod.query_point_no_sign(P, I, tree, Q[sel], 1e6)
+    assert_results_equal({k: got[k][sel] for k in ("result", "face", "u", "v")}, want, ("result", "face", "u", "v"))
+
+
+def test_query_stats_counters(wp, oracle_mod):
+    P, I = mg.noisy_sphere(4)
+    m = gpu_mesh(wp, P, I, 4)
+    Q = wp.array(mg.box_queries(P, 4096, seed=1), dtype=wp.vec3)
+    with wp.query_stats() as st:
+        wp.mesh_query_point_no_sign(m, Q, 1e6)
+        wp.synchronize()
+    assert st.pair_fetches > 4096 and st.tri_fetches > 4096
+    tree = oracle_mod.mesh_lbvh_build(P, I, 4)
+    want = oracle_mod.query_point_no_sign(P, I, tree, Q.numpy(), 1e6, stats=True)
+    assert st.tri_fetches == want["tris_tested"]  # same nodes visited in the same order

@@ -1,0 +1,184 @@
+"""CPU tests: the oracle restatement (oracle/lbvh_oracle.c) against the reference's golden vectors,
+the committed fixtures produced by the reference C++ (tests/golden/golden_cpu.npz), and -- when
+oracle/_ref is present -- the reference C++ itself on fresh random inputs."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_results_equal, random_boxes, visible_nodes
+from warp_b200 import meshgen as mg
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "golden_cpu.npz")
+POINT_FIELDS = ("result", "sign", "face", "u", "v")
+RAY_FIELDS = ("result", "sign", "face", "t", "u", "v", "normal")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def test_cube_golden_vectors(oracle_mod):
+    """warp/tests/geometry/test_mesh.py:111-187: face 1 / pos (0.1,0.2,0.5) / sign -+1; ray t 0.557828, face 4."""
+    o = oracle_mod
+    d = np.array([-1.2, 2.3, -3.4], np.float32)
+    d /= np.linalg.norm(d)
+    for idx, sgn in ((mg.CUBE_INDICES_RH, -1.0), (mg.CUBE_INDICES_LH, 1.0)):
+        for leaf in (1, 2, 4):
+            tree = o.mesh_lbvh_build(mg.CUBE_POINTS, idx, leaf)
+            p = o.query_point(mg.CUBE_POINTS, idx, tree, [[0.1, 0.2, 0.3]], 1e6)
+            assert p["result"][0] == 1 and p["face"][0] == 1 and p["sign"][0] == sgn
+            tri = mg.CUBE_POINTS[idx.reshape(-1, 3)[p["face"][0]]]
+            u, v = p["u"][0], p["v"][0]
+            pos = u * tri[0] + v * tri[1] + (1 - u - v) * tri[2]
+            assert np.allclose(pos, (0.1, 0.2, 0.5), atol=1e-6)
+            r = o.query_ray(mg.CUBE_POINTS, idx, tree, [[0.1, 0.2, 0.3]], [d], 1e6)
+            assert r["result"][0] == 1 and r["face"][0] == 4
+            assert abs(r["t"][0] - 0.557828) < 1e-6
+            assert np.sign(r["sign"][0]) == sgn
+            tri = mg.CUBE_POINTS[idx.reshape(-1, 3)[4]]
+            u, v = r["u"][0], r["v"][0]
+            pos = u * tri[0] + v * tri[1] + (1 - u - v) * tri[2]
+            assert np.allclose(pos, (-0.0565217, 0.5, -0.143478), atol=1e-6)
+
+
+def test_cube_matches_reference_fixture(oracle_mod, gold):
+    """LBVH-tree answers of the oracle == reference SAH/median-tree answers (tree independent fields)."""
+    o = oracle_mod
+    d = np.array([-1.2, 2.3, -3.4], np.float32)
+    d /= np.linalg.norm(d)
+    for name, idx in (("rh", mg.CUBE_INDICES_RH), ("lh", mg.CUBE_INDICES_LH)):
+        tree = o.mesh_lbvh_build(mg.CUBE_POINTS, idx, 4)
+        p = o.query_point(mg.CUBE_POINTS, idx, tree, [[0.1, 0.2, 0.3]], 1e6)
+        r = o.query_ray(mg.CUBE_POINTS, idx, tree, [[0.1, 0.2, 0.3]], [d], 1e6)
+        for cname in ("sah", "median"):
+            for leaf in (1, 2, 4):
+                for f in POINT_FIELDS:
+                    assert np.array_equal(p[f], gold[f"cube_{name}_{cname}_{leaf}_point_{f}"]), (name, cname, leaf, f)
+                for f in RAY_FIELDS:
+                    assert np.array_equal(r[f], gold[f"cube_{name}_{cname}_{leaf}_ray_{f}"]), (name, cname, leaf, f)
+
+
+def test_traversal_matches_reference_fixture(oracle_mod, gold):
+    """Our traversal restatement run on reference-built (SAH) and LBVH trees == the reference's traversal."""
+    o = oracle_mod
+    P, I, Q, S, D = (gold[k] for k in ("mesh_points", "mesh_indices", "queries", "ray_starts", "ray_dirs"))
+    for prefix in ("sah", "lbvh1", "lbvh4"):
+        tree = {k: gold[f"{prefix}_tree_{k}"] for k in ("node_lowers", "node_uppers", "primitive_indices")}
+        tree["root"] = int(gold[f"{prefix}_tree_root"])
+        assert_results_equal(o.query_point(P, I, tree, Q, 1e6), {f: gold[f"{prefix}_point_{f}"] for f in POINT_FIELDS}, POINT_FIELDS)
+        assert_results_equal(o.query_point(P, I, tree, Q, 0.5), {f: gold[f"{prefix}_point05_{f}"] for f in POINT_FIELDS}, POINT_FIELDS)
+        assert_results_equal(o.query_ray(P, I, tree, S, D, 1e6), {f: gold[f"{prefix}_ray_{f}"] for f in RAY_FIELDS}, RAY_FIELDS)
+        ns = o.query_point_no_sign(P, I, tree, Q, 1e6)
+        for f in ("result", "face", "u", "v"):
+            assert np.array_equal(ns[f], gold[f"{prefix}_point_{f}"])
+        assert not ns["sign"].any()
+
+
+def test_lbvh_build_matches_fixture(oracle_mod, gold):
+    """Rebuilding the fixture LBVH reproduces the stored keys / order / topology (regression pin)."""
+    o = oracle_mod
+    P, I = gold["mesh_points"], gold["mesh_indices"]
+    for leaf in (1, 4):
+        t = o.mesh_lbvh_build(P, I, leaf)
+        for k in ("keys", "primitive_indices", "parents", "node_lowers", "node_uppers"):
+            assert np.array_equal(t[k], gold[f"lbvh{leaf}_tree_{k}"]), k
+        assert t["root"] == int(gold[f"lbvh{leaf}_tree_root"])
+
+
+def test_primitives_match_reference_fixture(oracle_mod, gold):
+    o = oracle_mod
+    uv = np.stack([o.closest_point_to_triangle(t[0], t[1], t[2], p) for t, p in zip(gold["tri_abc"], gold["tri_p"])])
+    assert np.array_equal(uv, gold["tri_uv"])
+    codes = np.array([o.morton3(*map(float, v)) for v in gold["morton_xyz"]], np.uint32)
+    assert np.array_equal(codes, gold["morton_code"])
+
+
+def _check_tree_invariants(tree, lowers, uppers, leaf_size):
+    n = tree["n"]
+    lo, hi, par = tree["node_lowers"], tree["node_uppers"], tree["parents"]
+    assert np.all(np.diff(tree["keys"].astype(np.int64)) >= 0), "keys sorted"
+    assert sorted(tree["primitive_indices"].tolist()) == list(range(n)), "permutation"
+    # stable: equal keys keep ascending item order
+    same = tree["keys"][1:] == tree["keys"][:-1]
+    assert np.all(tree["primitive_indices"][1:][same] > tree["primitive_indices"][:-1][same])
+    assert par[tree["root"]] == -1
+    vis = visible_nodes(tree)
+    covered = []
+    for c in vis:
+        if lo["ib"][c] >> 31:
+            s, e = int(lo["ib"][c] & 0x7FFFFFFF), int(hi["ib"][c] & 0x7FFFFFFF)
+            covered.extend(range(s, e))
+            items = tree["primitive_indices"][s:e]
+            assert np.array_equal([lo["x"][c], lo["y"][c], lo["z"][c]], lowers[items].min(axis=0))
+            assert np.array_equal([hi["x"][c], hi["y"][c], hi["z"][c]], uppers[items].max(axis=0))
+        else:
+            l, r = int(lo["ib"][c] & 0x7FFFFFFF), int(hi["ib"][c] & 0x7FFFFFFF)
+            assert par[l] == c and par[r] == c
+            for f, agg, half in (("x", min, lo), ("y", min, lo), ("z", min, lo), ("x", max, hi), ("y", max, hi), ("z", max, hi)):
+                assert half[f][c] == agg(half[f][l], half[f][r])
+    assert sorted(covered) == list(range(n)), "visible leaves partition the items"
+
+
+@pytest.mark.parametrize("n,leaf", [(1, 1), (2, 1), (2, 2), (3, 4), (100, 1), (100, 4), (1000, 8)])
+def test_lbvh_invariants_random_boxes(oracle_mod, n, leaf):
+    lo, hi = random_boxes(n, seed=123 + n)
+    t = oracle_mod.lbvh_build(lo, hi, leaf)
+    _check_tree_invariants(t, lo, hi, leaf)
+
+
+def test_lbvh_depth_rule_on_duplicates(oracle_mod):
+    """Many identical boxes -> equal keys -> parity-driven ladders deeper than 32 -> depth-rule leaves."""
+    n = 600
+    lo = np.zeros((n, 3), np.float32)
+    lo[: n // 2] += 1.0
+    hi = lo + 0.5
+    t = oracle_mod.lbvh_build(lo, hi, 1)
+    _check_tree_invariants(t, lo, hi, 1)
+    sizes = [(int(t["node_uppers"]["ib"][c] & 0x7FFFFFFF) - int(t["node_lowers"]["ib"][c] & 0x7FFFFFFF))
+             for c in visible_nodes(t) if t["node_lowers"]["ib"][c] >> 31]
+    assert max(sizes) > 1, "expected at least one depth-forced leaf holding several items"
+
+
+def test_refit_matches_rebuild_bounds(oracle_mod):
+    o = oracle_mod
+    P, I = mg.noisy_sphere(3, seed=5)
+    t = o.mesh_lbvh_build(P, I, 4)
+    P2 = (P + np.float32(10.0) * np.array([1, 0, 0], np.float32)).astype(np.float32)
+    lo2, hi2 = o.triangle_bounds(P2, I)
+    o.lbvh_refit(t, lo2, hi2)
+    _check_tree_invariants(t, lo2, hi2, 4)
+    # ray that hit the old position now misses, ray at the new position hits (test_mesh.py:319-357)
+    d = np.array([[0.0, 0.0, -1.0]], np.float32)
+    assert o.query_ray(P2, I, t, [[0.0, 0.0, 5.0]], d, 1e6)["result"][0] == 0
+    assert o.query_ray(P2, I, t, [[10.0, 0.0, 5.0]], d, 1e6)["result"][0] == 1
+
+
+def test_live_reference_agreement(oracle_mod):
+    """Fresh random inputs through the reference C++ (skipped where oracle/_ref was not shipped)."""
+    o = oracle_mod
+    if not o.ref_available():
+        pytest.skip("oracle/_ref/libwarp_ref_cpu.so not present")
+    P, I = mg.noisy_sphere(3, noise=0.1, seed=77)
+    Q = mg.box_queries(P, 3000, seed=78)
+    S, D = mg.random_rays(P, 3000, seed=79)
+    for leaf in (1, 4, 8):
+        tree = o.mesh_lbvh_build(P, I, leaf)
+        rm = o.RefMesh.from_tree(P, I, tree)
+        assert_results_equal(o.query_point(P, I, tree, Q, 1e6), rm.query_point(Q, 1e6), POINT_FIELDS)
+        assert_results_equal(o.query_point(P, I, tree, Q, 0.05), rm.query_point(Q, 0.05), POINT_FIELDS)
+        assert_results_equal(o.query_ray(P, I, tree, S, D, 1e6), rm.query_ray(S, D, 1e6), RAY_FIELDS)
+    # reference refit of a reference-built SAH tree produces exact unions of the moved item boxes
+    rm = o.RefMesh(P, I, o.SAH, 4)
+    P2 = (P * np.float32(1.3)).astype(np.float32)
+    rm.points[:] = P2
+    rm.refit()
+    lo2, hi2 = o.triangle_bounds(P2, I)
+    t2 = rm.tree()
+    vis = visible_nodes(t2)
+    for c in vis[:: max(1, len(vis) // 200)]:
+        if t2["node_lowers"]["ib"][c] >> 31:
+            s, e = int(t2["node_lowers"]["ib"][c] & 0x7FFFFFFF), int(t2["node_uppers"]["ib"][c] & 0x7FFFFFFF)
+            items = t2["primitive_indices"][s:e]
+            assert np.array_equal([t2["node_lowers"][f][c] for f in "xyz"], lo2[items].min(axis=0))

@@ -1,0 +1,54 @@
+"""warp_b200 -- B200-native (sm_100a) mesh / BVH spatial queries behind Warp's ``Mesh`` / ``Bvh`` API.
+
+Drop-in for ONE path of NVIDIA/warp: ``wp.Mesh(points, indices, bvh_constructor="lbvh")`` /
+``wp.Bvh(lowers, uppers)`` with ``.id`` / ``.refit()`` / ``.rebuild()``, plus batched equivalents of
+``mesh_query_point_no_sign``, ``mesh_query_point`` and ``mesh_query_ray``.  Pure-Python host code
+(numpy only) over a ctypes C ABI (``include/warp_b200.h``) into hand-written CUDA.  No Warp
+codegen / NVRTC, no Triton, no torch, no CPU fallback.
+"""
+
+from .types import (  # noqa: F401
+    Bvh,
+    BvhConstructor,
+    Device,
+    Mesh,
+    array,
+    bool_,
+    empty,
+    float32,
+    from_numpy,
+    get_device,
+    int32,
+    synchronize,
+    synchronize_device,
+    uint8,
+    uint32,
+    uint64,
+    vec3,
+    zeros,
+)
+from .queries import (  # noqa: F401
+    MeshQueryPoint,
+    MeshQueryRay,
+    mesh_query_point,
+    mesh_query_point_no_sign,
+    mesh_query_ray,
+    query_stats,
+)
+
+__version__ = "0.1.0"
+
+
+def is_cuda_available() -> bool:
+    from . import _lib
+
+    try:
+        return _lib.core().wp_cuda_device_get_count() > 0
+    except RuntimeError:
+        return False
+
+
+def get_error_string() -> str:
+    from . import _lib
+
+    return _lib.error_string()

@@ -1,0 +1,80 @@
+"""Builds ``warp_b200/lib/libwarp_b200.so`` with nvcc for sm_100a (in-tree, so it travels to the GPU box).
+
+``python -m warp_b200.build [--force]``.  No torch, no JIT cache: plain ``nvcc`` on the ``.cu`` files.
+
+Flags that define the numerics:
+  * ``-fmad=false``  -- no implicit FMA contraction, so every float result is bit-identical to the
+    reference's host build (g++ on x86-64 without -mfma); explicit ``fmaf`` calls stay FMAs.
+  * nvcc defaults ``-prec-div=true -prec-sqrt=true`` (IEEE division and square root); never
+    ``--use_fast_math``.
+"""
+
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libwarp_b200.so")
+SOURCES = ["api.cu", "bvh_build.cu", "bvh_refit.cu", "query.cu", "nccl_gather.cu"]
+NVCC_FLAGS = [
+    "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v", "--expt-relaxed-constexpr",
+]  # fmt: skip
+
+
+def find_nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
+
+
+def _newest_source_mtime() -> float:
+    paths = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    paths += [os.path.join(HERE, "..", "include", "warp_b200.h"), os.path.abspath(__file__)]
+    return max(os.path.getmtime(p) for p in paths if os.path.exists(p))
+
+
+def is_stale() -> bool:
+    return not os.path.exists(LIB) or os.path.getmtime(LIB) < _newest_source_mtime()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not is_stale():
+        return LIB
+    nvcc = find_nvcc()
+    os.makedirs(LIBDIR, exist_ok=True)
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_one(src: str) -> str:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        log = os.path.join(objdir, src + ".log")
+        with open(log, "w") as f:
+            f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            print(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-lcudart", "-ldl"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(path)

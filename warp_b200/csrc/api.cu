@@ -1,0 +1,830 @@
+// C ABI of libwarp_b200.so (declared in include/warp_b200.h).
+#include "../../include/warp_b200.h"
+
+#include "query.h"
+#include "state.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+
+static_assert(sizeof(wp_array_t) == 56, "wp::array_t layout (warp/native/array.h:173-277)");
+static_assert(sizeof(wp_b200_bvh_desc) == 112, "wp::BVH layout (warp/native/bvh.h:176-207)");
+static_assert(sizeof(wp_b200_mesh_desc) == 328, "wp::Mesh layout (warp/native/mesh.h:18-35)");
+static_assert(sizeof(NodeRec) == 32, "node record");
+
+namespace {
+
+char g_error[4096] = "";
+std::mutex g_lock;
+std::map<uint64_t, BvhState*> g_bvhs;
+std::map<uint64_t, MeshState*> g_meshes;
+cudaStream_t g_stream[64] = {};  // current stream per device (0 = legacy default stream)
+
+thread_local bool t_stats_enabled = false;
+unsigned long long* g_stats_dev = nullptr;
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int current_device()
+{
+    int d = 0;
+    cudaGetDevice(&d);
+    return d;
+}
+
+int context_device(void* context) { return context ? (int)((intptr_t)context - 1) : current_device(); }
+
+cudaStream_t current_stream(int device) { return (device >= 0 && device < 64) ? g_stream[device] : 0; }
+
+struct DeviceGuard {
+    int prev;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (dev != prev)
+            cudaSetDevice(dev);
+    }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+bool check(cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess)
+        return true;
+    set_error("Warp B200 CUDA error in %s: %s", what, cudaGetErrorString(e));
+    return false;
+}
+
+void fill_bvh_desc(const BvhState& s, wp_b200_bvh_desc& d, void* context)
+{
+    memset(&d, 0, sizeof(d));
+    d.node_lowers = s.ref_lowers;
+    d.node_uppers = s.ref_uppers;
+    d.node_parents = s.ref_parents;
+    d.node_counts = s.ref_counts;
+    d.primitive_indices = s.prim;
+    d.max_depth = 0;
+    d.max_nodes = s.n > 0 ? 2 * s.n - 1 : 0;
+    d.num_nodes = d.max_nodes;
+    d.num_leaf_nodes = s.n;
+    d.root = s.ref_root;
+    d.item_lowers = (wp_vec3*)s.item_lowers;
+    d.item_uppers = (wp_vec3*)s.item_uppers;
+    d.item_groups = (int*)s.groups;
+    d.num_items = s.n;
+    d.leaf_size = s.leaf_size;
+    d.constructor_type = s.constructor_type;
+    d.context = context;
+}
+
+BvhState* find_tree(uint64_t id, MeshState** mesh_out = nullptr)
+{
+    std::lock_guard<std::mutex> g(g_lock);
+    auto m = g_meshes.find(id);
+    if (m != g_meshes.end()) {
+        if (mesh_out)
+            *mesh_out = m->second;
+        return &m->second->bvh;
+    }
+    auto b = g_bvhs.find(id);
+    if (b != g_bvhs.end())
+        return b->second;
+    return nullptr;
+}
+
+bool upload_desc(MeshState* ms, BvhState* bs)
+{
+    if (ms) {
+        wp_b200_mesh_desc d;
+        memset(&d, 0, sizeof(d));
+        d.points.data = ms->points_data, d.points.shape[0] = ms->points_shape0, d.points.strides[0] = 12, d.points.ndim = 1;
+        d.velocities.data = ms->velocities_data, d.velocities.shape[0] = ms->velocities_shape0;
+        d.velocities.strides[0] = 12, d.velocities.ndim = ms->velocities_data ? 1 : 0;
+        d.indices.data = ms->indices_data, d.indices.shape[0] = ms->num_tris * 3, d.indices.strides[0] = 4, d.indices.ndim = 1;
+        d.num_points = ms->num_points, d.num_tris = ms->num_tris;
+        fill_bvh_desc(ms->bvh, d.bvh, (void*)(intptr_t)(ms->bvh.device + 1));
+        d.context = d.bvh.context;
+        return check(cudaMemcpy(ms->dev_desc, &d, sizeof(d), cudaMemcpyHostToDevice), "descriptor upload");
+    }
+    wp_b200_bvh_desc d;
+    fill_bvh_desc(*bs, d, (void*)(intptr_t)(bs->device + 1));
+    return check(cudaMemcpy(bs->dev_desc, &d, sizeof(d), cudaMemcpyHostToDevice), "descriptor upload");
+}
+
+bool constructor_supported(int constructor_type)
+{
+    if (constructor_type == WP_BVH_CONSTRUCTOR_LBVH)
+        return true;
+    set_error("Warp error: BVH constructor %d is not available in the B200 library: it builds on the GPU only "
+              "(constructor 'lbvh' = %d); the reference's host builders (sah/median) and cuBQL are out of scope",
+              constructor_type, WP_BVH_CONSTRUCTOR_LBVH);
+    return false;
+}
+
+TreeView make_view(const BvhState& s)
+{
+    TreeView tv;
+    tv.pairs = s.pairs;
+    tv.header = s.header;
+    tv.tris = s.tris;
+    tv.prim = s.prim;
+    tv.n = s.n;
+    return tv;
+}
+
+unsigned long long* stats_buffer()
+{
+    if (!t_stats_enabled)
+        return nullptr;
+    if (!g_stats_dev) {
+        if (cudaMalloc(&g_stats_dev, 2 * sizeof(unsigned long long)) != cudaSuccess)
+            return nullptr;
+    }
+    cudaMemsetAsync(g_stats_dev, 0, 2 * sizeof(unsigned long long), current_stream(current_device()));
+    return g_stats_dev;
+}
+
+MeshState* query_mesh(uint64_t id)
+{
+    MeshState* ms = nullptr;
+    find_tree(id, &ms);
+    if (!ms)
+        set_error("Warp error: invalid mesh id");
+    return ms;
+}
+
+// grow-only device scratch for the *_host entry points: two lanes, each with its own stream
+struct HostLane {
+    cudaStream_t stream = nullptr;
+    void* buf = nullptr;
+    size_t bytes = 0;
+};
+HostLane g_lanes[64][2];
+
+bool lane_reserve(HostLane& l, size_t bytes)
+{
+    if (!l.stream && !check(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking), "stream create"))
+        return false;
+    if (bytes > l.bytes) {
+        if (l.buf)
+            cudaFree(l.buf);
+        l.buf = nullptr, l.bytes = 0;
+        if (!check(cudaMalloc(&l.buf, bytes), "scratch alloc"))
+            return false;
+        l.bytes = bytes;
+    }
+    return true;
+}
+
+constexpr int64_t HOST_CHUNK = 1 << 21;  // queries per staged chunk
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" {
+
+const char* wp_get_error_string(void) { return g_error; }
+
+int wp_init(const char*) { return 0; }
+int wp_is_cuda_enabled(void) { return 1; }
+
+int wp_cuda_device_get_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void* wp_cuda_device_get_primary_context(int ordinal) { return (void*)(intptr_t)(ordinal + 1); }
+void* wp_cuda_context_get_current(void) { return (void*)(intptr_t)(current_device() + 1); }
+void wp_cuda_context_set_current(void* context)
+{
+    if (context)
+        cudaSetDevice(context_device(context));
+}
+void wp_cuda_context_synchronize(void* context)
+{
+    DeviceGuard g(context_device(context));
+    check(cudaDeviceSynchronize(), "device synchronize");
+}
+void* wp_cuda_context_get_stream(void* context) { return current_stream(context_device(context)); }
+void wp_cuda_context_set_stream(void* context, void* stream, int sync)
+{
+    const int d = context_device(context);
+    if (d < 0 || d >= 64)
+        return;
+    if (sync)
+        cudaStreamSynchronize(g_stream[d]);
+    g_stream[d] = (cudaStream_t)stream;
+}
+void* wp_cuda_stream_create(void* context, int priority)
+{
+    DeviceGuard g(context_device(context));
+    cudaStream_t s = nullptr;
+    if (!check(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, priority), "stream create"))
+        return nullptr;
+    return s;
+}
+void wp_cuda_stream_destroy(void*, void* stream) { cudaStreamDestroy((cudaStream_t)stream); }
+void wp_cuda_stream_synchronize(void* stream) { check(cudaStreamSynchronize((cudaStream_t)stream), "stream synchronize"); }
+void* wp_cuda_event_create(void* context, unsigned flags)
+{
+    DeviceGuard g(context_device(context));
+    cudaEvent_t e = nullptr;
+    if (!check(cudaEventCreateWithFlags(&e, (flags & 1u) ? cudaEventDisableTiming : cudaEventDefault), "event create"))
+        return nullptr;
+    return e;
+}
+void wp_cuda_event_destroy(void* event) { cudaEventDestroy((cudaEvent_t)event); }
+void wp_cuda_event_record(void* event, void* stream, int) { check(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream), "event record"); }
+void wp_cuda_event_synchronize(void* event) { check(cudaEventSynchronize((cudaEvent_t)event), "event synchronize"); }
+float wp_cuda_event_elapsed_time(void* a, void* b)
+{
+    float ms = 0.f;
+    check(cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b), "event elapsed");
+    return ms;
+}
+
+void* wp_alloc_device(void* context, size_t s, const char*)
+{
+    DeviceGuard g(context_device(context));
+    void* p = nullptr;
+    if (s == 0)
+        return nullptr;
+    if (!check(cudaMalloc(&p, s), "wp_alloc_device"))
+        return nullptr;
+    return p;
+}
+void wp_free_device(void* context, void* ptr)
+{
+    if (!ptr)
+        return;
+    DeviceGuard g(context_device(context));
+    cudaFree(ptr);
+}
+void* wp_alloc_pinned(size_t s, const char*)
+{
+    void* p = nullptr;
+    if (s == 0)
+        return nullptr;
+    if (!check(cudaMallocHost(&p, s), "wp_alloc_pinned"))
+        return nullptr;
+    return p;
+}
+void wp_free_pinned(void* ptr)
+{
+    if (ptr)
+        cudaFreeHost(ptr);
+}
+int wp_memcpy_h2d(void* context, void* dest, void* src, size_t n, void* stream)
+{
+    DeviceGuard g(context_device(context));
+    return check(cudaMemcpyAsync(dest, src, n, cudaMemcpyHostToDevice, (cudaStream_t)stream), "memcpy h2d");
+}
+int wp_memcpy_d2h(void* context, void* dest, void* src, size_t n, void* stream)
+{
+    DeviceGuard g(context_device(context));
+    return check(cudaMemcpyAsync(dest, src, n, cudaMemcpyDeviceToHost, (cudaStream_t)stream), "memcpy d2h");
+}
+int wp_memcpy_d2d(void* context, void* dest, void* src, size_t n, void* stream)
+{
+    DeviceGuard g(context_device(context));
+    return check(cudaMemcpyAsync(dest, src, n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream), "memcpy d2d");
+}
+int wp_memset_device(void* context, void* dest, int value, size_t n, void* stream)
+{
+    DeviceGuard g(context_device(context));
+    return check(cudaMemsetAsync(dest, value, n, (cudaStream_t)stream), "memset");
+}
+
+int wp_b200_device_attr(int ordinal, const char* name, long long* value)
+{
+    int v = 0;
+    cudaError_t e = cudaSuccess;
+    if (!strcmp(name, "sm_count"))
+        e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, ordinal);
+    else if (!strcmp(name, "l2_bytes"))
+        e = cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, ordinal);
+    else if (!strcmp(name, "clock_khz"))
+        e = cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, ordinal);
+    else if (!strcmp(name, "cc_major"))
+        e = cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, ordinal);
+    else if (!strcmp(name, "cc_minor"))
+        e = cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, ordinal);
+    else if (!strcmp(name, "mem_free") || !strcmp(name, "mem_total")) {
+        DeviceGuard g(ordinal);
+        size_t f = 0, t = 0;
+        e = cudaMemGetInfo(&f, &t);
+        *value = (long long)(!strcmp(name, "mem_free") ? f : t);
+        return check(e, "mem info");
+    } else {
+        set_error("unknown device attribute %s", name);
+        return 0;
+    }
+    *value = v;
+    return check(e, "device attribute");
+}
+
+int wp_b200_device_name(int ordinal, char* buf, int len)
+{
+    cudaDeviceProp p;
+    if (!check(cudaGetDeviceProperties(&p, ordinal), "device properties"))
+        return 0;
+    snprintf(buf, len, "%s", p.name);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bvh
+// ------------------------------------------------------------------------------------------------
+uint64_t wp_bvh_create_device(void* context, wp_vec3* lowers, wp_vec3* uppers, int num_items, int constructor_type,
+                              int* groups, int leaf_size)
+{
+    if (!constructor_supported(constructor_type))
+        return 0;
+    if (num_items < 0 || leaf_size < 1) {
+        set_error("Warp error: invalid BVH arguments (num_items=%d, leaf_size=%d)", num_items, leaf_size);
+        return 0;
+    }
+    if (groups) {
+        set_error("Warp error: grouped BVHs are not supported by the B200 LBVH builder yet");
+        return 0;
+    }
+    const int dev = context_device(context);
+    DeviceGuard g(dev);
+    BvhState* s = new BvhState();
+    s->n = num_items, s->leaf_size = leaf_size, s->constructor_type = constructor_type, s->device = dev;
+    s->item_lowers = (const float*)lowers, s->item_uppers = (const float*)uppers, s->groups = groups;
+    const char* err = num_items > 0 ? wb_alloc_tree(*s) : nullptr;
+    if (!err)
+        err = wb_build(*s, current_stream(dev));
+    if (err || !check(cudaMalloc(&s->dev_desc, sizeof(wp_b200_bvh_desc)), "descriptor alloc") || !upload_desc(nullptr, s)) {
+        if (err)
+            set_error("Warp error: BVH build failed: %s", err);
+        wb_free_tree(*s);
+        delete s;
+        return 0;
+    }
+    const uint64_t id = (uint64_t)s->dev_desc;
+    std::lock_guard<std::mutex> l(g_lock);
+    g_bvhs[id] = s;
+    return id;
+}
+
+void wp_bvh_destroy_device(uint64_t id)
+{
+    BvhState* s = nullptr;
+    {
+        std::lock_guard<std::mutex> l(g_lock);
+        auto it = g_bvhs.find(id);
+        if (it == g_bvhs.end())
+            return;
+        s = it->second;
+        g_bvhs.erase(it);
+    }
+    DeviceGuard g(s->device);
+    cudaStreamSynchronize(current_stream(s->device));
+    cudaFree(s->dev_desc);
+    wb_free_tree(*s);
+    delete s;
+}
+
+void wp_bvh_refit_device(uint64_t id)
+{
+    BvhState* s = find_tree(id);
+    if (!s)
+        return;
+    DeviceGuard g(s->device);
+    const char* err = wb_refit(*s, current_stream(s->device));
+    if (err)
+        set_error("Warp error: BVH refit failed: %s", err);
+}
+
+void wp_bvh_rebuild_device(uint64_t id)
+{
+    BvhState* s = find_tree(id);
+    if (!s)
+        return;
+    DeviceGuard g(s->device);
+    const char* err = wb_build(*s, current_stream(s->device));
+    if (err)
+        set_error("Warp error: BVH rebuild failed: %s", err);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mesh
+// ------------------------------------------------------------------------------------------------
+uint64_t wp_mesh_create_device(void* context, wp_array_t points, wp_array_t velocities, wp_array_t tris, int num_points,
+                               int num_tris, int support_winding_number, int constructor_type, int* groups,
+                               int bvh_leaf_size)
+{
+    if (!constructor_supported(constructor_type))
+        return 0;
+    if (support_winding_number) {
+        set_error("Warp error: support_winding_number=True is out of scope for the B200 mesh path");
+        return 0;
+    }
+    if (groups) {
+        set_error("Warp error: grouped meshes are not supported by the B200 LBVH builder yet");
+        return 0;
+    }
+    if (num_points < 0 || num_tris < 0 || bvh_leaf_size < 1 || (num_tris > 0 && (!points.data || !tris.data))) {
+        set_error("Warp error: invalid mesh arguments (num_points=%d, num_tris=%d, leaf_size=%d)", num_points, num_tris,
+                  bvh_leaf_size);
+        return 0;
+    }
+    const int dev = context_device(context);
+    DeviceGuard g(dev);
+    MeshState* m = new MeshState();
+    m->points_data = points.data, m->velocities_data = velocities.data, m->indices_data = tris.data;
+    m->num_points = num_points, m->num_tris = num_tris;
+    m->points_shape0 = points.shape[0], m->velocities_shape0 = velocities.shape[0];
+    BvhState& s = m->bvh;
+    s.n = num_tris, s.leaf_size = bvh_leaf_size, s.constructor_type = constructor_type, s.device = dev;
+    s.is_mesh = true;
+    s.points = (const float*)points.data, s.indices = (const int*)tris.data, s.num_points = num_points;
+    const char* err = num_tris > 0 ? wb_alloc_tree(s) : nullptr;
+    if (!err)
+        err = wb_build(s, current_stream(dev));
+    if (err || !check(cudaMalloc(&m->dev_desc, sizeof(wp_b200_mesh_desc)), "descriptor alloc") || !upload_desc(m, nullptr)) {
+        if (err)
+            set_error("Warp error: mesh build failed: %s", err);
+        if (m->dev_desc)
+            cudaFree(m->dev_desc);
+        wb_free_tree(s);
+        delete m;
+        return 0;
+    }
+    const uint64_t id = (uint64_t)m->dev_desc;
+    std::lock_guard<std::mutex> l(g_lock);
+    g_meshes[id] = m;
+    return id;
+}
+
+void wp_mesh_destroy_device(uint64_t id)
+{
+    MeshState* m = nullptr;
+    {
+        std::lock_guard<std::mutex> l(g_lock);
+        auto it = g_meshes.find(id);
+        if (it == g_meshes.end())
+            return;
+        m = it->second;
+        g_meshes.erase(it);
+    }
+    DeviceGuard g(m->bvh.device);
+    cudaStreamSynchronize(current_stream(m->bvh.device));
+    cudaFree(m->dev_desc);
+    wb_free_tree(m->bvh);
+    delete m;
+}
+
+int wp_mesh_refit_device(uint64_t id)
+{
+    MeshState* m = nullptr;
+    find_tree(id, &m);
+    if (!m) {
+        set_error("Warp error: invalid mesh id");
+        return 0;
+    }
+    DeviceGuard g(m->bvh.device);
+    const char* err = wb_refit(m->bvh, current_stream(m->bvh.device));
+    if (err) {
+        set_error("Warp error: mesh refit failed: %s", err);
+        return 0;
+    }
+    return 1;
+}
+
+int wp_b200_mesh_rebuild_device(uint64_t id)
+{
+    MeshState* m = nullptr;
+    find_tree(id, &m);
+    if (!m) {
+        set_error("Warp error: invalid mesh id");
+        return 0;
+    }
+    DeviceGuard g(m->bvh.device);
+    const char* err = wb_build(m->bvh, current_stream(m->bvh.device));
+    if (err) {
+        set_error("Warp error: mesh rebuild failed: %s", err);
+        return 0;
+    }
+    return 1;
+}
+
+int wp_mesh_set_points_device(uint64_t id, wp_array_t points)
+{
+    MeshState* m = nullptr;
+    find_tree(id, &m);
+    if (!m) {
+        set_error("Warp error: invalid mesh id");
+        return 0;
+    }
+    if (points.ndim != 1 || points.shape[0] != m->points_shape0) {
+        set_error("Warp error: new points input for wp_mesh_set_points_device does not match the original points shape");
+        return 0;
+    }
+    DeviceGuard g(m->bvh.device);
+    m->points_data = points.data;
+    m->bvh.points = (const float*)points.data;
+    if (!upload_desc(m, nullptr))
+        return 0;
+    return wp_mesh_refit_device(id);
+}
+
+void wp_mesh_set_velocities_device(uint64_t id, wp_array_t velocities)
+{
+    MeshState* m = nullptr;
+    find_tree(id, &m);
+    if (!m) {
+        set_error("Warp error: invalid mesh id");
+        return;
+    }
+    if (velocities.ndim != 1 || velocities.shape[0] != m->velocities_shape0) {
+        set_error("Warp error: new velocities input for wp_mesh_set_velocities_device does not match the original "
+                  "velocities shape");
+        return;
+    }
+    DeviceGuard g(m->bvh.device);
+    m->velocities_data = velocities.data;
+    upload_desc(m, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// queries (device pointers)
+// ------------------------------------------------------------------------------------------------
+void wp_b200_query_stats_enable(int enable) { t_stats_enabled = enable != 0; }
+
+void wp_b200_query_stats_read(unsigned long long* pair_fetches, unsigned long long* tri_fetches)
+{
+    unsigned long long h[2] = { 0, 0 };
+    if (g_stats_dev) {
+        cudaStreamSynchronize(current_stream(current_device()));
+        cudaMemcpy(h, g_stats_dev, sizeof(h), cudaMemcpyDeviceToHost);
+    }
+    if (pair_fetches)
+        *pair_fetches = h[0];
+    if (tri_fetches)
+        *tri_fetches = h[1];
+}
+
+static int zero_point_outputs(int64_t n, uint8_t* result, float* sign, int32_t* face, float* u, float* v, cudaStream_t st)
+{
+    bool ok = check(cudaMemsetAsync(result, 0, (size_t)n, st), "memset");
+    if (sign)
+        ok = ok && check(cudaMemsetAsync(sign, 0, 4 * (size_t)n, st), "memset");
+    ok = ok && check(cudaMemsetAsync(face, 0, 4 * (size_t)n, st), "memset");
+    ok = ok && check(cudaMemsetAsync(u, 0, 4 * (size_t)n, st), "memset");
+    ok = ok && check(cudaMemsetAsync(v, 0, 4 * (size_t)n, st), "memset");
+    return ok ? 1 : 0;
+}
+
+static int query_point_on(MeshState* m, const float* points, int64_t n, float max_dist, int with_sign, uint8_t* result,
+                          float* sign, int32_t* face, float* u, float* v, cudaStream_t st)
+{
+    if (n <= 0)
+        return 1;
+    if (m->bvh.n == 0)
+        return zero_point_outputs(n, result, sign, face, u, v, st);
+    const char* err = wb_query_point(make_view(m->bvh), points, n, max_dist, with_sign, result, sign, face, u, v,
+                                     stats_buffer(), st);
+    if (err) {
+        set_error("Warp error: mesh point query failed: %s", err);
+        return 0;
+    }
+    return 1;
+}
+
+static int query_ray_on(MeshState* m, const float* starts, const float* dirs, int64_t n, float max_t, uint8_t* result,
+                        float* sign, int32_t* face, float* t, float* u, float* v, float* normal, cudaStream_t st)
+{
+    if (n <= 0)
+        return 1;
+    if (m->bvh.n == 0) {
+        int ok = zero_point_outputs(n, result, sign, face, u, v, st);
+        ok = ok && check(cudaMemsetAsync(t, 0, 4 * (size_t)n, st), "memset");
+        ok = ok && check(cudaMemsetAsync(normal, 0, 12 * (size_t)n, st), "memset");
+        return ok;
+    }
+    const char* err = wb_query_ray(make_view(m->bvh), starts, dirs, n, max_t, result, sign, face, t, u, v, normal,
+                                   stats_buffer(), st);
+    if (err) {
+        set_error("Warp error: mesh ray query failed: %s", err);
+        return 0;
+    }
+    return 1;
+}
+
+int wp_b200_mesh_query_point_no_sign(uint64_t id, const float* points, int64_t n, float max_dist, uint8_t* result,
+                                     int32_t* face, float* u, float* v)
+{
+    MeshState* m = query_mesh(id);
+    if (!m)
+        return 0;
+    DeviceGuard g(m->bvh.device);
+    return query_point_on(m, points, n, max_dist, 0, result, nullptr, face, u, v, current_stream(m->bvh.device));
+}
+
+int wp_b200_mesh_query_point(uint64_t id, const float* points, int64_t n, float max_dist, uint8_t* result, float* sign,
+                             int32_t* face, float* u, float* v)
+{
+    MeshState* m = query_mesh(id);
+    if (!m)
+        return 0;
+    DeviceGuard g(m->bvh.device);
+    return query_point_on(m, points, n, max_dist, 1, result, sign, face, u, v, current_stream(m->bvh.device));
+}
+
+int wp_b200_mesh_query_ray(uint64_t id, const float* starts, const float* dirs, int64_t n, float max_t, uint8_t* result,
+                           float* sign, int32_t* face, float* t, float* u, float* v, float* normal)
+{
+    MeshState* m = query_mesh(id);
+    if (!m)
+        return 0;
+    DeviceGuard g(m->bvh.device);
+    return query_ray_on(m, starts, dirs, n, max_t, result, sign, face, t, u, v, normal, current_stream(m->bvh.device));
+}
+
+// ------------------------------------------------------------------------------------------------
+// queries (host buffers): chunked, two lanes so the copies of one chunk overlap the traversal of
+// the other.  Fully asynchronous only when the caller's buffers are pinned (wp_alloc_pinned).
+// ------------------------------------------------------------------------------------------------
+static int point_host(uint64_t id, const float* points, int64_t n, float max_dist, int with_sign, uint8_t* result,
+                      float* sign, int32_t* face, float* u, float* v)
+{
+    MeshState* m = query_mesh(id);
+    if (!m)
+        return 0;
+    const int dev = m->bvh.device;
+    DeviceGuard g(dev);
+    cudaStreamSynchronize(current_stream(dev));  // the tree must be complete before the lanes read it
+    const int64_t chunk = n < HOST_CHUNK ? (n > 0 ? n : 1) : HOST_CHUNK;
+    const size_t o_pts = 0, o_res = o_pts + align256(12 * chunk), o_sign = o_res + align256(chunk),
+                 o_face = o_sign + align256(4 * chunk), o_u = o_face + align256(4 * chunk),
+                 o_v = o_u + align256(4 * chunk), total = o_v + align256(4 * chunk);
+    int ok = 1;
+    for (int64_t base = 0, k = 0; base < n && ok; base += chunk, ++k) {
+        HostLane& l = g_lanes[dev][k & 1];
+        if (!lane_reserve(l, total))
+            return 0;
+        const int64_t c = (n - base < chunk) ? n - base : chunk;
+        char* b = (char*)l.buf;
+        ok = ok && check(cudaMemcpyAsync(b + o_pts, points + 3 * base, 12 * c, cudaMemcpyHostToDevice, l.stream), "h2d");
+        ok = ok && query_point_on(m, (const float*)(b + o_pts), c, max_dist, with_sign, (uint8_t*)(b + o_res),
+                                  with_sign ? (float*)(b + o_sign) : nullptr, (int32_t*)(b + o_face), (float*)(b + o_u),
+                                  (float*)(b + o_v), l.stream);
+        ok = ok && check(cudaMemcpyAsync(result + base, b + o_res, c, cudaMemcpyDeviceToHost, l.stream), "d2h");
+        if (with_sign)
+            ok = ok && check(cudaMemcpyAsync(sign + base, b + o_sign, 4 * c, cudaMemcpyDeviceToHost, l.stream), "d2h");
+        ok = ok && check(cudaMemcpyAsync(face + base, b + o_face, 4 * c, cudaMemcpyDeviceToHost, l.stream), "d2h");
+        ok = ok && check(cudaMemcpyAsync(u + base, b + o_u, 4 * c, cudaMemcpyDeviceToHost, l.stream), "d2h");
+        ok = ok && check(cudaMemcpyAsync(v + base, b + o_v, 4 * c, cudaMemcpyDeviceToHost, l.stream), "d2h");
+    }
+    for (int k = 0; k < 2; ++k)
+        if (g_lanes[dev][k].stream)
+            ok = check(cudaStreamSynchronize(g_lanes[dev][k].stream), "lane synchronize") && ok;
+    return ok;
+}
+
+int wp_b200_mesh_query_point_no_sign_host(uint64_t id, const float* points, int64_t n, float max_dist, uint8_t* result,
+                                          int32_t* face, float* u, float* v)
+{
+    return point_host(id, points, n, max_dist, 0, result, nullptr, face, u, v);
+}
+
+int wp_b200_mesh_query_point_host(uint64_t id, const float* points, int64_t n, float max_dist, uint8_t* result,
+                                  float* sign, int32_t* face, float* u, float* v)
+{
+    return point_host(id, points, n, max_dist, 1, result, sign, face, u, v);
+}
+
+int wp_b200_mesh_query_ray_host(uint64_t id, const float* starts, const float* dirs, int64_t n, float max_t,
+                                uint8_t* result, float* sign, int32_t* face, float* t, float* u, float* v, float* normal)
+{
+    MeshState* m = query_mesh(id);
+    if (!m)
+        return 0;
+    const int dev = m->bvh.device;
+    DeviceGuard g(dev);
+    cudaStreamSynchronize(current_stream(dev));
+    const int64_t chunk = n < HOST_CHUNK ? (n > 0 ? n : 1) : HOST_CHUNK;
+    const size_t o_s = 0, o_d = o_s + align256(12 * chunk), o_res = o_d + align256(12 * chunk),
+                 o_sign = o_res + align256(chunk), o_face = o_sign + align256(4 * chunk),
+                 o_t = o_face + align256(4 * chunk), o_u = o_t + align256(4 * chunk), o_v = o_u + align256(4 * chunk),
+                 o_n = o_v + align256(4 * chunk), total = o_n + align256(12 * chunk);
+    int ok = 1;
+    for (int64_t base = 0, k = 0; base < n && ok; base += chunk, ++k) {
+        HostLane& l = g_lanes[dev][k & 1];
+        if (!lane_reserve(l, total))
+            return 0;
+        const int64_t c = (n - base < chunk) ? n - base : chunk;
+        char* b = (char*)l.buf;
+        ok = ok && check(cudaMemcpyAsync(b + o_s, starts + 3 * base, 12 * c, cudaMemcpyHostToDevice, l.stream), "h2d");
+        ok = ok && check(cudaMemcpyAsync(b + o_d, dirs + 3 * base, 12 * c, cudaMemcpyHostToDevice, l.stream), "h2d");
+        ok = ok && query_ray_on(m, (const float*)(b + o_s), (const float*)(b + o_d), c, max_t, (uint8_t*)(b + o_res),
+                                (float*)(b + o_sign), (int32_t*)(b + o_face), (float*)(b + o_t), (float*)(b + o_u),
+                                (float*)(b + o_v), (float*)(b + o_n), l.stream);
+        ok = ok && check(cudaMemcpyAsync(result + base, b + o_res, c, cudaMemcpyDeviceToHost, l.stream), "d2h");
+        ok = ok && check(cudaMemcpyAsync(sign + base, b + o_sign, 4 * c, cudaMemcpyDeviceToHost, l.stream), "d2h");
+        ok = ok && check(cudaMemcpyAsync(face + base, b + o_face, 4 * c, cudaMemcpyDeviceToHost, l.stream), "d2h");
+        ok = ok && check(cudaMemcpyAsync(t + base, b + o_t, 4 * c, cudaMemcpyDeviceToHost, l.stream), "d2h");
+        ok = ok && check(cudaMemcpyAsync(u + base, b + o_u, 4 * c, cudaMemcpyDeviceToHost, l.stream), "d2h");
+        ok = ok && check(cudaMemcpyAsync(v + base, b + o_v, 4 * c, cudaMemcpyDeviceToHost, l.stream), "d2h");
+        ok = ok && check(cudaMemcpyAsync(normal + 3 * base, b + o_n, 12 * c, cudaMemcpyDeviceToHost, l.stream), "d2h");
+    }
+    for (int k = 0; k < 2; ++k)
+        if (g_lanes[dev][k].stream)
+            ok = check(cudaStreamSynchronize(g_lanes[dev][k].stream), "lane synchronize") && ok;
+    return ok;
+}
+
+// ------------------------------------------------------------------------------------------------
+// introspection
+// ------------------------------------------------------------------------------------------------
+int wp_b200_bvh_info(uint64_t id, wp_b200_bvh_info_t* info)
+{
+    MeshState* m = nullptr;
+    BvhState* s = find_tree(id, &m);
+    if (!s) {
+        set_error("Warp error: invalid id");
+        return 0;
+    }
+    DeviceGuard g(s->device);
+    memset(info, 0, sizeof(*info));
+    info->num_items = s->n, info->leaf_size = s->leaf_size, info->max_nodes = s->n > 0 ? 2 * s->n - 1 : 0;
+    info->root = -1;
+    if (s->n == 0)
+        return 1;
+    TreeHeader h;
+    cudaStreamSynchronize(current_stream(s->device));
+    if (!check(cudaMemcpy(&h, s->header, sizeof(h), cudaMemcpyDeviceToHost), "header download"))
+        return 0;
+    info->root = (int)(h.root_ref & WB_IDX_MASK);
+    info->height = h.height, info->deep = h.deep;
+    for (int k = 0; k < 3; ++k)
+        info->total_lower[k] = h.total_lo[k], info->total_upper[k] = h.total_hi[k], info->inv_edges[k] = h.inv_edges[k];
+    return 1;
+}
+
+int wp_b200_bvh_sync_reference_layout(uint64_t id)
+{
+    MeshState* m = nullptr;
+    BvhState* s = find_tree(id, &m);
+    if (!s) {
+        set_error("Warp error: invalid id");
+        return 0;
+    }
+    DeviceGuard g(s->device);
+    const bool first = s->ref_lowers == nullptr;
+    const char* err = wb_export_reference_layout(*s, current_stream(s->device));
+    if (err) {
+        set_error("Warp error: reference-layout export failed: %s", err);
+        return 0;
+    }
+    if (first && s->n > 0)
+        return upload_desc(m, m ? nullptr : s) ? 1 : 0;
+    return 1;
+}
+
+int wp_b200_bvh_download(uint64_t id, uint32_t* keys, int32_t* primitive_indices, void* node_lowers, void* node_uppers,
+                         int32_t* node_parents, int32_t* root)
+{
+    if (!wp_b200_bvh_sync_reference_layout(id))
+        return 0;
+    BvhState* s = find_tree(id);
+    if (s->n == 0)
+        return 1;
+    DeviceGuard g(s->device);
+    cudaStream_t st = current_stream(s->device);
+    const size_t n = (size_t)s->n, mx = 2 * n - 1;
+    bool ok = check(cudaStreamSynchronize(st), "synchronize");
+    if (keys)
+        ok = ok && check(cudaMemcpy(keys, s->keys, 4 * n, cudaMemcpyDeviceToHost), "download");
+    if (primitive_indices)
+        ok = ok && check(cudaMemcpy(primitive_indices, s->prim, 4 * n, cudaMemcpyDeviceToHost), "download");
+    if (node_lowers)
+        ok = ok && check(cudaMemcpy(node_lowers, s->ref_lowers, 16 * mx, cudaMemcpyDeviceToHost), "download");
+    if (node_uppers)
+        ok = ok && check(cudaMemcpy(node_uppers, s->ref_uppers, 16 * mx, cudaMemcpyDeviceToHost), "download");
+    if (node_parents)
+        ok = ok && check(cudaMemcpy(node_parents, s->ref_parents, 4 * mx, cudaMemcpyDeviceToHost), "download");
+    if (root)
+        ok = ok && check(cudaMemcpy(root, s->ref_root, 4, cudaMemcpyDeviceToHost), "download");
+    return ok ? 1 : 0;
+}
+
+}  // extern "C"

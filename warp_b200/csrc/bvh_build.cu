@@ -1,0 +1,754 @@
+// LBVH construction for sm_100a: scene bounds -> 30-bit Morton keys + digit histograms ->
+// onesweep LSD radix sort of (key, item) -> bottom-up hierarchy emission directly into the
+// sibling-pair node layout (common.cuh) -> depth-rule fix-up -> (optional) export to the
+// reference's two-array layout.
+//
+// Behavioural contract = warp/native/bvh.cu:184-613 (reference LBVH): identical Morton keys,
+// identical sorted order (any stable sort), identical parent choice / tie break / packed-leaf
+// marking.  What differs is how the bytes move: 6 launches instead of ~20, 32-bit keys and 4 digit
+// passes instead of 64-bit keys and 8, no lowers/uppers round trip for meshes, no delta /
+// range / leaf-node passes (deltas are recomputed from the sorted keys, ranges travel in the
+// node records), height tracked in the arrival counters so the per-node depth walk of
+// mark_packed_leaf_nodes (bvh.cu:402-443) only runs for trees that are actually >= 32 deep.
+#include "state.h"
+
+#include <cub/device/device_radix_sort.cuh>  // WARP_B200_SORT=cub cross-check path only
+
+#include <cstdlib>
+#include <cstring>
+
+namespace {
+
+constexpr int BT = 256;  // threads per block for the streaming kernels
+
+__global__ void k_iota(int* out, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        out[i] = i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// block reductions
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_min(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// reduce (lo, hi) over the block; result valid in thread 0
+__device__ __forceinline__ void block_minmax(float3& lo, float3& hi, float (*sm)[6])
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    lo.x = warp_min(lo.x), lo.y = warp_min(lo.y), lo.z = warp_min(lo.z);
+    hi.x = warp_max(hi.x), hi.y = warp_max(hi.y), hi.z = warp_max(hi.z);
+    __syncthreads();
+    if (lane == 0) {
+        sm[warp][0] = lo.x, sm[warp][1] = lo.y, sm[warp][2] = lo.z;
+        sm[warp][3] = hi.x, sm[warp][4] = hi.y, sm[warp][5] = hi.z;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < BT / 32; ++w) {
+            lo.x = fminf(lo.x, sm[w][0]), lo.y = fminf(lo.y, sm[w][1]), lo.z = fminf(lo.z, sm[w][2]);
+            hi.x = fmaxf(hi.x, sm[w][3]), hi.y = fmaxf(hi.y, sm[w][4]), hi.z = fmaxf(hi.z, sm[w][5]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: scene AABB + 1/(extent + 1e-4)  (bvh.cu:449-488).  One pass, last block finishes.
+// Also clears the digit histograms and tile tickets used by the following kernels.
+// ---------------------------------------------------------------------------------------------
+template <class Src>
+__global__ void __launch_bounds__(BT)
+k_scene_bounds(Src src, int n, float* __restrict__ partials, unsigned* __restrict__ tickets,
+               TreeHeader* __restrict__ hdr, uint32_t* __restrict__ ghist)
+{
+    __shared__ float sm[BT / 32][6];
+    __shared__ bool is_last;
+
+    if (blockIdx.x == 0) {
+        for (int k = threadIdx.x; k < 4 * 256; k += BT)
+            ghist[k] = 0;
+        if (threadIdx.x < 4)
+            tickets[1 + threadIdx.x] = 0;  // per-pass tile tickets
+    }
+
+    float3 lo = make_float3(FLT_MAX, FLT_MAX, FLT_MAX), hi = make_float3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+    for (int i = blockIdx.x * BT + threadIdx.x; i < n; i += gridDim.x * BT) {
+        float3 a, b;
+        src.bounds(i, a, b);
+        lo = wb_min3(lo, a);
+        hi = wb_max3(hi, b);
+    }
+    block_minmax(lo, hi, sm);
+    if (threadIdx.x == 0) {
+        float* p = partials + 6 * blockIdx.x;
+        p[0] = lo.x, p[1] = lo.y, p[2] = lo.z, p[3] = hi.x, p[4] = hi.y, p[5] = hi.z;
+        __threadfence();
+        is_last = (atomicAdd(&tickets[0], 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last)
+        return;
+    __threadfence();
+    lo = make_float3(FLT_MAX, FLT_MAX, FLT_MAX), hi = make_float3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+    for (int b = threadIdx.x; b < gridDim.x; b += BT) {
+        const float* p = partials + 6 * b;
+        lo = wb_min3(lo, make_float3(__ldcg(p + 0), __ldcg(p + 1), __ldcg(p + 2)));
+        hi = wb_max3(hi, make_float3(__ldcg(p + 3), __ldcg(p + 4), __ldcg(p + 5)));
+    }
+    block_minmax(lo, hi, sm);
+    if (threadIdx.x == 0) {
+        hdr->total_lo[0] = lo.x, hdr->total_lo[1] = lo.y, hdr->total_lo[2] = lo.z;
+        hdr->total_hi[0] = hi.x, hdr->total_hi[1] = hi.y, hdr->total_hi[2] = hi.z;
+        // edges = upper - lower; edges += 1e-4; inv = 1 / edges  (IEEE division, bvh.cu:482-488)
+        hdr->inv_edges[0] = 1.0f / ((hi.x - lo.x) + 0.0001f);
+        hdr->inv_edges[1] = 1.0f / ((hi.y - lo.y) + 0.0001f);
+        hdr->inv_edges[2] = 1.0f / ((hi.z - lo.z) + 0.0001f);
+        tickets[0] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: Morton keys (bvh.h:257-275, bvh.cu:184-214) + the four 8-bit digit histograms of the sort
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t spread3(uint32_t v)
+{
+    v = (v ^ (v << 16)) & 0xff0000ffu;
+    v = (v ^ (v << 8)) & 0x0300f00fu;
+    v = (v ^ (v << 4)) & 0x030c30c3u;
+    v = (v ^ (v << 2)) & 0x09249249u;
+    return v;
+}
+__device__ __forceinline__ uint32_t quant1024(float x)
+{
+    const int q = (int)(x * 1024.0f);  // truncation toward zero
+    return (uint32_t)min(max(q, 0), 1023);
+}
+__device__ __forceinline__ uint32_t morton30(float x, float y, float z)
+{
+    return (spread3(quant1024(z)) << 2) | (spread3(quant1024(y)) << 1) | spread3(quant1024(x));
+}
+
+// warp-aggregated shared-memory histogram increment (neighbouring items share high digits)
+__device__ __forceinline__ void hist_add(uint32_t* h, uint32_t d, bool valid)
+{
+    const uint32_t key = valid ? d : 0xffffffffu;
+    const uint32_t peers = __match_any_sync(0xffffffffu, key);
+    if (valid && (__ffs(peers) - 1) == (int)(threadIdx.x & 31))
+        atomicAdd(&h[d], (uint32_t)__popc(peers));
+}
+
+template <class Src>
+__global__ void __launch_bounds__(BT)
+k_morton_hist(Src src, int n, const TreeHeader* __restrict__ hdr, uint32_t* __restrict__ keys,
+              uint32_t* __restrict__ ghist)
+{
+    __shared__ uint32_t h[4 * 256];
+    for (int k = threadIdx.x; k < 4 * 256; k += BT)
+        h[k] = 0;
+    __syncthreads();
+
+    const float glx = hdr->total_lo[0], gly = hdr->total_lo[1], glz = hdr->total_lo[2];
+    const float ivx = hdr->inv_edges[0], ivy = hdr->inv_edges[1], ivz = hdr->inv_edges[2];
+
+    const int stride = gridDim.x * BT;
+    const int iters = (n + stride - 1) / stride;
+    for (int it = 0; it < iters; ++it) {
+        const int i = it * stride + blockIdx.x * BT + threadIdx.x;
+        const bool valid = i < n;
+        uint32_t code = 0;
+        if (valid) {
+            float3 lo, hi;
+            src.bounds(i, lo, hi);
+            const float cx = 0.5f * (lo.x + hi.x), cy = 0.5f * (lo.y + hi.y), cz = 0.5f * (lo.z + hi.z);
+            code = morton30((cx - glx) * ivx, (cy - gly) * ivy, (cz - glz) * ivz);
+            keys[i] = code;
+        }
+        hist_add(h, code & 255u, valid);
+        hist_add(h + 256, (code >> 8) & 255u, valid);
+        hist_add(h + 512, (code >> 16) & 255u, valid);
+        hist_add(h + 768, (code >> 24) & 255u, valid);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 4 * 256; k += BT)
+        if (h[k])
+            atomicAdd(&ghist[k], h[k]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: one onesweep pass (8-bit digit): per-tile ranking with warp match, decoupled look-back
+// across tiles, shared-memory reorder so global writes are digit-contiguous.  Stable.
+// ---------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per tile
+constexpr uint32_t RS_FLAG_AGG = 1u << 30;
+constexpr uint32_t RS_FLAG_INC = 2u << 30;
+constexpr uint32_t RS_VAL_MASK = (1u << 30) - 1;
+
+template <bool IMPLICIT_VALS>
+__global__ void __launch_bounds__(RS_THREADS)
+k_onesweep_pass(const uint32_t* __restrict__ keys_in, const int* __restrict__ vals_in,
+                uint32_t* __restrict__ keys_out, int* __restrict__ vals_out, int n, int shift,
+                const uint32_t* __restrict__ ghist_pass, volatile uint32_t* __restrict__ tile_status,
+                unsigned* __restrict__ tile_ticket)
+{
+    __shared__ uint32_t warp_hist[RS_WARPS][257];  // bin 256 collects out-of-range lanes
+    __shared__ uint32_t s_keys[RS_TILE];
+    __shared__ int s_vals[RS_TILE];
+    __shared__ int s_delta[256];       // global position = s_delta[digit] + position in tile
+    __shared__ uint32_t s_scan[RS_WARPS];
+    __shared__ uint32_t s_scan2[RS_WARPS];
+    __shared__ int s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0)
+        s_tile = (int)atomicAdd(tile_ticket, 1u);  // tiles start in ticket order => look-back never waits on an unscheduled tile
+    for (int k = tid; k < RS_WARPS * 257; k += RS_THREADS)
+        (&warp_hist[0][0])[k] = 0;
+    __syncthreads();
+    const int tile = s_tile;
+    const int tile_base = tile * RS_TILE;
+    const int tile_count = min(RS_TILE, n - tile_base);
+
+    // -- load (warp-striped: item k of lane l sits at warp_base + 32k + l, so rank order = memory order)
+    uint32_t key[RS_ITEMS];
+    int val[RS_ITEMS];
+    uint32_t rank[RS_ITEMS];
+    const int warp_base = tile_base + warp * (32 * RS_ITEMS);
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        const int idx = warp_base + 32 * k + lane;
+        const bool valid = idx < n;
+        key[k] = valid ? keys_in[idx] : 0xffffffffu;
+        val[k] = IMPLICIT_VALS ? idx : (valid ? vals_in[idx] : 0);
+    }
+
+    // -- rank within the warp, item by item
+    uint32_t* wh = warp_hist[warp];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        const int idx = warp_base + 32 * k + lane;
+        const uint32_t d = (idx < n) ? ((key[k] >> shift) & 255u) : 256u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t before = wh[d];
+        __syncwarp();
+        if ((peers & lt_mask) == 0)
+            wh[d] = before + __popc(peers);
+        __syncwarp();
+        rank[k] = before + __popc(peers & lt_mask);
+    }
+    __syncthreads();
+
+    // -- per digit (thread == digit): exclusive offsets across warps, tile total
+    uint32_t count = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+        const uint32_t c = warp_hist[w][tid];
+        warp_hist[w][tid] = count;
+        count += c;
+    }
+
+    // -- publish the tile aggregate, then look back for the exclusive prefix of this digit
+    volatile uint32_t* my_status = tile_status + (size_t)tile * 256 + tid;
+    uint32_t excl = 0;
+    if (tile == 0) {
+        *my_status = RS_FLAG_INC | count;
+    } else {
+        *my_status = RS_FLAG_AGG | count;
+        for (int j = tile - 1;; --j) {
+            volatile uint32_t* st = tile_status + (size_t)j * 256 + tid;
+            uint32_t v;
+            do {
+                v = *st;
+            } while ((v & ~RS_VAL_MASK) == 0);
+            excl += v & RS_VAL_MASK;
+            if (v & RS_FLAG_INC)
+                break;
+        }
+        *my_status = RS_FLAG_INC | (excl + count);
+    }
+
+    // -- exclusive scans over the 256 digits: tile-local starts and global digit starts
+    const uint32_t gcount = ghist_pass[tid];
+    uint32_t inc_t = count, inc_g = gcount;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, inc_t, o);
+        const uint32_t b = __shfl_up_sync(0xffffffffu, inc_g, o);
+        if (lane >= o)
+            inc_t += a, inc_g += b;
+    }
+    if (lane == 31)
+        s_scan[warp] = inc_t, s_scan2[warp] = inc_g;
+    __syncthreads();
+    uint32_t off_t = 0, off_g = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w)
+        if (w < warp)
+            off_t += s_scan[w], off_g += s_scan2[w];
+    const uint32_t tile_start = off_t + inc_t - count;   // first slot of this digit inside the tile
+    const uint32_t glob_start = off_g + inc_g - gcount;  // first slot of this digit in the output
+    s_delta[tid] = (int)(glob_start + excl) - (int)tile_start;
+    // fold the tile-local digit start into the per-warp offsets
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w)
+        warp_hist[w][tid] += tile_start;
+    __syncthreads();
+
+    // -- reorder through shared memory
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        const int idx = warp_base + 32 * k + lane;
+        if (idx < n) {
+            const uint32_t d = (key[k] >> shift) & 255u;
+            const uint32_t pos = wh[d] + rank[k];
+            s_keys[pos] = key[k];
+            s_vals[pos] = val[k];
+        }
+    }
+    __syncthreads();
+
+    // -- digit-contiguous global writes
+    for (int j = tid; j < tile_count; j += RS_THREADS) {
+        const uint32_t kk = s_keys[j];
+        const int g = s_delta[(kk >> shift) & 255u] + j;
+        keys_out[g] = kk;
+        vals_out[g] = s_vals[j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: bottom-up hierarchy (bvh.cu:228-393) fused with leaf creation, packed-triangle gather and
+// size-rule leaf marking.  One thread per sorted position; the second thread to arrive at a
+// parent continues upward carrying the union box in registers.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int key_delta(const uint32_t* __restrict__ keys, int i)
+{
+    // common-prefix length of keys i and i+1 (bvh.cu:218-226 computes it on 64-bit keys: +32, and 64
+    // for equal keys; only comparisons between deltas are used, so the 32-bit form is equivalent)
+    return __clz((int)(__ldg(keys + i) ^ __ldg(keys + i + 1)));
+}
+
+__device__ __forceinline__ void store_rec(NodeRec* dst, float3 lo, float3 hi, uint32_t ref, uint32_t aux)
+{
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    d4[0] = make_float4(lo.x, lo.y, lo.z, __uint_as_float(ref));
+    d4[1] = make_float4(hi.x, hi.y, hi.z, __uint_as_float(aux));
+}
+
+template <class Src>
+__global__ void __launch_bounds__(BT)
+k_hierarchy(Src src, int n, int leaf_size, const uint32_t* __restrict__ keys, const int* __restrict__ prim,
+            NodeRec* pairs, int* parent_int, int* pos_parent, unsigned* counters, float4* __restrict__ tris,
+            TreeHeader* hdr)
+{
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= n)
+        return;
+
+    const int item = __ldg(prim + i);
+    float3 lo, hi;
+    if constexpr (Src::kIsMesh) {
+        float3 p, q, r;
+        src.tri(item, p, q, r);
+        lo = wb_min3(wb_min3(p, q), r);
+        hi = wb_max3(wb_max3(p, q), r);
+        // sliver flag of the closest-point query (mesh.h:557-564), a per-triangle constant
+        const float3 e0 = wb_sub(q, p), e1 = wb_sub(r, p), e2 = wb_sub(r, q);
+        const float3 nrm = wb_cross(e0, e1);
+        const float area2 = sqrtf(nrm.x * nrm.x + nrm.y * nrm.y + nrm.z * nrm.z);
+        const bool sliver = area2 / (wb_dot(e0, e0) + wb_dot(e1, e1) + wb_dot(e2, e2)) < 1.e-6f;
+        float4* t = tris + 3 * (size_t)i;
+        t[0] = make_float4(p.x, p.y, p.z, q.x);
+        t[1] = make_float4(q.y, q.z, r.x, r.y);
+        t[2] = make_float4(r.z, __int_as_float(item), __uint_as_float(sliver ? WB_TRI_SLIVER : 0u), 0.f);
+    } else {
+        src.bounds(item, lo, hi);
+    }
+    pos_parent[i] = WB_NO_PARENT;
+
+    int node = i;          // reference index of the node this thread currently owns
+    int left = i, right = i;
+    unsigned height = 0;
+
+    for (;;) {
+        const int size = right - left + 1;
+        const uint32_t self_ref = (uint32_t)node | (size <= leaf_size ? WB_LEAF : 0u);
+
+        if (left == 0 && right == n - 1) {  // root (bvh.cu:285-290)
+            hdr->lx = lo.x, hdr->ly = lo.y, hdr->lz = lo.z;
+            hdr->hx = hi.x, hdr->hy = hi.y, hdr->hz = hi.z;
+            hdr->root_ref = self_ref;
+            hdr->root_count = (uint32_t)n;
+            hdr->height = (int)height;
+            hdr->deep = 0;
+            hdr->n = n;
+            hdr->leaf_size = leaf_size;
+            if (node >= n)
+                parent_int[node - n] = WB_NO_PARENT;
+            if (self_ref & WB_LEAF)
+                pos_parent[0] = WB_ROOT_PARENT;
+            return;
+        }
+
+        // parent choice (bvh.cu:300-334, ungrouped): larger common prefix wins, ties by item parity
+        bool go_right;
+        if (left == 0) {
+            go_right = true;
+        } else if (right == n - 1) {
+            go_right = false;
+        } else {
+            const int dr = key_delta(keys, right), dl = key_delta(keys, left - 1);
+            if (dr > dl)
+                go_right = true;
+            else if (dr < dl)
+                go_right = false;
+            else
+                go_right = ((__ldg(prim + left - 1) % 2) ^ (__ldg(prim + right) % 2)) != 0;
+        }
+
+        // going right: we are the LEFT child of node n+right; else the RIGHT child of node n+left-1
+        const int s = go_right ? right : left - 1;
+        const int parent = n + s;
+        NodeRec* mine = pairs + 2 * (size_t)s + (go_right ? 0 : 1);
+        NodeRec* sibling = pairs + 2 * (size_t)s + (go_right ? 1 : 0);
+        store_rec(mine, lo, hi, self_ref, (uint32_t)(go_right ? left : right));
+        if (node >= n)
+            parent_int[node - n] = parent;
+
+        __threadfence();
+        const unsigned h = min(height, WB_HEIGHT_CAP);
+        const unsigned old = atomicAdd(&counters[s], 1u | (h << 8));
+        if ((old & 0xffu) == 0u)
+            return;  // first to arrive: the sibling's thread carries on
+        __threadfence();
+
+        // second arrival: fetch the sibling record (written by another SM: bypass L1)
+        const float4 s0 = __ldcg(reinterpret_cast<const float4*>(sibling));
+        const float4 s1 = __ldcg(reinterpret_cast<const float4*>(sibling) + 1);
+        const int far_end = (int)__float_as_uint(s1.w);
+        const int new_left = go_right ? left : far_end;
+        const int new_right = go_right ? far_end : right;
+
+        // visible packed leaves: children that fit leaf_size while this parent does not
+        const int parent_size = new_right - new_left + 1;
+        if (parent_size > leaf_size) {
+            const int lsize = s - new_left + 1, rsize = new_right - s;
+            if (lsize <= leaf_size)
+                pos_parent[new_left] = parent;
+            if (rsize <= leaf_size)
+                pos_parent[s + 1] = parent;
+        }
+
+        lo = wb_min3(lo, make_float3(s0.x, s0.y, s0.z));
+        hi = wb_max3(hi, make_float3(s1.x, s1.y, s1.z));
+        height = max(height, old >> 8) + 1u;
+        left = new_left, right = new_right;
+        node = parent;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5/K6: depth rule (bvh.cu:419-441): a node at depth >= 32 (root = 1) becomes a packed leaf
+// whatever its size.  Only trees taller than 30 edges can contain such a node; everything else
+// returns after one header read.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int depth_capped(const int* __restrict__ parent_int, int n, int internal_node)
+{
+    // depth of an internal node (root = 1), capped at WB_MAX_DEPTH + 1
+    int depth = 1;
+    int p = parent_int[internal_node - n];
+    while (p != WB_NO_PARENT && depth <= WB_MAX_DEPTH) {
+        p = parent_int[p - n];
+        depth++;
+    }
+    return depth;
+}
+
+// pass A (one thread per sorted position): visible leaves whose parent got muted lose their entry
+__global__ void __launch_bounds__(BT)
+k_deep_fix_positions(int n, int leaf_size, TreeHeader* hdr, const int* __restrict__ parent_int, int* pos_parent)
+{
+    if (hdr->height + 1 < WB_MAX_DEPTH)
+        return;
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= n)
+        return;
+    const int p = pos_parent[i];
+    if (p < 0)
+        return;
+    if (depth_capped(parent_int, n, p) >= WB_MAX_DEPTH)  // parent is itself a (possibly muted) depth leaf
+        pos_parent[i] = WB_NO_PARENT;
+}
+
+// pass B (one thread per internal node): nodes at depth exactly 32 become the visible leaves
+__global__ void __launch_bounds__(BT)
+k_deep_fix_nodes(int n, int leaf_size, TreeHeader* hdr, const int* __restrict__ parent_int, NodeRec* pairs,
+                 int* pos_parent)
+{
+    if (hdr->height + 1 < WB_MAX_DEPTH)
+        return;
+    const int s = blockIdx.x * BT + threadIdx.x;
+    if (s >= n - 1)
+        return;
+    const int node = n + s;
+    const int left = (int)pairs[2 * (size_t)s].aux, right = (int)pairs[2 * (size_t)s + 1].aux;
+    if (right - left + 1 <= leaf_size)
+        return;  // already a leaf (or below one) by the size rule
+    if (depth_capped(parent_int, n, node) != WB_MAX_DEPTH)
+        return;
+    const int parent = parent_int[s];  // depth 32 => has a parent at depth 31, which stays internal
+    const int ps = parent - n;
+    NodeRec* rec = pairs + 2 * (size_t)ps + (s < ps ? 0 : 1);
+    rec->ref |= WB_LEAF;
+    pos_parent[left] = parent;
+    hdr->deep = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// export: rebuild the reference's node_lowers / node_uppers / node_parents / root arrays
+// (bvh.h:161-207) from the pair layout, for parity checks and for Warp kernels that walk `id`.
+// ---------------------------------------------------------------------------------------------
+struct RefHalf {
+    float x, y, z;
+    uint32_t ib;
+};
+
+__global__ void __launch_bounds__(BT)
+k_export_reference_layout(int n, int leaf_size, const TreeHeader* __restrict__ hdr, const NodeRec* __restrict__ pairs,
+                          const int* __restrict__ parent_int, RefHalf* lowers, RefHalf* uppers, int* parents, int* root)
+{
+    const int c = blockIdx.x * BT + threadIdx.x;
+    if (c >= 2 * n - 1)
+        return;
+    const int root_node = (int)(hdr->root_ref & WB_IDX_MASK);
+    if (c == root_node) {
+        lowers[c].x = hdr->lx, lowers[c].y = hdr->ly, lowers[c].z = hdr->lz;
+        uppers[c].x = hdr->hx, uppers[c].y = hdr->hy, uppers[c].z = hdr->hz;
+        parents[c] = -1;
+        *root = c;
+    }
+    if (c < n) {  // original leaf: packed-leaf marking turns [c, c] into [c, c+1)
+        lowers[c].ib = WB_LEAF | (uint32_t)c;
+        uppers[c].ib = (uint32_t)(c + 1);
+        return;
+    }
+    const int s = c - n;
+    const NodeRec L = pairs[2 * (size_t)s], R = pairs[2 * (size_t)s + 1];
+    const int cl = (int)(L.ref & WB_IDX_MASK), cr = (int)(R.ref & WB_IDX_MASK);
+    lowers[cl].x = L.lx, lowers[cl].y = L.ly, lowers[cl].z = L.lz;
+    uppers[cl].x = L.hx, uppers[cl].y = L.hy, uppers[cl].z = L.hz;
+    lowers[cr].x = R.lx, lowers[cr].y = R.ly, lowers[cr].z = R.lz;
+    uppers[cr].x = R.hx, uppers[cr].y = R.hy, uppers[cr].z = R.hz;
+    parents[cl] = c;
+    parents[cr] = c;
+    const int left = (int)L.aux, right = (int)R.aux;
+    bool leaf = (right - left + 1) <= leaf_size;
+    if (!leaf && hdr->height + 1 >= WB_MAX_DEPTH)
+        leaf = depth_capped(parent_int, n, c) >= WB_MAX_DEPTH;
+    if (leaf) {
+        lowers[c].ib = WB_LEAF | (uint32_t)left;
+        uppers[c].ib = (uint32_t)(right + 1);
+    } else {
+        lowers[c].ib = (uint32_t)cl;
+        uppers[c].ib = (uint32_t)cr;
+    }
+}
+
+// single item: the root is leaf 0 (bvh.cu:285-290 with n == 1)
+template <class Src>
+__global__ void k_single_item(Src src, int leaf_size, int* prim, uint32_t* keys, int* pos_parent, float4* tris,
+                              TreeHeader* hdr)
+{
+    float3 lo, hi;
+    src.bounds(0, lo, hi);
+    if constexpr (Src::kIsMesh) {
+        float3 p, q, r;
+        src.tri(0, p, q, r);
+        const float3 e0 = wb_sub(q, p), e1 = wb_sub(r, p), e2 = wb_sub(r, q);
+        const float3 nrm = wb_cross(e0, e1);
+        const float area2 = sqrtf(nrm.x * nrm.x + nrm.y * nrm.y + nrm.z * nrm.z);
+        const bool sliver = area2 / (wb_dot(e0, e0) + wb_dot(e1, e1) + wb_dot(e2, e2)) < 1.e-6f;
+        tris[0] = make_float4(p.x, p.y, p.z, q.x);
+        tris[1] = make_float4(q.y, q.z, r.x, r.y);
+        tris[2] = make_float4(r.z, __int_as_float(0), __uint_as_float(sliver ? WB_TRI_SLIVER : 0u), 0.f);
+    }
+    prim[0] = 0;
+    pos_parent[0] = WB_ROOT_PARENT;
+    hdr->lx = lo.x, hdr->ly = lo.y, hdr->lz = lo.z;
+    hdr->hx = hi.x, hdr->hy = hi.y, hdr->hz = hi.z;
+    hdr->root_ref = WB_LEAF | 0u;
+    hdr->root_count = 1;
+    hdr->height = 0;
+    hdr->deep = 0;
+    hdr->n = 1;
+    hdr->leaf_size = leaf_size;
+    hdr->total_lo[0] = lo.x, hdr->total_lo[1] = lo.y, hdr->total_lo[2] = lo.z;
+    hdr->total_hi[0] = hi.x, hdr->total_hi[1] = hi.y, hdr->total_hi[2] = hi.z;
+    hdr->inv_edges[0] = 1.0f / ((hi.x - lo.x) + 0.0001f);
+    hdr->inv_edges[1] = 1.0f / ((hi.y - lo.y) + 0.0001f);
+    hdr->inv_edges[2] = 1.0f / ((hi.z - lo.z) + 0.0001f);
+    const float cx = 0.5f * (lo.x + hi.x), cy = 0.5f * (lo.y + hi.y), cz = 0.5f * (lo.z + hi.z);
+    keys[0] = morton30((cx - lo.x) * hdr->inv_edges[0], (cy - lo.y) * hdr->inv_edges[1], (cz - lo.z) * hdr->inv_edges[2]);
+}
+
+#define WB_CUDA_TRY(expr)                     \
+    do {                                      \
+        cudaError_t _e = (expr);              \
+        if (_e != cudaSuccess)                \
+            return cudaGetErrorString(_e);    \
+    } while (0)
+
+bool use_cub_sort()
+{
+    const char* v = getenv("WARP_B200_SORT");
+    return v && strcmp(v, "cub") == 0;
+}
+
+template <class Src> const char* build_impl(BvhState& s, Src src, cudaStream_t stream)
+{
+    const int n = s.n;
+    if (n == 1) {
+        k_single_item<<<1, 1, 0, stream>>>(src, s.leaf_size, s.prim, s.keys, s.pos_parent, s.tris, s.header);
+        WB_CUDA_TRY(cudaGetLastError());
+        return nullptr;
+    }
+
+    // K1 scene bounds (+ clears histograms / tickets)
+    k_scene_bounds<<<s.bounds_blocks, BT, 0, stream>>>(src, n, s.partials, s.tickets, s.header, s.ghist);
+    // look-back words and arrival counters start from zero
+    WB_CUDA_TRY(cudaMemsetAsync(s.tile_status, 0, sizeof(uint32_t) * 256 * 4 * (size_t)s.num_tiles, stream));
+    WB_CUDA_TRY(cudaMemsetAsync(s.counters, 0, sizeof(unsigned) * (size_t)(n - 1), stream));
+    // K2 Morton keys + histograms
+    k_morton_hist<<<s.bounds_blocks, BT, 0, stream>>>(src, n, s.header, s.keys, s.ghist);
+
+    if (use_cub_sort()) {
+        // library cross-check path (tests only): stable LSD sort of bits [0, 32)
+        size_t need = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, need, s.keys, s.keys_alt, s.prim_alt, s.prim, n, 0, 32, stream);
+        if (need > s.cub_temp_bytes) {
+            if (s.cub_temp)
+                cudaFree(s.cub_temp);
+            WB_CUDA_TRY(cudaMalloc(&s.cub_temp, need));
+            s.cub_temp_bytes = need;
+        }
+        k_iota<<<wb_div_up(n, BT), BT, 0, stream>>>(s.prim_alt, n);
+        WB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(s.cub_temp, need, s.keys, s.keys_alt, s.prim_alt, s.prim, n, 0, 32,
+                                                    stream));
+        WB_CUDA_TRY(cudaMemcpyAsync(s.keys, s.keys_alt, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
+    } else {
+        // K3 x4, ping-pong (keys, prim) <-> (keys_alt, prim_alt); an even pass count ends in (keys, prim),
+        // so the buffers the descriptor points at never change (rebuild stays capture safe)
+        for (int pass = 0; pass < 4; ++pass) {
+            volatile uint32_t* status = s.tile_status + (size_t)pass * 256 * s.num_tiles;
+            const bool fwd = (pass % 2) == 0;
+            const uint32_t* kin = fwd ? s.keys : s.keys_alt;
+            const int* vin = fwd ? s.prim : s.prim_alt;
+            uint32_t* kout = fwd ? s.keys_alt : s.keys;
+            int* vout = fwd ? s.prim_alt : s.prim;
+            if (pass == 0)
+                k_onesweep_pass<true><<<s.num_tiles, RS_THREADS, 0, stream>>>(
+                    kin, nullptr, kout, vout, n, 8 * pass, s.ghist + 256 * pass, status, s.tickets + 1 + pass);
+            else
+                k_onesweep_pass<false><<<s.num_tiles, RS_THREADS, 0, stream>>>(
+                    kin, vin, kout, vout, n, 8 * pass, s.ghist + 256 * pass, status, s.tickets + 1 + pass);
+        }
+    }
+
+    // K4 hierarchy
+    k_hierarchy<<<wb_div_up(n, BT), BT, 0, stream>>>(src, n, s.leaf_size, s.keys, s.prim, s.pairs, s.parent_int,
+                                                    s.pos_parent, s.counters, s.tris, s.header);
+    // K5/K6 depth rule (early-out unless the tree is at least 32 levels deep)
+    k_deep_fix_positions<<<wb_div_up(n, BT), BT, 0, stream>>>(n, s.leaf_size, s.header, s.parent_int, s.pos_parent);
+    k_deep_fix_nodes<<<wb_div_up(n - 1, BT), BT, 0, stream>>>(n, s.leaf_size, s.header, s.parent_int, s.pairs,
+                                                             s.pos_parent);
+    WB_CUDA_TRY(cudaGetLastError());
+    return nullptr;
+}
+
+}  // namespace
+
+const char* wb_alloc_tree(BvhState& s)
+{
+    const size_t n = (size_t)s.n;
+    const size_t ni = n > 1 ? n - 1 : 1;
+    s.num_tiles = wb_div_up((long long)n, RS_TILE);
+    s.bounds_blocks = min(1024, max(1, wb_div_up((long long)n, BT)));
+    WB_CUDA_TRY(cudaMalloc(&s.keys, sizeof(uint32_t) * n));
+    WB_CUDA_TRY(cudaMalloc(&s.keys_alt, sizeof(uint32_t) * n));
+    WB_CUDA_TRY(cudaMalloc(&s.prim, sizeof(int) * n));
+    WB_CUDA_TRY(cudaMalloc(&s.prim_alt, sizeof(int) * n));
+    WB_CUDA_TRY(cudaMalloc(&s.pairs, sizeof(NodeRec) * 2 * ni));
+    WB_CUDA_TRY(cudaMalloc(&s.parent_int, sizeof(int) * ni));
+    WB_CUDA_TRY(cudaMalloc(&s.pos_parent, sizeof(int) * n));
+    WB_CUDA_TRY(cudaMalloc(&s.counters, sizeof(unsigned) * ni));
+    if (s.is_mesh)
+        WB_CUDA_TRY(cudaMalloc(&s.tris, sizeof(float4) * 3 * n));
+    WB_CUDA_TRY(cudaMalloc(&s.header, sizeof(TreeHeader)));
+    WB_CUDA_TRY(cudaMemset(s.header, 0, sizeof(TreeHeader)));
+    WB_CUDA_TRY(cudaMalloc(&s.ghist, sizeof(uint32_t) * 4 * 256));
+    WB_CUDA_TRY(cudaMalloc(&s.tile_status, sizeof(uint32_t) * 256 * 4 * (size_t)s.num_tiles));
+    WB_CUDA_TRY(cudaMalloc(&s.tickets, sizeof(unsigned) * 8));
+    WB_CUDA_TRY(cudaMemset(s.tickets, 0, sizeof(unsigned) * 8));
+    WB_CUDA_TRY(cudaMalloc(&s.partials, sizeof(float) * 6 * (size_t)s.bounds_blocks));
+    return nullptr;
+}
+
+void wb_free_tree(BvhState& s)
+{
+    void* ptrs[] = { s.keys, s.keys_alt, s.prim, s.prim_alt, s.pairs, s.parent_int, s.pos_parent, s.counters,
+                     s.tris, s.header, s.ghist, s.tile_status, s.tickets, s.partials, s.cub_temp,
+                     s.ref_lowers, s.ref_uppers, s.ref_parents, s.ref_root, s.ref_counts };
+    for (void* p : ptrs)
+        if (p)
+            cudaFree(p);
+    s = BvhState();
+}
+
+const char* wb_build(BvhState& s, cudaStream_t stream)
+{
+    if (s.n <= 0)
+        return nullptr;
+    if (s.groups)
+        return "grouped BVHs are not supported by the B200 LBVH builder yet";
+    if (s.is_mesh)
+        return build_impl(s, MeshSource { s.points, s.indices }, stream);
+    return build_impl(s, BoxSource { s.item_lowers, s.item_uppers }, stream);
+}
+
+const char* wb_export_reference_layout(BvhState& s, cudaStream_t stream)
+{
+    if (s.n <= 0)
+        return nullptr;
+    const size_t m = 2 * (size_t)s.n - 1;
+    if (!s.ref_lowers) {
+        WB_CUDA_TRY(cudaMalloc(&s.ref_lowers, sizeof(RefHalf) * m));
+        WB_CUDA_TRY(cudaMalloc(&s.ref_uppers, sizeof(RefHalf) * m));
+        WB_CUDA_TRY(cudaMalloc(&s.ref_parents, sizeof(int) * m));
+        WB_CUDA_TRY(cudaMalloc(&s.ref_counts, sizeof(int) * m));
+        WB_CUDA_TRY(cudaMalloc(&s.ref_root, sizeof(int)));
+    }
+    WB_CUDA_TRY(cudaMemsetAsync(s.ref_lowers, 0, sizeof(RefHalf) * m, stream));
+    WB_CUDA_TRY(cudaMemsetAsync(s.ref_uppers, 0, sizeof(RefHalf) * m, stream));
+    k_export_reference_layout<<<wb_div_up((long long)m, BT), BT, 0, stream>>>(
+        s.n, s.leaf_size, s.header, s.pairs, s.parent_int, (RefHalf*)s.ref_lowers, (RefHalf*)s.ref_uppers,
+        s.ref_parents, s.ref_root);
+    WB_CUDA_TRY(cudaGetLastError());
+    return nullptr;
+}

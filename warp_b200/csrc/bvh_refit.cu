@@ -1,0 +1,120 @@
+// Bottom-up AABB refit over the sibling-pair layout.
+//
+// Behavioural contract = warp/native/bvh.cu:42-144 + mesh.cu:368-407: every visible node's box
+// becomes the exact union (fminf/fmaxf) of the boxes of the items below it.  The reference starts
+// one thread per ORIGINAL leaf and climbs through the muted nodes under each packed leaf; here one
+// thread starts per VISIBLE packed leaf (found through pos_parent[], written by the builder),
+// gathers its <= leaf_size triangles straight from the vertex array (no lowers/uppers round trip,
+// no edge-length / scan passes), refreshes the packed-triangle cache the queries read, and climbs
+// with one atomic arrival counter per internal node.  The counters are never cleared: they are
+// even after a build and every refit adds exactly 2, so "second to arrive" == odd old value.
+#include "state.h"
+
+namespace {
+
+constexpr int BT = 256;
+
+template <class Src>
+__global__ void __launch_bounds__(BT)
+k_refit(Src src, int n, const int* __restrict__ prim, const int* __restrict__ pos_parent,
+        const int* __restrict__ parent_int, NodeRec* pairs, unsigned* counters, float4* __restrict__ tris,
+        TreeHeader* hdr)
+{
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= n)
+        return;
+    const int parent = __ldg(pos_parent + i);
+    if (parent == WB_NO_PARENT)
+        return;
+
+    int s = parent - n;  // internal slot of the parent
+    int side = 0;
+    int count;
+    if (parent == WB_ROOT_PARENT) {
+        count = n;
+    } else if (i <= s) {
+        side = 0;
+        count = s - i + 1;
+    } else {
+        side = 1;
+        count = (int)pairs[2 * (size_t)s + 1].aux - s;
+    }
+
+    float3 lo = make_float3(FLT_MAX, FLT_MAX, FLT_MAX), hi = make_float3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+    for (int k = i; k < i + count; ++k) {
+        const int item = __ldg(prim + k);
+        if constexpr (Src::kIsMesh) {
+            float3 p, q, r;
+            src.tri(item, p, q, r);
+            lo = wb_min3(lo, wb_min3(wb_min3(p, q), r));
+            hi = wb_max3(hi, wb_max3(wb_max3(p, q), r));
+            const float3 e0 = wb_sub(q, p), e1 = wb_sub(r, p), e2 = wb_sub(r, q);
+            const float3 nrm = wb_cross(e0, e1);
+            const float area2 = sqrtf(nrm.x * nrm.x + nrm.y * nrm.y + nrm.z * nrm.z);
+            const bool sliver = area2 / (wb_dot(e0, e0) + wb_dot(e1, e1) + wb_dot(e2, e2)) < 1.e-6f;
+            float4* t = tris + 3 * (size_t)k;
+            t[0] = make_float4(p.x, p.y, p.z, q.x);
+            t[1] = make_float4(q.y, q.z, r.x, r.y);
+            t[2] = make_float4(r.z, __int_as_float(item), __uint_as_float(sliver ? WB_TRI_SLIVER : 0u), 0.f);
+        } else {
+            float3 a, b;
+            src.bounds(item, a, b);
+            lo = wb_min3(lo, a);
+            hi = wb_max3(hi, b);
+        }
+    }
+
+    if (parent == WB_ROOT_PARENT) {
+        hdr->lx = lo.x, hdr->ly = lo.y, hdr->lz = lo.z;
+        hdr->hx = hi.x, hdr->hy = hi.y, hdr->hz = hi.z;
+        return;
+    }
+
+    for (;;) {
+        NodeRec* mine = pairs + 2 * (size_t)s + side;
+        mine->lx = lo.x, mine->ly = lo.y, mine->lz = lo.z;
+        mine->hx = hi.x, mine->hy = hi.y, mine->hz = hi.z;
+        __threadfence();
+        const unsigned old = atomicAdd(&counters[s], 1u);
+        if ((old & 1u) == 0u)
+            return;  // first arrival
+        __threadfence();
+        const float4* sib = reinterpret_cast<const float4*>(pairs + 2 * (size_t)s + (1 - side));
+        const float4 s0 = __ldcg(sib), s1 = __ldcg(sib + 1);
+        lo = wb_min3(lo, make_float3(s0.x, s0.y, s0.z));
+        hi = wb_max3(hi, make_float3(s1.x, s1.y, s1.z));
+        const int up = __ldg(parent_int + s);
+        if (up == WB_NO_PARENT) {
+            hdr->lx = lo.x, hdr->ly = lo.y, hdr->lz = lo.z;
+            hdr->hx = hi.x, hdr->hy = hi.y, hdr->hz = hi.z;
+            return;
+        }
+        const int us = up - n;
+        side = (s < us) ? 0 : 1;
+        s = us;
+    }
+}
+
+}  // namespace
+
+#define WB_CUDA_TRY(expr)                  \
+    do {                                   \
+        cudaError_t _e = (expr);           \
+        if (_e != cudaSuccess)             \
+            return cudaGetErrorString(_e); \
+    } while (0)
+
+const char* wb_refit(BvhState& s, cudaStream_t stream)
+{
+    if (s.n <= 0)
+        return nullptr;
+    const int grid = wb_div_up(s.n, BT);
+    if (s.is_mesh)
+        k_refit<<<grid, BT, 0, stream>>>(MeshSource { s.points, s.indices }, s.n, s.prim, s.pos_parent, s.parent_int,
+                                         s.pairs, s.counters, s.tris, s.header);
+    else
+        k_refit<<<grid, BT, 0, stream>>>(BoxSource { s.item_lowers, s.item_uppers }, s.n, s.prim, s.pos_parent,
+                                         s.parent_int, s.pairs, s.counters, s.tris, s.header);
+    WB_CUDA_TRY(cudaGetLastError());
+    return nullptr;
+}

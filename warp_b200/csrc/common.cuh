@@ -1,0 +1,124 @@
+// Shared device/host definitions for the B200 LBVH path.
+//
+// Tree layout in HBM ("sibling-pair" layout):
+//   * every node is one 32-byte record (NodeRec): AABB + a reference word + one auxiliary word;
+//   * the two children of internal node p = N + s (s = split position in Morton order, the
+//     reference's numbering, warp/native/bvh.cu:337,349) are stored ADJACENT at pair[2s], pair[2s+1],
+//     so one aligned 64-byte fetch yields both child boxes -- the traversal never loads a node's
+//     own box, it arrives with the parent;
+//   * the record of a child carries ref = reference node index (| WB_LEAF when the child is a packed
+//     leaf) and aux = the FAR end of its key range (range start for a left child, range end for a
+//     right child); with s this gives the [start, start+count) primitive range without a side table.
+// The reference's two-array layout (bvh.h:161-207) is reproducible from this one bit-for-bit
+// (k_export_reference_layout) and is what the parity tests diff against the oracle.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#define WB_LEAF 0x80000000u
+#define WB_IDX_MASK 0x7fffffffu
+#define WB_NO_PARENT (-1)
+#define WB_ROOT_PARENT (-2)      // pos_parent[] value of a leaf that is the root itself
+#define WB_QUERY_STACK 32        // BVH_QUERY_STACK_SIZE, warp/native/bvh.h:18
+#define WB_MAX_DEPTH 32          // packed-leaf depth rule, warp/native/bvh.cu:437
+#define WB_HEIGHT_CAP 0xffffu
+
+// one node record = two float4: (lo.xyz, ref) (hi.xyz, aux)
+struct __align__(16) NodeRec {
+    float lx, ly, lz;
+    uint32_t ref;
+    float hx, hy, hz;
+    uint32_t aux;
+};
+
+// per-tree header kept in device memory (read by every query, written by build/refit)
+struct __align__(16) TreeHeader {
+    float lx, ly, lz;       // root AABB
+    uint32_t root_ref;      // reference index of the root (| WB_LEAF if the root is a packed leaf)
+    float hx, hy, hz;
+    uint32_t root_count;    // number of items (range of the root is [0, n))
+    int height;             // longest root-to-original-leaf path in edges (capped at WB_HEIGHT_CAP)
+    int deep;               // 1 when the depth>=32 rule fired on at least one node
+    int n;
+    int leaf_size;
+    // scene bounds used for the Morton grid (bvh.cu:449-488)
+    float total_lo[3];
+    float total_hi[3];
+    float inv_edges[3];
+    int pad[3];
+};
+
+// everything a kernel needs to know about one tree (passed by value)
+struct TreeView {
+    const NodeRec* pairs;        // 2*(n-1) records; children of internal node n+s at [2s], [2s+1]
+    const TreeHeader* header;
+    const float4* tris;          // 3 float4 per sorted position (mesh only): p, q, r, face, flags
+    const int* prim;             // primitive_indices (sorted position -> item)
+    int n;
+};
+
+#define WB_TRI_SLIVER 1u
+
+__host__ __device__ inline int wb_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float3 wb_min3(float3 a, float3 b)
+{
+    return make_float3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z));
+}
+__device__ __forceinline__ float3 wb_max3(float3 a, float3 b)
+{
+    return make_float3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z));
+}
+__device__ __forceinline__ float3 wb_sub(float3 a, float3 b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 wb_add(float3 a, float3 b) { return make_float3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 wb_scale(float s, float3 a) { return make_float3(a.x * s, a.y * s, a.z * s); }
+// a.x*b.x + a.y*b.y + a.z*b.z, summed left to right (vec.h:518-521); the library is built with
+// -fmad=false so this is three roundings + two, like the host build of the reference
+__device__ __forceinline__ float wb_dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float3 wb_cross(float3 a, float3 b)
+{
+    return make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ float wb_get(float3 a, int k) { return k == 0 ? a.x : (k == 1 ? a.y : a.z); }
+
+// item-bounds sources: a triangle mesh (bounds computed on the fly from vertices, replacing the
+// lowers/uppers round trip of mesh.cu:16-36) or caller-provided boxes (wp.Bvh)
+struct MeshSource {
+    const float* points;
+    const int* indices;
+    __device__ __forceinline__ void tri(int t, float3& p, float3& q, float3& r) const
+    {
+        const int i = __ldg(indices + 3 * (size_t)t + 0);
+        const int j = __ldg(indices + 3 * (size_t)t + 1);
+        const int k = __ldg(indices + 3 * (size_t)t + 2);
+        p = make_float3(__ldg(points + 3 * (size_t)i), __ldg(points + 3 * (size_t)i + 1), __ldg(points + 3 * (size_t)i + 2));
+        q = make_float3(__ldg(points + 3 * (size_t)j), __ldg(points + 3 * (size_t)j + 1), __ldg(points + 3 * (size_t)j + 2));
+        r = make_float3(__ldg(points + 3 * (size_t)k), __ldg(points + 3 * (size_t)k + 1), __ldg(points + 3 * (size_t)k + 2));
+    }
+    __device__ __forceinline__ void bounds(int t, float3& lo, float3& hi) const
+    {
+        float3 p, q, r;
+        tri(t, p, q, r);
+        lo = wb_min3(wb_min3(p, q), r);
+        hi = wb_max3(wb_max3(p, q), r);
+    }
+    static constexpr bool kIsMesh = true;
+};
+
+struct BoxSource {
+    const float* lowers;
+    const float* uppers;
+    __device__ __forceinline__ void bounds(int t, float3& lo, float3& hi) const
+    {
+        lo = make_float3(__ldg(lowers + 3 * (size_t)t), __ldg(lowers + 3 * (size_t)t + 1), __ldg(lowers + 3 * (size_t)t + 2));
+        hi = make_float3(__ldg(uppers + 3 * (size_t)t), __ldg(uppers + 3 * (size_t)t + 1), __ldg(uppers + 3 * (size_t)t + 2));
+    }
+    __device__ __forceinline__ void tri(int, float3&, float3&, float3&) const { }
+    static constexpr bool kIsMesh = false;
+};
+
+#endif  // __CUDACC__

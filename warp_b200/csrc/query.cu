@@ -1,0 +1,582 @@
+// Batched mesh queries over the sibling-pair tree: closest point (with / without inside-outside
+// sign) and closest ray hit.  One thread per query; every float operation is written in the order
+// the reference evaluates it (warp/native/mesh.h, intersect.h) and the library is compiled with
+// -fmad=false, so results are bit-identical to the reference's host build on the same tree --
+// including which face wins an exact distance tie, because nodes are visited in the same order.
+//
+// What differs from the reference kernels (mesh.h:128-307, 501-676, 1768-1891, 2286-2359):
+//   * one aligned 64-byte fetch per inner node (both child boxes) instead of 2 + 4 separate 16-byte
+//     loads from two arrays; a node's own box is never re-fetched (its distance rides on the stack);
+//   * leaf triangles come from the packed, Morton-ordered triangle cache (48 contiguous bytes per
+//     triangle incl. face id and sliver flag) instead of the prim -> indices -> points chain;
+//   * the nearer child is entered directly instead of being pushed and popped.
+#include "state.h"
+#include "query.h"
+
+namespace {
+
+constexpr int QT = 128;  // threads per block
+
+struct Entry {
+    uint32_t a;  // leaf: first sorted position | WB_LEAF ; inner: internal slot s
+    uint32_t b;  // leaf: primitive count
+};
+
+struct Tri {
+    float3 p, q, r;
+    int face;
+    uint32_t flags;
+};
+
+__device__ __forceinline__ Tri load_tri(const float4* __restrict__ tris, uint32_t pos)
+{
+    const float4 t0 = __ldg(tris + 3 * (size_t)pos), t1 = __ldg(tris + 3 * (size_t)pos + 1),
+                 t2 = __ldg(tris + 3 * (size_t)pos + 2);
+    Tri t;
+    t.p = make_float3(t0.x, t0.y, t0.z);
+    t.q = make_float3(t0.w, t1.x, t1.y);
+    t.r = make_float3(t1.z, t1.w, t2.x);
+    t.face = __float_as_int(t2.y);
+    t.flags = __float_as_uint(t2.z);
+    return t;
+}
+
+struct Pair {
+    float3 llo, lhi, rlo, rhi;
+    Entry left, right;
+};
+
+// fetch both children of internal slot s and decode their stack entries
+__device__ __forceinline__ Pair load_pair(const NodeRec* __restrict__ pairs, uint32_t s, int n)
+{
+    const float4* p4 = reinterpret_cast<const float4*>(pairs + 2 * (size_t)s);
+    const float4 a0 = __ldg(p4), a1 = __ldg(p4 + 1), b0 = __ldg(p4 + 2), b1 = __ldg(p4 + 3);
+    Pair pr;
+    pr.llo = make_float3(a0.x, a0.y, a0.z), pr.lhi = make_float3(a1.x, a1.y, a1.z);
+    pr.rlo = make_float3(b0.x, b0.y, b0.z), pr.rhi = make_float3(b1.x, b1.y, b1.z);
+    const uint32_t lref = __float_as_uint(a0.w), laux = __float_as_uint(a1.w);
+    const uint32_t rref = __float_as_uint(b0.w), raux = __float_as_uint(b1.w);
+    if (lref & WB_LEAF)
+        pr.left.a = laux | WB_LEAF, pr.left.b = s - laux + 1;  // range [laux, s]
+    else
+        pr.left.a = (lref & WB_IDX_MASK) - (uint32_t)n, pr.left.b = 0;
+    if (rref & WB_LEAF)
+        pr.right.a = (s + 1) | WB_LEAF, pr.right.b = raux - s;  // range [s+1, raux]
+    else
+        pr.right.a = (rref & WB_IDX_MASK) - (uint32_t)n, pr.right.b = 0;
+    return pr;
+}
+
+// squared distance point -> AABB (mesh.h:92-98)
+__device__ __forceinline__ float dist_aabb_sq(float3 p, float3 lo, float3 hi)
+{
+    const float dx = fminf(hi.x, fmaxf(lo.x, p.x)) - p.x;
+    const float dy = fminf(hi.y, fmaxf(lo.y, p.y)) - p.y;
+    const float dz = fminf(hi.z, fmaxf(lo.z, p.z)) - p.z;
+    return dx * dx + dy * dy + dz * dz;
+}
+
+// Voronoi-region closest point on a triangle (intersect.h:44-109); returns (v, w), u = 1 - v - w
+__device__ __forceinline__ void closest_vw(float3 a, float3 b, float3 c, float3 p, float& v, float& w)
+{
+    const float3 ab = wb_sub(b, a), ac = wb_sub(c, a), ap = wb_sub(p, a);
+    const float d1 = wb_dot(ab, ap), d2 = wb_dot(ac, ap);
+    if (d1 <= 0.0f && d2 <= 0.0f) {
+        v = 0.0f, w = 0.0f;
+        return;
+    }
+    const float3 bp = wb_sub(p, b);
+    const float d3 = wb_dot(ab, bp), d4 = wb_dot(ac, bp);
+    if (d3 >= 0.0f && d4 <= d3) {
+        v = 1.0f, w = 0.0f;
+        return;
+    }
+    const float vc = d1 * d4 - d3 * d2;
+    if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f) {
+        v = d1 / (d1 - d3), w = 0.0f;
+        return;
+    }
+    const float3 cp = wb_sub(p, c);
+    const float d5 = wb_dot(ab, cp), d6 = wb_dot(ac, cp);
+    if (d6 >= 0.0f && d5 <= d6) {
+        v = 0.0f, w = 1.0f;
+        return;
+    }
+    const float vb = d5 * d2 - d1 * d6;
+    if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) {
+        v = 0.0f, w = d2 / (d2 - d6);
+        return;
+    }
+    const float va = d3 * d6 - d5 * d4;
+    if (va <= 0.0f && (d4 - d3) >= 0.0f && (d5 - d6) >= 0.0f) {
+        w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        v = 1.0f - w;
+        return;
+    }
+    const float denom = 1.0f / (va + vb + vc);
+    v = vb * denom;
+    w = vc * denom;
+}
+
+// slab tests (intersect.h:127-181)
+__device__ __forceinline__ bool ray_aabb_fast(float3 pos, float3 rcp, float3 lo, float3 hi, float& t)
+{
+    float l1 = (lo.x - pos.x) * rcp.x, l2 = (hi.x - pos.x) * rcp.x;
+    float lmin = fminf(l1, l2), lmax = fmaxf(l1, l2);
+    l1 = (lo.y - pos.y) * rcp.y, l2 = (hi.y - pos.y) * rcp.y;
+    lmin = fmaxf(fminf(l1, l2), lmin), lmax = fminf(fmaxf(l1, l2), lmax);
+    l1 = (lo.z - pos.z) * rcp.z, l2 = (hi.z - pos.z) * rcp.z;
+    lmin = fmaxf(fminf(l1, l2), lmin), lmax = fminf(fmaxf(l1, l2), lmax);
+    const bool hit = (lmax >= 0.f) & (lmax >= lmin);
+    if (hit)
+        t = lmin;
+    return hit;
+}
+
+__device__ __forceinline__ bool ray_aabb_robust(float3 pos, float3 dir, float3 rcp, float3 lo, float3 hi, float& t)
+{
+    float lmin = -FLT_MAX, lmax = FLT_MAX;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float d = wb_get(dir, k), o = wb_get(pos, k), l = wb_get(lo, k), h = wb_get(hi, k);
+        if (d == 0.0f) {
+            if (o < l || o > h)
+                return false;
+        } else {
+            const float r = wb_get(rcp, k);
+            const float l1 = (l - o) * r, l2 = (h - o) * r;
+            lmin = fmaxf(fminf(l1, l2), lmin);
+            lmax = fminf(fmaxf(l1, l2), lmax);
+        }
+    }
+    const bool hit = (lmax >= 0.f) & (lmax >= lmin);
+    if (hit)
+        t = lmin;
+    return hit;
+}
+
+// per-ray constants of the watertight test (intersect.h:359-375)
+struct WoopRay {
+    int kx, ky, kz;
+    float Sx, Sy, Sz;
+};
+
+__device__ __forceinline__ WoopRay woop_setup(float3 dir)
+{
+    WoopRay w;
+    int kz = 0;
+    float best = fabsf(dir.x);
+    if (fabsf(dir.y) > best)
+        kz = 1, best = fabsf(dir.y);
+    if (fabsf(dir.z) > best)
+        kz = 2;
+    int kx = kz + 1 == 3 ? 0 : kz + 1;
+    int ky = kx + 1 == 3 ? 0 : kx + 1;
+    if (wb_get(dir, kz) < 0.0f) {
+        const int tmp = kx;
+        kx = ky, ky = tmp;
+    }
+    w.kx = kx, w.ky = ky, w.kz = kz;
+    w.Sx = wb_get(dir, kx) / wb_get(dir, kz);
+    w.Sy = wb_get(dir, ky) / wb_get(dir, kz);
+    w.Sz = 1.0f / wb_get(dir, kz);
+    return w;
+}
+
+// a*b - c*d with the error of c*d recovered by two explicit FMAs (intersect.h:334-341)
+__device__ __forceinline__ float diff_of_products(float a, float b, float c, float d)
+{
+    const float cd = __fmul_rn(c, d);
+    const float diff = __fmaf_rn(a, b, -cd);
+    const float err = __fmaf_rn(-c, d, cd);
+    return __fadd_rn(diff, err);
+}
+
+// watertight ray/triangle (intersect.h:377-444); t,u,v,sign written on a hit
+__device__ __forceinline__ bool ray_tri(const WoopRay& w, float3 org, float3 a, float3 b, float3 c, float& t, float& u,
+                                        float& v, float& sign)
+{
+    const float3 A = wb_sub(a, org), B = wb_sub(b, org), C = wb_sub(c, org);
+    const float Akz = wb_get(A, w.kz), Bkz = wb_get(B, w.kz), Ckz = wb_get(C, w.kz);
+    const float Ax = wb_get(A, w.kx) - w.Sx * Akz, Ay = wb_get(A, w.ky) - w.Sy * Akz;
+    const float Bx = wb_get(B, w.kx) - w.Sx * Bkz, By = wb_get(B, w.ky) - w.Sy * Bkz;
+    const float Cx = wb_get(C, w.kx) - w.Sx * Ckz, Cy = wb_get(C, w.ky) - w.Sy * Ckz;
+
+    float U = diff_of_products(Cx, By, Cy, Bx);
+    float V = diff_of_products(Ax, Cy, Ay, Cx);
+    float W = diff_of_products(Bx, Ay, By, Ax);
+    if (U == 0.0f || V == 0.0f || W == 0.0f) {
+        U = (float)__dsub_rn(__dmul_rn((double)Cx, (double)By), __dmul_rn((double)Cy, (double)Bx));
+        V = (float)__dsub_rn(__dmul_rn((double)Ax, (double)Cy), __dmul_rn((double)Ay, (double)Cx));
+        W = (float)__dsub_rn(__dmul_rn((double)Bx, (double)Ay), __dmul_rn((double)By, (double)Ax));
+    }
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f))
+        return false;
+    const float det = U + V + W;
+    if (det == 0.0f)
+        return false;
+    const float Az = w.Sz * Akz, Bz = w.Sz * Bkz, Cz = w.Sz * Ckz;
+    const float T = U * Az + V * Bz + W * Cz;
+    const uint32_t det_sign = __float_as_uint(det) & 0x80000000u;
+    if (__uint_as_float(__float_as_uint(T) ^ det_sign) < 0.0f)
+        return false;
+    const float rcp_det = 1.0f / det;
+    u = U * rcp_det;
+    v = V * rcp_det;
+    t = T * rcp_det;
+    sign = det;
+    return true;
+}
+
+struct Counters {
+    unsigned long long pairs = 0;  // 64-byte sibling-pair fetches
+    unsigned long long tris = 0;   // 48-byte packed-triangle fetches
+};
+
+// ------------------------------------------------------------------------------------------------
+// closest point, mesh.h:501-676
+// ------------------------------------------------------------------------------------------------
+template <bool COUNT>
+__device__ __forceinline__ bool closest_point(const TreeView& tv, const TreeHeader& h, float3 point, float max_dist,
+                                              int& face, float& u, float& v, Counters& cnt)
+{
+    Entry stack[WB_QUERY_STACK];
+    float stack_d[WB_QUERY_STACK];
+    int top = 0;
+
+    float best = max_dist * max_dist;
+    int best_face = 0;
+    float best_v = 0.f, best_w = 0.f;
+
+    Entry cur;
+    if (h.root_ref & WB_LEAF)
+        cur.a = WB_LEAF | 0u, cur.b = h.root_count;
+    else
+        cur.a = (h.root_ref & WB_IDX_MASK) - (uint32_t)tv.n, cur.b = 0;
+    float cur_d = dist_aabb_sq(point, make_float3(h.lx, h.ly, h.lz), make_float3(h.hx, h.hy, h.hz));
+    bool have = true;
+
+    for (;;) {
+        if (!have) {
+            if (top == 0)
+                break;
+            --top;
+            cur = stack[top];
+            cur_d = stack_d[top];
+        }
+        have = false;
+        if (cur_d > best)
+            continue;
+        if (cur.a & WB_LEAF) {
+            const uint32_t start = cur.a & WB_IDX_MASK;
+            for (uint32_t pos = start; pos < start + cur.b; ++pos) {
+                const Tri t = load_tri(tv.tris, pos);
+                if (COUNT)
+                    cnt.tris++;
+                if (t.flags & WB_TRI_SLIVER)
+                    continue;
+                float bv, bw;
+                closest_vw(t.p, t.q, t.r, point, bv, bw);
+                const float bu = 1.0f - bv - bw;       // what closest_point_to_triangle returns as u
+                const float w = 1.f - bu - bv;         // mesh.h:569 recomputes w from (u, v)
+                const float3 c = wb_add(wb_add(wb_scale(bu, t.p), wb_scale(bv, t.q)), wb_scale(w, t.r));
+                const float3 d = wb_sub(c, point);
+                const float dsq = wb_dot(d, d);
+                if (dsq < best) {
+                    best = dsq;
+                    best_v = bv;
+                    best_w = w;
+                    best_face = t.face;
+                }
+            }
+            continue;
+        }
+        const Pair pr = load_pair(tv.pairs, cur.a, tv.n);
+        if (COUNT)
+            cnt.pairs++;
+        const float dl = dist_aabb_sq(point, pr.llo, pr.lhi), dr = dist_aabb_sq(point, pr.rlo, pr.rhi);
+        Entry far_e, near_e;
+        float far_d, near_d;
+        if (dl < dr)
+            far_e = pr.right, far_d = dr, near_e = pr.left, near_d = dl;
+        else
+            far_e = pr.left, far_d = dl, near_e = pr.right, near_d = dr;
+        if (far_d < best) {
+            stack[top] = far_e;
+            stack_d[top] = far_d;
+            ++top;
+        }
+        if (near_d < best) {
+            cur = near_e;
+            cur_d = near_d;
+            have = true;
+        }
+    }
+    if (best < max_dist * max_dist) {
+        u = 1.0f - best_v - best_w;
+        v = best_v;
+        face = best_face;
+        return true;
+    }
+    return false;
+}
+
+// sign of the closest hit along an axis probe, push-both order (mesh.h:2286-2339)
+template <bool COUNT>
+__device__ __forceinline__ bool probe_sign(const TreeView& tv, const TreeHeader& h, float3 org, int axis, float& out_sign,
+                                           Counters& cnt)
+{
+    const float3 dir = make_float3(axis == 0 ? 1.f : 0.f, axis == 1 ? 1.f : 0.f, axis == 2 ? 1.f : 0.f);
+    const float3 rcp = make_float3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+    const WoopRay wr = woop_setup(dir);
+
+    Entry stack[WB_QUERY_STACK];
+    float stack_t[WB_QUERY_STACK];
+    int top = 0;
+    float min_t = FLT_MAX;
+    bool hit = false;
+
+    {
+        float tt;
+        if (ray_aabb_robust(org, dir, rcp, make_float3(h.lx, h.ly, h.lz), make_float3(h.hx, h.hy, h.hz), tt)) {
+            if (h.root_ref & WB_LEAF)
+                stack[0].a = WB_LEAF | 0u, stack[0].b = h.root_count;
+            else
+                stack[0].a = (h.root_ref & WB_IDX_MASK) - (uint32_t)tv.n, stack[0].b = 0;
+            stack_t[0] = tt;
+            top = 1;
+        }
+    }
+    while (top) {
+        --top;
+        const Entry cur = stack[top];
+        if (!(stack_t[top] < min_t))
+            continue;
+        if (cur.a & WB_LEAF) {
+            const uint32_t start = cur.a & WB_IDX_MASK;
+            for (uint32_t pos = start; pos < start + cur.b; ++pos) {
+                const Tri t = load_tri(tv.tris, pos);
+                if (COUNT)
+                    cnt.tris++;
+                float tt, tu, tvv, ts;
+                if (ray_tri(wr, org, t.p, t.q, t.r, tt, tu, tvv, ts)) {
+                    if (tt >= 0.0f && tt < min_t) {
+                        min_t = tt;
+                        out_sign = ts;
+                        hit = true;
+                    }
+                }
+            }
+        } else {
+            const Pair pr = load_pair(tv.pairs, cur.a, tv.n);
+            if (COUNT)
+                cnt.pairs++;
+            float tl, tr;
+            if (ray_aabb_robust(org, dir, rcp, pr.llo, pr.lhi, tl)) {
+                stack[top] = pr.left;
+                stack_t[top] = tl;
+                ++top;
+            }
+            if (ray_aabb_robust(org, dir, rcp, pr.rlo, pr.rhi, tr)) {
+                stack[top] = pr.right;
+                stack_t[top] = tr;
+                ++top;
+            }
+        }
+    }
+    return hit;
+}
+
+template <bool SIGN, bool COUNT>
+__global__ void __launch_bounds__(QT)
+k_query_point(TreeView tv, const float* __restrict__ pts, long long nq, float max_dist, uint8_t* __restrict__ result,
+              float* __restrict__ sign, int* __restrict__ face, float* __restrict__ u, float* __restrict__ v,
+              unsigned long long* __restrict__ stats)
+{
+    const TreeHeader h = *tv.header;
+    Counters cnt;
+    for (long long i = (long long)blockIdx.x * QT + threadIdx.x; i < nq; i += (long long)gridDim.x * QT) {
+        const float3 p = make_float3(__ldg(pts + 3 * i), __ldg(pts + 3 * i + 1), __ldg(pts + 3 * i + 2));
+        int f = 0;
+        float bu = 0.f, bv = 0.f, sg = 0.f;
+        const bool ok = closest_point<COUNT>(tv, h, p, max_dist, f, bu, bv, cnt);
+        if (SIGN && ok) {  // majority of three axis probes, mesh.h:2342-2359
+            int votes = 0;
+            float s = 0.f;
+#pragma unroll 1
+            for (int axis = 0; axis < 3; ++axis)
+                if (probe_sign<COUNT>(tv, h, p, axis, s, cnt) && s < 0.f)
+                    votes++;
+            sg = votes >= 2 ? -1.0f : 1.0f;
+        }
+        result[i] = ok ? 1 : 0;
+        face[i] = ok ? f : 0;
+        u[i] = ok ? bu : 0.f;
+        v[i] = ok ? bv : 0.f;
+        if (sign)
+            sign[i] = sg;
+    }
+    if (COUNT) {
+        atomicAdd(stats + 0, cnt.pairs);
+        atomicAdd(stats + 1, cnt.tris);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// closest ray hit, near child first (mesh.h:1735-1891)
+// ------------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(QT)
+k_query_ray(TreeView tv, const float* __restrict__ starts, const float* __restrict__ dirs, long long nq, float max_t,
+            uint8_t* __restrict__ result, float* __restrict__ sign, int* __restrict__ face, float* __restrict__ out_t,
+            float* __restrict__ out_u, float* __restrict__ out_v, float* __restrict__ normal,
+            unsigned long long* __restrict__ stats)
+{
+    const TreeHeader h = *tv.header;
+    Counters cnt;
+    for (long long i = (long long)blockIdx.x * QT + threadIdx.x; i < nq; i += (long long)gridDim.x * QT) {
+        const float3 org = make_float3(__ldg(starts + 3 * i), __ldg(starts + 3 * i + 1), __ldg(starts + 3 * i + 2));
+        const float3 dir = make_float3(__ldg(dirs + 3 * i), __ldg(dirs + 3 * i + 1), __ldg(dirs + 3 * i + 2));
+        float3 safe = dir;
+        if (safe.x == 0.0f)
+            safe.x = 1.0e-20f;
+        if (safe.y == 0.0f)
+            safe.y = 1.0e-20f;
+        if (safe.z == 0.0f)
+            safe.z = 1.0e-20f;
+        const float3 rcp = make_float3(1.0f / safe.x, 1.0f / safe.y, 1.0f / safe.z);
+        const bool fast = dir.x != 0.0f && dir.y != 0.0f && dir.z != 0.0f;
+        const WoopRay wr = woop_setup(dir);
+
+        Entry stack[WB_QUERY_STACK];
+        int top = 0;
+        Entry cur;
+        if (h.root_ref & WB_LEAF)
+            cur.a = WB_LEAF | 0u, cur.b = h.root_count;
+        else
+            cur.a = (h.root_ref & WB_IDX_MASK) - (uint32_t)tv.n, cur.b = 0;
+
+        float min_t = max_t, min_u = 0.f, min_v = 0.f, min_sign = 1.0f;
+        int min_face = 0;
+        uint32_t min_pos = 0;
+        bool hit = false;
+
+        for (;;) {
+            if (cur.a & WB_LEAF) {
+                const uint32_t start = cur.a & WB_IDX_MASK;
+                for (uint32_t pos = start; pos < start + cur.b; ++pos) {
+                    const Tri t = load_tri(tv.tris, pos);
+                    if (COUNT)
+                        cnt.tris++;
+                    float tt, tu, tvv, ts;
+                    if (ray_tri(wr, org, t.p, t.q, t.r, tt, tu, tvv, ts)) {
+                        if (tt < min_t && tt >= 0.0f) {
+                            min_t = tt, min_face = t.face, min_u = tu, min_v = tvv, min_sign = ts, min_pos = pos;
+                            hit = true;
+                        }
+                    }
+                }
+                if (top == 0)
+                    break;
+                cur = stack[--top];
+                continue;
+            }
+            const Pair pr = load_pair(tv.pairs, cur.a, tv.n);
+            if (COUNT)
+                cnt.pairs++;
+            float t0 = FLT_MAX, t1 = FLT_MAX;
+            const bool h0 = (fast ? ray_aabb_fast(org, rcp, pr.llo, pr.lhi, t0)
+                                  : ray_aabb_robust(org, dir, rcp, pr.llo, pr.lhi, t0))
+                && t0 < min_t;
+            const bool h1 = (fast ? ray_aabb_fast(org, rcp, pr.rlo, pr.rhi, t1)
+                                  : ray_aabb_robust(org, dir, rcp, pr.rlo, pr.rhi, t1))
+                && t1 < min_t;
+            if (h0 && h1) {
+                const bool near_left = t0 < t1;
+                if (top >= WB_QUERY_STACK)
+                    break;  // mesh.h:1860-1861
+                stack[top++] = near_left ? pr.right : pr.left;
+                cur = near_left ? pr.left : pr.right;
+            } else if (h0) {
+                cur = pr.left;
+            } else if (h1) {
+                cur = pr.right;
+            } else {
+                if (top == 0)
+                    break;
+                cur = stack[--top];
+            }
+        }
+
+        float3 nrm = make_float3(0.f, 0.f, 0.f);
+        if (hit) {
+            const Tri t = load_tri(tv.tris, min_pos);
+            const float3 g = wb_cross(wb_sub(t.q, t.p), wb_sub(t.r, t.p));
+            const float l = sqrtf(g.x * g.x + g.y * g.y + g.z * g.z);
+            if (l > 0.0f)
+                nrm = make_float3(g.x / l, g.y / l, g.z / l);
+        }
+        result[i] = hit ? 1 : 0;
+        sign[i] = hit ? min_sign : 0.f;
+        face[i] = hit ? min_face : 0;
+        out_t[i] = hit ? min_t : 0.f;
+        out_u[i] = hit ? min_u : 0.f;
+        out_v[i] = hit ? min_v : 0.f;
+        normal[3 * i + 0] = nrm.x;
+        normal[3 * i + 1] = nrm.y;
+        normal[3 * i + 2] = nrm.z;
+    }
+    if (COUNT) {
+        atomicAdd(stats + 0, cnt.pairs);
+        atomicAdd(stats + 1, cnt.tris);
+    }
+}
+
+int query_grid(long long nq)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long want = (nq + QT - 1) / QT;
+    const long long cap = (long long)sms * 64;  // grid-stride beyond that
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+}  // namespace
+
+const char* wb_query_point(const TreeView& tv, const float* pts, long long nq, float max_dist, int with_sign,
+                           uint8_t* result, float* sign, int* face, float* u, float* v, unsigned long long* stats,
+                           cudaStream_t stream)
+{
+    if (nq <= 0)
+        return nullptr;
+    const int grid = query_grid(nq);
+    if (with_sign) {
+        if (stats)
+            k_query_point<true, true><<<grid, QT, 0, stream>>>(tv, pts, nq, max_dist, result, sign, face, u, v, stats);
+        else
+            k_query_point<true, false><<<grid, QT, 0, stream>>>(tv, pts, nq, max_dist, result, sign, face, u, v, stats);
+    } else {
+        if (stats)
+            k_query_point<false, true><<<grid, QT, 0, stream>>>(tv, pts, nq, max_dist, result, sign, face, u, v, stats);
+        else
+            k_query_point<false, false><<<grid, QT, 0, stream>>>(tv, pts, nq, max_dist, result, sign, face, u, v, stats);
+    }
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+const char* wb_query_ray(const TreeView& tv, const float* starts, const float* dirs, long long nq, float max_t,
+                         uint8_t* result, float* sign, int* face, float* t, float* u, float* v, float* normal,
+                         unsigned long long* stats, cudaStream_t stream)
+{
+    if (nq <= 0)
+        return nullptr;
+    const int grid = query_grid(nq);
+    if (stats)
+        k_query_ray<true><<<grid, QT, 0, stream>>>(tv, starts, dirs, nq, max_t, result, sign, face, t, u, v, normal, stats);
+    else
+        k_query_ray<false><<<grid, QT, 0, stream>>>(tv, starts, dirs, nq, max_t, result, sign, face, t, u, v, normal, stats);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}

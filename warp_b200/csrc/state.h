@@ -1,0 +1,68 @@
+// Host-side bookkeeping for one BVH / mesh object.  The public handle ("id") is the address of a
+// device-resident descriptor laid out like the reference's wp::BVH / wp::Mesh (see
+// include/warp_b200.h); this struct is what the library itself works from.
+#pragma once
+
+#include "common.cuh"
+
+struct BvhState {
+    int n = 0;
+    int leaf_size = 1;
+    int constructor_type = 2;
+    bool is_mesh = false;
+    int device = 0;
+
+    // borrowed inputs (owned by the caller, like the reference: warp.h:105-106)
+    const float* item_lowers = nullptr;
+    const float* item_uppers = nullptr;
+    const int* groups = nullptr;
+    const float* points = nullptr;
+    const int* indices = nullptr;
+    int num_points = 0;
+
+    // owned tree storage
+    uint32_t* keys = nullptr;     // n sorted Morton keys
+    int* prim = nullptr;          // n primitive_indices
+    NodeRec* pairs = nullptr;     // 2*(n-1) node records
+    int* parent_int = nullptr;    // n-1: parent (reference index) of internal node n+s, -1 for the root
+    int* pos_parent = nullptr;    // n: parent of the visible leaf starting at sorted position i, else -1
+    unsigned* counters = nullptr; // n-1 arrival counters (build: count | height<<8; refit: parity)
+    float4* tris = nullptr;       // 3n packed triangles in sorted order (mesh only)
+    TreeHeader* header = nullptr;
+
+    // build workspace, kept so rebuild() allocates nothing (bvh.cu:790-803 semantics)
+    uint32_t* keys_alt = nullptr;
+    int* prim_alt = nullptr;
+    uint32_t* ghist = nullptr;        // 4 x 256 digit histograms
+    uint32_t* tile_status = nullptr;  // 4 passes x tiles x 256 look-back words
+    unsigned* tickets = nullptr;      // small block of counters (tile tickets, last-block tickets)
+    float* partials = nullptr;        // per-block scene-bounds partials
+    void* cub_temp = nullptr;         // only used by the WARP_B200_SORT=cub cross-check path
+    size_t cub_temp_bytes = 0;
+    int num_tiles = 0;
+    int bounds_blocks = 0;
+
+    // lazily materialised mirror in the reference's own node layout (bvh.h:161-207)
+    void* ref_lowers = nullptr;
+    void* ref_uppers = nullptr;
+    int* ref_parents = nullptr;
+    int* ref_root = nullptr;
+    int* ref_counts = nullptr;
+
+    void* dev_desc = nullptr;  // device copy of the reference-compatible descriptor; its address is the id
+};
+
+struct MeshState {
+    BvhState bvh;
+    uint64_t points_data = 0, velocities_data = 0, indices_data = 0;
+    int num_points = 0, num_tris = 0;
+    int points_shape0 = 0, velocities_shape0 = 0;
+    void* dev_desc = nullptr;
+};
+
+// build / refit / export drivers (bvh_build.cu, bvh_refit.cu); all enqueue on `stream`
+const char* wb_build(BvhState& s, cudaStream_t stream);
+const char* wb_refit(BvhState& s, cudaStream_t stream);
+const char* wb_export_reference_layout(BvhState& s, cudaStream_t stream);
+const char* wb_alloc_tree(BvhState& s);
+void wb_free_tree(BvhState& s);

@@ -1,0 +1,222 @@
+"""Query sharding across GPUs: one process per GPU, mesh + BVH replicated, query batch partitioned
+contiguously, SoA results gathered with NCCL over NVLink.  Build and refit are
+"replicas only": every rank builds its own (bit-identical, deterministic) tree.
+
+The reference has no multi-GPU driver for this path (its FAQ points at nccl4py / mpi4py,
+docs/user_guide/faq.rst:405-452); this module is the new call site.
+
+Host logic (``ShardPlan``, ``gather_fields``) is backend agnostic so it can be exercised on CPU with
+a gloo communicator (tests/test_distributed_cpu.py); the product backend is ``NcclCommunicator``.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import socket
+import struct
+import time
+
+import numpy as np
+
+from . import _lib
+
+
+class ShardPlan:
+    """Contiguous, equal-size (padded) partition of ``n`` queries over ``world`` ranks.
+
+    Equal sizes make the gather a plain all-gather; the last ranks may own fewer (or zero) real
+    queries, their tail is padding that is computed on nothing and trimmed after the gather.
+    """
+
+    def __init__(self, n: int, world: int):
+        if world < 1 or n < 0:
+            raise ValueError("ShardPlan: need world >= 1 and n >= 0")
+        self.n, self.world = int(n), int(world)
+        self.shard = (self.n + self.world - 1) // self.world if self.n else 0
+        self.padded = self.shard * self.world
+
+    def range(self, rank: int):
+        """[start, end) of the real queries owned by ``rank``."""
+        start = min(rank * self.shard, self.n)
+        return start, min(start + self.shard, self.n)
+
+    def count(self, rank: int) -> int:
+        s, e = self.range(rank)
+        return e - s
+
+
+class NcclCommunicator:
+    """Thin wrapper over the native NCCL entry points (device pointers, library's current stream)."""
+
+    def __init__(self, rank: int, world: int, unique_id: bytes):
+        self.rank, self.world = rank, world
+        buf = ctypes.create_string_buffer(unique_id, 128)
+        if not _lib.core().wp_b200_nccl_init(buf, world, rank):
+            raise RuntimeError("NCCL communicator initialisation failed")
+
+    @staticmethod
+    def load(path: str | None = None):
+        cand = [path] if path else [None]
+        try:  # the wheel-bundled NCCL (newer than the system one) if present
+            import importlib.util
+
+            spec = importlib.util.find_spec("nvidia.nccl")
+            if spec and spec.submodule_search_locations:
+                cand.insert(0, os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2"))
+        except Exception:
+            pass
+        for c in cand:
+            if c is None or os.path.exists(c):
+                if _lib.core().wp_b200_nccl_load(c.encode() if c else None):
+                    return
+        raise RuntimeError("cannot load libnccl.so.2")
+
+    @staticmethod
+    def new_unique_id() -> bytes:
+        NcclCommunicator.load()
+        buf = ctypes.create_string_buffer(128)
+        if not _lib.core().wp_b200_nccl_unique_id(buf):
+            raise RuntimeError("ncclGetUniqueId failed")
+        return buf.raw
+
+    def allgather(self, send, recv, nbytes_per_rank: int):
+        """``send`` / ``recv``: objects with ``.ptr`` (device arrays)."""
+        if not _lib.core().wp_b200_nccl_allgather(ctypes.c_void_p(send.ptr), ctypes.c_void_p(recv.ptr), nbytes_per_rank):
+            raise RuntimeError("ncclAllGather failed")
+
+    def allreduce_max(self, arr):
+        if not _lib.core().wp_b200_nccl_allreduce_max_f32(ctypes.c_void_p(arr.ptr), arr.size):
+            raise RuntimeError("ncclAllReduce failed")
+
+    def barrier(self):
+        if not _lib.core().wp_b200_nccl_barrier():
+            raise RuntimeError("NCCL barrier failed")
+
+    def close(self):
+        _lib.core().wp_b200_nccl_destroy()
+
+
+def exchange_unique_id(rank: int, world: int, make_id, addr: str | None = None, port: int | None = None,
+                       timeout: float = 300.0) -> bytes:
+    """Rank 0 creates an id with ``make_id()`` and serves it over TCP; the others fetch it.
+
+    Defaults come from the torchrun environment (MASTER_ADDR, MASTER_PORT + 1 -- torchrun's own
+    store owns MASTER_PORT); override the port with WARP_B200_BOOTSTRAP_PORT.
+    """
+    addr = addr or os.environ.get("MASTER_ADDR", "127.0.0.1")
+    if port is None:
+        port = int(os.environ.get("WARP_B200_BOOTSTRAP_PORT", int(os.environ.get("MASTER_PORT", "29500")) + 1))
+    if world == 1:
+        return make_id()
+    if rank == 0:
+        uid = make_id()
+        srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+        srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+        srv.bind((addr, port))
+        srv.listen(world)
+        srv.settimeout(timeout)
+        served = 0
+        while served < world - 1:
+            conn, _ = srv.accept()
+            conn.sendall(struct.pack("<I", len(uid)) + uid)
+            conn.close()
+            served += 1
+        srv.close()
+        return uid
+    deadline = time.time() + timeout
+    while True:
+        try:
+            s = socket.create_connection((addr, port), timeout=5.0)
+            break
+        except OSError:
+            if time.time() > deadline:
+                raise RuntimeError(f"rank {rank}: cannot reach the bootstrap server at {addr}:{port}") from None
+            time.sleep(0.1)
+    data = b""
+    while len(data) < 4:
+        data += s.recv(4 - len(data))
+    (ln,) = struct.unpack("<I", data)
+    uid = b""
+    while len(uid) < ln:
+        chunk = s.recv(ln - len(uid))
+        if not chunk:
+            raise RuntimeError("bootstrap connection closed early")
+        uid += chunk
+    s.close()
+    return uid
+
+
+def init_from_env():
+    """(rank, world, local_rank, communicator-or-None) from RANK / WORLD_SIZE / LOCAL_RANK (torchrun)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    _lib.core().wp_cuda_context_set_current(ctypes.c_void_p(local_rank + 1))
+    if world == 1:
+        return rank, world, local_rank, None
+    NcclCommunicator.load()
+    uid = exchange_unique_id(rank, world, NcclCommunicator.new_unique_id)
+    return rank, world, local_rank, NcclCommunicator(rank, world, uid)
+
+
+FIELD_BYTES = {"result": 1, "sign": 4, "face": 4, "t": 4, "u": 4, "v": 4, "normal": 12}
+
+
+def gather_fields(local: dict, plan: ShardPlan, comm, alloc):
+    """All-gather every field of a per-rank SoA result (arrays of ``plan.shard`` entries) into arrays
+    of ``plan.padded`` entries laid out rank-major, i.e. in global query order.
+
+    ``alloc(field, count)`` returns a destination buffer; ``comm.allgather(send, recv, nbytes)``
+    moves the bytes.  Returns {field: gathered buffer}; callers trim to ``plan.n``.
+    """
+    out = {}
+    for name, arr in local.items():
+        dst = alloc(name, plan.padded)
+        comm.allgather(arr, dst, plan.shard * FIELD_BYTES[name])
+        out[name] = dst
+    return out
+
+
+def sharded_query_point_no_sign(mesh, local_points, plan: ShardPlan, max_dist: float, comm, rank: int,
+                                local_out=None, global_out=None):
+    """Each rank answers its shard of a global batch; every rank ends up with all ``plan.n`` answers.
+
+    ``local_points``: device array with ``plan.shard`` vec3 entries (entries past ``plan.count(rank)``
+    are padding).  Returns ``(global_fields, n)``; fields are device arrays of ``plan.padded`` entries.
+    """
+    from .queries import mesh_query_point_no_sign
+    from .types import empty, float32, int32, uint8
+
+    dev = mesh.device
+    res = mesh_query_point_no_sign(mesh, local_points, max_dist, out=local_out)
+    local = {"result": res.result, "face": res.face, "u": res.u, "v": res.v}
+    dtypes = {"result": uint8, "face": int32, "u": float32, "v": float32}
+    if comm is None:
+        return local, plan.n
+    if global_out is None:
+        global_out = {k: empty(plan.padded, dtypes[k], dev) for k in local}
+    return gather_fields(local, plan, comm, lambda name, count: global_out[name]), plan.n
+
+
+class GlooCommunicator:
+    """CPU stand-in used by the world_size-2 tests: same ``allgather`` contract over numpy buffers."""
+
+    def __init__(self):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+    def allgather(self, send: np.ndarray, recv: np.ndarray, nbytes_per_rank: int):
+        import torch
+
+        s = torch.from_numpy(send.view(np.uint8).reshape(-1)[:nbytes_per_rank].copy())
+        parts = [torch.empty(nbytes_per_rank, dtype=torch.uint8) for _ in range(self.world)]
+        self.dist.all_gather(parts, s)
+        flat = recv.view(np.uint8).reshape(-1)
+        for r, p in enumerate(parts):
+            flat[r * nbytes_per_rank : (r + 1) * nbytes_per_rank] = p.numpy()
+
+    def barrier(self):
+        self.dist.barrier()

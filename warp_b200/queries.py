@@ -1,0 +1,172 @@
+"""Batched equivalents of ``wp.mesh_query_point_no_sign``, ``wp.mesh_query_point`` and
+``wp.mesh_query_ray`` (``warp/_src/builtins.py:8336-8440, 8569-8655, 8974-9081``).
+
+The reference evaluates these per thread inside user kernels and returns a ``MeshQueryPoint`` /
+``MeshQueryRay`` struct; here one call evaluates a whole batch and returns the same fields as
+arrays (struct of arrays).  On a miss ``result`` is 0 and every other field is 0, as for the
+struct-returning overloads (``warp/native/mesh.h:1514-1540, 2216-2257``).
+
+Inputs may be device ``array``s (results are device ``array``s; asynchronous on the current stream)
+or host numpy arrays (results are numpy arrays; the native ``*_host`` entry points stage the batch
+through the GPU in chunks and return when the results are valid).
+"""
+
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .types import Mesh, array, empty, float32, int32, uint8, vec3
+
+
+class MeshQueryPoint:
+    """``result`` (uint8), ``sign``, ``face``, ``u``, ``v`` -- one entry per query (types.py:7786-7815)."""
+
+    __slots__ = ("result", "sign", "face", "u", "v")
+
+    def __init__(self, result, sign, face, u, v):
+        self.result, self.sign, self.face, self.u, self.v = result, sign, face, u, v
+
+    def numpy(self):
+        return {k: (getattr(self, k).numpy() if isinstance(getattr(self, k), array) else getattr(self, k))
+                for k in self.__slots__}  # fmt: skip
+
+
+class MeshQueryRay:
+    """``result``, ``sign``, ``face``, ``t``, ``u``, ``v``, ``normal`` -- one entry per ray (types.py:7820-7848)."""
+
+    __slots__ = ("result", "sign", "face", "t", "u", "v", "normal")
+
+    def __init__(self, result, sign, face, t, u, v, normal):
+        self.result, self.sign, self.face, self.t, self.u, self.v, self.normal = result, sign, face, t, u, v, normal
+
+    def numpy(self):
+        return {k: (getattr(self, k).numpy() if isinstance(getattr(self, k), array) else getattr(self, k))
+                for k in self.__slots__}  # fmt: skip
+
+
+def _mesh_id(mesh):
+    if isinstance(mesh, Mesh):
+        if not mesh.id:
+            raise RuntimeError("mesh has no native object")
+        return mesh.id, mesh.device
+    raise TypeError("expected a warp_b200.Mesh")
+
+
+def _dev_vec3(a, what):
+    if a.dtype != vec3:
+        raise RuntimeError(f"{what} should be an array of type wp.vec3")
+    return a
+
+
+def _host_vec3(a, what):
+    h = np.ascontiguousarray(a, dtype=np.float32)
+    if h.ndim != 2 or h.shape[1] != 3:
+        raise RuntimeError(f"{what} should have shape (n, 3)")
+    return h
+
+
+def _p(a):
+    if isinstance(a, array):
+        return ctypes.c_void_p(a.ptr or 0)
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _check(ok, what):
+    if not ok:
+        raise RuntimeError(f"{what} failed: {_lib.error_string()}")
+
+
+def _point_query(mesh, points, max_dist, with_sign, out):
+    id_, dev = _mesh_id(mesh)
+    c = _lib.core()
+    if isinstance(points, array):
+        pts = _dev_vec3(points, "points")
+        n = len(pts)
+        if out is None:
+            out = MeshQueryPoint(empty(n, uint8, dev), empty(n, float32, dev), empty(n, int32, dev),
+                                 empty(n, float32, dev), empty(n, float32, dev))  # fmt: skip
+        if with_sign:
+            ok = c.wp_b200_mesh_query_point(id_, _p(pts), n, max_dist, _p(out.result), _p(out.sign), _p(out.face),
+                                            _p(out.u), _p(out.v))  # fmt: skip
+        else:
+            out.sign.zero_()
+            ok = c.wp_b200_mesh_query_point_no_sign(id_, _p(pts), n, max_dist, _p(out.result), _p(out.face),
+                                                    _p(out.u), _p(out.v))  # fmt: skip
+        _check(ok, "mesh_query_point")
+        return out
+    pts = _host_vec3(points, "points")
+    n = pts.shape[0]
+    if out is None:
+        out = MeshQueryPoint(np.zeros(n, np.uint8), np.zeros(n, np.float32), np.zeros(n, np.int32),
+                             np.zeros(n, np.float32), np.zeros(n, np.float32))  # fmt: skip
+    if with_sign:
+        ok = c.wp_b200_mesh_query_point_host(id_, _p(pts), n, max_dist, _p(out.result), _p(out.sign), _p(out.face),
+                                             _p(out.u), _p(out.v))  # fmt: skip
+    else:
+        ok = c.wp_b200_mesh_query_point_no_sign_host(id_, _p(pts), n, max_dist, _p(out.result), _p(out.face),
+                                                     _p(out.u), _p(out.v))  # fmt: skip
+    _check(ok, "mesh_query_point")
+    return out
+
+
+def mesh_query_point_no_sign(mesh, points, max_dist: float, out: MeshQueryPoint | None = None) -> MeshQueryPoint:
+    """Closest point on ``mesh`` to each of ``points`` within ``max_dist``; ``sign`` is 0 (mesh.h:501-676)."""
+    return _point_query(mesh, points, float(max_dist), False, out)
+
+
+def mesh_query_point(mesh, points, max_dist: float, out: MeshQueryPoint | None = None) -> MeshQueryPoint:
+    """Closest point + inside/outside ``sign`` by three axis-ray probes (mesh.h:128-307, 2342-2359)."""
+    return _point_query(mesh, points, float(max_dist), True, out)
+
+
+def mesh_query_ray(mesh, starts, dirs, max_t: float, out: MeshQueryRay | None = None) -> MeshQueryRay:
+    """Closest hit of each ray ``starts[i] + t * dirs[i]``, ``0 <= t < max_t`` (mesh.h:1768-1891)."""
+    id_, dev = _mesh_id(mesh)
+    c = _lib.core()
+    max_t = float(max_t)
+    if isinstance(starts, array) != isinstance(dirs, array):
+        raise RuntimeError("starts and dirs must both be device arrays or both be host arrays")
+    if isinstance(starts, array):
+        s, d = _dev_vec3(starts, "starts"), _dev_vec3(dirs, "dirs")
+        if len(s) != len(d):
+            raise RuntimeError("starts and dirs must have the same length")
+        n = len(s)
+        if out is None:
+            out = MeshQueryRay(empty(n, uint8, dev), empty(n, float32, dev), empty(n, int32, dev),
+                               empty(n, float32, dev), empty(n, float32, dev), empty(n, float32, dev),
+                               empty(n, vec3, dev))  # fmt: skip
+        ok = c.wp_b200_mesh_query_ray(id_, _p(s), _p(d), n, max_t, _p(out.result), _p(out.sign), _p(out.face),
+                                      _p(out.t), _p(out.u), _p(out.v), _p(out.normal))  # fmt: skip
+        _check(ok, "mesh_query_ray")
+        return out
+    s, d = _host_vec3(starts, "starts"), _host_vec3(dirs, "dirs")
+    if s.shape != d.shape:
+        raise RuntimeError("starts and dirs must have the same length")
+    n = s.shape[0]
+    if out is None:
+        out = MeshQueryRay(np.zeros(n, np.uint8), np.zeros(n, np.float32), np.zeros(n, np.int32),
+                           np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32),
+                           np.zeros((n, 3), np.float32))  # fmt: skip
+    ok = c.wp_b200_mesh_query_ray_host(id_, _p(s), _p(d), n, max_t, _p(out.result), _p(out.sign), _p(out.face),
+                                       _p(out.t), _p(out.u), _p(out.v), _p(out.normal))  # fmt: skip
+    _check(ok, "mesh_query_ray")
+    return out
+
+
+class query_stats:
+    """Context manager: count 64-byte pair fetches and 48-byte triangle fetches of the queries inside."""
+
+    def __enter__(self):
+        _lib.core().wp_b200_query_stats_enable(1)
+        self.pair_fetches = self.tri_fetches = 0
+        return self
+
+    def __exit__(self, *exc):
+        a, b = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+        _lib.core().wp_b200_query_stats_read(ctypes.byref(a), ctypes.byref(b))
+        self.pair_fetches, self.tri_fetches = a.value, b.value
+        _lib.core().wp_b200_query_stats_enable(0)
+        return False
