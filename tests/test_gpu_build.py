@@ -181,3 +181,21 @@ def test_native_failure_raises_with_error_string(wp):
     lo, hi = random_boxes(4)
     with pytest.raises(RuntimeError, match="Failed to create BVH"):
         wp.Bvh(wp.array(lo, dtype=wp.vec3), wp.array(hi, dtype=wp.vec3), constructor="median")
+
+
+REF_GOLD = os.path.join(os.path.dirname(__file__), "golden", "golden_ref_lbvh.npz")
+
+
+@pytest.mark.parametrize("name", ["cube", "ico2", "ico4", "height33", "cloth40", "dups"])
+@pytest.mark.parametrize("leaf", [1, 4])
+def test_build_equals_reference_cuda_lbvh_dump(wp, name, leaf):
+    """Directly against arrays dumped from the reference's own bvh.cu on a B200 (baseline/ref_cuda.py golden)."""
+    g = np.load(REF_GOLD)
+    m = gpu_mesh(wp, g[f"{name}_points"], g[f"{name}_indices"], leaf)
+    t = m.download_tree()
+    assert t["root"] == int(g[f"{name}_leaf{leaf}_root"])
+    assert np.array_equal(t["primitive_indices"], g[f"{name}_leaf{leaf}_primitive_indices"])
+    assert np.array_equal(t["parents"], g[f"{name}_leaf{leaf}_parents"])
+    for k in ("node_lowers", "node_uppers"):
+        for f in ("x", "y", "z", "ib"):
+            assert np.array_equal(t[k][f], g[f"{name}_leaf{leaf}_{k}"][f]), (k, f)

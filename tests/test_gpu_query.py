@@ -165,16 +165,18 @@ def test_empty_and_ragged_batches(wp, oracle_mod):
 
 
 def test_sliver_triangles_are_skipped(wp, oracle_mod):
-    """mesh.h:563: near-degenerate faces never win a closest-point query."""
-    P = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [1e-9, 0, 1], [5e-10, 1e-12, 1]], np.float32)
+    """mesh.h:563: faces with |n| / sum(|e|^2) < 1e-6 never win a closest-point query."""
+    P = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [0.5, 1e-8, 1]], np.float32)
     I = np.array([0, 1, 2, 3, 4, 5], np.int32)
     m = gpu_mesh(wp, P, I, 1)
     tree = oracle_mod.mesh_lbvh_build(P, I, 1)
-    Q = np.array([[0, 0, 1.0], [0.2, 0.2, 0.4], [0, 0, 0.9]], np.float32)
+    Q = np.array([[0.5, 0, 1.0], [0.2, 0.2, 0.9], [0.5, 0.0, 0.99]], np.float32)  # right on / next to the sliver
     want = oracle_mod.query_point_no_sign(P, I, tree, Q, 1e6)
     got = wp.mesh_query_point_no_sign(m, Q, 1e6).numpy()
-    assert (got["face"] == 0).all()
+    assert (got["face"] == 0).all() and got["result"].all()
     assert_results_equal(got, want, ("result", "face", "u", "v"))
+    r = wp.mesh_query_ray(m, np.array([[0.5, 0.0, 2.0]], np.float32), np.array([[0, 0, -1]], np.float32), 1e6)
+    assert r.result[0] == 1  # rays do not skip slivers (mesh.h:1805-1829)
 
 
 def test_large_batch_properties_c2_shape(wp, oracle_mod):

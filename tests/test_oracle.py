@@ -182,3 +182,66 @@ def test_live_reference_agreement(oracle_mod):
             s, e = int(t2["node_lowers"]["ib"][c] & 0x7FFFFFFF), int(t2["node_uppers"]["ib"][c] & 0x7FFFFFFF)
             items = t2["primitive_indices"][s:e]
             assert np.array_equal([t2["node_lowers"][f][c] for f in "xyz"], lo2[items].min(axis=0))
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's own CUDA LBVH (bvh.cu run on a B200; fixtures made by baseline/ref_cuda.py golden)
+# ------------------------------------------------------------------------------------------------
+REF_GOLD = os.path.join(os.path.dirname(__file__), "golden", "golden_ref_lbvh.npz")
+REF_CASES = ("cube", "ico2", "ico4", "height33", "cloth40", "dups")
+
+
+@pytest.fixture(scope="module")
+def ref_gold():
+    return np.load(REF_GOLD)
+
+
+@pytest.mark.parametrize("name", REF_CASES)
+@pytest.mark.parametrize("leaf", [1, 4])
+def test_lbvh_restatement_equals_reference_cuda_lbvh(oracle_mod, ref_gold, name, leaf):
+    """Sorted primitive order, parents, root and both half-node arrays (all 2N-1 nodes, muted ones
+    included) of the oracle are bit-identical to what the reference's bvh.cu produced on the GPU."""
+    g = ref_gold
+    t = oracle_mod.mesh_lbvh_build(g[f"{name}_points"], g[f"{name}_indices"], leaf)
+    assert t["root"] == int(g[f"{name}_leaf{leaf}_root"])
+    assert np.array_equal(t["primitive_indices"], g[f"{name}_leaf{leaf}_primitive_indices"])
+    assert np.array_equal(t["parents"], g[f"{name}_leaf{leaf}_parents"])
+    for k in ("node_lowers", "node_uppers"):
+        for f in ("x", "y", "z", "ib"):
+            assert np.array_equal(t[k][f], g[f"{name}_leaf{leaf}_{k}"][f]), (k, f)
+
+
+@pytest.mark.parametrize("name", ["cube", "ico2", "height33"])
+def test_queries_vs_reference_cuda_kernels(oracle_mod, ref_gold, name):
+    """Against the reference's NVRTC-compiled kernels (--fmad=true) the contract is the tolerance one:
+    result flags equal; faces equal except where both answers are the same geometric point (a shared
+    edge / vertex: an exact tie that FMA rounding breaks differently) -- counted; u, v, t within 1e-5."""
+    g = ref_gold
+    P, I = g[f"{name}_points"], g[f"{name}_indices"]
+    tri = I.reshape(-1, 3)
+    Q, S, D = g[f"{name}_queries"], g[f"{name}_ray_starts"], g[f"{name}_ray_dirs"]
+
+    def pos(face, u, v):
+        T = P[tri[face]]
+        return u[:, None] * T[:, 0] + v[:, None] * T[:, 1] + (1 - u - v)[:, None] * T[:, 2]
+
+    for leaf in (1, 4):
+        t = oracle_mod.mesh_lbvh_build(P, I, leaf)
+        a = oracle_mod.query_point(P, I, t, Q, 1e6)
+        r = {k: g[f"{name}_leaf{leaf}_point_{k}"] for k in POINT_FIELDS}
+        assert np.array_equal(a["result"], r["result"]) and np.array_equal(a["sign"], r["sign"])
+        same = a["face"] == r["face"]
+        assert np.allclose(a["u"][same], r["u"][same], rtol=0, atol=1e-5)
+        assert np.allclose(a["v"][same], r["v"][same], rtol=0, atol=1e-5)
+        ties = int((~same).sum())
+        assert ties <= len(Q) // 8, ties
+        pa, pr = pos(a["face"], a["u"], a["v"]), pos(r["face"], r["u"], r["v"])
+        assert np.abs(pa - pr).max() < 1e-5, "differing faces must still be the same closest point"
+        b = oracle_mod.query_ray(P, I, t, S, D, 1e6)
+        rr = {k: g[f"{name}_leaf{leaf}_ray_{k}"] for k in RAY_FIELDS}
+        assert np.array_equal(b["result"], rr["result"]) and np.array_equal(b["face"], rr["face"])
+        assert np.allclose(b["t"], rr["t"], rtol=1e-5, atol=0), "t within 1e-5 relative"
+        for k in ("u", "v"):  # barycentrics live in [0, 1]: 1e-5 of full scale
+            assert np.allclose(b[k], rr[k], rtol=0, atol=1e-5), k
+        assert np.allclose(b["normal"], rr["normal"], atol=1e-6)
+        assert np.array_equal(np.sign(b["sign"]), np.sign(rr["sign"]))
