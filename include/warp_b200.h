@@ -176,6 +176,12 @@ WP_B200_API int wp_b200_mesh_query_ray_host(uint64_t id, const float* starts, co
                                             float max_t, uint8_t* result, float* sign, int32_t* face, float* t,
                                             float* u, float* v, float* normal);
 
+/* thread-to-query assignment of the point queries: 0 = input order, 1 = Morton order of the batch
+ * (sorted on the device with the builder's radix sort; answers are unaffected), 2 = auto (default):
+ * Morton order for batches of >= 32768 points. */
+WP_B200_API void wp_b200_set_query_order(int mode);
+WP_B200_API int wp_b200_get_query_order(void);
+
 /* traversal counters of the NEXT query call on this thread: when `enable` is non-zero the next
  * query also counts 64-byte sibling-pair fetches and 48-byte triangle fetches (slower, used for the
  * bytes-fetched / nodes-per-second report); read them back with wp_b200_query_stats_read. */

@@ -215,3 +215,23 @@ def test_query_stats_counters(wp, oracle_mod):
     tree = oracle_mod.mesh_lbvh_build(P, I, 4)
     want = oracle_mod.query_point_no_sign(P, I, tree, Q.numpy(), 1e6, stats=True)
     assert st.tri_fetches == want["tris_tested"]  # same nodes visited in the same order
+
+
+def test_query_order_modes_agree(wp, oracle_mod):
+    """Morton-ordered thread assignment changes who answers, never the answer."""
+    P, I = mg.noisy_sphere(5, 0.05, 1)
+    m = gpu_mesh(wp, P, I, 4)
+    tree = oracle_mod.mesh_lbvh_build(P, I, 4)
+    Q = mg.box_queries(P, 50000, seed=8)
+    want = oracle_mod.query_point(P, I, tree, Q, 1e6)
+    try:
+        for mode in (wp.QUERY_ORDER_INPUT, wp.QUERY_ORDER_MORTON, wp.QUERY_ORDER_AUTO):
+            wp.set_query_order(mode)
+            assert wp.get_query_order() == mode
+            assert_results_equal(wp.mesh_query_point(m, wp.array(Q, dtype=wp.vec3), 1e6).numpy(), want, POINT_FIELDS)
+            assert_results_equal(wp.mesh_query_point(m, Q, 1e6).numpy(), want, POINT_FIELDS)
+            # coincident query points (all keys equal) and a tiny batch
+            Qs = np.repeat(Q[:3], 1000, axis=0)
+            assert_results_equal(wp.mesh_query_point_no_sign(m, Qs, 1e6).numpy(), oracle_mod.query_point_no_sign(P, I, tree, Qs, 1e6), ("result", "face", "u", "v"))
+    finally:
+        wp.set_query_order(wp.QUERY_ORDER_AUTO)

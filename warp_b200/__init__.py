@@ -28,7 +28,12 @@ from .types import (  # noqa: F401
     zeros,
 )
 from .queries import (  # noqa: F401
+    QUERY_ORDER_AUTO,
+    QUERY_ORDER_INPUT,
+    QUERY_ORDER_MORTON,
     MeshQueryPoint,
+    get_query_order,
+    set_query_order,
     MeshQueryRay,
     mesh_query_point,
     mesh_query_point_no_sign,

@@ -92,6 +92,8 @@ SIGNATURES = {
     "wp_b200_mesh_query_point_no_sign_host": (_i, [_u64, _vp, _i64, _f, _vp, _vp, _vp, _vp]),
     "wp_b200_mesh_query_point_host": (_i, [_u64, _vp, _i64, _f, _vp, _vp, _vp, _vp, _vp]),
     "wp_b200_mesh_query_ray_host": (_i, [_u64, _vp, _vp, _i64, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "wp_b200_set_query_order": (None, [_i]),
+    "wp_b200_get_query_order": (_i, []),
     "wp_b200_query_stats_enable": (None, [_i]),
     "wp_b200_query_stats_read": (None, [ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]),
     "wp_b200_mesh_rebuild_device": (_i, [_u64]),

@@ -1,11 +1,13 @@
 // C ABI of libwarp_b200.so (declared in include/warp_b200.h).
 #include "../../include/warp_b200.h"
 
+#include "order.h"
 #include "query.h"
 #include "state.h"
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -24,6 +26,10 @@ std::map<uint64_t, MeshState*> g_meshes;
 cudaStream_t g_stream[64] = {};  // current stream per device (0 = legacy default stream)
 
 thread_local bool t_stats_enabled = false;
+int g_query_order = 2;          // 0 input order, 1 Morton order, 2 auto (Morton for batches >= 32768 points)
+OrderScratch g_order[64][3];    // per device: [0] current-stream calls, [1], [2] the two host lanes
+unsigned long long* g_slot_counter[64][3] = {};  // claim counters of the persistent query kernels
+int g_point_kernel = -1;        // 1 = one thread per slot, 2 = persistent while-while (default); env WARP_B200_POINT_KERNEL
 unsigned long long* g_stats_dev = nullptr;
 
 void set_error(const char* fmt, ...)
@@ -569,6 +575,9 @@ void wp_mesh_set_velocities_device(uint64_t id, wp_array_t velocities)
 // ------------------------------------------------------------------------------------------------
 void wp_b200_query_stats_enable(int enable) { t_stats_enabled = enable != 0; }
 
+void wp_b200_set_query_order(int mode) { g_query_order = mode; }
+int wp_b200_get_query_order(void) { return g_query_order; }
+
 void wp_b200_query_stats_read(unsigned long long* pair_fetches, unsigned long long* tri_fetches)
 {
     unsigned long long h[2] = { 0, 0 };
@@ -594,14 +603,35 @@ static int zero_point_outputs(int64_t n, uint8_t* result, float* sign, int32_t* 
 }
 
 static int query_point_on(MeshState* m, const float* points, int64_t n, float max_dist, int with_sign, uint8_t* result,
-                          float* sign, int32_t* face, float* u, float* v, cudaStream_t st)
+                          float* sign, int32_t* face, float* u, float* v, cudaStream_t st, int lane = 0)
 {
     if (n <= 0)
         return 1;
     if (m->bvh.n == 0)
         return zero_point_outputs(n, result, sign, face, u, v, st);
-    const char* err = wb_query_point(make_view(m->bvh), points, n, max_dist, with_sign, result, sign, face, u, v,
-                                     stats_buffer(), st);
+    const int* perm = nullptr;
+    if ((g_query_order == 1 || (g_query_order == 2 && n >= 32768)) && n < (1ll << 30)) {
+        OrderScratch& ws = g_order[m->bvh.device][lane];
+        const char* oerr = wb_morton_order(ws, points, n, st);
+        if (oerr) {
+            set_error("Warp error: query ordering failed: %s", oerr);
+            return 0;
+        }
+        perm = ws.idx;
+    }
+    if (g_point_kernel < 0) {
+        const char* env = getenv("WARP_B200_POINT_KERNEL");
+        g_point_kernel = (env && env[0] == '1') ? 1 : 2;
+    }
+    unsigned long long* counter = nullptr;
+    if (g_point_kernel == 2) {
+        unsigned long long*& c = g_slot_counter[m->bvh.device][lane];
+        if (!c && !check(cudaMalloc(&c, sizeof(unsigned long long)), "counter alloc"))
+            return 0;
+        counter = c;
+    }
+    const char* err = wb_query_point(make_view(m->bvh), points, perm, n, max_dist, with_sign, result, sign, face, u, v,
+                                     stats_buffer(), counter, st);
     if (err) {
         set_error("Warp error: mesh point query failed: %s", err);
         return 0;
@@ -686,7 +716,7 @@ static int point_host(uint64_t id, const float* points, int64_t n, float max_dis
         ok = ok && check(cudaMemcpyAsync(b + o_pts, points + 3 * base, 12 * c, cudaMemcpyHostToDevice, l.stream), "h2d");
         ok = ok && query_point_on(m, (const float*)(b + o_pts), c, max_dist, with_sign, (uint8_t*)(b + o_res),
                                   with_sign ? (float*)(b + o_sign) : nullptr, (int32_t*)(b + o_face), (float*)(b + o_u),
-                                  (float*)(b + o_v), l.stream);
+                                  (float*)(b + o_v), l.stream, 1 + (int)(k & 1));
         ok = ok && check(cudaMemcpyAsync(result + base, b + o_res, c, cudaMemcpyDeviceToHost, l.stream), "d2h");
         if (with_sign)
             ok = ok && check(cudaMemcpyAsync(sign + base, b + o_sign, 4 * c, cudaMemcpyDeviceToHost, l.stream), "d2h");

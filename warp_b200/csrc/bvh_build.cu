@@ -752,3 +752,64 @@ const char* wb_export_reference_layout(BvhState& s, cudaStream_t stream)
     WB_CUDA_TRY(cudaGetLastError());
     return nullptr;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Morton ordering of query points (order.h)
+// ------------------------------------------------------------------------------------------------
+#include "order.h"
+
+void wb_order_free(OrderScratch& ws)
+{
+    void* ptrs[] = { ws.keys, ws.keys_alt, ws.idx, ws.idx_alt, ws.ghist, ws.tile_status, ws.tickets, ws.partials, ws.hdr };
+    for (void* p : ptrs)
+        if (p)
+            cudaFree(p);
+    ws = OrderScratch();
+}
+
+const char* wb_morton_order(OrderScratch& ws, const float* pts, long long n, cudaStream_t stream)
+{
+    if (n <= 0)
+        return nullptr;
+    if (n >= (1ll << 30))
+        return "query batches are ordered in chunks of fewer than 2^30 points";
+    if (n > ws.capacity) {
+        wb_order_free(ws);
+        const size_t cap = (size_t)n;
+        const size_t tiles = (size_t)wb_div_up(n, RS_TILE);
+        WB_CUDA_TRY(cudaMalloc(&ws.keys, 4 * cap));
+        WB_CUDA_TRY(cudaMalloc(&ws.keys_alt, 4 * cap));
+        WB_CUDA_TRY(cudaMalloc(&ws.idx, 4 * cap));
+        WB_CUDA_TRY(cudaMalloc(&ws.idx_alt, 4 * cap));
+        WB_CUDA_TRY(cudaMalloc(&ws.ghist, 4 * 4 * 256));
+        WB_CUDA_TRY(cudaMalloc(&ws.tile_status, 4 * 256 * 4 * tiles));
+        WB_CUDA_TRY(cudaMalloc(&ws.tickets, 4 * 8));
+        WB_CUDA_TRY(cudaMemset(ws.tickets, 0, 4 * 8));
+        WB_CUDA_TRY(cudaMalloc(&ws.partials, 4 * 6 * 1024));
+        WB_CUDA_TRY(cudaMalloc(&ws.hdr, sizeof(TreeHeader)));
+        ws.capacity = n;
+    }
+    const int ni = (int)n;
+    const int tiles = wb_div_up(n, RS_TILE);
+    const int blocks = min(1024, max(1, wb_div_up(n, BT)));
+    const BoxSource src { pts, pts };  // a point is its own (degenerate) box; its centroid is the point itself
+    k_scene_bounds<<<blocks, BT, 0, stream>>>(src, ni, ws.partials, ws.tickets, ws.hdr, ws.ghist);
+    WB_CUDA_TRY(cudaMemsetAsync(ws.tile_status, 0, sizeof(uint32_t) * 256 * 4 * (size_t)tiles, stream));
+    k_morton_hist<<<blocks, BT, 0, stream>>>(src, ni, ws.hdr, ws.keys, ws.ghist);
+    for (int pass = 0; pass < 4; ++pass) {
+        volatile uint32_t* status = ws.tile_status + (size_t)pass * 256 * tiles;
+        const bool fwd = (pass % 2) == 0;
+        const uint32_t* kin = fwd ? ws.keys : ws.keys_alt;
+        const int* vin = fwd ? ws.idx : ws.idx_alt;
+        uint32_t* kout = fwd ? ws.keys_alt : ws.keys;
+        int* vout = fwd ? ws.idx_alt : ws.idx;
+        if (pass == 0)
+            k_onesweep_pass<true><<<tiles, RS_THREADS, 0, stream>>>(kin, nullptr, kout, vout, ni, 8 * pass,
+                                                                   ws.ghist + 256 * pass, status, ws.tickets + 1 + pass);
+        else
+            k_onesweep_pass<false><<<tiles, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, ni, 8 * pass,
+                                                                    ws.ghist + 256 * pass, status, ws.tickets + 1 + pass);
+    }
+    WB_CUDA_TRY(cudaGetLastError());
+    return nullptr;
+}

@@ -1,0 +1,23 @@
+// Morton ordering of a batch of query points (bvh_build.cu): reuses the builder's scene-bounds,
+// key and onesweep kernels to produce a permutation that makes neighbouring threads traverse
+// neighbouring parts of the tree.  The permutation only changes WHICH thread answers a query, never
+// the answer.
+#pragma once
+#include "common.cuh"
+
+struct OrderScratch {
+    uint32_t* keys = nullptr;
+    uint32_t* keys_alt = nullptr;
+    int* idx = nullptr;
+    int* idx_alt = nullptr;
+    uint32_t* ghist = nullptr;
+    uint32_t* tile_status = nullptr;
+    unsigned* tickets = nullptr;
+    float* partials = nullptr;
+    TreeHeader* hdr = nullptr;
+    long long capacity = 0;
+};
+
+// after the call (stream-ordered) ws.idx[0..n) holds the query indices in Morton order
+const char* wb_morton_order(OrderScratch& ws, const float* pts, long long n, cudaStream_t stream);
+void wb_order_free(OrderScratch& ws);

@@ -170,3 +170,18 @@ class query_stats:
         self.pair_fetches, self.tri_fetches = a.value, b.value
         _lib.core().wp_b200_query_stats_enable(0)
         return False
+
+
+QUERY_ORDER_INPUT, QUERY_ORDER_MORTON, QUERY_ORDER_AUTO = 0, 1, 2
+
+
+def set_query_order(mode: int) -> None:
+    """How threads are assigned to the points of a batch: ``QUERY_ORDER_INPUT`` (thread i answers
+    point i), ``QUERY_ORDER_MORTON`` (the batch is Morton-sorted on the device first so a warp walks
+    one neighbourhood of the tree), ``QUERY_ORDER_AUTO`` (default: Morton for >= 32768 points).
+    Answers are identical in every mode."""
+    _lib.core().wp_b200_set_query_order(int(mode))
+
+
+def get_query_order() -> int:
+    return int(_lib.core().wp_b200_get_query_order())
