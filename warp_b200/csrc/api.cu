@@ -28,8 +28,6 @@ cudaStream_t g_stream[64] = {};  // current stream per device (0 = legacy defaul
 thread_local bool t_stats_enabled = false;
 int g_query_order = 2;          // 0 input order, 1 Morton order, 2 auto (Morton for batches >= 32768 points)
 OrderScratch g_order[64][3];    // per device: [0] current-stream calls, [1], [2] the two host lanes
-unsigned long long* g_slot_counter[64][3] = {};  // claim counters of the persistent query kernels
-int g_point_kernel = -1;        // 1 = one thread per slot, 2 = persistent while-while (default); env WARP_B200_POINT_KERNEL
 unsigned long long* g_stats_dev = nullptr;
 
 void set_error(const char* fmt, ...)
@@ -374,13 +372,13 @@ uint64_t wp_bvh_create_device(void* context, wp_vec3* lowers, wp_vec3* uppers, i
     BvhState* s = new BvhState();
     s->n = num_items, s->leaf_size = leaf_size, s->constructor_type = constructor_type, s->device = dev;
     s->item_lowers = (const float*)lowers, s->item_uppers = (const float*)uppers, s->groups = groups;
-    const char* err = num_items > 0 ? wb_alloc_tree(*s) : nullptr;
+    const char* err = num_items > 0 ? wb_alloc_tree(*s, current_stream(dev)) : nullptr;
     if (!err)
         err = wb_build(*s, current_stream(dev));
     if (err || !check(cudaMalloc(&s->dev_desc, sizeof(wp_b200_bvh_desc)), "descriptor alloc") || !upload_desc(nullptr, s)) {
         if (err)
             set_error("Warp error: BVH build failed: %s", err);
-        wb_free_tree(*s);
+        wb_free_tree(*s, current_stream(dev));
         delete s;
         return 0;
     }
@@ -404,7 +402,7 @@ void wp_bvh_destroy_device(uint64_t id)
     DeviceGuard g(s->device);
     cudaStreamSynchronize(current_stream(s->device));
     cudaFree(s->dev_desc);
-    wb_free_tree(*s);
+    wb_free_tree(*s, current_stream(s->device));
     delete s;
 }
 
@@ -462,7 +460,7 @@ uint64_t wp_mesh_create_device(void* context, wp_array_t points, wp_array_t velo
     s.n = num_tris, s.leaf_size = bvh_leaf_size, s.constructor_type = constructor_type, s.device = dev;
     s.is_mesh = true;
     s.points = (const float*)points.data, s.indices = (const int*)tris.data, s.num_points = num_points;
-    const char* err = num_tris > 0 ? wb_alloc_tree(s) : nullptr;
+    const char* err = num_tris > 0 ? wb_alloc_tree(s, current_stream(dev)) : nullptr;
     if (!err)
         err = wb_build(s, current_stream(dev));
     if (err || !check(cudaMalloc(&m->dev_desc, sizeof(wp_b200_mesh_desc)), "descriptor alloc") || !upload_desc(m, nullptr)) {
@@ -470,7 +468,7 @@ uint64_t wp_mesh_create_device(void* context, wp_array_t points, wp_array_t velo
             set_error("Warp error: mesh build failed: %s", err);
         if (m->dev_desc)
             cudaFree(m->dev_desc);
-        wb_free_tree(s);
+        wb_free_tree(s, current_stream(dev));
         delete m;
         return 0;
     }
@@ -494,7 +492,7 @@ void wp_mesh_destroy_device(uint64_t id)
     DeviceGuard g(m->bvh.device);
     cudaStreamSynchronize(current_stream(m->bvh.device));
     cudaFree(m->dev_desc);
-    wb_free_tree(m->bvh);
+    wb_free_tree(m->bvh, current_stream(m->bvh.device));
     delete m;
 }
 
@@ -619,19 +617,8 @@ static int query_point_on(MeshState* m, const float* points, int64_t n, float ma
         }
         perm = ws.idx;
     }
-    if (g_point_kernel < 0) {
-        const char* env = getenv("WARP_B200_POINT_KERNEL");
-        g_point_kernel = (env && env[0] == '1') ? 1 : 2;
-    }
-    unsigned long long* counter = nullptr;
-    if (g_point_kernel == 2) {
-        unsigned long long*& c = g_slot_counter[m->bvh.device][lane];
-        if (!c && !check(cudaMalloc(&c, sizeof(unsigned long long)), "counter alloc"))
-            return 0;
-        counter = c;
-    }
     const char* err = wb_query_point(make_view(m->bvh), points, perm, n, max_dist, with_sign, result, sign, face, u, v,
-                                     stats_buffer(), counter, st);
+                                     stats_buffer(), st);
     if (err) {
         set_error("Warp error: mesh point query failed: %s", err);
         return 0;

@@ -151,6 +151,23 @@ __device__ __forceinline__ void hist_add(uint32_t* h, uint32_t d, bool valid)
         atomicAdd(&h[d], (uint32_t)__popc(peers));
 }
 
+// histogram increment for digits that neighbouring items mostly share: if every valid lane of the
+// warp holds the same digit, one lane adds the population count; otherwise fall back to per-lane atomics
+__device__ __forceinline__ void hist_add_coherent(uint32_t* h, uint32_t d, bool valid)
+{
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    if (vmask == 0u)
+        return;
+    const int leader = __ffs(vmask) - 1;
+    const uint32_t d0 = __shfl_sync(0xffffffffu, d, leader);
+    if (__all_sync(0xffffffffu, !valid || d == d0)) {
+        if ((int)(threadIdx.x & 31) == leader)
+            atomicAdd(&h[d0], (uint32_t)__popc(vmask));
+    } else if (valid) {
+        atomicAdd(&h[d], 1u);
+    }
+}
+
 template <class Src>
 __global__ void __launch_bounds__(BT)
 k_morton_hist(Src src, int n, const TreeHeader* __restrict__ hdr, uint32_t* __restrict__ keys,
@@ -177,10 +194,13 @@ k_morton_hist(Src src, int n, const TreeHeader* __restrict__ hdr, uint32_t* __re
             code = morton30((cx - glx) * ivx, (cy - gly) * ivy, (cz - glz) * ivz);
             keys[i] = code;
         }
-        hist_add(h, code & 255u, valid);
-        hist_add(h + 256, (code >> 8) & 255u, valid);
-        hist_add(h + 512, (code >> 16) & 255u, valid);
-        hist_add(h + 768, (code >> 24) & 255u, valid);
+        // low digit: essentially random across a warp -> plain shared atomics; the three high digits are
+        // usually identical across a warp of neighbouring items -> one add per warp when they are
+        if (valid)
+            atomicAdd(&h[code & 255u], 1u);
+        hist_add_coherent(h + 256, (code >> 8) & 255u, valid);
+        hist_add_coherent(h + 512, (code >> 16) & 255u, valid);
+        hist_add_coherent(h + 768, (code >> 24) & 255u, valid);
     }
     __syncthreads();
     for (int k = threadIdx.x; k < 4 * 256; k += BT)
@@ -194,22 +214,26 @@ k_morton_hist(Src src, int n, const TreeHeader* __restrict__ hdr, uint32_t* __re
 // ---------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per tile
+constexpr int RS_ITEMS_LARGE = 16;  // 4096-key tiles: fewer look-back words for big inputs
+constexpr int RS_ITEMS_SMALL = 8;   // 2048-key tiles: more resident warps while the input is small enough to be latency bound
+constexpr long long RS_SMALL_LIMIT = 1ll << 24;
+__host__ __device__ inline int rs_items_for(long long n) { return n < RS_SMALL_LIMIT ? RS_ITEMS_SMALL : RS_ITEMS_LARGE; }
+__host__ __device__ inline int rs_tile_for(long long n) { return RS_THREADS * rs_items_for(n); }
 constexpr uint32_t RS_FLAG_AGG = 1u << 30;
 constexpr uint32_t RS_FLAG_INC = 2u << 30;
 constexpr uint32_t RS_VAL_MASK = (1u << 30) - 1;
 
-template <bool IMPLICIT_VALS>
+template <bool IMPLICIT_VALS, int ITEMS>
 __global__ void __launch_bounds__(RS_THREADS)
 k_onesweep_pass(const uint32_t* __restrict__ keys_in, const int* __restrict__ vals_in,
                 uint32_t* __restrict__ keys_out, int* __restrict__ vals_out, int n, int shift,
                 const uint32_t* __restrict__ ghist_pass, volatile uint32_t* __restrict__ tile_status,
                 unsigned* __restrict__ tile_ticket)
 {
+    constexpr int TILE = RS_THREADS * ITEMS;
     __shared__ uint32_t warp_hist[RS_WARPS][257];  // bin 256 collects out-of-range lanes
-    __shared__ uint32_t s_keys[RS_TILE];
-    __shared__ int s_vals[RS_TILE];
+    __shared__ uint32_t s_keys[TILE];
+    __shared__ int s_vals[TILE];
     __shared__ int s_delta[256];       // global position = s_delta[digit] + position in tile
     __shared__ uint32_t s_scan[RS_WARPS];
     __shared__ uint32_t s_scan2[RS_WARPS];
@@ -222,16 +246,16 @@ k_onesweep_pass(const uint32_t* __restrict__ keys_in, const int* __restrict__ va
         (&warp_hist[0][0])[k] = 0;
     __syncthreads();
     const int tile = s_tile;
-    const int tile_base = tile * RS_TILE;
-    const int tile_count = min(RS_TILE, n - tile_base);
+    const int tile_base = tile * TILE;
+    const int tile_count = min(TILE, n - tile_base);
 
     // -- load (warp-striped: item k of lane l sits at warp_base + 32k + l, so rank order = memory order)
-    uint32_t key[RS_ITEMS];
-    int val[RS_ITEMS];
-    uint32_t rank[RS_ITEMS];
-    const int warp_base = tile_base + warp * (32 * RS_ITEMS);
+    uint32_t key[ITEMS];
+    int val[ITEMS];
+    uint32_t rank[ITEMS];
+    const int warp_base = tile_base + warp * (32 * ITEMS);
 #pragma unroll
-    for (int k = 0; k < RS_ITEMS; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
         const int idx = warp_base + 32 * k + lane;
         const bool valid = idx < n;
         key[k] = valid ? keys_in[idx] : 0xffffffffu;
@@ -242,7 +266,7 @@ k_onesweep_pass(const uint32_t* __restrict__ keys_in, const int* __restrict__ va
     uint32_t* wh = warp_hist[warp];
     const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
-    for (int k = 0; k < RS_ITEMS; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
         const int idx = warp_base + 32 * k + lane;
         const uint32_t d = (idx < n) ? ((key[k] >> shift) & 255u) : 256u;
         const uint32_t peers = __match_any_sync(0xffffffffu, d);
@@ -313,7 +337,7 @@ k_onesweep_pass(const uint32_t* __restrict__ keys_in, const int* __restrict__ va
 
     // -- reorder through shared memory
 #pragma unroll
-    for (int k = 0; k < RS_ITEMS; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
         const int idx = warp_base + 32 * k + lane;
         if (idx < n) {
             const uint32_t d = (key[k] >> shift) & 255u;
@@ -330,6 +354,36 @@ k_onesweep_pass(const uint32_t* __restrict__ keys_in, const int* __restrict__ va
         const int g = s_delta[(kk >> shift) & 255u] + j;
         keys_out[g] = kk;
         vals_out[g] = s_vals[j];
+    }
+}
+
+// four 8-bit passes over (keys, vals) <-> (keys_alt, vals_alt); an even pass count ends in (keys, vals).
+// Pass 0 reads `keys` only and uses the element index as the value.
+static void onesweep_sort(uint32_t* keys, uint32_t* keys_alt, int* vals, int* vals_alt, int n, const uint32_t* ghist,
+                          uint32_t* tile_status, unsigned* tickets, cudaStream_t stream)
+{
+    const int items = rs_items_for(n);
+    const int tiles = wb_div_up(n, RS_THREADS * items);
+    for (int pass = 0; pass < 4; ++pass) {
+        volatile uint32_t* status = tile_status + (size_t)pass * 256 * tiles;
+        const bool fwd = (pass % 2) == 0;
+        const uint32_t* kin = fwd ? keys : keys_alt;
+        const int* vin = fwd ? vals : vals_alt;
+        uint32_t* kout = fwd ? keys_alt : keys;
+        int* vout = fwd ? vals_alt : vals;
+        const uint32_t* gh = ghist + 256 * pass;
+        unsigned* ticket = tickets + 1 + pass;
+        if (items == RS_ITEMS_SMALL) {
+            if (pass == 0)
+                k_onesweep_pass<true, RS_ITEMS_SMALL><<<tiles, RS_THREADS, 0, stream>>>(kin, nullptr, kout, vout, n, 8 * pass, gh, status, ticket);
+            else
+                k_onesweep_pass<false, RS_ITEMS_SMALL><<<tiles, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, n, 8 * pass, gh, status, ticket);
+        } else {
+            if (pass == 0)
+                k_onesweep_pass<true, RS_ITEMS_LARGE><<<tiles, RS_THREADS, 0, stream>>>(kin, nullptr, kout, vout, n, 8 * pass, gh, status, ticket);
+            else
+                k_onesweep_pass<false, RS_ITEMS_LARGE><<<tiles, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, n, 8 * pass, gh, status, ticket);
+        }
     }
 }
 
@@ -432,12 +486,10 @@ k_hierarchy(Src src, int n, int leaf_size, const uint32_t* __restrict__ keys, co
         if (node >= n)
             parent_int[node - n] = parent;
 
-        __threadfence();
         const unsigned h = min(height, WB_HEIGHT_CAP);
-        const unsigned old = atomicAdd(&counters[s], 1u | (h << 8));
+        const unsigned old = wb_arrive(&counters[s], 1u | (h << 8));
         if ((old & 0xffu) == 0u)
             return;  // first to arrive: the sibling's thread carries on
-        __threadfence();
 
         // second arrival: fetch the sibling record (written by another SM: bypass L1)
         const float4 s0 = __ldcg(reinterpret_cast<const float4*>(sibling));
@@ -655,20 +707,7 @@ template <class Src> const char* build_impl(BvhState& s, Src src, cudaStream_t s
     } else {
         // K3 x4, ping-pong (keys, prim) <-> (keys_alt, prim_alt); an even pass count ends in (keys, prim),
         // so the buffers the descriptor points at never change (rebuild stays capture safe)
-        for (int pass = 0; pass < 4; ++pass) {
-            volatile uint32_t* status = s.tile_status + (size_t)pass * 256 * s.num_tiles;
-            const bool fwd = (pass % 2) == 0;
-            const uint32_t* kin = fwd ? s.keys : s.keys_alt;
-            const int* vin = fwd ? s.prim : s.prim_alt;
-            uint32_t* kout = fwd ? s.keys_alt : s.keys;
-            int* vout = fwd ? s.prim_alt : s.prim;
-            if (pass == 0)
-                k_onesweep_pass<true><<<s.num_tiles, RS_THREADS, 0, stream>>>(
-                    kin, nullptr, kout, vout, n, 8 * pass, s.ghist + 256 * pass, status, s.tickets + 1 + pass);
-            else
-                k_onesweep_pass<false><<<s.num_tiles, RS_THREADS, 0, stream>>>(
-                    kin, vin, kout, vout, n, 8 * pass, s.ghist + 256 * pass, status, s.tickets + 1 + pass);
-        }
+        onesweep_sort(s.keys, s.keys_alt, s.prim, s.prim_alt, n, s.ghist, s.tile_status, s.tickets, stream);
     }
 
     // K4 hierarchy
@@ -684,37 +723,68 @@ template <class Src> const char* build_impl(BvhState& s, Src src, cudaStream_t s
 
 }  // namespace
 
-const char* wb_alloc_tree(BvhState& s)
+// one stream-ordered arena per tree: a single cudaMallocAsync from the device's default pool (kept
+// warm by an unlimited release threshold), carved into 256-byte aligned sub-buffers
+static bool pool_ready(int device)
+{
+    static bool done[64] = {};
+    if (device < 0 || device >= 64)
+        return false;
+    if (!done[device]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess)
+            return false;
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        done[device] = true;
+    }
+    return true;
+}
+
+const char* wb_alloc_tree(BvhState& s, cudaStream_t stream)
 {
     const size_t n = (size_t)s.n;
     const size_t ni = n > 1 ? n - 1 : 1;
-    s.num_tiles = wb_div_up((long long)n, RS_TILE);
-    s.bounds_blocks = min(1024, max(1, wb_div_up((long long)n, BT)));
-    WB_CUDA_TRY(cudaMalloc(&s.keys, sizeof(uint32_t) * n));
-    WB_CUDA_TRY(cudaMalloc(&s.keys_alt, sizeof(uint32_t) * n));
-    WB_CUDA_TRY(cudaMalloc(&s.prim, sizeof(int) * n));
-    WB_CUDA_TRY(cudaMalloc(&s.prim_alt, sizeof(int) * n));
-    WB_CUDA_TRY(cudaMalloc(&s.pairs, sizeof(NodeRec) * 2 * ni));
-    WB_CUDA_TRY(cudaMalloc(&s.parent_int, sizeof(int) * ni));
-    WB_CUDA_TRY(cudaMalloc(&s.pos_parent, sizeof(int) * n));
-    WB_CUDA_TRY(cudaMalloc(&s.counters, sizeof(unsigned) * ni));
-    if (s.is_mesh)
-        WB_CUDA_TRY(cudaMalloc(&s.tris, sizeof(float4) * 3 * n));
-    WB_CUDA_TRY(cudaMalloc(&s.header, sizeof(TreeHeader)));
-    WB_CUDA_TRY(cudaMemset(s.header, 0, sizeof(TreeHeader)));
-    WB_CUDA_TRY(cudaMalloc(&s.ghist, sizeof(uint32_t) * 4 * 256));
-    WB_CUDA_TRY(cudaMalloc(&s.tile_status, sizeof(uint32_t) * 256 * 4 * (size_t)s.num_tiles));
-    WB_CUDA_TRY(cudaMalloc(&s.tickets, sizeof(unsigned) * 8));
-    WB_CUDA_TRY(cudaMemset(s.tickets, 0, sizeof(unsigned) * 8));
-    WB_CUDA_TRY(cudaMalloc(&s.partials, sizeof(float) * 6 * (size_t)s.bounds_blocks));
+    s.num_tiles = wb_div_up((long long)n, rs_tile_for((long long)n));
+    s.bounds_blocks = min(4096, max(1, wb_div_up((long long)n, BT)));
+    size_t off = 0;
+    auto take = [&off](size_t bytes) {
+        const size_t at = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return at;
+    };
+    const size_t o_header = take(sizeof(TreeHeader)), o_tickets = take(sizeof(unsigned) * 8),
+                 o_ghist = take(sizeof(uint32_t) * 4 * 256), o_partials = take(sizeof(float) * 6 * (size_t)s.bounds_blocks),
+                 o_keys = take(4 * n), o_keys_alt = take(4 * n), o_prim = take(4 * n), o_prim_alt = take(4 * n),
+                 o_pairs = take(sizeof(NodeRec) * 2 * ni), o_parent = take(4 * ni), o_pos = take(4 * n),
+                 o_counters = take(4 * ni), o_tris = take(s.is_mesh ? sizeof(float4) * 3 * n : 0),
+                 o_status = take(sizeof(uint32_t) * 256 * 4 * (size_t)s.num_tiles);
+    s.arena_bytes = off;
+    s.arena_async = pool_ready(s.device);
+    if (s.arena_async)
+        WB_CUDA_TRY(cudaMallocAsync(&s.arena, off, stream));
+    else
+        WB_CUDA_TRY(cudaMalloc(&s.arena, off));
+    char* b = (char*)s.arena;
+    s.header = (TreeHeader*)(b + o_header), s.tickets = (unsigned*)(b + o_tickets), s.ghist = (uint32_t*)(b + o_ghist);
+    s.partials = (float*)(b + o_partials), s.keys = (uint32_t*)(b + o_keys), s.keys_alt = (uint32_t*)(b + o_keys_alt);
+    s.prim = (int*)(b + o_prim), s.prim_alt = (int*)(b + o_prim_alt), s.pairs = (NodeRec*)(b + o_pairs);
+    s.parent_int = (int*)(b + o_parent), s.pos_parent = (int*)(b + o_pos), s.counters = (unsigned*)(b + o_counters);
+    s.tris = s.is_mesh ? (float4*)(b + o_tris) : nullptr, s.tile_status = (uint32_t*)(b + o_status);
+    // header, tickets, histograms start from zero (one small memset: they are adjacent)
+    WB_CUDA_TRY(cudaMemsetAsync(s.arena, 0, o_partials, stream));
     return nullptr;
 }
 
-void wb_free_tree(BvhState& s)
+void wb_free_tree(BvhState& s, cudaStream_t stream)
 {
-    void* ptrs[] = { s.keys, s.keys_alt, s.prim, s.prim_alt, s.pairs, s.parent_int, s.pos_parent, s.counters,
-                     s.tris, s.header, s.ghist, s.tile_status, s.tickets, s.partials, s.cub_temp,
-                     s.ref_lowers, s.ref_uppers, s.ref_parents, s.ref_root, s.ref_counts };
+    if (s.arena) {
+        if (s.arena_async)
+            cudaFreeAsync(s.arena, stream);
+        else
+            cudaFree(s.arena);
+    }
+    void* ptrs[] = { s.cub_temp, s.ref_lowers, s.ref_uppers, s.ref_parents, s.ref_root, s.ref_counts };
     for (void* p : ptrs)
         if (p)
             cudaFree(p);
@@ -776,7 +846,7 @@ const char* wb_morton_order(OrderScratch& ws, const float* pts, long long n, cud
     if (n > ws.capacity) {
         wb_order_free(ws);
         const size_t cap = (size_t)n;
-        const size_t tiles = (size_t)wb_div_up(n, RS_TILE);
+        const size_t tiles = (size_t)wb_div_up(n, RS_THREADS * RS_ITEMS_SMALL);
         WB_CUDA_TRY(cudaMalloc(&ws.keys, 4 * cap));
         WB_CUDA_TRY(cudaMalloc(&ws.keys_alt, 4 * cap));
         WB_CUDA_TRY(cudaMalloc(&ws.idx, 4 * cap));
@@ -785,31 +855,18 @@ const char* wb_morton_order(OrderScratch& ws, const float* pts, long long n, cud
         WB_CUDA_TRY(cudaMalloc(&ws.tile_status, 4 * 256 * 4 * tiles));
         WB_CUDA_TRY(cudaMalloc(&ws.tickets, 4 * 8));
         WB_CUDA_TRY(cudaMemset(ws.tickets, 0, 4 * 8));
-        WB_CUDA_TRY(cudaMalloc(&ws.partials, 4 * 6 * 1024));
+        WB_CUDA_TRY(cudaMalloc(&ws.partials, 4 * 6 * 4096));
         WB_CUDA_TRY(cudaMalloc(&ws.hdr, sizeof(TreeHeader)));
         ws.capacity = n;
     }
     const int ni = (int)n;
-    const int tiles = wb_div_up(n, RS_TILE);
-    const int blocks = min(1024, max(1, wb_div_up(n, BT)));
+    const int tiles = wb_div_up(n, rs_tile_for(n));
+    const int blocks = min(4096, max(1, wb_div_up(n, BT)));
     const BoxSource src { pts, pts };  // a point is its own (degenerate) box; its centroid is the point itself
     k_scene_bounds<<<blocks, BT, 0, stream>>>(src, ni, ws.partials, ws.tickets, ws.hdr, ws.ghist);
     WB_CUDA_TRY(cudaMemsetAsync(ws.tile_status, 0, sizeof(uint32_t) * 256 * 4 * (size_t)tiles, stream));
     k_morton_hist<<<blocks, BT, 0, stream>>>(src, ni, ws.hdr, ws.keys, ws.ghist);
-    for (int pass = 0; pass < 4; ++pass) {
-        volatile uint32_t* status = ws.tile_status + (size_t)pass * 256 * tiles;
-        const bool fwd = (pass % 2) == 0;
-        const uint32_t* kin = fwd ? ws.keys : ws.keys_alt;
-        const int* vin = fwd ? ws.idx : ws.idx_alt;
-        uint32_t* kout = fwd ? ws.keys_alt : ws.keys;
-        int* vout = fwd ? ws.idx_alt : ws.idx;
-        if (pass == 0)
-            k_onesweep_pass<true><<<tiles, RS_THREADS, 0, stream>>>(kin, nullptr, kout, vout, ni, 8 * pass,
-                                                                   ws.ghist + 256 * pass, status, ws.tickets + 1 + pass);
-        else
-            k_onesweep_pass<false><<<tiles, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, ni, 8 * pass,
-                                                                    ws.ghist + 256 * pass, status, ws.tickets + 1 + pass);
-    }
+    onesweep_sort(ws.keys, ws.keys_alt, ws.idx, ws.idx_alt, ni, ws.ghist, ws.tile_status, ws.tickets, stream);
     WB_CUDA_TRY(cudaGetLastError());
     return nullptr;
 }

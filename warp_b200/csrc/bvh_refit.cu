@@ -74,11 +74,9 @@ k_refit(Src src, int n, const int* __restrict__ prim, const int* __restrict__ po
         NodeRec* mine = pairs + 2 * (size_t)s + side;
         mine->lx = lo.x, mine->ly = lo.y, mine->lz = lo.z;
         mine->hx = hi.x, mine->hy = hi.y, mine->hz = hi.z;
-        __threadfence();
-        const unsigned old = atomicAdd(&counters[s], 1u);
+        const unsigned old = wb_arrive(&counters[s], 1u);
         if ((old & 1u) == 0u)
             return;  // first arrival
-        __threadfence();
         const float4* sib = reinterpret_cast<const float4*>(pairs + 2 * (size_t)s + (1 - side));
         const float4 s0 = __ldcg(sib), s1 = __ldcg(sib + 1);
         lo = wb_min3(lo, make_float3(s0.x, s0.y, s0.z));

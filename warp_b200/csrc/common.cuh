@@ -85,6 +85,16 @@ __device__ __forceinline__ float3 wb_cross(float3 a, float3 b)
 }
 __device__ __forceinline__ float wb_get(float3 a, int k) { return k == 0 ? a.x : (k == 1 ? a.y : a.z); }
 
+// arrival counter update with release (our record stores are visible before the count) and acquire (the
+// sibling's record is visible after it) semantics in ONE instruction: MEMBAR.ALL.GPU + ATOMG + CCTL.IVALL,
+// versus MEMBAR.SC + CCTL.IVALL twice for __threadfence(); atomicAdd(); __threadfence().
+__device__ __forceinline__ unsigned wb_arrive(unsigned* counter, unsigned add)
+{
+    unsigned old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(counter), "r"(add) : "memory");
+    return old;
+}
+
 // item-bounds sources: a triangle mesh (bounds computed on the fly from vertices, replacing the
 // lowers/uppers round trip of mesh.cu:16-36) or caller-provided boxes (wp.Bvh)
 struct MeshSource {

@@ -13,6 +13,8 @@
 #include "state.h"
 #include "query.h"
 
+#include <cstdlib>
+
 namespace {
 
 constexpr int QT = 128;  // threads per block
@@ -425,163 +427,6 @@ k_query_point(TreeView tv, const float* __restrict__ pts, const int* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
-// closest point, persistent "while-while" form.  Same per-query visit order and arithmetic as
-// closest_point() above; what changes is how a warp spends its issue slots:
-//   * lanes first descend until each holds a leaf to test (or has finished), THEN all lanes with a
-//     leaf run the triangle loop together -- node steps and triangle tests no longer serialise;
-//   * a lane whose query is finished takes the next unclaimed query of the batch from a global
-//     counter instead of idling until the slowest lane of its warp is done.
-// ------------------------------------------------------------------------------------------------
-template <bool SIGN, bool COUNT>
-__global__ void __launch_bounds__(QT)
-k_query_point_ww(TreeView tv, const float* __restrict__ pts, const int* __restrict__ perm, long long nq, float max_dist,
-                 uint8_t* __restrict__ result, float* __restrict__ sign, int* __restrict__ face, float* __restrict__ u,
-                 float* __restrict__ v, unsigned long long* __restrict__ next_slot,
-                 unsigned long long* __restrict__ stats)
-{
-    const TreeHeader h = *tv.header;
-    const unsigned lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
-    const float max_sq = max_dist * max_dist;
-    const float3 root_lo = make_float3(h.lx, h.ly, h.lz), root_hi = make_float3(h.hx, h.hy, h.hz);
-    Entry root;
-    if (h.root_ref & WB_LEAF)
-        root.a = WB_LEAF | 0u, root.b = h.root_count;
-    else
-        root.a = (h.root_ref & WB_IDX_MASK) - (uint32_t)tv.n, root.b = 0;
-
-    Counters cnt;
-    Entry stack[WB_QUERY_STACK];
-    float stack_d[WB_QUERY_STACK];
-    int top = 0;
-    bool active = false, have = false, exhausted = false;
-    long long qi = 0;
-    float3 p = make_float3(0.f, 0.f, 0.f);
-    float best = 0.f, best_v = 0.f, best_w = 0.f, cur_d = 0.f;
-    int best_face = 0;
-    Entry cur = root;
-
-    for (;;) {
-        // ---- idle lanes claim the next queries of the batch
-        const unsigned idle = __ballot_sync(0xffffffffu, !active);
-        if (idle && !exhausted) {
-            const int n_idle = __popc(idle);
-            const int leader = __ffs(idle) - 1;
-            unsigned long long base = 0;
-            if ((int)lane == leader)
-                base = atomicAdd(next_slot, (unsigned long long)n_idle);
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if ((long long)(base + n_idle) >= nq)
-                exhausted = true;
-            if (!active) {
-                const long long slot = (long long)base + __popc(idle & lt_mask);
-                if (slot < nq) {
-                    qi = perm ? (long long)__ldg(perm + slot) : slot;
-                    p = make_float3(__ldg(pts + 3 * qi), __ldg(pts + 3 * qi + 1), __ldg(pts + 3 * qi + 2));
-                    best = max_sq, best_face = 0, best_v = 0.f, best_w = 0.f;
-                    top = 0;
-                    cur = root;
-                    cur_d = dist_aabb_sq(p, root_lo, root_hi);
-                    have = true;
-                    active = true;
-                }
-            }
-        }
-        if (__ballot_sync(0xffffffffu, active) == 0u)
-            break;
-
-        // ---- phase 1: descend until this lane holds a leaf that survives the cull, or runs dry
-        bool leaf_ready = false;
-        if (active) {
-            for (;;) {
-                if (!have) {
-                    if (top == 0)
-                        break;
-                    --top;
-                    cur = stack[top];
-                    cur_d = stack_d[top];
-                }
-                have = false;
-                if (cur_d > best)
-                    continue;
-                if (cur.a & WB_LEAF) {
-                    leaf_ready = true;
-                    break;
-                }
-                const Pair pr = load_pair(tv.pairs, cur.a, tv.n);
-                if (COUNT)
-                    cnt.pairs++;
-                const float dl = dist_aabb_sq(p, pr.llo, pr.lhi), dr = dist_aabb_sq(p, pr.rlo, pr.rhi);
-                Entry far_e, near_e;
-                float far_d, near_d;
-                if (dl < dr)
-                    far_e = pr.right, far_d = dr, near_e = pr.left, near_d = dl;
-                else
-                    far_e = pr.left, far_d = dl, near_e = pr.right, near_d = dr;
-                if (far_d < best) {
-                    stack[top] = far_e;
-                    stack_d[top] = far_d;
-                    ++top;
-                }
-                if (near_d < best) {
-                    cur = near_e;
-                    cur_d = near_d;
-                    have = true;
-                }
-            }
-        }
-
-        // ---- phase 2: triangle tests for the lanes that reached a leaf
-        if (leaf_ready) {
-            const uint32_t start = cur.a & WB_IDX_MASK;
-            for (uint32_t pos = start; pos < start + cur.b; ++pos) {
-                const Tri t = load_tri(tv.tris, pos);
-                if (COUNT)
-                    cnt.tris++;
-                if (t.flags & WB_TRI_SLIVER)
-                    continue;
-                float bv, bw;
-                closest_vw(t.p, t.q, t.r, p, bv, bw);
-                const float bu = 1.0f - bv - bw;
-                const float w = 1.f - bu - bv;
-                const float3 c = wb_add(wb_add(wb_scale(bu, t.p), wb_scale(bv, t.q)), wb_scale(w, t.r));
-                const float3 d = wb_sub(c, p);
-                const float dsq = wb_dot(d, d);
-                if (dsq < best) {
-                    best = dsq;
-                    best_v = bv;
-                    best_w = w;
-                    best_face = t.face;
-                }
-            }
-        } else if (active) {
-            // ---- stack empty: the query is answered
-            const bool ok = best < max_sq;
-            float sg = 0.f;
-            if (SIGN && ok) {
-                int votes = 0;
-                float sp = 0.f;
-#pragma unroll 1
-                for (int axis = 0; axis < 3; ++axis)
-                    if (probe_sign<COUNT>(tv, h, p, axis, sp, cnt) && sp < 0.f)
-                        votes++;
-                sg = votes >= 2 ? -1.0f : 1.0f;
-            }
-            result[qi] = ok ? 1 : 0;
-            face[qi] = ok ? best_face : 0;
-            u[qi] = ok ? 1.0f - best_v - best_w : 0.f;
-            v[qi] = ok ? best_v : 0.f;
-            if (sign)
-                sign[qi] = sg;
-            active = false;
-        }
-    }
-    if (COUNT) {
-        atomicAdd(stats + 0, cnt.pairs);
-        atomicAdd(stats + 1, cnt.tris);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // closest ray hit, near child first (mesh.h:1735-1891)
 // ------------------------------------------------------------------------------------------------
 template <bool COUNT>
@@ -703,59 +548,23 @@ int query_grid(long long nq)
 
 }  // namespace
 
-template <class K> int persistent_grid(K kernel)
-{
-    int dev = 0, sms = 148, per_sm = 4;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, QT, 0) != cudaSuccess || per_sm < 1)
-        per_sm = 4;
-    return sms * per_sm;
-}
-
 const char* wb_query_point(const TreeView& tv, const float* pts, const int* perm, long long nq, float max_dist,
                            int with_sign, uint8_t* result, float* sign, int* face, float* u, float* v,
-                           unsigned long long* stats, unsigned long long* next_slot, cudaStream_t stream)
+                           unsigned long long* stats, cudaStream_t stream)
 {
     if (nq <= 0)
         return nullptr;
-    if (next_slot) {  // persistent while-while kernel with dynamic query claiming
-        cudaMemsetAsync(next_slot, 0, sizeof(unsigned long long), stream);
-#define WB_LAUNCH_WW(S, C)                                                                                         \
-    do {                                                                                                           \
-        static int grid_cache = 0;                                                                                 \
-        if (!grid_cache)                                                                                           \
-            grid_cache = persistent_grid(k_query_point_ww<S, C>);                                                  \
-        const long long want = (nq + QT - 1) / QT;                                                                 \
-        const int grid = (int)(want < grid_cache ? want : grid_cache);                                             \
-        k_query_point_ww<S, C><<<grid, QT, 0, stream>>>(tv, pts, perm, nq, max_dist, result, sign, face, u, v,     \
-                                                        next_slot, stats);                                         \
-    } while (0)
-        if (with_sign) {
-            if (stats)
-                WB_LAUNCH_WW(true, true);
-            else
-                WB_LAUNCH_WW(true, false);
-        } else {
-            if (stats)
-                WB_LAUNCH_WW(false, true);
-            else
-                WB_LAUNCH_WW(false, false);
-        }
-#undef WB_LAUNCH_WW
+    const int grid = query_grid(nq);
+    if (with_sign) {
+        if (stats)
+            k_query_point<true, true><<<grid, QT, 0, stream>>>(tv, pts, perm, nq, max_dist, result, sign, face, u, v, stats);
+        else
+            k_query_point<true, false><<<grid, QT, 0, stream>>>(tv, pts, perm, nq, max_dist, result, sign, face, u, v, stats);
     } else {
-        const int grid = query_grid(nq);
-        if (with_sign) {
-            if (stats)
-                k_query_point<true, true><<<grid, QT, 0, stream>>>(tv, pts, perm, nq, max_dist, result, sign, face, u, v, stats);
-            else
-                k_query_point<true, false><<<grid, QT, 0, stream>>>(tv, pts, perm, nq, max_dist, result, sign, face, u, v, stats);
-        } else {
-            if (stats)
-                k_query_point<false, true><<<grid, QT, 0, stream>>>(tv, pts, perm, nq, max_dist, result, sign, face, u, v, stats);
-            else
-                k_query_point<false, false><<<grid, QT, 0, stream>>>(tv, pts, perm, nq, max_dist, result, sign, face, u, v, stats);
-        }
+        if (stats)
+            k_query_point<false, true><<<grid, QT, 0, stream>>>(tv, pts, perm, nq, max_dist, result, sign, face, u, v, stats);
+        else
+            k_query_point<false, false><<<grid, QT, 0, stream>>>(tv, pts, perm, nq, max_dist, result, sign, face, u, v, stats);
     }
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);

@@ -2,11 +2,10 @@
 #pragma once
 #include "common.cuh"
 
-// next_slot: device counter for the persistent kernel (NULL selects the one-thread-per-slot kernel)
 // perm: optional permutation (thread slot -> query index), e.g. from wb_morton_order
 const char* wb_query_point(const TreeView& tv, const float* pts, const int* perm, long long nq, float max_dist,
                            int with_sign, uint8_t* result, float* sign, int* face, float* u, float* v,
-                           unsigned long long* stats, unsigned long long* next_slot, cudaStream_t stream);
+                           unsigned long long* stats, cudaStream_t stream);
 const char* wb_query_ray(const TreeView& tv, const float* starts, const float* dirs, long long nq, float max_t,
                          uint8_t* result, float* sign, int* face, float* t, float* u, float* v, float* normal,
                          unsigned long long* stats, cudaStream_t stream);

@@ -20,7 +20,10 @@ struct BvhState {
     const int* indices = nullptr;
     int num_points = 0;
 
-    // owned tree storage
+    // owned tree storage: every pointer below up to `partials` is carved out of one arena
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+    bool arena_async = false;
     uint32_t* keys = nullptr;     // n sorted Morton keys
     int* prim = nullptr;          // n primitive_indices
     NodeRec* pairs = nullptr;     // 2*(n-1) node records
@@ -64,5 +67,5 @@ struct MeshState {
 const char* wb_build(BvhState& s, cudaStream_t stream);
 const char* wb_refit(BvhState& s, cudaStream_t stream);
 const char* wb_export_reference_layout(BvhState& s, cudaStream_t stream);
-const char* wb_alloc_tree(BvhState& s);
-void wb_free_tree(BvhState& s);
+const char* wb_alloc_tree(BvhState& s, cudaStream_t stream);
+void wb_free_tree(BvhState& s, cudaStream_t stream);
