@@ -11,6 +11,7 @@
 // node records), height tracked in the arrival counters so the per-node depth walk of
 // mark_packed_leaf_nodes (bvh.cu:402-443) only runs for trees that are actually >= 32 deep.
 #include "state.h"
+#include "merge.cuh"
 
 #include <cub/device/device_radix_sort.cuh>  // WARP_B200_SORT=cub cross-check path only
 
@@ -67,26 +68,38 @@ __device__ __forceinline__ void block_minmax(float3& lo, float3& hi, float (*sm)
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1: scene AABB + 1/(extent + 1e-4)  (bvh.cu:449-488).  One pass, last block finishes.
-// Also clears the digit histograms and tile tickets used by the following kernels.
+// K1: per-block partial scene bounds (bvh.cu:449-479).  No cross-block handshake here: the few
+// hundred partials are reduced redundantly by every block of K2 (a 14 KB L2 read), which removes
+// the same-address ticket atomics and the extra kernel.  Also clears the digit histograms and
+// tile tickets used by the following kernels.
 // ---------------------------------------------------------------------------------------------
 template <class Src>
 __global__ void __launch_bounds__(BT)
 k_scene_bounds(Src src, int n, float* __restrict__ partials, unsigned* __restrict__ tickets,
-               TreeHeader* __restrict__ hdr, uint32_t* __restrict__ ghist)
+               uint32_t* __restrict__ ghist)
 {
     __shared__ float sm[BT / 32][6];
-    __shared__ bool is_last;
 
     if (blockIdx.x == 0) {
         for (int k = threadIdx.x; k < 4 * 256; k += BT)
             ghist[k] = 0;
-        if (threadIdx.x < 4)
-            tickets[1 + threadIdx.x] = 0;  // per-pass tile tickets
+        if (threadIdx.x < 8)
+            tickets[threadIdx.x] = 0;  // per-pass tile tickets
     }
 
     float3 lo = make_float3(FLT_MAX, FLT_MAX, FLT_MAX), hi = make_float3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
-    for (int i = blockIdx.x * BT + threadIdx.x; i < n; i += gridDim.x * BT) {
+    const int stride = gridDim.x * BT;
+    int i = blockIdx.x * BT + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {  // four independent gathers in flight
+        float3 a0, b0, a1, b1, a2, b2, a3, b3;
+        src.bounds(i, a0, b0);
+        src.bounds(i + stride, a1, b1);
+        src.bounds(i + 2 * stride, a2, b2);
+        src.bounds(i + 3 * stride, a3, b3);
+        lo = wb_min3(wb_min3(lo, wb_min3(a0, a1)), wb_min3(a2, a3));
+        hi = wb_max3(wb_max3(hi, wb_max3(b0, b1)), wb_max3(b2, b3));
+    }
+    for (; i < n; i += stride) {
         float3 a, b;
         src.bounds(i, a, b);
         lo = wb_min3(lo, a);
@@ -96,29 +109,26 @@ k_scene_bounds(Src src, int n, float* __restrict__ partials, unsigned* __restric
     if (threadIdx.x == 0) {
         float* p = partials + 6 * blockIdx.x;
         p[0] = lo.x, p[1] = lo.y, p[2] = lo.z, p[3] = hi.x, p[4] = hi.y, p[5] = hi.z;
-        __threadfence();
-        is_last = (atomicAdd(&tickets[0], 1u) == gridDim.x - 1);
     }
-    __syncthreads();
-    if (!is_last)
-        return;
-    __threadfence();
+}
+
+// reduce the K1 partials inside a block; every thread returns the scene bounds
+__device__ __forceinline__ void reduce_partials(const float* __restrict__ partials, int num_partials, float (*sm)[6],
+                                                float3& lo, float3& hi)
+{
+    __shared__ float total[6];
     lo = make_float3(FLT_MAX, FLT_MAX, FLT_MAX), hi = make_float3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
-    for (int b = threadIdx.x; b < gridDim.x; b += BT) {
+    for (int b = threadIdx.x; b < num_partials; b += BT) {
         const float* p = partials + 6 * b;
-        lo = wb_min3(lo, make_float3(__ldcg(p + 0), __ldcg(p + 1), __ldcg(p + 2)));
-        hi = wb_max3(hi, make_float3(__ldcg(p + 3), __ldcg(p + 4), __ldcg(p + 5)));
+        lo = wb_min3(lo, make_float3(p[0], p[1], p[2]));
+        hi = wb_max3(hi, make_float3(p[3], p[4], p[5]));
     }
     block_minmax(lo, hi, sm);
-    if (threadIdx.x == 0) {
-        hdr->total_lo[0] = lo.x, hdr->total_lo[1] = lo.y, hdr->total_lo[2] = lo.z;
-        hdr->total_hi[0] = hi.x, hdr->total_hi[1] = hi.y, hdr->total_hi[2] = hi.z;
-        // edges = upper - lower; edges += 1e-4; inv = 1 / edges  (IEEE division, bvh.cu:482-488)
-        hdr->inv_edges[0] = 1.0f / ((hi.x - lo.x) + 0.0001f);
-        hdr->inv_edges[1] = 1.0f / ((hi.y - lo.y) + 0.0001f);
-        hdr->inv_edges[2] = 1.0f / ((hi.z - lo.z) + 0.0001f);
-        tickets[0] = 0;
-    }
+    if (threadIdx.x == 0)
+        total[0] = lo.x, total[1] = lo.y, total[2] = lo.z, total[3] = hi.x, total[4] = hi.y, total[5] = hi.z;
+    __syncthreads();
+    lo = make_float3(total[0], total[1], total[2]);
+    hi = make_float3(total[3], total[4], total[5]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -170,16 +180,26 @@ __device__ __forceinline__ void hist_add_coherent(uint32_t* h, uint32_t d, bool 
 
 template <class Src>
 __global__ void __launch_bounds__(BT)
-k_morton_hist(Src src, int n, const TreeHeader* __restrict__ hdr, uint32_t* __restrict__ keys,
-              uint32_t* __restrict__ ghist)
+k_morton_hist(Src src, int n, const float* __restrict__ partials, int num_partials, TreeHeader* __restrict__ hdr,
+              uint32_t* __restrict__ keys, uint32_t* __restrict__ ghist)
 {
     __shared__ uint32_t h[4 * 256];
+    __shared__ float sm[BT / 32][6];
     for (int k = threadIdx.x; k < 4 * 256; k += BT)
         h[k] = 0;
-    __syncthreads();
 
-    const float glx = hdr->total_lo[0], gly = hdr->total_lo[1], glz = hdr->total_lo[2];
-    const float ivx = hdr->inv_edges[0], ivy = hdr->inv_edges[1], ivz = hdr->inv_edges[2];
+    // scene bounds and 1 / (extent + 1e-4) (IEEE division, bvh.cu:482-488), recomputed by every block
+    float3 glo, ghi;
+    reduce_partials(partials, num_partials, sm, glo, ghi);
+    const float glx = glo.x, gly = glo.y, glz = glo.z;
+    const float ivx = 1.0f / ((ghi.x - glo.x) + 0.0001f);
+    const float ivy = 1.0f / ((ghi.y - glo.y) + 0.0001f);
+    const float ivz = 1.0f / ((ghi.z - glo.z) + 0.0001f);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        hdr->total_lo[0] = glo.x, hdr->total_lo[1] = glo.y, hdr->total_lo[2] = glo.z;
+        hdr->total_hi[0] = ghi.x, hdr->total_hi[1] = ghi.y, hdr->total_hi[2] = ghi.z;
+        hdr->inv_edges[0] = ivx, hdr->inv_edges[1] = ivy, hdr->inv_edges[2] = ivz;
+    }
 
     const int stride = gridDim.x * BT;
     const int iters = (n + stride - 1) / stride;
@@ -219,9 +239,9 @@ constexpr int RS_ITEMS_SMALL = 8;   // 2048-key tiles: more resident warps while
 constexpr long long RS_SMALL_LIMIT = 1ll << 24;
 __host__ __device__ inline int rs_items_for(long long n) { return n < RS_SMALL_LIMIT ? RS_ITEMS_SMALL : RS_ITEMS_LARGE; }
 __host__ __device__ inline int rs_tile_for(long long n) { return RS_THREADS * rs_items_for(n); }
-constexpr uint32_t RS_FLAG_AGG = 1u << 30;
-constexpr uint32_t RS_FLAG_INC = 2u << 30;
-constexpr uint32_t RS_VAL_MASK = (1u << 30) - 1;
+#define RS_FLAG_AGG (1u << 30)
+#define RS_FLAG_INC (2u << 30)
+#define RS_VAL_MASK ((1u << 30) - 1u)
 
 template <bool IMPLICIT_VALS, int ITEMS>
 __global__ void __launch_bounds__(RS_THREADS)
@@ -295,15 +315,26 @@ k_onesweep_pass(const uint32_t* __restrict__ keys_in, const int* __restrict__ va
         *my_status = RS_FLAG_INC | count;
     } else {
         *my_status = RS_FLAG_AGG | count;
-        for (int j = tile - 1;; --j) {
-            volatile uint32_t* st = tile_status + (size_t)j * 256 + tid;
-            uint32_t v;
-            do {
-                v = *st;
-            } while ((v & ~RS_VAL_MASK) == 0);
-            excl += v & RS_VAL_MASK;
-            if (v & RS_FLAG_INC)
-                break;
+        // walk back over the predecessors' words LB at a time: the loads of one batch are issued
+        // back to back (one L2 round trip for the batch instead of one per tile), then consumed in
+        // order; a word that is not published yet is re-polled in place
+        constexpr int LB = 16;
+        bool found = false;
+        for (int j = tile - 1; !found; j -= LB) {
+            uint32_t v[LB];
+#pragma unroll
+            for (int b = 0; b < LB; ++b)
+                v[b] = (j - b >= 0) ? tile_status[(size_t)(j - b) * 256 + tid] : RS_FLAG_INC;
+#pragma unroll
+            for (int b = 0; b < LB; ++b) {
+                if (!found) {
+                    uint32_t w = v[b];
+                    while ((w & ~RS_VAL_MASK) == 0)
+                        w = tile_status[(size_t)(j - b) * 256 + tid];
+                    excl += w & RS_VAL_MASK;
+                    found = (w & RS_FLAG_INC) != 0;
+                }
+            }
         }
         *my_status = RS_FLAG_INC | (excl + count);
     }
@@ -388,34 +419,18 @@ static void onesweep_sort(uint32_t* keys, uint32_t* keys_alt, int* vals, int* va
 }
 
 // ---------------------------------------------------------------------------------------------
-// K4: bottom-up hierarchy (bvh.cu:228-393) fused with leaf creation, packed-triangle gather and
-// size-rule leaf marking.  One thread per sorted position; the second thread to arrive at a
-// parent continues upward carrying the union box in registers.
+// K4a: leaves (bvh.cu:228-255) -- one thread per sorted position: gather the triangle, refresh the
+// packed-triangle cache and write the leaf's node record straight into its parent's pair (which
+// pair is a function of the neighbouring keys only).  K4b (merge.cuh) then merges bottom-up.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int key_delta(const uint32_t* __restrict__ keys, int i)
-{
-    // common-prefix length of keys i and i+1 (bvh.cu:218-226 computes it on 64-bit keys: +32, and 64
-    // for equal keys; only comparisons between deltas are used, so the 32-bit form is equivalent)
-    return __clz((int)(__ldg(keys + i) ^ __ldg(keys + i + 1)));
-}
-
-__device__ __forceinline__ void store_rec(NodeRec* dst, float3 lo, float3 hi, uint32_t ref, uint32_t aux)
-{
-    float4* d4 = reinterpret_cast<float4*>(dst);
-    d4[0] = make_float4(lo.x, lo.y, lo.z, __uint_as_float(ref));
-    d4[1] = make_float4(hi.x, hi.y, hi.z, __uint_as_float(aux));
-}
-
 template <class Src>
 __global__ void __launch_bounds__(BT)
-k_hierarchy(Src src, int n, int leaf_size, const uint32_t* __restrict__ keys, const int* __restrict__ prim,
-            NodeRec* pairs, int* parent_int, int* pos_parent, unsigned* counters, float4* __restrict__ tris,
-            TreeHeader* hdr)
+k_leaves(Src src, int n, const uint32_t* __restrict__ keys, const int* __restrict__ prim, NodeRec* __restrict__ pairs,
+         int* __restrict__ pos_parent, float4* __restrict__ tris)
 {
     const int i = blockIdx.x * BT + threadIdx.x;
     if (i >= n)
         return;
-
     const int item = __ldg(prim + i);
     float3 lo, hi;
     if constexpr (Src::kIsMesh) {
@@ -436,84 +451,9 @@ k_hierarchy(Src src, int n, int leaf_size, const uint32_t* __restrict__ keys, co
         src.bounds(item, lo, hi);
     }
     pos_parent[i] = WB_NO_PARENT;
-
-    int node = i;          // reference index of the node this thread currently owns
-    int left = i, right = i;
-    unsigned height = 0;
-
-    for (;;) {
-        const int size = right - left + 1;
-        const uint32_t self_ref = (uint32_t)node | (size <= leaf_size ? WB_LEAF : 0u);
-
-        if (left == 0 && right == n - 1) {  // root (bvh.cu:285-290)
-            hdr->lx = lo.x, hdr->ly = lo.y, hdr->lz = lo.z;
-            hdr->hx = hi.x, hdr->hy = hi.y, hdr->hz = hi.z;
-            hdr->root_ref = self_ref;
-            hdr->root_count = (uint32_t)n;
-            hdr->height = (int)height;
-            hdr->deep = 0;
-            hdr->n = n;
-            hdr->leaf_size = leaf_size;
-            if (node >= n)
-                parent_int[node - n] = WB_NO_PARENT;
-            if (self_ref & WB_LEAF)
-                pos_parent[0] = WB_ROOT_PARENT;
-            return;
-        }
-
-        // parent choice (bvh.cu:300-334, ungrouped): larger common prefix wins, ties by item parity
-        bool go_right;
-        if (left == 0) {
-            go_right = true;
-        } else if (right == n - 1) {
-            go_right = false;
-        } else {
-            const int dr = key_delta(keys, right), dl = key_delta(keys, left - 1);
-            if (dr > dl)
-                go_right = true;
-            else if (dr < dl)
-                go_right = false;
-            else
-                go_right = ((__ldg(prim + left - 1) % 2) ^ (__ldg(prim + right) % 2)) != 0;
-        }
-
-        // going right: we are the LEFT child of node n+right; else the RIGHT child of node n+left-1
-        const int s = go_right ? right : left - 1;
-        const int parent = n + s;
-        NodeRec* mine = pairs + 2 * (size_t)s + (go_right ? 0 : 1);
-        NodeRec* sibling = pairs + 2 * (size_t)s + (go_right ? 1 : 0);
-        store_rec(mine, lo, hi, self_ref, (uint32_t)(go_right ? left : right));
-        if (node >= n)
-            parent_int[node - n] = parent;
-
-        const unsigned h = min(height, WB_HEIGHT_CAP);
-        const unsigned old = wb_arrive(&counters[s], 1u | (h << 8));
-        if ((old & 0xffu) == 0u)
-            return;  // first to arrive: the sibling's thread carries on
-
-        // second arrival: fetch the sibling record (written by another SM: bypass L1)
-        const float4 s0 = __ldcg(reinterpret_cast<const float4*>(sibling));
-        const float4 s1 = __ldcg(reinterpret_cast<const float4*>(sibling) + 1);
-        const int far_end = (int)__float_as_uint(s1.w);
-        const int new_left = go_right ? left : far_end;
-        const int new_right = go_right ? far_end : right;
-
-        // visible packed leaves: children that fit leaf_size while this parent does not
-        const int parent_size = new_right - new_left + 1;
-        if (parent_size > leaf_size) {
-            const int lsize = s - new_left + 1, rsize = new_right - s;
-            if (lsize <= leaf_size)
-                pos_parent[new_left] = parent;
-            if (rsize <= leaf_size)
-                pos_parent[s + 1] = parent;
-        }
-
-        lo = wb_min3(lo, make_float3(s0.x, s0.y, s0.z));
-        hi = wb_max3(hi, make_float3(s1.x, s1.y, s1.z));
-        height = max(height, old >> 8) + 1u;
-        left = new_left, right = new_right;
-        node = parent;
-    }
+    const bool go_right = wb_goes_right(keys, prim, n, i, i);
+    NodeRec* rec = pairs + 2 * (size_t)(go_right ? i : i - 1) + (go_right ? 0 : 1);
+    wb_store_rec(rec, lo, hi, (uint32_t)i | WB_LEAF, (uint32_t)i);  // a single item always fits leaf_size >= 1
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -683,12 +623,12 @@ template <class Src> const char* build_impl(BvhState& s, Src src, cudaStream_t s
     }
 
     // K1 scene bounds (+ clears histograms / tickets)
-    k_scene_bounds<<<s.bounds_blocks, BT, 0, stream>>>(src, n, s.partials, s.tickets, s.header, s.ghist);
+    k_scene_bounds<<<s.bounds_blocks, BT, 0, stream>>>(src, n, s.partials, s.tickets, s.ghist);
     // look-back words and arrival counters start from zero
     WB_CUDA_TRY(cudaMemsetAsync(s.tile_status, 0, sizeof(uint32_t) * 256 * 4 * (size_t)s.num_tiles, stream));
     WB_CUDA_TRY(cudaMemsetAsync(s.counters, 0, sizeof(unsigned) * (size_t)(n - 1), stream));
     // K2 Morton keys + histograms
-    k_morton_hist<<<s.bounds_blocks, BT, 0, stream>>>(src, n, s.header, s.keys, s.ghist);
+    k_morton_hist<<<s.bounds_blocks, BT, 0, stream>>>(src, n, s.partials, s.bounds_blocks, s.header, s.keys, s.ghist);
 
     if (use_cub_sort()) {
         // library cross-check path (tests only): stable LSD sort of bits [0, 32)
@@ -710,9 +650,13 @@ template <class Src> const char* build_impl(BvhState& s, Src src, cudaStream_t s
         onesweep_sort(s.keys, s.keys_alt, s.prim, s.prim_alt, n, s.ghist, s.tile_status, s.tickets, stream);
     }
 
-    // K4 hierarchy
-    k_hierarchy<<<wb_div_up(n, BT), BT, 0, stream>>>(src, n, s.leaf_size, s.keys, s.prim, s.pairs, s.parent_int,
-                                                    s.pos_parent, s.counters, s.tris, s.header);
+    // K4a leaves, K4b chunked bottom-up merge
+    k_leaves<<<wb_div_up(n, BT), BT, 0, stream>>>(src, n, s.keys, s.prim, s.pairs, s.pos_parent, s.tris);
+    {
+        const MergeArgs ma { n, s.leaf_size, s.keys, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters, s.header };
+        const int merge_threads = wb_div_up(n, MC);
+        k_merge<false><<<wb_div_up(merge_threads, 128), 128, 0, stream>>>(ma);
+    }
     // K5/K6 depth rule (early-out unless the tree is at least 32 levels deep)
     k_deep_fix_positions<<<wb_div_up(n, BT), BT, 0, stream>>>(n, s.leaf_size, s.header, s.parent_int, s.pos_parent);
     k_deep_fix_nodes<<<wb_div_up(n - 1, BT), BT, 0, stream>>>(n, s.leaf_size, s.header, s.parent_int, s.pairs,
@@ -741,12 +685,25 @@ static bool pool_ready(int device)
     return true;
 }
 
+// streaming kernels K1/K2: four blocks per SM, each thread strides over ~n / (148*4*256) items
+static int bounds_grid(long long n)
+{
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = 148;
+    }
+    return (int)min((long long)sms * 4, max(1ll, (n + BT - 1) / BT));
+}
+
 const char* wb_alloc_tree(BvhState& s, cudaStream_t stream)
 {
     const size_t n = (size_t)s.n;
     const size_t ni = n > 1 ? n - 1 : 1;
     s.num_tiles = wb_div_up((long long)n, rs_tile_for((long long)n));
-    s.bounds_blocks = min(4096, max(1, wb_div_up((long long)n, BT)));
+    s.bounds_blocks = bounds_grid((long long)n);
     size_t off = 0;
     auto take = [&off](size_t bytes) {
         const size_t at = off;
@@ -861,11 +818,11 @@ const char* wb_morton_order(OrderScratch& ws, const float* pts, long long n, cud
     }
     const int ni = (int)n;
     const int tiles = wb_div_up(n, rs_tile_for(n));
-    const int blocks = min(4096, max(1, wb_div_up(n, BT)));
+    const int blocks = bounds_grid(n);
     const BoxSource src { pts, pts };  // a point is its own (degenerate) box; its centroid is the point itself
-    k_scene_bounds<<<blocks, BT, 0, stream>>>(src, ni, ws.partials, ws.tickets, ws.hdr, ws.ghist);
+    k_scene_bounds<<<blocks, BT, 0, stream>>>(src, ni, ws.partials, ws.tickets, ws.ghist);
     WB_CUDA_TRY(cudaMemsetAsync(ws.tile_status, 0, sizeof(uint32_t) * 256 * 4 * (size_t)tiles, stream));
-    k_morton_hist<<<blocks, BT, 0, stream>>>(src, ni, ws.hdr, ws.keys, ws.ghist);
+    k_morton_hist<<<blocks, BT, 0, stream>>>(src, ni, ws.partials, blocks, ws.hdr, ws.keys, ws.ghist);
     onesweep_sort(ws.keys, ws.keys_alt, ws.idx, ws.idx_alt, ni, ws.ghist, ws.tile_status, ws.tickets, stream);
     WB_CUDA_TRY(cudaGetLastError());
     return nullptr;

@@ -9,6 +9,7 @@
 // with one atomic arrival counter per internal node.  The counters are never cleared: they are
 // even after a build and every refit adds exactly 2, so "second to arrive" == odd old value.
 #include "state.h"
+#include "merge.cuh"
 
 namespace {
 
@@ -16,9 +17,8 @@ constexpr int BT = 256;
 
 template <class Src>
 __global__ void __launch_bounds__(BT)
-k_refit(Src src, int n, const int* __restrict__ prim, const int* __restrict__ pos_parent,
-        const int* __restrict__ parent_int, NodeRec* pairs, unsigned* counters, float4* __restrict__ tris,
-        TreeHeader* hdr)
+k_refit_leaves(Src src, int n, const int* __restrict__ prim, const int* __restrict__ pos_parent, NodeRec* pairs,
+               float4* __restrict__ tris, TreeHeader* hdr)
 {
     const int i = blockIdx.x * BT + threadIdx.x;
     if (i >= n)
@@ -70,27 +70,8 @@ k_refit(Src src, int n, const int* __restrict__ prim, const int* __restrict__ po
         return;
     }
 
-    for (;;) {
-        NodeRec* mine = pairs + 2 * (size_t)s + side;
-        mine->lx = lo.x, mine->ly = lo.y, mine->lz = lo.z;
-        mine->hx = hi.x, mine->hy = hi.y, mine->hz = hi.z;
-        const unsigned old = wb_arrive(&counters[s], 1u);
-        if ((old & 1u) == 0u)
-            return;  // first arrival
-        const float4* sib = reinterpret_cast<const float4*>(pairs + 2 * (size_t)s + (1 - side));
-        const float4 s0 = __ldcg(sib), s1 = __ldcg(sib + 1);
-        lo = wb_min3(lo, make_float3(s0.x, s0.y, s0.z));
-        hi = wb_max3(hi, make_float3(s1.x, s1.y, s1.z));
-        const int up = __ldg(parent_int + s);
-        if (up == WB_NO_PARENT) {
-            hdr->lx = lo.x, hdr->ly = lo.y, hdr->lz = lo.z;
-            hdr->hx = hi.x, hdr->hy = hi.y, hdr->hz = hi.z;
-            return;
-        }
-        const int us = up - n;
-        side = (s < us) ? 0 : 1;
-        s = us;
-    }
+    // the merge pass (k_merge<true>, merge.cuh) unions these leaf boxes bottom-up
+    wb_store_box(pairs + 2 * (size_t)s + side, lo, hi);
 }
 
 }  // namespace
@@ -108,11 +89,15 @@ const char* wb_refit(BvhState& s, cudaStream_t stream)
         return nullptr;
     const int grid = wb_div_up(s.n, BT);
     if (s.is_mesh)
-        k_refit<<<grid, BT, 0, stream>>>(MeshSource { s.points, s.indices }, s.n, s.prim, s.pos_parent, s.parent_int,
-                                         s.pairs, s.counters, s.tris, s.header);
+        k_refit_leaves<<<grid, BT, 0, stream>>>(MeshSource { s.points, s.indices }, s.n, s.prim, s.pos_parent, s.pairs,
+                                                s.tris, s.header);
     else
-        k_refit<<<grid, BT, 0, stream>>>(BoxSource { s.item_lowers, s.item_uppers }, s.n, s.prim, s.pos_parent,
-                                         s.parent_int, s.pairs, s.counters, s.tris, s.header);
+        k_refit_leaves<<<grid, BT, 0, stream>>>(BoxSource { s.item_lowers, s.item_uppers }, s.n, s.prim, s.pos_parent,
+                                                s.pairs, s.tris, s.header);
+    if (s.n > 1) {
+        const MergeArgs ma { s.n, s.leaf_size, s.keys, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters, s.header };
+        k_merge<true><<<wb_div_up(wb_div_up(s.n, MC), 128), 128, 0, stream>>>(ma);
+    }
     WB_CUDA_TRY(cudaGetLastError());
     return nullptr;
 }
