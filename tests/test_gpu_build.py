@@ -199,3 +199,34 @@ def test_build_equals_reference_cuda_lbvh_dump(wp, name, leaf):
     for k in ("node_lowers", "node_uppers"):
         for f in ("x", "y", "z", "ib"):
             assert np.array_equal(t[k][f], g[f"{name}_leaf{leaf}_{k}"][f]), (k, f)
+
+
+def test_c3_heightfield_10m_build_bit_exact(wp, oracle_mod):
+    """Config C3 mesh (9 999 392 triangles): 68 % duplicate 30-bit keys, depth 44 -> the depth >= 32 rule and
+    the parity tie-break decide a large part of the topology.  Full diff of all 2N-1 nodes."""
+    P, I = mg.heightfield(2237, 4)
+    m = gpu_mesh(wp, P, I, 4)
+    got = m.download_tree()
+    assert got["deep"] == 1 and got["height"] >= 32
+    want = oracle_mod.mesh_lbvh_build(P, I, 4)
+    assert_tree_equal(got, want)
+    # refit after a vertical deformation: visible boxes equal the oracle's
+    P2 = P.copy()
+    P2[:, 2] += 0.01 * np.sin(40.0 * P2[:, 0]).astype(np.float32)
+    m.points.assign(P2)
+    m.refit()
+    got = m.download_tree()
+    lo2, hi2 = oracle_mod.triangle_bounds(P2, I)
+    oracle_mod.lbvh_refit(want, lo2, hi2)
+    lo, hi = want["node_lowers"], want["node_uppers"]
+    # walk the visible tree iteratively (20 M nodes: vectorised frontier expansion)
+    frontier = np.array([want["root"]])
+    vis = []
+    while frontier.size:
+        vis.append(frontier)
+        inner = frontier[(lo["ib"][frontier] >> 31) == 0]
+        frontier = np.concatenate([lo["ib"][inner] & 0x7FFFFFFF, hi["ib"][inner] & 0x7FFFFFFF]).astype(np.int64)
+    vis = np.concatenate(vis)
+    for name in ("node_lowers", "node_uppers"):
+        for f in "xyz":
+            assert np.array_equal(got[name][f][vis], want[name][f][vis]), (name, f)

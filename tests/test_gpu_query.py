@@ -235,3 +235,50 @@ def test_query_order_modes_agree(wp, oracle_mod):
             assert_results_equal(wp.mesh_query_point_no_sign(m, Qs, 1e6).numpy(), oracle_mod.query_point_no_sign(P, I, tree, Qs, 1e6), ("result", "face", "u", "v"))
     finally:
         wp.set_query_order(wp.QUERY_ORDER_AUTO)
+
+
+def test_c3_rays_on_10m_heightfield(wp, oracle_mod):
+    """Config C3 shapes: 10 M-triangle heightfield (deep, duplicate-heavy tree), a 1024 x 1024 pinhole image
+    (1 M of the 16.8 M rays) bit-exact on a 100 k sample, plus image-level properties on all of it."""
+    P, I = mg.heightfield(2237, 4)
+    m = gpu_mesh(wp, P, I, 4)
+    S, D = mg.pinhole_rays(1024, 1024)
+    got = wp.mesh_query_ray(m, wp.array(S, dtype=wp.vec3), wp.array(D, dtype=wp.vec3), 1e6).numpy()
+    hit = got["result"] == 1
+    assert 0.3 < hit.mean() < 0.7
+    assert (got["t"][hit] > 0).all() and (got["u"][hit] >= -1e-6).all() and (got["v"][hit] >= -1e-6).all()
+    assert np.allclose(np.linalg.norm(got["normal"][hit], axis=1), 1.0, atol=1e-5)
+    hp = S[hit] + got["t"][hit, None] * D[hit]
+    assert (hp[:, 0] > -1e-4).all() and (hp[:, 0] < 1 + 1e-4).all() and (hp[:, 1] > -1e-4).all() and (hp[:, 1] < 1 + 1e-4).all()
+    tree = oracle_mod.mesh_lbvh_build(P, I, 4)
+    sel = np.random.default_rng(3).integers(0, S.shape[0], 100000)
+    want = oracle_mod.query_ray(P, I, tree, S[sel], D[sel], 1e6)
+    assert_results_equal({k: got[k][sel] for k in RAY_FIELDS}, want, RAY_FIELDS)
+    # closest-point queries near the surface of the same deep tree, signed
+    Q = (P[np.random.default_rng(4).integers(0, P.shape[0], 20000)] + np.random.default_rng(5).normal(0, 0.01, (20000, 3))).astype(np.float32)
+    assert_results_equal(wp.mesh_query_point(m, Q, 0.05).numpy(), oracle_mod.query_point(P, I, tree, Q, 0.05), POINT_FIELDS)
+
+
+def test_c4_cloth_refit_query_loop(wp, oracle_mod):
+    """Config C4 shape: 4 M-triangle cloth, per frame = deform in place + refit + closest-point queries within
+    0.05 of the previous frame's vertices.  3 frames, bit-exact on 20 k sampled queries per frame."""
+    n = 1415
+    P, I = mg.cloth(n, frame=0)
+    pts = wp.array(P, dtype=wp.vec3)
+    m = wp.Mesh(pts, wp.array(I, dtype=wp.int32))
+    tree = oracle_mod.mesh_lbvh_build(P, I, 4)
+    prev = P
+    for frame in (1, 2, 3):
+        Pf, _ = mg.cloth(n, frame=frame * 40)
+        pts.assign(Pf)
+        m.refit()
+        lo, hi = oracle_mod.triangle_bounds(Pf, I)
+        oracle_mod.lbvh_refit(tree, lo, hi)
+        rng = np.random.default_rng(5 + frame)
+        Q = (prev[rng.integers(0, prev.shape[0], 1 << 20)] + rng.normal(0, 0.01, (1 << 20, 3))).astype(np.float32)
+        got = wp.mesh_query_point_no_sign(m, wp.array(Q, dtype=wp.vec3), 0.05).numpy()
+        assert 0.5 < got["result"].mean() <= 1.0
+        sel = rng.integers(0, Q.shape[0], 20000)
+        want = oracle_mod.query_point_no_sign(Pf, I, tree, Q[sel], 0.05)
+        assert_results_equal({k: got[k][sel] for k in ("result", "face", "u", "v")}, want, ("result", "face", "u", "v"))
+        prev = Pf
