@@ -300,9 +300,15 @@ def main():
         kernel_ms = statistics.median([event_ms(core, lambda: wp.mesh_query_point_no_sign(mesh, q_dev, MAX_DIST, out=out), stream)
                                        for _ in range(3)])  # fmt: skip
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:  # DRAM bytes of this kernel from the committed ncu --set full capture (same workload), scaled to this batch
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_query_point<no_sign>"]
+        traffic = tj["dram_bytes_per_launch"] * nq / tj["queries"]
+    except Exception:
+        pass
     roofline = {
         "kernel": "k_query_point<no_sign>", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-        "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": kernel_ms,
         "pair_fetches_per_query": st.pair_fetches / nq, "tri_fetches_per_query": st.tri_fetches / nq,
         "nodes_per_s": 2 * st.pair_fetches / (kernel_ms * 1e-3),
@@ -389,6 +395,18 @@ def side_measurements(wp, core, mg, dev, stream, mesh, pts, P, I, peak_gbs, rank
         out["build_ms_kernels"] = lib_build
         out["build_roofline"] = {"bound": "hbm", "algorithmic_bytes": 396 * T, "achieved": 396 * T / (lib_build * 1e-3) / 1e9,
                                  "peak": peak_gbs, "unit": "GB/s", "frac": 396 * T / (lib_build * 1e-3) / 1e9 / peak_gbs}  # fmt: skip
+    # signed closest point (mesh_query_point: + three axis-probe traversals per query) on 2 M of the C2 queries
+    try:
+        ns = 1 << 21
+        qs = wp.array(mg.box_queries(P, ns, seed=2), dtype=wp.vec3, device=dev)
+        s_out = wp.MeshQueryPoint(*(wp.empty(ns, dt, dev) for dt in (wp.uint8, wp.float32, wp.int32, wp.float32, wp.float32)))
+        run_s = lambda: wp.mesh_query_point(mesh, qs, MAX_DIST, out=s_out)  # noqa: E731
+        run_s()
+        ms = statistics.median([event_ms(core, run_s, stream) for _ in range(3)])
+        out["signed"] = {"workload": "C2 mesh, 2 097 152 mesh_query_point (signed) queries", "queries_per_s": ns / (ms * 1e-3),
+                         "ms": ms, "inside_fraction": float((s_out.sign.numpy() < 0).mean())}  # fmt: skip
+    except Exception as e:
+        out["signed"] = {"error": repr(e)}
     # rays: config C3 (10M-triangle heightfield, 4096 x 4096 primary rays)
     try:
         Ph, Ih = mg.heightfield(2237, 4)

@@ -1,0 +1,18 @@
+#!/bin/bash
+# round profiles: launch list of the bench command + ncu --set full of the dominant kernels
+mkdir -p gpurun_out
+R=${ROUND:-r01}
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${R}_launches_bench.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${R}_bench_under_ncu.json 2> gpurun_out/${R}_bench_under_ncu.err
+echo "launch list exit $?"
+# the query kernel at full bench size (one launch), build + refit kernels at C2 size
+export PROF_NQ=$((1<<24))
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'k_query_point' -s 1 -c 1 -f -o gpurun_out/${R}_query_point python scripts/prof_driver.py > gpurun_out/${R}_prof_q.log 2>&1
+echo "query exit $?"
+export PROF_NQ=$((1<<20))
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'k_scene|k_morton|k_onesweep|k_leaves|k_merge|k_refit|k_deep|k_query_ray' -s 12 -c 16 -f -o gpurun_out/${R}_build_refit python scripts/prof_driver.py > gpurun_out/${R}_prof_b.log 2>&1
+echo "build exit $?"
+for f in ${R}_query_point ${R}_build_refit; do
+  ncu -i gpurun_out/$f.ncu-rep --page raw --csv > gpurun_out/$f.raw.csv 2>/dev/null
+done
+ls -la gpurun_out | tail -12

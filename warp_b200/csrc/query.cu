@@ -323,14 +323,31 @@ __device__ __forceinline__ bool closest_point(const TreeView& tv, const TreeHead
     return false;
 }
 
+// robust slab test specialised for the probe direction e_axis (intersect.h:158-181 with dir = unit axis):
+// the two other axes only ask "is the origin inside the slab", and on the probe axis rcp_dir = 1/1 = 1, so
+// (bound - origin) * rcp_dir == bound - origin exactly.  Same value of `t`, same hit decision, fewer instructions.
+__device__ __forceinline__ bool ray_aabb_axis(float oa, float o1, float o2, int axis, int a1, int a2, float3 lo, float3 hi,
+                                              float& t)
+{
+    if (o1 < wb_get(lo, a1) || o1 > wb_get(hi, a1) || o2 < wb_get(lo, a2) || o2 > wb_get(hi, a2))
+        return false;
+    const float l1 = wb_get(lo, axis) - oa, l2 = wb_get(hi, axis) - oa;
+    const float lmin = fmaxf(fminf(l1, l2), -FLT_MAX), lmax = fminf(fmaxf(l1, l2), FLT_MAX);
+    const bool hit = (lmax >= 0.f) & (lmax >= lmin);
+    if (hit)
+        t = lmin;
+    return hit;
+}
+
 // sign of the closest hit along an axis probe, push-both order (mesh.h:2286-2339)
 template <bool COUNT>
 __device__ __forceinline__ bool probe_sign(const TreeView& tv, const TreeHeader& h, float3 org, int axis, float& out_sign,
                                            Counters& cnt)
 {
     const float3 dir = make_float3(axis == 0 ? 1.f : 0.f, axis == 1 ? 1.f : 0.f, axis == 2 ? 1.f : 0.f);
-    const float3 rcp = make_float3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
     const WoopRay wr = woop_setup(dir);
+    const int a1 = axis == 0 ? 1 : 0, a2 = axis == 2 ? 1 : 2;  // the two axes the probe is parallel to
+    const float oa = wb_get(org, axis), o1 = wb_get(org, a1), o2 = wb_get(org, a2);
 
     Entry stack[WB_QUERY_STACK];
     float stack_t[WB_QUERY_STACK];
@@ -340,7 +357,7 @@ __device__ __forceinline__ bool probe_sign(const TreeView& tv, const TreeHeader&
 
     {
         float tt;
-        if (ray_aabb_robust(org, dir, rcp, make_float3(h.lx, h.ly, h.lz), make_float3(h.hx, h.hy, h.hz), tt)) {
+        if (ray_aabb_axis(oa, o1, o2, axis, a1, a2, make_float3(h.lx, h.ly, h.lz), make_float3(h.hx, h.hy, h.hz), tt)) {
             if (h.root_ref & WB_LEAF)
                 stack[0].a = WB_LEAF | 0u, stack[0].b = h.root_count;
             else
@@ -374,12 +391,12 @@ __device__ __forceinline__ bool probe_sign(const TreeView& tv, const TreeHeader&
             if (COUNT)
                 cnt.pairs++;
             float tl, tr;
-            if (ray_aabb_robust(org, dir, rcp, pr.llo, pr.lhi, tl)) {
+            if (ray_aabb_axis(oa, o1, o2, axis, a1, a2, pr.llo, pr.lhi, tl)) {
                 stack[top] = pr.left;
                 stack_t[top] = tl;
                 ++top;
             }
-            if (ray_aabb_robust(org, dir, rcp, pr.rlo, pr.rhi, tr)) {
+            if (ray_aabb_axis(oa, o1, o2, axis, a1, a2, pr.rlo, pr.rhi, tr)) {
                 stack[top] = pr.right;
                 stack_t[top] = tr;
                 ++top;
