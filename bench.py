@@ -349,7 +349,9 @@ def main():
                    "l2": "256 MB memset between timed steps; query inputs (201 MB) + outputs (218 MB) exceed the 126 MB L2; "
                          "the tree is meant to stay L2-resident",
                    "gather": "ncclAllGather of result/face/u/v inside the step" if comm else "none (1 GPU)"},
-        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": args.steps * 1, "roofline": roofline,
+        "clocks": clocks.summary(), "e2e": e2e,
+        # per step: Morton ordering of the batch (k_scene_bounds, k_morton_hist, 4 x k_onesweep_pass) + k_query_point
+        "gpu_launches": args.steps * 7, "roofline": roofline,
         "wall_ms_timed_region": wall_ms, "extra": extra,
     }  # fmt: skip
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -90,7 +90,8 @@ typedef struct {
  * ------------------------------------------------------------------------------------------- */
 
 /* replaces warp/native/bvh.cu:852-875 (decl. warp.h:99-101).  Only constructor_type LBVH builds on
- * the GPU; SAH / MEDIAN / CUBQL return 0 with an error string (this library has no CPU builder). */
+ * the GPU; SAH / MEDIAN / CUBQL return 0 with an error string (this library has no CPU builder).
+ * `groups` (optional, one int per item) builds a grouped tree: no subtree mixes groups until a group is complete. */
 WP_B200_API uint64_t wp_bvh_create_device(void* context, wp_vec3* lowers, wp_vec3* uppers, int num_items,
                                           int constructor_type, int* groups, int leaf_size);
 /* replaces bvh.cu:878-888 (warp.h:102) */
@@ -176,6 +177,13 @@ WP_B200_API int wp_b200_mesh_query_ray_host(uint64_t id, const float* starts, co
                                             float max_t, uint8_t* result, float* sign, int32_t* face, float* t,
                                             float* u, float* v, float* normal);
 
+/* Morton resolution of trees created AFTER the call: 30 (default; the reference's 1024^3 grid, the only
+ * mode with bit-exact parity) or 63 (2 097 152^3 grid, 64-bit keys: a tree-quality option for meshes with
+ * far more than 2^20 occupied cells, where the 30-bit code degenerates into long runs of equal keys).
+ * Grouped trees always use 64-bit keys (group << 32 | 30-bit code, bvh.cu:205-209). */
+WP_B200_API void wp_b200_set_morton_bits(int bits);
+WP_B200_API int wp_b200_get_morton_bits(void);
+
 /* thread-to-query assignment of the point queries: 0 = input order, 1 = Morton order of the batch
  * (sorted on the device with the builder's radix sort; answers are unaffected), 2 = auto (default):
  * Morton order for batches of >= 32768 points. */
@@ -194,17 +202,17 @@ WP_B200_API int wp_b200_mesh_rebuild_device(uint64_t id);
 
 /* introspection for parity checks / drop-in kernels */
 typedef struct {
-    int num_items, leaf_size, max_nodes, root, height, deep;
+    int num_items, leaf_size, max_nodes, root, height, deep, key_bits;
     float total_lower[3], total_upper[3], inv_edges[3];
 } wp_b200_bvh_info_t;
 WP_B200_API int wp_b200_bvh_info(uint64_t id, wp_b200_bvh_info_t* info); /* synchronises the stream */
 /* (re)materialise node_lowers / node_uppers / node_parents / root of the descriptor at `id` in the
  * reference's layout (bvh.h:161-207) from the native pair layout.  Works for Bvh and Mesh ids. */
 WP_B200_API int wp_b200_bvh_sync_reference_layout(uint64_t id);
-/* host copies of the tree products (any pointer may be NULL): sorted 32-bit Morton keys [n],
+/* host copies of the tree products (any pointer may be NULL): sorted keys [n] (key_bits / 8 bytes each),
  * primitive_indices [n], node_lowers / node_uppers [2n-1] x 16 bytes, node_parents [2n-1], root [1].
  * Calls wp_b200_bvh_sync_reference_layout first and synchronises. */
-WP_B200_API int wp_b200_bvh_download(uint64_t id, uint32_t* keys, int32_t* primitive_indices, void* node_lowers,
+WP_B200_API int wp_b200_bvh_download(uint64_t id, void* keys, int32_t* primitive_indices, void* node_lowers,
                                      void* node_uppers, int32_t* node_parents, int32_t* root);
 
 /* ---------------------------------------------------------------------------------------------

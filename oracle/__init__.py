@@ -110,7 +110,7 @@ def morton3(x, y, z) -> int:
     return int(orc().orc_morton3_1024(x, y, z))
 
 
-def lbvh_build(lowers, uppers, leaf_size=1, groups=None):
+def lbvh_build(lowers, uppers, leaf_size=1, groups=None, morton_bits=30):
     """Reference-layout LBVH over item boxes (restates bvh.cu:515-613).  Returns a dict of arrays."""
     lowers = _f32(lowers, (-1, 3))
     uppers = _f32(uppers, (-1, 3))
@@ -132,7 +132,7 @@ def lbvh_build(lowers, uppers, leaf_size=1, groups=None):
     g = _i32(groups) if groups is not None else None
     orc().orc_lbvh_build(
         _p(lowers, _f32p), _p(uppers, _f32p), ctypes.c_int(n), _p(g, _i32p), ctypes.c_int(leaf_size),
-        _p(out["keys"], _u64p), _p(out["primitive_indices"], _i32p),
+        ctypes.c_int(morton_bits), _p(out["keys"], _u64p), _p(out["primitive_indices"], _i32p),
         out["node_lowers"].ctypes.data_as(ctypes.c_void_p), out["node_uppers"].ctypes.data_as(ctypes.c_void_p),
         _p(out["parents"], _i32p), ctypes.byref(root),
         _p(out["total_lower"], _f32p), _p(out["total_upper"], _f32p), _p(out["inv_edges"], _f32p),
@@ -153,9 +153,9 @@ def lbvh_refit(tree, lowers, uppers):
     return tree
 
 
-def mesh_lbvh_build(points, indices, leaf_size=4, groups=None):
+def mesh_lbvh_build(points, indices, leaf_size=4, groups=None, morton_bits=30):
     lo, hi = triangle_bounds(points, indices)
-    t = lbvh_build(lo, hi, leaf_size, groups)
+    t = lbvh_build(lo, hi, leaf_size, groups, morton_bits)
     t["item_lowers"], t["item_uppers"] = lo, hi
     return t
 

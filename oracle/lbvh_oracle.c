@@ -123,9 +123,35 @@ uint32_t orc_morton3_1024(float x, float y, float z)
     return (spread3(quant1024(z)) << 2) | (spread3(quant1024(y)) << 1) | spread3(quant1024(x));
 }
 
-/* key = group << 32 | morton(centroid) -- bvh.cu:184-214 */
+/* 21 bits per axis on a 2 097 152^3 grid: the quality option of the B200 builder (no reference counterpart;
+ * same centroid / scale arithmetic as bvh.cu:198-207, only the quantisation and interleave are wider) */
+static inline uint64_t spread3_21(uint64_t v)
+{
+    v &= 0x1fffffull;
+    v = (v | (v << 32)) & 0x1f00000000ffffull;
+    v = (v | (v << 16)) & 0x1f0000ff0000ffull;
+    v = (v | (v << 8)) & 0x100f00f00f00f00full;
+    v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+}
+static inline uint64_t quant2m(float x)
+{
+    int q = (int)(x * 2097152.0f);
+    if (q < 0)
+        q = 0;
+    if (q > 2097151)
+        q = 2097151;
+    return (uint64_t)q;
+}
+uint64_t orc_morton3_63(float x, float y, float z)
+{
+    return (spread3_21(quant2m(z)) << 2) | (spread3_21(quant2m(y)) << 1) | spread3_21(quant2m(x));
+}
+
+/* key = group << 32 | morton(centroid) -- bvh.cu:184-214; morton_bits 63 selects the wide code (ungrouped only) */
 void orc_morton_keys(const float* lowers, const float* uppers, int n, const float* grid_lower, const float* inv_edges,
-                     const int* groups, uint64_t* keys)
+                     const int* groups, int morton_bits, uint64_t* keys)
 {
     for (int i = 0; i < n; ++i) {
         v3 lo = v3_ld(lowers, i), hi = v3_ld(uppers, i);
@@ -134,7 +160,10 @@ void orc_morton_keys(const float* lowers, const float* uppers, int n, const floa
         float ly = (cy - grid_lower[1]) * inv_edges[1];
         float lz = (cz - grid_lower[2]) * inv_edges[2];
         uint64_t g = groups ? (uint64_t)(uint32_t)groups[i] : 0u;
-        keys[i] = (g << 32) | (uint64_t)orc_morton3_1024(lx, ly, lz);
+        if (morton_bits == 63)
+            keys[i] = orc_morton3_63(lx, ly, lz);
+        else
+            keys[i] = (g << 32) | (uint64_t)orc_morton3_1024(lx, ly, lz);
     }
 }
 
@@ -189,7 +218,7 @@ static inline int clz64(uint64_t x) { return x ? __builtin_clzll(x) : 64; }
  * a node's parent is a function of its key range only.
  */
 void orc_lbvh_build(const float* item_lowers, const float* item_uppers, int n, const int* groups, int leaf_size,
-                    uint64_t* keys, int* primitive_indices, orc_half* node_lowers, orc_half* node_uppers,
+                    int morton_bits, uint64_t* keys, int* primitive_indices, orc_half* node_lowers, orc_half* node_uppers,
                     int* parents, int* root, float* total_lower, float* total_upper, float* inv_edges)
 {
     if (n <= 0)
@@ -204,7 +233,8 @@ void orc_lbvh_build(const float* item_lowers, const float* item_uppers, int n, c
     if (inv_edges)
         memcpy(inv_edges, inv, sizeof(inv));
 
-    orc_morton_keys(item_lowers, item_uppers, n, tl, inv, groups, keys);
+    orc_morton_keys(item_lowers, item_uppers, n, tl, inv, groups, morton_bits, keys);
+    const int grouped = groups != NULL; /* without groups the group rule is vacuous for 30-bit keys and must be off for 63-bit ones */
     for (int i = 0; i < n; ++i)
         primitive_indices[i] = i;
     orc_sort_pairs(keys, primitive_indices, n);
@@ -244,7 +274,7 @@ void orc_lbvh_build(const float* item_lowers, const float* item_uppers, int n, c
                 int decided = 0;
                 go_right = 0;
                 const uint32_t gl = (uint32_t)(keys[left] >> 32), gr = (uint32_t)(keys[right] >> 32);
-                if (gl == gr) { /* stay inside the group when exactly one neighbour allows it */
+                if (grouped && gl == gr) { /* stay inside the group when exactly one neighbour allows it */
                     const int right_same = (right < n - 1) && ((uint32_t)(keys[right + 1] >> 32) == gl);
                     const int left_same = ((uint32_t)(keys[left - 1] >> 32) == gl);
                     if (right_same != left_same) {
@@ -298,7 +328,7 @@ void orc_lbvh_build(const float* item_lowers, const float* item_uppers, int n, c
         for (int p = parents[node]; p != -1; p = parents[p])
             depth++;
         const int left = range_l[node], right = range_r[node] + 1;
-        const int single_group = (keys[left] >> 32) == (keys[right - 1] >> 32);
+        const int single_group = !grouped || (keys[left] >> 32) == (keys[right - 1] >> 32);
         if (single_group && (right - left <= leaf_size || depth >= ORC_STACK)) {
             node_lowers[node].ib = 0x80000000u | (uint32_t)left;
             node_uppers[node].ib = (node_uppers[node].ib & 0x80000000u) | (uint32_t)right;

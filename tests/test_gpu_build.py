@@ -230,3 +230,77 @@ def test_c3_heightfield_10m_build_bit_exact(wp, oracle_mod):
     for name in ("node_lowers", "node_uppers"):
         for f in "xyz":
             assert np.array_equal(got[name][f][vis], want[name][f][vis]), (name, f)
+
+
+def test_grouped_bvh_build_bit_exact(wp, oracle_mod):
+    """Grouped trees (key = group << 32 | code, group-aware parent choice, no packed leaf across groups:
+    bvh.cu:205-209, 296-321, 431-437) against the oracle; procedure of warp/tests/geometry/test_grouped_bvh.py."""
+    rng = np.random.default_rng(7)
+    for n, ngroups, leaf in ((64, 4, 1), (1000, 7, 4), (5000, 3, 2), (300, 300, 4)):
+        lo, hi = random_boxes(n, seed=n + 1)
+        groups = rng.integers(0, ngroups, n).astype(np.int32)
+        b = wp.Bvh(wp.array(lo, dtype=wp.vec3), wp.array(hi, dtype=wp.vec3), groups=wp.array(groups, dtype=wp.int32), leaf_size=leaf)
+        got = b.download_tree()
+        assert got["key_bits"] == 64
+        want = oracle_mod.lbvh_build(lo, hi, leaf, groups=groups)
+        assert_tree_equal(got, want)
+        # every visible leaf holds items of a single group
+        for c in visible_nodes(got):
+            if got["node_lowers"]["ib"][c] >> 31:
+                s, e = int(got["node_lowers"]["ib"][c] & 0x7FFFFFFF), int(got["node_uppers"]["ib"][c] & 0x7FFFFFFF)
+                assert len(set(groups[got["primitive_indices"][s:e]].tolist())) == 1
+        lo2, hi2 = lo + 1.0, hi + 2.0
+        b.lowers.assign(lo2), b.uppers.assign(hi2)
+        b.refit()
+        got = b.download_tree()
+        oracle_mod.lbvh_refit(want, lo2, hi2)
+        vis = visible_nodes(want)
+        for f in "xyz":
+            assert np.array_equal(got["node_lowers"][f][vis], want["node_lowers"][f][vis])
+            assert np.array_equal(got["node_uppers"][f][vis], want["node_uppers"][f][vis])
+
+
+def test_grouped_mesh(wp, oracle_mod):
+    P, I = mg.noisy_sphere(4, 0.03, 2)
+    T = len(I) // 3
+    groups = (np.arange(T) * 5 // T).astype(np.int32)
+    m = wp.Mesh(wp.array(P, dtype=wp.vec3), wp.array(I, dtype=wp.int32), groups=wp.array(groups, dtype=wp.int32))
+    want = oracle_mod.mesh_lbvh_build(P, I, 4, groups=groups)
+    assert_tree_equal(m.download_tree(), want)
+    Q = mg.box_queries(P, 5000, seed=3)
+    got = wp.mesh_query_point(m, Q, 1e6).numpy()
+    ref = oracle_mod.query_point(P, I, want, Q, 1e6)
+    for k in ("result", "sign", "face", "u", "v"):
+        assert np.array_equal(got[k], ref[k]), k
+
+
+@pytest.mark.parametrize("name", ["ico5_noisy", "height65"])
+def test_morton63_quality_mode(wp, oracle_mod, name):
+    """63-bit Morton option (NOT a reference parity mode): same pipeline, wider keys; checked against the
+    oracle run with the same key width, and queries on it against the oracle traversal of that tree."""
+    P, I = MESHES[name]()
+    m = wp.Mesh(wp.array(P, dtype=wp.vec3), wp.array(I, dtype=wp.int32), morton_bits=63)
+    got = m.download_tree()
+    assert got["key_bits"] == 64
+    want = oracle_mod.mesh_lbvh_build(P, I, 4, morton_bits=63)
+    assert_tree_equal(got, want)
+    Q = mg.box_queries(P, 5000, seed=3)
+    a, b = wp.mesh_query_point_no_sign(m, Q, 1e6).numpy(), oracle_mod.query_point_no_sign(P, I, want, Q, 1e6)
+    for k in ("result", "face", "u", "v"):
+        assert np.array_equal(a[k], b[k]), k
+    m30 = wp.Mesh(wp.array(P, dtype=wp.vec3), wp.array(I, dtype=wp.int32))
+    assert m30.download_tree()["key_bits"] == 32  # the option does not leak into later trees
+
+
+def test_morton63_removes_duplicate_keys_on_10m_heightfield(wp):
+    P, I = mg.heightfield(2237, 4)
+    m = wp.Mesh(wp.array(P, dtype=wp.vec3), wp.array(I, dtype=wp.int32), morton_bits=63)
+    t = m.download_tree()
+    keys = t["keys"]
+    # what is left are the two triangles of a quad whose AABBs coincide (same box centre by construction): pairs, not runs
+    dup, run3 = (keys[1:] == keys[:-1]).mean(), (keys[2:] == keys[:-2]).mean()
+    assert dup < 0.3 and run3 < 0.05, (dup, run3)
+    t30 = wp.Mesh(m.points, m.indices).download_tree()
+    k30 = t30["keys"]
+    assert (k30[1:] == k30[:-1]).mean() > 0.6 and t30["height"] > t["height"]  # 30-bit keys: long runs, deeper tree
+    assert np.array_equal(np.sort(t["primitive_indices"]), np.arange(len(I) // 3))

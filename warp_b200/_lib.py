@@ -36,6 +36,7 @@ class bvh_info_t(ctypes.Structure):
         ("root", ctypes.c_int),
         ("height", ctypes.c_int),
         ("deep", ctypes.c_int),
+        ("key_bits", ctypes.c_int),
         ("total_lower", ctypes.c_float * 3),
         ("total_upper", ctypes.c_float * 3),
         ("inv_edges", ctypes.c_float * 3),
@@ -92,6 +93,8 @@ SIGNATURES = {
     "wp_b200_mesh_query_point_no_sign_host": (_i, [_u64, _vp, _i64, _f, _vp, _vp, _vp, _vp]),
     "wp_b200_mesh_query_point_host": (_i, [_u64, _vp, _i64, _f, _vp, _vp, _vp, _vp, _vp]),
     "wp_b200_mesh_query_ray_host": (_i, [_u64, _vp, _vp, _i64, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "wp_b200_set_morton_bits": (None, [_i]),
+    "wp_b200_get_morton_bits": (_i, []),
     "wp_b200_set_query_order": (None, [_i]),
     "wp_b200_get_query_order": (_i, []),
     "wp_b200_query_stats_enable": (None, [_i]),

@@ -26,6 +26,7 @@ std::map<uint64_t, MeshState*> g_meshes;
 cudaStream_t g_stream[64] = {};  // current stream per device (0 = legacy default stream)
 
 thread_local bool t_stats_enabled = false;
+int g_morton_bits = 30;         // Morton resolution of subsequently created trees: 30 (reference parity) or 63
 int g_query_order = 2;          // 0 input order, 1 Morton order, 2 auto (Morton for batches >= 32768 points)
 OrderScratch g_order[64][3];    // per device: [0] current-stream calls, [1], [2] the two host lanes
 unsigned long long* g_stats_dev = nullptr;
@@ -377,14 +378,11 @@ uint64_t wp_bvh_create_device(void* context, wp_vec3* lowers, wp_vec3* uppers, i
         set_error("Warp error: invalid BVH arguments (num_items=%d, leaf_size=%d)", num_items, leaf_size);
         return 0;
     }
-    if (groups) {
-        set_error("Warp error: grouped BVHs are not supported by the B200 LBVH builder yet");
-        return 0;
-    }
     const int dev = context_device(context);
     DeviceGuard g(dev);
     BvhState* s = new BvhState();
     s->n = num_items, s->leaf_size = leaf_size, s->constructor_type = constructor_type, s->device = dev;
+    s->key_bytes = (groups || g_morton_bits == 63) ? 8 : 4;
     s->item_lowers = (const float*)lowers, s->item_uppers = (const float*)uppers, s->groups = groups;
     const char* err = num_items > 0 ? wb_alloc_tree(*s, current_stream(dev)) : nullptr;
     if (!err)
@@ -455,10 +453,6 @@ uint64_t wp_mesh_create_device(void* context, wp_array_t points, wp_array_t velo
         set_error("Warp error: support_winding_number=True is out of scope for the B200 mesh path");
         return 0;
     }
-    if (groups) {
-        set_error("Warp error: grouped meshes are not supported by the B200 LBVH builder yet");
-        return 0;
-    }
     if (num_points < 0 || num_tris < 0 || bvh_leaf_size < 1 || (num_tris > 0 && (!points.data || !tris.data))) {
         set_error("Warp error: invalid mesh arguments (num_points=%d, num_tris=%d, leaf_size=%d)", num_points, num_tris,
                   bvh_leaf_size);
@@ -473,6 +467,8 @@ uint64_t wp_mesh_create_device(void* context, wp_array_t points, wp_array_t velo
     BvhState& s = m->bvh;
     s.n = num_tris, s.leaf_size = bvh_leaf_size, s.constructor_type = constructor_type, s.device = dev;
     s.is_mesh = true;
+    s.groups = groups;
+    s.key_bytes = (groups || g_morton_bits == 63) ? 8 : 4;
     s.points = (const float*)points.data, s.indices = (const int*)tris.data, s.num_points = num_points;
     const char* err = num_tris > 0 ? wb_alloc_tree(s, current_stream(dev)) : nullptr;
     if (!err)
@@ -587,6 +583,8 @@ void wp_mesh_set_velocities_device(uint64_t id, wp_array_t velocities)
 // ------------------------------------------------------------------------------------------------
 void wp_b200_query_stats_enable(int enable) { t_stats_enabled = enable != 0; }
 
+void wp_b200_set_morton_bits(int bits) { g_morton_bits = (bits == 63) ? 63 : 30; }
+int wp_b200_get_morton_bits(void) { return g_morton_bits; }
 void wp_b200_set_query_order(int mode) { g_query_order = mode; }
 int wp_b200_get_query_order(void) { return g_query_order; }
 
@@ -806,6 +804,7 @@ int wp_b200_bvh_info(uint64_t id, wp_b200_bvh_info_t* info)
         return 0;
     info->root = (int)(h.root_ref & WB_IDX_MASK);
     info->height = h.height, info->deep = h.deep;
+    info->key_bits = 8 * s->key_bytes;
     for (int k = 0; k < 3; ++k)
         info->total_lower[k] = h.total_lo[k], info->total_upper[k] = h.total_hi[k], info->inv_edges[k] = h.inv_edges[k];
     return 1;
@@ -831,7 +830,7 @@ int wp_b200_bvh_sync_reference_layout(uint64_t id)
     return 1;
 }
 
-int wp_b200_bvh_download(uint64_t id, uint32_t* keys, int32_t* primitive_indices, void* node_lowers, void* node_uppers,
+int wp_b200_bvh_download(uint64_t id, void* keys, int32_t* primitive_indices, void* node_lowers, void* node_uppers,
                          int32_t* node_parents, int32_t* root)
 {
     if (!wp_b200_bvh_sync_reference_layout(id))
@@ -844,7 +843,7 @@ int wp_b200_bvh_download(uint64_t id, uint32_t* keys, int32_t* primitive_indices
     const size_t n = (size_t)s->n, mx = 2 * n - 1;
     bool ok = check(cudaStreamSynchronize(st), "synchronize");
     if (keys)
-        ok = ok && check(cudaMemcpy(keys, s->keys, 4 * n, cudaMemcpyDeviceToHost), "download");
+        ok = ok && check(cudaMemcpy(keys, s->keys, (size_t)s->key_bytes * n, cudaMemcpyDeviceToHost), "download");
     if (primitive_indices)
         ok = ok && check(cudaMemcpy(primitive_indices, s->prim, 4 * n, cudaMemcpyDeviceToHost), "download");
     if (node_lowers)

@@ -1,17 +1,22 @@
-// LBVH construction for sm_100a: scene bounds -> 30-bit Morton keys + digit histograms ->
-// onesweep LSD radix sort of (key, item) -> bottom-up hierarchy emission directly into the
+// LBVH construction for sm_100a: scene bounds -> Morton keys + digit histograms -> onesweep LSD
+// radix sort of (key, item) -> leaf records -> chunked bottom-up merge directly into the
 // sibling-pair node layout (common.cuh) -> depth-rule fix-up -> (optional) export to the
 // reference's two-array layout.
 //
 // Behavioural contract = warp/native/bvh.cu:184-613 (reference LBVH): identical Morton keys,
 // identical sorted order (any stable sort), identical parent choice / tie break / packed-leaf
-// marking.  What differs is how the bytes move: 6 launches instead of ~20, 32-bit keys and 4 digit
-// passes instead of 64-bit keys and 8, no lowers/uppers round trip for meshes, no delta /
-// range / leaf-node passes (deltas are recomputed from the sorted keys, ranges travel in the
-// node records), height tracked in the arrival counters so the per-node depth walk of
+// marking.  What differs is how the bytes move: 9 launches instead of ~20, 32-bit keys and 4 digit
+// passes instead of 64-bit keys and 8 when there are no groups, no lowers/uppers round trip for
+// meshes, no delta / range passes (deltas are recomputed from the sorted keys, ranges travel in
+// the node records), height tracked in the arrival counters so the per-node depth walk of
 // mark_packed_leaf_nodes (bvh.cu:402-443) only runs for trees that are actually >= 32 deep.
+//
+// Key flavours (template KeyT / GROUPED, see merge.cuh): uint32 30-bit code (parity mode, default),
+// uint64 group<<32|code (grouped trees, bvh.cu:205-209), uint64 63-bit code (quality option for very
+// large meshes; NOT a parity mode -- the reference only ever produces the 30-bit code).
 #include "state.h"
 #include "merge.cuh"
+#include "order.h"
 
 #include <cub/device/device_radix_sort.cuh>  // WARP_B200_SORT=cub cross-check path only
 
@@ -21,6 +26,13 @@
 namespace {
 
 constexpr int BT = 256;  // threads per block for the streaming kernels
+
+#define WB_CUDA_TRY(expr)                  \
+    do {                                   \
+        cudaError_t _e = (expr);           \
+        if (_e != cudaSuccess)             \
+            return cudaGetErrorString(_e); \
+    } while (0)
 
 __global__ void k_iota(int* out, int n)
 {
@@ -81,9 +93,9 @@ k_scene_bounds(Src src, int n, float* __restrict__ partials, unsigned* __restric
     __shared__ float sm[BT / 32][6];
 
     if (blockIdx.x == 0) {
-        for (int k = threadIdx.x; k < 4 * 256; k += BT)
+        for (int k = threadIdx.x; k < 8 * 256; k += BT)
             ghist[k] = 0;
-        if (threadIdx.x < 8)
+        if (threadIdx.x < 16)
             tickets[threadIdx.x] = 0;  // per-pass tile tickets
     }
 
@@ -132,7 +144,7 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ partia
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2: Morton keys (bvh.h:257-275, bvh.cu:184-214) + the four 8-bit digit histograms of the sort
+// K2: Morton keys (bvh.h:257-275, bvh.cu:184-214) + the 8-bit digit histograms of the sort
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t spread3(uint32_t v)
 {
@@ -151,14 +163,37 @@ __device__ __forceinline__ uint32_t morton30(float x, float y, float z)
 {
     return (spread3(quant1024(z)) << 2) | (spread3(quant1024(y)) << 1) | spread3(quant1024(x));
 }
-
-// warp-aggregated shared-memory histogram increment (neighbouring items share high digits)
-__device__ __forceinline__ void hist_add(uint32_t* h, uint32_t d, bool valid)
+// 21 bits per axis (2 097 152^3 grid); same centroid / scale arithmetic as the 30-bit code
+__device__ __forceinline__ uint64_t spread3_21(uint64_t v)
 {
-    const uint32_t key = valid ? d : 0xffffffffu;
-    const uint32_t peers = __match_any_sync(0xffffffffu, key);
-    if (valid && (__ffs(peers) - 1) == (int)(threadIdx.x & 31))
-        atomicAdd(&h[d], (uint32_t)__popc(peers));
+    v &= 0x1fffffull;
+    v = (v | (v << 32)) & 0x1f00000000ffffull;
+    v = (v | (v << 16)) & 0x1f0000ff0000ffull;
+    v = (v | (v << 8)) & 0x100f00f00f00f00full;
+    v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+}
+__device__ __forceinline__ uint64_t quant2m(float x)
+{
+    const int q = (int)(x * 2097152.0f);
+    return (uint64_t)min(max(q, 0), 2097151);
+}
+__device__ __forceinline__ uint64_t morton63(float x, float y, float z)
+{
+    return (spread3_21(quant2m(z)) << 2) | (spread3_21(quant2m(y)) << 1) | spread3_21(quant2m(x));
+}
+
+template <class KeyT, bool GROUPED>
+__device__ __forceinline__ KeyT make_key(float x, float y, float z, const int* __restrict__ groups, int item)
+{
+    if constexpr (sizeof(KeyT) == 4) {
+        return morton30(x, y, z);
+    } else if constexpr (GROUPED) {
+        return ((uint64_t)(uint32_t)__ldg(groups + item) << 32) | (uint64_t)morton30(x, y, z);
+    } else {
+        return morton63(x, y, z);
+    }
 }
 
 // histogram increment for digits that neighbouring items mostly share: if every valid lane of the
@@ -178,14 +213,15 @@ __device__ __forceinline__ void hist_add_coherent(uint32_t* h, uint32_t d, bool 
     }
 }
 
-template <class Src>
+template <class Src, class KeyT, bool GROUPED>
 __global__ void __launch_bounds__(BT)
 k_morton_hist(Src src, int n, const float* __restrict__ partials, int num_partials, TreeHeader* __restrict__ hdr,
-              uint32_t* __restrict__ keys, uint32_t* __restrict__ ghist)
+              const int* __restrict__ groups, KeyT* __restrict__ keys, uint32_t* __restrict__ ghist)
 {
-    __shared__ uint32_t h[4 * 256];
+    constexpr int PASSES = sizeof(KeyT);
+    __shared__ uint32_t h[PASSES * 256];
     __shared__ float sm[BT / 32][6];
-    for (int k = threadIdx.x; k < 4 * 256; k += BT)
+    for (int k = threadIdx.x; k < PASSES * 256; k += BT)
         h[k] = 0;
 
     // scene bounds and 1 / (extent + 1e-4) (IEEE division, bvh.cu:482-488), recomputed by every block
@@ -206,24 +242,24 @@ k_morton_hist(Src src, int n, const float* __restrict__ partials, int num_partia
     for (int it = 0; it < iters; ++it) {
         const int i = it * stride + blockIdx.x * BT + threadIdx.x;
         const bool valid = i < n;
-        uint32_t code = 0;
+        KeyT code = 0;
         if (valid) {
             float3 lo, hi;
             src.bounds(i, lo, hi);
             const float cx = 0.5f * (lo.x + hi.x), cy = 0.5f * (lo.y + hi.y), cz = 0.5f * (lo.z + hi.z);
-            code = morton30((cx - glx) * ivx, (cy - gly) * ivy, (cz - glz) * ivz);
+            code = make_key<KeyT, GROUPED>((cx - glx) * ivx, (cy - gly) * ivy, (cz - glz) * ivz, groups, i);
             keys[i] = code;
         }
-        // low digit: essentially random across a warp -> plain shared atomics; the three high digits are
+        // low digit: essentially random across a warp -> plain shared atomics; the higher digits are
         // usually identical across a warp of neighbouring items -> one add per warp when they are
         if (valid)
-            atomicAdd(&h[code & 255u], 1u);
-        hist_add_coherent(h + 256, (code >> 8) & 255u, valid);
-        hist_add_coherent(h + 512, (code >> 16) & 255u, valid);
-        hist_add_coherent(h + 768, (code >> 24) & 255u, valid);
+            atomicAdd(&h[(uint32_t)code & 255u], 1u);
+#pragma unroll
+        for (int p = 1; p < PASSES; ++p)
+            hist_add_coherent(h + 256 * p, (uint32_t)(code >> (8 * p)) & 255u, valid);
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < 4 * 256; k += BT)
+    for (int k = threadIdx.x; k < PASSES * 256; k += BT)
         if (h[k])
             atomicAdd(&ghist[k], h[k]);
 }
@@ -237,24 +273,27 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ITEMS_LARGE = 16;  // 4096-key tiles: fewer look-back words for big inputs
 constexpr int RS_ITEMS_SMALL = 8;   // 2048-key tiles: more resident warps while the input is small enough to be latency bound
 constexpr long long RS_SMALL_LIMIT = 1ll << 24;
-__host__ __device__ inline int rs_items_for(long long n) { return n < RS_SMALL_LIMIT ? RS_ITEMS_SMALL : RS_ITEMS_LARGE; }
-__host__ __device__ inline int rs_tile_for(long long n) { return RS_THREADS * rs_items_for(n); }
+// 64-bit keys always use the small tile (a 4096-key tile of 8-byte keys would not fit 48 KB of static shared memory)
+__host__ __device__ inline int rs_items_for(long long n, int key_bytes = 4)
+{
+    return (n < RS_SMALL_LIMIT || key_bytes == 8) ? RS_ITEMS_SMALL : RS_ITEMS_LARGE;
+}
+__host__ __device__ inline int rs_tile_for(long long n, int key_bytes = 4) { return RS_THREADS * rs_items_for(n, key_bytes); }
 #define RS_FLAG_AGG (1u << 30)
 #define RS_FLAG_INC (2u << 30)
 #define RS_VAL_MASK ((1u << 30) - 1u)
 
-template <bool IMPLICIT_VALS, int ITEMS>
+template <bool IMPLICIT_VALS, int ITEMS, class KeyT>
 __global__ void __launch_bounds__(RS_THREADS)
-k_onesweep_pass(const uint32_t* __restrict__ keys_in, const int* __restrict__ vals_in,
-                uint32_t* __restrict__ keys_out, int* __restrict__ vals_out, int n, int shift,
-                const uint32_t* __restrict__ ghist_pass, volatile uint32_t* __restrict__ tile_status,
-                unsigned* __restrict__ tile_ticket)
+k_onesweep_pass(const KeyT* __restrict__ keys_in, const int* __restrict__ vals_in, KeyT* __restrict__ keys_out,
+                int* __restrict__ vals_out, int n, int shift, const uint32_t* __restrict__ ghist_pass,
+                volatile uint32_t* __restrict__ tile_status, unsigned* __restrict__ tile_ticket)
 {
     constexpr int TILE = RS_THREADS * ITEMS;
     __shared__ uint32_t warp_hist[RS_WARPS][257];  // bin 256 collects out-of-range lanes
-    __shared__ uint32_t s_keys[TILE];
+    __shared__ KeyT s_keys[TILE];
     __shared__ int s_vals[TILE];
-    __shared__ int s_delta[256];       // global position = s_delta[digit] + position in tile
+    __shared__ int s_delta[256];  // global position = s_delta[digit] + position in tile
     __shared__ uint32_t s_scan[RS_WARPS];
     __shared__ uint32_t s_scan2[RS_WARPS];
     __shared__ int s_tile;
@@ -270,7 +309,7 @@ k_onesweep_pass(const uint32_t* __restrict__ keys_in, const int* __restrict__ va
     const int tile_count = min(TILE, n - tile_base);
 
     // -- load (warp-striped: item k of lane l sits at warp_base + 32k + l, so rank order = memory order)
-    uint32_t key[ITEMS];
+    KeyT key[ITEMS];
     int val[ITEMS];
     uint32_t rank[ITEMS];
     const int warp_base = tile_base + warp * (32 * ITEMS);
@@ -278,7 +317,7 @@ k_onesweep_pass(const uint32_t* __restrict__ keys_in, const int* __restrict__ va
     for (int k = 0; k < ITEMS; ++k) {
         const int idx = warp_base + 32 * k + lane;
         const bool valid = idx < n;
-        key[k] = valid ? keys_in[idx] : 0xffffffffu;
+        key[k] = valid ? keys_in[idx] : (KeyT)~(KeyT)0;
         val[k] = IMPLICIT_VALS ? idx : (valid ? vals_in[idx] : 0);
     }
 
@@ -288,7 +327,7 @@ k_onesweep_pass(const uint32_t* __restrict__ keys_in, const int* __restrict__ va
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const int idx = warp_base + 32 * k + lane;
-        const uint32_t d = (idx < n) ? ((key[k] >> shift) & 255u) : 256u;
+        const uint32_t d = (idx < n) ? ((uint32_t)(key[k] >> shift) & 255u) : 256u;
         const uint32_t peers = __match_any_sync(0xffffffffu, d);
         const uint32_t before = wh[d];
         __syncwarp();
@@ -371,7 +410,7 @@ k_onesweep_pass(const uint32_t* __restrict__ keys_in, const int* __restrict__ va
     for (int k = 0; k < ITEMS; ++k) {
         const int idx = warp_base + 32 * k + lane;
         if (idx < n) {
-            const uint32_t d = (key[k] >> shift) & 255u;
+            const uint32_t d = (uint32_t)(key[k] >> shift) & 255u;
             const uint32_t pos = wh[d] + rank[k];
             s_keys[pos] = key[k];
             s_vals[pos] = val[k];
@@ -381,39 +420,41 @@ k_onesweep_pass(const uint32_t* __restrict__ keys_in, const int* __restrict__ va
 
     // -- digit-contiguous global writes
     for (int j = tid; j < tile_count; j += RS_THREADS) {
-        const uint32_t kk = s_keys[j];
-        const int g = s_delta[(kk >> shift) & 255u] + j;
+        const KeyT kk = s_keys[j];
+        const int g = s_delta[(uint32_t)(kk >> shift) & 255u] + j;
         keys_out[g] = kk;
         vals_out[g] = s_vals[j];
     }
 }
 
-// four 8-bit passes over (keys, vals) <-> (keys_alt, vals_alt); an even pass count ends in (keys, vals).
-// Pass 0 reads `keys` only and uses the element index as the value.
-static void onesweep_sort(uint32_t* keys, uint32_t* keys_alt, int* vals, int* vals_alt, int n, const uint32_t* ghist,
-                          uint32_t* tile_status, unsigned* tickets, cudaStream_t stream)
+// sizeof(KeyT) 8-bit passes over (keys, vals) <-> (keys_alt, vals_alt); the pass count is even, so the
+// result ends in (keys, vals) and the buffers the descriptor points at never change (rebuild stays
+// capture safe).  Pass 0 reads `keys` only and uses the element index as the value.
+template <class KeyT>
+void onesweep_sort(KeyT* keys, KeyT* keys_alt, int* vals, int* vals_alt, int n, const uint32_t* ghist,
+                   uint32_t* tile_status, unsigned* tickets, cudaStream_t stream)
 {
-    const int items = rs_items_for(n);
+    const int items = rs_items_for(n, (int)sizeof(KeyT));
     const int tiles = wb_div_up(n, RS_THREADS * items);
-    for (int pass = 0; pass < 4; ++pass) {
+    for (int pass = 0; pass < (int)sizeof(KeyT); ++pass) {
         volatile uint32_t* status = tile_status + (size_t)pass * 256 * tiles;
         const bool fwd = (pass % 2) == 0;
-        const uint32_t* kin = fwd ? keys : keys_alt;
+        const KeyT* kin = fwd ? keys : keys_alt;
         const int* vin = fwd ? vals : vals_alt;
-        uint32_t* kout = fwd ? keys_alt : keys;
+        KeyT* kout = fwd ? keys_alt : keys;
         int* vout = fwd ? vals_alt : vals;
         const uint32_t* gh = ghist + 256 * pass;
-        unsigned* ticket = tickets + 1 + pass;
+        unsigned* ticket = tickets + pass;
         if (items == RS_ITEMS_SMALL) {
             if (pass == 0)
-                k_onesweep_pass<true, RS_ITEMS_SMALL><<<tiles, RS_THREADS, 0, stream>>>(kin, nullptr, kout, vout, n, 8 * pass, gh, status, ticket);
+                k_onesweep_pass<true, RS_ITEMS_SMALL, KeyT><<<tiles, RS_THREADS, 0, stream>>>(kin, nullptr, kout, vout, n, 8 * pass, gh, status, ticket);
             else
-                k_onesweep_pass<false, RS_ITEMS_SMALL><<<tiles, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, n, 8 * pass, gh, status, ticket);
-        } else {
+                k_onesweep_pass<false, RS_ITEMS_SMALL, KeyT><<<tiles, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, n, 8 * pass, gh, status, ticket);
+        } else if constexpr (sizeof(KeyT) == 4) {
             if (pass == 0)
-                k_onesweep_pass<true, RS_ITEMS_LARGE><<<tiles, RS_THREADS, 0, stream>>>(kin, nullptr, kout, vout, n, 8 * pass, gh, status, ticket);
+                k_onesweep_pass<true, RS_ITEMS_LARGE, KeyT><<<tiles, RS_THREADS, 0, stream>>>(kin, nullptr, kout, vout, n, 8 * pass, gh, status, ticket);
             else
-                k_onesweep_pass<false, RS_ITEMS_LARGE><<<tiles, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, n, 8 * pass, gh, status, ticket);
+                k_onesweep_pass<false, RS_ITEMS_LARGE, KeyT><<<tiles, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, n, 8 * pass, gh, status, ticket);
         }
     }
 }
@@ -423,9 +464,9 @@ static void onesweep_sort(uint32_t* keys, uint32_t* keys_alt, int* vals, int* va
 // packed-triangle cache and write the leaf's node record straight into its parent's pair (which
 // pair is a function of the neighbouring keys only).  K4b (merge.cuh) then merges bottom-up.
 // ---------------------------------------------------------------------------------------------
-template <class Src>
+template <class Src, class KeyT, bool GROUPED>
 __global__ void __launch_bounds__(BT)
-k_leaves(Src src, int n, const uint32_t* __restrict__ keys, const int* __restrict__ prim, NodeRec* __restrict__ pairs,
+k_leaves(Src src, int n, const KeyT* __restrict__ keys, const int* __restrict__ prim, NodeRec* __restrict__ pairs,
          int* __restrict__ pos_parent, float4* __restrict__ tris)
 {
     const int i = blockIdx.x * BT + threadIdx.x;
@@ -451,15 +492,15 @@ k_leaves(Src src, int n, const uint32_t* __restrict__ keys, const int* __restric
         src.bounds(item, lo, hi);
     }
     pos_parent[i] = WB_NO_PARENT;
-    const bool go_right = wb_goes_right(keys, prim, n, i, i);
+    const bool go_right = wb_goes_right<KeyT, GROUPED>(keys, prim, n, i, i);
     NodeRec* rec = pairs + 2 * (size_t)(go_right ? i : i - 1) + (go_right ? 0 : 1);
     wb_store_rec(rec, lo, hi, (uint32_t)i | WB_LEAF, (uint32_t)i);  // a single item always fits leaf_size >= 1
 }
 
 // ---------------------------------------------------------------------------------------------
-// K5/K6: depth rule (bvh.cu:419-441): a node at depth >= 32 (root = 1) becomes a packed leaf
-// whatever its size.  Only trees taller than 30 edges can contain such a node; everything else
-// returns after one header read.
+// K5/K6: depth rule (bvh.cu:419-441): a single-group node at depth >= 32 (root = 1) becomes a
+// packed leaf whatever its size.  Only trees taller than 30 edges can contain such a node;
+// everything else returns after one header read.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int depth_capped(const int* __restrict__ parent_int, int n, int internal_node)
 {
@@ -473,9 +514,27 @@ __device__ __forceinline__ int depth_capped(const int* __restrict__ parent_int, 
     return depth;
 }
 
-// pass A (one thread per sorted position): visible leaves whose parent got muted lose their entry
+template <class KeyT, bool GROUPED>
+__device__ __forceinline__ bool node_single_group(const KeyT* __restrict__ keys, const NodeRec* __restrict__ pairs, int s)
+{
+    if (!GROUPED)
+        return true;
+    return wb_group_of(keys, (int)pairs[2 * (size_t)s].aux) == wb_group_of(keys, (int)pairs[2 * (size_t)s + 1].aux);
+}
+
+// marked by the depth rule: internal node n+s that is not a size leaf, single group, depth >= 32
+template <class KeyT, bool GROUPED>
+__device__ __forceinline__ bool depth_marked(const KeyT* __restrict__ keys, const NodeRec* __restrict__ pairs,
+                                             const int* __restrict__ parent_int, int n, int s)
+{
+    return node_single_group<KeyT, GROUPED>(keys, pairs, s) && depth_capped(parent_int, n, n + s) >= WB_MAX_DEPTH;
+}
+
+// pass A (one thread per sorted position): visible size-leaves whose parent got marked lose their entry
+template <class KeyT, bool GROUPED>
 __global__ void __launch_bounds__(BT)
-k_deep_fix_positions(int n, int leaf_size, TreeHeader* hdr, const int* __restrict__ parent_int, int* pos_parent)
+k_deep_fix_positions(int n, TreeHeader* hdr, const KeyT* __restrict__ keys, const NodeRec* __restrict__ pairs,
+                     const int* __restrict__ parent_int, int* pos_parent)
 {
     if (hdr->height + 1 < WB_MAX_DEPTH)
         return;
@@ -485,28 +544,30 @@ k_deep_fix_positions(int n, int leaf_size, TreeHeader* hdr, const int* __restric
     const int p = pos_parent[i];
     if (p < 0)
         return;
-    if (depth_capped(parent_int, n, p) >= WB_MAX_DEPTH)  // parent is itself a (possibly muted) depth leaf
+    if (depth_marked<KeyT, GROUPED>(keys, pairs, parent_int, n, p - n))
         pos_parent[i] = WB_NO_PARENT;
 }
 
-// pass B (one thread per internal node): nodes at depth exactly 32 become the visible leaves
+// pass B (one thread per internal node): depth-marked nodes whose parent is not marked become visible leaves
+template <class KeyT, bool GROUPED>
 __global__ void __launch_bounds__(BT)
-k_deep_fix_nodes(int n, int leaf_size, TreeHeader* hdr, const int* __restrict__ parent_int, NodeRec* pairs,
-                 int* pos_parent)
+k_deep_fix_nodes(int n, int leaf_size, TreeHeader* hdr, const KeyT* __restrict__ keys, const int* __restrict__ parent_int,
+                 NodeRec* pairs, int* pos_parent)
 {
     if (hdr->height + 1 < WB_MAX_DEPTH)
         return;
     const int s = blockIdx.x * BT + threadIdx.x;
     if (s >= n - 1)
         return;
-    const int node = n + s;
     const int left = (int)pairs[2 * (size_t)s].aux, right = (int)pairs[2 * (size_t)s + 1].aux;
-    if (right - left + 1 <= leaf_size)
+    if (wb_size_leaf<KeyT, GROUPED>(keys, leaf_size, left, right))
         return;  // already a leaf (or below one) by the size rule
-    if (depth_capped(parent_int, n, node) != WB_MAX_DEPTH)
+    if (!depth_marked<KeyT, GROUPED>(keys, pairs, parent_int, n, s))
         return;
-    const int parent = parent_int[s];  // depth 32 => has a parent at depth 31, which stays internal
+    const int parent = parent_int[s];  // depth >= 32 => it has a parent
     const int ps = parent - n;
+    if (depth_marked<KeyT, GROUPED>(keys, pairs, parent_int, n, ps))
+        return;  // muted below another depth leaf
     NodeRec* rec = pairs + 2 * (size_t)ps + (s < ps ? 0 : 1);
     rec->ref |= WB_LEAF;
     pos_parent[left] = parent;
@@ -522,9 +583,11 @@ struct RefHalf {
     uint32_t ib;
 };
 
+template <class KeyT, bool GROUPED>
 __global__ void __launch_bounds__(BT)
-k_export_reference_layout(int n, int leaf_size, const TreeHeader* __restrict__ hdr, const NodeRec* __restrict__ pairs,
-                          const int* __restrict__ parent_int, RefHalf* lowers, RefHalf* uppers, int* parents, int* root)
+k_export_reference_layout(int n, int leaf_size, const TreeHeader* __restrict__ hdr, const KeyT* __restrict__ keys,
+                          const NodeRec* __restrict__ pairs, const int* __restrict__ parent_int, RefHalf* lowers,
+                          RefHalf* uppers, int* parents, int* root)
 {
     const int c = blockIdx.x * BT + threadIdx.x;
     if (c >= 2 * n - 1)
@@ -551,9 +614,9 @@ k_export_reference_layout(int n, int leaf_size, const TreeHeader* __restrict__ h
     parents[cl] = c;
     parents[cr] = c;
     const int left = (int)L.aux, right = (int)R.aux;
-    bool leaf = (right - left + 1) <= leaf_size;
+    bool leaf = wb_size_leaf<KeyT, GROUPED>(keys, leaf_size, left, right);
     if (!leaf && hdr->height + 1 >= WB_MAX_DEPTH)
-        leaf = depth_capped(parent_int, n, c) >= WB_MAX_DEPTH;
+        leaf = depth_marked<KeyT, GROUPED>(keys, pairs, parent_int, n, s);
     if (leaf) {
         lowers[c].ib = WB_LEAF | (uint32_t)left;
         uppers[c].ib = (uint32_t)(right + 1);
@@ -564,9 +627,9 @@ k_export_reference_layout(int n, int leaf_size, const TreeHeader* __restrict__ h
 }
 
 // single item: the root is leaf 0 (bvh.cu:285-290 with n == 1)
-template <class Src>
-__global__ void k_single_item(Src src, int leaf_size, int* prim, uint32_t* keys, int* pos_parent, float4* tris,
-                              TreeHeader* hdr)
+template <class Src, class KeyT, bool GROUPED>
+__global__ void k_single_item(Src src, int leaf_size, const int* groups, int* prim, KeyT* keys, int* pos_parent,
+                              float4* tris, TreeHeader* hdr)
 {
     float3 lo, hi;
     src.bounds(0, lo, hi);
@@ -597,15 +660,9 @@ __global__ void k_single_item(Src src, int leaf_size, int* prim, uint32_t* keys,
     hdr->inv_edges[1] = 1.0f / ((hi.y - lo.y) + 0.0001f);
     hdr->inv_edges[2] = 1.0f / ((hi.z - lo.z) + 0.0001f);
     const float cx = 0.5f * (lo.x + hi.x), cy = 0.5f * (lo.y + hi.y), cz = 0.5f * (lo.z + hi.z);
-    keys[0] = morton30((cx - lo.x) * hdr->inv_edges[0], (cy - lo.y) * hdr->inv_edges[1], (cz - lo.z) * hdr->inv_edges[2]);
+    keys[0] = make_key<KeyT, GROUPED>((cx - lo.x) * hdr->inv_edges[0], (cy - lo.y) * hdr->inv_edges[1],
+                                      (cz - lo.z) * hdr->inv_edges[2], groups, 0);
 }
-
-#define WB_CUDA_TRY(expr)                     \
-    do {                                      \
-        cudaError_t _e = (expr);              \
-        if (_e != cudaSuccess)                \
-            return cudaGetErrorString(_e);    \
-    } while (0)
 
 bool use_cub_sort()
 {
@@ -613,11 +670,15 @@ bool use_cub_sort()
     return v && strcmp(v, "cub") == 0;
 }
 
-template <class Src> const char* build_impl(BvhState& s, Src src, cudaStream_t stream)
+template <class Src, class KeyT, bool GROUPED> const char* build_impl(BvhState& s, Src src, cudaStream_t stream)
 {
     const int n = s.n;
+    KeyT* keys = (KeyT*)s.keys;
+    KeyT* keys_alt = (KeyT*)s.keys_alt;
+    constexpr int PASSES = sizeof(KeyT);
     if (n == 1) {
-        k_single_item<<<1, 1, 0, stream>>>(src, s.leaf_size, s.prim, s.keys, s.pos_parent, s.tris, s.header);
+        k_single_item<Src, KeyT, GROUPED><<<1, 1, 0, stream>>>(src, s.leaf_size, s.groups, s.prim, keys, s.pos_parent,
+                                                               s.tris, s.header);
         WB_CUDA_TRY(cudaGetLastError());
         return nullptr;
     }
@@ -625,15 +686,16 @@ template <class Src> const char* build_impl(BvhState& s, Src src, cudaStream_t s
     // K1 scene bounds (+ clears histograms / tickets)
     k_scene_bounds<<<s.bounds_blocks, BT, 0, stream>>>(src, n, s.partials, s.tickets, s.ghist);
     // look-back words and arrival counters start from zero
-    WB_CUDA_TRY(cudaMemsetAsync(s.tile_status, 0, sizeof(uint32_t) * 256 * 4 * (size_t)s.num_tiles, stream));
+    WB_CUDA_TRY(cudaMemsetAsync(s.tile_status, 0, sizeof(uint32_t) * 256 * PASSES * (size_t)s.num_tiles, stream));
     WB_CUDA_TRY(cudaMemsetAsync(s.counters, 0, sizeof(unsigned) * (size_t)(n - 1), stream));
     // K2 Morton keys + histograms
-    k_morton_hist<<<s.bounds_blocks, BT, 0, stream>>>(src, n, s.partials, s.bounds_blocks, s.header, s.keys, s.ghist);
+    k_morton_hist<Src, KeyT, GROUPED><<<s.bounds_blocks, BT, 0, stream>>>(src, n, s.partials, s.bounds_blocks, s.header,
+                                                                         s.groups, keys, s.ghist);
 
     if (use_cub_sort()) {
-        // library cross-check path (tests only): stable LSD sort of bits [0, 32)
+        // library cross-check path (tests only): stable LSD sort over every key bit
         size_t need = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, need, s.keys, s.keys_alt, s.prim_alt, s.prim, n, 0, 32, stream);
+        cub::DeviceRadixSort::SortPairs(nullptr, need, keys, keys_alt, s.prim_alt, s.prim, n, 0, 8 * PASSES, stream);
         if (need > s.cub_temp_bytes) {
             if (s.cub_temp)
                 cudaFree(s.cub_temp);
@@ -641,35 +703,42 @@ template <class Src> const char* build_impl(BvhState& s, Src src, cudaStream_t s
             s.cub_temp_bytes = need;
         }
         k_iota<<<wb_div_up(n, BT), BT, 0, stream>>>(s.prim_alt, n);
-        WB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(s.cub_temp, need, s.keys, s.keys_alt, s.prim_alt, s.prim, n, 0, 32,
-                                                    stream));
-        WB_CUDA_TRY(cudaMemcpyAsync(s.keys, s.keys_alt, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
+        WB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(s.cub_temp, need, keys, keys_alt, s.prim_alt, s.prim, n, 0,
+                                                    8 * PASSES, stream));
+        WB_CUDA_TRY(cudaMemcpyAsync(keys, keys_alt, sizeof(KeyT) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
     } else {
-        // K3 x4, ping-pong (keys, prim) <-> (keys_alt, prim_alt); an even pass count ends in (keys, prim),
-        // so the buffers the descriptor points at never change (rebuild stays capture safe)
-        onesweep_sort(s.keys, s.keys_alt, s.prim, s.prim_alt, n, s.ghist, s.tile_status, s.tickets, stream);
+        // K3 x PASSES
+        onesweep_sort<KeyT>(keys, keys_alt, s.prim, s.prim_alt, n, s.ghist, s.tile_status, s.tickets, stream);
     }
 
     // K4a leaves, K4b chunked bottom-up merge
-    k_leaves<<<wb_div_up(n, BT), BT, 0, stream>>>(src, n, s.keys, s.prim, s.pairs, s.pos_parent, s.tris);
+    k_leaves<Src, KeyT, GROUPED><<<wb_div_up(n, BT), BT, 0, stream>>>(src, n, keys, s.prim, s.pairs, s.pos_parent, s.tris);
     {
-        const MergeArgs ma { n, s.leaf_size, s.keys, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters, s.header };
+        const MergeArgs<KeyT> ma { n, s.leaf_size, keys, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters, s.header };
         const int merge_threads = wb_div_up(n, MC);
-        k_merge<false><<<wb_div_up(merge_threads, 128), 128, 0, stream>>>(ma);
+        k_merge<false, KeyT, GROUPED><<<wb_div_up(merge_threads, 128), 128, 0, stream>>>(ma);
     }
     // K5/K6 depth rule (early-out unless the tree is at least 32 levels deep)
-    k_deep_fix_positions<<<wb_div_up(n, BT), BT, 0, stream>>>(n, s.leaf_size, s.header, s.parent_int, s.pos_parent);
-    k_deep_fix_nodes<<<wb_div_up(n - 1, BT), BT, 0, stream>>>(n, s.leaf_size, s.header, s.parent_int, s.pairs,
-                                                             s.pos_parent);
+    k_deep_fix_positions<KeyT, GROUPED><<<wb_div_up(n, BT), BT, 0, stream>>>(n, s.header, keys, s.pairs, s.parent_int,
+                                                                            s.pos_parent);
+    k_deep_fix_nodes<KeyT, GROUPED><<<wb_div_up(n - 1, BT), BT, 0, stream>>>(n, s.leaf_size, s.header, keys, s.parent_int,
+                                                                            s.pairs, s.pos_parent);
     WB_CUDA_TRY(cudaGetLastError());
     return nullptr;
 }
 
-}  // namespace
+template <class Src> const char* build_dispatch(BvhState& s, Src src, cudaStream_t stream)
+{
+    if (s.key_bytes == 4)
+        return build_impl<Src, uint32_t, false>(s, src, stream);
+    if (s.groups)
+        return build_impl<Src, uint64_t, true>(s, src, stream);
+    return build_impl<Src, uint64_t, false>(s, src, stream);
+}
 
 // one stream-ordered arena per tree: a single cudaMallocAsync from the device's default pool (kept
 // warm by an unlimited release threshold), carved into 256-byte aligned sub-buffers
-static bool pool_ready(int device)
+bool pool_ready(int device)
 {
     static bool done[64] = {};
     if (device < 0 || device >= 64)
@@ -686,7 +755,7 @@ static bool pool_ready(int device)
 }
 
 // streaming kernels K1/K2: four blocks per SM, each thread strides over ~n / (148*4*256) items
-static int bounds_grid(long long n)
+int bounds_grid(long long n)
 {
     static int sms = 0;
     if (!sms) {
@@ -698,11 +767,14 @@ static int bounds_grid(long long n)
     return (int)min((long long)sms * 4, max(1ll, (n + BT - 1) / BT));
 }
 
+}  // namespace
+
 const char* wb_alloc_tree(BvhState& s, cudaStream_t stream)
 {
     const size_t n = (size_t)s.n;
     const size_t ni = n > 1 ? n - 1 : 1;
-    s.num_tiles = wb_div_up((long long)n, rs_tile_for((long long)n));
+    const size_t kb = (size_t)s.key_bytes;
+    s.num_tiles = wb_div_up((long long)n, rs_tile_for((long long)n, s.key_bytes));
     s.bounds_blocks = bounds_grid((long long)n);
     size_t off = 0;
     auto take = [&off](size_t bytes) {
@@ -710,12 +782,12 @@ const char* wb_alloc_tree(BvhState& s, cudaStream_t stream)
         off += (bytes + 255) & ~(size_t)255;
         return at;
     };
-    const size_t o_header = take(sizeof(TreeHeader)), o_tickets = take(sizeof(unsigned) * 8),
-                 o_ghist = take(sizeof(uint32_t) * 4 * 256), o_partials = take(sizeof(float) * 6 * (size_t)s.bounds_blocks),
-                 o_keys = take(4 * n), o_keys_alt = take(4 * n), o_prim = take(4 * n), o_prim_alt = take(4 * n),
+    const size_t o_header = take(sizeof(TreeHeader)), o_tickets = take(sizeof(unsigned) * 16),
+                 o_ghist = take(sizeof(uint32_t) * 8 * 256), o_partials = take(sizeof(float) * 6 * (size_t)s.bounds_blocks),
+                 o_keys = take(kb * n), o_keys_alt = take(kb * n), o_prim = take(4 * n), o_prim_alt = take(4 * n),
                  o_pairs = take(sizeof(NodeRec) * 2 * ni), o_parent = take(4 * ni), o_pos = take(4 * n),
                  o_counters = take(4 * ni), o_tris = take(s.is_mesh ? sizeof(float4) * 3 * n : 0),
-                 o_status = take(sizeof(uint32_t) * 256 * 4 * (size_t)s.num_tiles);
+                 o_status = take(sizeof(uint32_t) * 256 * kb * (size_t)s.num_tiles);
     s.arena_bytes = off;
     s.arena_async = pool_ready(s.device);
     if (s.arena_async)
@@ -724,7 +796,7 @@ const char* wb_alloc_tree(BvhState& s, cudaStream_t stream)
         WB_CUDA_TRY(cudaMalloc(&s.arena, off));
     char* b = (char*)s.arena;
     s.header = (TreeHeader*)(b + o_header), s.tickets = (unsigned*)(b + o_tickets), s.ghist = (uint32_t*)(b + o_ghist);
-    s.partials = (float*)(b + o_partials), s.keys = (uint32_t*)(b + o_keys), s.keys_alt = (uint32_t*)(b + o_keys_alt);
+    s.partials = (float*)(b + o_partials), s.keys = b + o_keys, s.keys_alt = b + o_keys_alt;
     s.prim = (int*)(b + o_prim), s.prim_alt = (int*)(b + o_prim_alt), s.pairs = (NodeRec*)(b + o_pairs);
     s.parent_int = (int*)(b + o_parent), s.pos_parent = (int*)(b + o_pos), s.counters = (unsigned*)(b + o_counters);
     s.tris = s.is_mesh ? (float4*)(b + o_tris) : nullptr, s.tile_status = (uint32_t*)(b + o_status);
@@ -752,11 +824,9 @@ const char* wb_build(BvhState& s, cudaStream_t stream)
 {
     if (s.n <= 0)
         return nullptr;
-    if (s.groups)
-        return "grouped BVHs are not supported by the B200 LBVH builder yet";
     if (s.is_mesh)
-        return build_impl(s, MeshSource { s.points, s.indices }, stream);
-    return build_impl(s, BoxSource { s.item_lowers, s.item_uppers }, stream);
+        return build_dispatch(s, MeshSource { s.points, s.indices }, stream);
+    return build_dispatch(s, BoxSource { s.item_lowers, s.item_uppers }, stream);
 }
 
 const char* wb_export_reference_layout(BvhState& s, cudaStream_t stream)
@@ -773,9 +843,35 @@ const char* wb_export_reference_layout(BvhState& s, cudaStream_t stream)
     }
     WB_CUDA_TRY(cudaMemsetAsync(s.ref_lowers, 0, sizeof(RefHalf) * m, stream));
     WB_CUDA_TRY(cudaMemsetAsync(s.ref_uppers, 0, sizeof(RefHalf) * m, stream));
-    k_export_reference_layout<<<wb_div_up((long long)m, BT), BT, 0, stream>>>(
-        s.n, s.leaf_size, s.header, s.pairs, s.parent_int, (RefHalf*)s.ref_lowers, (RefHalf*)s.ref_uppers,
-        s.ref_parents, s.ref_root);
+    const int grid = wb_div_up((long long)m, BT);
+    RefHalf* lo = (RefHalf*)s.ref_lowers;
+    RefHalf* hi = (RefHalf*)s.ref_uppers;
+    if (s.key_bytes == 4)
+        k_export_reference_layout<uint32_t, false><<<grid, BT, 0, stream>>>(s.n, s.leaf_size, s.header, (const uint32_t*)s.keys,
+                                                                            s.pairs, s.parent_int, lo, hi, s.ref_parents, s.ref_root);
+    else if (s.groups)
+        k_export_reference_layout<uint64_t, true><<<grid, BT, 0, stream>>>(s.n, s.leaf_size, s.header, (const uint64_t*)s.keys,
+                                                                           s.pairs, s.parent_int, lo, hi, s.ref_parents, s.ref_root);
+    else
+        k_export_reference_layout<uint64_t, false><<<grid, BT, 0, stream>>>(s.n, s.leaf_size, s.header, (const uint64_t*)s.keys,
+                                                                            s.pairs, s.parent_int, lo, hi, s.ref_parents, s.ref_root);
+    WB_CUDA_TRY(cudaGetLastError());
+    return nullptr;
+}
+
+// the refit's merge pass lives here because it shares the key-typed instantiations
+const char* wb_refit_merge(BvhState& s, cudaStream_t stream)
+{
+    if (s.n <= 1)
+        return nullptr;
+    const int grid = wb_div_up(wb_div_up(s.n, MC), 128);
+    if (s.key_bytes == 4) {
+        const MergeArgs<uint32_t> ma { s.n, s.leaf_size, (const uint32_t*)s.keys, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters, s.header };
+        k_merge<true, uint32_t, false><<<grid, 128, 0, stream>>>(ma);
+    } else {
+        const MergeArgs<uint64_t> ma { s.n, s.leaf_size, (const uint64_t*)s.keys, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters, s.header };
+        k_merge<true, uint64_t, false><<<grid, 128, 0, stream>>>(ma);  // the static-tree replay never consults groups
+    }
     WB_CUDA_TRY(cudaGetLastError());
     return nullptr;
 }
@@ -783,8 +879,6 @@ const char* wb_export_reference_layout(BvhState& s, cudaStream_t stream)
 // ------------------------------------------------------------------------------------------------
 // Morton ordering of query points (order.h)
 // ------------------------------------------------------------------------------------------------
-#include "order.h"
-
 void wb_order_free(OrderScratch& ws)
 {
     void* ptrs[] = { ws.keys, ws.keys_alt, ws.idx, ws.idx_alt, ws.ghist, ws.tile_status, ws.tickets, ws.partials, ws.hdr };
@@ -808,10 +902,10 @@ const char* wb_morton_order(OrderScratch& ws, const float* pts, long long n, cud
         WB_CUDA_TRY(cudaMalloc(&ws.keys_alt, 4 * cap));
         WB_CUDA_TRY(cudaMalloc(&ws.idx, 4 * cap));
         WB_CUDA_TRY(cudaMalloc(&ws.idx_alt, 4 * cap));
-        WB_CUDA_TRY(cudaMalloc(&ws.ghist, 4 * 4 * 256));
+        WB_CUDA_TRY(cudaMalloc(&ws.ghist, 4 * 8 * 256));
         WB_CUDA_TRY(cudaMalloc(&ws.tile_status, 4 * 256 * 4 * tiles));
-        WB_CUDA_TRY(cudaMalloc(&ws.tickets, 4 * 8));
-        WB_CUDA_TRY(cudaMemset(ws.tickets, 0, 4 * 8));
+        WB_CUDA_TRY(cudaMalloc(&ws.tickets, 4 * 16));
+        WB_CUDA_TRY(cudaMemset(ws.tickets, 0, 4 * 16));
         WB_CUDA_TRY(cudaMalloc(&ws.partials, 4 * 6 * 4096));
         WB_CUDA_TRY(cudaMalloc(&ws.hdr, sizeof(TreeHeader)));
         ws.capacity = n;
@@ -822,8 +916,9 @@ const char* wb_morton_order(OrderScratch& ws, const float* pts, long long n, cud
     const BoxSource src { pts, pts };  // a point is its own (degenerate) box; its centroid is the point itself
     k_scene_bounds<<<blocks, BT, 0, stream>>>(src, ni, ws.partials, ws.tickets, ws.ghist);
     WB_CUDA_TRY(cudaMemsetAsync(ws.tile_status, 0, sizeof(uint32_t) * 256 * 4 * (size_t)tiles, stream));
-    k_morton_hist<<<blocks, BT, 0, stream>>>(src, ni, ws.partials, blocks, ws.hdr, ws.keys, ws.ghist);
-    onesweep_sort(ws.keys, ws.keys_alt, ws.idx, ws.idx_alt, ni, ws.ghist, ws.tile_status, ws.tickets, stream);
+    k_morton_hist<BoxSource, uint32_t, false><<<blocks, BT, 0, stream>>>(src, ni, ws.partials, blocks, ws.hdr, nullptr,
+                                                                         ws.keys, ws.ghist);
+    onesweep_sort<uint32_t>(ws.keys, ws.keys_alt, ws.idx, ws.idx_alt, ni, ws.ghist, ws.tile_status, ws.tickets, stream);
     WB_CUDA_TRY(cudaGetLastError());
     return nullptr;
 }

@@ -9,7 +9,7 @@
 // with one atomic arrival counter per internal node.  The counters are never cleared: they are
 // even after a build and every refit adds exactly 2, so "second to arrive" == odd old value.
 #include "state.h"
-#include "merge.cuh"
+#include "merge.cuh"  // wb_store_box
 
 namespace {
 
@@ -94,10 +94,6 @@ const char* wb_refit(BvhState& s, cudaStream_t stream)
     else
         k_refit_leaves<<<grid, BT, 0, stream>>>(BoxSource { s.item_lowers, s.item_uppers }, s.n, s.prim, s.pos_parent,
                                                 s.pairs, s.tris, s.header);
-    if (s.n > 1) {
-        const MergeArgs ma { s.n, s.leaf_size, s.keys, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters, s.header };
-        k_merge<true><<<wb_div_up(wb_div_up(s.n, MC), 128), 128, 0, stream>>>(ma);
-    }
     WB_CUDA_TRY(cudaGetLastError());
-    return nullptr;
+    return wb_refit_merge(s, stream);
 }

@@ -8,6 +8,9 @@
 // and no waiting.  Only nodes whose sibling is carried by another thread (chunk boundaries and
 // the spine above them) use the global arrival counter.  The parent of a node is a function of
 // its key range alone, so the tree is bit-identical to the reference's.
+//
+// Key flavours: uint32 = the reference's 30-bit Morton code (ungrouped parity mode);
+// uint64 + GROUPED = group << 32 | 30-bit code (bvh.cu:205-209); uint64 ungrouped = 63-bit code.
 #pragma once
 
 #include "common.cuh"
@@ -17,10 +20,10 @@
 #endif
 constexpr int MC = WB_MC;  // sorted positions per merge thread
 
-struct MergeArgs {
+template <class KeyT> struct MergeArgs {
     int n;
     int leaf_size;
-    const uint32_t* keys;
+    const KeyT* keys;
     const int* prim;
     NodeRec* pairs;
     int* parent_int;
@@ -29,20 +32,49 @@ struct MergeArgs {
     TreeHeader* hdr;
 };
 
-__device__ __forceinline__ int wb_key_delta(const uint32_t* __restrict__ keys, int i)
+__device__ __forceinline__ int wb_clz_key(uint32_t x) { return __clz((int)x); }
+__device__ __forceinline__ int wb_clz_key(uint64_t x) { return __clzll((long long)x); }
+
+// common-prefix length of keys i and i+1 (bvh.cu:218-226; equal keys give the full width, i.e. the
+// reference's 64; only comparisons between deltas of the same width are ever made)
+template <class KeyT> __device__ __forceinline__ int wb_key_delta(const KeyT* __restrict__ keys, int i)
 {
-    // common-prefix length of keys i and i+1 (bvh.cu:218-226 computes it on 64-bit keys: +32, and 64
-    // for equal keys; only comparisons between deltas are used, so the 32-bit form is equivalent)
-    return __clz((int)(__ldg(keys + i) ^ __ldg(keys + i + 1)));
+    return wb_clz_key((KeyT)(__ldg(keys + i) ^ __ldg(keys + i + 1)));
 }
 
-// parent choice of the node covering sorted positions [left, right] (bvh.cu:300-334, ungrouped):
+template <class KeyT> __device__ __forceinline__ uint32_t wb_group_of(const KeyT* __restrict__ keys, int i)
+{
+    return (uint32_t)((uint64_t)__ldg(keys + i) >> 32);
+}
+
+// packed-leaf eligibility by size: fits leaf_size and (grouped trees) does not straddle groups (bvh.cu:431-437)
+template <class KeyT, bool GROUPED>
+__device__ __forceinline__ bool wb_size_leaf(const KeyT* __restrict__ keys, int leaf_size, int left, int right)
+{
+    if (right - left + 1 > leaf_size)
+        return false;
+    if (GROUPED)
+        return wb_group_of(keys, left) == wb_group_of(keys, right);
+    return true;
+}
+
+// parent choice of the node covering sorted positions [left, right] (bvh.cu:300-334):
 // true = it becomes the LEFT child of node n+right, false = the RIGHT child of node n+left-1
-__device__ __forceinline__ bool wb_goes_right(const uint32_t* __restrict__ keys, const int* __restrict__ prim, int n,
+template <class KeyT, bool GROUPED>
+__device__ __forceinline__ bool wb_goes_right(const KeyT* __restrict__ keys, const int* __restrict__ prim, int n,
                                               int left, int right)
 {
     if (left == 0)
         return true;
+    if (GROUPED) {  // stay inside the group when exactly one neighbour allows it (bvh.cu:305-321)
+        const uint32_t gl = wb_group_of(keys, left), gr = wb_group_of(keys, right);
+        if (gl == gr) {
+            const bool right_same = (right < n - 1) && wb_group_of(keys, right + 1) == gl;
+            const bool left_same = wb_group_of(keys, left - 1) == gl;
+            if (right_same != left_same)
+                return right_same;
+        }
+    }
     if (right == n - 1)
         return false;
     const int dr = wb_key_delta(keys, right), dl = wb_key_delta(keys, left - 1);
@@ -64,9 +96,9 @@ __device__ __forceinline__ void wb_store_box(NodeRec* dst, float3 lo, float3 hi)
     dst->hx = hi.x, dst->hy = hi.y, dst->hz = hi.z;
 }
 
-template <bool REFIT>
+template <bool REFIT, class KeyT, bool GROUPED>
 __global__ void __launch_bounds__(128)
-k_merge(MergeArgs a)
+k_merge(MergeArgs<KeyT> a)
 {
     const int n = a.n;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -138,7 +170,7 @@ k_merge(MergeArgs a)
                 have = true, fresh = true;
             } else {
                 // next original leaf (its record was written by the leaf pass)
-                const bool gr = wb_goes_right(a.keys, a.prim, n, pos, pos);
+                const bool gr = wb_goes_right<KeyT, GROUPED>(a.keys, a.prim, n, pos, pos);
                 const NodeRec* rec = a.pairs + 2 * (size_t)(gr ? pos : pos - 1) + (gr ? 0 : 1);
                 xl = xr = pos;
                 lo = make_float3(rec->lx, rec->ly, rec->lz);
@@ -162,7 +194,8 @@ k_merge(MergeArgs a)
                 go_right = (xr == s);  // a left child's range ends at the split
             } else {
                 if (xl == 0 && xr == n - 1) {
-                    const uint32_t self_ref = xnode | ((xr - xl + 1) <= a.leaf_size ? WB_LEAF : 0u);
+                    const uint32_t self_ref =
+                        xnode | (wb_size_leaf<KeyT, GROUPED>(a.keys, a.leaf_size, xl, xr) ? WB_LEAF : 0u);
                     a.hdr->lx = lo.x, a.hdr->ly = lo.y, a.hdr->lz = lo.z;
                     a.hdr->hx = hi.x, a.hdr->hy = hi.y, a.hdr->hz = hi.z;
                     a.hdr->root_ref = self_ref;
@@ -176,7 +209,7 @@ k_merge(MergeArgs a)
                         a.pos_parent[0] = WB_ROOT_PARENT;
                     return;
                 }
-                go_right = wb_goes_right(a.keys, a.prim, n, xl, xr);
+                go_right = wb_goes_right<KeyT, GROUPED>(a.keys, a.prim, n, xl, xr);
                 s = go_right ? xr : xl - 1;
                 if (xnode >= (uint32_t)n)
                     a.parent_int[xnode - n] = n + s;
@@ -187,7 +220,8 @@ k_merge(MergeArgs a)
                 if (REFIT)
                     wb_store_box(mine, lo, hi);
                 else
-                    wb_store_rec(mine, lo, hi, xnode | ((xr - xl + 1) <= a.leaf_size ? WB_LEAF : 0u),
+                    wb_store_rec(mine, lo, hi,
+                                 xnode | (wb_size_leaf<KeyT, GROUPED>(a.keys, a.leaf_size, xl, xr) ? WB_LEAF : 0u),
                                  (uint32_t)(go_right ? xl : xr));
             }
 
@@ -230,11 +264,11 @@ k_merge(MergeArgs a)
         const int new_left = go_right ? xl : far_end;
         const int new_right = go_right ? far_end : xr;
         if (!REFIT) {
-            const int lsize = s - new_left + 1, rsize = new_right - s;
-            if (new_right - new_left + 1 > a.leaf_size) {
-                if (lsize <= a.leaf_size)
+            // visible packed leaves: children that qualify by size while this parent does not
+            if (!wb_size_leaf<KeyT, GROUPED>(a.keys, a.leaf_size, new_left, new_right)) {
+                if (wb_size_leaf<KeyT, GROUPED>(a.keys, a.leaf_size, new_left, s))
                     a.pos_parent[new_left] = n + s;
-                if (rsize <= a.leaf_size)
+                if (wb_size_leaf<KeyT, GROUPED>(a.keys, a.leaf_size, s + 1, new_right))
                     a.pos_parent[s + 1] = n + s;
             }
             xh = max(xh, other_h) + 1u;

@@ -24,7 +24,8 @@ struct BvhState {
     void* arena = nullptr;
     size_t arena_bytes = 0;
     bool arena_async = false;
-    uint32_t* keys = nullptr;     // n sorted Morton keys
+    void* keys = nullptr;         // n sorted keys: uint32 (30-bit Morton) or uint64 (group<<32|code, or 63-bit Morton)
+    int key_bytes = 4;
     int* prim = nullptr;          // n primitive_indices
     NodeRec* pairs = nullptr;     // 2*(n-1) node records
     int* parent_int = nullptr;    // n-1: parent (reference index) of internal node n+s, -1 for the root
@@ -34,7 +35,7 @@ struct BvhState {
     TreeHeader* header = nullptr;
 
     // build workspace, kept so rebuild() allocates nothing (bvh.cu:790-803 semantics)
-    uint32_t* keys_alt = nullptr;
+    void* keys_alt = nullptr;
     int* prim_alt = nullptr;
     uint32_t* ghist = nullptr;        // 4 x 256 digit histograms
     uint32_t* tile_status = nullptr;  // 4 passes x tiles x 256 look-back words
@@ -66,6 +67,7 @@ struct MeshState {
 // build / refit / export drivers (bvh_build.cu, bvh_refit.cu); all enqueue on `stream`
 const char* wb_build(BvhState& s, cudaStream_t stream);
 const char* wb_refit(BvhState& s, cudaStream_t stream);
+const char* wb_refit_merge(BvhState& s, cudaStream_t stream);  // bottom-up pass of the refit (bvh_build.cu)
 const char* wb_export_reference_layout(BvhState& s, cudaStream_t stream);
 const char* wb_alloc_tree(BvhState& s, cudaStream_t stream);
 void wb_free_tree(BvhState& s, cudaStream_t stream);

@@ -315,6 +315,27 @@ class BvhConstructor(enum.IntEnum):
             ) from None
 
 
+class _morton_bits:
+    """Extension (not in the reference API): ``morton_bits=63`` builds the tree on a 2 097 152^3 Morton grid
+    instead of the reference's 1024^3 -- a quality option for meshes with far more than 2^20 occupied cells.
+    Only ``morton_bits=30`` (default) reproduces the reference tree bit for bit."""
+
+    def __init__(self, bits, groups):
+        if bits not in (30, 63):
+            raise ValueError(f"morton_bits must be 30 or 63, current value: {bits}")
+        if bits == 63 and groups is not None:
+            raise RuntimeError("morton_bits=63 cannot be combined with groups (the key holds group << 32 | 30-bit code)")
+        self.bits = bits
+
+    def __enter__(self):
+        self.prev = _lib.core().wp_b200_get_morton_bits()
+        _lib.core().wp_b200_set_morton_bits(self.bits)
+
+    def __exit__(self, *exc):
+        _lib.core().wp_b200_set_morton_bits(self.prev)
+        return False
+
+
 def _void_p(arr):
     return ctypes.c_void_p(arr.ptr) if arr is not None and arr.ptr else ctypes.c_void_p(0)
 
@@ -331,7 +352,7 @@ class Bvh:
         instance.id = None
         return instance
 
-    def __init__(self, lowers, uppers, constructor=None, groups=None, leaf_size: int = 1):
+    def __init__(self, lowers, uppers, constructor=None, groups=None, leaf_size: int = 1, morton_bits: int = 30):
         if len(lowers) != len(uppers):
             raise RuntimeError("The same number of lower and upper bounds must be provided")
         if lowers.device != uppers.device:
@@ -364,10 +385,11 @@ class Bvh:
         if self.device.is_cpu:
             raise RuntimeError("warp_b200.Bvh: CPU trees are not available (no CPU fallback for this path)")
 
-        self.id = _lib.core().wp_bvh_create_device(
-            self.device.context, _void_p(lowers), _void_p(uppers), len(lowers), int(constructor), _void_p(groups),
-            leaf_size,
-        )  # fmt: skip
+        with _morton_bits(morton_bits, groups):
+            self.id = _lib.core().wp_bvh_create_device(
+                self.device.context, _void_p(lowers), _void_p(uppers), len(lowers), int(constructor), _void_p(groups),
+                leaf_size,
+            )  # fmt: skip
         self._constructor = constructor
         self.leaf_size = leaf_size
         if not self.id:
@@ -424,6 +446,7 @@ class Mesh:
         bvh_constructor=None,
         bvh_leaf_size: int | None = None,
         groups=None,
+        morton_bits: int = 30,
     ):
         if points.device != indices.device:
             raise RuntimeError("Mesh points and indices must live on the same device")
@@ -471,12 +494,13 @@ class Mesh:
             raise RuntimeError("warp_b200.Mesh: CPU meshes are not available (no CPU fallback for this path)")
 
         self.bvh_leaf_size = bvh_leaf_size
-        self.id = _lib.core().wp_mesh_create_device(
-            self.device.context, points.__ctype__(),
-            velocities.__ctype__() if velocities else _lib.array_t(), indices.__ctype__(),
-            len(points), int(indices.size // 3), int(support_winding_number), int(bvh_constructor),
-            _void_p(groups), bvh_leaf_size,
-        )  # fmt: skip
+        with _morton_bits(morton_bits, groups):
+            self.id = _lib.core().wp_mesh_create_device(
+                self.device.context, points.__ctype__(),
+                velocities.__ctype__() if velocities else _lib.array_t(), indices.__ctype__(),
+                len(points), int(indices.size // 3), int(support_winding_number), int(bvh_constructor),
+                _void_p(groups), bvh_leaf_size,
+            )  # fmt: skip
         if not self.id:
             raise RuntimeError(f"Failed to create mesh: {_lib.error_string()}")
 
@@ -556,7 +580,8 @@ def _download_tree(id_, n):
     out = {
         "n": n,
         "leaf_size": info.leaf_size,
-        "keys": np.zeros(n, np.uint32),
+        "keys": np.zeros(n, np.uint64 if info.key_bits == 64 else np.uint32),
+        "key_bits": info.key_bits,
         "primitive_indices": np.zeros(n, np.int32),
         "node_lowers": np.zeros(m, HALF_DTYPE),
         "node_uppers": np.zeros(m, HALF_DTYPE),
