@@ -189,6 +189,10 @@ WP_B200_API int wp_b200_get_morton_bits(void);
  * Morton order for batches of >= 32768 points. */
 WP_B200_API void wp_b200_set_query_order(int mode);
 WP_B200_API int wp_b200_get_query_order(void);
+/* thread-to-ray assignment of wp_b200_mesh_query_ray: 0 = input order (default; primary rays are coherent as
+ * given), 1 = sort the batch by origin cell, then direction cell, before tracing (incoherent batches). */
+WP_B200_API void wp_b200_set_ray_order(int mode);
+WP_B200_API int wp_b200_get_ray_order(void);
 
 /* traversal counters of the NEXT query call on this thread: when `enable` is non-zero the next
  * query also counts 64-byte sibling-pair fetches and 48-byte triangle fetches (slower, used for the

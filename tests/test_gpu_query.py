@@ -282,3 +282,22 @@ def test_c4_cloth_refit_query_loop(wp, oracle_mod):
         want = oracle_mod.query_point_no_sign(Pf, I, tree, Q[sel], 0.05)
         assert_results_equal({k: got[k][sel] for k in ("result", "face", "u", "v")}, want, ("result", "face", "u", "v"))
         prev = Pf
+
+
+def test_ray_order_modes_agree(wp, oracle_mod):
+    """Origin/direction ordering of a ray batch changes who traces a ray, never the answer."""
+    P, I = mg.noisy_sphere(5, 0.05, 1)
+    m = gpu_mesh(wp, P, I, 4)
+    tree = oracle_mod.mesh_lbvh_build(P, I, 4)
+    S, D = mg.random_rays(P, 60000, seed=21)
+    D[:100] = np.array([0, 0, -1], np.float32)  # zero components
+    S[100:200] = S[100]                        # shared origin
+    want = oracle_mod.query_ray(P, I, tree, S, D, 1e6)
+    try:
+        for mode in (wp.QUERY_ORDER_INPUT, wp.QUERY_ORDER_MORTON):
+            wp.set_ray_order(mode)
+            assert wp.get_ray_order() == mode
+            assert_results_equal(wp.mesh_query_ray(m, wp.array(S, dtype=wp.vec3), wp.array(D, dtype=wp.vec3), 1e6).numpy(), want, RAY_FIELDS)
+            assert_results_equal(wp.mesh_query_ray(m, S, D, 1e6).numpy(), want, RAY_FIELDS)
+    finally:
+        wp.set_ray_order(wp.QUERY_ORDER_INPUT)

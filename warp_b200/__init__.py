@@ -33,7 +33,9 @@ from .queries import (  # noqa: F401
     QUERY_ORDER_MORTON,
     MeshQueryPoint,
     get_query_order,
+    get_ray_order,
     set_query_order,
+    set_ray_order,
     MeshQueryRay,
     mesh_query_point,
     mesh_query_point_no_sign,

@@ -97,6 +97,8 @@ SIGNATURES = {
     "wp_b200_get_morton_bits": (_i, []),
     "wp_b200_set_query_order": (None, [_i]),
     "wp_b200_get_query_order": (_i, []),
+    "wp_b200_set_ray_order": (None, [_i]),
+    "wp_b200_get_ray_order": (_i, []),
     "wp_b200_query_stats_enable": (None, [_i]),
     "wp_b200_query_stats_read": (None, [ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]),
     "wp_b200_mesh_rebuild_device": (_i, [_u64]),

@@ -28,6 +28,7 @@ cudaStream_t g_stream[64] = {};  // current stream per device (0 = legacy defaul
 thread_local bool t_stats_enabled = false;
 int g_morton_bits = 30;         // Morton resolution of subsequently created trees: 30 (reference parity) or 63
 int g_query_order = 2;          // 0 input order, 1 Morton order, 2 auto (Morton for batches >= 32768 points)
+int g_ray_order = 0;            // 0 input order (default), 1 origin/direction order
 OrderScratch g_order[64][3];    // per device: [0] current-stream calls, [1], [2] the two host lanes
 unsigned long long* g_stats_dev = nullptr;
 
@@ -586,6 +587,8 @@ void wp_b200_query_stats_enable(int enable) { t_stats_enabled = enable != 0; }
 void wp_b200_set_morton_bits(int bits) { g_morton_bits = (bits == 63) ? 63 : 30; }
 int wp_b200_get_morton_bits(void) { return g_morton_bits; }
 void wp_b200_set_query_order(int mode) { g_query_order = mode; }
+void wp_b200_set_ray_order(int mode) { g_ray_order = mode ? 1 : 0; }
+int wp_b200_get_ray_order(void) { return g_ray_order; }
 int wp_b200_get_query_order(void) { return g_query_order; }
 
 void wp_b200_query_stats_read(unsigned long long* pair_fetches, unsigned long long* tri_fetches)
@@ -639,7 +642,7 @@ static int query_point_on(MeshState* m, const float* points, int64_t n, float ma
 }
 
 static int query_ray_on(MeshState* m, const float* starts, const float* dirs, int64_t n, float max_t, uint8_t* result,
-                        float* sign, int32_t* face, float* t, float* u, float* v, float* normal, cudaStream_t st)
+                        float* sign, int32_t* face, float* t, float* u, float* v, float* normal, cudaStream_t st, int lane = 0)
 {
     if (n <= 0)
         return 1;
@@ -649,7 +652,17 @@ static int query_ray_on(MeshState* m, const float* starts, const float* dirs, in
         ok = ok && check(cudaMemsetAsync(normal, 0, 12 * (size_t)n, st), "memset");
         return ok;
     }
-    const char* err = wb_query_ray(make_view(m->bvh), starts, dirs, n, max_t, result, sign, face, t, u, v, normal,
+    const int* perm = nullptr;
+    if (g_ray_order == 1 && n < (1ll << 30)) {  // opt-in: coherent batches (primary rays) gain nothing from it
+        OrderScratch& ws = g_order[m->bvh.device][lane];
+        const char* oerr = wb_ray_order(ws, starts, dirs, n, st);
+        if (oerr) {
+            set_error("Warp error: ray ordering failed: %s", oerr);
+            return 0;
+        }
+        perm = ws.idx;
+    }
+    const char* err = wb_query_ray(make_view(m->bvh), starts, dirs, perm, n, max_t, result, sign, face, t, u, v, normal,
                                    stats_buffer(), st);
     if (err) {
         set_error("Warp error: mesh ray query failed: %s", err);
@@ -766,7 +779,7 @@ int wp_b200_mesh_query_ray_host(uint64_t id, const float* starts, const float* d
         ok = ok && check(cudaMemcpyAsync(b + o_d, dirs + 3 * base, 12 * c, cudaMemcpyHostToDevice, l.stream), "h2d");
         ok = ok && query_ray_on(m, (const float*)(b + o_s), (const float*)(b + o_d), c, max_t, (uint8_t*)(b + o_res),
                                 (float*)(b + o_sign), (int32_t*)(b + o_face), (float*)(b + o_t), (float*)(b + o_u),
-                                (float*)(b + o_v), (float*)(b + o_n), l.stream);
+                                (float*)(b + o_v), (float*)(b + o_n), l.stream, 1 + (int)(k & 1));
         ok = ok && check(cudaMemcpyAsync(result + base, b + o_res, c, cudaMemcpyDeviceToHost, l.stream), "d2h");
         ok = ok && check(cudaMemcpyAsync(sign + base, b + o_sign, 4 * c, cudaMemcpyDeviceToHost, l.stream), "d2h");
         ok = ok && check(cudaMemcpyAsync(face + base, b + o_face, 4 * c, cudaMemcpyDeviceToHost, l.stream), "d2h");

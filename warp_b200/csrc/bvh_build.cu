@@ -922,3 +922,115 @@ const char* wb_morton_order(OrderScratch& ws, const float* pts, long long n, cud
     WB_CUDA_TRY(cudaGetLastError());
     return nullptr;
 }
+
+// ------------------------------------------------------------------------------------------------
+// ordering of rays: key = Morton code of the origin on a 64^3 grid (18 bits) above an octahedral 64 x 64
+// direction cell (12 bits).  Like the point ordering this only decides which thread traces which ray.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ uint32_t spread3_6(uint32_t v)  // 6 bits -> every third bit
+{
+    v &= 63u;
+    v = (v | (v << 8)) & 0x0000300fu;
+    v = (v | (v << 4)) & 0x000030c3u;
+    v = (v | (v << 2)) & 0x00009249u;
+    return v;
+}
+
+__global__ void __launch_bounds__(BT)
+k_ray_key_hist(const float* __restrict__ starts, const float* __restrict__ dirs, int n, const float* __restrict__ partials,
+               int num_partials, uint32_t* __restrict__ keys, uint32_t* __restrict__ ghist)
+{
+    __shared__ uint32_t h[4 * 256];
+    __shared__ float sm[BT / 32][6];
+    for (int k = threadIdx.x; k < 4 * 256; k += BT)
+        h[k] = 0;
+    float3 glo, ghi;
+    reduce_partials(partials, num_partials, sm, glo, ghi);
+    const float ivx = 64.0f / ((ghi.x - glo.x) + 0.0001f), ivy = 64.0f / ((ghi.y - glo.y) + 0.0001f),
+                ivz = 64.0f / ((ghi.z - glo.z) + 0.0001f);
+    const int stride = gridDim.x * BT;
+    const int iters = (n + stride - 1) / stride;
+    for (int it = 0; it < iters; ++it) {
+        const int i = it * stride + blockIdx.x * BT + threadIdx.x;
+        const bool valid = i < n;
+        uint32_t code = 0;
+        if (valid) {
+            const float ox = __ldg(starts + 3 * (size_t)i), oy = __ldg(starts + 3 * (size_t)i + 1), oz = __ldg(starts + 3 * (size_t)i + 2);
+            const float dx = __ldg(dirs + 3 * (size_t)i), dy = __ldg(dirs + 3 * (size_t)i + 1), dz = __ldg(dirs + 3 * (size_t)i + 2);
+            const uint32_t qx = (uint32_t)min(max((int)((ox - glo.x) * ivx), 0), 63);
+            const uint32_t qy = (uint32_t)min(max((int)((oy - glo.y) * ivy), 0), 63);
+            const uint32_t qz = (uint32_t)min(max((int)((oz - glo.z) * ivz), 0), 63);
+            // octahedral map of the direction to [0,1]^2
+            const float l1 = fabsf(dx) + fabsf(dy) + fabsf(dz);
+            const float inv = l1 > 0.f ? 1.0f / l1 : 0.f;
+            float u = dx * inv, v = dy * inv;
+            if (dz < 0.f) {
+                const float uu = (1.0f - fabsf(v)) * (u >= 0.f ? 1.f : -1.f), vv = (1.0f - fabsf(u)) * (v >= 0.f ? 1.f : -1.f);
+                u = uu, v = vv;
+            }
+            const uint32_t du = (uint32_t)min(max((int)((u * 0.5f + 0.5f) * 64.0f), 0), 63);
+            const uint32_t dv = (uint32_t)min(max((int)((v * 0.5f + 0.5f) * 64.0f), 0), 63);
+            const uint32_t omort = (spread3_6(qz) << 2) | (spread3_6(qy) << 1) | spread3_6(qx);  // 18 bits
+            uint32_t dmort = 0;                                                                   // 12 bits, 2-D interleave
+#pragma unroll
+            for (int b = 0; b < 6; ++b)
+                dmort |= (((du >> b) & 1u) << (2 * b)) | (((dv >> b) & 1u) << (2 * b + 1));
+            code = (omort << 12) | dmort;
+            keys[i] = code;
+        }
+        if (valid)
+            atomicAdd(&h[code & 255u], 1u);
+#pragma unroll
+        for (int p = 1; p < 4; ++p)
+            hist_add_coherent(h + 256 * p, (code >> (8 * p)) & 255u, valid);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 4 * 256; k += BT)
+        if (h[k])
+            atomicAdd(&ghist[k], h[k]);
+}
+
+}  // namespace
+
+static const char* order_reserve(OrderScratch& ws, long long n)
+{
+    if (n <= ws.capacity)
+        return nullptr;
+    wb_order_free(ws);
+    const size_t cap = (size_t)n;
+    const size_t tiles = (size_t)wb_div_up(n, RS_THREADS * RS_ITEMS_SMALL);
+    WB_CUDA_TRY(cudaMalloc(&ws.keys, 4 * cap));
+    WB_CUDA_TRY(cudaMalloc(&ws.keys_alt, 4 * cap));
+    WB_CUDA_TRY(cudaMalloc(&ws.idx, 4 * cap));
+    WB_CUDA_TRY(cudaMalloc(&ws.idx_alt, 4 * cap));
+    WB_CUDA_TRY(cudaMalloc(&ws.ghist, 4 * 8 * 256));
+    WB_CUDA_TRY(cudaMalloc(&ws.tile_status, 4 * 256 * 4 * tiles));
+    WB_CUDA_TRY(cudaMalloc(&ws.tickets, 4 * 16));
+    WB_CUDA_TRY(cudaMemset(ws.tickets, 0, 4 * 16));
+    WB_CUDA_TRY(cudaMalloc(&ws.partials, 4 * 6 * 4096));
+    WB_CUDA_TRY(cudaMalloc(&ws.hdr, sizeof(TreeHeader)));
+    ws.capacity = n;
+    return nullptr;
+}
+
+const char* wb_ray_order(OrderScratch& ws, const float* starts, const float* dirs, long long n, cudaStream_t stream)
+{
+    if (n <= 0)
+        return nullptr;
+    if (n >= (1ll << 30))
+        return "ray batches are ordered in chunks of fewer than 2^30 rays";
+    if (const char* e = order_reserve(ws, n))
+        return e;
+    const int ni = (int)n;
+    const int tiles = wb_div_up(n, rs_tile_for(n));
+    const int blocks = bounds_grid(n);
+    const BoxSource src { starts, starts };
+    k_scene_bounds<<<blocks, BT, 0, stream>>>(src, ni, ws.partials, ws.tickets, ws.ghist);
+    WB_CUDA_TRY(cudaMemsetAsync(ws.tile_status, 0, sizeof(uint32_t) * 256 * 4 * (size_t)tiles, stream));
+    k_ray_key_hist<<<blocks, BT, 0, stream>>>(starts, dirs, ni, ws.partials, blocks, ws.keys, ws.ghist);
+    onesweep_sort<uint32_t>(ws.keys, ws.keys_alt, ws.idx, ws.idx_alt, ni, ws.ghist, ws.tile_status, ws.tickets, stream);
+    WB_CUDA_TRY(cudaGetLastError());
+    return nullptr;
+}

@@ -20,4 +20,7 @@ struct OrderScratch {
 
 // after the call (stream-ordered) ws.idx[0..n) holds the query indices in Morton order
 const char* wb_morton_order(OrderScratch& ws, const float* pts, long long n, cudaStream_t stream);
+// same for rays: 18 bits of origin cell (64^3 grid over the origins' bounds) above 12 bits of direction cell
+// (octahedral 64 x 64), so rays that start together and point the same way share a warp
+const char* wb_ray_order(OrderScratch& ws, const float* starts, const float* dirs, long long n, cudaStream_t stream);
 void wb_order_free(OrderScratch& ws);

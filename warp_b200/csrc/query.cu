@@ -448,14 +448,16 @@ k_query_point(TreeView tv, const float* __restrict__ pts, const int* __restrict_
 // ------------------------------------------------------------------------------------------------
 template <bool COUNT>
 __global__ void __launch_bounds__(QT)
-k_query_ray(TreeView tv, const float* __restrict__ starts, const float* __restrict__ dirs, long long nq, float max_t,
-            uint8_t* __restrict__ result, float* __restrict__ sign, int* __restrict__ face, float* __restrict__ out_t,
-            float* __restrict__ out_u, float* __restrict__ out_v, float* __restrict__ normal,
+k_query_ray(TreeView tv, const float* __restrict__ starts, const float* __restrict__ dirs, const int* __restrict__ perm,
+            long long nq, float max_t, uint8_t* __restrict__ result, float* __restrict__ sign, int* __restrict__ face,
+            float* __restrict__ out_t, float* __restrict__ out_u, float* __restrict__ out_v, float* __restrict__ normal,
             unsigned long long* __restrict__ stats)
 {
     const TreeHeader h = *tv.header;
     Counters cnt;
-    for (long long i = (long long)blockIdx.x * QT + threadIdx.x; i < nq; i += (long long)gridDim.x * QT) {
+    for (long long slot = (long long)blockIdx.x * QT + threadIdx.x; slot < nq; slot += (long long)gridDim.x * QT) {
+        // `perm` (optional): origin/direction ordering of the batch, thread `slot` traces ray perm[slot]
+        const long long i = perm ? (long long)__ldg(perm + slot) : slot;
         const float3 org = make_float3(__ldg(starts + 3 * i), __ldg(starts + 3 * i + 1), __ldg(starts + 3 * i + 2));
         const float3 dir = make_float3(__ldg(dirs + 3 * i), __ldg(dirs + 3 * i + 1), __ldg(dirs + 3 * i + 2));
         float3 safe = dir;
@@ -587,17 +589,17 @@ const char* wb_query_point(const TreeView& tv, const float* pts, const int* perm
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
-const char* wb_query_ray(const TreeView& tv, const float* starts, const float* dirs, long long nq, float max_t,
-                         uint8_t* result, float* sign, int* face, float* t, float* u, float* v, float* normal,
-                         unsigned long long* stats, cudaStream_t stream)
+const char* wb_query_ray(const TreeView& tv, const float* starts, const float* dirs, const int* perm, long long nq,
+                         float max_t, uint8_t* result, float* sign, int* face, float* t, float* u, float* v,
+                         float* normal, unsigned long long* stats, cudaStream_t stream)
 {
     if (nq <= 0)
         return nullptr;
     const int grid = query_grid(nq);
     if (stats)
-        k_query_ray<true><<<grid, QT, 0, stream>>>(tv, starts, dirs, nq, max_t, result, sign, face, t, u, v, normal, stats);
+        k_query_ray<true><<<grid, QT, 0, stream>>>(tv, starts, dirs, perm, nq, max_t, result, sign, face, t, u, v, normal, stats);
     else
-        k_query_ray<false><<<grid, QT, 0, stream>>>(tv, starts, dirs, nq, max_t, result, sign, face, t, u, v, normal, stats);
+        k_query_ray<false><<<grid, QT, 0, stream>>>(tv, starts, dirs, perm, nq, max_t, result, sign, face, t, u, v, normal, stats);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

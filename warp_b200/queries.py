@@ -185,3 +185,14 @@ def set_query_order(mode: int) -> None:
 
 def get_query_order() -> int:
     return int(_lib.core().wp_b200_get_query_order())
+
+
+def set_ray_order(mode: int) -> None:
+    """``QUERY_ORDER_INPUT`` (default: thread i traces ray i -- right for primary rays, which are coherent
+    as given) or ``QUERY_ORDER_MORTON`` (the batch is sorted by origin cell, then direction cell, on the
+    device first -- for incoherent batches).  Answers are identical in both modes."""
+    _lib.core().wp_b200_set_ray_order(1 if mode else 0)
+
+
+def get_ray_order() -> int:
+    return int(_lib.core().wp_b200_get_ray_order())
