@@ -203,6 +203,55 @@ def timing():
     res["c3_triangles"] = len(Ih) // 3
     res["c3_ray_ms_median"], res["c3_rays_per_s"] = ms, n / (mn * 1e-3)
     res["c3_hit_fraction"] = float(r.numpy().mean())
+    del hm, s, d, r, f, sg, t, u, v, nrm
+    # C4: 4 M-triangle cloth, per frame = refit + 8.4 M closest-point queries within 0.05
+    n = 1415
+    Pc, Ic = mg.cloth(n, 0)
+    cp = wp.array(Pc, dtype=wp.vec3, device=DEV)
+    cm = wp.Mesh(cp, wp.array(Ic, dtype=wp.int32, device=DEV), bvh_constructor="lbvh")
+    nq = 1 << 23
+    r, f = wp.zeros(nq, dtype=wp.int32, device=DEV), wp.zeros(nq, dtype=wp.int32, device=DEV)
+    u, v = wp.zeros(nq, dtype=float, device=DEV), wp.zeros(nq, dtype=float, device=DEV)
+    frames, prev = [], Pc
+    for fr in range(1, 13):
+        Pf, _ = mg.cloth(n, fr)
+        rng = np.random.default_rng(5 + fr)
+        Q = (prev[rng.integers(0, prev.shape[0], nq)] + rng.normal(0, 0.01, (nq, 3))).astype(np.float32)
+        q = wp.array(Q, dtype=wp.vec3, device=DEV)
+        cp.assign(Pf)
+        wp.synchronize()
+        t0 = time.perf_counter()
+        cm.refit()
+        wp.launch(k_point_no_sign, dim=nq, inputs=[cm.id, q, 0.05], outputs=[r, f, u, v], device=DEV)
+        wp.synchronize()
+        frames.append(1e3 * (time.perf_counter() - t0))
+        prev = Pf
+    res["c4_triangles"] = len(Ic) // 3
+    res["c4_frame_ms_median"] = float(np.median(frames[2:]))
+    res["c4_frame_ms_all"] = frames
+    del cm, cp, q
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "ref_cuda_timing.json"), "w"), indent=1)  # partial, in case C5 fails
+    # C5: 100 M-triangle heightfield, build + a 16.8 M-query sample of the 125 M-query shard
+    P5, I5 = mg.heightfield(7072, 4)
+    p5, i5 = wp.array(P5, dtype=wp.vec3, device=DEV), wp.array(I5, dtype=wp.int32, device=DEV)
+    wp.synchronize()
+    t0 = time.perf_counter()
+    m5 = wp.Mesh(p5, i5, bvh_constructor="lbvh")
+    wp.synchronize()
+    res["c5_triangles"] = len(I5) // 3
+    res["c5_build_ms_first"] = 1e3 * (time.perf_counter() - t0)
+    res["c5_refit_ms_median"], _ = timed(m5.refit, 3, warm=1)
+    rng = np.random.default_rng(6)
+    lo, hi = P5.min(0), P5.max(0)
+    c, h = 0.5 * (lo + hi), 0.6 * (hi - lo)
+    nq = 1 << 24
+    Q = (c + (rng.random((nq, 3), dtype=np.float32) * 2 - 1) * h).astype(np.float32)
+    q = wp.array(Q, dtype=wp.vec3, device=DEV)
+    r, f = wp.zeros(nq, dtype=wp.int32, device=DEV), wp.zeros(nq, dtype=wp.int32, device=DEV)
+    u, v = wp.zeros(nq, dtype=float, device=DEV), wp.zeros(nq, dtype=float, device=DEV)
+    ms, mn = timed(lambda: wp.launch(k_point_no_sign, dim=nq, inputs=[m5.id, q, 1.0e6], outputs=[r, f, u, v], device=DEV), 2, warm=1)
+    res["c5_point_no_sign_ms_16M_sample"], res["c5_point_no_sign_qps"] = ms, nq / (mn * 1e-3)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     path = os.path.join(ROOT, "gpurun_out", "ref_cuda_timing.json")
     json.dump(res, open(path, "w"), indent=1)

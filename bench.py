@@ -63,7 +63,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)  # fmt: skip
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -272,11 +272,11 @@ def main():
         core.wp_cuda_context_synchronize(None)
 
     # ---- timed region: W warm-up steps, then exactly K steps, device-timed, L2 flushed in between -----
-    for _ in range(args.warmup):
-        step()
-    barrier()
     step_ms = []
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank) as clocks:  # started before the warm-up so nvidia-smi is already sampling when timing starts
+        for _ in range(args.warmup):
+            step()
+        barrier()
         wall0 = time.perf_counter()
         for _ in range(args.steps):
             l2_flush()
