@@ -200,6 +200,23 @@ WP_B200_API int wp_b200_get_ray_order(void);
 WP_B200_API void wp_b200_query_stats_enable(int enable);
 WP_B200_API void wp_b200_query_stats_read(unsigned long long* pair_fetches, unsigned long long* tri_fetches);
 
+/* ---------------------------------------------------------------------------------------------
+ * Generic wp.Bvh queries (batched forms of wp.bvh_query_aabb / wp.bvh_query_ray + bvh_query_next,
+ * warp/native/bvh.h:494-600): every item whose AABB overlaps the query box / is entered by the query ray
+ * before max_dist.  Hits are produced in the order the reference iterator yields them, in CSR form:
+ *   1. *_count  -> counts[n]          2. wp_b200_exclusive_scan_i32(counts, offsets, n) -> offsets[n+1]
+ *   3. *_fill   -> indices[offsets[n]]        (all device pointers, current stream; 1 ok / 0 error)
+ * ------------------------------------------------------------------------------------------- */
+WP_B200_API int wp_b200_bvh_query_aabb_count(uint64_t id, const float* lowers, const float* uppers, int64_t n,
+                                             int32_t* counts);
+WP_B200_API int wp_b200_bvh_query_aabb_fill(uint64_t id, const float* lowers, const float* uppers, int64_t n,
+                                            const int32_t* offsets, int32_t* indices);
+WP_B200_API int wp_b200_bvh_query_ray_count(uint64_t id, const float* starts, const float* dirs, int64_t n,
+                                            float max_dist, int32_t* counts);
+WP_B200_API int wp_b200_bvh_query_ray_fill(uint64_t id, const float* starts, const float* dirs, int64_t n,
+                                           float max_dist, const int32_t* offsets, int32_t* indices);
+WP_B200_API int wp_b200_exclusive_scan_i32(const int32_t* counts, int32_t* offsets, int64_t n);
+
 /* in-place LBVH rebuild of a mesh's tree from the current vertices (the reference only offers this
  * for wp.Bvh, bvh.cu:819-843; here a Mesh gets it too): no allocation, same buffers. 1 ok / 0 error */
 WP_B200_API int wp_b200_mesh_rebuild_device(uint64_t id);

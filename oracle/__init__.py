@@ -32,7 +32,7 @@ _u64p = ctypes.POINTER(ctypes.c_uint64)
 def build(force: bool = False) -> None:
     """Compile the checkers (``make -C oracle``); the ``_ref`` target is a no-op without /root/reference."""
     if force or not os.path.exists(_ORC_PATH) or (
-        os.path.getmtime(_ORC_PATH) < os.path.getmtime(os.path.join(_HERE, "lbvh_oracle.c"))
+        os.path.getmtime(_ORC_PATH) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("lbvh_oracle.c", "bvh_query_oracle.c"))
     ):
         subprocess.run(["make", "-C", _HERE, "liblbvh_oracle.so"], check=True, capture_output=True)
     if os.path.isdir("/root/reference/warp/native") and (force or not os.path.exists(_REF_PATH)):
@@ -356,3 +356,18 @@ def ref_morton3(x, y, z) -> int:
 
 def ref_max_threads() -> int:
     return int(ref().ref_max_threads())
+
+
+def bvh_query(tree, item_lowers, item_uppers, qa, qb, ray=False, max_dist=3.4028234663852886e38):
+    """Generic BVH query restatement (bvh.h:494-600): returns (offsets[n+1], indices) in iterator order."""
+    lo, hi = _f32(item_lowers, (-1, 3)), _f32(item_uppers, (-1, 3))
+    a, b = _f32(qa, (-1, 3)), _f32(qb, (-1, 3))
+    n = a.shape[0]
+    offsets = np.zeros(n + 1, np.int32)
+    args = (tree["node_lowers"].ctypes.data_as(ctypes.c_void_p), tree["node_uppers"].ctypes.data_as(ctypes.c_void_p),
+            _p(tree["primitive_indices"], _i32p), ctypes.c_int(tree["root"]), _p(lo, _f32p), _p(hi, _f32p),
+            ctypes.c_int(1 if ray else 0), _p(a, _f32p), _p(b, _f32p), ctypes.c_int64(n), ctypes.c_float(max_dist))
+    orc().orc_bvh_query(*args, _p(offsets, _i32p), None)
+    indices = np.zeros(max(int(offsets[-1]), 1), np.int32)
+    orc().orc_bvh_query(*args, _p(offsets, _i32p), _p(indices, _i32p))
+    return offsets, indices[: int(offsets[-1])]

@@ -1,0 +1,70 @@
+"""GPU parity of the batched generic wp.Bvh queries against the restatement of the reference iterator
+(exact hit lists IN ITERATOR ORDER) and against numpy brute force (exact sets), following the procedure of
+warp/tests/geometry/test_bvh.py:186-262: build, query, refit, query, rebuild, query."""
+import numpy as np
+import pytest
+
+from helpers import random_boxes
+from test_oracle import _brute_aabb, _brute_ray
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(wp, oracle_mod, bvh, tree, lo, hi, qlo, qhi, s, d):
+    off, idx = wp.bvh_query_aabb(bvh, qlo, qhi).numpy()
+    woff, widx = oracle_mod.bvh_query(tree, lo, hi, qlo, qhi)
+    assert np.array_equal(off, woff) and np.array_equal(idx, widx)
+    for i, want in enumerate(_brute_aabb(lo, hi, qlo, qhi)):
+        assert sorted(idx[off[i] : off[i + 1]].tolist()) == want.tolist()
+    for md in (3.4028234663852886e38, 4.0):
+        off, idx = wp.bvh_query_ray(bvh, wp.array(s, dtype=wp.vec3), wp.array(d, dtype=wp.vec3), md).numpy()
+        woff, widx = oracle_mod.bvh_query(tree, lo, hi, s, d, ray=True, max_dist=md)
+        assert np.array_equal(off, woff) and np.array_equal(idx, widx)
+        for i, want in enumerate(_brute_ray(lo, hi, s, d, np.float32(md))):
+            assert sorted(idx[off[i] : off[i + 1]].tolist()) == want.tolist()
+
+
+@pytest.mark.parametrize("leaf", [1, 2, 4])
+def test_bvh_queries_build_refit_rebuild(wp, oracle_mod, leaf):
+    lo, hi = random_boxes(100, seed=123)
+    lo_d, hi_d = wp.array(lo, dtype=wp.vec3), wp.array(hi, dtype=wp.vec3)
+    bvh = wp.Bvh(lo_d, hi_d, constructor="lbvh", leaf_size=leaf)
+    tree = oracle_mod.lbvh_build(lo, hi, leaf)
+    rng = np.random.default_rng(5)
+    qlo = (rng.random((257, 3)) * 10).astype(np.float32)
+    qhi = (qlo + rng.random((257, 3)).astype(np.float32) * 3).astype(np.float32)
+    s = (rng.random((257, 3)) * 10).astype(np.float32)
+    d = rng.standard_normal((257, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    _check(wp, oracle_mod, bvh, tree, lo, hi, qlo, qhi, s, d)
+    lo2, hi2 = random_boxes(100, seed=124)
+    lo_d.assign(lo2), hi_d.assign(hi2)
+    bvh.refit()
+    oracle_mod.lbvh_refit(tree, lo2, hi2)
+    _check(wp, oracle_mod, bvh, tree, lo2, hi2, qlo, qhi, s, d)
+    bvh.rebuild()
+    _check(wp, oracle_mod, bvh, oracle_mod.lbvh_build(lo2, hi2, leaf), lo2, hi2, qlo, qhi, s, d)
+
+
+def test_bvh_queries_large_and_edge_cases(wp, oracle_mod):
+    lo, hi = random_boxes(200000, seed=9, extent=50.0)
+    bvh = wp.Bvh(wp.array(lo, dtype=wp.vec3), wp.array(hi, dtype=wp.vec3), leaf_size=4)
+    tree = oracle_mod.lbvh_build(lo, hi, 4)
+    rng = np.random.default_rng(6)
+    qlo = (rng.random((50000, 3)) * 50).astype(np.float32)
+    qhi = (qlo + rng.random((50000, 3)).astype(np.float32) * 2).astype(np.float32)
+    res = wp.bvh_query_aabb(bvh, qlo, qhi)
+    off, idx = res.numpy()
+    woff, widx = oracle_mod.bvh_query(tree, lo, hi, qlo, qhi)
+    assert res.total == int(woff[-1]) > 50000
+    assert np.array_equal(off, woff) and np.array_equal(idx, widx)
+    # no hits at all, empty batch, single-item tree
+    far = np.full((7, 3), 1e6, np.float32)
+    r = wp.bvh_query_aabb(bvh, far, far + 1)
+    assert r.total == 0 and not r.numpy()[0].any()
+    assert wp.bvh_query_aabb(bvh, np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32)).total == 0
+    one = wp.Bvh(wp.array(lo[:1], dtype=wp.vec3), wp.array(hi[:1], dtype=wp.vec3))
+    r = wp.bvh_query_aabb(one, lo[:1] - 1, hi[:1] + 1)
+    assert r.lists()[0].tolist() == [0]
+    with pytest.raises(TypeError):
+        wp.bvh_query_aabb(object(), far, far)

@@ -245,3 +245,38 @@ def test_queries_vs_reference_cuda_kernels(oracle_mod, ref_gold, name):
             assert np.allclose(b[k], rr[k], rtol=0, atol=1e-5), k
         assert np.allclose(b["normal"], rr["normal"], atol=1e-6)
         assert np.array_equal(np.sign(b["sign"]), np.sign(rr["sign"]))
+
+
+def _brute_aabb(lo, hi, qlo, qhi):
+    return [np.flatnonzero(~((qlo[i] > hi).any(1) | (qhi[i] < lo).any(1))) for i in range(len(qlo))]
+
+
+def _brute_ray(lo, hi, s, d, max_dist):
+    out = []
+    for i in range(len(s)):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            rcp = np.float32(1.0) / d[i]
+            l1, l2 = (lo - s[i]) * rcp, (hi - s[i]) * rcp
+        lmin, lmax = np.minimum(l1, l2).max(1), np.maximum(l1, l2).min(1)
+        out.append(np.flatnonzero((lmax >= 0) & (lmax >= lmin) & ~(lmin >= max_dist)))
+    return out
+
+
+@pytest.mark.parametrize("leaf", [1, 2, 4])
+def test_generic_bvh_query_restatement_vs_brute_force(oracle_mod, leaf):
+    """warp/tests/geometry/test_bvh.py:186-262 criterion: exact overlap-set equality with numpy brute force."""
+    lo, hi = random_boxes(100, seed=123)
+    tree = oracle_mod.lbvh_build(lo, hi, leaf)
+    rng = np.random.default_rng(5)
+    qlo = (rng.random((64, 3)) * 10).astype(np.float32)
+    qhi = (qlo + rng.random((64, 3)).astype(np.float32) * 3).astype(np.float32)
+    off, idx = oracle_mod.bvh_query(tree, lo, hi, qlo, qhi)
+    for i, want in enumerate(_brute_aabb(lo, hi, qlo, qhi)):
+        assert sorted(idx[off[i] : off[i + 1]].tolist()) == want.tolist()
+    s = (rng.random((64, 3)) * 10).astype(np.float32)
+    d = rng.standard_normal((64, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    for md in (3.4e38, 4.0):
+        off, idx = oracle_mod.bvh_query(tree, lo, hi, s, d, ray=True, max_dist=md)
+        for i, want in enumerate(_brute_ray(lo, hi, s, d, np.float32(md))):
+            assert sorted(idx[off[i] : off[i + 1]].tolist()) == want.tolist()

@@ -43,6 +43,8 @@ from .queries import (  # noqa: F401
     query_stats,
 )
 
+from .bvh_queries import BvhQueryResult, bvh_query_aabb, bvh_query_ray  # noqa: F401,E402
+
 __version__ = "0.1.0"
 
 

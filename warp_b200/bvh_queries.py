@@ -1,0 +1,84 @@
+"""Batched generic ``wp.Bvh`` queries: ``bvh_query_aabb`` / ``bvh_query_ray`` (+ the ``bvh_query_next`` loop)
+of the reference (``warp/_src/builtins.py`` bvh_query_*, ``warp/native/bvh.h:494-600``) evaluated for a whole
+batch.  The reference yields hits one at a time inside a user kernel; here every query's hits come back at
+once in CSR form, in the order the reference iterator would produce them."""
+
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .types import Bvh, array, empty, int32, vec3
+
+FLT_MAX = float(np.finfo(np.float32).max)
+
+
+class BvhQueryResult:
+    """``offsets`` (int32, n + 1) and ``indices`` (int32, total): the items hit by query ``i`` are
+    ``indices[offsets[i]:offsets[i + 1]]``."""
+
+    __slots__ = ("offsets", "indices", "total")
+
+    def __init__(self, offsets, indices, total):
+        self.offsets, self.indices, self.total = offsets, indices, total
+
+    def numpy(self):
+        return self.offsets.numpy(), (self.indices.numpy() if self.total else np.zeros(0, np.int32))
+
+    def lists(self):
+        off, idx = self.numpy()
+        return [idx[off[i] : off[i + 1]] for i in range(len(off) - 1)]
+
+
+def _as_dev(a, dev, what):
+    if isinstance(a, array):
+        if a.dtype != vec3:
+            raise RuntimeError(f"{what} should be an array of type wp.vec3")
+        return a
+    h = np.ascontiguousarray(a, dtype=np.float32)
+    if h.ndim != 2 or h.shape[1] != 3:
+        raise RuntimeError(f"{what} should have shape (n, 3)")
+    return array(h, dtype=vec3, device=dev)
+
+
+def _run(bvh, qa, qb, ray, max_dist):
+    if not isinstance(bvh, Bvh) or not bvh.id:
+        raise TypeError("expected a warp_b200.Bvh")
+    dev = bvh.device
+    qa, qb = _as_dev(qa, dev, "first query array"), _as_dev(qb, dev, "second query array")
+    if len(qa) != len(qb):
+        raise RuntimeError("query arrays must have the same length")
+    n = len(qa)
+    c = _lib.core()
+    p = lambda a: ctypes.c_void_p(a.ptr or 0)  # noqa: E731
+    counts = empty(n, int32, dev)
+    offsets = empty(n + 1, int32, dev)
+    if ray:
+        ok = c.wp_b200_bvh_query_ray_count(bvh.id, p(qa), p(qb), n, max_dist, p(counts))
+    else:
+        ok = c.wp_b200_bvh_query_aabb_count(bvh.id, p(qa), p(qb), n, p(counts))
+    ok = ok and c.wp_b200_exclusive_scan_i32(p(counts), p(offsets), n)
+    if not ok:
+        raise RuntimeError(f"bvh query failed: {_lib.error_string()}")
+    total = int(offsets.numpy()[-1])  # the one host round trip: the hit list has to be allocated
+    indices = empty(max(total, 1), int32, dev)
+    if total:
+        if ray:
+            ok = c.wp_b200_bvh_query_ray_fill(bvh.id, p(qa), p(qb), n, max_dist, p(offsets), p(indices))
+        else:
+            ok = c.wp_b200_bvh_query_aabb_fill(bvh.id, p(qa), p(qb), n, p(offsets), p(indices))
+        if not ok:
+            raise RuntimeError(f"bvh query failed: {_lib.error_string()}")
+    return BvhQueryResult(offsets, indices, total)
+
+
+def bvh_query_aabb(bvh, lowers, uppers) -> BvhQueryResult:
+    """All items whose AABB overlaps ``[lowers[i], uppers[i]]`` (closed boxes, ``intersect.h:183-192``)."""
+    return _run(bvh, lowers, uppers, False, 0.0)
+
+
+def bvh_query_ray(bvh, starts, dirs, max_dist: float = FLT_MAX) -> BvhQueryResult:
+    """All items whose AABB the ray ``starts[i] + t * dirs[i]`` enters at ``t < max_dist`` (``bvh.h:483-487``)."""
+    return _run(bvh, starts, dirs, True, float(max_dist))

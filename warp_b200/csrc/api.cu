@@ -795,6 +795,79 @@ int wp_b200_mesh_query_ray_host(uint64_t id, const float* starts, const float* d
 }
 
 // ------------------------------------------------------------------------------------------------
+// generic BVH queries (wp.Bvh): count pass, device scan, fill pass
+// ------------------------------------------------------------------------------------------------
+static long long* g_scan_scratch[64] = {};
+static size_t g_scan_scratch_words[64] = {};
+
+static int bvh_query_common(uint64_t id, int ray, const float* qa, const float* qb, int64_t n, float max_dist,
+                            int32_t* counts, const int32_t* offsets, int32_t* indices)
+{
+    MeshState* ms = nullptr;
+    BvhState* s = find_tree(id, &ms);
+    if (!s || ms) {
+        set_error("Warp error: invalid BVH id (generic queries take a wp.Bvh)");
+        return 0;
+    }
+    DeviceGuard g(s->device);
+    cudaStream_t st = current_stream(s->device);
+    if (n <= 0)
+        return 1;
+    if (s->n == 0) {
+        if (!offsets)
+            return check(cudaMemsetAsync(counts, 0, 4 * (size_t)n, st), "memset") ? 1 : 0;
+        return 1;
+    }
+    const char* err = wb_bvh_query(make_view(*s), s->item_lowers, s->item_uppers, ray, qa, qb, n, max_dist, counts,
+                                   offsets, indices, st);
+    if (err) {
+        set_error("Warp error: BVH query failed: %s", err);
+        return 0;
+    }
+    return 1;
+}
+
+int wp_b200_bvh_query_aabb_count(uint64_t id, const float* lowers, const float* uppers, int64_t n, int32_t* counts)
+{
+    return bvh_query_common(id, 0, lowers, uppers, n, 0.f, counts, nullptr, nullptr);
+}
+int wp_b200_bvh_query_aabb_fill(uint64_t id, const float* lowers, const float* uppers, int64_t n, const int32_t* offsets,
+                                int32_t* indices)
+{
+    return bvh_query_common(id, 0, lowers, uppers, n, 0.f, nullptr, offsets, indices);
+}
+int wp_b200_bvh_query_ray_count(uint64_t id, const float* starts, const float* dirs, int64_t n, float max_dist,
+                                int32_t* counts)
+{
+    return bvh_query_common(id, 1, starts, dirs, n, max_dist, counts, nullptr, nullptr);
+}
+int wp_b200_bvh_query_ray_fill(uint64_t id, const float* starts, const float* dirs, int64_t n, float max_dist,
+                               const int32_t* offsets, int32_t* indices)
+{
+    return bvh_query_common(id, 1, starts, dirs, n, max_dist, nullptr, offsets, indices);
+}
+
+int wp_b200_exclusive_scan_i32(const int32_t* counts, int32_t* offsets, int64_t n)
+{
+    const int dev = current_device();
+    const size_t words = (size_t)(n > 0 ? (n + 2047) / 2048 : 0) + 2;
+    if (words > g_scan_scratch_words[dev]) {
+        if (g_scan_scratch[dev])
+            cudaFree(g_scan_scratch[dev]);
+        g_scan_scratch[dev] = nullptr, g_scan_scratch_words[dev] = 0;
+        if (!check(cudaMalloc(&g_scan_scratch[dev], 8 * words), "scan scratch"))
+            return 0;
+        g_scan_scratch_words[dev] = words;
+    }
+    const char* err = wb_exclusive_scan(counts, offsets, n, g_scan_scratch[dev], current_stream(dev));
+    if (err) {
+        set_error("Warp error: scan failed: %s", err);
+        return 0;
+    }
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // introspection
 // ------------------------------------------------------------------------------------------------
 int wp_b200_bvh_info(uint64_t id, wp_b200_bvh_info_t* info)

@@ -1,0 +1,256 @@
+// Batched generic BVH queries: all items whose AABB overlaps a query box, or is
+// hit by a query ray, for a batch of queries against a wp.Bvh -- the broad phase of a collision loop.
+//
+// Behavioural contract = the reference's iterator (warp/native/bvh.h:494-600): depth-first, children pushed
+// left then right (so the right subtree is reported first), node test on pop, a single-item leaf is reported
+// without an item-level test (its box IS the item's box), items of a packed leaf are tested one by one in
+// leaf order against item_lowers/item_uppers.  One call evaluates a whole batch; hits come back in CSR form
+// (offsets[n+1], indices[total]) in exactly the order the reference iterator would yield them.
+#include "query.h"
+#include "state.h"
+
+namespace {
+
+constexpr int BQ = 128;
+
+struct Entry2 {
+    uint32_t a;  // leaf: first sorted position | WB_LEAF ; inner: internal slot s
+    uint32_t b;  // leaf: item count
+};
+
+__device__ __forceinline__ bool overlap_aabb(float3 alo, float3 ahi, float3 blo, float3 bhi)
+{
+    // intersect_aabb_aabb (intersect.h:183-192)
+    return !(alo.x > bhi.x || alo.y > bhi.y || alo.z > bhi.z || ahi.x < blo.x || ahi.y < blo.y || ahi.z < blo.z);
+}
+
+__device__ __forceinline__ bool ray_box(float3 pos, float3 rcp, float3 lo, float3 hi, float max_dist)
+{
+    // intersect_ray_aabb (intersect.h:127-152) + the half-open max_dist bound of bvh_query_test<RAY> (bvh.h:483-487)
+    float l1 = (lo.x - pos.x) * rcp.x, l2 = (hi.x - pos.x) * rcp.x;
+    float lmin = fminf(l1, l2), lmax = fmaxf(l1, l2);
+    l1 = (lo.y - pos.y) * rcp.y, l2 = (hi.y - pos.y) * rcp.y;
+    lmin = fmaxf(fminf(l1, l2), lmin), lmax = fminf(fmaxf(l1, l2), lmax);
+    l1 = (lo.z - pos.z) * rcp.z, l2 = (hi.z - pos.z) * rcp.z;
+    lmin = fmaxf(fminf(l1, l2), lmin), lmax = fminf(fmaxf(l1, l2), lmax);
+    const bool hit = (lmax >= 0.f) & (lmax >= lmin);
+    return hit && !(lmin >= max_dist);
+}
+
+template <bool RAY>
+__device__ __forceinline__ bool test_box(float3 qa, float3 qb, float3 lo, float3 hi, float max_dist)
+{
+    if (RAY)
+        return ray_box(qa, qb, lo, hi, max_dist);
+    return overlap_aabb(qa, qb, lo, hi);
+}
+
+__device__ __forceinline__ float3 ld3(const float* __restrict__ p, size_t i)
+{
+    return make_float3(__ldg(p + 3 * i), __ldg(p + 3 * i + 1), __ldg(p + 3 * i + 2));
+}
+
+// RAY: (qa, qb) = (start, 1/dir);  AABB: (qa, qb) = (lower, upper).  FILL = false counts, true writes indices.
+template <bool RAY, bool FILL>
+__global__ void __launch_bounds__(BQ)
+k_bvh_query(TreeView tv, const float* __restrict__ item_lowers, const float* __restrict__ item_uppers,
+            const float* __restrict__ qa_in, const float* __restrict__ qb_in, long long nq, float max_dist,
+            int* __restrict__ counts, const int* __restrict__ offsets, int* __restrict__ indices)
+{
+    const TreeHeader h = *tv.header;
+    for (long long i = (long long)blockIdx.x * BQ + threadIdx.x; i < nq; i += (long long)gridDim.x * BQ) {
+        const float3 qa = ld3(qa_in, (size_t)i);
+        float3 qb = ld3(qb_in, (size_t)i);
+        if (RAY)
+            qb = make_float3(1.0f / qb.x, 1.0f / qb.y, 1.0f / qb.z);  // bvh_query_ray stores 1/dir (bvh.h:526-531)
+        int found = 0;
+        int* out = FILL ? indices + offsets[i] : nullptr;
+
+        Entry2 stack[WB_QUERY_STACK];
+        int top = 0;
+        if (test_box<RAY>(qa, qb, make_float3(h.lx, h.ly, h.lz), make_float3(h.hx, h.hy, h.hz), max_dist)) {
+            if (h.root_ref & WB_LEAF)
+                stack[0].a = WB_LEAF | 0u, stack[0].b = h.root_count;
+            else
+                stack[0].a = (h.root_ref & WB_IDX_MASK) - (uint32_t)tv.n, stack[0].b = 0;
+            top = 1;
+        }
+        while (top) {
+            const Entry2 cur = stack[--top];
+            if (cur.a & WB_LEAF) {
+                const uint32_t start = cur.a & WB_IDX_MASK;
+                if (cur.b == 1u) {  // single-item leaf: reported without an item test (bvh.h:576-581)
+                    if (FILL)
+                        out[found] = __ldg(tv.prim + start);
+                    ++found;
+                } else {
+                    for (uint32_t k = 0; k < cur.b; ++k) {
+                        const int item = __ldg(tv.prim + start + k);
+                        if (test_box<RAY>(qa, qb, ld3(item_lowers, (size_t)item), ld3(item_uppers, (size_t)item), max_dist)) {
+                            if (FILL)
+                                out[found] = item;
+                            ++found;
+                        }
+                    }
+                }
+                continue;
+            }
+            const uint32_t s = cur.a;
+            const float4* p4 = reinterpret_cast<const float4*>(tv.pairs + 2 * (size_t)s);
+            const float4 a0 = __ldg(p4), a1 = __ldg(p4 + 1), b0 = __ldg(p4 + 2), b1 = __ldg(p4 + 3);
+            const uint32_t lref = __float_as_uint(a0.w), laux = __float_as_uint(a1.w);
+            const uint32_t rref = __float_as_uint(b0.w), raux = __float_as_uint(b1.w);
+            // left is pushed first, right second => the right child is popped (reported) first (bvh.h:603-606);
+            // a child whose box fails the test is simply not pushed (the reference pops and discards it)
+            if (test_box<RAY>(qa, qb, make_float3(a0.x, a0.y, a0.z), make_float3(a1.x, a1.y, a1.z), max_dist)) {
+                Entry2 e;
+                if (lref & WB_LEAF)
+                    e.a = laux | WB_LEAF, e.b = s - laux + 1;
+                else
+                    e.a = (lref & WB_IDX_MASK) - (uint32_t)tv.n, e.b = 0;
+                stack[top++] = e;
+            }
+            if (test_box<RAY>(qa, qb, make_float3(b0.x, b0.y, b0.z), make_float3(b1.x, b1.y, b1.z), max_dist)) {
+                Entry2 e;
+                if (rref & WB_LEAF)
+                    e.a = (s + 1) | WB_LEAF, e.b = raux - s;
+                else
+                    e.a = (rref & WB_IDX_MASK) - (uint32_t)tv.n, e.b = 0;
+                stack[top++] = e;
+            }
+        }
+        if (!FILL)
+            counts[i] = found;
+    }
+}
+
+// ---- exclusive scan of int32 counts into offsets[n+1] (three small kernels; n up to 2^31) ----
+constexpr int SCAN_T = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_T * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SCAN_T)
+k_scan_tiles(const int* __restrict__ in, int* __restrict__ out, long long n, long long* __restrict__ tile_sums)
+{
+    __shared__ int warp_sums[SCAN_T / 32];
+    const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        sum += v[k];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o)
+            inc += t;
+    }
+    if (lane == 31)
+        warp_sums[warp] = inc;
+    __syncthreads();
+    int off = 0;
+    for (int w = 0; w < warp; ++w)
+        off += warp_sums[w];
+    int run = off + inc - sum;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n)
+            out[base + k] = run;  // tile-local exclusive prefix; the tile offset is added by k_scan_add
+        run += v[k];
+    }
+    if (threadIdx.x == SCAN_T - 1)
+        tile_sums[blockIdx.x] = run;
+}
+
+__global__ void __launch_bounds__(1024)
+k_scan_tile_sums(long long* tile_sums, int tiles, int* total_out)
+{
+    // one block: every thread owns a contiguous segment of the tile sums
+    __shared__ long long seg[1024];
+    const int per = (tiles + 1023) / 1024;
+    const int t0 = min(tiles, (int)threadIdx.x * per), t1 = min(tiles, t0 + per);
+    long long sum = 0;
+    for (int t = t0; t < t1; ++t)
+        sum += tile_sums[t];
+    seg[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan of the 1024 segment sums
+        const long long add = threadIdx.x >= (unsigned)o ? seg[threadIdx.x - o] : 0;
+        __syncthreads();
+        seg[threadIdx.x] += add;
+        __syncthreads();
+    }
+    long long run = seg[threadIdx.x] - sum;
+    for (int t = t0; t < t1; ++t) {
+        const long long c = tile_sums[t];
+        tile_sums[t] = run;
+        run += c;
+    }
+    if (threadIdx.x == 1023) {
+        const long long total = seg[1023];
+        *total_out = (int)(total > 0x7fffffffll ? 0x7fffffffll : total);
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_T)
+k_scan_add(int* __restrict__ out, long long n, const long long* __restrict__ tile_sums, const int* __restrict__ total)
+{
+    const long long base = (long long)blockIdx.x * SCAN_TILE;
+    const int off = (int)tile_sums[blockIdx.x];
+    for (int k = threadIdx.x; k < SCAN_TILE; k += SCAN_T)
+        if (base + k < n)
+            out[base + k] += off;
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        out[n] = *total;
+}
+
+int grid_for(long long nq)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long want = (nq + BQ - 1) / BQ, cap = (long long)sms * 64;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+}  // namespace
+
+const char* wb_bvh_query(const TreeView& tv, const float* item_lowers, const float* item_uppers, int ray,
+                         const float* qa, const float* qb, long long nq, float max_dist, int* counts,
+                         const int* offsets, int* indices, cudaStream_t stream)
+{
+    if (nq <= 0)
+        return nullptr;
+    const int grid = grid_for(nq);
+    const bool fill = offsets != nullptr;
+    if (ray) {
+        if (fill)
+            k_bvh_query<true, true><<<grid, BQ, 0, stream>>>(tv, item_lowers, item_uppers, qa, qb, nq, max_dist, counts, offsets, indices);
+        else
+            k_bvh_query<true, false><<<grid, BQ, 0, stream>>>(tv, item_lowers, item_uppers, qa, qb, nq, max_dist, counts, offsets, indices);
+    } else {
+        if (fill)
+            k_bvh_query<false, true><<<grid, BQ, 0, stream>>>(tv, item_lowers, item_uppers, qa, qb, nq, max_dist, counts, offsets, indices);
+        else
+            k_bvh_query<false, false><<<grid, BQ, 0, stream>>>(tv, item_lowers, item_uppers, qa, qb, nq, max_dist, counts, offsets, indices);
+    }
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+// offsets[0..n] = exclusive prefix sums of counts[0..n); scratch = ceil(n / 2048) + 1 int64 words
+const char* wb_exclusive_scan(const int* counts, int* offsets, long long n, long long* scratch, cudaStream_t stream)
+{
+    if (n <= 0) {
+        cudaMemsetAsync(offsets, 0, sizeof(int), stream);
+        return nullptr;
+    }
+    const int tiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+    int* total = reinterpret_cast<int*>(scratch + tiles);
+    k_scan_tiles<<<tiles, SCAN_T, 0, stream>>>(counts, offsets, n, scratch);
+    k_scan_tile_sums<<<1, 1024, 0, stream>>>(scratch, tiles, total);
+    k_scan_add<<<tiles, SCAN_T, 0, stream>>>(offsets, n, scratch, total);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}

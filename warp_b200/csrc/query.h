@@ -2,6 +2,14 @@
 #pragma once
 #include "common.cuh"
 
+// generic BVH queries (bvh_query.cu): ray != 0 -> (qa, qb) = (start, dir) else (lower, upper).  offsets == NULL
+// counts hits into counts[nq]; otherwise writes the hit items of query i at indices[offsets[i]...]
+const char* wb_bvh_query(const TreeView& tv, const float* item_lowers, const float* item_uppers, int ray,
+                         const float* qa, const float* qb, long long nq, float max_dist, int* counts,
+                         const int* offsets, int* indices, cudaStream_t stream);
+// offsets[0..n] = exclusive prefix sums of counts[0..n); scratch = ceil(n / 2048) + 1 int64 words
+const char* wb_exclusive_scan(const int* counts, int* offsets, long long n, long long* scratch, cudaStream_t stream);
+
 // perm: optional permutation (thread slot -> query index), e.g. from wb_morton_order
 const char* wb_query_point(const TreeView& tv, const float* pts, const int* perm, long long nq, float max_dist,
                            int with_sign, uint8_t* result, float* sign, int* face, float* u, float* v,
