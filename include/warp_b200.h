@@ -165,8 +165,20 @@ WP_B200_API int wp_b200_mesh_query_point(uint64_t id, const float* points, int64
 WP_B200_API int wp_b200_mesh_query_ray(uint64_t id, const float* starts, const float* dirs, int64_t n, float max_t,
                                        uint8_t* result, float* sign, int32_t* face, float* t, float* u, float* v,
                                        float* normal);
+/* wp.mesh_query_ray_anyhit (mesh.h:1893-1974): result[i] = 1 when some triangle is hit with 0 <= t < max_t */
+WP_B200_API int wp_b200_mesh_query_ray_anyhit(uint64_t id, const float* starts, const float* dirs, int64_t n,
+                                              float max_t, uint8_t* result);
+/* wp.mesh_query_ray_count_intersections (mesh.h:1976-2032): number of triangles hit with t >= 0, unbounded ray */
+WP_B200_API int wp_b200_mesh_query_ray_count_intersections(uint64_t id, const float* starts, const float* dirs,
+                                                           int64_t n, int32_t* counts);
+/* wp.mesh_eval_position / wp.mesh_eval_velocity (mesh.h:2767-2805): out[i] = p*u + q*v + r*(1-u-v) of triangle
+ * face[i], read from the mesh's CURRENT point / velocity array (zeros when the mesh has none); out is n x 3 */
+WP_B200_API int wp_b200_mesh_eval_position(uint64_t id, const int32_t* face, const float* u, const float* v,
+                                           int64_t n, float* out);
+WP_B200_API int wp_b200_mesh_eval_velocity(uint64_t id, const int32_t* face, const float* u, const float* v,
+                                           int64_t n, float* out);
 
-/* same three calls with HOST buffers: inputs are copied to the device, the query runs, results are
+/* the first three calls with HOST buffers: inputs are copied to the device, the query runs, results are
  * copied back, and the call returns after the results are valid (synchronous).  Work is chunked and
  * double-buffered through pinned staging so copies overlap traversal. */
 WP_B200_API int wp_b200_mesh_query_point_no_sign_host(uint64_t id, const float* points, int64_t n, float max_dist,

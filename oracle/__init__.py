@@ -223,6 +223,37 @@ def query_ray(points, indices, tree, starts, dirs, max_t, stats=False):
     return res
 
 
+def query_ray_anyhit(points, indices, tree, starts, dirs, max_t):
+    """mesh_query_ray_anyhit restatement (mesh.h:1893-1974)."""
+    points, indices, targs = _tree_args(points, indices, tree)
+    s, d = _f32(starts, (-1, 3)), _f32(dirs, (-1, 3))
+    out = np.zeros(s.shape[0], np.uint8)
+    orc().orc_query_ray_anyhit(*targs, _p(s, _f32p), _p(d, _f32p), ctypes.c_int64(s.shape[0]), ctypes.c_float(max_t),
+                               _p(out, _u8p))  # fmt: skip
+    return out
+
+
+def query_ray_count(points, indices, tree, starts, dirs):
+    """mesh_query_ray_count_intersections restatement (mesh.h:1976-2032)."""
+    points, indices, targs = _tree_args(points, indices, tree)
+    s, d = _f32(starts, (-1, 3)), _f32(dirs, (-1, 3))
+    out = np.zeros(s.shape[0], np.int32)
+    orc().orc_query_ray_count(*targs, _p(s, _f32p), _p(d, _f32p), ctypes.c_int64(s.shape[0]), _p(out, _i32p))
+    return out
+
+
+def mesh_eval(attr, indices, face, u, v):
+    """mesh_eval_position / mesh_eval_velocity restatement (mesh.h:2767-2805)."""
+    a = _f32(attr, (-1, 3))
+    idx = np.ascontiguousarray(indices, np.int32).reshape(-1)
+    f = np.ascontiguousarray(face, np.int32)
+    uu, vv = _f32(u), _f32(v)
+    out = np.zeros((f.shape[0], 3), np.float32)
+    orc().orc_mesh_eval(_p(a, _f32p), _p(idx, _i32p), _p(f, _i32p), _p(uu, _f32p), _p(vv, _f32p),
+                        ctypes.c_int64(f.shape[0]), _p(out, _f32p))  # fmt: skip
+    return out
+
+
 def closest_point_to_triangle(a, b, c, p):
     uv = np.zeros(2, np.float32)
     orc().orc_closest_point_to_triangle(_p(_f32(a), _f32p), _p(_f32(b), _f32p), _p(_f32(c), _f32p),
@@ -341,6 +372,29 @@ class RefMesh:
             _p(res["u"], _f32p), _p(res["v"], _f32p), _p(res["normal"], _f32p), ctypes.c_int(nthreads),
         )  # fmt: skip
         return res
+
+
+    def query_ray_anyhit(self, starts, dirs, max_t, nthreads=1):
+        s, d = _f32(starts, (-1, 3)), _f32(dirs, (-1, 3))
+        out = np.zeros(s.shape[0], np.uint8)
+        ref().ref_query_ray_anyhit(ctypes.c_uint64(self.id), _p(s, _f32p), _p(d, _f32p), ctypes.c_int64(s.shape[0]),
+                                   ctypes.c_float(max_t), _p(out, _u8p), ctypes.c_int(nthreads))  # fmt: skip
+        return out
+
+    def query_ray_count(self, starts, dirs, nthreads=1):
+        s, d = _f32(starts, (-1, 3)), _f32(dirs, (-1, 3))
+        out = np.zeros(s.shape[0], np.int32)
+        ref().ref_query_ray_count(ctypes.c_uint64(self.id), _p(s, _f32p), _p(d, _f32p), ctypes.c_int64(s.shape[0]),
+                                  _p(out, _i32p), ctypes.c_int(nthreads))  # fmt: skip
+        return out
+
+    def eval(self, face, u, v, velocity=False):
+        f = np.ascontiguousarray(face, np.int32)
+        uu, vv = _f32(u), _f32(v)
+        out = np.zeros((f.shape[0], 3), np.float32)
+        ref().ref_mesh_eval(ctypes.c_uint64(self.id), ctypes.c_int(1 if velocity else 0), _p(f, _i32p), _p(uu, _f32p),
+                            _p(vv, _f32p), ctypes.c_int64(f.shape[0]), _p(out, _f32p))  # fmt: skip
+        return out
 
 
 def ref_closest_point_to_triangle(a, b, c, p):

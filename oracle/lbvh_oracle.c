@@ -894,3 +894,129 @@ void orc_query_ray(const float* points, const int* indices, const orc_half* node
     if (stats)
         stats[0] = st.nodes_visited, stats[1] = st.tris_tested;
 }
+
+/* any hit with 0 <= t < max_t, near child first, fixed bound -- mesh.h:1893-1974 */
+static int ray_anyhit_one(const orc_mesh* m, v3 start, v3 dir, float max_t)
+{
+    ray_entry stack[ORC_STACK];
+    int size = 0;
+    ray_entry cur = { HALF_B(m->node_lowers[m->root]), HALF_I(m->node_lowers[m->root]), HALF_I(m->node_uppers[m->root]) };
+    v3 safe = dir;
+    if (safe.x == 0.0f)
+        safe.x = 1.0e-20f;
+    if (safe.y == 0.0f)
+        safe.y = 1.0e-20f;
+    if (safe.z == 0.0f)
+        safe.z = 1.0e-20f;
+    const v3 rcp = v3_make(1.0f / safe.x, 1.0f / safe.y, 1.0f / safe.z);
+    const int fast = dir.x != 0.0f && dir.y != 0.0f && dir.z != 0.0f;
+    for (;;) {
+        if (cur.leaf) {
+            for (int pc = cur.lo_payload; pc < cur.hi_payload; ++pc) {
+                const int prim = m->primitive_indices[pc];
+                const v3 p = v3_ld(m->points, m->indices[3 * prim + 0]);
+                const v3 q = v3_ld(m->points, m->indices[3 * prim + 1]);
+                const v3 r = v3_ld(m->points, m->indices[3 * prim + 2]);
+                float tt, tu, tv, ts;
+                v3 n;
+                if (ray_tri_watertight(start, dir, p, q, r, &tt, &tu, &tv, &ts, &n) && tt < max_t && tt >= 0.0f)
+                    return 1;
+            }
+            if (size == 0)
+                return 0;
+            cur = stack[--size];
+            continue;
+        }
+        const int li = cur.lo_payload, ri = cur.hi_payload;
+        const orc_half llo = m->node_lowers[li], lhi = m->node_uppers[li];
+        const orc_half rlo = m->node_lowers[ri], rhi = m->node_uppers[ri];
+        float t0 = FLT_MAX, t1 = FLT_MAX;
+        const int h0 = (fast ? ray_aabb_fast(start, rcp, &llo, &lhi, &t0)
+                             : ray_aabb_robust(start, dir, rcp, &llo, &lhi, &t0))
+            && t0 < max_t;
+        const int h1 = (fast ? ray_aabb_fast(start, rcp, &rlo, &rhi, &t1)
+                             : ray_aabb_robust(start, dir, rcp, &rlo, &rhi, &t1))
+            && t1 < max_t;
+        ray_entry le = { HALF_B(llo), HALF_I(llo), HALF_I(lhi) };
+        ray_entry re = { HALF_B(rlo), HALF_I(rlo), HALF_I(rhi) };
+        if (h0 && h1) {
+            if (size >= ORC_STACK)
+                return 0; /* mesh.h:1958-1959 */
+            const int near_left = t0 < t1;
+            stack[size++] = near_left ? re : le;
+            cur = near_left ? le : re;
+        } else if (h0) {
+            cur = le;
+        } else if (h1) {
+            cur = re;
+        } else {
+            if (size == 0)
+                return 0;
+            cur = stack[--size];
+        }
+    }
+}
+
+/* number of triangles hit with t >= 0 along the whole ray, push-both traversal -- mesh.h:1976-2032.
+ * The reference pushes without an overflow check; trees deeper than the stack are outside its defined
+ * behaviour and this restatement stops pushing there. */
+static int ray_count_one(const orc_mesh* m, v3 start, v3 dir)
+{
+    int stack[ORC_STACK + 2];
+    int count = 1, hits = 0;
+    stack[0] = m->root;
+    const v3 rcp = v3_make(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+    while (count) {
+        const int node = stack[--count];
+        const orc_half lo = m->node_lowers[node], hi = m->node_uppers[node];
+        float tt;
+        if (!ray_aabb_robust(start, dir, rcp, &lo, &hi, &tt))
+            continue;
+        if (HALF_B(lo)) {
+            for (int pc = HALF_I(lo); pc < HALF_I(hi); ++pc) {
+                const int prim = m->primitive_indices[pc];
+                const v3 p = v3_ld(m->points, m->indices[3 * prim + 0]);
+                const v3 q = v3_ld(m->points, m->indices[3 * prim + 1]);
+                const v3 r = v3_ld(m->points, m->indices[3 * prim + 2]);
+                float t, u, v, s;
+                v3 n;
+                if (ray_tri_watertight(start, dir, p, q, r, &t, &u, &v, &s, &n) && t >= 0.0f)
+                    hits++;
+            }
+        } else if (count < ORC_STACK) {
+            stack[count++] = HALF_I(lo);
+            stack[count++] = HALF_I(hi);
+        }
+    }
+    return hits;
+}
+
+void orc_query_ray_anyhit(const float* points, const int* indices, const orc_half* node_lowers,
+                          const orc_half* node_uppers, const int* primitive_indices, int root, const float* starts,
+                          const float* dirs, int64_t n, float max_t, uint8_t* result)
+{
+    const orc_mesh m = make_mesh(points, indices, node_lowers, node_uppers, primitive_indices, root);
+    for (int64_t i = 0; i < n; ++i)
+        result[i] = (uint8_t)ray_anyhit_one(&m, v3_ld(starts, i), v3_ld(dirs, i), max_t);
+}
+
+void orc_query_ray_count(const float* points, const int* indices, const orc_half* node_lowers,
+                         const orc_half* node_uppers, const int* primitive_indices, int root, const float* starts,
+                         const float* dirs, int64_t n, int* counts)
+{
+    const orc_mesh m = make_mesh(points, indices, node_lowers, node_uppers, primitive_indices, root);
+    for (int64_t i = 0; i < n; ++i)
+        counts[i] = ray_count_one(&m, v3_ld(starts, i), v3_ld(dirs, i));
+}
+
+/* p*u + q*v + r*(1 - u - v) -- mesh.h:2767-2805 (vec3 scale then add, left to right) */
+void orc_mesh_eval(const float* attr, const int* indices, const int* face, const float* u, const float* v, int64_t n,
+                   float* out)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        const int f = face[i];
+        const v3 p = v3_ld(attr, indices[3 * f + 0]), q = v3_ld(attr, indices[3 * f + 1]), r = v3_ld(attr, indices[3 * f + 2]);
+        const v3 x = v3_add(v3_add(v3_scale(u[i], p), v3_scale(v[i], q)), v3_scale(1.0f - u[i] - v[i], r));
+        out[3 * i] = x.x, out[3 * i + 1] = x.y, out[3 * i + 2] = x.z;
+    }
+}

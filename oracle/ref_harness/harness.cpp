@@ -192,6 +192,33 @@ void ref_query_ray(
     });
 }
 
+void ref_query_ray_anyhit(uint64_t id, const float* starts, const float* dirs, int64_t n, float max_t, uint8_t* result,
+                          int nthreads)
+{
+    parallel_for(n, nthreads, [&](int64_t i) {
+        result[i] = mesh_query_ray_anyhit(id, vec3(starts[3 * i], starts[3 * i + 1], starts[3 * i + 2]),
+                                          vec3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), max_t, -1)
+            ? 1
+            : 0;
+    });
+}
+
+void ref_query_ray_count(uint64_t id, const float* starts, const float* dirs, int64_t n, int* counts, int nthreads)
+{
+    parallel_for(n, nthreads, [&](int64_t i) {
+        counts[i] = mesh_query_ray_count_intersections(id, vec3(starts[3 * i], starts[3 * i + 1], starts[3 * i + 2]),
+                                                       vec3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), -1);
+    });
+}
+
+void ref_mesh_eval(uint64_t id, int velocity, const int* face, const float* u, const float* v, int64_t n, float* out)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        vec3 r = velocity ? mesh_eval_velocity(id, face[i], u[i], v[i]) : mesh_eval_position(id, face[i], u[i], v[i]);
+        out[3 * i] = r[0], out[3 * i + 1] = r[1], out[3 * i + 2] = r[2];
+    }
+}
+
 // standalone primitives for unit-level pinning of the restatement
 void ref_closest_point_to_triangle(const float* a, const float* b, const float* c, const float* p, float* uv)
 {

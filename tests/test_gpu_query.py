@@ -301,3 +301,83 @@ def test_ray_order_modes_agree(wp, oracle_mod):
             assert_results_equal(wp.mesh_query_ray(m, S, D, 1e6).numpy(), want, RAY_FIELDS)
     finally:
         wp.set_ray_order(wp.QUERY_ORDER_INPUT)
+
+
+# ------------------------------------------------------------------------------------------------
+# any-hit / intersection count / eval_position, eval_velocity
+# ------------------------------------------------------------------------------------------------
+def test_ray_variants_reference_fixture(wp):
+    """Answers recorded from the reference C++ (tests/golden/golden_ray_variants.npz)."""
+    g = np.load(GOLD)
+    rv = np.load(os.path.join(os.path.dirname(GOLD), "golden_ray_variants.npz"))
+    P, I = g["mesh_points"], g["mesh_indices"]
+    for leaf in (1, 4):
+        m = gpu_mesh(wp, P, I, leaf)
+        for mt in (0.5, 1.0, 1e6):
+            got = wp.mesh_query_ray_anyhit(m, rv["starts"], rv["dirs"], mt)
+            assert got.dtype == bool and np.array_equal(got, rv[f"lbvh{leaf}_anyhit_{mt:g}"].astype(bool))
+        assert np.array_equal(wp.mesh_query_ray_count_intersections(m, rv["starts"], rv["dirs"]), rv[f"lbvh{leaf}_count"])
+        pos = wp.mesh_eval_position(m, rv["eval_face"], rv["eval_u"], rv["eval_v"])
+        assert np.array_equal(pos, rv[f"lbvh{leaf}_eval_position"])
+
+
+@pytest.mark.parametrize("leaf", [1, 4, 8])
+def test_ray_variants_bit_exact(wp, oracle_mod, leaf):
+    P, I = mg.noisy_sphere(5, 0.05, 3)
+    m = gpu_mesh(wp, P, I, leaf)
+    tree = oracle_mod.mesh_lbvh_build(P, I, leaf)
+    S, D = mg.random_rays(P, 30000, seed=4)
+    S[::3] *= np.float32(0.2)  # a third of the rays start inside
+    D[:60] = np.eye(3, dtype=np.float32)[np.arange(60) % 3] * np.float32(-1.0) ** (np.arange(60) // 3)[:, None].astype(np.float32)
+    for mt in (0.6, 1e6):
+        got = wp.mesh_query_ray_anyhit(m, S, D, mt)
+        assert np.array_equal(got, oracle_mod.query_ray_anyhit(P, I, tree, S, D, mt).astype(bool))
+        assert np.array_equal(got, wp.mesh_query_ray(m, S, D, mt).result.astype(bool))
+    cnt = wp.mesh_query_ray_count_intersections(m, S, D)
+    assert np.array_equal(cnt, oracle_mod.query_ray_count(P, I, tree, S, D))
+    inside = np.linalg.norm(S, axis=1) < 0.8
+    assert inside.sum() > 5000 and np.all(cnt[inside] % 2 == 1) and np.all(cnt[~inside & (np.linalg.norm(S, axis=1) > 1.3)] % 2 == 0)
+    # device arrays in -> device arrays out
+    ds, dd = wp.array(S, dtype=wp.vec3), wp.array(D, dtype=wp.vec3)
+    assert np.array_equal(wp.mesh_query_ray_count_intersections(m, ds, dd).numpy(), cnt)
+    assert np.array_equal(wp.mesh_query_ray_anyhit(m, ds, dd, 1e6).numpy().astype(bool), got)
+
+
+def test_mesh_eval_follows_point_and_velocity_updates(wp, oracle_mod):
+    P, I = mg.noisy_sphere(3, 0.05, 9)
+    rng = np.random.default_rng(10)
+    vel = rng.standard_normal(P.shape).astype(np.float32)
+    nt = len(I.reshape(-1, 3))
+    F = rng.integers(0, nt, 5000).astype(np.int32)
+    U = rng.random(5000).astype(np.float32)
+    V = ((1 - U) * rng.random(5000)).astype(np.float32)
+    m = wp.Mesh(wp.array(P, dtype=wp.vec3), wp.array(I, dtype=wp.int32), bvh_constructor="lbvh")
+    assert np.array_equal(wp.mesh_eval_position(m, F, U, V), oracle_mod.mesh_eval(P, I, F, U, V))
+    assert np.array_equal(wp.mesh_eval_velocity(m, F, U, V), np.zeros((5000, 3), np.float32))  # mesh.h:2791-2792
+    m = wp.Mesh(wp.array(P, dtype=wp.vec3), wp.array(I, dtype=wp.int32), velocities=wp.array(vel, dtype=wp.vec3),
+                bvh_constructor="lbvh")
+    assert np.array_equal(wp.mesh_eval_velocity(m, F, U, V), oracle_mod.mesh_eval(vel, I, F, U, V))
+    vel2 = (vel * np.float32(-2.0)).astype(np.float32)
+    m.velocities = wp.array(vel2, dtype=wp.vec3)
+    assert np.array_equal(wp.mesh_eval_velocity(m, F, U, V), oracle_mod.mesh_eval(vel2, I, F, U, V))
+    P2 = (P * np.float32(1.5) + np.float32(0.25)).astype(np.float32)
+    m.points = wp.array(P2, dtype=wp.vec3)
+    assert np.array_equal(wp.mesh_eval_position(m, F, U, V), oracle_mod.mesh_eval(P2, I, F, U, V))
+    # closest point of a query evaluates back onto the surface point the query found
+    Q = mg.box_queries(P2, 2000, seed=11)
+    r = wp.mesh_query_point_no_sign(m, Q, 1e6)
+    pos = wp.mesh_eval_position(m, r.face, r.u, r.v)
+    want = oracle_mod.query_point_no_sign(P2, I, oracle_mod.mesh_lbvh_build(P2, I, 4), Q, 1e6)
+    assert np.array_equal(r.face, want["face"])
+    assert np.all(np.linalg.norm(pos - Q, axis=1) <= np.linalg.norm(P2, axis=1).max() * 2)
+
+
+def test_ray_variants_empty_inputs(wp):
+    P, I = mg.noisy_sphere(1, 0.0, 1)
+    m = gpu_mesh(wp, P, I, 4)
+    z = np.zeros((0, 3), np.float32)
+    assert wp.mesh_query_ray_anyhit(m, z, z, 1.0).shape == (0,)
+    assert wp.mesh_query_ray_count_intersections(m, z, z).shape == (0,)
+    assert wp.mesh_eval_position(m, np.zeros(0, np.int32), np.zeros(0, np.float32), np.zeros(0, np.float32)).shape == (0, 3)
+    with pytest.raises(RuntimeError):
+        wp.mesh_query_ray_anyhit(m, np.zeros((3, 3), np.float32), np.zeros((2, 3), np.float32), 1.0)

@@ -280,3 +280,47 @@ def test_generic_bvh_query_restatement_vs_brute_force(oracle_mod, leaf):
         off, idx = oracle_mod.bvh_query(tree, lo, hi, s, d, ray=True, max_dist=md)
         for i, want in enumerate(_brute_ray(lo, hi, s, d, np.float32(md))):
             assert sorted(idx[off[i] : off[i + 1]].tolist()) == want.tolist()
+
+
+# ------------------------------------------------------------------------------------------------
+# any-hit / intersection count / eval_position
+# ------------------------------------------------------------------------------------------------
+RAYV_GOLD = os.path.join(os.path.dirname(__file__), "golden", "golden_ray_variants.npz")
+
+
+def test_ray_variants_match_reference_fixture(oracle_mod, gold):
+    o = oracle_mod
+    rv = np.load(RAYV_GOLD)
+    P, I = gold["mesh_points"], gold["mesh_indices"]
+    S, D = rv["starts"], rv["dirs"]
+    for name in ("sah", "lbvh1", "lbvh4"):
+        tree = {k: gold[f"{name}_tree_{k}"] for k in ("node_lowers", "node_uppers", "primitive_indices")}
+        tree["root"] = int(gold[f"{name}_tree_root"])
+        for mt in (0.5, 1.0, 1e6):
+            assert np.array_equal(o.query_ray_anyhit(P, I, tree, S, D, mt), rv[f"{name}_anyhit_{mt:g}"])
+        cnt = o.query_ray_count(P, I, tree, S, D)
+        assert np.array_equal(cnt, rv[f"{name}_count"])
+        assert np.array_equal(o.mesh_eval(P, I, rv["eval_face"], rv["eval_u"], rv["eval_v"]), rv[f"{name}_eval_position"])
+    # closed surface: rays starting inside (even rows) cross it an odd number of times, and the counts do
+    # not depend on the tree
+    assert np.all(rv["sah_count"][::2][np.linalg.norm(S[::2], axis=1) < 0.8] % 2 == 1)
+    assert np.array_equal(rv["sah_count"], rv["lbvh1_count"])
+    assert rv["sah_anyhit_1e+06"].sum() > 256 and rv["sah_anyhit_0.5"].sum() < rv["sah_anyhit_1e+06"].sum()
+
+
+def test_ray_variants_live_reference(oracle_mod):
+    o = oracle_mod
+    if not o.ref_available():
+        pytest.skip("oracle/_ref/libwarp_ref_cpu.so not present")
+    P, I = mg.noisy_sphere(3, noise=0.1, seed=5)
+    S, D = mg.random_rays(P, 4000, seed=6)
+    S[::3] *= np.float32(0.2)
+    D[:30] = np.eye(3, dtype=np.float32)[np.arange(30) % 3]
+    for leaf in (1, 4):
+        tree = o.mesh_lbvh_build(P, I, leaf)
+        rm = o.RefMesh.from_tree(P, I, tree)
+        for mt in (0.7, 1e6):
+            a = o.query_ray_anyhit(P, I, tree, S, D, mt)
+            assert np.array_equal(a, rm.query_ray_anyhit(S, D, mt))
+            assert np.array_equal(a, o.query_ray(P, I, tree, S, D, mt)["result"])
+        assert np.array_equal(o.query_ray_count(P, I, tree, S, D), rm.query_ray_count(S, D))

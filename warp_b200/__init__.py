@@ -39,7 +39,11 @@ from .queries import (  # noqa: F401
     MeshQueryRay,
     mesh_query_point,
     mesh_query_point_no_sign,
+    mesh_eval_position,
+    mesh_eval_velocity,
     mesh_query_ray,
+    mesh_query_ray_anyhit,
+    mesh_query_ray_count_intersections,
     query_stats,
 )
 

@@ -701,6 +701,76 @@ int wp_b200_mesh_query_ray(uint64_t id, const float* starts, const float* dirs, 
     return query_ray_on(m, starts, dirs, n, max_t, result, sign, face, t, u, v, normal, current_stream(m->bvh.device));
 }
 
+int wp_b200_mesh_query_ray_anyhit(uint64_t id, const float* starts, const float* dirs, int64_t n, float max_t,
+                                  uint8_t* result)
+{
+    MeshState* m = query_mesh(id);
+    if (!m)
+        return 0;
+    DeviceGuard g(m->bvh.device);
+    cudaStream_t st = current_stream(m->bvh.device);
+    if (n <= 0)
+        return 1;
+    if (m->bvh.n == 0)
+        return check(cudaMemsetAsync(result, 0, (size_t)n, st), "memset");
+    const char* err = wb_query_ray_anyhit(make_view(m->bvh), starts, dirs, n, max_t, result, st);
+    if (err) {
+        set_error("Warp error: mesh any-hit query failed: %s", err);
+        return 0;
+    }
+    return 1;
+}
+
+int wp_b200_mesh_query_ray_count_intersections(uint64_t id, const float* starts, const float* dirs, int64_t n,
+                                               int32_t* counts)
+{
+    MeshState* m = query_mesh(id);
+    if (!m)
+        return 0;
+    DeviceGuard g(m->bvh.device);
+    cudaStream_t st = current_stream(m->bvh.device);
+    if (n <= 0)
+        return 1;
+    if (m->bvh.n == 0)
+        return check(cudaMemsetAsync(counts, 0, 4 * (size_t)n, st), "memset");
+    const char* err = wb_query_ray_count(make_view(m->bvh), starts, dirs, n, counts, st);
+    if (err) {
+        set_error("Warp error: mesh intersection count failed: %s", err);
+        return 0;
+    }
+    return 1;
+}
+
+static int mesh_eval(uint64_t id, int velocity, const int32_t* face, const float* u, const float* v, int64_t n, float* out)
+{
+    MeshState* m = query_mesh(id);
+    if (!m)
+        return 0;
+    DeviceGuard g(m->bvh.device);
+    cudaStream_t st = current_stream(m->bvh.device);
+    if (n <= 0)
+        return 1;
+    const uint64_t attr = velocity ? m->velocities_data : m->points_data;
+    if (!attr || !m->indices_data)  // mesh.h:2771-2772, 2791-2792: vec3()
+        return check(cudaMemsetAsync(out, 0, 12 * (size_t)n, st), "memset");
+    const char* err = wb_mesh_eval((const float*)attr, (const int*)m->indices_data, face, u, v, n, out, st);
+    if (err) {
+        set_error("Warp error: mesh evaluation failed: %s", err);
+        return 0;
+    }
+    return 1;
+}
+
+int wp_b200_mesh_eval_position(uint64_t id, const int32_t* face, const float* u, const float* v, int64_t n, float* out)
+{
+    return mesh_eval(id, 0, face, u, v, n, out);
+}
+
+int wp_b200_mesh_eval_velocity(uint64_t id, const int32_t* face, const float* u, const float* v, int64_t n, float* out)
+{
+    return mesh_eval(id, 1, face, u, v, n, out);
+}
+
 // ------------------------------------------------------------------------------------------------
 // queries (host buffers): chunked, two lanes so the copies of one chunk overlap the traversal of
 // the other.  Fully asynchronous only when the caller's buffers are pinned (wp_alloc_pinned).

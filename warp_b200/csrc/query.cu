@@ -555,6 +555,131 @@ k_query_ray(TreeView tv, const float* __restrict__ starts, const float* __restri
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// further ray queries sharing the traversal core
+//   ANYHIT: mesh_query_ray_anyhit (mesh.h:1893-1974) -- is there any hit with 0 <= t < max_t
+//   COUNT : mesh_query_ray_count_intersections (mesh.h:1976-2032) -- number of hits with t >= 0 along the
+//           whole ray (robust slab test, push-both traversal, no distance bound)
+// Both answers are order independent (a fixed bound, no running minimum), so they equal the reference's.
+// ------------------------------------------------------------------------------------------------
+template <bool COUNT_MODE>
+__global__ void __launch_bounds__(QT)
+k_query_ray_aux(TreeView tv, const float* __restrict__ starts, const float* __restrict__ dirs, long long nq, float max_t,
+                uint8_t* __restrict__ any_out, int* __restrict__ count_out)
+{
+    const TreeHeader h = *tv.header;
+    for (long long i = (long long)blockIdx.x * QT + threadIdx.x; i < nq; i += (long long)gridDim.x * QT) {
+        const float3 org = make_float3(__ldg(starts + 3 * i), __ldg(starts + 3 * i + 1), __ldg(starts + 3 * i + 2));
+        const float3 dir = make_float3(__ldg(dirs + 3 * i), __ldg(dirs + 3 * i + 1), __ldg(dirs + 3 * i + 2));
+        const WoopRay wr = woop_setup(dir);
+        Entry stack[WB_QUERY_STACK];
+        int top = 0;
+        Entry root;
+        if (h.root_ref & WB_LEAF)
+            root.a = WB_LEAF | 0u, root.b = h.root_count;
+        else
+            root.a = (h.root_ref & WB_IDX_MASK) - (uint32_t)tv.n, root.b = 0;
+
+        if (COUNT_MODE) {
+            const float3 rcp = make_float3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+            int hits = 0;
+            float tt;
+            if (ray_aabb_robust(org, dir, rcp, make_float3(h.lx, h.ly, h.lz), make_float3(h.hx, h.hy, h.hz), tt))
+                stack[top++] = root;
+            while (top) {
+                const Entry cur = stack[--top];
+                if (cur.a & WB_LEAF) {
+                    const uint32_t start = cur.a & WB_IDX_MASK;
+                    for (uint32_t pos = start; pos < start + cur.b; ++pos) {
+                        const Tri t = load_tri(tv.tris, pos);
+                        float t_hit, tu, tvv, ts;
+                        if (ray_tri(wr, org, t.p, t.q, t.r, t_hit, tu, tvv, ts) && t_hit >= 0.0f)
+                            hits++;
+                    }
+                } else {
+                    const Pair pr = load_pair(tv.pairs, cur.a, tv.n);
+                    // children are tested before the push (the reference tests on pop, mesh.h:1996): same
+                    // count, shallower stack.  The reference has no overflow check here (undefined past 32
+                    // entries); subtrees that do not fit are dropped instead.
+                    if (top < WB_QUERY_STACK && ray_aabb_robust(org, dir, rcp, pr.llo, pr.lhi, tt))
+                        stack[top++] = pr.left;
+                    if (top < WB_QUERY_STACK && ray_aabb_robust(org, dir, rcp, pr.rlo, pr.rhi, tt))
+                        stack[top++] = pr.right;
+                }
+            }
+            count_out[i] = hits;
+        } else {
+            float3 safe = dir;
+            if (safe.x == 0.0f)
+                safe.x = 1.0e-20f;
+            if (safe.y == 0.0f)
+                safe.y = 1.0e-20f;
+            if (safe.z == 0.0f)
+                safe.z = 1.0e-20f;
+            const float3 rcp = make_float3(1.0f / safe.x, 1.0f / safe.y, 1.0f / safe.z);
+            const bool fast = dir.x != 0.0f && dir.y != 0.0f && dir.z != 0.0f;
+            Entry cur = root;
+            bool found = false;
+            for (;;) {
+                if (cur.a & WB_LEAF) {
+                    const uint32_t start = cur.a & WB_IDX_MASK;
+                    for (uint32_t pos = start; pos < start + cur.b && !found; ++pos) {
+                        const Tri t = load_tri(tv.tris, pos);
+                        float t_hit, tu, tvv, ts;
+                        if (ray_tri(wr, org, t.p, t.q, t.r, t_hit, tu, tvv, ts) && t_hit < max_t && t_hit >= 0.0f)
+                            found = true;
+                    }
+                    if (found || top == 0)
+                        break;
+                    cur = stack[--top];
+                    continue;
+                }
+                const Pair pr = load_pair(tv.pairs, cur.a, tv.n);
+                float t0 = FLT_MAX, t1 = FLT_MAX;
+                const bool h0 = (fast ? ray_aabb_fast(org, rcp, pr.llo, pr.lhi, t0)
+                                      : ray_aabb_robust(org, dir, rcp, pr.llo, pr.lhi, t0))
+                    && t0 < max_t;
+                const bool h1 = (fast ? ray_aabb_fast(org, rcp, pr.rlo, pr.rhi, t1)
+                                      : ray_aabb_robust(org, dir, rcp, pr.rlo, pr.rhi, t1))
+                    && t1 < max_t;
+                if (h0 && h1) {
+                    if (top >= WB_QUERY_STACK)
+                        break;  // mesh.h:1957-1958 returns false
+                    const bool near_left = t0 < t1;
+                    stack[top++] = near_left ? pr.right : pr.left;
+                    cur = near_left ? pr.left : pr.right;
+                } else if (h0) {
+                    cur = pr.left;
+                } else if (h1) {
+                    cur = pr.right;
+                } else {
+                    if (top == 0)
+                        break;
+                    cur = stack[--top];
+                }
+            }
+            any_out[i] = found ? 1 : 0;
+        }
+    }
+}
+
+// mesh_eval_position / mesh_eval_velocity (mesh.h:2767-2807): p*u + q*v + r*(1-u-v) from the caller's arrays
+__global__ void __launch_bounds__(QT)
+k_mesh_eval(const float* __restrict__ attr, const int* __restrict__ indices, const int* __restrict__ face,
+            const float* __restrict__ u, const float* __restrict__ v, long long n, float* __restrict__ out)
+{
+    for (long long i = (long long)blockIdx.x * QT + threadIdx.x; i < n; i += (long long)gridDim.x * QT) {
+        const int f = face[i];
+        const int a = __ldg(indices + 3 * (size_t)f), b = __ldg(indices + 3 * (size_t)f + 1), c = __ldg(indices + 3 * (size_t)f + 2);
+        const float uu = u[i], vv = v[i], ww = 1.0f - uu - vv;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float p = __ldg(attr + 3 * (size_t)a + k), q = __ldg(attr + 3 * (size_t)b + k), r = __ldg(attr + 3 * (size_t)c + k);
+            out[3 * i + k] = p * uu + q * vv + r * ww;
+        }
+    }
+}
+
 int query_grid(long long nq)
 {
     int dev = 0, sms = 148;
@@ -600,6 +725,36 @@ const char* wb_query_ray(const TreeView& tv, const float* starts, const float* d
         k_query_ray<true><<<grid, QT, 0, stream>>>(tv, starts, dirs, perm, nq, max_t, result, sign, face, t, u, v, normal, stats);
     else
         k_query_ray<false><<<grid, QT, 0, stream>>>(tv, starts, dirs, perm, nq, max_t, result, sign, face, t, u, v, normal, stats);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+const char* wb_query_ray_anyhit(const TreeView& tv, const float* starts, const float* dirs, long long nq, float max_t,
+                                uint8_t* result, cudaStream_t stream)
+{
+    if (nq <= 0)
+        return nullptr;
+    k_query_ray_aux<false><<<query_grid(nq), QT, 0, stream>>>(tv, starts, dirs, nq, max_t, result, nullptr);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+const char* wb_query_ray_count(const TreeView& tv, const float* starts, const float* dirs, long long nq, int* counts,
+                               cudaStream_t stream)
+{
+    if (nq <= 0)
+        return nullptr;
+    k_query_ray_aux<true><<<query_grid(nq), QT, 0, stream>>>(tv, starts, dirs, nq, 0.0f, nullptr, counts);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+const char* wb_mesh_eval(const float* attr, const int* indices, const int* face, const float* u, const float* v,
+                         long long n, float* out, cudaStream_t stream)
+{
+    if (n <= 0)
+        return nullptr;
+    k_mesh_eval<<<query_grid(n), QT, 0, stream>>>(attr, indices, face, u, v, n, out);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

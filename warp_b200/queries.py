@@ -18,7 +18,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from .types import Mesh, array, empty, float32, int32, uint8, vec3
+from .types import Mesh, array, empty, float32, from_numpy, int32, uint8, vec3
 
 
 class MeshQueryPoint:
@@ -154,6 +154,77 @@ def mesh_query_ray(mesh, starts, dirs, max_t: float, out: MeshQueryRay | None = 
                                        _p(out.t), _p(out.u), _p(out.v), _p(out.normal))  # fmt: skip
     _check(ok, "mesh_query_ray")
     return out
+
+
+def _stage(a, dtype, dev, what):
+    """(device array, was_host): host arrays are uploaded; device arrays are type-checked and passed through."""
+    if isinstance(a, array):
+        if a.dtype != dtype:
+            raise RuntimeError(f"{what} should be an array of type {dtype!r}")
+        return a, False
+    if dtype == vec3:
+        return from_numpy(_host_vec3(a, what), vec3, dev), True
+    h = np.ascontiguousarray(a, dtype=dtype.np_dtype)
+    if h.ndim != 1:
+        raise RuntimeError(f"{what} should be one-dimensional")
+    return from_numpy(h, dtype, dev), True
+
+
+def _ray_pair(mesh, starts, dirs):
+    id_, dev = _mesh_id(mesh)
+    if isinstance(starts, array) != isinstance(dirs, array):
+        raise RuntimeError("starts and dirs must both be device arrays or both be host arrays")
+    s, host = _stage(starts, vec3, dev, "starts")
+    d, _ = _stage(dirs, vec3, dev, "dirs")
+    if len(s) != len(d):
+        raise RuntimeError("starts and dirs must have the same length")
+    return id_, dev, s, d, host
+
+
+def mesh_query_ray_anyhit(mesh, starts, dirs, max_t: float):
+    """``result[i]`` = some triangle is hit by ray i with ``0 <= t < max_t`` (mesh.h:1893-1974).
+    Device arrays in -> device ``uint8`` array out; host arrays in -> numpy ``bool`` array out."""
+    id_, dev, s, d, host = _ray_pair(mesh, starts, dirs)
+    out = empty(len(s), uint8, dev)
+    ok = _lib.core().wp_b200_mesh_query_ray_anyhit(id_, _p(s), _p(d), len(s), float(max_t), _p(out))
+    _check(ok, "mesh_query_ray_anyhit")
+    return out.numpy().astype(bool) if host else out
+
+
+def mesh_query_ray_count_intersections(mesh, starts, dirs):
+    """Number of triangles hit by ray i with ``t >= 0``, over the whole ray (mesh.h:1976-2032)."""
+    id_, dev, s, d, host = _ray_pair(mesh, starts, dirs)
+    out = empty(len(s), int32, dev)
+    ok = _lib.core().wp_b200_mesh_query_ray_count_intersections(id_, _p(s), _p(d), len(s), _p(out))
+    _check(ok, "mesh_query_ray_count_intersections")
+    return out.numpy() if host else out
+
+
+def _mesh_eval(mesh, face, u, v, velocity):
+    id_, dev = _mesh_id(mesh)
+    kinds = {isinstance(x, array) for x in (face, u, v)}
+    if len(kinds) != 1:
+        raise RuntimeError("face, u and v must all be device arrays or all be host arrays")
+    f, host = _stage(face, int32, dev, "face")
+    uu, _ = _stage(u, float32, dev, "u")
+    vv, _ = _stage(v, float32, dev, "v")
+    if not (len(f) == len(uu) == len(vv)):
+        raise RuntimeError("face, u and v must have the same length")
+    out = empty(len(f), vec3, dev)
+    c = _lib.core()
+    fn = c.wp_b200_mesh_eval_velocity if velocity else c.wp_b200_mesh_eval_position
+    _check(fn(id_, _p(f), _p(uu), _p(vv), len(f), _p(out)), "mesh_eval")
+    return out.numpy() if host else out
+
+
+def mesh_eval_position(mesh, face, u, v):
+    """``p*u + q*v + r*(1-u-v)`` on triangle ``face[i]`` of the mesh's current points (mesh.h:2767-2785)."""
+    return _mesh_eval(mesh, face, u, v, False)
+
+
+def mesh_eval_velocity(mesh, face, u, v):
+    """Same interpolation over the mesh's velocities; zeros when it has none (mesh.h:2787-2805)."""
+    return _mesh_eval(mesh, face, u, v, True)
 
 
 class query_stats:
