@@ -132,7 +132,7 @@ def load(path: str | None = None) -> ctypes.CDLL:
     global _core
     if _core is not None and path is None:
         return _core
-    p = path or LIB_PATH
+    p = path or os.environ.get("WARP_B200_LIB") or LIB_PATH  # WARP_B200_LIB: A/B builds (scripts/build_variants.sh)
     if not os.path.exists(p):
         raise RuntimeError(
             f"warp_b200: native library {p} is not built; run `python -m warp_b200.build` "

@@ -715,8 +715,7 @@ template <class Src, class KeyT, bool GROUPED> const char* build_impl(BvhState& 
     k_leaves<Src, KeyT, GROUPED><<<wb_div_up(n, BT), BT, 0, stream>>>(src, n, keys, s.prim, s.pairs, s.pos_parent, s.tris);
     {
         const MergeArgs<KeyT> ma { n, s.leaf_size, keys, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters, s.header };
-        const int merge_threads = wb_div_up(n, MC);
-        k_merge<false, KeyT, GROUPED><<<wb_div_up(merge_threads, 128), 128, 0, stream>>>(ma);
+        k_merge<false, KeyT, GROUPED><<<wb_div_up(n, BP), TBM, 0, stream>>>(ma);
     }
     // K5/K6 depth rule (early-out unless the tree is at least 32 levels deep)
     k_deep_fix_positions<KeyT, GROUPED><<<wb_div_up(n, BT), BT, 0, stream>>>(n, s.header, keys, s.pairs, s.parent_int,
@@ -864,13 +863,13 @@ const char* wb_refit_merge(BvhState& s, cudaStream_t stream)
 {
     if (s.n <= 1)
         return nullptr;
-    const int grid = wb_div_up(wb_div_up(s.n, MC), 128);
+    const int grid = wb_div_up(s.n, BP);
     if (s.key_bytes == 4) {
         const MergeArgs<uint32_t> ma { s.n, s.leaf_size, (const uint32_t*)s.keys, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters, s.header };
-        k_merge<true, uint32_t, false><<<grid, 128, 0, stream>>>(ma);
+        k_merge<true, uint32_t, false><<<grid, TBM, 0, stream>>>(ma);
     } else {
         const MergeArgs<uint64_t> ma { s.n, s.leaf_size, (const uint64_t*)s.keys, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters, s.header };
-        k_merge<true, uint64_t, false><<<grid, 128, 0, stream>>>(ma);  // the static-tree replay never consults groups
+        k_merge<true, uint64_t, false><<<grid, TBM, 0, stream>>>(ma);  // the static-tree replay never consults groups
     }
     WB_CUDA_TRY(cudaGetLastError());
     return nullptr;
