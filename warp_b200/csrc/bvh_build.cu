@@ -460,6 +460,44 @@ void onesweep_sort(KeyT* keys, KeyT* keys_alt, int* vals, int* vals_alt, int n, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// K4a: leaves (bvh.cu:228-255) -- one thread per sorted position: gather the triangle, refresh the
+// packed-triangle cache and write the leaf's node record straight into its parent's pair (which
+// pair is a function of the neighbouring keys only).  K4b (merge.cuh) then merges bottom-up.
+// ---------------------------------------------------------------------------------------------
+template <class Src, class KeyT, bool GROUPED>
+__global__ void __launch_bounds__(BT)
+k_leaves(Src src, int n, const KeyT* __restrict__ keys, const int* __restrict__ prim, NodeRec* __restrict__ pairs,
+         int* __restrict__ pos_parent, float4* __restrict__ tris)
+{
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= n)
+        return;
+    const int item = __ldg(prim + i);
+    float3 lo, hi;
+    if constexpr (Src::kIsMesh) {
+        float3 p, q, r;
+        src.tri(item, p, q, r);
+        lo = wb_min3(wb_min3(p, q), r);
+        hi = wb_max3(wb_max3(p, q), r);
+        // sliver flag of the closest-point query (mesh.h:557-564), a per-triangle constant
+        const float3 e0 = wb_sub(q, p), e1 = wb_sub(r, p), e2 = wb_sub(r, q);
+        const float3 nrm = wb_cross(e0, e1);
+        const float area2 = sqrtf(nrm.x * nrm.x + nrm.y * nrm.y + nrm.z * nrm.z);
+        const bool sliver = area2 / (wb_dot(e0, e0) + wb_dot(e1, e1) + wb_dot(e2, e2)) < 1.e-6f;
+        float4* t = tris + 3 * (size_t)i;
+        t[0] = make_float4(p.x, p.y, p.z, q.x);
+        t[1] = make_float4(q.y, q.z, r.x, r.y);
+        t[2] = make_float4(r.z, __int_as_float(item), __uint_as_float(sliver ? WB_TRI_SLIVER : 0u), 0.f);
+    } else {
+        src.bounds(item, lo, hi);
+    }
+    pos_parent[i] = WB_NO_PARENT;
+    const bool go_right = wb_goes_right<KeyT, GROUPED>(keys, prim, n, i, i);
+    NodeRec* rec = pairs + 2 * (size_t)(go_right ? i : i - 1) + (go_right ? 0 : 1);
+    wb_store_rec(rec, lo, hi, (uint32_t)i | WB_LEAF, (uint32_t)i);  // a single item always fits leaf_size >= 1
+}
+
+// ---------------------------------------------------------------------------------------------
 // K5/K6: depth rule (bvh.cu:419-441): a single-group node at depth >= 32 (root = 1) becomes a
 // packed leaf whatever its size.  Only trees taller than 30 edges can contain such a node;
 // everything else returns after one header read.
@@ -673,11 +711,11 @@ template <class Src, class KeyT, bool GROUPED> const char* build_impl(BvhState& 
         onesweep_sort<KeyT>(keys, keys_alt, s.prim, s.prim_alt, n, s.ghist, s.tile_status, s.tickets, stream);
     }
 
-    // K4 leaves (bvh.cu:228-255) + hierarchy (bvh.cu:261-393) in one kernel (merge.cuh)
+    // K4a leaves, K4b chunked bottom-up merge
+    k_leaves<Src, KeyT, GROUPED><<<wb_div_up(n, BT), BT, 0, stream>>>(src, n, keys, s.prim, s.pairs, s.pos_parent, s.tris);
     {
-        const MergeArgs<Src, KeyT> ma { src, n, s.leaf_size, keys, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters,
-                                        s.header, s.tris };
-        WB_CUDA_TRY((wb_launch_tree<false, Src, KeyT, GROUPED>(ma, stream)));
+        const MergeArgs<KeyT> ma { n, s.leaf_size, keys, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters, s.header };
+        k_merge<false, KeyT, GROUPED><<<wb_div_up(n, BP), TBM, 0, stream>>>(ma);
     }
     // K5/K6 depth rule (early-out unless the tree is at least 32 levels deep)
     k_deep_fix_positions<KeyT, GROUPED><<<wb_div_up(n, BT), BT, 0, stream>>>(n, s.header, keys, s.pairs, s.parent_int,
@@ -816,6 +854,23 @@ const char* wb_export_reference_layout(BvhState& s, cudaStream_t stream)
     else
         k_export_reference_layout<uint64_t, false><<<grid, BT, 0, stream>>>(s.n, s.leaf_size, s.header, (const uint64_t*)s.keys,
                                                                             s.pairs, s.parent_int, lo, hi, s.ref_parents, s.ref_root);
+    WB_CUDA_TRY(cudaGetLastError());
+    return nullptr;
+}
+
+// the refit's merge pass lives here because it shares the key-typed instantiations
+const char* wb_refit_merge(BvhState& s, cudaStream_t stream)
+{
+    if (s.n <= 1)
+        return nullptr;
+    const int grid = wb_div_up(s.n, BP);
+    if (s.key_bytes == 4) {
+        const MergeArgs<uint32_t> ma { s.n, s.leaf_size, (const uint32_t*)s.keys, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters, s.header };
+        k_merge<true, uint32_t, false><<<grid, TBM, 0, stream>>>(ma);
+    } else {
+        const MergeArgs<uint64_t> ma { s.n, s.leaf_size, (const uint64_t*)s.keys, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters, s.header };
+        k_merge<true, uint64_t, false><<<grid, TBM, 0, stream>>>(ma);  // the static-tree replay never consults groups
+    }
     WB_CUDA_TRY(cudaGetLastError());
     return nullptr;
 }

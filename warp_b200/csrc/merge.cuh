@@ -20,18 +20,16 @@
 #endif
 constexpr int MC = WB_MC;  // sorted positions per merge thread
 
-template <class Src, class KeyT> struct MergeArgs {
-    Src src;  // item source: triangles of a mesh or caller-provided boxes
+template <class KeyT> struct MergeArgs {
     int n;
     int leaf_size;
-    const KeyT* keys;  // builder only
+    const KeyT* keys;
     const int* prim;
     NodeRec* pairs;
     int* parent_int;
     int* pos_parent;
     unsigned* counters;
     TreeHeader* hdr;
-    float4* tris;  // packed-triangle cache (meshes)
 };
 
 __device__ __forceinline__ int wb_clz_key(uint32_t x) { return __clz((int)x); }
@@ -135,16 +133,8 @@ __device__ __forceinline__ void wb_store_box(NodeRec* dst, float3 lo, float3 hi)
 #ifndef WB_TBM
 #define WB_TBM 256
 #endif
-constexpr int TBM = WB_TBM;   // threads per block
+constexpr int TBM = WB_TBM;   // merge threads per block
 constexpr int BP = TBM * MC;  // sorted positions per block
-static_assert(BP <= 4096, "the shared arrival word keeps 12 bits of range offset");
-
-// shared arrival word of an interior split: bit 0 arrival parity, bit 1 side of the first arrival (1 = right
-// child), bits 2..13 far end of its range (offset from the block start), bits 14..29 its height
-__device__ __forceinline__ unsigned wb_pack_arrival(bool right_child, int far_off, unsigned h)
-{
-    return 1u | (right_child ? 2u : 0u) | ((unsigned)far_off << 2) | (h << 14);
-}
 
 // arrival at a block-private counter: release / acquire at CTA scope only (MEMBAR.CTA, no L1 invalidation)
 __device__ __forceinline__ unsigned wb_arrive_cta(unsigned* counter, unsigned add)
@@ -155,34 +145,9 @@ __device__ __forceinline__ unsigned wb_arrive_cta(unsigned* counter, unsigned ad
     return old;
 }
 
-// item at sorted position k: its bounds and, for meshes, its packed-triangle record (sliver flag of the
-// closest-point query, mesh.h:557-564, is a per-triangle constant)
-template <class Src, bool WRITE>
-__device__ __forceinline__ void wb_load_item(const Src& src, int item, float4* __restrict__ tris, int k, float3& lo, float3& hi)
-{
-    if constexpr (Src::kIsMesh) {
-        float3 p, q, r;
-        src.tri(item, p, q, r);
-        lo = wb_min3(wb_min3(p, q), r);
-        hi = wb_max3(wb_max3(p, q), r);
-        if (WRITE) {
-            const float3 e0 = wb_sub(q, p), e1 = wb_sub(r, p), e2 = wb_sub(r, q);
-            const float3 nrm = wb_cross(e0, e1);
-            const float area2 = sqrtf(nrm.x * nrm.x + nrm.y * nrm.y + nrm.z * nrm.z);
-            const bool sliver = area2 / (wb_dot(e0, e0) + wb_dot(e1, e1) + wb_dot(e2, e2)) < 1.e-6f;
-            float4* t = tris + 3 * (size_t)k;
-            t[0] = make_float4(p.x, p.y, p.z, q.x);
-            t[1] = make_float4(q.y, q.z, r.x, r.y);
-            t[2] = make_float4(r.z, __int_as_float(item), __uint_as_float(sliver ? WB_TRI_SLIVER : 0u), 0.f);
-        }
-    } else {
-        src.bounds(item, lo, hi);
-    }
-}
-
 // builder: the node in hand covers [0, n-1]
-template <class A, class KeyT, bool GROUPED>
-__device__ __forceinline__ void wb_write_root(const A& a, uint32_t xnode, unsigned xh, float3 lo, float3 hi)
+template <class KeyT, bool GROUPED>
+__device__ __forceinline__ void wb_write_root(const MergeArgs<KeyT>& a, uint32_t xnode, unsigned xh, float3 lo, float3 hi)
 {
     const int n = a.n;
     const uint32_t self_ref = xnode | (wb_size_leaf<KeyT, GROUPED>(a.keys, a.leaf_size, 0, n - 1) ? WB_LEAF : 0u);
@@ -199,12 +164,13 @@ __device__ __forceinline__ void wb_write_root(const A& a, uint32_t xnode, unsign
         a.pos_parent[0] = WB_ROOT_PARENT;
 }
 
-// the node in hand -- a child of n+s, the left one when go_right -- absorbs its sibling (box slo/shi, range ending
-// at far_end, height other_h) and becomes n+s
-template <bool REFIT, bool GROUPED, class A, class K>
-__device__ __forceinline__ void wb_absorb(const A& a, const K& kv, int s, bool go_right, float3 slo, float3 shi, int far_end,
+// the node in hand -- a child of n+s, the left one when go_right -- absorbs its sibling's record (s0, s1) and
+// becomes n+s
+template <bool REFIT, class KeyT, bool GROUPED, class K>
+__device__ __forceinline__ void wb_absorb(const MergeArgs<KeyT>& a, const K& kv, int s, bool go_right, float4 s0, float4 s1,
                                           unsigned other_h, float3& lo, float3& hi, int& xl, int& xr, unsigned& xh)
 {
+    const int far_end = (int)__float_as_uint(s1.w);
     const int new_left = go_right ? xl : far_end;
     const int new_right = go_right ? far_end : xr;
     if (!REFIT) {
@@ -217,15 +183,15 @@ __device__ __forceinline__ void wb_absorb(const A& a, const K& kv, int s, bool g
         }
         xh = max(xh, other_h) + 1u;
     }
-    lo = wb_min3(lo, slo);
-    hi = wb_max3(hi, shi);
+    lo = wb_min3(lo, make_float3(s0.x, s0.y, s0.z));
+    hi = wb_max3(hi, make_float3(s1.x, s1.y, s1.z));
     xl = new_left, xr = new_right;
 }
 
 // Phase B: child `side` (0 left, 1 right) of n+s, whose record is in memory, arrives at the GLOBAL counter of
 // n+s and, whenever it is the second child to do so, becomes the parent and climbs on (bvh.cu:261-393, 42-144)
-template <bool REFIT, class KeyT, bool GROUPED, class A>
-__device__ __noinline__ void wb_climb(const A& a, int s, int side, unsigned h)
+template <bool REFIT, class KeyT, bool GROUPED>
+__device__ __noinline__ void wb_climb(const MergeArgs<KeyT>& a, int s, int side, unsigned h)
 {
     const int n = a.n;
     float3 lo = make_float3(0.f, 0.f, 0.f), hi = lo;
@@ -249,8 +215,8 @@ __device__ __noinline__ void wb_climb(const A& a, int s, int side, unsigned h)
             loaded = true;
         }
         const float4 s0 = __ldcg(pair4 + 2 * (1 - side)), s1 = __ldcg(pair4 + 2 * (1 - side) + 1);
-        wb_absorb<REFIT, GROUPED>(a, GlobalKeys<KeyT> { a.keys, a.prim }, s, side == 0, make_float3(s0.x, s0.y, s0.z),
-                                  make_float3(s1.x, s1.y, s1.z), (int)__float_as_uint(s1.w), old >> 8, lo, hi, xl, xr, xh);
+        wb_absorb<REFIT, KeyT, GROUPED>(a, GlobalKeys<KeyT> { a.keys, a.prim }, s, side == 0, s0, s1, old >> 8, lo, hi, xl,
+                                        xr, xh);
         const uint32_t xnode = (uint32_t)(n + s);
 
         int ps;
@@ -267,7 +233,7 @@ __device__ __noinline__ void wb_climb(const A& a, int s, int side, unsigned h)
             wb_store_box(a.pairs + 2 * (size_t)ps + (go_right ? 0 : 1), lo, hi);
         } else {
             if (xl == 0 && xr == n - 1) {
-                wb_write_root<A, KeyT, GROUPED>(a, xnode, xh, lo, hi);
+                wb_write_root<KeyT, GROUPED>(a, xnode, xh, lo, hi);
                 return;
             }
             go_right = wb_goes_right<KeyT, GROUPED>(a.keys, a.prim, n, xl, xr);
@@ -282,75 +248,33 @@ __device__ __noinline__ void wb_climb(const A& a, int s, int side, unsigned h)
     }
 }
 
-// dynamic shared memory of k_tree
-template <bool REFIT, class KeyT> constexpr size_t wb_tree_smem()
-{
-    return (size_t)BP * (6 * sizeof(float) + sizeof(unsigned))
-        + (REFIT ? (size_t)BP * 2 * sizeof(int) : (size_t)(BP + 2) * (sizeof(KeyT) + 1) + 16);
-}
-
-// K4: leaves + hierarchy (builder) / leaf refresh + bottom-up union (refit) in one kernel.
-//
-// A block owns BP consecutive sorted positions, a thread MC of them.
-//  stage 1  one thread per position, coalesced: gather the item, (re)write its packed-triangle record, put its box
-//           in shared memory; stage the block's keys / primitive parities (builder) or parents (refit) there too.
-//  stage 2  every node whose range lies inside the block is produced from shared memory alone: inside a thread's
-//           chunk sequentially with a small stack of parked nodes (a node that wants to merge to the right waits
-//           until the thread itself produces its right sibling -- no atomic, no fence), across the threads of the
-//           block through SHARED arrival words with CTA-scope fences.  Boxes live in one slot per position: a
-//           node that goes right sits in the slot of its last position, one that goes left in the slot of its
-//           first; the two uses of a slot never overlap in time.  Global memory only receives the records.
-//  stage 3  a node left waiting for a sibling that spans a block boundary, or that reached a split shared with
-//           a neighbouring block, is announced on the GLOBAL counter and climbs the spine above the blocks.
-// The parent of a node is a function of its key range alone, so the tree is bit-identical to
-// the reference's whatever the arrival order.
-template <bool REFIT, class Src, class KeyT, bool GROUPED>
+// Phase A: a block owns BP consecutive sorted positions, a thread MC of them.  Every node whose range lies inside
+// the block is produced here: inside a thread's chunk sequentially (no atomics), across the threads of the block
+// through SHARED-memory arrival counters with CTA-scope fences.  A node that has to wait for a sibling spanning a
+// block boundary stays "pending" in its counter; phase B re-announces the pending nodes (and the nodes that
+// reach the splits shared with the neighbouring blocks) on the global counters and climbs the spine above.
+template <bool REFIT, class KeyT, bool GROUPED>
 __global__ void __launch_bounds__(TBM)
-k_tree(MergeArgs<Src, KeyT> a)
+k_merge(MergeArgs<KeyT> a)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* sbox = reinterpret_cast<float*>(smem_raw);                    // [6][BP], one box slot per position
-    unsigned* scount = reinterpret_cast<unsigned*>(sbox + 6 * BP);       // [BP] arrival words
-    int* sparent = reinterpret_cast<int*>(scount + BP);                  // REFIT: parent_int of the block's splits
-    int* spp = sparent + BP;                                             // REFIT: pos_parent of the block
-    KeyT* skeys = reinterpret_cast<KeyT*>(reinterpret_cast<uintptr_t>(scount + BP + 3) & ~(uintptr_t)15);  // builder
-    unsigned char* spar = reinterpret_cast<unsigned char*>(skeys + BP + 2);
+    // bit 0: arrival parity, bit 1: side of the first arrival, bits 8..: its height
+    __shared__ unsigned scount[BP];
 
     const int n = a.n;
     const int tid = threadIdx.x;
     const int b0 = blockIdx.x * BP;
     const int b1 = min(b0 + BP - 1, n - 1);
-
-    // ---- stage 1
     for (int k = tid; k < BP; k += TBM)
         scount[k] = 0u;
-    if (REFIT) {
-        for (int k = tid; k < BP; k += TBM) {
-            const int g = b0 + k;
-            if (g <= b1) {
-                float3 lo, hi;
-                wb_load_item<Src, true>(a.src, __ldg(a.prim + g), a.tris, g, lo, hi);
-                sbox[0 * BP + k] = lo.x, sbox[1 * BP + k] = lo.y, sbox[2 * BP + k] = lo.z;
-                sbox[3 * BP + k] = hi.x, sbox[4 * BP + k] = hi.y, sbox[5 * BP + k] = hi.z;
-                spp[k] = __ldg(a.pos_parent + g);
-                sparent[k] = g < n - 1 ? __ldg(a.parent_int + g) : WB_NO_PARENT;
-            }
-        }
-    } else {
-        for (int k = tid; k < BP + 2; k += TBM) {  // one halo key each side
+    // builder: the block's keys (one halo key each side) and primitive parities, loaded once, coalesced
+    __shared__ KeyT skeys[REFIT ? 1 : BP + 2];
+    __shared__ unsigned char spar[REFIT ? 1 : BP + 2];
+    if (!REFIT) {
+        for (int k = tid; k < BP + 2; k += TBM) {
             const long long g = (long long)b0 - 1 + k;
-            if (g >= 0 && g < n && g <= (long long)b1 + 1) {
-                const int item = __ldg(a.prim + g);
+            if (g >= 0 && g < n) {
                 skeys[k] = __ldg(a.keys + g);
-                spar[k] = (unsigned char)(item % 2);
-                if (k >= 1 && g <= b1) {
-                    float3 lo, hi;
-                    wb_load_item<Src, true>(a.src, item, a.tris, (int)g, lo, hi);
-                    const int q = k - 1;
-                    sbox[0 * BP + q] = lo.x, sbox[1 * BP + q] = lo.y, sbox[2 * BP + q] = lo.z;
-                    sbox[3 * BP + q] = hi.x, sbox[4 * BP + q] = hi.y, sbox[5 * BP + q] = hi.z;
-                    a.pos_parent[g] = WB_NO_PARENT;
-                }
+                spar[k] = (unsigned char)(__ldg(a.prim + g) % 2);
             }
         }
     }
@@ -362,21 +286,20 @@ k_tree(MergeArgs<Src, KeyT> a)
     const int c0 = active ? (int)c0l : n - 1;
     const int c1 = min(c0 + MC - 1, n - 1);
 
-    // arrivals this thread owes to the GLOBAL counters in stage 3: a node of the block reaching a split shared with
+    // arrivals this thread owes to the GLOBAL counters in phase B: a node of the block reaching a split shared with
     // a neighbouring block (b0-1 or b1), or a leaf unit that itself spans the block boundary (refit: packed leaves)
     int dsplit[4];
     unsigned dinfo[4];  // bit 1: side, bits 8..: height
     int ndefer = 0;
 
-    // ---- stage 2
     if (active) {
-        int rstack[MC];       // parked nodes: split position (each is the LEFT child of n + rstack[k]),
-        int lstack[MC];       // first position of the range,
-        unsigned hstack[MC];  // height (builder only)
+        int rstack[MC];       // split positions of parked nodes (each is the LEFT child of n + rstack[k])
+        unsigned hstack[MC];  // their heights (build only)
         int depth = 0;
         int pos = c0;
 
-        bool have = false;  // a node is in hand
+        // the node currently in hand
+        bool have = false, fresh = false;  // fresh: a leaf unit whose record is already in memory
         int xl = 0, xr = 0;
         uint32_t xnode = 0;
         unsigned xh = 0;
@@ -385,7 +308,7 @@ k_tree(MergeArgs<Src, KeyT> a)
 
         for (;;) {
             bool go_right = false;
-            int s = 0, far_end = 0;
+            int s = 0;
             unsigned other_h = 0;
             bool resumed = false;  // true when a parked node was handed over and found its sibling waiting
 
@@ -397,66 +320,49 @@ k_tree(MergeArgs<Src, KeyT> a)
                     --depth;
                     s = rstack[depth];  // c0 <= s < c1: interior to the block
                     const unsigned h = min(hstack[depth], WB_HEIGHT_CAP);
-                    const unsigned old = wb_arrive_cta(&scount[s - b0], wb_pack_arrival(false, lstack[depth] - b0, h));
+                    const unsigned old = wb_arrive_cta(&scount[s - b0], 1u | (h << 8));
                     if (!(old & 1u))
                         continue;
                     // the right sibling was already there: take the parked node back in hand and merge below
-                    const int q = s - b0;
-                    lo = make_float3(sbox[0 * BP + q], sbox[1 * BP + q], sbox[2 * BP + q]);
-                    hi = make_float3(sbox[3 * BP + q], sbox[4 * BP + q], sbox[5 * BP + q]);
-                    xl = lstack[depth];
+                    const NodeRec L = a.pairs[2 * (size_t)s];  // our own earlier store
+                    lo = make_float3(L.lx, L.ly, L.lz);
+                    hi = make_float3(L.hx, L.hy, L.hz);
+                    xl = (int)L.aux;
                     xr = s;
+                    xnode = L.ref & WB_IDX_MASK;
                     xh = h;
-                    go_right = true, other_h = old >> 14, far_end = b0 + (int)((old >> 2) & 0xfffu);
-                    have = true, resumed = true;
+                    go_right = true, other_h = old >> 8;
+                    have = true, fresh = false, resumed = true;
                 } else if (REFIT) {
-                    // next visible leaf of this chunk: union of its items' boxes
-                    const int p = spp[pos - b0];
+                    // next visible leaf of this chunk (its box was refreshed by the leaf pass)
+                    const int p = a.pos_parent[pos];
                     if (p == WB_NO_PARENT) {
                         ++pos;
                         continue;
                     }
+                    if (p == WB_ROOT_PARENT)
+                        break;  // the root is a packed leaf: the leaf pass already wrote the header box
+                    const int ps = p - n;
+                    const NodeRec* rec = a.pairs + 2 * (size_t)ps + (pos <= ps ? 0 : 1);
                     xl = pos;
-                    if (p == WB_ROOT_PARENT) {
-                        xr = n - 1;
-                    } else if (pos <= p - n) {
-                        xr = p - n;  // a left child's range ends at the split
-                    } else {
-                        int q = pos + 1;  // the leaf ends where the next one starts
-                        while (q <= b1 && spp[q - b0] == WB_NO_PARENT)
-                            ++q;
-                        xr = (q <= b1 || b1 == n - 1) ? q - 1 : (int)a.pairs[2 * (size_t)(p - n) + 1].aux;
-                    }
-                    lo = make_float3(FLT_MAX, FLT_MAX, FLT_MAX), hi = make_float3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
-                    for (int k = xl; k <= min(xr, b1); ++k) {
-                        const int q = k - b0;
-                        lo = wb_min3(lo, make_float3(sbox[0 * BP + q], sbox[1 * BP + q], sbox[2 * BP + q]));
-                        hi = wb_max3(hi, make_float3(sbox[3 * BP + q], sbox[4 * BP + q], sbox[5 * BP + q]));
-                    }
-                    for (int k = b1 + 1; k <= xr; ++k) {  // items past the block: gathered again (their block writes the cache)
-                        float3 u, v;
-                        wb_load_item<Src, false>(a.src, __ldg(a.prim + k), a.tris, k, u, v);
-                        lo = wb_min3(lo, u);
-                        hi = wb_max3(hi, v);
-                    }
-                    if (p == WB_ROOT_PARENT) {  // the root is a packed leaf
-                        a.hdr->lx = lo.x, a.hdr->ly = lo.y, a.hdr->lz = lo.z;
-                        a.hdr->hx = hi.x, a.hdr->hy = hi.y, a.hdr->hz = hi.z;
-                        break;
-                    }
+                    xr = (pos <= ps) ? ps : (int)rec->aux;
+                    lo = make_float3(rec->lx, rec->ly, rec->lz);
+                    hi = make_float3(rec->hx, rec->hy, rec->hz);
                     static_parent = p;
+                    xnode = 0;  // unused for leaf units
                     pos = xr + 1;
-                    have = true;
+                    have = true, fresh = true;
                 } else {
-                    // next original leaf
-                    const int q = pos - b0;
+                    // next original leaf (its record was written by the leaf pass)
+                    const bool gr = wb_goes_right_k<GROUPED>(bk, n, pos, pos);
+                    const NodeRec* rec = a.pairs + 2 * (size_t)(gr ? pos : pos - 1) + (gr ? 0 : 1);
                     xl = xr = pos;
-                    lo = make_float3(sbox[0 * BP + q], sbox[1 * BP + q], sbox[2 * BP + q]);
-                    hi = make_float3(sbox[3 * BP + q], sbox[4 * BP + q], sbox[5 * BP + q]);
+                    lo = make_float3(rec->lx, rec->ly, rec->lz);
+                    hi = make_float3(rec->hx, rec->hy, rec->hz);
                     xnode = (uint32_t)pos;
                     xh = 0;
                     ++pos;
-                    have = true;
+                    have = true, fresh = true;
                 }
             }
 
@@ -472,7 +378,7 @@ k_tree(MergeArgs<Src, KeyT> a)
                     go_right = (xr == s);  // a left child's range ends at the split
                 } else {
                     if (xl == 0 && xr == n - 1) {
-                        wb_write_root<MergeArgs<Src, KeyT>, KeyT, GROUPED>(a, xnode, xh, lo, hi);
+                        wb_write_root<KeyT, GROUPED>(a, xnode, xh, lo, hi);
                         break;
                     }
                     go_right = wb_goes_right_k<GROUPED>(bk, n, xl, xr);
@@ -481,23 +387,18 @@ k_tree(MergeArgs<Src, KeyT> a)
                         a.parent_int[xnode - n] = n + s;
                 }
 
-                // the record goes to memory; the box also to the node's shared slot when a block-mate may need it
                 NodeRec* mine = a.pairs + 2 * (size_t)s + (go_right ? 0 : 1);
-                if (REFIT)
-                    wb_store_box(mine, lo, hi);
-                else
-                    wb_store_rec(mine, lo, hi, xnode | (wb_size_leaf_k<GROUPED>(bk, a.leaf_size, xl, xr) ? WB_LEAF : 0u),
-                                 (uint32_t)(go_right ? xl : xr));
-                const bool inblock = xl >= b0 && xr <= b1;
-                if (inblock && (REFIT || xl != xr)) {  // a builder leaf already sits in its slot
-                    const int q = (go_right ? xr : xl) - b0;
-                    sbox[0 * BP + q] = lo.x, sbox[1 * BP + q] = lo.y, sbox[2 * BP + q] = lo.z;
-                    sbox[3 * BP + q] = hi.x, sbox[4 * BP + q] = hi.y, sbox[5 * BP + q] = hi.z;
+                if (!fresh) {
+                    if (REFIT)
+                        wb_store_box(mine, lo, hi);
+                    else
+                        wb_store_rec(mine, lo, hi,
+                                     xnode | (wb_size_leaf_k<GROUPED>(bk, a.leaf_size, xl, xr) ? WB_LEAF : 0u),
+                                     (uint32_t)(go_right ? xl : xr));
                 }
 
                 if (go_right && xr < c1) {  // our own next unit will become (part of) the right sibling: park
                     rstack[depth] = s;
-                    lstack[depth] = xl;
                     hstack[depth] = xh;
                     ++depth;
                     have = false;
@@ -507,40 +408,35 @@ k_tree(MergeArgs<Src, KeyT> a)
                     // the parked top is exactly the left child of n+s: both children are in our hands
                     --depth;
                     other_h = hstack[depth];
-                    far_end = lstack[depth];
                 } else {
                     const unsigned h = min(xh, WB_HEIGHT_CAP);
-                    if (!inblock || s < b0 || s >= b1) {  // not a block-private merge: announced in stage 3
+                    if (xl < b0 || xr > b1 || s < b0 || s >= b1) {  // not a block-private merge: announced in phase B
                         dsplit[ndefer] = s;
                         dinfo[ndefer] = (go_right ? 0u : 2u) | (h << 8);
                         ++ndefer;
                         have = false;
                         continue;
                     }
-                    const unsigned old =
-                        wb_arrive_cta(&scount[s - b0], wb_pack_arrival(!go_right, (go_right ? xl : xr) - b0, h));
+                    const unsigned old = wb_arrive_cta(&scount[s - b0], 1u | (go_right ? 0u : 2u) | (h << 8));
                     if (!(old & 1u)) {
                         have = false;  // the sibling's carrier continues; parked nodes (if any) are handed over above
                         continue;
                     }
-                    other_h = old >> 14;
-                    far_end = b0 + (int)((old >> 2) & 0xfffu);
+                    other_h = old >> 8;
                 }
             }
 
-            // ---- second to complete n+s: union with the sibling's slot and become the parent
-            {
-                const int q = (go_right ? s + 1 : s) - b0;
-                const float3 slo = make_float3(sbox[0 * BP + q], sbox[1 * BP + q], sbox[2 * BP + q]);
-                const float3 shi = make_float3(sbox[3 * BP + q], sbox[4 * BP + q], sbox[5 * BP + q]);
-                wb_absorb<REFIT, GROUPED>(a, bk, s, go_right, slo, shi, far_end, other_h, lo, hi, xl, xr, xh);
-            }
+            // ---- second to complete n+s: union with the sibling record and become the parent
+            const float4* sibling = reinterpret_cast<const float4*>(a.pairs + 2 * (size_t)s + (go_right ? 1 : 0));
+            const float4 s0 = sibling[0], s1 = sibling[1];  // written by this thread or published through scount
+            wb_absorb<REFIT, KeyT, GROUPED>(a, bk, s, go_right, s0, s1, other_h, lo, hi, xl, xr, xh);
             xnode = (uint32_t)(n + s);
-            static_parent = REFIT ? sparent[s - b0] : WB_NO_PARENT;
+            static_parent = REFIT ? a.parent_int[s] : WB_NO_PARENT;
+            fresh = false;
         }
     }
 
-    // ---- stage 3: everything written above becomes visible device-wide, then the pending nodes go global
+    // ---- phase B: everything written above becomes visible device-wide, then the pending nodes go global
     __threadfence();
     __syncthreads();
     unsigned pending = 0;  // bit k < MC: interior split c0 + k waits for a spanning sibling; bit MC + j: dsplit[j]
@@ -554,29 +450,10 @@ k_tree(MergeArgs<Src, KeyT> a)
         pending &= pending - 1;
         if (k < MC) {
             const unsigned v = scount[c0 + k - b0];
-            wb_climb<REFIT, KeyT, GROUPED>(a, c0 + k, (int)((v >> 1) & 1u), v >> 14);
+            wb_climb<REFIT, KeyT, GROUPED>(a, c0 + k, (int)((v >> 1) & 1u), v >> 8);
         } else {
             const unsigned v = dinfo[k - MC];
             wb_climb<REFIT, KeyT, GROUPED>(a, dsplit[k - MC], (int)((v >> 1) & 1u), v >> 8);
         }
     }
-}
-
-// host side: one launch; opts the instantiation into its dynamic shared memory once
-template <bool REFIT, class Src, class KeyT, bool GROUPED>
-inline cudaError_t wb_launch_tree(const MergeArgs<Src, KeyT>& a, cudaStream_t stream)
-{
-    constexpr size_t smem = wb_tree_smem<REFIT, KeyT>();
-    static bool configured[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_tree<REFIT, Src, KeyT, GROUPED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
-        if (e != cudaSuccess)
-            return e;
-        configured[dev] = true;
-    }
-    k_tree<REFIT, Src, KeyT, GROUPED><<<wb_div_up(a.n, BP), TBM, smem, stream>>>(a);
-    return cudaGetLastError();
 }

@@ -67,6 +67,7 @@ struct MeshState {
 // build / refit / export drivers (bvh_build.cu, bvh_refit.cu); all enqueue on `stream`
 const char* wb_build(BvhState& s, cudaStream_t stream);
 const char* wb_refit(BvhState& s, cudaStream_t stream);
+const char* wb_refit_merge(BvhState& s, cudaStream_t stream);  // bottom-up pass of the refit (bvh_build.cu)
 const char* wb_export_reference_layout(BvhState& s, cudaStream_t stream);
 const char* wb_alloc_tree(BvhState& s, cudaStream_t stream);
 void wb_free_tree(BvhState& s, cudaStream_t stream);
