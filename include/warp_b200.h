@@ -136,6 +136,14 @@ WP_B200_API void wp_cuda_event_destroy(void* event);
 WP_B200_API void wp_cuda_event_record(void* event, void* stream, int external);
 WP_B200_API void wp_cuda_event_synchronize(void* event);
 WP_B200_API float wp_cuda_event_elapsed_time(void* start_event, void* end_event);
+/* CUDA graph capture of the stream work of this path (warp.h:766-771; 1 ok / 0 error).  `stream` must be a created
+ * stream; mode = cudaStreamCaptureMode (0 global, 1 thread local, 2 relaxed); external != 0: capture already active */
+WP_B200_API int wp_cuda_graph_begin_capture(void* context, void* stream, int external, int mode);
+WP_B200_API int wp_cuda_graph_end_capture(void* context, void* stream, void** graph_ret);
+WP_B200_API int wp_cuda_graph_create_exec(void* context, void* stream, void* graph, void** graph_exec_ret);
+WP_B200_API int wp_cuda_graph_launch(void* graph_exec, void* stream);
+WP_B200_API int wp_cuda_graph_destroy(void* context, void* graph);
+WP_B200_API int wp_cuda_graph_exec_destroy(void* context, void* graph_exec);
 WP_B200_API void* wp_alloc_device(void* context, size_t s, const char* tag);
 WP_B200_API void wp_free_device(void* context, void* ptr);
 WP_B200_API void* wp_alloc_pinned(size_t s, const char* tag);
@@ -212,6 +220,12 @@ WP_B200_API int wp_b200_get_ray_order(void);
 WP_B200_API void wp_b200_query_stats_enable(int enable);
 WP_B200_API void wp_b200_query_stats_read(unsigned long long* pair_fetches, unsigned long long* tri_fetches);
 
+/* wp.mesh_query_aabb (mesh.h:2476-2712): faces whose AABB (as of the last build / refit) overlaps the query box, in
+ * the reference iterator's order; same count -> scan -> fill protocol as the wp.Bvh queries above */
+WP_B200_API int wp_b200_mesh_query_aabb_count(uint64_t id, const float* lowers, const float* uppers, int64_t n,
+                                              int32_t* counts);
+WP_B200_API int wp_b200_mesh_query_aabb_fill(uint64_t id, const float* lowers, const float* uppers, int64_t n,
+                                             const int32_t* offsets, int32_t* indices);
 /* ---------------------------------------------------------------------------------------------
  * Generic wp.Bvh queries (batched forms of wp.bvh_query_aabb / wp.bvh_query_ray + bvh_query_next,
  * warp/native/bvh.h:494-600): every item whose AABB overlaps the query box / is entered by the query ray

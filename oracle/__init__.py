@@ -388,6 +388,21 @@ class RefMesh:
                                   _p(out, _i32p), ctypes.c_int(nthreads))  # fmt: skip
         return out
 
+    def query_aabb(self, lowers, uppers, item_bounds=None):
+        """mesh_query_aabb iterator run to exhaustion per query: (offsets[n+1], indices).  ``item_bounds`` =
+        (lowers, uppers) per triangle for meshes wrapped with from_tree (reference-built meshes have their own)."""
+        lo, hi = _f32(lowers, (-1, 3)), _f32(uppers, (-1, 3))
+        if item_bounds is not None:
+            self._item_bounds = (_f32(item_bounds[0], (-1, 3)), _f32(item_bounds[1], (-1, 3)))
+            ref().ref_mesh_set_bounds(ctypes.c_uint64(self.id), _p(self._item_bounds[0], _f32p), _p(self._item_bounds[1], _f32p))
+        n = lo.shape[0]
+        offsets = np.zeros(n + 1, np.int32)
+        ref().ref_mesh_query_aabb(ctypes.c_uint64(self.id), _p(lo, _f32p), _p(hi, _f32p), ctypes.c_int64(n), _p(offsets, _i32p), None)
+        indices = np.zeros(max(int(offsets[-1]), 1), np.int32)
+        ref().ref_mesh_query_aabb(ctypes.c_uint64(self.id), _p(lo, _f32p), _p(hi, _f32p), ctypes.c_int64(n), _p(offsets, _i32p),
+                                  _p(indices, _i32p))
+        return offsets, indices[: int(offsets[-1])]
+
     def eval(self, face, u, v, velocity=False):
         f = np.ascontiguousarray(face, np.int32)
         uu, vv = _f32(u), _f32(v)

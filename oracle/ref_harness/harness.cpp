@@ -219,6 +219,32 @@ void ref_mesh_eval(uint64_t id, int velocity, const int* face, const float* u, c
     }
 }
 
+// from_tree meshes borrow per-triangle bounds (mesh.lowers / mesh.uppers, read by mesh_query_aabb's item test)
+void ref_mesh_set_bounds(uint64_t id, const float* lowers, const float* uppers)
+{
+    Mesh* m = (Mesh*)id;
+    m->lowers = (vec3*)lowers;
+    m->uppers = (vec3*)uppers;
+}
+
+// mesh_query_aabb + mesh_query_aabb_next loop (mesh.h:2476-2712): offsets[n+1]; indices may be NULL (count only)
+void ref_mesh_query_aabb(uint64_t id, const float* lowers, const float* uppers, int64_t n, int* offsets, int* indices)
+{
+    int run = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        offsets[i] = run;
+        mesh_query_aabb_t q = mesh_query_aabb(id, vec3(lowers[3 * i], lowers[3 * i + 1], lowers[3 * i + 2]),
+                                              vec3(uppers[3 * i], uppers[3 * i + 1], uppers[3 * i + 2]));
+        int face;
+        while (mesh_query_aabb_next(q, face)) {
+            if (indices)
+                indices[run] = face;
+            ++run;
+        }
+    }
+    offsets[n] = run;
+}
+
 // standalone primitives for unit-level pinning of the restatement
 void ref_closest_point_to_triangle(const float* a, const float* b, const float* c, const float* p, float* uv)
 {

@@ -1,6 +1,7 @@
 """Generates tests/golden/golden_ray_variants.npz by running the UNMODIFIED reference C++
 (oracle/_ref/libwarp_ref_cpu.so) in the dev container: mesh_query_ray_anyhit,
-mesh_query_ray_count_intersections and mesh_eval_position (warp/native/mesh.h:1893-2032, 2767-2785)
+mesh_query_ray_count_intersections, mesh_eval_position and the mesh_query_aabb iterator
+(warp/native/mesh.h:1893-2032, 2767-2785, 2476-2712)
 on the mesh / rays of golden_cpu.npz, over the reference's own SAH tree and over the LBVH trees stored there.
 
     python tests/golden/make_golden_ray_variants.py
@@ -27,6 +28,12 @@ V = ((1 - U) * rng.random(512)).astype(np.float32)
 out["eval_face"], out["eval_u"], out["eval_v"] = F, U, V
 
 
+QLO = (rng.random((128, 3)) * 2.2 - 1.2).astype(np.float32)
+QHI = (QLO + rng.random((128, 3)).astype(np.float32) * 0.6).astype(np.float32)
+out["aabb_lowers"], out["aabb_uppers"] = QLO, QHI
+TLO, THI = oracle.triangle_bounds(P, I)
+
+
 def tree_of(prefix):
     return {k: g[f"{prefix}_tree_{k}"] for k in ("node_lowers", "node_uppers", "primitive_indices")} | {
         "root": int(g[f"{prefix}_tree_root"])}
@@ -38,6 +45,7 @@ for name in ("sah", "lbvh1", "lbvh4"):
         out[f"{name}_anyhit_{mt:g}"] = m.query_ray_anyhit(S2, D, mt)
     out[f"{name}_count"] = m.query_ray_count(S2, D)
     out[f"{name}_eval_position"] = m.eval(F, U, V)
+    out[f"{name}_aabb_offsets"], out[f"{name}_aabb_indices"] = m.query_aabb(QLO, QHI, item_bounds=(TLO, THI))
 
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "golden_ray_variants.npz"), **out)
 print({k: (v.shape, v.dtype) for k, v in out.items()})

@@ -68,3 +68,41 @@ def test_bvh_queries_large_and_edge_cases(wp, oracle_mod):
     assert r.lists()[0].tolist() == [0]
     with pytest.raises(TypeError):
         wp.bvh_query_aabb(object(), far, far)
+
+
+def test_mesh_query_aabb(wp, oracle_mod):
+    """wp.mesh_query_aabb batched: reference fixture (iterator order), oracle on a bigger mesh, refit follows the points."""
+    import os
+    from warp_b200 import meshgen as mg
+
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    g, rv = np.load(os.path.join(gdir, "golden_cpu.npz")), np.load(os.path.join(gdir, "golden_ray_variants.npz"))
+    P, I = g["mesh_points"], g["mesh_indices"]
+    for leaf in (1, 4):
+        m = wp.Mesh(wp.array(P, dtype=wp.vec3), wp.array(I, dtype=wp.int32), bvh_constructor="lbvh", bvh_leaf_size=leaf)
+        off, idx = wp.mesh_query_aabb(m, rv["aabb_lowers"], rv["aabb_uppers"]).numpy()
+        assert np.array_equal(off, rv[f"lbvh{leaf}_aabb_offsets"]) and np.array_equal(idx, rv[f"lbvh{leaf}_aabb_indices"])
+
+    P, I = mg.noisy_sphere(5, 0.05, 21)
+    pts = wp.array(P, dtype=wp.vec3)
+    m = wp.Mesh(pts, wp.array(I, dtype=wp.int32), bvh_constructor="lbvh", bvh_leaf_size=4)
+    tree = oracle_mod.mesh_lbvh_build(P, I, 4)
+    rng = np.random.default_rng(22)
+    qlo = (rng.random((3000, 3)) * 2.4 - 1.3).astype(np.float32)
+    qhi = (qlo + rng.random((3000, 3)).astype(np.float32) * 0.3).astype(np.float32)
+    tlo, thi = oracle_mod.triangle_bounds(P, I)
+    off, idx = wp.mesh_query_aabb(m, wp.array(qlo, dtype=wp.vec3), wp.array(qhi, dtype=wp.vec3)).numpy()
+    woff, widx = oracle_mod.bvh_query(tree, tlo, thi, qlo, qhi)
+    assert off[-1] > 10000 and np.array_equal(off, woff) and np.array_equal(idx, widx)
+    for i, want in enumerate(_brute_aabb(tlo, thi, qlo[:200], qhi[:200])):
+        assert sorted(idx[off[i] : off[i + 1]].tolist()) == want.tolist()
+    # move the points, refit: the item boxes the query tests are the refreshed ones
+    P2 = (P * np.float32(1.25)).astype(np.float32)
+    pts.assign(P2)
+    m.refit()
+    tlo2, thi2 = oracle_mod.triangle_bounds(P2, I)
+    off2, idx2 = wp.mesh_query_aabb(m, qlo, qhi).numpy()
+    for i, want in enumerate(_brute_aabb(tlo2, thi2, qlo[:300], qhi[:300])):
+        assert sorted(idx2[off2[i] : off2[i + 1]].tolist()) == want.tolist()
+    with pytest.raises(TypeError):
+        wp.mesh_query_aabb(wp.Bvh(wp.array(tlo, dtype=wp.vec3), wp.array(thi, dtype=wp.vec3)), qlo, qhi)

@@ -324,3 +324,21 @@ def test_ray_variants_live_reference(oracle_mod):
             assert np.array_equal(a, rm.query_ray_anyhit(S, D, mt))
             assert np.array_equal(a, o.query_ray(P, I, tree, S, D, mt)["result"])
         assert np.array_equal(o.query_ray_count(P, I, tree, S, D), rm.query_ray_count(S, D))
+
+
+def test_mesh_query_aabb_restatement_matches_reference_fixture(oracle_mod, gold):
+    """mesh_query_aabb + mesh_query_aabb_next (mesh.h:2476-2712) == the generic iterator restatement over
+    per-triangle boxes: hit lists equal IN ORDER on the reference's SAH tree and on LBVH trees."""
+    o = oracle_mod
+    rv = np.load(RAYV_GOLD)
+    P, I = gold["mesh_points"], gold["mesh_indices"]
+    tlo, thi = o.triangle_bounds(P, I)
+    for name in ("sah", "lbvh1", "lbvh4"):
+        tree = {k: gold[f"{name}_tree_{k}"] for k in ("node_lowers", "node_uppers", "primitive_indices")}
+        tree["root"] = int(gold[f"{name}_tree_root"])
+        off, idx = o.bvh_query(tree, tlo, thi, rv["aabb_lowers"], rv["aabb_uppers"])
+        assert np.array_equal(off, rv[f"{name}_aabb_offsets"]) and np.array_equal(idx, rv[f"{name}_aabb_indices"])
+        assert off[-1] > 500
+    for i, want in enumerate(_brute_aabb(tlo, thi, rv["aabb_lowers"], rv["aabb_uppers"])):
+        o_, x_ = rv["lbvh4_aabb_offsets"], rv["lbvh4_aabb_indices"]
+        assert sorted(x_[o_[i] : o_[i + 1]].tolist()) == want.tolist()

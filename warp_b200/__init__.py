@@ -47,7 +47,17 @@ from .queries import (  # noqa: F401
     query_stats,
 )
 
-from .bvh_queries import BvhQueryResult, bvh_query_aabb, bvh_query_ray  # noqa: F401,E402
+from .bvh_queries import BvhQueryResult, bvh_query_aabb, bvh_query_ray, mesh_query_aabb  # noqa: F401,E402
+
+from .capture import (  # noqa: F401,E402
+    Graph,
+    ScopedCapture,
+    ScopedStream,
+    Stream,
+    capture_begin,
+    capture_end,
+    capture_launch,
+)
 
 __version__ = "0.1.0"
 

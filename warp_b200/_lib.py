@@ -76,6 +76,12 @@ SIGNATURES = {
     "wp_cuda_event_record": (None, [_vp, _vp, _i]),
     "wp_cuda_event_synchronize": (None, [_vp]),
     "wp_cuda_event_elapsed_time": (_f, [_vp, _vp]),
+    "wp_cuda_graph_begin_capture": (_i, [_vp, _vp, _i, _i]),
+    "wp_cuda_graph_end_capture": (_i, [_vp, _vp, ctypes.POINTER(ctypes.c_void_p)]),
+    "wp_cuda_graph_create_exec": (_i, [_vp, _vp, _vp, ctypes.POINTER(ctypes.c_void_p)]),
+    "wp_cuda_graph_launch": (_i, [_vp, _vp]),
+    "wp_cuda_graph_destroy": (_i, [_vp, _vp]),
+    "wp_cuda_graph_exec_destroy": (_i, [_vp, _vp]),
     "wp_alloc_device": (_vp, [_vp, _sz, ctypes.c_char_p]),
     "wp_free_device": (None, [_vp, _vp]),
     "wp_alloc_pinned": (_vp, [_sz, ctypes.c_char_p]),
@@ -109,6 +115,8 @@ SIGNATURES = {
     "wp_b200_bvh_query_aabb_fill": (_i, [_u64, _vp, _vp, _i64, _vp, _vp]),
     "wp_b200_bvh_query_ray_count": (_i, [_u64, _vp, _vp, _i64, _f, _vp]),
     "wp_b200_bvh_query_ray_fill": (_i, [_u64, _vp, _vp, _i64, _f, _vp, _vp]),
+    "wp_b200_mesh_query_aabb_count": (_i, [_u64, _vp, _vp, _i64, _vp]),
+    "wp_b200_mesh_query_aabb_fill": (_i, [_u64, _vp, _vp, _i64, _vp, _vp]),
     "wp_b200_exclusive_scan_i32": (_i, [_vp, _vp, _i64]),
     "wp_b200_mesh_rebuild_device": (_i, [_u64]),
     "wp_b200_bvh_info": (_i, [_u64, ctypes.POINTER(bvh_info_t)]),

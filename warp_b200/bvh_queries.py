@@ -10,7 +10,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from .types import Bvh, array, empty, int32, vec3
+from .types import Bvh, Mesh, array, empty, int32, vec3
 
 FLT_MAX = float(np.finfo(np.float32).max)
 
@@ -43,8 +43,11 @@ def _as_dev(a, dev, what):
     return array(h, dtype=vec3, device=dev)
 
 
-def _run(bvh, qa, qb, ray, max_dist):
-    if not isinstance(bvh, Bvh) or not bvh.id:
+def _run(bvh, qa, qb, ray, max_dist, mesh=False):
+    if mesh:
+        if not isinstance(bvh, Mesh) or not bvh.id:
+            raise TypeError("expected a warp_b200.Mesh")
+    elif not isinstance(bvh, Bvh) or not bvh.id:
         raise TypeError("expected a warp_b200.Bvh")
     dev = bvh.device
     qa, qb = _as_dev(qa, dev, "first query array"), _as_dev(qb, dev, "second query array")
@@ -55,7 +58,9 @@ def _run(bvh, qa, qb, ray, max_dist):
     p = lambda a: ctypes.c_void_p(a.ptr or 0)  # noqa: E731
     counts = empty(n, int32, dev)
     offsets = empty(n + 1, int32, dev)
-    if ray:
+    if mesh:
+        ok = c.wp_b200_mesh_query_aabb_count(bvh.id, p(qa), p(qb), n, p(counts))
+    elif ray:
         ok = c.wp_b200_bvh_query_ray_count(bvh.id, p(qa), p(qb), n, max_dist, p(counts))
     else:
         ok = c.wp_b200_bvh_query_aabb_count(bvh.id, p(qa), p(qb), n, p(counts))
@@ -65,7 +70,9 @@ def _run(bvh, qa, qb, ray, max_dist):
     total = int(offsets.numpy()[-1])  # the one host round trip: the hit list has to be allocated
     indices = empty(max(total, 1), int32, dev)
     if total:
-        if ray:
+        if mesh:
+            ok = c.wp_b200_mesh_query_aabb_fill(bvh.id, p(qa), p(qb), n, p(offsets), p(indices))
+        elif ray:
             ok = c.wp_b200_bvh_query_ray_fill(bvh.id, p(qa), p(qb), n, max_dist, p(offsets), p(indices))
         else:
             ok = c.wp_b200_bvh_query_aabb_fill(bvh.id, p(qa), p(qb), n, p(offsets), p(indices))
@@ -82,3 +89,9 @@ def bvh_query_aabb(bvh, lowers, uppers) -> BvhQueryResult:
 def bvh_query_ray(bvh, starts, dirs, max_dist: float = FLT_MAX) -> BvhQueryResult:
     """All items whose AABB the ray ``starts[i] + t * dirs[i]`` enters at ``t < max_dist`` (``bvh.h:483-487``)."""
     return _run(bvh, starts, dirs, True, float(max_dist))
+
+
+def mesh_query_aabb(mesh, lowers, uppers) -> BvhQueryResult:
+    """All faces of ``mesh`` whose AABB (as of its last build / refit) overlaps ``[lowers[i], uppers[i]]``, in the
+    order the reference's ``mesh_query_aabb`` / ``mesh_query_aabb_next`` loop yields them (``mesh.h:2476-2712``)."""
+    return _run(mesh, lowers, uppers, False, 0.0, mesh=True)

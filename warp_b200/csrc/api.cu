@@ -278,6 +278,45 @@ float wp_cuda_event_elapsed_time(void* a, void* b)
     return ms;
 }
 
+// CUDA graph capture of the path's stream work (refit / in-place rebuild / device-buffer queries), names and
+// argument meaning of warp/native/warp.h:766-771.  The stream must be a created stream (not the legacy default).
+int wp_cuda_graph_begin_capture(void* context, void* stream, int external, int mode)
+{
+    if (external)
+        return 1;  // the caller's own capture is already active on `stream`
+    DeviceGuard g(context_device(context));
+    return check(cudaStreamBeginCapture((cudaStream_t)stream, (cudaStreamCaptureMode)mode), "graph begin capture") ? 1 : 0;
+}
+int wp_cuda_graph_end_capture(void* context, void* stream, void** graph_ret)
+{
+    DeviceGuard g(context_device(context));
+    cudaGraph_t graph = nullptr;
+    const bool ok = check(cudaStreamEndCapture((cudaStream_t)stream, &graph), "graph end capture");
+    if (graph_ret)
+        *graph_ret = graph;
+    else if (graph)
+        cudaGraphDestroy(graph);
+    return ok && graph ? 1 : 0;
+}
+int wp_cuda_graph_create_exec(void* context, void*, void* graph, void** graph_exec_ret)
+{
+    DeviceGuard g(context_device(context));
+    cudaGraphExec_t exec = nullptr;
+    if (!check(cudaGraphInstantiateWithFlags(&exec, (cudaGraph_t)graph, 0), "graph instantiate"))
+        return 0;
+    *graph_exec_ret = exec;
+    return 1;
+}
+int wp_cuda_graph_launch(void* graph_exec, void* stream)
+{
+    return check(cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream), "graph launch") ? 1 : 0;
+}
+int wp_cuda_graph_destroy(void*, void* graph) { return check(cudaGraphDestroy((cudaGraph_t)graph), "graph destroy") ? 1 : 0; }
+int wp_cuda_graph_exec_destroy(void*, void* graph_exec)
+{
+    return check(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec), "graph exec destroy") ? 1 : 0;
+}
+
 void* wp_alloc_device(void* context, size_t s, const char*)
 {
     DeviceGuard g(context_device(context));
@@ -871,12 +910,12 @@ static long long* g_scan_scratch[64] = {};
 static size_t g_scan_scratch_words[64] = {};
 
 static int bvh_query_common(uint64_t id, int ray, const float* qa, const float* qb, int64_t n, float max_dist,
-                            int32_t* counts, const int32_t* offsets, int32_t* indices)
+                            int32_t* counts, const int32_t* offsets, int32_t* indices, bool want_mesh = false)
 {
     MeshState* ms = nullptr;
     BvhState* s = find_tree(id, &ms);
-    if (!s || ms) {
-        set_error("Warp error: invalid BVH id (generic queries take a wp.Bvh)");
+    if (!s || (ms != nullptr) != want_mesh) {
+        set_error(want_mesh ? "Warp error: invalid mesh id" : "Warp error: invalid BVH id (generic queries take a wp.Bvh)");
         return 0;
     }
     DeviceGuard g(s->device);
@@ -888,8 +927,8 @@ static int bvh_query_common(uint64_t id, int ray, const float* qa, const float* 
             return check(cudaMemsetAsync(counts, 0, 4 * (size_t)n, st), "memset") ? 1 : 0;
         return 1;
     }
-    const char* err = wb_bvh_query(make_view(*s), s->item_lowers, s->item_uppers, ray, qa, qb, n, max_dist, counts,
-                                   offsets, indices, st);
+    const char* err = wb_bvh_query(make_view(*s), want_mesh ? nullptr : s->item_lowers, want_mesh ? nullptr : s->item_uppers,
+                                   ray, qa, qb, n, max_dist, counts, offsets, indices, st);
     if (err) {
         set_error("Warp error: BVH query failed: %s", err);
         return 0;
@@ -915,6 +954,16 @@ int wp_b200_bvh_query_ray_fill(uint64_t id, const float* starts, const float* di
                                const int32_t* offsets, int32_t* indices)
 {
     return bvh_query_common(id, 1, starts, dirs, n, max_dist, nullptr, offsets, indices);
+}
+
+int wp_b200_mesh_query_aabb_count(uint64_t id, const float* lowers, const float* uppers, int64_t n, int32_t* counts)
+{
+    return bvh_query_common(id, 0, lowers, uppers, n, 0.f, counts, nullptr, nullptr, true);
+}
+int wp_b200_mesh_query_aabb_fill(uint64_t id, const float* lowers, const float* uppers, int64_t n, const int32_t* offsets,
+                                 int32_t* indices)
+{
+    return bvh_query_common(id, 0, lowers, uppers, n, 0.f, nullptr, offsets, indices, true);
 }
 
 int wp_b200_exclusive_scan_i32(const int32_t* counts, int32_t* offsets, int64_t n)

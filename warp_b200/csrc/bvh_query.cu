@@ -51,7 +51,9 @@ __device__ __forceinline__ float3 ld3(const float* __restrict__ p, size_t i)
 }
 
 // RAY: (qa, qb) = (start, 1/dir);  AABB: (qa, qb) = (lower, upper).  FILL = false counts, true writes indices.
-template <bool RAY, bool FILL>
+// MESH: the tree is a wp.Mesh's (mesh_query_aabb, mesh.h:2476-2712): an item's box is its triangle's, taken from
+// the packed-triangle cache (== mesh.lowers/uppers of the last build / refit, mesh.cu:16-36)
+template <bool RAY, bool FILL, bool MESH>
 __global__ void __launch_bounds__(BQ)
 k_bvh_query(TreeView tv, const float* __restrict__ item_lowers, const float* __restrict__ item_uppers,
             const float* __restrict__ qa_in, const float* __restrict__ qb_in, long long nq, float max_dist,
@@ -86,7 +88,19 @@ k_bvh_query(TreeView tv, const float* __restrict__ item_lowers, const float* __r
                 } else {
                     for (uint32_t k = 0; k < cur.b; ++k) {
                         const int item = __ldg(tv.prim + start + k);
-                        if (test_box<RAY>(qa, qb, ld3(item_lowers, (size_t)item), ld3(item_uppers, (size_t)item), max_dist)) {
+                        float3 ilo, ihi;
+                        if (MESH) {
+                            const float4* t = tv.tris + 3 * (size_t)(start + k);
+                            const float4 t0 = __ldg(t), t1 = __ldg(t + 1), t2 = __ldg(t + 2);
+                            const float3 p = make_float3(t0.x, t0.y, t0.z), q = make_float3(t0.w, t1.x, t1.y),
+                                         r = make_float3(t1.z, t1.w, t2.x);
+                            ilo = wb_min3(wb_min3(p, q), r);
+                            ihi = wb_max3(wb_max3(p, q), r);
+                        } else {
+                            ilo = ld3(item_lowers, (size_t)item);
+                            ihi = ld3(item_uppers, (size_t)item);
+                        }
+                        if (test_box<RAY>(qa, qb, ilo, ihi, max_dist)) {
                             if (FILL)
                                 out[found] = item;
                             ++found;
@@ -224,17 +238,28 @@ const char* wb_bvh_query(const TreeView& tv, const float* item_lowers, const flo
         return nullptr;
     const int grid = grid_for(nq);
     const bool fill = offsets != nullptr;
-    if (ray) {
+    const bool mesh = item_lowers == nullptr;  // items are the triangles of tv.tris
+#define WB_BQ_LAUNCH(R, F, M) \
+    k_bvh_query<R, F, M><<<grid, BQ, 0, stream>>>(tv, item_lowers, item_uppers, qa, qb, nq, max_dist, counts, offsets, indices)
+    if (mesh) {
+        if (ray)
+            return "ray hit lists are defined for wp.Bvh only";
         if (fill)
-            k_bvh_query<true, true><<<grid, BQ, 0, stream>>>(tv, item_lowers, item_uppers, qa, qb, nq, max_dist, counts, offsets, indices);
+            WB_BQ_LAUNCH(false, true, true);
         else
-            k_bvh_query<true, false><<<grid, BQ, 0, stream>>>(tv, item_lowers, item_uppers, qa, qb, nq, max_dist, counts, offsets, indices);
+            WB_BQ_LAUNCH(false, false, true);
+    } else if (ray) {
+        if (fill)
+            WB_BQ_LAUNCH(true, true, false);
+        else
+            WB_BQ_LAUNCH(true, false, false);
     } else {
         if (fill)
-            k_bvh_query<false, true><<<grid, BQ, 0, stream>>>(tv, item_lowers, item_uppers, qa, qb, nq, max_dist, counts, offsets, indices);
+            WB_BQ_LAUNCH(false, true, false);
         else
-            k_bvh_query<false, false><<<grid, BQ, 0, stream>>>(tv, item_lowers, item_uppers, qa, qb, nq, max_dist, counts, offsets, indices);
+            WB_BQ_LAUNCH(false, false, false);
     }
+#undef WB_BQ_LAUNCH
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
