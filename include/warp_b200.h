@@ -233,14 +233,20 @@ WP_B200_API int wp_b200_mesh_query_aabb_fill(uint64_t id, const float* lowers, c
  *   1. *_count  -> counts[n]          2. wp_b200_exclusive_scan_i32(counts, offsets, n) -> offsets[n+1]
  *   3. *_fill   -> indices[offsets[n]]        (all device pointers, current stream; 1 ok / 0 error)
  * ------------------------------------------------------------------------------------------- */
-WP_B200_API int wp_b200_bvh_query_aabb_count(uint64_t id, const float* lowers, const float* uppers, int64_t n,
-                                             int32_t* counts);
-WP_B200_API int wp_b200_bvh_query_aabb_fill(uint64_t id, const float* lowers, const float* uppers, int64_t n,
-                                            const int32_t* offsets, int32_t* indices);
-WP_B200_API int wp_b200_bvh_query_ray_count(uint64_t id, const float* starts, const float* dirs, int64_t n,
-                                            float max_dist, int32_t* counts);
-WP_B200_API int wp_b200_bvh_query_ray_fill(uint64_t id, const float* starts, const float* dirs, int64_t n,
-                                           float max_dist, const int32_t* offsets, int32_t* indices);
+/* `roots` (optional, NULL = whole tree): per-query start node, a reference node index such as the ones
+ * wp_b200_bvh_get_group_root returns (bvh.h:504: root == -1 means the tree root) */
+WP_B200_API int wp_b200_bvh_query_aabb_count(uint64_t id, const float* lowers, const float* uppers, const int32_t* roots,
+                                             int64_t n, int32_t* counts);
+WP_B200_API int wp_b200_bvh_query_aabb_fill(uint64_t id, const float* lowers, const float* uppers, const int32_t* roots,
+                                            int64_t n, const int32_t* offsets, int32_t* indices);
+WP_B200_API int wp_b200_bvh_query_ray_count(uint64_t id, const float* starts, const float* dirs, const int32_t* roots,
+                                            int64_t n, float max_dist, int32_t* counts);
+WP_B200_API int wp_b200_bvh_query_ray_fill(uint64_t id, const float* starts, const float* dirs, const int32_t* roots,
+                                           int64_t n, float max_dist, const int32_t* offsets, int32_t* indices);
+/* wp.bvh_get_group_root (bvh.h:376-390) for a batch of group ids: roots[i] = reference index of the node that holds
+ * exactly the items of group_ids[i] (a leaf for a one-item group), -1 when the group does not occur.  On a tree
+ * built without groups every item is in group 0. */
+WP_B200_API int wp_b200_bvh_get_group_root(uint64_t id, const int32_t* group_ids, int64_t n, int32_t* roots);
 WP_B200_API int wp_b200_exclusive_scan_i32(const int32_t* counts, int32_t* offsets, int64_t n);
 
 /* in-place LBVH rebuild of a mesh's tree from the current vertices (the reference only offers this

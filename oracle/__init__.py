@@ -427,16 +427,62 @@ def ref_max_threads() -> int:
     return int(ref().ref_max_threads())
 
 
-def bvh_query(tree, item_lowers, item_uppers, qa, qb, ray=False, max_dist=3.4028234663852886e38):
-    """Generic BVH query restatement (bvh.h:494-600): returns (offsets[n+1], indices) in iterator order."""
+def bvh_query(tree, item_lowers, item_uppers, qa, qb, ray=False, max_dist=3.4028234663852886e38, roots=None):
+    """Generic BVH query restatement (bvh.h:494-600): returns (offsets[n+1], indices) in iterator order.
+    ``roots``: optional per-query start node (reference node index, -1 = tree root)."""
     lo, hi = _f32(item_lowers, (-1, 3)), _f32(item_uppers, (-1, 3))
     a, b = _f32(qa, (-1, 3)), _f32(qb, (-1, 3))
     n = a.shape[0]
     offsets = np.zeros(n + 1, np.int32)
+    r = None if roots is None else _i32(roots)
     args = (tree["node_lowers"].ctypes.data_as(ctypes.c_void_p), tree["node_uppers"].ctypes.data_as(ctypes.c_void_p),
             _p(tree["primitive_indices"], _i32p), ctypes.c_int(tree["root"]), _p(lo, _f32p), _p(hi, _f32p),
-            ctypes.c_int(1 if ray else 0), _p(a, _f32p), _p(b, _f32p), ctypes.c_int64(n), ctypes.c_float(max_dist))
+            ctypes.c_int(1 if ray else 0), _p(a, _f32p), _p(b, _f32p), _p(r, _i32p), ctypes.c_int64(n),
+            ctypes.c_float(max_dist))  # fmt: skip
     orc().orc_bvh_query(*args, _p(offsets, _i32p), None)
     indices = np.zeros(max(int(offsets[-1]), 1), np.int32)
     orc().orc_bvh_query(*args, _p(offsets, _i32p), _p(indices, _i32p))
     return offsets, indices[: int(offsets[-1])]
+
+
+def bvh_group_roots(tree, groups, group_ids):
+    """bvh_get_group_root restatement (bvh.h:287-390): reference node index per queried group id, -1 if absent.
+    ``groups`` = the per-item group array the tree was built with (None for an ungrouped tree)."""
+    gid = _i32(group_ids)
+    g = None if groups is None else _i32(groups)
+    par = _i32(tree["parents"])
+    roots = np.zeros(gid.shape[0], np.int32)
+    orc().orc_bvh_group_roots(tree["node_lowers"].ctypes.data_as(ctypes.c_void_p), _p(tree["primitive_indices"], _i32p),
+                              _p(par, _i32p), _p(g, _i32p), ctypes.c_int(len(tree["primitive_indices"])), _p(gid, _i32p),
+                              ctypes.c_int64(gid.shape[0]), _p(roots, _i32p))  # fmt: skip
+    return roots
+
+
+def ref_bvh_query(tree, item_lowers, item_uppers, qa, qb, ray=False, max_dist=3.4028234663852886e38, roots=None):
+    """The reference's own iterator (bvh.h:494-664, oracle/_ref) run to exhaustion per query: (offsets, indices)."""
+    lo, hi = _f32(item_lowers, (-1, 3)), _f32(item_uppers, (-1, 3))
+    a, b = _f32(qa, (-1, 3)), _f32(qb, (-1, 3))
+    n = a.shape[0]
+    offsets = np.zeros(n + 1, np.int32)
+    r = None if roots is None else _i32(roots)
+    args = (tree["node_lowers"].ctypes.data_as(ctypes.c_void_p), tree["node_uppers"].ctypes.data_as(ctypes.c_void_p),
+            _p(tree["primitive_indices"], _i32p), ctypes.c_int(tree["root"]), _p(lo, _f32p), _p(hi, _f32p),
+            ctypes.c_int(lo.shape[0]), ctypes.c_int(1 if ray else 0), _p(a, _f32p), _p(b, _f32p), _p(r, _i32p),
+            ctypes.c_int64(n), ctypes.c_float(max_dist))  # fmt: skip
+    ref().ref_bvh_query(*args, _p(offsets, _i32p), None)
+    indices = np.zeros(max(int(offsets[-1]), 1), np.int32)
+    ref().ref_bvh_query(*args, _p(offsets, _i32p), _p(indices, _i32p))
+    return offsets, indices[: int(offsets[-1])]
+
+
+def ref_bvh_group_roots(tree, groups, group_ids):
+    """The reference's own bvh_get_group_root (bvh.h:376-390, oracle/_ref)."""
+    gid = _i32(group_ids)
+    g = None if groups is None else _i32(groups)
+    par = _i32(tree["parents"])
+    roots = np.zeros(gid.shape[0], np.int32)
+    ref().ref_bvh_group_roots(tree["node_lowers"].ctypes.data_as(ctypes.c_void_p),
+                              tree["node_uppers"].ctypes.data_as(ctypes.c_void_p), _p(par, _i32p),
+                              _p(tree["primitive_indices"], _i32p), _p(g, _i32p), ctypes.c_int(len(tree["primitive_indices"])),
+                              ctypes.c_int(tree["root"]), _p(gid, _i32p), ctypes.c_int64(gid.shape[0]), _p(roots, _i32p))  # fmt: skip
+    return roots

@@ -87,16 +87,82 @@ static int query_one(const half_t* lowers, const half_t* uppers, const int* prim
     return found;
 }
 
-/* offsets[n+1] and (if indices != NULL) indices[offsets[n]]; call once with indices NULL to size the output */
+/* offsets[n+1] and (if indices != NULL) indices[offsets[n]]; call once with indices NULL to size the output.
+ * roots (optional): per-query start node; -1 = the tree root (bvh.h:504) */
 void orc_bvh_query(const void* node_lowers, const void* node_uppers, const int* prim, int root, const float* item_lowers,
-                   const float* item_uppers, int ray, const float* qa, const float* qb, int64_t n, float max_dist,
-                   int* offsets, int* indices)
+                   const float* item_uppers, int ray, const float* qa, const float* qb, const int* roots, int64_t n,
+                   float max_dist, int* offsets, int* indices)
 {
     int run = 0;
     for (int64_t i = 0; i < n; ++i) {
         offsets[i] = run;
-        run += query_one((const half_t*)node_lowers, (const half_t*)node_uppers, prim, root, item_lowers, item_uppers, ray,
+        const int start = (roots && roots[i] != -1) ? roots[i] : root;
+        run += query_one((const half_t*)node_lowers, (const half_t*)node_uppers, prim, start, item_lowers, item_uppers, ray,
                          qa + 3 * i, qb + 3 * i, max_dist, indices ? indices + run : NULL);
     }
     offsets[n] = run;
+}
+
+/* get_leaf_group / lower_bound_group / upper_bound_group / lca / bvh_get_group_root, bvh.h:287-390 */
+static int leaf_group(const half_t* lowers, const int* prim, const int* item_groups, int leaf)
+{
+    if (!item_groups)
+        return 0;
+    return item_groups[prim[H_I(lowers[leaf])]];
+}
+
+static int lca(int a, int b, const int* parent)
+{
+    int da = 0, db = 0;
+    for (int t = a; t != -1; t = parent[t])
+        ++da;
+    for (int t = b; t != -1; t = parent[t])
+        ++db;
+    if (da > db) {
+        int diff = da - db;
+        while (diff-- && a != -1)
+            a = parent[a];
+    } else if (db > da) {
+        int diff = db - da;
+        while (diff-- && b != -1)
+            b = parent[b];
+    }
+    while (a != b) {
+        if (a == -1 || b == -1)
+            return -1;
+        a = parent[a];
+        b = parent[b];
+    }
+    return a;
+}
+
+void orc_bvh_group_roots(const void* node_lowers, const int* prim, const int* parents, const int* item_groups,
+                         int num_leaf_nodes, const int* group_ids, int64_t n, int* roots)
+{
+    const half_t* lowers = (const half_t*)node_lowers;
+    for (int64_t i = 0; i < n; ++i) {
+        const int group = group_ids[i];
+        int lo = 0, hi = num_leaf_nodes;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (leaf_group(lowers, prim, item_groups, mid) < group)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        if (lo == num_leaf_nodes || leaf_group(lowers, prim, item_groups, lo) != group) {
+            roots[i] = -1;
+            continue;
+        }
+        const int first = lo;
+        lo = 0, hi = num_leaf_nodes;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (leaf_group(lowers, prim, item_groups, mid) <= group)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        roots[i] = lca(first, lo - 1, parents);
+    }
 }

@@ -245,6 +245,56 @@ void ref_mesh_query_aabb(uint64_t id, const float* lowers, const float* uppers, 
     offsets[n] = run;
 }
 
+// generic wp.Bvh iterator (bvh.h:494-664) and bvh_get_group_root (bvh.h:376-390) over a caller-supplied tree in the
+// reference layout.  ray: (qa, qb) = (start, dir), else (lower, upper); roots optional (-1 / NULL = tree root).
+static BVH make_bvh(const void* node_lowers, const void* node_uppers, const int* parents, const int* prim,
+                    const float* item_lowers, const float* item_uppers, const int* item_groups, int num_items, int* root)
+{
+    BVH b;
+    b.node_lowers = (BVHPackedNodeHalf*)node_lowers;
+    b.node_uppers = (BVHPackedNodeHalf*)node_uppers;
+    b.node_parents = (int*)parents;
+    b.primitive_indices = (int*)prim;
+    b.item_lowers = (vec3*)item_lowers;
+    b.item_uppers = (vec3*)item_uppers;
+    b.item_groups = (int*)item_groups;
+    b.num_items = num_items;
+    b.num_leaf_nodes = num_items;
+    b.max_nodes = b.num_nodes = 2 * num_items - 1;
+    b.root = root;
+    return b;
+}
+
+void ref_bvh_query(const void* node_lowers, const void* node_uppers, const int* prim, int root, const float* item_lowers,
+                   const float* item_uppers, int num_items, int ray, const float* qa, const float* qb, const int* roots,
+                   int64_t n, float max_dist, int* offsets, int* indices)
+{
+    BVH b = make_bvh(node_lowers, node_uppers, nullptr, prim, item_lowers, item_uppers, nullptr, num_items, &root);
+    const uint64_t id = (uint64_t)&b;
+    int run = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        offsets[i] = run;
+        const vec3 a(qa[3 * i], qa[3 * i + 1], qa[3 * i + 2]), c(qb[3 * i], qb[3 * i + 1], qb[3 * i + 2]);
+        const int r = roots ? roots[i] : -1;
+        bvh_query_t q = ray ? bvh_query_ray(id, a, c, r) : bvh_query_aabb(id, a, c, r);
+        int item;
+        while (ray ? bvh_query_ray_next(q, item, max_dist) : bvh_query_next(q, item, max_dist)) {
+            if (indices)
+                indices[run] = item;
+            ++run;
+        }
+    }
+    offsets[n] = run;
+}
+
+void ref_bvh_group_roots(const void* node_lowers, const void* node_uppers, const int* parents, const int* prim,
+                         const int* item_groups, int num_items, int root, const int* group_ids, int64_t n, int* roots)
+{
+    BVH b = make_bvh(node_lowers, node_uppers, parents, prim, nullptr, nullptr, item_groups, num_items, &root);
+    for (int64_t i = 0; i < n; ++i)
+        roots[i] = bvh_get_group_root((uint64_t)&b, group_ids[i]);
+}
+
 // standalone primitives for unit-level pinning of the restatement
 void ref_closest_point_to_triangle(const float* a, const float* b, const float* c, const float* p, float* uv)
 {

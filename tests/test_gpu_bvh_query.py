@@ -106,3 +106,43 @@ def test_mesh_query_aabb(wp, oracle_mod):
         assert sorted(idx2[off2[i] : off2[i + 1]].tolist()) == want.tolist()
     with pytest.raises(TypeError):
         wp.mesh_query_aabb(wp.Bvh(wp.array(tlo, dtype=wp.vec3), wp.array(thi, dtype=wp.vec3)), qlo, qhi)
+
+
+@pytest.mark.parametrize("leaf", [1, 4])
+def test_group_roots_and_rooted_queries(wp, oracle_mod, leaf):
+    """wp.bvh_get_group_root + root= traversal (warp/tests/geometry/test_grouped_bvh.py): fixture from the
+    reference's header code, then the oracle on a larger grouped tree, before and after a refit."""
+    import os
+    from test_oracle import _group_case
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_group_queries.npz"))
+    lo, hi, groups, qlo, qhi, s, d, gid = _group_case(900 + leaf, 400, 6)
+    bvh = wp.Bvh(wp.array(lo, dtype=wp.vec3), wp.array(hi, dtype=wp.vec3), groups=wp.array(groups, dtype=wp.int32), leaf_size=leaf)
+    roots = wp.bvh_get_group_root(bvh, gid)
+    assert np.array_equal(roots, g[f"leaf{leaf}_roots"])
+    off, idx = wp.bvh_query_aabb(bvh, qlo, qhi, roots=roots).numpy()
+    assert np.array_equal(off, g[f"leaf{leaf}_aabb_offsets"]) and np.array_equal(idx, g[f"leaf{leaf}_aabb_indices"])
+    off, idx = wp.bvh_query_ray(bvh, s, d, 6.0, roots=wp.array(roots, dtype=wp.int32)).numpy()
+    assert np.array_equal(off, g[f"leaf{leaf}_ray_offsets"]) and np.array_equal(idx, g[f"leaf{leaf}_ray_indices"])
+
+    lo, hi, groups, qlo, qhi, s, d, gid = _group_case(77 + leaf, 20000, 37)
+    lo_d, hi_d = wp.array(lo, dtype=wp.vec3), wp.array(hi, dtype=wp.vec3)
+    bvh = wp.Bvh(lo_d, hi_d, groups=wp.array(groups, dtype=wp.int32), leaf_size=leaf)
+    tree = oracle_mod.lbvh_build(lo, hi, leaf, groups=groups)
+    roots = wp.bvh_get_group_root(bvh, wp.array(gid, dtype=wp.int32)).numpy()
+    assert np.array_equal(roots, oracle_mod.bvh_group_roots(tree, groups, gid))
+    for r in (roots, np.full(64, -1, np.int32)):
+        off, idx = wp.bvh_query_aabb(bvh, qlo, qhi, roots=r).numpy()
+        woff, widx = oracle_mod.bvh_query(tree, lo, hi, qlo, qhi, roots=r)
+        assert np.array_equal(off, woff) and np.array_equal(idx, widx)
+    lo2, hi2 = (lo + np.float32(0.5)).astype(np.float32), (hi + np.float32(0.75)).astype(np.float32)
+    lo_d.assign(lo2), hi_d.assign(hi2)
+    bvh.refit()
+    oracle_mod.lbvh_refit(tree, lo2, hi2)
+    off, idx = wp.bvh_query_ray(bvh, s, d, 8.0, roots=roots).numpy()
+    woff, widx = oracle_mod.bvh_query(tree, lo2, hi2, s, d, ray=True, max_dist=8.0, roots=roots)
+    assert np.array_equal(off, woff) and np.array_equal(idx, widx)
+    # an ungrouped tree: every item is in group 0
+    plain = wp.Bvh(lo_d, hi_d, leaf_size=leaf)
+    info_root = plain.download_tree()["root"]
+    assert wp.bvh_get_group_root(plain, np.array([0, 1, -3], np.int32)).tolist() == [info_root, -1, -1]

@@ -342,3 +342,62 @@ def test_mesh_query_aabb_restatement_matches_reference_fixture(oracle_mod, gold)
     for i, want in enumerate(_brute_aabb(tlo, thi, rv["aabb_lowers"], rv["aabb_uppers"])):
         o_, x_ = rv["lbvh4_aabb_offsets"], rv["lbvh4_aabb_indices"]
         assert sorted(x_[o_[i] : o_[i + 1]].tolist()) == want.tolist()
+
+
+# ------------------------------------------------------------------------------------------------
+# generic iterator + group roots pinned on the reference's own header code (oracle/_ref) and on a fixture
+# ------------------------------------------------------------------------------------------------
+GROUP_GOLD = os.path.join(os.path.dirname(__file__), "golden", "golden_group_queries.npz")
+
+
+def _group_case(seed, n, ngroups):
+    rng = np.random.default_rng(seed)
+    lo, hi = random_boxes(n, seed=seed)
+    groups = rng.integers(0, ngroups, n).astype(np.int32)
+    qlo = (rng.random((64, 3)) * 10).astype(np.float32)
+    qhi = (qlo + rng.random((64, 3)).astype(np.float32) * 4).astype(np.float32)
+    s = (rng.random((64, 3)) * 10).astype(np.float32)
+    d = rng.standard_normal((64, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    gid = rng.integers(-1, ngroups + 2, 64).astype(np.int32)  # some absent groups
+    return lo, hi, groups, qlo, qhi, s, d, gid
+
+
+def test_group_roots_and_rooted_queries_match_reference_fixture(oracle_mod):
+    o = oracle_mod
+    g = np.load(GROUP_GOLD)
+    for leaf in (1, 4):
+        lo, hi, groups, qlo, qhi, s, d, gid = _group_case(900 + leaf, 400, 6)
+        tree = o.lbvh_build(lo, hi, leaf, groups=groups)
+        roots = o.bvh_group_roots(tree, groups, gid)
+        assert np.array_equal(roots, g[f"leaf{leaf}_roots"])
+        assert (roots == -1).sum() > 0 and (roots >= 0).sum() > 30
+        off, idx = o.bvh_query(tree, lo, hi, qlo, qhi, roots=roots)
+        assert np.array_equal(off, g[f"leaf{leaf}_aabb_offsets"]) and np.array_equal(idx, g[f"leaf{leaf}_aabb_indices"])
+        off, idx = o.bvh_query(tree, lo, hi, s, d, ray=True, max_dist=6.0, roots=roots)
+        assert np.array_equal(off, g[f"leaf{leaf}_ray_offsets"]) and np.array_equal(idx, g[f"leaf{leaf}_ray_indices"])
+        # a rooted query reports exactly the whole-tree hits that belong to the group (absent group -> whole tree)
+        woff, widx = o.bvh_query(tree, lo, hi, qlo, qhi)
+        off, idx = o.bvh_query(tree, lo, hi, qlo, qhi, roots=roots)
+        for i in range(64):
+            whole = widx[woff[i] : woff[i + 1]]
+            want = whole if roots[i] == -1 else whole[groups[whole] == gid[i]]
+            assert sorted(idx[off[i] : off[i + 1]].tolist()) == sorted(want.tolist())
+
+
+def test_generic_iterator_live_reference(oracle_mod):
+    o = oracle_mod
+    if not o.ref_available():
+        pytest.skip("oracle/_ref/libwarp_ref_cpu.so not present")
+    for seed, n, ng, leaf in ((1, 300, 5, 1), (2, 1000, 9, 4), (3, 64, 64, 2), (4, 500, 1, 8)):
+        lo, hi, groups, qlo, qhi, s, d, gid = _group_case(seed, n, ng)
+        for grp in (groups, None):
+            tree = o.lbvh_build(lo, hi, leaf, groups=grp)
+            roots = o.bvh_group_roots(tree, grp, gid)
+            assert np.array_equal(roots, o.ref_bvh_group_roots(tree, grp, gid))
+            for r in (None, roots):
+                a, b = o.bvh_query(tree, lo, hi, qlo, qhi, roots=r), o.ref_bvh_query(tree, lo, hi, qlo, qhi, roots=r)
+                assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+                a = o.bvh_query(tree, lo, hi, s, d, ray=True, max_dist=5.0, roots=r)
+                b = o.ref_bvh_query(tree, lo, hi, s, d, ray=True, max_dist=5.0, roots=r)
+                assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])

@@ -47,7 +47,13 @@ from .queries import (  # noqa: F401
     query_stats,
 )
 
-from .bvh_queries import BvhQueryResult, bvh_query_aabb, bvh_query_ray, mesh_query_aabb  # noqa: F401,E402
+from .bvh_queries import (  # noqa: F401,E402
+    BvhQueryResult,
+    bvh_get_group_root,
+    bvh_query_aabb,
+    bvh_query_ray,
+    mesh_query_aabb,
+)
 
 from .capture import (  # noqa: F401,E402
     Graph,

@@ -111,10 +111,11 @@ SIGNATURES = {
     "wp_b200_get_ray_order": (_i, []),
     "wp_b200_query_stats_enable": (None, [_i]),
     "wp_b200_query_stats_read": (None, [ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]),
-    "wp_b200_bvh_query_aabb_count": (_i, [_u64, _vp, _vp, _i64, _vp]),
-    "wp_b200_bvh_query_aabb_fill": (_i, [_u64, _vp, _vp, _i64, _vp, _vp]),
-    "wp_b200_bvh_query_ray_count": (_i, [_u64, _vp, _vp, _i64, _f, _vp]),
-    "wp_b200_bvh_query_ray_fill": (_i, [_u64, _vp, _vp, _i64, _f, _vp, _vp]),
+    "wp_b200_bvh_query_aabb_count": (_i, [_u64, _vp, _vp, _vp, _i64, _vp]),
+    "wp_b200_bvh_query_aabb_fill": (_i, [_u64, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "wp_b200_bvh_query_ray_count": (_i, [_u64, _vp, _vp, _vp, _i64, _f, _vp]),
+    "wp_b200_bvh_query_ray_fill": (_i, [_u64, _vp, _vp, _vp, _i64, _f, _vp, _vp]),
+    "wp_b200_bvh_get_group_root": (_i, [_u64, _vp, _i64, _vp]),
     "wp_b200_mesh_query_aabb_count": (_i, [_u64, _vp, _vp, _i64, _vp]),
     "wp_b200_mesh_query_aabb_fill": (_i, [_u64, _vp, _vp, _i64, _vp, _vp]),
     "wp_b200_exclusive_scan_i32": (_i, [_vp, _vp, _i64]),

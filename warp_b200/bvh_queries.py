@@ -43,7 +43,17 @@ def _as_dev(a, dev, what):
     return array(h, dtype=vec3, device=dev)
 
 
-def _run(bvh, qa, qb, ray, max_dist, mesh=False):
+def _roots_arg(roots, n, dev):
+    if roots is None:
+        return None
+    if not isinstance(roots, array):
+        roots = array(np.ascontiguousarray(roots, dtype=np.int32), dtype=int32, device=dev)
+    if roots.dtype != int32 or len(roots) != n:
+        raise RuntimeError("roots should be an int32 array with one entry per query")
+    return roots
+
+
+def _run(bvh, qa, qb, ray, max_dist, mesh=False, roots=None):
     if mesh:
         if not isinstance(bvh, Mesh) or not bvh.id:
             raise TypeError("expected a warp_b200.Mesh")
@@ -58,12 +68,14 @@ def _run(bvh, qa, qb, ray, max_dist, mesh=False):
     p = lambda a: ctypes.c_void_p(a.ptr or 0)  # noqa: E731
     counts = empty(n, int32, dev)
     offsets = empty(n + 1, int32, dev)
+    roots = _roots_arg(roots, n, dev)
+    pr = ctypes.c_void_p(roots.ptr or 0) if roots is not None else None
     if mesh:
         ok = c.wp_b200_mesh_query_aabb_count(bvh.id, p(qa), p(qb), n, p(counts))
     elif ray:
-        ok = c.wp_b200_bvh_query_ray_count(bvh.id, p(qa), p(qb), n, max_dist, p(counts))
+        ok = c.wp_b200_bvh_query_ray_count(bvh.id, p(qa), p(qb), pr, n, max_dist, p(counts))
     else:
-        ok = c.wp_b200_bvh_query_aabb_count(bvh.id, p(qa), p(qb), n, p(counts))
+        ok = c.wp_b200_bvh_query_aabb_count(bvh.id, p(qa), p(qb), pr, n, p(counts))
     ok = ok and c.wp_b200_exclusive_scan_i32(p(counts), p(offsets), n)
     if not ok:
         raise RuntimeError(f"bvh query failed: {_lib.error_string()}")
@@ -73,22 +85,41 @@ def _run(bvh, qa, qb, ray, max_dist, mesh=False):
         if mesh:
             ok = c.wp_b200_mesh_query_aabb_fill(bvh.id, p(qa), p(qb), n, p(offsets), p(indices))
         elif ray:
-            ok = c.wp_b200_bvh_query_ray_fill(bvh.id, p(qa), p(qb), n, max_dist, p(offsets), p(indices))
+            ok = c.wp_b200_bvh_query_ray_fill(bvh.id, p(qa), p(qb), pr, n, max_dist, p(offsets), p(indices))
         else:
-            ok = c.wp_b200_bvh_query_aabb_fill(bvh.id, p(qa), p(qb), n, p(offsets), p(indices))
+            ok = c.wp_b200_bvh_query_aabb_fill(bvh.id, p(qa), p(qb), pr, n, p(offsets), p(indices))
         if not ok:
             raise RuntimeError(f"bvh query failed: {_lib.error_string()}")
     return BvhQueryResult(offsets, indices, total)
 
 
-def bvh_query_aabb(bvh, lowers, uppers) -> BvhQueryResult:
-    """All items whose AABB overlaps ``[lowers[i], uppers[i]]`` (closed boxes, ``intersect.h:183-192``)."""
-    return _run(bvh, lowers, uppers, False, 0.0)
+def bvh_query_aabb(bvh, lowers, uppers, roots=None) -> BvhQueryResult:
+    """All items whose AABB overlaps ``[lowers[i], uppers[i]]`` (closed boxes, ``intersect.h:183-192``).
+    ``roots`` (optional, one int per query): start the traversal at that node -- e.g. a group's subtree from
+    :func:`bvh_get_group_root` -- instead of the tree root; ``-1`` means the tree root (``bvh.h:494-518``)."""
+    return _run(bvh, lowers, uppers, False, 0.0, roots=roots)
 
 
-def bvh_query_ray(bvh, starts, dirs, max_dist: float = FLT_MAX) -> BvhQueryResult:
+def bvh_query_ray(bvh, starts, dirs, max_dist: float = FLT_MAX, roots=None) -> BvhQueryResult:
     """All items whose AABB the ray ``starts[i] + t * dirs[i]`` enters at ``t < max_dist`` (``bvh.h:483-487``)."""
-    return _run(bvh, starts, dirs, True, float(max_dist))
+    return _run(bvh, starts, dirs, True, float(max_dist), roots=roots)
+
+
+def bvh_get_group_root(bvh, group_ids):
+    """``wp.bvh_get_group_root`` for a batch of group ids (``bvh.h:376-390``): the node whose subtree holds exactly the
+    items of each group (``-1`` where the group does not occur), as reference node indices usable as ``roots=``.
+    Device array in -> device array out; anything else -> numpy array out."""
+    if not isinstance(bvh, (Bvh, Mesh)) or not bvh.id:
+        raise TypeError("expected a warp_b200.Bvh or warp_b200.Mesh")
+    dev = bvh.device
+    host = not isinstance(group_ids, array)
+    g = array(np.ascontiguousarray(group_ids, dtype=np.int32), dtype=int32, device=dev) if host else group_ids
+    if g.dtype != int32:
+        raise RuntimeError("group_ids should be an int32 array")
+    out = empty(len(g), int32, dev)
+    if not _lib.core().wp_b200_bvh_get_group_root(bvh.id, ctypes.c_void_p(g.ptr or 0), len(g), ctypes.c_void_p(out.ptr or 0)):
+        raise RuntimeError(f"bvh_get_group_root failed: {_lib.error_string()}")
+    return out.numpy() if host else out
 
 
 def mesh_query_aabb(mesh, lowers, uppers) -> BvhQueryResult:

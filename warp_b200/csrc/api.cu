@@ -143,6 +143,7 @@ TreeView make_view(const BvhState& s)
     tv.header = s.header;
     tv.tris = s.tris;
     tv.prim = s.prim;
+    tv.parent_int = s.parent_int;
     tv.n = s.n;
     return tv;
 }
@@ -909,8 +910,8 @@ int wp_b200_mesh_query_ray_host(uint64_t id, const float* starts, const float* d
 static long long* g_scan_scratch[64] = {};
 static size_t g_scan_scratch_words[64] = {};
 
-static int bvh_query_common(uint64_t id, int ray, const float* qa, const float* qb, int64_t n, float max_dist,
-                            int32_t* counts, const int32_t* offsets, int32_t* indices, bool want_mesh = false)
+static int bvh_query_common(uint64_t id, int ray, const float* qa, const float* qb, const int32_t* roots, int64_t n,
+                            float max_dist, int32_t* counts, const int32_t* offsets, int32_t* indices, bool want_mesh = false)
 {
     MeshState* ms = nullptr;
     BvhState* s = find_tree(id, &ms);
@@ -928,7 +929,7 @@ static int bvh_query_common(uint64_t id, int ray, const float* qa, const float* 
         return 1;
     }
     const char* err = wb_bvh_query(make_view(*s), want_mesh ? nullptr : s->item_lowers, want_mesh ? nullptr : s->item_uppers,
-                                   ray, qa, qb, n, max_dist, counts, offsets, indices, st);
+                                   ray, qa, qb, roots, n, max_dist, counts, offsets, indices, st);
     if (err) {
         set_error("Warp error: BVH query failed: %s", err);
         return 0;
@@ -936,34 +937,59 @@ static int bvh_query_common(uint64_t id, int ray, const float* qa, const float* 
     return 1;
 }
 
-int wp_b200_bvh_query_aabb_count(uint64_t id, const float* lowers, const float* uppers, int64_t n, int32_t* counts)
+int wp_b200_bvh_query_aabb_count(uint64_t id, const float* lowers, const float* uppers, const int32_t* roots, int64_t n,
+                                 int32_t* counts)
 {
-    return bvh_query_common(id, 0, lowers, uppers, n, 0.f, counts, nullptr, nullptr);
+    return bvh_query_common(id, 0, lowers, uppers, roots, n, 0.f, counts, nullptr, nullptr);
 }
-int wp_b200_bvh_query_aabb_fill(uint64_t id, const float* lowers, const float* uppers, int64_t n, const int32_t* offsets,
-                                int32_t* indices)
+int wp_b200_bvh_query_aabb_fill(uint64_t id, const float* lowers, const float* uppers, const int32_t* roots, int64_t n,
+                                const int32_t* offsets, int32_t* indices)
 {
-    return bvh_query_common(id, 0, lowers, uppers, n, 0.f, nullptr, offsets, indices);
+    return bvh_query_common(id, 0, lowers, uppers, roots, n, 0.f, nullptr, offsets, indices);
 }
-int wp_b200_bvh_query_ray_count(uint64_t id, const float* starts, const float* dirs, int64_t n, float max_dist,
-                                int32_t* counts)
+int wp_b200_bvh_query_ray_count(uint64_t id, const float* starts, const float* dirs, const int32_t* roots, int64_t n,
+                                float max_dist, int32_t* counts)
 {
-    return bvh_query_common(id, 1, starts, dirs, n, max_dist, counts, nullptr, nullptr);
+    return bvh_query_common(id, 1, starts, dirs, roots, n, max_dist, counts, nullptr, nullptr);
 }
-int wp_b200_bvh_query_ray_fill(uint64_t id, const float* starts, const float* dirs, int64_t n, float max_dist,
-                               const int32_t* offsets, int32_t* indices)
+int wp_b200_bvh_query_ray_fill(uint64_t id, const float* starts, const float* dirs, const int32_t* roots, int64_t n,
+                               float max_dist, const int32_t* offsets, int32_t* indices)
 {
-    return bvh_query_common(id, 1, starts, dirs, n, max_dist, nullptr, offsets, indices);
+    return bvh_query_common(id, 1, starts, dirs, roots, n, max_dist, nullptr, offsets, indices);
 }
 
 int wp_b200_mesh_query_aabb_count(uint64_t id, const float* lowers, const float* uppers, int64_t n, int32_t* counts)
 {
-    return bvh_query_common(id, 0, lowers, uppers, n, 0.f, counts, nullptr, nullptr, true);
+    return bvh_query_common(id, 0, lowers, uppers, nullptr, n, 0.f, counts, nullptr, nullptr, true);
 }
 int wp_b200_mesh_query_aabb_fill(uint64_t id, const float* lowers, const float* uppers, int64_t n, const int32_t* offsets,
                                  int32_t* indices)
 {
-    return bvh_query_common(id, 0, lowers, uppers, n, 0.f, nullptr, offsets, indices, true);
+    return bvh_query_common(id, 0, lowers, uppers, nullptr, n, 0.f, nullptr, offsets, indices, true);
+}
+
+// bvh_get_group_root (bvh.h:376-390) for a batch of group ids: reference node index of the subtree that holds
+// exactly the items of the group, -1 when the group does not occur
+int wp_b200_bvh_get_group_root(uint64_t id, const int32_t* group_ids, int64_t n, int32_t* roots)
+{
+    MeshState* ms = nullptr;
+    BvhState* s = find_tree(id, &ms);
+    if (!s) {
+        set_error("Warp error: invalid id");
+        return 0;
+    }
+    DeviceGuard g(s->device);
+    cudaStream_t st = current_stream(s->device);
+    if (n <= 0)
+        return 1;
+    if (s->n == 0)
+        return check(cudaMemsetAsync(roots, 0xff, 4 * (size_t)n, st), "memset") ? 1 : 0;
+    const char* err = wb_group_roots(make_view(*s), s->groups ? s->keys : nullptr, group_ids, n, roots, st);
+    if (err) {
+        set_error("Warp error: group root lookup failed: %s", err);
+        return 0;
+    }
+    return 1;
 }
 
 int wp_b200_exclusive_scan_i32(const int32_t* counts, int32_t* offsets, int64_t n)

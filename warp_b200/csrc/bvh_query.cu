@@ -8,6 +8,7 @@
 // (offsets[n+1], indices[total]) in exactly the order the reference iterator would yield them.
 #include "query.h"
 #include "state.h"
+#include "merge.cuh"  // wb_goes_right
 
 namespace {
 
@@ -56,8 +57,8 @@ __device__ __forceinline__ float3 ld3(const float* __restrict__ p, size_t i)
 template <bool RAY, bool FILL, bool MESH>
 __global__ void __launch_bounds__(BQ)
 k_bvh_query(TreeView tv, const float* __restrict__ item_lowers, const float* __restrict__ item_uppers,
-            const float* __restrict__ qa_in, const float* __restrict__ qb_in, long long nq, float max_dist,
-            int* __restrict__ counts, const int* __restrict__ offsets, int* __restrict__ indices)
+            const float* __restrict__ qa_in, const float* __restrict__ qb_in, const int* __restrict__ roots, long long nq,
+            float max_dist, int* __restrict__ counts, const int* __restrict__ offsets, int* __restrict__ indices)
 {
     const TreeHeader h = *tv.header;
     for (long long i = (long long)blockIdx.x * BQ + threadIdx.x; i < nq; i += (long long)gridDim.x * BQ) {
@@ -70,13 +71,44 @@ k_bvh_query(TreeView tv, const float* __restrict__ item_lowers, const float* __r
 
         Entry2 stack[WB_QUERY_STACK];
         int top = 0;
-        if (test_box<RAY>(qa, qb, make_float3(h.lx, h.ly, h.lz), make_float3(h.hx, h.hy, h.hz), max_dist)) {
-            if (h.root_ref & WB_LEAF)
-                stack[0].a = WB_LEAF | 0u, stack[0].b = h.root_count;
-            else
-                stack[0].a = (h.root_ref & WB_IDX_MASK) - (uint32_t)tv.n, stack[0].b = 0;
-            top = 1;
+        // start node: the tree root, or the caller's `root` (bvh.h:504: root == -1 ? *bvh.root : root).  A node's own
+        // box and leaf flag live in its parent's pair.
+        float3 rlo = make_float3(h.lx, h.ly, h.lz), rhi = make_float3(h.hx, h.hy, h.hz);
+        Entry2 start;
+        if (h.root_ref & WB_LEAF)
+            start.a = WB_LEAF | 0u, start.b = h.root_count;
+        else
+            start.a = (h.root_ref & WB_IDX_MASK) - (uint32_t)tv.n, start.b = 0;
+        const int r = roots ? __ldg(roots + i) : -1;
+        if (r >= 0 && r < tv.n) {  // an original leaf: one item
+            start.a = (uint32_t)r | WB_LEAF, start.b = 1u;
+            if (MESH) {
+                const float4* t = tv.tris + 3 * (size_t)r;
+                const float4 t0 = __ldg(t), t1 = __ldg(t + 1), t2 = __ldg(t + 2);
+                const float3 p = make_float3(t0.x, t0.y, t0.z), q = make_float3(t0.w, t1.x, t1.y), w = make_float3(t1.z, t1.w, t2.x);
+                rlo = wb_min3(wb_min3(p, q), w), rhi = wb_max3(wb_max3(p, q), w);
+            } else {
+                const int item = __ldg(tv.prim + r);
+                rlo = ld3(item_lowers, (size_t)item), rhi = ld3(item_uppers, (size_t)item);
+            }
+        } else if (r >= tv.n && r < 2 * tv.n - 1) {
+            const int s = r - tv.n;
+            const int p = __ldg(tv.parent_int + s);
+            if (p != WB_NO_PARENT) {
+                const int ps = p - tv.n;
+                const int side = ((int)tv.pairs[2 * (size_t)s + 1].aux == ps) ? 0 : 1;  // a left child's range ends at the split
+                const NodeRec rec = tv.pairs[2 * (size_t)ps + side];
+                rlo = make_float3(rec.lx, rec.ly, rec.lz), rhi = make_float3(rec.hx, rec.hy, rec.hz);
+                if (rec.ref & WB_LEAF) {
+                    const uint32_t first = side ? (uint32_t)ps + 1u : rec.aux, last = side ? rec.aux : (uint32_t)ps;
+                    start.a = first | WB_LEAF, start.b = last - first + 1u;
+                } else {
+                    start.a = (uint32_t)s, start.b = 0;
+                }
+            }
         }
+        if (test_box<RAY>(qa, qb, rlo, rhi, max_dist))
+            stack[top++] = start;
         while (top) {
             const Entry2 cur = stack[--top];
             if (cur.a & WB_LEAF) {
@@ -219,6 +251,68 @@ k_scan_add(int* __restrict__ out, long long n, const long long* __restrict__ til
         out[n] = *total;
 }
 
+// bvh_get_group_root (bvh.h:287-390): binary search of the group's first / last sorted position (keys are sorted
+// by group << 32 | code), then the lowest node covering [first, last] -- the reference walks node_parents from both
+// leaves (lca); here the climb goes from the first leaf through parent_int until the range covers the last.
+__global__ void __launch_bounds__(BQ)
+k_group_roots(TreeView tv, const uint64_t* __restrict__ keys, const int* __restrict__ group_ids, long long nq,
+              int* __restrict__ roots)
+{
+    const long long i = (long long)blockIdx.x * BQ + threadIdx.x;
+    if (i >= nq)
+        return;
+    const TreeHeader h = *tv.header;
+    const int n = tv.n, g = __ldg(group_ids + i);
+    int first, last;
+    if (!keys) {  // get_leaf_group == 0 for every leaf (bvh.h:287-292)
+        first = (g == 0) ? 0 : -1;
+        last = n - 1;
+    } else {
+        int lo = 0, hi = n;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((int)(__ldg(keys + mid) >> 32) < g)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        first = (lo == n || (int)(__ldg(keys + lo) >> 32) != g) ? -1 : lo;
+        lo = 0, hi = n;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((int)(__ldg(keys + mid) >> 32) <= g)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        last = lo - 1;
+    }
+    int root = -1;
+    if (first >= 0) {
+        if (first == last) {
+            root = (n == 1) ? (int)(h.root_ref & WB_IDX_MASK) : first;
+        } else if (first == 0 && last == n - 1) {
+            root = (int)(h.root_ref & WB_IDX_MASK);
+        } else {
+            // parent of leaf `first`: the same rule the builder applied (merge.cuh)
+            const bool gr = keys ? wb_goes_right<uint64_t, true>(keys, tv.prim, n, first, first) : true;
+            int s = gr ? first : first - 1;
+            for (int guard = 0; guard < 4096; ++guard) {
+                const int l = (int)tv.pairs[2 * (size_t)s].aux, r = (int)tv.pairs[2 * (size_t)s + 1].aux;
+                if (l <= first && r >= last) {
+                    root = n + s;
+                    break;
+                }
+                const int p = __ldg(tv.parent_int + s);
+                if (p == WB_NO_PARENT)
+                    break;
+                s = p - n;
+            }
+        }
+    }
+    roots[i] = root;
+}
+
 int grid_for(long long nq)
 {
     int dev = 0, sms = 148;
@@ -231,7 +325,7 @@ int grid_for(long long nq)
 }  // namespace
 
 const char* wb_bvh_query(const TreeView& tv, const float* item_lowers, const float* item_uppers, int ray,
-                         const float* qa, const float* qb, long long nq, float max_dist, int* counts,
+                         const float* qa, const float* qb, const int* roots, long long nq, float max_dist, int* counts,
                          const int* offsets, int* indices, cudaStream_t stream)
 {
     if (nq <= 0)
@@ -240,7 +334,7 @@ const char* wb_bvh_query(const TreeView& tv, const float* item_lowers, const flo
     const bool fill = offsets != nullptr;
     const bool mesh = item_lowers == nullptr;  // items are the triangles of tv.tris
 #define WB_BQ_LAUNCH(R, F, M) \
-    k_bvh_query<R, F, M><<<grid, BQ, 0, stream>>>(tv, item_lowers, item_uppers, qa, qb, nq, max_dist, counts, offsets, indices)
+    k_bvh_query<R, F, M><<<grid, BQ, 0, stream>>>(tv, item_lowers, item_uppers, qa, qb, roots, nq, max_dist, counts, offsets, indices)
     if (mesh) {
         if (ray)
             return "ray hit lists are defined for wp.Bvh only";
@@ -260,6 +354,16 @@ const char* wb_bvh_query(const TreeView& tv, const float* item_lowers, const flo
             WB_BQ_LAUNCH(false, false, false);
     }
 #undef WB_BQ_LAUNCH
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+const char* wb_group_roots(const TreeView& tv, const void* keys, const int* group_ids, long long nq, int* roots,
+                           cudaStream_t stream)
+{
+    if (nq <= 0)
+        return nullptr;
+    k_group_roots<<<(int)((nq + BQ - 1) / BQ), BQ, 0, stream>>>(tv, (const uint64_t*)keys, group_ids, nq, roots);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

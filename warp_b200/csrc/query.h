@@ -4,9 +4,13 @@
 
 // generic BVH queries (bvh_query.cu): ray != 0 -> (qa, qb) = (start, dir) else (lower, upper).  offsets == NULL
 // counts hits into counts[nq]; otherwise writes the hit items of query i at indices[offsets[i]...]
+// roots: optional per-query start node (reference node index, e.g. from wb_group_roots; < 0 = the tree root)
 const char* wb_bvh_query(const TreeView& tv, const float* item_lowers, const float* item_uppers, int ray,
-                         const float* qa, const float* qb, long long nq, float max_dist, int* counts,
+                         const float* qa, const float* qb, const int* roots, long long nq, float max_dist, int* counts,
                          const int* offsets, int* indices, cudaStream_t stream);
+// bvh_get_group_root for a batch; keys = the tree's 64-bit (group << 32 | code) keys, NULL for an ungrouped tree
+const char* wb_group_roots(const TreeView& tv, const void* keys, const int* group_ids, long long nq, int* roots,
+                           cudaStream_t stream);
 // offsets[0..n] = exclusive prefix sums of counts[0..n); scratch = ceil(n / 2048) + 1 int64 words
 const char* wb_exclusive_scan(const int* counts, int* offsets, long long n, long long* scratch, cudaStream_t stream);
 
