@@ -13,8 +13,9 @@
  *     vectors of warp/tests/geometry/test_mesh.py and on random trees (tests/test_oracle.py);
  *   - LBVH (Morton keys, sorted order, topology): the reference LBVH is CUDA-only
  *     (warp/native/bvh.cpp:226-233 rejects it on the host); pinned by traversing the tree this
- *     file builds with the reference's own query code and, on the GPU box, against the reference
- *     bvh.cu kernels compiled from source (oracle/_ref/libwarp_ref_lbvh.so).
+ *     file builds with the reference's own query code and against arrays dumped on a B200 from the
+ *     reference's own bvh.cu (full reference build, baseline/ref_cuda.py golden ->
+ *     tests/golden/golden_ref_lbvh.npz): all 2N-1 nodes equal bit for bit.
  *
  * Float semantics: IEEE binary32, round-to-nearest, NO fused multiply-add except where the
  * reference calls fmaf() explicitly (intersect.h:334-341).  Build with -ffp-contract=off and no
