@@ -339,7 +339,7 @@ def main():
     # ---- side measurements: build / refit (C2) and rays (C3) ---------------------------------------
     extra = {"triangles": T, "first_build_ms_incl_alloc": first_build_ms, "queries_found": found}
     if not args.no_extra:
-        extra.update(side_measurements(wp, core, mg, dev, stream, mesh, pts, P, I, peak_gbs, rank))
+        extra.update(side_measurements(wp, core, mg, dev, stream, mesh, pts, P, I, peak_gbs, rank, comm, world))
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -364,7 +364,7 @@ def main():
     return 0
 
 
-def side_measurements(wp, core, mg, dev, stream, mesh, pts, P, I, peak_gbs, rank):
+def side_measurements(wp, core, mg, dev, stream, mesh, pts, P, I, peak_gbs, rank, comm=None, world=1):
     """LBVH build + refit ms on C2 (with their HBM rooflines) and ray throughput on C3."""
     T = len(I) // 3
     out = {}
@@ -427,6 +427,28 @@ def side_measurements(wp, core, mg, dev, stream, mesh, pts, P, I, peak_gbs, rank
                        "ms": ms, "hit_fraction": float(r_out.result.numpy().mean()),
                        "pair_fetches_per_ray": st.pair_fetches / n, "tri_fetches_per_ray": st.tri_fetches / n,
                        "bytes_fetched_GBps": (n * (24 + 37) + 64 * st.pair_fetches + 48 * st.tri_fetches) / (ms * 1e-3) / 1e9}  # fmt: skip
+        if comm is not None:
+            # rays at N GPUs (weak scaling): every rank traces its own 4096 x 4096 image of the replicated terrain
+            # (eye shifted per rank) and the seven result fields are all-gathered into global ray order
+            from warp_b200.distributed import ShardPlan, sharded_query_ray
+
+            S2, D2 = mg.pinhole_rays(4096, 4096, eye=(0.5 + 0.02 * rank, -0.6, 0.9))
+            s_d.assign(S2), d_d.assign(D2)
+            plan = ShardPlan(n * world, world)
+            dts = {"result": wp.uint8, "sign": wp.float32, "face": wp.int32, "t": wp.float32, "u": wp.float32,
+                   "v": wp.float32, "normal": wp.vec3}
+            g_out = {k: wp.empty(plan.padded, dt, dev) for k, dt in dts.items()}
+            run_n = lambda: sharded_query_ray(hm, s_d, d_d, plan, 1.0e6, comm, rank, local_out=r_out, global_out=g_out)  # noqa: E731
+            run_n()
+            comm.barrier()
+            core.wp_cuda_context_synchronize(None)
+            ms_n = statistics.median([event_ms(core, run_n, stream) for _ in range(3)])
+            tmax = wp.array(np.array([ms_n], np.float32), dtype=wp.float32, device=dev)
+            comm.allreduce_max(tmax)
+            ms_n = float(tmax.numpy()[0])
+            out["rays_sharded"] = {"workload": "C3 terrain replicated, 4096x4096 rays per GPU, 7 fields all-gathered (NCCL)",
+                                   "n_gpus": world, "rays_per_s": n * world / (ms_n * 1e-3), "ms": ms_n,
+                                   "hits_all_ranks": int(g_out["result"].numpy().sum())}  # fmt: skip
     except Exception as e:  # the headline must not die on a side measurement
         out["rays"] = {"error": repr(e)}
     return out

@@ -50,6 +50,19 @@ glob = gather_fields(local, plan, comm, lambda name, count: np.zeros(count, dt[n
 want = oracle.query_point_no_sign(P, I, tree, Q, 1e6)
 for k in local:
     assert np.array_equal(glob[k][: plan.n], want[k]), (rank, k)
+# rays: seven fields incl. the 12-byte normals (what sharded_query_ray gathers on GPUs)
+S, D = mg.random_rays(P, 777, seed=6)
+rplan = ShardPlan(S.shape[0], 2)
+s, e = rplan.range(rank)
+ls = np.zeros((rplan.shard, 3), np.float32); ld = np.ones((rplan.shard, 3), np.float32)
+ls[: e - s] = S[s:e]; ld[: e - s] = D[s:e]
+rres = oracle.query_ray(P, I, tree, ls, ld, 1e6)
+rdt = {{"result": np.uint8, "sign": np.float32, "face": np.int32, "t": np.float32, "u": np.float32, "v": np.float32}}
+rglob = gather_fields({{k: rres[k] for k in ("result", "sign", "face", "t", "u", "v", "normal")}}, rplan, comm,
+                      lambda name, count: np.zeros((count, 3), np.float32) if name == "normal" else np.zeros(count, rdt[name]))
+rwant = oracle.query_ray(P, I, tree, S, D, 1e6)
+for k in rglob:
+    assert np.array_equal(rglob[k][: rplan.n], rwant[k]), (rank, k)
 # bootstrap: rank 0 invents 128 bytes, rank 1 must receive exactly those
 uid = exchange_unique_id(rank, 2, lambda: bytes(range(128)), addr="127.0.0.1", port={port2})
 assert uid == bytes(range(128))

@@ -178,6 +178,16 @@ def gather_fields(local: dict, plan: ShardPlan, comm, alloc):
     return out
 
 
+def _sharded(local: dict, dtypes: dict, plan: ShardPlan, comm, dev, global_out):
+    from .types import empty
+
+    if comm is None:
+        return local, plan.n
+    if global_out is None:
+        global_out = {k: empty(plan.padded, dtypes[k], dev) for k in local}
+    return gather_fields(local, plan, comm, lambda name, count: global_out[name]), plan.n
+
+
 def sharded_query_point_no_sign(mesh, local_points, plan: ShardPlan, max_dist: float, comm, rank: int,
                                 local_out=None, global_out=None):
     """Each rank answers its shard of a global batch; every rank ends up with all ``plan.n`` answers.
@@ -186,17 +196,38 @@ def sharded_query_point_no_sign(mesh, local_points, plan: ShardPlan, max_dist: f
     are padding).  Returns ``(global_fields, n)``; fields are device arrays of ``plan.padded`` entries.
     """
     from .queries import mesh_query_point_no_sign
-    from .types import empty, float32, int32, uint8
+    from .types import float32, int32, uint8
 
-    dev = mesh.device
     res = mesh_query_point_no_sign(mesh, local_points, max_dist, out=local_out)
     local = {"result": res.result, "face": res.face, "u": res.u, "v": res.v}
     dtypes = {"result": uint8, "face": int32, "u": float32, "v": float32}
-    if comm is None:
-        return local, plan.n
-    if global_out is None:
-        global_out = {k: empty(plan.padded, dtypes[k], dev) for k in local}
-    return gather_fields(local, plan, comm, lambda name, count: global_out[name]), plan.n
+    return _sharded(local, dtypes, plan, comm, mesh.device, global_out)
+
+
+def sharded_query_point(mesh, local_points, plan: ShardPlan, max_dist: float, comm, rank: int, local_out=None,
+                        global_out=None):
+    """Signed closest point (``mesh_query_point``), sharded like :func:`sharded_query_point_no_sign`; adds ``sign``."""
+    from .queries import mesh_query_point
+    from .types import float32, int32, uint8
+
+    res = mesh_query_point(mesh, local_points, max_dist, out=local_out)
+    local = {"result": res.result, "sign": res.sign, "face": res.face, "u": res.u, "v": res.v}
+    dtypes = {"result": uint8, "sign": float32, "face": int32, "u": float32, "v": float32}
+    return _sharded(local, dtypes, plan, comm, mesh.device, global_out)
+
+
+def sharded_query_ray(mesh, local_starts, local_dirs, plan: ShardPlan, max_t: float, comm, rank: int, local_out=None,
+                      global_out=None):
+    """Closest ray hit (``mesh_query_ray``) for this rank's shard of a global ray batch; the seven result fields
+    are all-gathered into global ray order (``normal`` as 12-byte vec3 entries)."""
+    from .queries import mesh_query_ray
+    from .types import float32, int32, uint8, vec3
+
+    res = mesh_query_ray(mesh, local_starts, local_dirs, max_t, out=local_out)
+    local = {"result": res.result, "sign": res.sign, "face": res.face, "t": res.t, "u": res.u, "v": res.v,
+             "normal": res.normal}  # fmt: skip
+    dtypes = {"result": uint8, "sign": float32, "face": int32, "t": float32, "u": float32, "v": float32, "normal": vec3}
+    return _sharded(local, dtypes, plan, comm, mesh.device, global_out)
 
 
 class GlooCommunicator:
