@@ -249,6 +249,12 @@ WP_B200_API int wp_b200_bvh_query_ray_fill(uint64_t id, const float* starts, con
 WP_B200_API int wp_b200_bvh_get_group_root(uint64_t id, const int32_t* group_ids, int64_t n, int32_t* roots);
 WP_B200_API int wp_b200_exclusive_scan_i32(const int32_t* counts, int32_t* offsets, int64_t n);
 
+/* how refit() walks the tree: 0 = auto (default: wavefront from 2^21 items up), 1 = atomic arrival counters
+ * (the reference's scheme, bvh.cu:42-144), 2 = wavefront: a visiting order planned once per build, levels inside
+ * blocks of 1024 sorted positions in shared memory, counters only above the blocks.  Same boxes bit for bit. */
+WP_B200_API void wp_b200_set_refit_mode(int mode);
+WP_B200_API int wp_b200_get_refit_mode(void);
+
 /* in-place LBVH rebuild of a mesh's tree from the current vertices (the reference only offers this
  * for wp.Bvh, bvh.cu:819-843; here a Mesh gets it too): no allocation, same buffers. 1 ok / 0 error */
 WP_B200_API int wp_b200_mesh_rebuild_device(uint64_t id);

@@ -13,7 +13,7 @@ for n in [int(a) for a in sys.argv[1:]] or [810, 2237, 4473, 7072]:
     T = len(I) // 3
     pts = wp.array(P, dtype=wp.vec3); idx = wp.array(I, dtype=wp.int32)
     core.wp_cuda_context_synchronize(None)
-    t0 = time.perf_counter(); m = wp.Mesh(pts, idx); core.wp_cuda_context_synchronize(None); ctor = 1e3 * (time.perf_counter() - t0)
+    t0 = time.perf_counter(); m = wp.Mesh(pts, idx, morton_bits=int(os.environ.get('PROBE_BITS', '30'))); core.wp_cuda_context_synchronize(None); ctor = 1e3 * (time.perf_counter() - t0)
     fn = core.wp_b200_mesh_rebuild_device
     b = statistics.median([event_ms(core, lambda: fn(m.id), stream) for _ in range(5)])
     r = statistics.median([event_ms(core, m.refit, stream) for _ in range(5)])

@@ -304,3 +304,74 @@ def test_morton63_removes_duplicate_keys_on_10m_heightfield(wp):
     k30 = t30["keys"]
     assert (k30[1:] == k30[:-1]).mean() > 0.6 and t30["height"] > t["height"]  # 30-bit keys: long runs, deeper tree
     assert np.array_equal(np.sort(t["primitive_indices"]), np.arange(len(I) // 3))
+
+
+# ------------------------------------------------------------------------------------------------
+# refit variants: atomic arrival counters vs the planned wavefront (levels in shared memory)
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture
+def refit_mode(wp):
+    from warp_b200 import _lib
+
+    core = _lib.core()
+
+    def set_mode(mode):
+        core.wp_b200_set_refit_mode(mode)
+
+    yield set_mode
+    core.wp_b200_set_refit_mode(0)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("leaf", [1, 4, 8])
+def test_refit_variants_mesh(wp, oracle_mod, refit_mode, mode, leaf):
+    """Both refit variants give the oracle's boxes on every visible node, refit after refit (the counters are
+    never cleared), and after an in-place rebuild (the wavefront plan is rebuilt)."""
+    refit_mode(mode)
+    P, I = mg.noisy_sphere(5, 0.02, 11)  # 20 480 triangles = 20 wavefront blocks
+    pts = wp.array(P, dtype=wp.vec3)
+    m = wp.Mesh(pts, wp.array(I, dtype=wp.int32), bvh_leaf_size=leaf)
+    want = oracle_mod.mesh_lbvh_build(P, I, leaf)
+    for k in range(3):
+        _refit_and_compare(wp, oracle_mod, m, pts, mg.renoise_sphere(P, 0.03 * (k + 1), 20 + k), I, want)
+    P3 = mg.renoise_sphere(P, 0.2, 30)
+    pts.assign(P3)
+    m.rebuild()
+    want = oracle_mod.mesh_lbvh_build(P3, I, leaf)
+    assert_tree_equal(m.download_tree(), want)
+    _refit_and_compare(wp, oracle_mod, m, pts, mg.renoise_sphere(P, 0.05, 31), I, want)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_refit_variants_deep_grouped_and_tiny(wp, oracle_mod, refit_mode, mode):
+    refit_mode(mode)
+    rng = np.random.default_rng(5)
+    # coincident boxes: depth-rule leaves with hundreds of items, muted subtrees that are not flagged themselves
+    n = 5000
+    lo = np.zeros((n, 3), np.float32)
+    lo[: n // 2] += 1.0
+    lo[n // 3 : n // 2, 1] += 2.0
+    hi = lo + 0.5
+    cases = [(lo, hi, None, 1), (lo, hi, None, 4)]
+    # grouped tree, items of a group scattered; tiny trees (root is a packed leaf / a single block)
+    glo, ghi = random_boxes(7000, seed=6)
+    cases.append((glo, ghi, rng.integers(0, 9, 7000).astype(np.int32), 4))
+    for m_ in (1, 2, 3, 5, 9):
+        tlo, thi = random_boxes(m_, seed=m_)
+        cases.append((tlo, thi, None, 4))
+    for lo, hi, groups, leaf in cases:
+        lo_d, hi_d = wp.array(lo, dtype=wp.vec3), wp.array(hi, dtype=wp.vec3)
+        b = wp.Bvh(lo_d, hi_d, leaf_size=leaf, groups=None if groups is None else wp.array(groups, dtype=wp.int32))
+        want = oracle_mod.lbvh_build(lo, hi, leaf, groups=groups)
+        for k in range(2):
+            d = rng.standard_normal(lo.shape).astype(np.float32) * np.float32(0.3)
+            lo2, hi2 = (lo + d).astype(np.float32), (hi + d + np.float32(0.1 * k)).astype(np.float32)
+            lo_d.assign(lo2), hi_d.assign(hi2)
+            b.refit()
+            oracle_mod.lbvh_refit(want, lo2, hi2)
+            got = b.download_tree()
+            vis = visible_nodes(want)
+            for name in ("node_lowers", "node_uppers"):
+                assert np.array_equal(got[name]["ib"], want[name]["ib"])
+                for f in "xyz":
+                    assert np.array_equal(got[name][f][vis], want[name][f][vis]), (len(lo), leaf, name, f)

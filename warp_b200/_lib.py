@@ -119,6 +119,8 @@ SIGNATURES = {
     "wp_b200_mesh_query_aabb_count": (_i, [_u64, _vp, _vp, _i64, _vp]),
     "wp_b200_mesh_query_aabb_fill": (_i, [_u64, _vp, _vp, _i64, _vp, _vp]),
     "wp_b200_exclusive_scan_i32": (_i, [_vp, _vp, _i64]),
+    "wp_b200_set_refit_mode": (None, [_i]),
+    "wp_b200_get_refit_mode": (_i, []),
     "wp_b200_mesh_rebuild_device": (_i, [_u64]),
     "wp_b200_bvh_info": (_i, [_u64, ctypes.POINTER(bvh_info_t)]),
     "wp_b200_bvh_sync_reference_layout": (_i, [_u64]),

@@ -564,6 +564,9 @@ int wp_mesh_refit_device(uint64_t id)
     return 1;
 }
 
+void wp_b200_set_refit_mode(int mode) { g_wb_refit_mode = (mode == 1 || mode == 2) ? mode : 0; }
+int wp_b200_get_refit_mode(void) { return g_wb_refit_mode; }
+
 int wp_b200_mesh_rebuild_device(uint64_t id)
 {
     MeshState* m = nullptr;

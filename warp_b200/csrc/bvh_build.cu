@@ -714,7 +714,8 @@ template <class Src, class KeyT, bool GROUPED> const char* build_impl(BvhState& 
     // K4a leaves, K4b chunked bottom-up merge
     k_leaves<Src, KeyT, GROUPED><<<wb_div_up(n, BT), BT, 0, stream>>>(src, n, keys, s.prim, s.pairs, s.pos_parent, s.tris);
     {
-        const MergeArgs<KeyT> ma { n, s.leaf_size, keys, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters, s.header };
+        const MergeArgs<KeyT> ma { n, s.leaf_size, keys, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters, s.header, s.heights };
+        s.plan_valid = false;
         k_merge<false, KeyT, GROUPED><<<wb_div_up(n, BP), TBM, 0, stream>>>(ma);
     }
     // K5/K6 depth rule (early-out unless the tree is at least 32 levels deep)
@@ -786,7 +787,11 @@ const char* wb_alloc_tree(BvhState& s, cudaStream_t stream)
                  o_keys = take(kb * n), o_keys_alt = take(kb * n), o_prim = take(4 * n), o_prim_alt = take(4 * n),
                  o_pairs = take(sizeof(NodeRec) * 2 * ni), o_parent = take(4 * ni), o_pos = take(4 * n),
                  o_counters = take(4 * ni), o_tris = take(s.is_mesh ? sizeof(float4) * 3 * n : 0),
-                 o_status = take(sizeof(uint32_t) * 256 * kb * (size_t)s.num_tiles);
+                 o_status = take(sizeof(uint32_t) * 256 * kb * (size_t)s.num_tiles), o_heights = take(2 * ni),
+                 o_pkeys = take(4 * ni), o_pnodes = take(4 * ni), o_pdst = take(4 * ni),
+                 o_pbegin = take(4 * (size_t)wb_div_up((long long)n, WB_WAVE_BP)),
+                 o_pend = take(4 * (size_t)wb_div_up((long long)n, WB_WAVE_BP)), o_uflags = take(n), o_ptop = take(4 * n),
+                 o_pntop = take(4);
     s.arena_bytes = off;
     s.arena_async = pool_ready(s.device);
     if (s.arena_async)
@@ -799,6 +804,10 @@ const char* wb_alloc_tree(BvhState& s, cudaStream_t stream)
     s.prim = (int*)(b + o_prim), s.prim_alt = (int*)(b + o_prim_alt), s.pairs = (NodeRec*)(b + o_pairs);
     s.parent_int = (int*)(b + o_parent), s.pos_parent = (int*)(b + o_pos), s.counters = (unsigned*)(b + o_counters);
     s.tris = s.is_mesh ? (float4*)(b + o_tris) : nullptr, s.tile_status = (uint32_t*)(b + o_status);
+    s.heights = (uint16_t*)(b + o_heights), s.plan_keys = (uint32_t*)(b + o_pkeys), s.plan_nodes = (int*)(b + o_pnodes);
+    s.plan_dst = (uint32_t*)(b + o_pdst), s.plan_begin = (int*)(b + o_pbegin), s.plan_end = (int*)(b + o_pend);
+    s.unit_flags = (uint8_t*)(b + o_uflags), s.plan_top = (uint32_t*)(b + o_ptop), s.plan_ntop = (int*)(b + o_pntop);
+    s.plan_valid = false;
     // header, tickets, histograms start from zero (one small memset: they are adjacent)
     WB_CUDA_TRY(cudaMemsetAsync(s.arena, 0, o_partials, stream));
     return nullptr;
@@ -872,6 +881,151 @@ const char* wb_refit_merge(BvhState& s, cudaStream_t stream)
         k_merge<true, uint64_t, false><<<grid, TBM, 0, stream>>>(ma);  // the static-tree replay never consults groups
     }
     WB_CUDA_TRY(cudaGetLastError());
+    return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Refit plan (consumed by k_refit_wave, bvh_refit.cu).  The tree is static between builds, so the order in which
+// a refit may visit the nodes can be fixed once: every visible internal node whose range lies inside one block of
+// WB_WAVE_BP sorted positions gets the key  block << 12 | height  and the nodes are sorted by it (same onesweep) --
+// a block then walks its own nodes level by level with __syncthreads() instead of atomic arrival counters.  Nodes
+// that span blocks (key TOP) are left to the global counters; packed leaves and muted nodes (key SKIP) need nothing.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// the leaf flag of internal node n+s lives in its record inside the parent's pair (the root's in the header)
+__device__ __forceinline__ bool plan_flagged_leaf(const NodeRec* __restrict__ pairs, const int* __restrict__ parent_int,
+                                                  const TreeHeader* __restrict__ hdr, int n, int s)
+{
+    const int p = __ldg(parent_int + s);
+    if (p == WB_NO_PARENT)
+        return (hdr->root_ref & WB_LEAF) != 0u;
+    const int ps = p - n;
+    return (pairs[2 * (size_t)ps + ((int)pairs[2 * (size_t)s + 1].aux == ps ? 0 : 1)].ref & WB_LEAF) != 0u;
+}
+
+__global__ void __launch_bounds__(BT)
+k_plan_keys(int n, const NodeRec* __restrict__ pairs, const int* __restrict__ parent_int, const TreeHeader* __restrict__ hdr,
+            const uint16_t* __restrict__ heights, uint32_t* __restrict__ keys, uint32_t* __restrict__ ghist)
+{
+    __shared__ uint32_t h[4 * 256];
+    for (int k = threadIdx.x; k < 4 * 256; k += BT)
+        h[k] = 0;
+    __syncthreads();
+    const int m = n - 1;
+    const int stride = gridDim.x * BT;
+    const int iters = (m + stride - 1) / stride;
+    for (int it = 0; it < iters; ++it) {
+        const int s = it * stride + blockIdx.x * BT + threadIdx.x;
+        const bool valid = s < m;
+        uint32_t key = 0;
+        if (valid) {
+            const int l = (int)pairs[2 * (size_t)s].aux, r = (int)pairs[2 * (size_t)s + 1].aux;
+            // packed leaves and everything below a size leaf carry the flag themselves; below a DEPTH-rule leaf
+            // (hdr->deep, bvh.cu:419-441) only the topmost node is flagged, so look for a flagged ancestor
+            bool leaf = plan_flagged_leaf(pairs, parent_int, hdr, n, s);
+            if (!leaf && hdr->deep) {
+                for (int q = __ldg(parent_int + s); q != WB_NO_PARENT; q = __ldg(parent_int + (q - n)))
+                    if (plan_flagged_leaf(pairs, parent_int, hdr, n, q - n)) {
+                        leaf = true;
+                        break;
+                    }
+            }
+            if (leaf)
+                key = WB_PLAN_SKIP;
+            else if (l / WB_WAVE_BP != r / WB_WAVE_BP)
+                key = WB_PLAN_TOP;
+            else
+                key = ((uint32_t)(l / WB_WAVE_BP) << WB_PLAN_HEIGHT_BITS) | min((uint32_t)__ldg(heights + s), (1u << WB_PLAN_HEIGHT_BITS) - 1u);
+            keys[s] = key;
+        }
+#pragma unroll
+        for (int pass = 0; pass < 4; ++pass)
+            hist_add_coherent(h + 256 * pass, (key >> (8 * pass)) & 255u, valid);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 4 * 256; k += BT)
+        if (h[k])
+            atomicAdd(&ghist[k], h[k]);
+}
+
+// after the sort: where each entry's box goes, and the [begin, end) run of every block
+__global__ void __launch_bounds__(BT)
+k_plan_finish(int n, const uint32_t* __restrict__ keys, const int* __restrict__ nodes, const NodeRec* __restrict__ pairs,
+              const int* __restrict__ parent_int, uint32_t* __restrict__ dst, int* __restrict__ begin, int* __restrict__ end,
+              uint32_t* __restrict__ top, int* __restrict__ ntop)
+{
+    const int i = blockIdx.x * BT + threadIdx.x;
+    const int m = n - 1;
+    if (i >= m)
+        return;
+    const uint32_t key = keys[i];
+    if (key >= WB_PLAN_TOP)
+        return;
+    const int s = nodes[i];
+    const int p = __ldg(parent_int + s);
+    if (p == WB_NO_PARENT) {
+        dst[i] = WB_PLAN_DST_ROOT;
+    } else {
+        const int ps = p - n;
+        const int side = ((int)pairs[2 * (size_t)s + 1].aux == ps) ? 0 : 1;
+        const int pl = (int)pairs[2 * (size_t)ps].aux, pr = (int)pairs[2 * (size_t)ps + 1].aux;
+        const bool spans = pl / WB_WAVE_BP != pr / WB_WAVE_BP;
+        dst[i] = (uint32_t)(2 * ps + side) | (spans ? 0x80000000u : 0u);
+        if (spans)
+            top[atomicAdd(ntop, 1)] = (uint32_t)(2 * ps + side);
+    }
+    const uint32_t b = key >> WB_PLAN_HEIGHT_BITS;
+    if (i == 0 || (keys[i - 1] >> WB_PLAN_HEIGHT_BITS) != b)
+        begin[b] = i;
+    const uint32_t next = (i + 1 < m) ? keys[i + 1] : WB_PLAN_SKIP;
+    if (next >= WB_PLAN_TOP || (next >> WB_PLAN_HEIGHT_BITS) != b)
+        end[b] = i + 1;
+}
+
+// visible leaves whose parent spans blocks announce themselves on the global counters
+__global__ void __launch_bounds__(BT)
+k_plan_units(int n, const int* __restrict__ pos_parent, const NodeRec* __restrict__ pairs, uint8_t* __restrict__ flags,
+             uint32_t* __restrict__ top, int* __restrict__ ntop)
+{
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= n)
+        return;
+    const int p = __ldg(pos_parent + i);
+    uint8_t f = 0;
+    if (p >= 0) {
+        const int ps = p - n;
+        f = ((int)pairs[2 * (size_t)ps].aux / WB_WAVE_BP != (int)pairs[2 * (size_t)ps + 1].aux / WB_WAVE_BP) ? 1 : 0;
+        if (f)
+            top[atomicAdd(ntop, 1)] = (uint32_t)(2 * ps + (i <= ps ? 0 : 1));
+    }
+    flags[i] = f;
+}
+
+}  // namespace
+
+const char* wb_refit_plan(BvhState& s, cudaStream_t stream)
+{
+    const int n = s.n, m = n - 1;
+    if (m < 1)
+        return nullptr;
+    const int tiles = wb_div_up(m, rs_tile_for(m));
+    const int nblocks = wb_div_up(n, WB_WAVE_BP);
+    WB_CUDA_TRY(cudaMemsetAsync(s.ghist, 0, sizeof(uint32_t) * 8 * 256, stream));
+    WB_CUDA_TRY(cudaMemsetAsync(s.tickets, 0, sizeof(unsigned) * 16, stream));
+    WB_CUDA_TRY(cudaMemsetAsync(s.tile_status, 0, sizeof(uint32_t) * 256 * 4 * (size_t)tiles, stream));
+    WB_CUDA_TRY(cudaMemsetAsync(s.plan_begin, 0, sizeof(int) * (size_t)nblocks, stream));
+    WB_CUDA_TRY(cudaMemsetAsync(s.plan_end, 0, sizeof(int) * (size_t)nblocks, stream));
+    WB_CUDA_TRY(cudaMemsetAsync(s.plan_ntop, 0, sizeof(int), stream));
+    k_plan_keys<<<bounds_grid(m), BT, 0, stream>>>(n, s.pairs, s.parent_int, s.header, s.heights, s.plan_keys, s.ghist);
+    // keys_alt / prim_alt are build scratch (>= 4 bytes per item), free between builds
+    onesweep_sort<uint32_t>(s.plan_keys, (uint32_t*)s.keys_alt, s.plan_nodes, s.prim_alt, m, s.ghist, s.tile_status, s.tickets,
+                            stream);
+    k_plan_finish<<<wb_div_up(m, BT), BT, 0, stream>>>(n, s.plan_keys, s.plan_nodes, s.pairs, s.parent_int, s.plan_dst,
+                                                       s.plan_begin, s.plan_end, s.plan_top, s.plan_ntop);
+    k_plan_units<<<wb_div_up(n, BT), BT, 0, stream>>>(n, s.pos_parent, s.pairs, s.unit_flags, s.plan_top, s.plan_ntop);
+    WB_CUDA_TRY(cudaGetLastError());
+    s.plan_valid = true;
     return nullptr;
 }
 

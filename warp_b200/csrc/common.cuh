@@ -62,6 +62,13 @@ struct TreeView {
 
 #define WB_TRI_SLIVER 1u
 
+// wavefront refit (bvh_refit.cu): positions per block, key layout of the plan
+#define WB_WAVE_BP 1024
+#define WB_PLAN_HEIGHT_BITS 12
+#define WB_PLAN_TOP 0xFFFFFFFEu
+#define WB_PLAN_SKIP 0xFFFFFFFFu
+#define WB_PLAN_DST_ROOT 0xFFFFFFFFu
+
 __host__ __device__ inline int wb_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 #ifdef __CUDACC__

@@ -30,6 +30,7 @@ template <class KeyT> struct MergeArgs {
     int* pos_parent;
     unsigned* counters;
     TreeHeader* hdr;
+    uint16_t* heights;  // builder: height of every internal node, for the refit plan
 };
 
 __device__ __forceinline__ int wb_clz_key(uint32_t x) { return __clz((int)x); }
@@ -182,6 +183,7 @@ __device__ __forceinline__ void wb_absorb(const MergeArgs<KeyT>& a, const K& kv,
                 a.pos_parent[s + 1] = a.n + s;
         }
         xh = max(xh, other_h) + 1u;
+        a.heights[s] = (uint16_t)min(xh, 0xffffu);
     }
     lo = wb_min3(lo, make_float3(s0.x, s0.y, s0.z));
     hi = wb_max3(hi, make_float3(s1.x, s1.y, s1.z));

@@ -33,6 +33,19 @@ struct BvhState {
     unsigned* counters = nullptr; // n-1 arrival counters (build: count | height<<8; refit: parity)
     float4* tris = nullptr;       // 3n packed triangles in sorted order (mesh only)
     TreeHeader* header = nullptr;
+    uint16_t* heights = nullptr;  // n-1: height of internal node n+s (original leaves = 0), capped at 0xffff
+
+    // refit plan (bvh_refit.cu), built lazily by the first refit after a build: the visible internal nodes whose
+    // range lies inside one block of WB_WAVE_BP sorted positions, grouped by block and ordered by height
+    bool plan_valid = false;
+    uint32_t* plan_keys = nullptr;   // n-1 sorted keys: block << 12 | height; 0xFFFFFFFE spanning, 0xFFFFFFFF leaf / muted
+    int* plan_nodes = nullptr;       // n-1: internal slot s of each entry
+    uint32_t* plan_dst = nullptr;    // n-1: record the entry's box goes to (2 * parent slot + side; bit 31: parent spans blocks)
+    int* plan_begin = nullptr;       // per block: its entries are [plan_begin[b], plan_end[b])
+    int* plan_end = nullptr;
+    uint8_t* unit_flags = nullptr;   // n: 1 where the visible leaf starting at the position has a block-spanning parent
+    uint32_t* plan_top = nullptr;    // <= n entries (2 * parent slot + side): the nodes / leaves that announce themselves
+    int* plan_ntop = nullptr;        //   on the global counters, and their number (device side)
 
     // build workspace, kept so rebuild() allocates nothing (bvh.cu:790-803 semantics)
     void* keys_alt = nullptr;
@@ -67,6 +80,8 @@ struct MeshState {
 // build / refit / export drivers (bvh_build.cu, bvh_refit.cu); all enqueue on `stream`
 const char* wb_build(BvhState& s, cudaStream_t stream);
 const char* wb_refit(BvhState& s, cudaStream_t stream);
+extern int g_wb_refit_mode;  // 0 auto, 1 atomic counters, 2 wavefront
+const char* wb_refit_plan(BvhState& s, cudaStream_t stream);  // (bvh_build.cu: shares the radix sort)
 const char* wb_refit_merge(BvhState& s, cudaStream_t stream);  // bottom-up pass of the refit (bvh_build.cu)
 const char* wb_export_reference_layout(BvhState& s, cudaStream_t stream);
 const char* wb_alloc_tree(BvhState& s, cudaStream_t stream);
