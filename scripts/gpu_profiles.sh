@@ -12,7 +12,9 @@ echo "query exit $?"
 export PROF_NQ=$((1<<20))
 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'k_scene|k_morton|k_onesweep|k_leaves|k_merge|k_refit|k_deep|k_query_ray' -s 12 -c 16 -f -o gpurun_out/${R}_build_refit python scripts/prof_driver.py > gpurun_out/${R}_prof_b.log 2>&1
 echo "build exit $?"
-for f in ${R}_query_point ${R}_build_refit; do
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_refit|k_plan' -s 0 -c 12 -f -o gpurun_out/${R}_refit_wave python scripts/prof_refit_driver.py > gpurun_out/${R}_prof_r.log 2>&1
+echo "refit-wave exit $?"
+for f in ${R}_query_point ${R}_build_refit ${R}_refit_wave; do
   ncu -i gpurun_out/$f.ncu-rep --page raw --csv > gpurun_out/$f.raw.csv 2>/dev/null
 done
 ls -la gpurun_out | tail -12

@@ -94,5 +94,9 @@ table(os.path.join(G, f"{R}_build_refit.raw.csv"), "Build / refit / ray kernels 
       "command: `ncu --set full --clock-control none --import-source on -k regex:'k_scene|k_morton|k_onesweep|k_leaves|k_merge|k_refit|k_deep|k_query_ray' "
       "-s 12 -c 16 python scripts/prof_driver.py`.")
 
+table(os.path.join(G, f"{R}_refit_wave.raw.csv"), "Wavefront refit + its one-time plan at C4 size (3 998 792-triangle cloth)",
+      "command: `ncu --set full --clock-control none --import-source on -k regex:'k_refit|k_plan' -s 0 -c 12 python scripts/prof_refit_driver.py`. "
+      "`k_plan_*` (+ 4 sort passes, not captured here) run once per build; a refit is `k_refit_leaves` + `k_refit_levels` + `k_refit_climb`.")
+
 open(os.path.join(OUT, f"{R}_summary.md"), "w").write(f"# ncu summaries, round {R}\n\n" + "\n".join(lines) + "\n")
 print("wrote", os.path.join(OUT, f"{R}_summary.md"))

@@ -31,6 +31,11 @@ from .queries import (  # noqa: F401
     QUERY_ORDER_AUTO,
     QUERY_ORDER_INPUT,
     QUERY_ORDER_MORTON,
+    REFIT_ATOMIC,
+    REFIT_AUTO,
+    REFIT_WAVEFRONT,
+    get_refit_mode,
+    set_refit_mode,
     MeshQueryPoint,
     get_query_order,
     get_ray_order,

@@ -7,7 +7,9 @@ allocation -- the reason the reference has ``wp_bvh_rebuild_device``, ``bvh.cu:8
 DEVICE arrays with a preallocated ``out=``.  A per-step collision loop (refit + queries, BASELINE config 4) becomes
 one graph launch per frame.  Not capturable: constructors (they allocate), host-array queries (they synchronise),
 and the CSR hit-list queries (the hit count comes back to the host between the count and the fill pass).
-Run the loop body once before capturing so that grow-only scratch (query ordering) is already allocated.
+Run the loop body once before capturing so that grow-only scratch (query ordering) is already allocated and the
+refit plan of a large tree exists.  A graph that contains ``refit()`` of a tree with 2**21 items or more replays the
+plan of the build it was captured after: re-capture it after a ``rebuild()`` that ran outside the graph.
 """
 
 from __future__ import annotations

@@ -267,3 +267,18 @@ def set_ray_order(mode: int) -> None:
 
 def get_ray_order() -> int:
     return int(_lib.core().wp_b200_get_ray_order())
+
+
+REFIT_AUTO, REFIT_ATOMIC, REFIT_WAVEFRONT = 0, 1, 2
+
+
+def set_refit_mode(mode: int) -> None:
+    """How ``refit()`` walks the tree: ``REFIT_ATOMIC`` = one atomic arrival counter per internal node (the reference's
+    scheme, ``bvh.cu:42-144``); ``REFIT_WAVEFRONT`` = a visiting order planned once per build, levels inside blocks of
+    1024 sorted positions in shared memory, counters only above the blocks; ``REFIT_AUTO`` (default) picks the
+    wavefront from 2**21 items up.  The boxes are identical bit for bit."""
+    _lib.core().wp_b200_set_refit_mode(int(mode))
+
+
+def get_refit_mode() -> int:
+    return int(_lib.core().wp_b200_get_refit_mode())
