@@ -95,7 +95,9 @@ __device__ __forceinline__ float wb_get(float3 a, int k) { return k == 0 ? a.x :
 
 // arrival counter update with release (our record stores are visible before the count) and acquire (the
 // sibling's record is visible after it) semantics in ONE instruction: MEMBAR.ALL.GPU + ATOMG + CCTL.IVALL,
-// versus MEMBAR.SC + CCTL.IVALL twice for __threadfence(); atomicAdd(); __threadfence().
+// versus MEMBAR.SC + CCTL.IVALL twice for __threadfence(); atomicAdd(); __threadfence().  (A release-only arrival,
+// legal here because every load after it bypasses L1 or reads static data, measured the same: the fences are not
+// what bounds the climb.)
 __device__ __forceinline__ unsigned wb_arrive(unsigned* counter, unsigned add)
 {
     unsigned old;
