@@ -375,3 +375,28 @@ def test_refit_variants_deep_grouped_and_tiny(wp, oracle_mod, refit_mode, mode):
                 assert np.array_equal(got[name]["ib"], want[name]["ib"])
                 for f in "xyz":
                     assert np.array_equal(got[name][f][vis], want[name][f][vis]), (len(lo), leaf, name, f)
+
+
+@pytest.mark.parametrize("n", [2, 3, 1023, 1024, 1025, 2047, 2048, 2049, 4097, 6144])
+def test_block_boundary_sizes_build_and_refit(wp, oracle_mod, refit_mode, n):
+    """Item counts around the block sizes of the hierarchy kernel (2048) and of the wavefront refit (1024):
+    full tree diff after the build, visible boxes after a refit in both modes."""
+    rng = np.random.default_rng(n)
+    lo, hi = random_boxes(n, seed=n)
+    for leaf in (1, 4):
+        lo_d, hi_d = wp.array(lo, dtype=wp.vec3), wp.array(hi, dtype=wp.vec3)
+        b = wp.Bvh(lo_d, hi_d, leaf_size=leaf)
+        want = oracle_mod.lbvh_build(lo, hi, leaf)
+        assert_tree_equal(b.download_tree(), want)
+        for mode in (1, 2):
+            refit_mode(mode)
+            d = rng.standard_normal(lo.shape).astype(np.float32)
+            lo2, hi2 = (lo + d).astype(np.float32), (hi + d).astype(np.float32)
+            lo_d.assign(lo2), hi_d.assign(hi2)
+            b.refit()
+            oracle_mod.lbvh_refit(want, lo2, hi2)
+            got = b.download_tree()
+            vis = visible_nodes(want)
+            for name in ("node_lowers", "node_uppers"):
+                for f in "xyz":
+                    assert np.array_equal(got[name][f][vis], want[name][f][vis]), (n, leaf, mode, name, f)
