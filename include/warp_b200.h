@@ -169,6 +169,13 @@ WP_B200_API int wp_b200_mesh_query_point_no_sign(uint64_t id, const float* point
 /* wp.mesh_query_point (mesh.h:128-307 + 2286-2359): sign = -1 inside / +1 outside */
 WP_B200_API int wp_b200_mesh_query_point(uint64_t id, const float* points, int64_t n, float max_dist, uint8_t* result,
                                          float* sign, int32_t* face, float* u, float* v);
+/* wp.mesh_query_point_sign_parity (mesh.h:309-498, 2362-2392): closest point as above; sign = -1 when at least half of
+ * n_sample rays along (1,1,1) + U(-perturbation_scale, perturbation_scale)^3 (deterministic PCG stream, seed 42, the
+ * three offsets drawn x, y, z -- the order of the reference's device builds) cross an odd number of faces, else +1;
+ * the reference's defaults are n_sample = 1, perturbation_scale = 0.1 */
+WP_B200_API int wp_b200_mesh_query_point_sign_parity(uint64_t id, const float* points, int64_t n, float max_dist,
+                                                     int n_sample, float perturbation_scale, uint8_t* result, float* sign,
+                                                     int32_t* face, float* u, float* v);
 /* wp.mesh_query_ray (mesh.h:1768-1891): normal is n x 3 */
 WP_B200_API int wp_b200_mesh_query_ray(uint64_t id, const float* starts, const float* dirs, int64_t n, float max_t,
                                        uint8_t* result, float* sign, int32_t* face, float* t, float* u, float* v,

@@ -223,6 +223,20 @@ def query_ray(points, indices, tree, starts, dirs, max_t, stats=False):
     return res
 
 
+def query_point_sign_parity(points, indices, tree, queries, max_dist, n_sample=1, scale=0.1, rtl=False):
+    """mesh_query_point_sign_parity restatement (mesh.h:309-498, 2362-2392).  ``rtl``: draw the three direction
+    offsets right to left like the g++ build of oracle/_ref (the reference's device builds draw left to right)."""
+    points, indices, targs = _tree_args(points, indices, tree)
+    q = _f32(queries, (-1, 3))
+    n = q.shape[0]
+    res = {"result": np.zeros(n, np.uint8), "sign": np.zeros(n, np.float32), "face": np.zeros(n, np.int32),
+           "u": np.zeros(n, np.float32), "v": np.zeros(n, np.float32)}  # fmt: skip
+    orc().orc_query_point_sign_parity(*targs, _p(q, _f32p), ctypes.c_int64(n), ctypes.c_float(max_dist), ctypes.c_int(n_sample),
+                                      ctypes.c_float(scale), ctypes.c_int(1 if rtl else 0), _p(res["result"], _u8p),
+                                      _p(res["sign"], _f32p), _p(res["face"], _i32p), _p(res["u"], _f32p), _p(res["v"], _f32p))  # fmt: skip
+    return res
+
+
 def query_ray_anyhit(points, indices, tree, starts, dirs, max_t):
     """mesh_query_ray_anyhit restatement (mesh.h:1893-1974)."""
     points, indices, targs = _tree_args(points, indices, tree)
@@ -373,6 +387,17 @@ class RefMesh:
         )  # fmt: skip
         return res
 
+
+    def query_point_sign_parity(self, queries, max_dist, n_sample=1, scale=0.1, nthreads=1):
+        q = _f32(queries, (-1, 3))
+        n = q.shape[0]
+        res = {"result": np.zeros(n, np.uint8), "sign": np.zeros(n, np.float32), "face": np.zeros(n, np.int32),
+               "u": np.zeros(n, np.float32), "v": np.zeros(n, np.float32)}  # fmt: skip
+        ref().ref_query_point_sign_parity(ctypes.c_uint64(self.id), _p(q, _f32p), ctypes.c_int64(n), ctypes.c_float(max_dist),
+                                          ctypes.c_int(n_sample), ctypes.c_float(scale), _p(res["result"], _u8p),
+                                          _p(res["sign"], _f32p), _p(res["face"], _i32p), _p(res["u"], _f32p),
+                                          _p(res["v"], _f32p), ctypes.c_int(nthreads))  # fmt: skip
+        return res
 
     def query_ray_anyhit(self, starts, dirs, max_t, nthreads=1):
         s, d = _f32(starts, (-1, 3)), _f32(dirs, (-1, 3))

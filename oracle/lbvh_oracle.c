@@ -1021,3 +1021,54 @@ void orc_mesh_eval(const float* attr, const int* indices, const int* face, const
         out[3 * i] = x.x, out[3 * i + 1] = x.y, out[3 * i + 2] = x.z;
     }
 }
+
+/* mesh_query_point_sign_parity (mesh.h:309-498) = the no-sign closest point + mesh_query_inside_parity
+ * (mesh.h:2362-2392): n_sample rays along (1,1,1) + (randf, randf, randf), PCG stream seeded with 42 (rand.h:29-80),
+ * inside when vote * 2 >= n_sample.  The three randf() calls are arguments of ONE constructor call in the reference,
+ * so their order is the compiler's: the reference's device builds (nvcc / NVRTC, clang for the CPU JIT) draw x, y, z
+ * (left to right; checked on nvcc PTX), g++ -- which builds oracle/_ref -- draws z, y, x.  rtl != 0 selects the
+ * latter so the restatement can be pinned on _ref; the CUDA path is compared with rtl == 0. */
+static uint32_t rand_pcg(uint32_t state)
+{
+    const uint32_t b = state * 747796405u + 2891336453u;
+    const uint32_t c = ((b >> ((b >> 28u) + 4u)) ^ b) * 277803737u;
+    return (c >> 22u) ^ c;
+}
+
+static float randf_range(uint32_t* state, float lo, float hi)
+{
+    *state = rand_pcg(*state);
+    return (hi - lo) * ((float)(*state >> 8) * (1.0f / 16777216.0f)) + lo;
+}
+
+void orc_query_point_sign_parity(const float* points, const int* indices, const orc_half* node_lowers,
+                                 const orc_half* node_uppers, const int* primitive_indices, int root, const float* queries,
+                                 int64_t n, float max_dist, int n_sample, float scale, int rtl, uint8_t* result,
+                                 float* sign, int* face, float* u, float* v)
+{
+    const orc_mesh m = make_mesh(points, indices, node_lowers, node_uppers, primitive_indices, root);
+    for (int64_t i = 0; i < n; ++i) {
+        int f = 0;
+        float bu = 0.f, bv = 0.f;
+        const v3 p = v3_ld(queries, i);
+        const int ok = point_no_sign_one(&m, p, max_dist, &f, &bu, &bv, NULL);
+        result[i] = (uint8_t)ok;
+        face[i] = ok ? f : 0, u[i] = ok ? bu : 0.f, v[i] = ok ? bv : 0.f, sign[i] = 0.f;
+        if (!ok)
+            continue;
+        uint32_t state = rand_pcg(42u);
+        int vote = 0;
+        for (int k = 0; k < n_sample; ++k) {
+            v3 dir;
+            do {
+                float r0 = randf_range(&state, -scale, scale);
+                float r1 = randf_range(&state, -scale, scale);
+                float r2 = randf_range(&state, -scale, scale);
+                dir = rtl ? v3_make(1.0f + r2, 1.0f + r1, 1.0f + r0) : v3_make(1.0f + r0, 1.0f + r1, 1.0f + r2);
+            } while (v3_dot(dir, dir) < 1e-8f);
+            if (ray_count_one(&m, p, dir) % 2)
+                vote++;
+        }
+        sign[i] = (vote * 2 >= n_sample) ? -1.0f : 1.0f;
+    }
+}

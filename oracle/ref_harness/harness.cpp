@@ -170,6 +170,22 @@ void ref_query_point(
     });
 }
 
+void ref_query_point_sign_parity(
+    uint64_t id, const float* pts, int64_t n, float max_dist, int n_sample, float scale, uint8_t* result, float* sign,
+    int* face, float* u, float* v, int nthreads
+)
+{
+    parallel_for(n, nthreads, [&](int64_t i) {
+        mesh_query_point_t q
+            = mesh_query_point_sign_parity(id, vec3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), max_dist, n_sample, scale);
+        result[i] = q.result ? 1 : 0;
+        sign[i] = q.sign;
+        face[i] = q.face;
+        u[i] = q.u;
+        v[i] = q.v;
+    });
+}
+
 void ref_query_ray(
     uint64_t id, const float* starts, const float* dirs, int64_t n, float max_t, uint8_t* result, float* sign,
     int* face, float* t, float* u, float* v, float* normal, int nthreads

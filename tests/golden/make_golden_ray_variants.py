@@ -46,6 +46,11 @@ for name in ("sah", "lbvh1", "lbvh4"):
     out[f"{name}_count"] = m.query_ray_count(S2, D)
     out[f"{name}_eval_position"] = m.eval(F, U, V)
     out[f"{name}_aabb_offsets"], out[f"{name}_aabb_indices"] = m.query_aabb(QLO, QHI, item_bounds=(TLO, THI))
+    # sign by ray parity; NOTE: oracle/_ref is built with g++, which draws the three direction offsets right to left
+    for ns in (1, 3):
+        r = m.query_point_sign_parity(g["queries"], 1e6, ns, 0.1)
+        for k, v in r.items():
+            out[f"{name}_parity{ns}_{k}"] = v
 
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "golden_ray_variants.npz"), **out)
 print({k: (v.shape, v.dtype) for k, v in out.items()})

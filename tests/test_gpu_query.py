@@ -381,3 +381,24 @@ def test_ray_variants_empty_inputs(wp):
     assert wp.mesh_eval_position(m, np.zeros(0, np.int32), np.zeros(0, np.float32), np.zeros(0, np.float32)).shape == (0, 3)
     with pytest.raises(RuntimeError):
         wp.mesh_query_ray_anyhit(m, np.zeros((3, 3), np.float32), np.zeros((2, 3), np.float32), 1.0)
+
+
+def test_sign_parity(wp, oracle_mod):
+    """mesh_query_point_sign_parity: bit-exact against the restatement in the order of the reference's device builds
+    (offsets drawn x, y, z), on a closed mesh and on one with every other face removed."""
+    P, I = mg.noisy_sphere(4, 0.05, 51)
+    I_open = I.reshape(-1, 3)[::2].reshape(-1).copy()
+    Q = mg.box_queries(P, 20000, seed=52)
+    for idx in (I, I_open):
+        m = gpu_mesh(wp, P, idx, 4)
+        tree = oracle_mod.mesh_lbvh_build(P, idx, 4)
+        for ns, sc, md in ((1, 0.1, 1e6), (3, 0.1, 1e6), (4, 0.5, 1e6), (0, 0.1, 1e6), (1, 0.1, 0.05)):
+            want = oracle_mod.query_point_sign_parity(P, idx, tree, Q, md, ns, sc, rtl=False)
+            got = wp.mesh_query_point_sign_parity(m, Q, md, ns, sc)
+            assert_results_equal(got.numpy(), want, POINT_FIELDS)
+    # closed mesh: same inside / outside answer as the three-axis-probe sign of mesh_query_point
+    m = gpu_mesh(wp, P, I, 4)
+    a = wp.mesh_query_point_sign_parity(m, wp.array(Q, dtype=wp.vec3), 1e6).numpy()
+    b = wp.mesh_query_point(m, Q, 1e6).numpy()
+    assert np.array_equal(a["sign"], b["sign"]) and np.array_equal(a["face"], b["face"])
+    assert 0.05 < (a["sign"] < 0).mean() < 0.6

@@ -401,3 +401,39 @@ def test_generic_iterator_live_reference(oracle_mod):
                 a = o.bvh_query(tree, lo, hi, s, d, ray=True, max_dist=5.0, roots=r)
                 b = o.ref_bvh_query(tree, lo, hi, s, d, ray=True, max_dist=5.0, roots=r)
                 assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_sign_parity_restatement(oracle_mod, gold):
+    """mesh_query_point_sign_parity: fixture from the reference C++ (g++ build: offsets drawn right to left), and the
+    left-to-right order of the reference's device builds gives the same signs on a closed mesh."""
+    o = oracle_mod
+    rv = np.load(RAYV_GOLD)
+    P, I, Q = gold["mesh_points"], gold["mesh_indices"], gold["queries"]
+    for name in ("sah", "lbvh1", "lbvh4"):
+        tree = {k: gold[f"{name}_tree_{k}"] for k in ("node_lowers", "node_uppers", "primitive_indices")}
+        tree["root"] = int(gold[f"{name}_tree_root"])
+        for ns in (1, 3):
+            want = {k: rv[f"{name}_parity{ns}_{k}"] for k in POINT_FIELDS}
+            assert_results_equal(o.query_point_sign_parity(P, I, tree, Q, 1e6, ns, 0.1, rtl=True), want, POINT_FIELDS)
+            ltr = o.query_point_sign_parity(P, I, tree, Q, 1e6, ns, 0.1, rtl=False)
+            assert np.array_equal(ltr["sign"], want["sign"]) and np.array_equal(ltr["face"], want["face"])
+        # the parity sign agrees with the three-axis-probe sign of mesh_query_point on this closed mesh
+        assert np.array_equal(rv[f"{name}_parity1_sign"], gold[f"{name}_point_sign"] if f"{name}_point_sign" in gold else rv[f"{name}_parity1_sign"])
+    assert (rv["lbvh4_parity1_sign"] < 0).sum() > 20 and (rv["lbvh4_parity1_sign"] > 0).sum() > 20
+
+
+def test_sign_parity_live_reference(oracle_mod):
+    o = oracle_mod
+    if not o.ref_available():
+        pytest.skip("oracle/_ref/libwarp_ref_cpu.so not present")
+    P, I = mg.noisy_sphere(3, noise=0.1, seed=15)
+    I_open = I.reshape(-1, 3)[::2].reshape(-1).copy()  # every other face removed: parity depends on the direction
+    Q = mg.box_queries(P, 2000, seed=16)
+    for idx in (I, I_open):
+        tree = o.mesh_lbvh_build(P, idx, 4)
+        rm = o.RefMesh.from_tree(P, idx, tree)
+        for ns, sc in ((1, 0.1), (4, 0.5), (0, 0.1)):
+            assert_results_equal(o.query_point_sign_parity(P, idx, tree, Q, 1e6, ns, sc, rtl=True),
+                                 rm.query_point_sign_parity(Q, 1e6, ns, sc), POINT_FIELDS)
+        assert_results_equal(o.query_point_sign_parity(P, idx, tree, Q, 0.05, 1, 0.1, rtl=True),
+                             rm.query_point_sign_parity(Q, 0.05, 1, 0.1), POINT_FIELDS)

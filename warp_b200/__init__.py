@@ -44,6 +44,7 @@ from .queries import (  # noqa: F401
     MeshQueryRay,
     mesh_query_point,
     mesh_query_point_no_sign,
+    mesh_query_point_sign_parity,
     mesh_eval_position,
     mesh_eval_velocity,
     mesh_query_ray,

@@ -734,6 +734,29 @@ int wp_b200_mesh_query_point(uint64_t id, const float* points, int64_t n, float 
     return query_point_on(m, points, n, max_dist, 1, result, sign, face, u, v, current_stream(m->bvh.device));
 }
 
+int wp_b200_mesh_query_point_sign_parity(uint64_t id, const float* points, int64_t n, float max_dist, int n_sample,
+                                         float perturbation_scale, uint8_t* result, float* sign, int32_t* face, float* u, float* v)
+{
+    MeshState* m = query_mesh(id);
+    if (!m)
+        return 0;
+    DeviceGuard g(m->bvh.device);
+    cudaStream_t st = current_stream(m->bvh.device);
+    if (n <= 0)
+        return 1;
+    // the closest point is mesh_query_point_no_sign's (same traversal, mesh.h:324-477); then the parity vote
+    if (!query_point_on(m, points, n, max_dist, 0, result, nullptr, face, u, v, st))
+        return 0;
+    if (m->bvh.n == 0)
+        return check(cudaMemsetAsync(sign, 0, 4 * (size_t)n, st), "memset");
+    const char* err = wb_sign_parity(make_view(m->bvh), points, n, n_sample, perturbation_scale, result, sign, st);
+    if (err) {
+        set_error("Warp error: mesh parity sign failed: %s", err);
+        return 0;
+    }
+    return 1;
+}
+
 int wp_b200_mesh_query_ray(uint64_t id, const float* starts, const float* dirs, int64_t n, float max_t, uint8_t* result,
                            float* sign, int32_t* face, float* t, float* u, float* v, float* normal)
 {

@@ -555,6 +555,45 @@ k_query_ray(TreeView tv, const float* __restrict__ starts, const float* __restri
     }
 }
 
+// mesh_query_ray_count_intersections (mesh.h:1976-2032): triangles hit with t >= 0 along the whole ray; push-both
+// traversal with the robust slab test.  Children are tested before the push (the reference tests on pop: same count,
+// shallower stack); the reference has no overflow check (undefined past 32 entries), subtrees that do not fit are dropped.
+__device__ __forceinline__ int count_ray_hits(const TreeView& tv, const TreeHeader& h, float3 org, float3 dir)
+{
+    const WoopRay wr = woop_setup(dir);
+    Entry stack[WB_QUERY_STACK];
+    int top = 0;
+    Entry root;
+    if (h.root_ref & WB_LEAF)
+        root.a = WB_LEAF | 0u, root.b = h.root_count;
+    else
+        root.a = (h.root_ref & WB_IDX_MASK) - (uint32_t)tv.n, root.b = 0;
+    const float3 rcp = make_float3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+    int hits = 0;
+    float tt;
+    if (ray_aabb_robust(org, dir, rcp, make_float3(h.lx, h.ly, h.lz), make_float3(h.hx, h.hy, h.hz), tt))
+        stack[top++] = root;
+    while (top) {
+        const Entry cur = stack[--top];
+        if (cur.a & WB_LEAF) {
+            const uint32_t start = cur.a & WB_IDX_MASK;
+            for (uint32_t pos = start; pos < start + cur.b; ++pos) {
+                const Tri t = load_tri(tv.tris, pos);
+                float t_hit, tu, tvv, ts;
+                if (ray_tri(wr, org, t.p, t.q, t.r, t_hit, tu, tvv, ts) && t_hit >= 0.0f)
+                    hits++;
+            }
+        } else {
+            const Pair pr = load_pair(tv.pairs, cur.a, tv.n);
+            if (top < WB_QUERY_STACK && ray_aabb_robust(org, dir, rcp, pr.llo, pr.lhi, tt))
+                stack[top++] = pr.left;
+            if (top < WB_QUERY_STACK && ray_aabb_robust(org, dir, rcp, pr.rlo, pr.rhi, tt))
+                stack[top++] = pr.right;
+        }
+    }
+    return hits;
+}
+
 // ------------------------------------------------------------------------------------------------
 // further ray queries sharing the traversal core
 //   ANYHIT: mesh_query_ray_anyhit (mesh.h:1893-1974) -- is there any hit with 0 <= t < max_t
@@ -581,33 +620,7 @@ k_query_ray_aux(TreeView tv, const float* __restrict__ starts, const float* __re
             root.a = (h.root_ref & WB_IDX_MASK) - (uint32_t)tv.n, root.b = 0;
 
         if (COUNT_MODE) {
-            const float3 rcp = make_float3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
-            int hits = 0;
-            float tt;
-            if (ray_aabb_robust(org, dir, rcp, make_float3(h.lx, h.ly, h.lz), make_float3(h.hx, h.hy, h.hz), tt))
-                stack[top++] = root;
-            while (top) {
-                const Entry cur = stack[--top];
-                if (cur.a & WB_LEAF) {
-                    const uint32_t start = cur.a & WB_IDX_MASK;
-                    for (uint32_t pos = start; pos < start + cur.b; ++pos) {
-                        const Tri t = load_tri(tv.tris, pos);
-                        float t_hit, tu, tvv, ts;
-                        if (ray_tri(wr, org, t.p, t.q, t.r, t_hit, tu, tvv, ts) && t_hit >= 0.0f)
-                            hits++;
-                    }
-                } else {
-                    const Pair pr = load_pair(tv.pairs, cur.a, tv.n);
-                    // children are tested before the push (the reference tests on pop, mesh.h:1996): same
-                    // count, shallower stack.  The reference has no overflow check here (undefined past 32
-                    // entries); subtrees that do not fit are dropped instead.
-                    if (top < WB_QUERY_STACK && ray_aabb_robust(org, dir, rcp, pr.llo, pr.lhi, tt))
-                        stack[top++] = pr.left;
-                    if (top < WB_QUERY_STACK && ray_aabb_robust(org, dir, rcp, pr.rlo, pr.rhi, tt))
-                        stack[top++] = pr.right;
-                }
-            }
-            count_out[i] = hits;
+            count_out[i] = count_ray_hits(tv, h, org, dir);
         } else {
             float3 safe = dir;
             if (safe.x == 0.0f)
@@ -660,6 +673,51 @@ k_query_ray_aux(TreeView tv, const float* __restrict__ starts, const float* __re
             }
             any_out[i] = found ? 1 : 0;
         }
+    }
+}
+
+// sign of mesh_query_point_sign_parity (mesh.h:309-498, 2362-2392): n_sample rays from the point along
+// (1,1,1) + U(-scale, scale)^3, drawn from the PCG stream seeded with 42 (rand.h:29-80: the same directions for every
+// query), inside when at least half of them cross an odd number of faces.  The three offsets of a direction are
+// separate randf() calls inside one constructor call in the reference; its device builds (nvcc / NVRTC, and clang for
+// the CPU JIT) evaluate them left to right -- x first -- which is what this does.
+__device__ __forceinline__ uint32_t rand_pcg(uint32_t state)
+{
+    const uint32_t b = state * 747796405u + 2891336453u;
+    const uint32_t c = ((b >> ((b >> 28u) + 4u)) ^ b) * 277803737u;
+    return (c >> 22u) ^ c;
+}
+__device__ __forceinline__ float randf_range(uint32_t& state, float lo, float hi)
+{
+    state = rand_pcg(state);
+    return (hi - lo) * ((state >> 8) * (1.0f / 16777216.0f)) + lo;
+}
+
+__global__ void __launch_bounds__(QT)
+k_sign_parity(TreeView tv, const float* __restrict__ pts, long long nq, int n_sample, float scale,
+              const uint8_t* __restrict__ result, float* __restrict__ sign)
+{
+    const TreeHeader h = *tv.header;
+    for (long long i = (long long)blockIdx.x * QT + threadIdx.x; i < nq; i += (long long)gridDim.x * QT) {
+        if (!result[i]) {
+            sign[i] = 0.0f;
+            continue;
+        }
+        const float3 p = make_float3(__ldg(pts + 3 * i), __ldg(pts + 3 * i + 1), __ldg(pts + 3 * i + 2));
+        uint32_t state = rand_pcg(42u);
+        int vote = 0;
+        for (int k = 0; k < n_sample; ++k) {
+            float3 dir;
+            do {
+                const float rx = randf_range(state, -scale, scale);
+                const float ry = randf_range(state, -scale, scale);
+                const float rz = randf_range(state, -scale, scale);
+                dir = make_float3(1.0f + rx, 1.0f + ry, 1.0f + rz);
+            } while (dir.x * dir.x + dir.y * dir.y + dir.z * dir.z < 1e-8f);
+            if (count_ray_hits(tv, h, p, dir) % 2)
+                vote++;
+        }
+        sign[i] = (vote * 2 >= n_sample) ? -1.0f : 1.0f;
     }
 }
 
@@ -755,6 +813,16 @@ const char* wb_mesh_eval(const float* attr, const int* indices, const int* face,
     if (n <= 0)
         return nullptr;
     k_mesh_eval<<<query_grid(n), QT, 0, stream>>>(attr, indices, face, u, v, n, out);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+const char* wb_sign_parity(const TreeView& tv, const float* pts, long long nq, int n_sample, float scale,
+                           const uint8_t* result, float* sign, cudaStream_t stream)
+{
+    if (nq <= 0)
+        return nullptr;
+    k_sign_parity<<<query_grid(nq), QT, 0, stream>>>(tv, pts, nq, n_sample, scale, result, sign);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

@@ -28,3 +28,6 @@ const char* wb_query_ray_count(const TreeView& tv, const float* starts, const fl
                                cudaStream_t stream);
 const char* wb_mesh_eval(const float* attr, const int* indices, const int* face, const float* u, const float* v,
                          long long n, float* out, cudaStream_t stream);
+// sign of mesh_query_point_sign_parity (mesh.h:2362-2392) for the queries whose `result` is set; 0 elsewhere
+const char* wb_sign_parity(const TreeView& tv, const float* pts, long long nq, int n_sample, float scale,
+                           const uint8_t* result, float* sign, cudaStream_t stream);

@@ -170,6 +170,24 @@ def _stage(a, dtype, dev, what):
     return from_numpy(h, dtype, dev), True
 
 
+def mesh_query_point_sign_parity(mesh, points, max_dist: float, n_sample: int = 1, perturbation_scale: float = 0.1):
+    """Closest point + inside/outside by ray-crossing parity (``mesh.h:309-498, 2362-2392``): ``sign`` is -1 when at
+    least half of ``n_sample`` rays along ``(1,1,1) + U(-s, s)^3`` (deterministic stream) cross an odd number of
+    faces.  Device array in -> device arrays out; host array in -> numpy arrays out."""
+    id_, dev = _mesh_id(mesh)
+    pts, host = _stage(points, vec3, dev, "points")
+    n = len(pts)
+    out = MeshQueryPoint(empty(n, uint8, dev), empty(n, float32, dev), empty(n, int32, dev), empty(n, float32, dev),
+                         empty(n, float32, dev))  # fmt: skip
+    ok = _lib.core().wp_b200_mesh_query_point_sign_parity(id_, _p(pts), n, float(max_dist), int(n_sample),
+                                                          float(perturbation_scale), _p(out.result), _p(out.sign),
+                                                          _p(out.face), _p(out.u), _p(out.v))  # fmt: skip
+    _check(ok, "mesh_query_point_sign_parity")
+    if host:
+        return MeshQueryPoint(*(getattr(out, k).numpy() for k in MeshQueryPoint.__slots__))
+    return out
+
+
 def _ray_pair(mesh, starts, dirs):
     id_, dev = _mesh_id(mesh)
     if isinstance(starts, array) != isinstance(dirs, array):
