@@ -176,16 +176,17 @@ WP_B200_API int wp_b200_mesh_query_point(uint64_t id, const float* points, int64
 WP_B200_API int wp_b200_mesh_query_point_sign_parity(uint64_t id, const float* points, int64_t n, float max_dist,
                                                      int n_sample, float perturbation_scale, uint8_t* result, float* sign,
                                                      int32_t* face, float* u, float* v);
-/* wp.mesh_query_ray (mesh.h:1768-1891): normal is n x 3 */
+/* wp.mesh_query_ray (mesh.h:1768-1891): normal is n x 3.  `roots` (optional, NULL = whole tree) restricts ray i to the
+ * subtree of that node, as the reference's `root` argument does (e.g. a group root from wp_b200_bvh_get_group_root) */
 WP_B200_API int wp_b200_mesh_query_ray(uint64_t id, const float* starts, const float* dirs, int64_t n, float max_t,
                                        uint8_t* result, float* sign, int32_t* face, float* t, float* u, float* v,
-                                       float* normal);
+                                       float* normal, const int32_t* roots);
 /* wp.mesh_query_ray_anyhit (mesh.h:1893-1974): result[i] = 1 when some triangle is hit with 0 <= t < max_t */
 WP_B200_API int wp_b200_mesh_query_ray_anyhit(uint64_t id, const float* starts, const float* dirs, int64_t n,
-                                              float max_t, uint8_t* result);
+                                              float max_t, uint8_t* result, const int32_t* roots);
 /* wp.mesh_query_ray_count_intersections (mesh.h:1976-2032): number of triangles hit with t >= 0, unbounded ray */
 WP_B200_API int wp_b200_mesh_query_ray_count_intersections(uint64_t id, const float* starts, const float* dirs,
-                                                           int64_t n, int32_t* counts);
+                                                           int64_t n, int32_t* counts, const int32_t* roots);
 /* wp.mesh_eval_position / wp.mesh_eval_velocity (mesh.h:2767-2805): out[i] = p*u + q*v + r*(1-u-v) of triangle
  * face[i], read from the mesh's CURRENT point / velocity array (zeros when the mesh has none); out is n x 3 */
 WP_B200_API int wp_b200_mesh_eval_position(uint64_t id, const int32_t* face, const float* u, const float* v,

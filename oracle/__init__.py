@@ -204,7 +204,7 @@ def query_point(points, indices, tree, queries, max_dist, stats=False):
     return res
 
 
-def query_ray(points, indices, tree, starts, dirs, max_t, stats=False):
+def query_ray(points, indices, tree, starts, dirs, max_t, stats=False, roots=None):
     points, indices, targs = _tree_args(points, indices, tree)
     s = _f32(starts, (-1, 3))
     d = _f32(dirs, (-1, 3))
@@ -217,6 +217,7 @@ def query_ray(points, indices, tree, starts, dirs, max_t, stats=False):
         *targs, _p(s, _f32p), _p(d, _f32p), ctypes.c_int64(n), ctypes.c_float(max_t),
         _p(res["result"], _u8p), _p(res["sign"], _f32p), _p(res["face"], _i32p), _p(res["t"], _f32p),
         _p(res["u"], _f32p), _p(res["v"], _f32p), _p(res["normal"], _f32p), _p(st, _u64p),
+        _p(None if roots is None else _i32(roots), _i32p),
     )  # fmt: skip
     if stats:
         res["nodes_visited"], res["tris_tested"] = int(st[0]), int(st[1])
@@ -237,22 +238,23 @@ def query_point_sign_parity(points, indices, tree, queries, max_dist, n_sample=1
     return res
 
 
-def query_ray_anyhit(points, indices, tree, starts, dirs, max_t):
+def query_ray_anyhit(points, indices, tree, starts, dirs, max_t, roots=None):
     """mesh_query_ray_anyhit restatement (mesh.h:1893-1974)."""
     points, indices, targs = _tree_args(points, indices, tree)
     s, d = _f32(starts, (-1, 3)), _f32(dirs, (-1, 3))
     out = np.zeros(s.shape[0], np.uint8)
     orc().orc_query_ray_anyhit(*targs, _p(s, _f32p), _p(d, _f32p), ctypes.c_int64(s.shape[0]), ctypes.c_float(max_t),
-                               _p(out, _u8p))  # fmt: skip
+                               _p(out, _u8p), _p(None if roots is None else _i32(roots), _i32p))  # fmt: skip
     return out
 
 
-def query_ray_count(points, indices, tree, starts, dirs):
+def query_ray_count(points, indices, tree, starts, dirs, roots=None):
     """mesh_query_ray_count_intersections restatement (mesh.h:1976-2032)."""
     points, indices, targs = _tree_args(points, indices, tree)
     s, d = _f32(starts, (-1, 3)), _f32(dirs, (-1, 3))
     out = np.zeros(s.shape[0], np.int32)
-    orc().orc_query_ray_count(*targs, _p(s, _f32p), _p(d, _f32p), ctypes.c_int64(s.shape[0]), _p(out, _i32p))
+    orc().orc_query_ray_count(*targs, _p(s, _f32p), _p(d, _f32p), ctypes.c_int64(s.shape[0]), _p(out, _i32p),
+                              _p(None if roots is None else _i32(roots), _i32p))
     return out
 
 
@@ -373,7 +375,7 @@ class RefMesh:
         )  # fmt: skip
         return res
 
-    def query_ray(self, starts, dirs, max_t, nthreads=1):
+    def query_ray(self, starts, dirs, max_t, nthreads=1, roots=None):
         s = _f32(starts, (-1, 3))
         d = _f32(dirs, (-1, 3))
         n = s.shape[0]
@@ -384,6 +386,7 @@ class RefMesh:
             ctypes.c_uint64(self.id), _p(s, _f32p), _p(d, _f32p), ctypes.c_int64(n), ctypes.c_float(max_t),
             _p(res["result"], _u8p), _p(res["sign"], _f32p), _p(res["face"], _i32p), _p(res["t"], _f32p),
             _p(res["u"], _f32p), _p(res["v"], _f32p), _p(res["normal"], _f32p), ctypes.c_int(nthreads),
+            _p(None if roots is None else _i32(roots), _i32p),
         )  # fmt: skip
         return res
 
@@ -399,18 +402,19 @@ class RefMesh:
                                           _p(res["v"], _f32p), ctypes.c_int(nthreads))  # fmt: skip
         return res
 
-    def query_ray_anyhit(self, starts, dirs, max_t, nthreads=1):
+    def query_ray_anyhit(self, starts, dirs, max_t, nthreads=1, roots=None):
         s, d = _f32(starts, (-1, 3)), _f32(dirs, (-1, 3))
         out = np.zeros(s.shape[0], np.uint8)
         ref().ref_query_ray_anyhit(ctypes.c_uint64(self.id), _p(s, _f32p), _p(d, _f32p), ctypes.c_int64(s.shape[0]),
-                                   ctypes.c_float(max_t), _p(out, _u8p), ctypes.c_int(nthreads))  # fmt: skip
+                                   ctypes.c_float(max_t), _p(out, _u8p), ctypes.c_int(nthreads),
+                                   _p(None if roots is None else _i32(roots), _i32p))  # fmt: skip
         return out
 
-    def query_ray_count(self, starts, dirs, nthreads=1):
+    def query_ray_count(self, starts, dirs, nthreads=1, roots=None):
         s, d = _f32(starts, (-1, 3)), _f32(dirs, (-1, 3))
         out = np.zeros(s.shape[0], np.int32)
         ref().ref_query_ray_count(ctypes.c_uint64(self.id), _p(s, _f32p), _p(d, _f32p), ctypes.c_int64(s.shape[0]),
-                                  _p(out, _i32p), ctypes.c_int(nthreads))  # fmt: skip
+                                  _p(out, _i32p), ctypes.c_int(nthreads), _p(None if roots is None else _i32(roots), _i32p))  # fmt: skip
         return out
 
     def query_aabb(self, lowers, uppers, item_bounds=None):

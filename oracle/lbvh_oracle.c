@@ -872,14 +872,15 @@ void orc_query_point(const float* points, const int* indices, const orc_half* no
 void orc_query_ray(const float* points, const int* indices, const orc_half* node_lowers, const orc_half* node_uppers,
                    const int* primitive_indices, int root, const float* starts, const float* dirs, int64_t n,
                    float max_t, uint8_t* result, float* sign, int* face, float* t, float* u, float* v, float* normal,
-                   uint64_t* stats)
+                   uint64_t* stats, const int* roots)
 {
-    const orc_mesh m = make_mesh(points, indices, node_lowers, node_uppers, primitive_indices, root);
+    orc_mesh m = make_mesh(points, indices, node_lowers, node_uppers, primitive_indices, root);
     orc_stats st = { 0, 0 };
     for (int64_t i = 0; i < n; ++i) {
         float tt = 0.f, tu = 0.f, tv = 0.f, ts = 0.f;
         int f = 0;
         v3 nrm = v3_make(0, 0, 0);
+        m.root = (roots && roots[i] != -1) ? roots[i] : root; /* mesh_query_ray(..., root), mesh.h:1778 */
         const int ok = ray_one(&m, v3_ld(starts, i), v3_ld(dirs, i), max_t, &tt, &tu, &tv, &ts, &nrm, &f,
                                stats ? &st : NULL);
         result[i] = (uint8_t)ok;
@@ -994,20 +995,24 @@ static int ray_count_one(const orc_mesh* m, v3 start, v3 dir)
 
 void orc_query_ray_anyhit(const float* points, const int* indices, const orc_half* node_lowers,
                           const orc_half* node_uppers, const int* primitive_indices, int root, const float* starts,
-                          const float* dirs, int64_t n, float max_t, uint8_t* result)
+                          const float* dirs, int64_t n, float max_t, uint8_t* result, const int* roots)
 {
-    const orc_mesh m = make_mesh(points, indices, node_lowers, node_uppers, primitive_indices, root);
-    for (int64_t i = 0; i < n; ++i)
+    orc_mesh m = make_mesh(points, indices, node_lowers, node_uppers, primitive_indices, root);
+    for (int64_t i = 0; i < n; ++i) {
+        m.root = (roots && roots[i] != -1) ? roots[i] : root;
         result[i] = (uint8_t)ray_anyhit_one(&m, v3_ld(starts, i), v3_ld(dirs, i), max_t);
+    }
 }
 
 void orc_query_ray_count(const float* points, const int* indices, const orc_half* node_lowers,
                          const orc_half* node_uppers, const int* primitive_indices, int root, const float* starts,
-                         const float* dirs, int64_t n, int* counts)
+                         const float* dirs, int64_t n, int* counts, const int* roots)
 {
-    const orc_mesh m = make_mesh(points, indices, node_lowers, node_uppers, primitive_indices, root);
-    for (int64_t i = 0; i < n; ++i)
+    orc_mesh m = make_mesh(points, indices, node_lowers, node_uppers, primitive_indices, root);
+    for (int64_t i = 0; i < n; ++i) {
+        m.root = (roots && roots[i] != -1) ? roots[i] : root;
         counts[i] = ray_count_one(&m, v3_ld(starts, i), v3_ld(dirs, i));
+    }
 }
 
 /* p*u + q*v + r*(1 - u - v) -- mesh.h:2767-2805 (vec3 scale then add, left to right) */

@@ -188,13 +188,13 @@ void ref_query_point_sign_parity(
 
 void ref_query_ray(
     uint64_t id, const float* starts, const float* dirs, int64_t n, float max_t, uint8_t* result, float* sign,
-    int* face, float* t, float* u, float* v, float* normal, int nthreads
+    int* face, float* t, float* u, float* v, float* normal, int nthreads, const int* roots
 )
 {
     parallel_for(n, nthreads, [&](int64_t i) {
         mesh_query_ray_t q = mesh_query_ray(
             id, vec3(starts[3 * i], starts[3 * i + 1], starts[3 * i + 2]),
-            vec3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), max_t, -1
+            vec3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), max_t, roots ? roots[i] : -1
         );
         result[i] = q.result ? 1 : 0;
         sign[i] = q.sign;
@@ -209,21 +209,22 @@ void ref_query_ray(
 }
 
 void ref_query_ray_anyhit(uint64_t id, const float* starts, const float* dirs, int64_t n, float max_t, uint8_t* result,
-                          int nthreads)
+                          int nthreads, const int* roots)
 {
     parallel_for(n, nthreads, [&](int64_t i) {
         result[i] = mesh_query_ray_anyhit(id, vec3(starts[3 * i], starts[3 * i + 1], starts[3 * i + 2]),
-                                          vec3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), max_t, -1)
+                                          vec3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), max_t, roots ? roots[i] : -1)
             ? 1
             : 0;
     });
 }
 
-void ref_query_ray_count(uint64_t id, const float* starts, const float* dirs, int64_t n, int* counts, int nthreads)
+void ref_query_ray_count(uint64_t id, const float* starts, const float* dirs, int64_t n, int* counts, int nthreads,
+                         const int* roots)
 {
     parallel_for(n, nthreads, [&](int64_t i) {
         counts[i] = mesh_query_ray_count_intersections(id, vec3(starts[3 * i], starts[3 * i + 1], starts[3 * i + 2]),
-                                                       vec3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), -1);
+                                                       vec3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), roots ? roots[i] : -1);
     });
 }
 

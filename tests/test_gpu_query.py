@@ -402,3 +402,33 @@ def test_sign_parity(wp, oracle_mod):
     b = wp.mesh_query_point(m, Q, 1e6).numpy()
     assert np.array_equal(a["sign"], b["sign"]) and np.array_equal(a["face"], b["face"])
     assert 0.05 < (a["sign"] < 0).mean() < 0.6
+
+
+def test_rooted_mesh_rays(wp, oracle_mod):
+    """mesh_query_ray / _anyhit / _count_intersections restricted to a group's subtree (`root` argument of the
+    reference): fixture from the reference C++, then the oracle; group roots of a grouped MESH."""
+    from test_oracle import _grouped_mesh_case
+
+    g = np.load(os.path.join(os.path.dirname(GOLD), "golden_group_queries.npz"))
+    P, I, T, groups, S, D, gid = _grouped_mesh_case()
+    m = wp.Mesh(wp.array(P, dtype=wp.vec3), wp.array(I, dtype=wp.int32), groups=wp.array(groups, dtype=wp.int32),
+                bvh_constructor="lbvh", bvh_leaf_size=4)
+    roots = wp.bvh_get_group_root(m, gid)
+    assert np.array_equal(roots, g["mesh_roots"])
+    Sd, Dd, Rd = wp.array(S, dtype=wp.vec3), wp.array(D, dtype=wp.vec3), wp.array(roots, dtype=wp.int32)
+    got = wp.mesh_query_ray(m, Sd, Dd, 1e6, roots=Rd).numpy()
+    assert_results_equal(got, {k: g[f"mesh_ray_{k}"] for k in RAY_FIELDS}, RAY_FIELDS)
+    assert np.array_equal(wp.mesh_query_ray_anyhit(m, Sd, Dd, 0.9, roots=Rd).numpy(), g["mesh_anyhit"])
+    assert np.array_equal(wp.mesh_query_ray_count_intersections(m, Sd, Dd, roots=roots).numpy(), g["mesh_count"])
+    hit = (got["result"] == 1) & (roots != -1)
+    assert hit.sum() > 100 and np.array_equal(groups[got["face"][hit]], gid[hit])
+    # leaf size 1 and a bigger batch against the oracle
+    m1 = wp.Mesh(wp.array(P, dtype=wp.vec3), wp.array(I, dtype=wp.int32), groups=wp.array(groups, dtype=wp.int32),
+                 bvh_constructor="lbvh", bvh_leaf_size=1)
+    tree = oracle_mod.mesh_lbvh_build(P, I, 1, groups=groups)
+    S2, D2 = mg.random_rays(P, 20000, seed=64)
+    gid2 = np.random.default_rng(65).integers(0, 5, 20000).astype(np.int32)
+    r2 = wp.bvh_get_group_root(m1, gid2)
+    assert np.array_equal(r2, oracle_mod.bvh_group_roots(tree, groups, gid2))
+    got2 = wp.mesh_query_ray(m1, wp.array(S2, dtype=wp.vec3), wp.array(D2, dtype=wp.vec3), 1e6, roots=r2).numpy()
+    assert_results_equal(got2, oracle_mod.query_ray(P, I, tree, S2, D2, 1e6, roots=r2), RAY_FIELDS)

@@ -437,3 +437,34 @@ def test_sign_parity_live_reference(oracle_mod):
                                  rm.query_point_sign_parity(Q, 1e6, ns, sc), POINT_FIELDS)
         assert_results_equal(o.query_point_sign_parity(P, idx, tree, Q, 0.05, 1, 0.1, rtl=True),
                              rm.query_point_sign_parity(Q, 0.05, 1, 0.1), POINT_FIELDS)
+
+
+def _grouped_mesh_case():
+    P, I = mg.noisy_sphere(3, noise=0.05, seed=61)
+    T = len(I) // 3
+    cz = P[I.reshape(-1, 3)].mean(axis=1)[:, 2]
+    groups = np.clip(((cz + 1.1) / 2.2 * 5).astype(np.int32), 0, 4)  # five z bands
+    S, D = mg.random_rays(P, 1500, seed=62)
+    S[::3] *= np.float32(0.2)
+    gid = np.random.default_rng(63).integers(-1, 6, 1500).astype(np.int32)
+    return P, I, T, groups, S, D, gid
+
+
+def test_rooted_mesh_rays_live_reference(oracle_mod):
+    """mesh_query_ray / _anyhit / _count_intersections with a `root` argument (a group's subtree) against the
+    reference C++; a rooted ray sees exactly the faces of its group."""
+    o = oracle_mod
+    if not o.ref_available():
+        pytest.skip("oracle/_ref/libwarp_ref_cpu.so not present")
+    P, I, T, groups, S, D, gid = _grouped_mesh_case()
+    for leaf in (1, 4):
+        tree = o.mesh_lbvh_build(P, I, leaf, groups=groups)
+        roots = o.bvh_group_roots(tree, groups, gid)
+        assert np.array_equal(roots, o.ref_bvh_group_roots(tree, groups, gid))
+        rm = o.RefMesh.from_tree(P, I, tree)
+        got = o.query_ray(P, I, tree, S, D, 1e6, roots=roots)
+        assert_results_equal(got, rm.query_ray(S, D, 1e6, roots=roots), RAY_FIELDS)
+        assert np.array_equal(o.query_ray_anyhit(P, I, tree, S, D, 0.9, roots=roots), rm.query_ray_anyhit(S, D, 0.9, roots=roots))
+        assert np.array_equal(o.query_ray_count(P, I, tree, S, D, roots=roots), rm.query_ray_count(S, D, roots=roots))
+        hit = (got["result"] == 1) & (roots != -1)
+        assert hit.sum() > 100 and np.array_equal(groups[got["face"][hit]], gid[hit])

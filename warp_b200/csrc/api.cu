@@ -685,7 +685,8 @@ static int query_point_on(MeshState* m, const float* points, int64_t n, float ma
 }
 
 static int query_ray_on(MeshState* m, const float* starts, const float* dirs, int64_t n, float max_t, uint8_t* result,
-                        float* sign, int32_t* face, float* t, float* u, float* v, float* normal, cudaStream_t st, int lane = 0)
+                        float* sign, int32_t* face, float* t, float* u, float* v, float* normal, cudaStream_t st, int lane = 0,
+                        const int32_t* roots = nullptr)
 {
     if (n <= 0)
         return 1;
@@ -705,7 +706,7 @@ static int query_ray_on(MeshState* m, const float* starts, const float* dirs, in
         }
         perm = ws.idx;
     }
-    const char* err = wb_query_ray(make_view(m->bvh), starts, dirs, perm, n, max_t, result, sign, face, t, u, v, normal,
+    const char* err = wb_query_ray(make_view(m->bvh), starts, dirs, perm, roots, n, max_t, result, sign, face, t, u, v, normal,
                                    stats_buffer(), st);
     if (err) {
         set_error("Warp error: mesh ray query failed: %s", err);
@@ -758,17 +759,17 @@ int wp_b200_mesh_query_point_sign_parity(uint64_t id, const float* points, int64
 }
 
 int wp_b200_mesh_query_ray(uint64_t id, const float* starts, const float* dirs, int64_t n, float max_t, uint8_t* result,
-                           float* sign, int32_t* face, float* t, float* u, float* v, float* normal)
+                           float* sign, int32_t* face, float* t, float* u, float* v, float* normal, const int32_t* roots)
 {
     MeshState* m = query_mesh(id);
     if (!m)
         return 0;
     DeviceGuard g(m->bvh.device);
-    return query_ray_on(m, starts, dirs, n, max_t, result, sign, face, t, u, v, normal, current_stream(m->bvh.device));
+    return query_ray_on(m, starts, dirs, n, max_t, result, sign, face, t, u, v, normal, current_stream(m->bvh.device), 0, roots);
 }
 
 int wp_b200_mesh_query_ray_anyhit(uint64_t id, const float* starts, const float* dirs, int64_t n, float max_t,
-                                  uint8_t* result)
+                                  uint8_t* result, const int32_t* roots)
 {
     MeshState* m = query_mesh(id);
     if (!m)
@@ -779,7 +780,7 @@ int wp_b200_mesh_query_ray_anyhit(uint64_t id, const float* starts, const float*
         return 1;
     if (m->bvh.n == 0)
         return check(cudaMemsetAsync(result, 0, (size_t)n, st), "memset");
-    const char* err = wb_query_ray_anyhit(make_view(m->bvh), starts, dirs, n, max_t, result, st);
+    const char* err = wb_query_ray_anyhit(make_view(m->bvh), starts, dirs, roots, n, max_t, result, st);
     if (err) {
         set_error("Warp error: mesh any-hit query failed: %s", err);
         return 0;
@@ -788,7 +789,7 @@ int wp_b200_mesh_query_ray_anyhit(uint64_t id, const float* starts, const float*
 }
 
 int wp_b200_mesh_query_ray_count_intersections(uint64_t id, const float* starts, const float* dirs, int64_t n,
-                                               int32_t* counts)
+                                               int32_t* counts, const int32_t* roots)
 {
     MeshState* m = query_mesh(id);
     if (!m)
@@ -799,7 +800,7 @@ int wp_b200_mesh_query_ray_count_intersections(uint64_t id, const float* starts,
         return 1;
     if (m->bvh.n == 0)
         return check(cudaMemsetAsync(counts, 0, 4 * (size_t)n, st), "memset");
-    const char* err = wb_query_ray_count(make_view(m->bvh), starts, dirs, n, counts, st);
+    const char* err = wb_query_ray_count(make_view(m->bvh), starts, dirs, roots, n, counts, st);
     if (err) {
         set_error("Warp error: mesh intersection count failed: %s", err);
         return 0;

@@ -91,21 +91,8 @@ k_bvh_query(TreeView tv, const float* __restrict__ item_lowers, const float* __r
                 const int item = __ldg(tv.prim + r);
                 rlo = ld3(item_lowers, (size_t)item), rhi = ld3(item_uppers, (size_t)item);
             }
-        } else if (r >= tv.n && r < 2 * tv.n - 1) {
-            const int s = r - tv.n;
-            const int p = __ldg(tv.parent_int + s);
-            if (p != WB_NO_PARENT) {
-                const int ps = p - tv.n;
-                const int side = ((int)tv.pairs[2 * (size_t)s + 1].aux == ps) ? 0 : 1;  // a left child's range ends at the split
-                const NodeRec rec = tv.pairs[2 * (size_t)ps + side];
-                rlo = make_float3(rec.lx, rec.ly, rec.lz), rhi = make_float3(rec.hx, rec.hy, rec.hz);
-                if (rec.ref & WB_LEAF) {
-                    const uint32_t first = side ? (uint32_t)ps + 1u : rec.aux, last = side ? rec.aux : (uint32_t)ps;
-                    start.a = first | WB_LEAF, start.b = last - first + 1u;
-                } else {
-                    start.a = (uint32_t)s, start.b = 0;
-                }
-            }
+        } else if (r >= tv.n) {
+            wb_root_entry(tv, r, start.a, start.b, rlo, rhi);
         }
         if (test_box<RAY>(qa, qb, rlo, rhi, max_dist))
             stack[top++] = start;

@@ -105,6 +105,31 @@ __device__ __forceinline__ unsigned wb_arrive(unsigned* counter, unsigned add)
     return old;
 }
 
+// Start of a traversal at the caller's `root` (a reference node index, e.g. from bvh_get_group_root; bvh.h:504:
+// root == -1 ? *bvh.root : root).  Internal node n+s that is not the tree root: its own box, leaf flag and range live
+// in its record inside the parent's pair.  Returns false when r is not such a node (the caller keeps its default).
+// a / b are the traversal entry: leaf = first sorted position | WB_LEAF and item count, inner = internal slot and 0.
+__device__ __forceinline__ bool wb_root_entry(const TreeView& tv, int r, uint32_t& a, uint32_t& b, float3& lo, float3& hi)
+{
+    if (r < tv.n || r >= 2 * tv.n - 1)
+        return false;
+    const int s = r - tv.n;
+    const int p = __ldg(tv.parent_int + s);
+    if (p == WB_NO_PARENT)
+        return false;  // the tree root itself
+    const int ps = p - tv.n;
+    const int side = ((int)tv.pairs[2 * (size_t)s + 1].aux == ps) ? 0 : 1;  // a left child's range ends at the split
+    const NodeRec rec = tv.pairs[2 * (size_t)ps + side];
+    lo = make_float3(rec.lx, rec.ly, rec.lz), hi = make_float3(rec.hx, rec.hy, rec.hz);
+    if (rec.ref & WB_LEAF) {
+        const uint32_t first = side ? (uint32_t)ps + 1u : rec.aux, last = side ? rec.aux : (uint32_t)ps;
+        a = first | WB_LEAF, b = last - first + 1u;
+    } else {
+        a = (uint32_t)s, b = 0;
+    }
+    return true;
+}
+
 // item-bounds sources: a triangle mesh (bounds computed on the fly from vertices, replacing the
 // lowers/uppers round trip of mesh.cu:16-36) or caller-provided boxes (wp.Bvh)
 struct MeshSource {

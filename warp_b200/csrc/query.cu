@@ -443,13 +443,34 @@ k_query_point(TreeView tv, const float* __restrict__ pts, const int* __restrict_
     }
 }
 
+// start entry of a ray traversal: the tree root, or the caller's root node (mesh_query_ray(..., root), mesh.h:1768)
+__device__ __forceinline__ Entry ray_start_entry(const TreeView& tv, const TreeHeader& h, const int* __restrict__ roots,
+                                                 long long i, float3& lo, float3& hi)
+{
+    Entry e;
+    if (h.root_ref & WB_LEAF)
+        e.a = WB_LEAF | 0u, e.b = h.root_count;
+    else
+        e.a = (h.root_ref & WB_IDX_MASK) - (uint32_t)tv.n, e.b = 0;
+    lo = make_float3(h.lx, h.ly, h.lz), hi = make_float3(h.hx, h.hy, h.hz);
+    const int r = roots ? __ldg(roots + i) : -1;
+    if (r >= 0 && r < tv.n) {  // an original leaf: one triangle
+        e.a = (uint32_t)r | WB_LEAF, e.b = 1u;
+        const Tri t = load_tri(tv.tris, (uint32_t)r);
+        lo = wb_min3(wb_min3(t.p, t.q), t.r), hi = wb_max3(wb_max3(t.p, t.q), t.r);
+    } else if (r >= tv.n) {
+        wb_root_entry(tv, r, e.a, e.b, lo, hi);
+    }
+    return e;
+}
+
 // ------------------------------------------------------------------------------------------------
 // closest ray hit, near child first (mesh.h:1735-1891)
 // ------------------------------------------------------------------------------------------------
 template <bool COUNT>
 __global__ void __launch_bounds__(QT)
 k_query_ray(TreeView tv, const float* __restrict__ starts, const float* __restrict__ dirs, const int* __restrict__ perm,
-            long long nq, float max_t, uint8_t* __restrict__ result, float* __restrict__ sign, int* __restrict__ face,
+            const int* __restrict__ roots, long long nq, float max_t, uint8_t* __restrict__ result, float* __restrict__ sign, int* __restrict__ face,
             float* __restrict__ out_t, float* __restrict__ out_u, float* __restrict__ out_v, float* __restrict__ normal,
             unsigned long long* __restrict__ stats)
 {
@@ -473,11 +494,8 @@ k_query_ray(TreeView tv, const float* __restrict__ starts, const float* __restri
 
         Entry stack[WB_QUERY_STACK];
         int top = 0;
-        Entry cur;
-        if (h.root_ref & WB_LEAF)
-            cur.a = WB_LEAF | 0u, cur.b = h.root_count;
-        else
-            cur.a = (h.root_ref & WB_IDX_MASK) - (uint32_t)tv.n, cur.b = 0;
+        float3 start_lo, start_hi;  // the start node's box is not tested (mesh.h:1779)
+        Entry cur = ray_start_entry(tv, h, roots, i, start_lo, start_hi);
 
         float min_t = max_t, min_u = 0.f, min_v = 0.f, min_sign = 1.0f;
         int min_face = 0;
@@ -558,20 +576,16 @@ k_query_ray(TreeView tv, const float* __restrict__ starts, const float* __restri
 // mesh_query_ray_count_intersections (mesh.h:1976-2032): triangles hit with t >= 0 along the whole ray; push-both
 // traversal with the robust slab test.  Children are tested before the push (the reference tests on pop: same count,
 // shallower stack); the reference has no overflow check (undefined past 32 entries), subtrees that do not fit are dropped.
-__device__ __forceinline__ int count_ray_hits(const TreeView& tv, const TreeHeader& h, float3 org, float3 dir)
+__device__ __forceinline__ int count_ray_hits(const TreeView& tv, float3 org, float3 dir, Entry root, float3 root_lo,
+                                              float3 root_hi)
 {
     const WoopRay wr = woop_setup(dir);
     Entry stack[WB_QUERY_STACK];
     int top = 0;
-    Entry root;
-    if (h.root_ref & WB_LEAF)
-        root.a = WB_LEAF | 0u, root.b = h.root_count;
-    else
-        root.a = (h.root_ref & WB_IDX_MASK) - (uint32_t)tv.n, root.b = 0;
     const float3 rcp = make_float3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
     int hits = 0;
     float tt;
-    if (ray_aabb_robust(org, dir, rcp, make_float3(h.lx, h.ly, h.lz), make_float3(h.hx, h.hy, h.hz), tt))
+    if (ray_aabb_robust(org, dir, rcp, root_lo, root_hi, tt))
         stack[top++] = root;
     while (top) {
         const Entry cur = stack[--top];
@@ -603,8 +617,9 @@ __device__ __forceinline__ int count_ray_hits(const TreeView& tv, const TreeHead
 // ------------------------------------------------------------------------------------------------
 template <bool COUNT_MODE>
 __global__ void __launch_bounds__(QT)
-k_query_ray_aux(TreeView tv, const float* __restrict__ starts, const float* __restrict__ dirs, long long nq, float max_t,
-                uint8_t* __restrict__ any_out, int* __restrict__ count_out)
+k_query_ray_aux(TreeView tv, const float* __restrict__ starts, const float* __restrict__ dirs,
+                const int* __restrict__ roots, long long nq, float max_t, uint8_t* __restrict__ any_out,
+                int* __restrict__ count_out)
 {
     const TreeHeader h = *tv.header;
     for (long long i = (long long)blockIdx.x * QT + threadIdx.x; i < nq; i += (long long)gridDim.x * QT) {
@@ -613,14 +628,11 @@ k_query_ray_aux(TreeView tv, const float* __restrict__ starts, const float* __re
         const WoopRay wr = woop_setup(dir);
         Entry stack[WB_QUERY_STACK];
         int top = 0;
-        Entry root;
-        if (h.root_ref & WB_LEAF)
-            root.a = WB_LEAF | 0u, root.b = h.root_count;
-        else
-            root.a = (h.root_ref & WB_IDX_MASK) - (uint32_t)tv.n, root.b = 0;
+        float3 start_lo, start_hi;
+        const Entry root = ray_start_entry(tv, h, roots, i, start_lo, start_hi);
 
         if (COUNT_MODE) {
-            count_out[i] = count_ray_hits(tv, h, org, dir);
+            count_out[i] = count_ray_hits(tv, org, dir, root, start_lo, start_hi);
         } else {
             float3 safe = dir;
             if (safe.x == 0.0f)
@@ -714,7 +726,9 @@ k_sign_parity(TreeView tv, const float* __restrict__ pts, long long nq, int n_sa
                 const float rz = randf_range(state, -scale, scale);
                 dir = make_float3(1.0f + rx, 1.0f + ry, 1.0f + rz);
             } while (dir.x * dir.x + dir.y * dir.y + dir.z * dir.z < 1e-8f);
-            if (count_ray_hits(tv, h, p, dir) % 2)
+            float3 rlo, rhi;
+            const Entry root = ray_start_entry(tv, h, nullptr, i, rlo, rhi);
+            if (count_ray_hits(tv, p, dir, root, rlo, rhi) % 2)
                 vote++;
         }
         sign[i] = (vote * 2 >= n_sample) ? -1.0f : 1.0f;
@@ -772,37 +786,37 @@ const char* wb_query_point(const TreeView& tv, const float* pts, const int* perm
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
-const char* wb_query_ray(const TreeView& tv, const float* starts, const float* dirs, const int* perm, long long nq,
-                         float max_t, uint8_t* result, float* sign, int* face, float* t, float* u, float* v,
+const char* wb_query_ray(const TreeView& tv, const float* starts, const float* dirs, const int* perm, const int* roots,
+                         long long nq, float max_t, uint8_t* result, float* sign, int* face, float* t, float* u, float* v,
                          float* normal, unsigned long long* stats, cudaStream_t stream)
 {
     if (nq <= 0)
         return nullptr;
     const int grid = query_grid(nq);
     if (stats)
-        k_query_ray<true><<<grid, QT, 0, stream>>>(tv, starts, dirs, perm, nq, max_t, result, sign, face, t, u, v, normal, stats);
+        k_query_ray<true><<<grid, QT, 0, stream>>>(tv, starts, dirs, perm, roots, nq, max_t, result, sign, face, t, u, v, normal, stats);
     else
-        k_query_ray<false><<<grid, QT, 0, stream>>>(tv, starts, dirs, perm, nq, max_t, result, sign, face, t, u, v, normal, stats);
+        k_query_ray<false><<<grid, QT, 0, stream>>>(tv, starts, dirs, perm, roots, nq, max_t, result, sign, face, t, u, v, normal, stats);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
-const char* wb_query_ray_anyhit(const TreeView& tv, const float* starts, const float* dirs, long long nq, float max_t,
-                                uint8_t* result, cudaStream_t stream)
+const char* wb_query_ray_anyhit(const TreeView& tv, const float* starts, const float* dirs, const int* roots, long long nq,
+                                float max_t, uint8_t* result, cudaStream_t stream)
 {
     if (nq <= 0)
         return nullptr;
-    k_query_ray_aux<false><<<query_grid(nq), QT, 0, stream>>>(tv, starts, dirs, nq, max_t, result, nullptr);
+    k_query_ray_aux<false><<<query_grid(nq), QT, 0, stream>>>(tv, starts, dirs, roots, nq, max_t, result, nullptr);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
-const char* wb_query_ray_count(const TreeView& tv, const float* starts, const float* dirs, long long nq, int* counts,
-                               cudaStream_t stream)
+const char* wb_query_ray_count(const TreeView& tv, const float* starts, const float* dirs, const int* roots, long long nq,
+                               int* counts, cudaStream_t stream)
 {
     if (nq <= 0)
         return nullptr;
-    k_query_ray_aux<true><<<query_grid(nq), QT, 0, stream>>>(tv, starts, dirs, nq, 0.0f, nullptr, counts);
+    k_query_ray_aux<true><<<query_grid(nq), QT, 0, stream>>>(tv, starts, dirs, roots, nq, 0.0f, nullptr, counts);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

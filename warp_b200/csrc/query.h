@@ -18,14 +18,15 @@ const char* wb_exclusive_scan(const int* counts, int* offsets, long long n, long
 const char* wb_query_point(const TreeView& tv, const float* pts, const int* perm, long long nq, float max_dist,
                            int with_sign, uint8_t* result, float* sign, int* face, float* u, float* v,
                            unsigned long long* stats, cudaStream_t stream);
-const char* wb_query_ray(const TreeView& tv, const float* starts, const float* dirs, const int* perm, long long nq,
-                         float max_t, uint8_t* result, float* sign, int* face, float* t, float* u, float* v,
+// roots: optional per-ray start node (reference node index; < 0 or NULL = the tree root)
+const char* wb_query_ray(const TreeView& tv, const float* starts, const float* dirs, const int* perm, const int* roots,
+                         long long nq, float max_t, uint8_t* result, float* sign, int* face, float* t, float* u, float* v,
                          float* normal, unsigned long long* stats, cudaStream_t stream);
 // mesh_query_ray_anyhit / mesh_query_ray_count_intersections / mesh_eval_{position,velocity} (mesh.h:1893-2032, 2767-2807)
-const char* wb_query_ray_anyhit(const TreeView& tv, const float* starts, const float* dirs, long long nq, float max_t,
-                                uint8_t* result, cudaStream_t stream);
-const char* wb_query_ray_count(const TreeView& tv, const float* starts, const float* dirs, long long nq, int* counts,
-                               cudaStream_t stream);
+const char* wb_query_ray_anyhit(const TreeView& tv, const float* starts, const float* dirs, const int* roots, long long nq,
+                                float max_t, uint8_t* result, cudaStream_t stream);
+const char* wb_query_ray_count(const TreeView& tv, const float* starts, const float* dirs, const int* roots, long long nq,
+                               int* counts, cudaStream_t stream);
 const char* wb_mesh_eval(const float* attr, const int* indices, const int* face, const float* u, const float* v,
                          long long n, float* out, cudaStream_t stream);
 // sign of mesh_query_point_sign_parity (mesh.h:2362-2392) for the queries whose `result` is set; 0 elsewhere

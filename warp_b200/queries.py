@@ -122,8 +122,9 @@ def mesh_query_point(mesh, points, max_dist: float, out: MeshQueryPoint | None =
     return _point_query(mesh, points, float(max_dist), True, out)
 
 
-def mesh_query_ray(mesh, starts, dirs, max_t: float, out: MeshQueryRay | None = None) -> MeshQueryRay:
-    """Closest hit of each ray ``starts[i] + t * dirs[i]``, ``0 <= t < max_t`` (mesh.h:1768-1891)."""
+def mesh_query_ray(mesh, starts, dirs, max_t: float, out: MeshQueryRay | None = None, roots=None) -> MeshQueryRay:
+    """Closest hit of each ray ``starts[i] + t * dirs[i]``, ``0 <= t < max_t`` (mesh.h:1768-1891).  ``roots`` (device
+    arrays only): per-ray start node, e.g. a group root from :func:`warp_b200.bvh_get_group_root`."""
     id_, dev = _mesh_id(mesh)
     c = _lib.core()
     max_t = float(max_t)
@@ -139,9 +140,11 @@ def mesh_query_ray(mesh, starts, dirs, max_t: float, out: MeshQueryRay | None = 
                                empty(n, float32, dev), empty(n, float32, dev), empty(n, float32, dev),
                                empty(n, vec3, dev))  # fmt: skip
         ok = c.wp_b200_mesh_query_ray(id_, _p(s), _p(d), n, max_t, _p(out.result), _p(out.sign), _p(out.face),
-                                      _p(out.t), _p(out.u), _p(out.v), _p(out.normal))  # fmt: skip
+                                      _p(out.t), _p(out.u), _p(out.v), _p(out.normal), _roots(roots, n, dev))  # fmt: skip
         _check(ok, "mesh_query_ray")
         return out
+    if roots is not None:
+        raise RuntimeError("roots= needs device arrays (wp.array) for starts and dirs")
     s, d = _host_vec3(starts, "starts"), _host_vec3(dirs, "dirs")
     if s.shape != d.shape:
         raise RuntimeError("starts and dirs must have the same length")
@@ -154,6 +157,18 @@ def mesh_query_ray(mesh, starts, dirs, max_t: float, out: MeshQueryRay | None = 
                                        _p(out.t), _p(out.u), _p(out.v), _p(out.normal))  # fmt: skip
     _check(ok, "mesh_query_ray")
     return out
+
+
+def _roots(roots, n, dev):
+    """ctypes pointer to an optional per-query int32 roots array (host arrays are uploaded)."""
+    if roots is None:
+        return None
+    if not isinstance(roots, array):
+        roots = from_numpy(np.ascontiguousarray(roots, dtype=np.int32), int32, dev)
+    if roots.dtype != int32 or len(roots) != n:
+        raise RuntimeError("roots should be an int32 array with one entry per ray")
+    _roots.keep = roots  # keep the upload alive until the (stream-ordered) call has been enqueued and used
+    return ctypes.c_void_p(roots.ptr or 0)
 
 
 def _stage(a, dtype, dev, what):
@@ -199,21 +214,21 @@ def _ray_pair(mesh, starts, dirs):
     return id_, dev, s, d, host
 
 
-def mesh_query_ray_anyhit(mesh, starts, dirs, max_t: float):
+def mesh_query_ray_anyhit(mesh, starts, dirs, max_t: float, roots=None):
     """``result[i]`` = some triangle is hit by ray i with ``0 <= t < max_t`` (mesh.h:1893-1974).
     Device arrays in -> device ``uint8`` array out; host arrays in -> numpy ``bool`` array out."""
     id_, dev, s, d, host = _ray_pair(mesh, starts, dirs)
     out = empty(len(s), uint8, dev)
-    ok = _lib.core().wp_b200_mesh_query_ray_anyhit(id_, _p(s), _p(d), len(s), float(max_t), _p(out))
+    ok = _lib.core().wp_b200_mesh_query_ray_anyhit(id_, _p(s), _p(d), len(s), float(max_t), _p(out), _roots(roots, len(s), dev))
     _check(ok, "mesh_query_ray_anyhit")
     return out.numpy().astype(bool) if host else out
 
 
-def mesh_query_ray_count_intersections(mesh, starts, dirs):
+def mesh_query_ray_count_intersections(mesh, starts, dirs, roots=None):
     """Number of triangles hit by ray i with ``t >= 0``, over the whole ray (mesh.h:1976-2032)."""
     id_, dev, s, d, host = _ray_pair(mesh, starts, dirs)
     out = empty(len(s), int32, dev)
-    ok = _lib.core().wp_b200_mesh_query_ray_count_intersections(id_, _p(s), _p(d), len(s), _p(out))
+    ok = _lib.core().wp_b200_mesh_query_ray_count_intersections(id_, _p(s), _p(d), len(s), _p(out), _roots(roots, len(s), dev))
     _check(ok, "mesh_query_ray_count_intersections")
     return out.numpy() if host else out
 
