@@ -406,8 +406,11 @@ __device__ __forceinline__ bool probe_sign(const TreeView& tv, const TreeHeader&
     return hit;
 }
 
+#ifndef WB_QP_MIN_BLOCKS
+#define WB_QP_MIN_BLOCKS 10  // measured on C2: 9 (ptxas default, 52 registers) 653, 10: 668, 11: 617, 12: 617, 16: 464 M queries/s
+#endif
 template <bool SIGN, bool COUNT>
-__global__ void __launch_bounds__(QT)
+__global__ void __launch_bounds__(QT, WB_QP_MIN_BLOCKS)
 k_query_point(TreeView tv, const float* __restrict__ pts, const int* __restrict__ perm, long long nq, float max_dist,
               uint8_t* __restrict__ result, float* __restrict__ sign, int* __restrict__ face, float* __restrict__ u,
               float* __restrict__ v, unsigned long long* __restrict__ stats)
@@ -467,8 +470,11 @@ __device__ __forceinline__ Entry ray_start_entry(const TreeView& tv, const TreeH
 // ------------------------------------------------------------------------------------------------
 // closest ray hit, near child first (mesh.h:1735-1891)
 // ------------------------------------------------------------------------------------------------
+#ifndef WB_QR_MIN_BLOCKS
+#define WB_QR_MIN_BLOCKS 10  // measured on C3: unhinted 2.98, (QT, 1) 2.88, 8: 2.86, 10: 3.01, 12: 2.83 G rays/s
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(QT)
+__global__ void __launch_bounds__(QT, WB_QR_MIN_BLOCKS)
 k_query_ray(TreeView tv, const float* __restrict__ starts, const float* __restrict__ dirs, const int* __restrict__ perm,
             const int* __restrict__ roots, long long nq, float max_t, uint8_t* __restrict__ result, float* __restrict__ sign, int* __restrict__ face,
             float* __restrict__ out_t, float* __restrict__ out_u, float* __restrict__ out_v, float* __restrict__ normal,
