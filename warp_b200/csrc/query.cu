@@ -17,7 +17,10 @@
 
 namespace {
 
-constexpr int QT = 128;  // threads per block
+#ifndef WB_QT
+#define WB_QT 128
+#endif
+constexpr int QT = WB_QT;  // threads per block
 
 struct Entry {
     uint32_t a;  // leaf: first sorted position | WB_LEAF ; inner: internal slot s
@@ -409,15 +412,19 @@ __device__ __forceinline__ bool probe_sign(const TreeView& tv, const TreeHeader&
 #ifndef WB_QP_MIN_BLOCKS
 #define WB_QP_MIN_BLOCKS 10  // measured on C2: 9 (ptxas default, 52 registers) 653, 10: 668, 11: 617, 12: 617, 16: 464 M queries/s
 #endif
+// the signed variant (three extra probe traversals per query) runs best with 256-thread blocks at 5-6 blocks / SM:
+// 107 -> 117 M queries/s on C2; the unsigned one with 128-thread blocks
+constexpr int QT_SIGN = 256;
 template <bool SIGN, bool COUNT>
-__global__ void __launch_bounds__(QT, WB_QP_MIN_BLOCKS)
+__global__ void __launch_bounds__(SIGN ? QT_SIGN : QT, SIGN ? 6 : WB_QP_MIN_BLOCKS)
 k_query_point(TreeView tv, const float* __restrict__ pts, const int* __restrict__ perm, long long nq, float max_dist,
               uint8_t* __restrict__ result, float* __restrict__ sign, int* __restrict__ face, float* __restrict__ u,
               float* __restrict__ v, unsigned long long* __restrict__ stats)
 {
     const TreeHeader h = *tv.header;
     Counters cnt;
-    for (long long slot = (long long)blockIdx.x * QT + threadIdx.x; slot < nq; slot += (long long)gridDim.x * QT) {
+    constexpr int T = SIGN ? QT_SIGN : QT;
+    for (long long slot = (long long)blockIdx.x * T + threadIdx.x; slot < nq; slot += (long long)gridDim.x * T) {
         // `perm` (optional) is a Morton ordering of the batch: thread `slot` answers query perm[slot]
         const long long i = perm ? (long long)__ldg(perm + slot) : slot;
         const float3 p = make_float3(__ldg(pts + 3 * i), __ldg(pts + 3 * i + 1), __ldg(pts + 3 * i + 2));
@@ -758,13 +765,16 @@ k_mesh_eval(const float* __restrict__ attr, const int* __restrict__ indices, con
     }
 }
 
-int query_grid(long long nq)
+int query_grid(long long nq, int threads = QT)
 {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long want = (nq + QT - 1) / QT;
-    const long long cap = (long long)sms * 64;  // grid-stride beyond that
+    const long long want = (nq + threads - 1) / threads;
+#ifndef WB_QGRID_CAP
+#define WB_QGRID_CAP 4096  // blocks per SM before grid-striding: 16: 577, 64: 670, 256: 689, 4096: 694 M queries/s (C2)
+#endif
+    const long long cap = (long long)sms * WB_QGRID_CAP * QT / threads;  // grid-stride beyond that
     return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
@@ -778,10 +788,11 @@ const char* wb_query_point(const TreeView& tv, const float* pts, const int* perm
         return nullptr;
     const int grid = query_grid(nq);
     if (with_sign) {
+        const int sgrid = query_grid(nq, QT_SIGN);
         if (stats)
-            k_query_point<true, true><<<grid, QT, 0, stream>>>(tv, pts, perm, nq, max_dist, result, sign, face, u, v, stats);
+            k_query_point<true, true><<<sgrid, QT_SIGN, 0, stream>>>(tv, pts, perm, nq, max_dist, result, sign, face, u, v, stats);
         else
-            k_query_point<true, false><<<grid, QT, 0, stream>>>(tv, pts, perm, nq, max_dist, result, sign, face, u, v, stats);
+            k_query_point<true, false><<<sgrid, QT_SIGN, 0, stream>>>(tv, pts, perm, nq, max_dist, result, sign, face, u, v, stats);
     } else {
         if (stats)
             k_query_point<false, true><<<grid, QT, 0, stream>>>(tv, pts, perm, nq, max_dist, result, sign, face, u, v, stats);
