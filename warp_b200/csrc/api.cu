@@ -192,20 +192,27 @@ bool lane_reserve(HostLane& l, size_t bytes)
     return true;
 }
 
-// Queries per staged chunk of the *_host entry points (env WARP_B200_HOST_CHUNK overrides).  Measured on
-// B200 / C2 / 16.8 M pinned queries: 0.5 M: 47.0 ms, 1 M: 37.2, 2 M: 33.9, 4 M: 31.9, unchunked: 33.0 -- small
-// chunks lose more in traversal coherence (a Morton-sorted chunk is sparser than the sorted batch) than
-// they gain in copy overlap.  A three-stage copy/compute/copy pipeline was slower still (34.6 ms at 4 M).
-int64_t host_chunk()
+// Queries per staged chunk of the *_host entry points (env WARP_B200_HOST_CHUNK forces a fixed size).  Measured on
+// B200 / C2 / 16.8 M pinned queries, fixed chunk sizes: 2 M 516, 3 M 538, 4 M 547, 6 M 555, 8 M 552 M queries/s -- small
+// chunks lose more in traversal coherence (a Morton-sorted chunk is sparser than the sorted batch) than they gain
+// in copy overlap; a three-stage copy/compute/copy pipeline was slower still.  Default: batches up to 4 M go in one
+// piece, larger ones in ceil(n / 6 M) >= 2 equal chunks.
+int64_t host_chunk(int64_t n)
 {
-    static int64_t v = 0;
-    if (!v) {
+    static int64_t forced = -1;
+    if (forced < 0) {
         const char* e = getenv("WARP_B200_HOST_CHUNK");
-        v = e ? atoll(e) : (1ll << 22);
-        if (v < 1024)
-            v = 1024;
+        forced = e ? atoll(e) : 0;
+        if (forced && forced < 1024)
+            forced = 1024;
     }
-    return v;
+    if (forced)
+        return forced;
+    if (n <= (1ll << 22))
+        return n > 0 ? n : 1;
+    const int64_t k = (n + (6ll << 20) - 1) / (6ll << 20);
+    const int64_t parts = k < 2 ? 2 : k;
+    return (((n + parts - 1) / parts) + 1023) & ~(int64_t)1023;
 }
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -851,7 +858,7 @@ static int point_host(uint64_t id, const float* points, int64_t n, float max_dis
     const int dev = m->bvh.device;
     DeviceGuard g(dev);
     cudaStreamSynchronize(current_stream(dev));  // the tree must be complete before the lanes read it
-    const int64_t chunk = n < host_chunk() ? (n > 0 ? n : 1) : host_chunk();
+    const int64_t chunk = n < host_chunk(n) ? (n > 0 ? n : 1) : host_chunk(n);
     const size_t o_pts = 0, o_res = o_pts + align256(12 * chunk), o_sign = o_res + align256(chunk),
                  o_face = o_sign + align256(4 * chunk), o_u = o_face + align256(4 * chunk),
                  o_v = o_u + align256(4 * chunk), total = o_v + align256(4 * chunk);
@@ -900,7 +907,7 @@ int wp_b200_mesh_query_ray_host(uint64_t id, const float* starts, const float* d
     const int dev = m->bvh.device;
     DeviceGuard g(dev);
     cudaStreamSynchronize(current_stream(dev));
-    const int64_t chunk = n < host_chunk() ? (n > 0 ? n : 1) : host_chunk();
+    const int64_t chunk = n < host_chunk(n) ? (n > 0 ? n : 1) : host_chunk(n);
     const size_t o_s = 0, o_d = o_s + align256(12 * chunk), o_res = o_d + align256(12 * chunk),
                  o_sign = o_res + align256(chunk), o_face = o_sign + align256(4 * chunk),
                  o_t = o_face + align256(4 * chunk), o_u = o_t + align256(4 * chunk), o_v = o_u + align256(4 * chunk),
