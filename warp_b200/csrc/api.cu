@@ -196,8 +196,9 @@ bool lane_reserve(HostLane& l, size_t bytes)
 // B200 / C2 / 16.8 M pinned queries, fixed chunk sizes: 2 M 516, 3 M 538, 4 M 547, 6 M 555, 8 M 552 M queries/s -- small
 // chunks lose more in traversal coherence (a Morton-sorted chunk is sparser than the sorted batch) than they gain
 // in copy overlap; a three-stage copy/compute/copy pipeline was slower still.  Default: batches up to 4 M go in one
-// piece, larger ones in ceil(n / 6 M) >= 2 equal chunks.
-int64_t host_chunk(int64_t n)
+// piece, larger ones in ceil(n / 6 M) >= 2 equal chunks; above 8 M the closest-point calls additionally start and
+// end with a 1 M chunk (563 vs 557 M queries/s: the first upload and the last download are the exposed copies).
+int64_t host_chunk_forced()
 {
     static int64_t forced = -1;
     if (forced < 0) {
@@ -206,7 +207,12 @@ int64_t host_chunk(int64_t n)
         if (forced && forced < 1024)
             forced = 1024;
     }
-    if (forced)
+    return forced;
+}
+
+int64_t host_chunk(int64_t n)
+{
+    if (const int64_t forced = host_chunk_forced())
         return forced;
     if (n <= (1ll << 22))
         return n > 0 ? n : 1;
@@ -859,15 +865,25 @@ static int point_host(uint64_t id, const float* points, int64_t n, float max_dis
     DeviceGuard g(dev);
     cudaStreamSynchronize(current_stream(dev));  // the tree must be complete before the lanes read it
     const int64_t chunk = n < host_chunk(n) ? (n > 0 ? n : 1) : host_chunk(n);
-    const size_t o_pts = 0, o_res = o_pts + align256(12 * chunk), o_sign = o_res + align256(chunk),
-                 o_face = o_sign + align256(4 * chunk), o_u = o_face + align256(4 * chunk),
-                 o_v = o_u + align256(4 * chunk), total = o_v + align256(4 * chunk);
+    // a short first and last chunk (1 M) keep the copies nobody can overlap -- the first upload, the last download -- small
+    const int64_t edge = (!host_chunk_forced() && n > (1ll << 23)) ? (1ll << 20) : 0;
+    const int64_t middle = n - 2 * edge;
+    const int64_t mid_parts = (middle + (6ll << 20) - 1) / (6ll << 20);  // equal middle chunks of at most 6 M
+    const int64_t mid_chunk = edge ? (((middle + mid_parts - 1) / mid_parts + 1023) & ~(int64_t)1023) : chunk;
+    const int64_t cap = edge ? (mid_chunk > edge ? mid_chunk : edge) : chunk;
+    const size_t o_pts = 0, o_res = o_pts + align256(12 * cap), o_sign = o_res + align256(cap),
+                 o_face = o_sign + align256(4 * cap), o_u = o_face + align256(4 * cap),
+                 o_v = o_u + align256(4 * cap), total = o_v + align256(4 * cap);
     int ok = 1;
-    for (int64_t base = 0, k = 0; base < n && ok; base += chunk, ++k) {
+    for (int64_t base = 0, k = 0; base < n && ok; ++k) {
         HostLane& l = g_lanes[dev][k & 1];
         if (!lane_reserve(l, total))
             return 0;
-        const int64_t c = (n - base < chunk) ? n - base : chunk;
+        int64_t c = edge ? ((base == 0 || n - base <= edge) ? edge : mid_chunk) : chunk;
+        if (edge && base > 0 && n - base > edge && n - base - c < edge)
+            c = n - base - edge;  // the last middle chunk stops where the tail chunk starts
+        if (c > n - base)
+            c = n - base;
         char* b = (char*)l.buf;
         ok = ok && check(cudaMemcpyAsync(b + o_pts, points + 3 * base, 12 * c, cudaMemcpyHostToDevice, l.stream), "h2d");
         ok = ok && query_point_on(m, (const float*)(b + o_pts), c, max_dist, with_sign, (uint8_t*)(b + o_res),
@@ -879,6 +895,7 @@ static int point_host(uint64_t id, const float* points, int64_t n, float max_dis
         ok = ok && check(cudaMemcpyAsync(face + base, b + o_face, 4 * c, cudaMemcpyDeviceToHost, l.stream), "d2h");
         ok = ok && check(cudaMemcpyAsync(u + base, b + o_u, 4 * c, cudaMemcpyDeviceToHost, l.stream), "d2h");
         ok = ok && check(cudaMemcpyAsync(v + base, b + o_v, 4 * c, cudaMemcpyDeviceToHost, l.stream), "d2h");
+        base += c;
     }
     for (int k = 0; k < 2; ++k)
         if (g_lanes[dev][k].stream)
