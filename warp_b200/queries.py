@@ -139,8 +139,9 @@ def mesh_query_ray(mesh, starts, dirs, max_t: float, out: MeshQueryRay | None = 
             out = MeshQueryRay(empty(n, uint8, dev), empty(n, float32, dev), empty(n, int32, dev),
                                empty(n, float32, dev), empty(n, float32, dev), empty(n, float32, dev),
                                empty(n, vec3, dev))  # fmt: skip
+        r = _roots(roots, n, dev)
         ok = c.wp_b200_mesh_query_ray(id_, _p(s), _p(d), n, max_t, _p(out.result), _p(out.sign), _p(out.face),
-                                      _p(out.t), _p(out.u), _p(out.v), _p(out.normal), _roots(roots, n, dev))  # fmt: skip
+                                      _p(out.t), _p(out.u), _p(out.v), _p(out.normal), _p(r) if r is not None else None)  # fmt: skip
         _check(ok, "mesh_query_ray")
         return out
     if roots is not None:
@@ -160,15 +161,16 @@ def mesh_query_ray(mesh, starts, dirs, max_t: float, out: MeshQueryRay | None = 
 
 
 def _roots(roots, n, dev):
-    """ctypes pointer to an optional per-query int32 roots array (host arrays are uploaded)."""
+    """Optional per-query int32 roots as a device array (host arrays are uploaded); the caller holds the result
+    until the native call has returned -- freeing a device array synchronises, so an upload cannot vanish under
+    a kernel that is still reading it."""
     if roots is None:
         return None
     if not isinstance(roots, array):
         roots = from_numpy(np.ascontiguousarray(roots, dtype=np.int32), int32, dev)
     if roots.dtype != int32 or len(roots) != n:
         raise RuntimeError("roots should be an int32 array with one entry per ray")
-    _roots.keep = roots  # keep the upload alive until the (stream-ordered) call has been enqueued and used
-    return ctypes.c_void_p(roots.ptr or 0)
+    return roots
 
 
 def _stage(a, dtype, dev, what):
@@ -219,7 +221,9 @@ def mesh_query_ray_anyhit(mesh, starts, dirs, max_t: float, roots=None):
     Device arrays in -> device ``uint8`` array out; host arrays in -> numpy ``bool`` array out."""
     id_, dev, s, d, host = _ray_pair(mesh, starts, dirs)
     out = empty(len(s), uint8, dev)
-    ok = _lib.core().wp_b200_mesh_query_ray_anyhit(id_, _p(s), _p(d), len(s), float(max_t), _p(out), _roots(roots, len(s), dev))
+    r = _roots(roots, len(s), dev)
+    ok = _lib.core().wp_b200_mesh_query_ray_anyhit(id_, _p(s), _p(d), len(s), float(max_t), _p(out),
+                                                   _p(r) if r is not None else None)  # fmt: skip
     _check(ok, "mesh_query_ray_anyhit")
     return out.numpy().astype(bool) if host else out
 
@@ -228,7 +232,9 @@ def mesh_query_ray_count_intersections(mesh, starts, dirs, roots=None):
     """Number of triangles hit by ray i with ``t >= 0``, over the whole ray (mesh.h:1976-2032)."""
     id_, dev, s, d, host = _ray_pair(mesh, starts, dirs)
     out = empty(len(s), int32, dev)
-    ok = _lib.core().wp_b200_mesh_query_ray_count_intersections(id_, _p(s), _p(d), len(s), _p(out), _roots(roots, len(s), dev))
+    r = _roots(roots, len(s), dev)
+    ok = _lib.core().wp_b200_mesh_query_ray_count_intersections(id_, _p(s), _p(d), len(s), _p(out),
+                                                                _p(r) if r is not None else None)  # fmt: skip
     _check(ok, "mesh_query_ray_count_intersections")
     return out.numpy() if host else out
 
