@@ -41,6 +41,12 @@ MAX_DIST = 1.0e6
 WORKLOAD = "C2: LBVH of 1.31M-triangle noisy icosphere; 16.8M mesh_query_point_no_sign queries in 1.2x AABB per GPU"
 
 
+# pieces of the pipelined gather at N > 1 (distributed.sharded_query_point_no_sign(parts=)).  Measured at 2 GPUs:
+# 1 piece 24.9 ms/step, 4 pieces 32.6 ms -- a quarter-size batch is Morton-sorted on its own and is sparser than the
+# whole batch, which costs more than the 0.7 ms (2 GPUs) / 2.7 ms (8 GPUs) of gather it hides.  So: one piece.
+GATHER_PARTS = int(os.environ.get("BENCH_GATHER_PARTS", "1"))
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -260,7 +266,9 @@ def main():
 
     def step():
         # one launch of k_query_point (+ 4 NCCL all-gathers when sharded)
-        distributed.sharded_query_point_no_sign(mesh, q_dev, plan, MAX_DIST, comm, rank, local_out=out, global_out=gathered)
+        # sharded: the shard is answered in GATHER_PARTS pieces, the gather of a piece runs under the next piece's traversal
+        distributed.sharded_query_point_no_sign(mesh, q_dev, plan, MAX_DIST, comm, rank, local_out=out, global_out=gathered,
+                                                parts=GATHER_PARTS if comm is not None else 1)
 
     def l2_flush():
         core.wp_memset_device(None, ctypes.c_void_p(flush.ptr), 0, flush.nbytes, stream)
@@ -348,10 +356,11 @@ def main():
         "config": {"workload": WORKLOAD, "triangles": T, "queries_per_gpu": nq, "leaf_size": 4, "max_dist": MAX_DIST,
                    "l2": "256 MB memset between timed steps; query inputs (201 MB) + outputs (218 MB) exceed the 126 MB L2; "
                          "the tree is meant to stay L2-resident",
-                   "gather": "ncclAllGather of result/face/u/v inside the step" if comm else "none (1 GPU)"},
+                   "gather": ("ncclAllGather of result/face/u/v inside the step" if GATHER_PARTS == 1 else
+                              f"result/face/u/v gathered inside the step, pipelined in {GATHER_PARTS} pieces") if comm else "none (1 GPU)"},
         "clocks": clocks.summary(), "e2e": e2e,
         # per step: Morton ordering of the batch (k_scene_bounds, k_morton_hist, 4 x k_onesweep_pass) + k_query_point
-        "gpu_launches": args.steps * 7, "roofline": roofline,
+        "gpu_launches": args.steps * 7 * (GATHER_PARTS if comm is not None else 1), "roofline": roofline,
         "wall_ms_timed_region": wall_ms, "extra": extra,
     }  # fmt: skip
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

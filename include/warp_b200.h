@@ -290,6 +290,13 @@ WP_B200_API int wp_b200_nccl_load(const char* libnccl_path);       /* NULL = def
 WP_B200_API int wp_b200_nccl_unique_id(void* id128);               /* rank 0: fills 128 bytes */
 WP_B200_API int wp_b200_nccl_init(const void* id128, int world_size, int rank);
 WP_B200_API int wp_b200_nccl_allgather(const void* send, void* recv, size_t bytes_per_rank); /* device ptrs */
+/* pipelined gather of one part of every shard into the rank-major result, on the library's communication stream:
+ * recv + r * shard_stride_bytes + offset_bytes <- rank r's `send` (part_bytes); fork = the communication stream waits
+ * for the current stream (the part's query), join = the current stream waits for the communication stream */
+WP_B200_API int wp_b200_nccl_allgather_part(const void* send, void* recv, size_t part_bytes, size_t shard_stride_bytes,
+                                            size_t offset_bytes);
+WP_B200_API int wp_b200_nccl_fork(void);
+WP_B200_API int wp_b200_nccl_join(void);
 WP_B200_API int wp_b200_nccl_allreduce_max_f32(float* inout_device, size_t count);
 WP_B200_API int wp_b200_nccl_barrier(void);
 WP_B200_API void wp_b200_nccl_destroy(void);

@@ -34,7 +34,7 @@ import torch.distributed as dist
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
 import oracle
 from warp_b200 import meshgen as mg
-from warp_b200.distributed import ShardPlan, GlooCommunicator, gather_fields, exchange_unique_id
+from warp_b200.distributed import ShardPlan, GlooCommunicator, gather_fields, exchange_unique_id, part_ranges, FIELD_BYTES
 rank = dist.get_rank()
 comm = GlooCommunicator()
 P, I = mg.noisy_sphere(2, 0.05, 11)
@@ -50,6 +50,17 @@ glob = gather_fields(local, plan, comm, lambda name, count: np.zeros(count, dt[n
 want = oracle.query_point_no_sign(P, I, tree, Q, 1e6)
 for k in local:
     assert np.array_equal(glob[k][: plan.n], want[k]), (rank, k)
+# pipelined gather: the shard goes out in pieces, each placed at its offset inside every rank's slot
+for parts in (2, 3, 7):
+    pg = {{k: np.zeros(plan.padded, dt[k]) for k in local}}
+    pieces = part_ranges(plan.shard, parts)
+    assert pieces[0][0] == 0 and pieces[-1][1] == plan.shard and all(x[1] == y[0] for x, y in zip(pieces, pieces[1:]))
+    for a, b in pieces:
+        for k in local:
+            w = FIELD_BYTES[k]
+            comm.allgather_part(local[k][a:b], pg[k], w * (b - a), w * plan.shard, w * a)
+    for k in local:
+        assert np.array_equal(pg[k][: plan.n], want[k]), (rank, parts, k)
 # rays: seven fields incl. the 12-byte normals (what sharded_query_ray gathers on GPUs)
 S, D = mg.random_rays(P, 777, seed=6)
 rplan = ShardPlan(S.shape[0], 2)

@@ -131,6 +131,9 @@ SIGNATURES = {
     "wp_b200_nccl_unique_id": (_i, [_vp]),
     "wp_b200_nccl_init": (_i, [_vp, _i, _i]),
     "wp_b200_nccl_allgather": (_i, [_vp, _vp, _sz]),
+    "wp_b200_nccl_allgather_part": (_i, [_vp, _vp, _sz, _sz, _sz]),
+    "wp_b200_nccl_fork": (_i, []),
+    "wp_b200_nccl_join": (_i, []),
     "wp_b200_nccl_allreduce_max_f32": (_i, [_vp, _sz]),
     "wp_b200_nccl_barrier": (_i, []),
     "wp_b200_nccl_destroy": (None, []),

@@ -21,6 +21,9 @@ typedef int (*fn_comm_destroy)(NcclComm);
 typedef int (*fn_all_gather)(const void*, void*, size_t, int, NcclComm, cudaStream_t);
 typedef int (*fn_all_reduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t);
 typedef const char* (*fn_error_string)(int);
+typedef int (*fn_send)(const void*, size_t, int, int, NcclComm, cudaStream_t);
+typedef int (*fn_recv)(void*, size_t, int, int, NcclComm, cudaStream_t);
+typedef int (*fn_group)(void);
 
 constexpr int kNcclInt8 = 0, kNcclFloat32 = 7, kNcclMax = 2;
 
@@ -31,7 +34,12 @@ fn_comm_destroy p_comm_destroy = nullptr;
 fn_all_gather p_all_gather = nullptr;
 fn_all_reduce p_all_reduce = nullptr;
 fn_error_string p_error_string = nullptr;
+fn_send p_send = nullptr;
+fn_recv p_recv = nullptr;
+fn_group p_group_start = nullptr, p_group_end = nullptr;
 NcclComm g_comm = nullptr;
+int g_world = 0;
+cudaEvent_t g_fork_event = nullptr, g_join_event = nullptr;
 cudaStream_t g_comm_stream = nullptr;
 char g_nccl_error[512] = "";
 
@@ -62,6 +70,10 @@ int wp_b200_nccl_load(const char* path)
     p_all_gather = (fn_all_gather)dlsym(g_lib, "ncclAllGather");
     p_all_reduce = (fn_all_reduce)dlsym(g_lib, "ncclAllReduce");
     p_error_string = (fn_error_string)dlsym(g_lib, "ncclGetErrorString");
+    p_send = (fn_send)dlsym(g_lib, "ncclSend");
+    p_recv = (fn_recv)dlsym(g_lib, "ncclRecv");
+    p_group_start = (fn_group)dlsym(g_lib, "ncclGroupStart");
+    p_group_end = (fn_group)dlsym(g_lib, "ncclGroupEnd");
     if (!p_get_unique_id || !p_comm_init_rank || !p_comm_destroy || !p_all_gather || !p_all_reduce) {
         snprintf(g_nccl_error, sizeof(g_nccl_error), "NCCL library lacks required symbols");
         return 0;
@@ -90,8 +102,13 @@ int wp_b200_nccl_init(const void* id128, int world_size, int rank)
     const int rc = p_comm_init_rank(&g_comm, world_size, id, rank);
     if (rc)
         return fail("ncclCommInitRank", rc);
+    g_world = world_size;
     if (!g_comm_stream)
         cudaStreamCreateWithFlags(&g_comm_stream, cudaStreamNonBlocking);
+    if (!g_fork_event) {
+        cudaEventCreateWithFlags(&g_fork_event, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&g_join_event, cudaEventDisableTiming);
+    }
     return 1;
 }
 
@@ -103,6 +120,46 @@ int wp_b200_nccl_allgather(const void* send, void* recv, size_t bytes_per_rank)
     cudaStream_t st = (cudaStream_t)wp_cuda_context_get_stream(nullptr);
     const int rc = p_all_gather(send, recv, bytes_per_rank, kNcclInt8, g_comm, st);
     return rc ? fail("ncclAllGather", rc) : 1;
+}
+
+// Pipelined gather: part [offset, offset + part_bytes) of every rank's shard goes to recv + r * shard_stride + offset
+// on every rank (the final rank-major layout, no staging), as one group of ncclSend / ncclRecv on the library's
+// COMMUNICATION stream, so that it runs under the traversal of the next part.  wp_b200_nccl_fork() makes the
+// communication stream wait for what has been enqueued on the current stream (the part's query), and
+// wp_b200_nccl_join() makes the current stream wait for the communication stream (end of the step).
+int wp_b200_nccl_allgather_part(const void* send, void* recv, size_t part_bytes, size_t shard_stride_bytes, size_t offset_bytes)
+{
+    if (!g_comm)
+        return fail("allgather_part (communicator not initialised)", 0);
+    if (!p_send || !p_recv || !p_group_start || !p_group_end)
+        return fail("allgather_part (ncclSend / ncclRecv not available)", 0);
+    if (part_bytes == 0)
+        return 1;
+    int rc = p_group_start();
+    for (int r = 0; r < g_world && !rc; ++r) {
+        rc = p_send(send, part_bytes, kNcclInt8, r, g_comm, g_comm_stream);
+        if (!rc)
+            rc = p_recv((char*)recv + (size_t)r * shard_stride_bytes + offset_bytes, part_bytes, kNcclInt8, r, g_comm,
+                        g_comm_stream);
+    }
+    const int rc2 = p_group_end();
+    return (rc || rc2) ? fail("ncclSend/ncclRecv group", rc ? rc : rc2) : 1;
+}
+
+int wp_b200_nccl_fork(void)
+{
+    if (!g_comm)
+        return fail("fork (communicator not initialised)", 0);
+    cudaStream_t st = (cudaStream_t)wp_cuda_context_get_stream(nullptr);
+    return cudaEventRecord(g_fork_event, st) == cudaSuccess && cudaStreamWaitEvent(g_comm_stream, g_fork_event, 0) == cudaSuccess;
+}
+
+int wp_b200_nccl_join(void)
+{
+    if (!g_comm)
+        return fail("join (communicator not initialised)", 0);
+    cudaStream_t st = (cudaStream_t)wp_cuda_context_get_stream(nullptr);
+    return cudaEventRecord(g_join_event, g_comm_stream) == cudaSuccess && cudaStreamWaitEvent(st, g_join_event, 0) == cudaSuccess;
 }
 
 int wp_b200_nccl_allreduce_max_f32(float* inout_device, size_t count)

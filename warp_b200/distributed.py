@@ -85,6 +85,20 @@ class NcclCommunicator:
         if not _lib.core().wp_b200_nccl_allgather(ctypes.c_void_p(send.ptr), ctypes.c_void_p(recv.ptr), nbytes_per_rank):
             raise RuntimeError("ncclAllGather failed")
 
+    def allgather_part(self, send_ptr: int, recv, part_bytes: int, shard_stride_bytes: int, offset_bytes: int):
+        """One part of every rank's shard into the rank-major ``recv``, on the communication stream."""
+        if not _lib.core().wp_b200_nccl_allgather_part(ctypes.c_void_p(send_ptr), ctypes.c_void_p(recv.ptr), part_bytes,
+                                                       shard_stride_bytes, offset_bytes):
+            raise RuntimeError("pipelined all-gather failed")
+
+    def fork(self):
+        if not _lib.core().wp_b200_nccl_fork():
+            raise RuntimeError("NCCL fork failed")
+
+    def join(self):
+        if not _lib.core().wp_b200_nccl_join():
+            raise RuntimeError("NCCL join failed")
+
     def allreduce_max(self, arr):
         if not _lib.core().wp_b200_nccl_allreduce_max_f32(ctypes.c_void_p(arr.ptr), arr.size):
             raise RuntimeError("ncclAllReduce failed")
@@ -188,15 +202,51 @@ def _sharded(local: dict, dtypes: dict, plan: ShardPlan, comm, dev, global_out):
     return gather_fields(local, plan, comm, lambda name, count: global_out[name]), plan.n
 
 
+def part_ranges(shard: int, parts: int):
+    """Contiguous sub-ranges of a shard for the pipelined gather: ``parts`` nearly equal pieces (fewer for tiny shards)."""
+    parts = max(1, min(int(parts), shard)) if shard > 0 else 1
+    step = -(-shard // parts)
+    return [(a, min(a + step, shard)) for a in range(0, max(shard, 1), max(step, 1)) if a < shard or shard == 0]
+
+
 def sharded_query_point_no_sign(mesh, local_points, plan: ShardPlan, max_dist: float, comm, rank: int,
-                                local_out=None, global_out=None):
+                                local_out=None, global_out=None, parts: int = 1):
     """Each rank answers its shard of a global batch; every rank ends up with all ``plan.n`` answers.
 
     ``local_points``: device array with ``plan.shard`` vec3 entries (entries past ``plan.count(rank)``
     are padding).  Returns ``(global_fields, n)``; fields are device arrays of ``plan.padded`` entries.
+    ``parts`` > 1 pipelines the step: the shard is answered in that many pieces and the gather of
+    piece k runs on the communication stream under the traversal of piece k + 1.
     """
-    from .queries import mesh_query_point_no_sign
-    from .types import float32, int32, uint8
+    from . import _lib
+    from .queries import MeshQueryPoint, mesh_query_point_no_sign
+    from .types import empty, float32, int32, uint8
+
+    if comm is not None and parts > 1 and hasattr(comm, "allgather_part") and plan.shard > 0:
+        import ctypes
+
+        dev = mesh.device
+        n = plan.shard
+        if local_out is None:
+            local_out = MeshQueryPoint(empty(n, uint8, dev), empty(n, float32, dev).zero_(), empty(n, int32, dev),
+                                       empty(n, float32, dev), empty(n, float32, dev))  # fmt: skip
+        dtypes = {"result": uint8, "face": int32, "u": float32, "v": float32}
+        if global_out is None:
+            global_out = {k: empty(plan.padded, dt, dev) for k, dt in dtypes.items()}
+        c = _lib.core()
+        vp = ctypes.c_void_p
+        for a, b in part_ranges(n, parts):
+            ok = c.wp_b200_mesh_query_point_no_sign(mesh.id, vp(local_points.ptr + 12 * a), b - a, float(max_dist),
+                                                    vp(local_out.result.ptr + a), vp(local_out.face.ptr + 4 * a),
+                                                    vp(local_out.u.ptr + 4 * a), vp(local_out.v.ptr + 4 * a))  # fmt: skip
+            if not ok:
+                raise RuntimeError(f"mesh_query_point_no_sign failed: {_lib.error_string()}")
+            comm.fork()  # the communication stream picks up after this piece's traversal
+            for name in dtypes:
+                w = FIELD_BYTES[name]
+                comm.allgather_part(getattr(local_out, name).ptr + w * a, global_out[name], w * (b - a), w * n, w * a)
+        comm.join()  # the step ends when the last piece has been gathered
+        return global_out, plan.n
 
     res = mesh_query_point_no_sign(mesh, local_points, max_dist, out=local_out)
     local = {"result": res.result, "face": res.face, "u": res.u, "v": res.v}
@@ -248,6 +298,24 @@ class GlooCommunicator:
         flat = recv.view(np.uint8).reshape(-1)
         for r, p in enumerate(parts):
             flat[r * nbytes_per_rank : (r + 1) * nbytes_per_rank] = p.numpy()
+
+    def allgather_part(self, send: np.ndarray, recv: np.ndarray, part_bytes: int, shard_stride_bytes: int, offset_bytes: int):
+        """CPU stand-in for NcclCommunicator.allgather_part (``send`` = the part itself, as a numpy view)."""
+        import torch
+
+        world = self.dist.get_world_size()
+        mine = torch.from_numpy(np.ascontiguousarray(send).view(np.uint8).reshape(-1)[:part_bytes].copy())
+        bufs = [torch.empty(part_bytes, dtype=torch.uint8) for _ in range(world)]
+        self.dist.all_gather(bufs, mine)
+        flat = recv.view(np.uint8).reshape(-1)
+        for r, b in enumerate(bufs):
+            flat[r * shard_stride_bytes + offset_bytes : r * shard_stride_bytes + offset_bytes + part_bytes] = b.numpy()
+
+    def fork(self):
+        pass
+
+    def join(self):
+        pass
 
     def barrier(self):
         self.dist.barrier()
