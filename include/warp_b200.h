@@ -176,6 +176,16 @@ WP_B200_API int wp_b200_mesh_query_point(uint64_t id, const float* points, int64
 WP_B200_API int wp_b200_mesh_query_point_sign_parity(uint64_t id, const float* points, int64_t n, float max_dist,
                                                      int n_sample, float perturbation_scale, uint8_t* result, float* sign,
                                                      int32_t* face, float* u, float* v);
+/* wp.mesh_query_point_sign_normal (mesh.h:860-1090): closest point on distances with a welding band of
+ * average_edge_length * epsilon (reference default epsilon = 1e-3); sign = +1 when the angle-weighted normal
+ * accumulated over the faces inside the band points towards the query, else -1.  The mesh's average edge length
+ * (mesh.cu:38-60, 299-307) is recomputed from the current points by every call and stored in the descriptor field
+ * wp::Mesh::average_edge_length. */
+WP_B200_API int wp_b200_mesh_query_point_sign_normal(uint64_t id, const float* points, int64_t n, float max_dist,
+                                                     float epsilon, uint8_t* result, float* sign, int32_t* face, float* u,
+                                                     float* v);
+/* Mesh.average_edge_length of the current points (synchronises the stream); returns 0 on an invalid id */
+WP_B200_API int wp_b200_mesh_average_edge_length(uint64_t id, float* out);
 /* wp.mesh_query_ray (mesh.h:1768-1891): normal is n x 3.  `roots` (optional, NULL = whole tree) restricts ray i to the
  * subtree of that node, as the reference's `root` argument does (e.g. a group root from wp_b200_bvh_get_group_root) */
 WP_B200_API int wp_b200_mesh_query_ray(uint64_t id, const float* starts, const float* dirs, int64_t n, float max_t,

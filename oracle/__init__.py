@@ -238,6 +238,29 @@ def query_point_sign_parity(points, indices, tree, queries, max_dist, n_sample=1
     return res
 
 
+def average_edge_length(points, indices, mode=1):
+    """Mesh.average_edge_length: mode 0 = the reference's CPU loop in float (mesh.cpp:140-155); mode 1 = the same
+    float terms (mesh.cu:53 order) summed in double, which is what the CUDA path of this repo computes."""
+    p = _f32(points, (-1, 3))
+    i = _i32(indices)
+    fn = orc().orc_average_edge_length
+    fn.restype = ctypes.c_float
+    return float(np.float32(fn(_p(p, _f32p), _p(i, _i32p), ctypes.c_int(i.size // 3), ctypes.c_int(mode))))
+
+
+def query_point_sign_normal(points, indices, tree, queries, max_dist, average_edge, epsilon=1e-3):
+    """mesh_query_point_sign_normal restatement (mesh.h:860-1090); ``average_edge`` = Mesh.average_edge_length."""
+    points, indices, targs = _tree_args(points, indices, tree)
+    q = _f32(queries, (-1, 3))
+    n = q.shape[0]
+    res = {"result": np.zeros(n, np.uint8), "sign": np.zeros(n, np.float32), "face": np.zeros(n, np.int32),
+           "u": np.zeros(n, np.float32), "v": np.zeros(n, np.float32)}  # fmt: skip
+    orc().orc_query_point_sign_normal(*targs, _p(q, _f32p), ctypes.c_int64(n), ctypes.c_float(max_dist),
+                                      ctypes.c_float(average_edge), ctypes.c_float(epsilon), _p(res["result"], _u8p),
+                                      _p(res["sign"], _f32p), _p(res["face"], _i32p), _p(res["u"], _f32p), _p(res["v"], _f32p))  # fmt: skip
+    return res
+
+
 def query_ray_anyhit(points, indices, tree, starts, dirs, max_t, roots=None):
     """mesh_query_ray_anyhit restatement (mesh.h:1893-1974)."""
     points, indices, targs = _tree_args(points, indices, tree)
@@ -400,6 +423,27 @@ class RefMesh:
                                           ctypes.c_int(n_sample), ctypes.c_float(scale), _p(res["result"], _u8p),
                                           _p(res["sign"], _f32p), _p(res["face"], _i32p), _p(res["u"], _f32p),
                                           _p(res["v"], _f32p), ctypes.c_int(nthreads))  # fmt: skip
+        return res
+
+    @property
+    def average_edge_length(self):
+        fn = ref().ref_mesh_get_average_edge_length
+        fn.restype = ctypes.c_float
+        return float(np.float32(fn(ctypes.c_uint64(self.id))))
+
+    @average_edge_length.setter
+    def average_edge_length(self, value):
+        ref().ref_mesh_set_average_edge_length(ctypes.c_uint64(self.id), ctypes.c_float(value))
+
+    def query_point_sign_normal(self, queries, max_dist, epsilon=1e-3, nthreads=1):
+        q = _f32(queries, (-1, 3))
+        n = q.shape[0]
+        res = {"result": np.zeros(n, np.uint8), "sign": np.zeros(n, np.float32), "face": np.zeros(n, np.int32),
+               "u": np.zeros(n, np.float32), "v": np.zeros(n, np.float32)}  # fmt: skip
+        ref().ref_query_point_sign_normal(ctypes.c_uint64(self.id), _p(q, _f32p), ctypes.c_int64(n), ctypes.c_float(max_dist),
+                                          ctypes.c_float(epsilon), _p(res["result"], _u8p), _p(res["sign"], _f32p),
+                                          _p(res["face"], _i32p), _p(res["u"], _f32p), _p(res["v"], _f32p),
+                                          ctypes.c_int(nthreads))  # fmt: skip
         return res
 
     def query_ray_anyhit(self, starts, dirs, max_t, nthreads=1, roots=None):

@@ -1077,3 +1077,150 @@ void orc_query_point_sign_parity(const float* points, const int* indices, const 
         sign[i] = (vote * 2 >= n_sample) ? -1.0f : 1.0f;
     }
 }
+
+/* mesh_query_point_sign_normal (mesh.h:860-1090): closest point on DISTANCES with an epsilon band
+ * eps = average_edge_length * epsilon; every triangle within eps of the running minimum adds
+ * weight * normalize(normal) (vertex: corner angle via acosf, edge: pi, interior: 2 pi); sign = +1 when the
+ * accumulated normal points towards the query.  average_edge_length is an INPUT here: the reference computes it
+ * with a float loop on the CPU (mesh.cpp:140-155, orc_average_edge_length mode 0) and with a CUB scan on the GPU
+ * (mesh.cu:38-60, 299-307); the CUDA path of this repo reduces the same float terms in double (mode 1). */
+float orc_average_edge_length(const float* points, const int* indices, int num_tris, int mode)
+{
+    float fsum = 0.0f;
+    double dsum = 0.0;
+    for (int t = 0; t < num_tris; ++t) {
+        const v3 p = v3_ld(points, indices[3 * t + 0]), q = v3_ld(points, indices[3 * t + 1]),
+                 r = v3_ld(points, indices[3 * t + 2]);
+        if (mode == 0) { /* mesh.cpp:153: length(p0 - p1) + length(p0 - p2) + length(p2 - p1) */
+            const v3 a = v3_sub(p, q), b = v3_sub(p, r), c = v3_sub(r, q);
+            fsum += sqrtf(v3_dot(a, a)) + sqrtf(v3_dot(b, b)) + sqrtf(v3_dot(c, c));
+        } else { /* mesh.cu:53: length(p - q) + length(p - r) + length(q - r) */
+            const v3 a = v3_sub(p, q), b = v3_sub(p, r), c = v3_sub(q, r);
+            dsum += (double)(sqrtf(v3_dot(a, a)) + sqrtf(v3_dot(b, b)) + sqrtf(v3_dot(c, c)));
+        }
+    }
+    if (mode == 0)
+        return fsum / (float)(num_tris * 3);
+    return (float)dsum / (float)(3 * num_tris);
+}
+
+static inline v3 v3_normalize(v3 a) /* vec.h:1111-1118, kEps = 0 */
+{
+    const float l = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z);
+    if (l > 0.0f)
+        return v3_make(a.x / l, a.y / l, a.z / l);
+    return v3_make(0.f, 0.f, 0.f);
+}
+
+static int point_sign_normal_one(const orc_mesh* m, v3 point, float max_dist, float eps, float* inside, int* face,
+                                 float* u, float* v)
+{
+    int stack[ORC_STACK];
+    int count = 1;
+    stack[0] = m->root;
+    float min_dist = max_dist;
+    int min_face = 0;
+    float min_v = 0.f, min_w = 0.f;
+    v3 acc = v3_make(0.f, 0.f, 0.f);
+    const float eps_sq = eps * eps;
+
+    while (count) {
+        const int node = stack[--count];
+        const orc_half lo = m->node_lowers[node], hi = m->node_uppers[node];
+        if (dist_aabb_sq(point, &lo, &hi) > (min_dist + eps) * (min_dist + eps))
+            continue;
+        const int li = HALF_I(lo), ri = HALF_I(hi);
+        if (HALF_B(lo)) {
+            for (int pc = li; pc < ri; ++pc) {
+                const int prim = m->primitive_indices[pc];
+                const v3 p = v3_ld(m->points, m->indices[3 * prim + 0]);
+                const v3 q = v3_ld(m->points, m->indices[3 * prim + 1]);
+                const v3 r = v3_ld(m->points, m->indices[3 * prim + 2]);
+                const v3 e0 = v3_sub(q, p), e1 = v3_sub(r, p), e2 = v3_sub(r, q);
+                const v3 nrm = v3_cross(e0, e1);
+                const float e0n = v3_dot(e0, e0), e1n = v3_dot(e1, e1), e2n = v3_dot(e2, e2);
+                if (sqrtf(nrm.x * nrm.x + nrm.y * nrm.y + nrm.z * nrm.z) / (e0n + e1n + e2n) < 1.e-6f)
+                    continue;
+                float uv[2];
+                orc_closest_point_to_triangle(&p.x, &q.x, &r.x, &point.x, uv);
+                const float bu = uv[0], bv = uv[1], bw = 1.f - bu - bv;
+                const v3 c = v3_add(v3_add(v3_scale(bu, p), v3_scale(bv, q)), v3_scale(bw, r));
+                const v3 d = v3_sub(c, point);
+                const float dist = sqrtf(v3_dot(d, d));
+                if (dist < min_dist + eps) {
+                    float weight;
+                    const v3 cp = v3_sub(c, p), cq = v3_sub(c, q), cr = v3_sub(c, r);
+                    const float lcp = v3_dot(cp, cp), lcq = v3_dot(cq, cq), lcr = v3_dot(cr, cr);
+                    const v3 ne0 = v3_make(-e0.x, -e0.y, -e0.z), ne1 = v3_make(-e1.x, -e1.y, -e1.z),
+                             ne2 = v3_make(-e2.x, -e2.y, -e2.z);
+                    if (lcp < eps_sq) {
+                        weight = acosf(v3_dot(v3_normalize(e0), v3_normalize(e1)));
+                    } else if (lcq < eps_sq) {
+                        weight = acosf(v3_dot(v3_normalize(e2), v3_normalize(ne0)));
+                    } else if (lcr < eps_sq) {
+                        weight = acosf(v3_dot(v3_normalize(ne1), v3_normalize(ne2)));
+                    } else {
+                        const float e0cp = v3_dot(e0, cp), e2cq = v3_dot(e2, cq), e1cp = v3_dot(e1, cp);
+                        if ((lcp * e0n - e0cp * e0cp < eps_sq * e0n) || (lcq * e2n - e2cq * e2cq < eps_sq * e2n)
+                            || (lcp * e1n - e1cp * e1cp < eps_sq * e1n))
+                            weight = 3.14159265359f;
+                        else
+                            weight = 2.0f * 3.14159265359f;
+                    }
+                    const v3 wn = v3_scale(weight, v3_normalize(nrm));
+                    if (dist > min_dist - eps) {
+                        acc = v3_add(acc, wn);
+                        if (dist < min_dist)
+                            min_dist = dist, min_v = bv, min_w = bw, min_face = prim;
+                    } else {
+                        min_dist = dist, min_v = bv, min_w = bw, min_face = prim;
+                        acc = wn;
+                    }
+                }
+            }
+        } else {
+            const orc_half llo = m->node_lowers[li], lhi = m->node_uppers[li];
+            const orc_half rlo = m->node_lowers[ri], rhi = m->node_uppers[ri];
+            const float dl = dist_aabb_sq(point, &llo, &lhi), dr = dist_aabb_sq(point, &rlo, &rhi);
+            int first, second;
+            float dfirst, dsecond;
+            if (dl < dr) {
+                first = ri, second = li, dfirst = dr, dsecond = dl;
+            } else {
+                first = li, second = ri, dfirst = dl, dsecond = dr;
+            }
+            if (dfirst < (min_dist + eps) * (min_dist + eps))
+                stack[count++] = first;
+            if (dsecond < (min_dist + eps) * (min_dist + eps))
+                stack[count++] = second;
+        }
+    }
+    if (min_dist < max_dist) {
+        *u = 1.0f - min_v - min_w;
+        *v = min_v;
+        *face = min_face;
+        const v3 p = v3_ld(m->points, m->indices[3 * min_face + 0]);
+        const v3 q = v3_ld(m->points, m->indices[3 * min_face + 1]);
+        const v3 r = v3_ld(m->points, m->indices[3 * min_face + 2]);
+        const v3 cpt = v3_add(v3_add(v3_scale(*u, p), v3_scale(*v, q)), v3_scale(min_w, r));
+        *inside = v3_dot(acc, v3_sub(point, cpt)) > 0.0f ? 1.0f : -1.0f;
+        return 1;
+    }
+    return 0;
+}
+
+void orc_query_point_sign_normal(const float* points, const int* indices, const orc_half* node_lowers,
+                                 const orc_half* node_uppers, const int* primitive_indices, int root, const float* queries,
+                                 int64_t n, float max_dist, float average_edge_length, float epsilon, uint8_t* result,
+                                 float* sign, int* face, float* u, float* v)
+{
+    const orc_mesh m = make_mesh(points, indices, node_lowers, node_uppers, primitive_indices, root);
+    const float eps = average_edge_length * epsilon;
+    for (int64_t i = 0; i < n; ++i) {
+        int f = 0;
+        float bu = 0.f, bv = 0.f, sg = 0.f;
+        const int ok = point_sign_normal_one(&m, v3_ld(queries, i), max_dist, eps, &sg, &f, &bu, &bv);
+        result[i] = (uint8_t)ok;
+        face[i] = ok ? f : 0, u[i] = ok ? bu : 0.f, v[i] = ok ? bv : 0.f, sign[i] = ok ? sg : 0.f;
+    }
+}

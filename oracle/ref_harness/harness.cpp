@@ -186,6 +186,27 @@ void ref_query_point_sign_parity(
     });
 }
 
+// mesh_query_point_sign_normal (mesh.h:860-1090).  The reference's host constructor fills average_edge_length
+// (mesh.cpp:140-155); a mesh wrapped around a caller's tree gets it through the setter below.
+float ref_mesh_get_average_edge_length(uint64_t id) { return ((Mesh*)id)->average_edge_length; }
+void ref_mesh_set_average_edge_length(uint64_t id, float v) { ((Mesh*)id)->average_edge_length = v; }
+
+void ref_query_point_sign_normal(
+    uint64_t id, const float* pts, int64_t n, float max_dist, float epsilon, uint8_t* result, float* sign, int* face,
+    float* u, float* v, int nthreads
+)
+{
+    parallel_for(n, nthreads, [&](int64_t i) {
+        mesh_query_point_t q
+            = mesh_query_point_sign_normal(id, vec3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), max_dist, epsilon);
+        result[i] = q.result ? 1 : 0;
+        sign[i] = q.sign;
+        face[i] = q.face;
+        u[i] = q.u;
+        v[i] = q.v;
+    });
+}
+
 void ref_query_ray(
     uint64_t id, const float* starts, const float* dirs, int64_t n, float max_t, uint8_t* result, float* sign,
     int* face, float* t, float* u, float* v, float* normal, int nthreads, const int* roots

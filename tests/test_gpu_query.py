@@ -404,6 +404,41 @@ def test_sign_parity(wp, oracle_mod):
     assert 0.05 < (a["sign"] < 0).mean() < 0.6
 
 
+def test_sign_normal(wp, oracle_mod):
+    """mesh_query_point_sign_normal: result / face / u / v bit-exact against the restatement (pinned on the reference
+    C++); the sign may differ only where CUDA's acosf and glibc's round a corner angle differently AND the accumulated
+    normal is perpendicular to the offset -- counted, and bounded at 0.1 %.  average_edge_length: float terms of
+    mesh.cu:53 summed in double."""
+    P, I = mg.noisy_sphere(4, 0.05, 53)
+    rng = np.random.default_rng(54)
+    T = I.reshape(-1, 3)
+    tri = T[rng.integers(0, len(T), 3000)]
+    Q = np.concatenate([mg.box_queries(P, 20000, seed=55), P[rng.integers(0, len(P), 3000)] + rng.normal(0, 1e-4, (3000, 3)),
+                        0.5 * (P[tri[:, 0]] + P[tri[:, 1]]), P[:2000]]).astype(np.float32)
+    m = gpu_mesh(wp, P, I, 4)
+    tree = oracle_mod.mesh_lbvh_build(P, I, 4)
+    avg = wp.mesh_average_edge_length(m)
+    assert np.float32(avg) == np.float32(oracle_mod.average_edge_length(P, I, mode=1))
+    fields = [f for f in POINT_FIELDS if f != "sign"]
+    for eps, md in ((1e-3, 1e6), (0.1, 1e6), (0.0, 1e6), (1e-3, 0.05)):
+        want = oracle_mod.query_point_sign_normal(P, I, tree, Q, md, avg, eps)
+        got = wp.mesh_query_point_sign_normal(m, Q, md, eps).numpy()
+        assert_results_equal(got, want, fields)
+        assert (got["sign"] != want["sign"]).mean() <= 1e-3
+        assert np.array_equal(got["sign"] == 0, want["result"] == 0)
+    # device arrays in -> device arrays out, unordered batch path (< 32768 queries) and the ordered one agree
+    a = wp.mesh_query_point_sign_normal(m, wp.array(Q[:1000], dtype=wp.vec3), 1e6).numpy()
+    b = wp.mesh_query_point_sign_normal(m, np.tile(Q[:1000], (40, 1)), 1e6).numpy()
+    assert all(np.array_equal(a[k], b[k][:1000]) for k in POINT_FIELDS)
+    # the average follows the points: refit after scaling the mesh by 2
+    pts = wp.array(P, dtype=wp.vec3)
+    m2 = wp.Mesh(pts, wp.array(I, dtype=wp.int32), bvh_constructor="lbvh")
+    pts.assign((2.0 * P).astype(np.float32))
+    m2.refit()
+    assert abs(wp.mesh_average_edge_length(m2) - 2.0 * avg) <= 1e-5 * avg
+    assert wp.mesh_query_point_sign_normal(m2, np.zeros((0, 3), np.float32), 1.0).numpy()["face"].shape == (0,)
+
+
 def test_rooted_mesh_rays(wp, oracle_mod):
     """mesh_query_ray / _anyhit / _count_intersections restricted to a group's subtree (`root` argument of the
     reference): fixture from the reference C++, then the oracle; group roots of a grouped MESH."""

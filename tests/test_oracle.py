@@ -439,6 +439,52 @@ def test_sign_parity_live_reference(oracle_mod):
                              rm.query_point_sign_parity(Q, 0.05, 1, 0.1), POINT_FIELDS)
 
 
+SIGNN_GOLD = os.path.join(os.path.dirname(__file__), "golden", "golden_sign_normal.npz")
+
+
+def test_sign_normal_restatement(oracle_mod, gold):
+    """mesh_query_point_sign_normal + Mesh.average_edge_length: fixture produced by the reference C++
+    (tests/golden/make_golden_sign_normal.py), SAH and LBVH trees, welding bands 1e-3 / 1e-1, near / far max_dist."""
+    o = oracle_mod
+    sn = np.load(SIGNN_GOLD)
+    P, I, Q = gold["mesh_points"], gold["mesh_indices"], sn["queries"]
+    avg = float(sn["average_edge_length"])
+    assert np.float32(o.average_edge_length(P, I, mode=0)) == np.float32(avg)  # the reference's float loop, bit for bit
+    assert abs(o.average_edge_length(P, I, mode=1) - avg) <= 1e-6 * avg       # double accumulation (the CUDA path's)
+    for name in ("sah", "lbvh1", "lbvh4"):
+        tree = {k: gold[f"{name}_tree_{k}"] for k in ("node_lowers", "node_uppers", "primitive_indices")}
+        tree["root"] = int(gold[f"{name}_tree_root"])
+        for tag, eps, md in (("e3", 1e-3, 1e6), ("e1", 1e-1, 1e6), ("e3near", 1e-3, 0.05)):
+            want = {k: sn[f"{name}_{tag}_{k}"] for k in POINT_FIELDS}
+            assert_results_equal(o.query_point_sign_normal(P, I, tree, Q, md, avg, eps), want, POINT_FIELDS)
+    s = sn["lbvh4_e3_sign"]
+    assert (s < 0).sum() > 50 and (s > 0).sum() > 50
+    # closed mesh: away from the welding band the normal sign is the ray-vote sign of mesh_query_point
+    box = o.query_point(P, I, tree, Q[:600], 1e6)
+    assert (box["sign"] == sn["lbvh4_e3_sign"][:600]).mean() > 0.99
+
+
+def test_sign_normal_live_reference(oracle_mod):
+    o = oracle_mod
+    if not o.ref_available():
+        pytest.skip("oracle/_ref/libwarp_ref_cpu.so not present")
+    P, I = mg.noisy_sphere(3, noise=0.1, seed=17)
+    rng = np.random.default_rng(18)
+    T = I.reshape(-1, 3)
+    tri = T[rng.integers(0, len(T), 500)]
+    Q = np.concatenate([mg.box_queries(P, 2000, seed=19), P[rng.integers(0, len(P), 500)] + rng.normal(0, 1e-4, (500, 3)),
+                        0.5 * (P[tri[:, 0]] + P[tri[:, 2]]), P[:300]]).astype(np.float32)
+    rm = o.RefMesh(P, I)
+    avg = rm.average_edge_length
+    assert np.float32(avg) == np.float32(o.average_edge_length(P, I, mode=0))
+    tree = o.mesh_lbvh_build(P, I, 4)
+    rl = o.RefMesh.from_tree(P, I, tree)
+    rl.average_edge_length = avg
+    for eps, md in ((1e-3, 1e6), (0.2, 1e6), (0.0, 1e6), (1e-3, 0.05)):
+        assert_results_equal(o.query_point_sign_normal(P, I, tree, Q, md, avg, eps), rl.query_point_sign_normal(Q, md, eps),
+                             POINT_FIELDS)
+
+
 def _grouped_mesh_case():
     P, I = mg.noisy_sphere(3, noise=0.05, seed=61)
     T = len(I) // 3

@@ -45,6 +45,8 @@ from .queries import (  # noqa: F401
     mesh_query_point,
     mesh_query_point_no_sign,
     mesh_query_point_sign_parity,
+    mesh_query_point_sign_normal,
+    mesh_average_edge_length,
     mesh_eval_position,
     mesh_eval_velocity,
     mesh_query_ray,

@@ -96,6 +96,8 @@ SIGNATURES = {
     "wp_b200_mesh_query_point_no_sign": (_i, [_u64, _vp, _i64, _f, _vp, _vp, _vp, _vp]),
     "wp_b200_mesh_query_point": (_i, [_u64, _vp, _i64, _f, _vp, _vp, _vp, _vp, _vp]),
     "wp_b200_mesh_query_point_sign_parity": (_i, [_u64, _vp, _i64, _f, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    "wp_b200_mesh_query_point_sign_normal": (_i, [_u64, _vp, _i64, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    "wp_b200_mesh_average_edge_length": (_i, [_u64, _vp]),
     "wp_b200_mesh_query_ray": (_i, [_u64, _vp, _vp, _i64, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wp_b200_mesh_query_ray_anyhit": (_i, [_u64, _vp, _vp, _i64, _f, _vp, _vp]),
     "wp_b200_mesh_query_ray_count_intersections": (_i, [_u64, _vp, _vp, _i64, _vp, _vp]),

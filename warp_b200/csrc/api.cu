@@ -771,6 +771,60 @@ int wp_b200_mesh_query_point_sign_parity(uint64_t id, const float* points, int64
     return 1;
 }
 
+int wp_b200_mesh_query_point_sign_normal(uint64_t id, const float* points, int64_t n, float max_dist, float epsilon,
+                                         uint8_t* result, float* sign, int32_t* face, float* u, float* v)
+{
+    MeshState* m = query_mesh(id);
+    if (!m)
+        return 0;
+    DeviceGuard g(m->bvh.device);
+    cudaStream_t st = current_stream(m->bvh.device);
+    if (n <= 0)
+        return 1;
+    if (m->bvh.n == 0)
+        return zero_point_outputs(n, result, sign, face, u, v, st);
+    const int* perm = nullptr;
+    if ((g_query_order == 1 || (g_query_order == 2 && n >= 32768)) && n < (1ll << 30)) {
+        OrderScratch& ws = g_order[m->bvh.device][0];
+        const char* oerr = wb_morton_order(ws, points, n, st);
+        if (oerr) {
+            set_error("Warp error: query ordering failed: %s", oerr);
+            return 0;
+        }
+        perm = ws.idx;
+    }
+    float* avg = &((wp_b200_mesh_desc*)m->dev_desc)->average_edge_length;
+    const char* err = wb_query_point_sign_normal(make_view(m->bvh), m->bvh.points, m->bvh.indices, points, perm, n, max_dist,
+                                                 epsilon, (double*)m->bvh.partials, avg, result, sign, face, u, v, st);
+    if (err) {
+        set_error("Warp error: mesh normal-sign query failed: %s", err);
+        return 0;
+    }
+    return 1;
+}
+
+int wp_b200_mesh_average_edge_length(uint64_t id, float* out)
+{
+    MeshState* m = query_mesh(id);
+    if (!m)
+        return 0;
+    DeviceGuard g(m->bvh.device);
+    cudaStream_t st = current_stream(m->bvh.device);
+    float* avg = &((wp_b200_mesh_desc*)m->dev_desc)->average_edge_length;
+    *out = 0.0f;
+    if (m->bvh.n == 0)
+        return 1;
+    const char* err = wb_query_point_sign_normal(make_view(m->bvh), m->bvh.points, m->bvh.indices, nullptr, nullptr, 0, 0.f,
+                                                 0.f, (double*)m->bvh.partials, avg, nullptr, nullptr, nullptr, nullptr,
+                                                 nullptr, st);
+    if (err) {
+        set_error("Warp error: average edge length failed: %s", err);
+        return 0;
+    }
+    return check(cudaMemcpyAsync(out, avg, sizeof(float), cudaMemcpyDeviceToHost, st), "memcpy")
+        && check(cudaStreamSynchronize(st), "synchronize");
+}
+
 int wp_b200_mesh_query_ray(uint64_t id, const float* starts, const float* dirs, int64_t n, float max_t, uint8_t* result,
                            float* sign, int32_t* face, float* t, float* u, float* v, float* normal, const int32_t* roots)
 {

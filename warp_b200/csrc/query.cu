@@ -748,6 +748,177 @@ k_sign_parity(TreeView tv, const float* __restrict__ pts, long long nq, int n_sa
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// mesh_query_point_sign_normal (mesh.h:860-1090): closest point with an epsilon band -- every triangle whose distance
+// is within eps = average_edge_length * epsilon of the running minimum adds its angle-weighted normal (vertex: the
+// corner angle, edge: pi, interior: 2 pi); sign = +1 when the accumulated normal points towards the query.
+// Works on distances, not squared distances, like the reference.  The average edge length (mesh.cu:38-60) is reduced
+// in a fixed order (per-thread grid-stride sums in double, block tree, one finishing block), so it is run-to-run
+// deterministic; the reference sums the same float terms with a CUB scan (GPU) or a float loop (CPU).
+// ------------------------------------------------------------------------------------------------
+constexpr int EDGE_BLOCKS = 296;
+
+__global__ void __launch_bounds__(256)
+k_edge_partials(const float* __restrict__ points, const int* __restrict__ indices, int n, double* __restrict__ partials)
+{
+    __shared__ double sm[256];
+    double acc = 0.0;
+    for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < n; t += (long long)gridDim.x * 256) {
+        float3 p, q, r;
+        MeshSource { points, indices }.tri((int)t, p, q, r);
+        const float3 pq = wb_sub(p, q), pr = wb_sub(p, r), qr = wb_sub(q, r);
+        acc += (double)(sqrtf(wb_dot(pq, pq)) + sqrtf(wb_dot(pr, pr)) + sqrtf(wb_dot(qr, qr)));
+    }
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o)
+            sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        partials[blockIdx.x] = sm[0];
+}
+
+__global__ void k_edge_finish(const double* __restrict__ partials, int nb, int n, float* __restrict__ out)
+{
+    double total = 0.0;
+    for (int b = 0; b < nb; ++b)
+        total += partials[b];
+    *out = (float)total / (float)(3 * n);
+}
+
+__device__ __forceinline__ float3 normalize3(float3 a)  // vec.h:1111-1118 (kEps = 0)
+{
+    const float l = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z);
+    if (l > 0.0f)
+        return make_float3(a.x / l, a.y / l, a.z / l);
+    return make_float3(0.f, 0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(QT)
+k_query_point_sign_normal(TreeView tv, const float* __restrict__ pts, const int* __restrict__ perm, long long nq,
+                          float max_dist, float epsilon, const float* __restrict__ avg_edge, uint8_t* __restrict__ result,
+                          float* __restrict__ sign, int* __restrict__ face, float* __restrict__ u, float* __restrict__ v)
+{
+    const TreeHeader h = *tv.header;
+    const float eps = *avg_edge * epsilon;
+    const float eps_sq = eps * eps;
+    for (long long slot = (long long)blockIdx.x * QT + threadIdx.x; slot < nq; slot += (long long)gridDim.x * QT) {
+        const long long qi = perm ? (long long)__ldg(perm + slot) : slot;
+        const float3 point = make_float3(__ldg(pts + 3 * qi), __ldg(pts + 3 * qi + 1), __ldg(pts + 3 * qi + 2));
+
+        Entry stack[WB_QUERY_STACK];
+        float stack_d[WB_QUERY_STACK];
+        int top = 0;
+        float min_dist = max_dist;
+        int min_face = 0;
+        float min_v = 0.f, min_w = 0.f;
+        float3 min_p = make_float3(0.f, 0.f, 0.f), min_q = min_p, min_r = min_p;
+        float3 acc = make_float3(0.f, 0.f, 0.f);
+
+        Entry cur;
+        if (h.root_ref & WB_LEAF)
+            cur.a = WB_LEAF | 0u, cur.b = h.root_count;
+        else
+            cur.a = (h.root_ref & WB_IDX_MASK) - (uint32_t)tv.n, cur.b = 0;
+        float cur_d = dist_aabb_sq(point, make_float3(h.lx, h.ly, h.lz), make_float3(h.hx, h.hy, h.hz));
+        bool have = true;
+        for (;;) {
+            if (!have) {
+                if (top == 0)
+                    break;
+                --top;
+                cur = stack[top];
+                cur_d = stack_d[top];
+            }
+            have = false;
+            if (cur_d > (min_dist + eps) * (min_dist + eps))
+                continue;
+            if (cur.a & WB_LEAF) {
+                const uint32_t start = cur.a & WB_IDX_MASK;
+                for (uint32_t pos = start; pos < start + cur.b; ++pos) {
+                    const Tri t = load_tri(tv.tris, pos);
+                    if (t.flags & WB_TRI_SLIVER)
+                        continue;
+                    const float3 e0 = wb_sub(t.q, t.p), e1 = wb_sub(t.r, t.p), e2 = wb_sub(t.r, t.q);
+                    const float3 normal = wb_cross(e0, e1);
+                    const float e0n = wb_dot(e0, e0), e1n = wb_dot(e1, e1), e2n = wb_dot(e2, e2);
+                    float bv, bw;
+                    closest_vw(t.p, t.q, t.r, point, bv, bw);
+                    const float bu = 1.0f - bv - bw;
+                    const float w = 1.f - bu - bv;
+                    const float3 c = wb_add(wb_add(wb_scale(bu, t.p), wb_scale(bv, t.q)), wb_scale(w, t.r));
+                    const float3 d = wb_sub(c, point);
+                    const float dist = sqrtf(wb_dot(d, d));
+                    if (dist < min_dist + eps) {
+                        float weight;
+                        const float3 cp = wb_sub(c, t.p), cq = wb_sub(c, t.q), cr = wb_sub(c, t.r);
+                        const float lcp = wb_dot(cp, cp), lcq = wb_dot(cq, cq), lcr = wb_dot(cr, cr);
+                        const float3 neg_e0 = make_float3(-e0.x, -e0.y, -e0.z), neg_e1 = make_float3(-e1.x, -e1.y, -e1.z),
+                                     neg_e2 = make_float3(-e2.x, -e2.y, -e2.z);
+                        if (lcp < eps_sq) {
+                            weight = acosf(wb_dot(normalize3(e0), normalize3(e1)));
+                        } else if (lcq < eps_sq) {
+                            weight = acosf(wb_dot(normalize3(e2), normalize3(neg_e0)));
+                        } else if (lcr < eps_sq) {
+                            weight = acosf(wb_dot(normalize3(neg_e1), normalize3(neg_e2)));
+                        } else {
+                            const float e0cp = wb_dot(e0, cp), e2cq = wb_dot(e2, cq), e1cp = wb_dot(e1, cp);
+                            if ((lcp * e0n - e0cp * e0cp < eps_sq * e0n) || (lcq * e2n - e2cq * e2cq < eps_sq * e2n)
+                                || (lcp * e1n - e1cp * e1cp < eps_sq * e1n))
+                                weight = 3.14159265359f;
+                            else
+                                weight = 2.0f * 3.14159265359f;
+                        }
+                        const float3 wn = wb_scale(weight, normalize3(normal));
+                        if (dist > min_dist - eps) {  // treated as equal: accumulate
+                            acc = wb_add(acc, wn);
+                            if (dist < min_dist)
+                                min_dist = dist, min_v = bv, min_w = w, min_face = t.face, min_p = t.p, min_q = t.q, min_r = t.r;
+                        } else {
+                            min_dist = dist, min_v = bv, min_w = w, min_face = t.face, min_p = t.p, min_q = t.q, min_r = t.r;
+                            acc = wn;
+                        }
+                    }
+                }
+                continue;
+            }
+            const Pair pr = load_pair(tv.pairs, cur.a, tv.n);
+            const float dl = dist_aabb_sq(point, pr.llo, pr.lhi), dr = dist_aabb_sq(point, pr.rlo, pr.rhi);
+            Entry far_e, near_e;
+            float far_d, near_d;
+            if (dl < dr)
+                far_e = pr.right, far_d = dr, near_e = pr.left, near_d = dl;
+            else
+                far_e = pr.left, far_d = dl, near_e = pr.right, near_d = dr;
+            const float bound = (min_dist + eps) * (min_dist + eps);
+            if (far_d < bound) {
+                stack[top] = far_e;
+                stack_d[top] = far_d;
+                ++top;
+            }
+            if (near_d < bound) {
+                cur = near_e;
+                cur_d = near_d;
+                have = true;
+            }
+        }
+        const bool ok = min_dist < max_dist;
+        float bu = 0.f, sg = 0.f;
+        if (ok) {
+            bu = 1.0f - min_v - min_w;
+            const float3 cpt = wb_add(wb_add(wb_scale(bu, min_p), wb_scale(min_v, min_q)), wb_scale(min_w, min_r));
+            sg = wb_dot(acc, wb_sub(point, cpt)) > 0.0f ? 1.0f : -1.0f;
+        }
+        result[qi] = ok ? 1 : 0;
+        sign[qi] = sg;
+        face[qi] = ok ? min_face : 0;
+        u[qi] = bu;
+        v[qi] = ok ? min_v : 0.f;
+    }
+}
+
 // mesh_eval_position / mesh_eval_velocity (mesh.h:2767-2807): p*u + q*v + r*(1-u-v) from the caller's arrays
 __global__ void __launch_bounds__(QT)
 k_mesh_eval(const float* __restrict__ attr, const int* __restrict__ indices, const int* __restrict__ face,
@@ -854,6 +1025,21 @@ const char* wb_sign_parity(const TreeView& tv, const float* pts, long long nq, i
     if (nq <= 0)
         return nullptr;
     k_sign_parity<<<query_grid(nq), QT, 0, stream>>>(tv, pts, nq, n_sample, scale, result, sign);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+const char* wb_query_point_sign_normal(const TreeView& tv, const float* mesh_points, const int* mesh_indices,
+                                       const float* pts, const int* perm, long long nq, float max_dist, float epsilon,
+                                       double* partials, float* avg_edge, uint8_t* result, float* sign, int* face, float* u,
+                                       float* v, cudaStream_t stream)
+{
+    const int nb = tv.n < EDGE_BLOCKS * 256 ? (tv.n + 255) / 256 : EDGE_BLOCKS;
+    k_edge_partials<<<nb, 256, 0, stream>>>(mesh_points, mesh_indices, tv.n, partials);
+    k_edge_finish<<<1, 1, 0, stream>>>(partials, nb, tv.n, avg_edge);
+    if (nq > 0)
+        k_query_point_sign_normal<<<query_grid(nq), QT, 0, stream>>>(tv, pts, perm, nq, max_dist, epsilon, avg_edge, result, sign,
+                                                                face, u, v);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

@@ -29,6 +29,12 @@ const char* wb_query_ray_count(const TreeView& tv, const float* starts, const fl
                                int* counts, cudaStream_t stream);
 const char* wb_mesh_eval(const float* attr, const int* indices, const int* face, const float* u, const float* v,
                          long long n, float* out, cudaStream_t stream);
+// mesh_query_point_sign_normal (mesh.h:860-1090); partials: >= 296 doubles of scratch, avg_edge: device float that
+// receives Mesh.average_edge_length (recomputed from mesh_points / mesh_indices first).  nq == 0 only refreshes it.
+const char* wb_query_point_sign_normal(const TreeView& tv, const float* mesh_points, const int* mesh_indices,
+                                       const float* pts, const int* perm, long long nq, float max_dist, float epsilon,
+                                       double* partials, float* avg_edge, uint8_t* result, float* sign, int* face, float* u,
+                                       float* v, cudaStream_t stream);
 // sign of mesh_query_point_sign_parity (mesh.h:2362-2392) for the queries whose `result` is set; 0 elsewhere
 const char* wb_sign_parity(const TreeView& tv, const float* pts, long long nq, int n_sample, float scale,
                            const uint8_t* result, float* sign, cudaStream_t stream);

@@ -205,6 +205,34 @@ def mesh_query_point_sign_parity(mesh, points, max_dist: float, n_sample: int = 
     return out
 
 
+def mesh_query_point_sign_normal(mesh, points, max_dist: float, epsilon: float = 1e-3):
+    """Closest point + inside/outside from angle-weighted normals (``mesh.h:860-1090``): faces whose distance is within
+    ``average_edge_length * epsilon`` of the minimum are welded, ``sign`` is +1 when their accumulated normal points
+    towards the query.  Device array in -> device arrays out; host array in -> numpy arrays out."""
+    id_, dev = _mesh_id(mesh)
+    pts, host = _stage(points, vec3, dev, "points")
+    n = len(pts)
+    out = MeshQueryPoint(empty(n, uint8, dev), empty(n, float32, dev), empty(n, int32, dev), empty(n, float32, dev),
+                         empty(n, float32, dev))  # fmt: skip
+    ok = _lib.core().wp_b200_mesh_query_point_sign_normal(id_, _p(pts), n, float(max_dist), float(epsilon), _p(out.result),
+                                                          _p(out.sign), _p(out.face), _p(out.u), _p(out.v))  # fmt: skip
+    _check(ok, "mesh_query_point_sign_normal")
+    if host:
+        return MeshQueryPoint(*(getattr(out, k).numpy() for k in MeshQueryPoint.__slots__))
+    return out
+
+
+def mesh_average_edge_length(mesh) -> float:
+    """``Mesh.average_edge_length`` of the current points (``mesh.cu:38-60``), the welding scale of
+    :func:`mesh_query_point_sign_normal`."""
+    import ctypes
+
+    id_, _ = _mesh_id(mesh)
+    v = ctypes.c_float(0.0)
+    _check(_lib.core().wp_b200_mesh_average_edge_length(id_, ctypes.byref(v)), "mesh_average_edge_length")
+    return float(np.float32(v.value))
+
+
 def _ray_pair(mesh, starts, dirs):
     id_, dev = _mesh_id(mesh)
     if isinstance(starts, array) != isinstance(dirs, array):
