@@ -530,48 +530,91 @@ __device__ __forceinline__ bool depth_marked(const KeyT* __restrict__ keys, cons
     return node_single_group<KeyT, GROUPED>(keys, pairs, s) && depth_capped(parent_int, n, n + s) >= WB_MAX_DEPTH;
 }
 
-// pass A (one thread per sorted position): visible size-leaves whose parent got marked lose their entry
-template <class KeyT, bool GROUPED>
-__global__ void __launch_bounds__(BT)
-k_deep_fix_positions(int n, TreeHeader* hdr, const KeyT* __restrict__ keys, const NodeRec* __restrict__ pairs,
-                     const int* __restrict__ parent_int, int* pos_parent)
+// The reference walks the whole parent chain of every node (bvh.cu:402-443): ~32 dependent loads per node, which at
+// 10 M items costs as much as the sort.  Here depths are memoised in a byte per internal node (0 = unknown, else the
+// depth capped at WB_MAX_DEPTH + 1): k_deep_top initialises the table and walks the chains of the few nodes whose
+// subtree is at least DEEP_TOP_HEIGHT tall; every other walk (k_deep_fix) stops at the first ancestor whose depth is
+// known -- a tall node is at most DEEP_TOP_HEIGHT hops away -- and records its own result for the walks below it.
+// Racing readers see either 0 or the final value, so the outcome does not depend on timing.
+constexpr int DEEP_TOP_HEIGHT = 6;
+
+__device__ __forceinline__ int depth_memo(const int* __restrict__ parent_int, const uint8_t* memo, int n, int slot)
 {
-    if (hdr->height + 1 < WB_MAX_DEPTH)
-        return;
-    const int i = blockIdx.x * BT + threadIdx.x;
-    if (i >= n)
-        return;
-    const int p = pos_parent[i];
-    if (p < 0)
-        return;
-    if (depth_marked<KeyT, GROUPED>(keys, pairs, parent_int, n, p - n))
-        pos_parent[i] = WB_NO_PARENT;
+    int hops = 0;
+    int a = slot;
+    for (;;) {
+        const int p = parent_int[a];
+        if (p == WB_NO_PARENT)
+            return hops + 1;  // `a` is the root (depth 1)
+        a = p - n;
+        ++hops;
+        if (memo) {
+            const int d = (int)__ldcg(memo + a);
+            if (d)
+                return min(d + hops, WB_MAX_DEPTH + 1);
+        }
+        if (hops >= WB_MAX_DEPTH)
+            return WB_MAX_DEPTH + 1;
+    }
 }
 
-// pass B (one thread per internal node): depth-marked nodes whose parent is not marked become visible leaves
-template <class KeyT, bool GROUPED>
 __global__ void __launch_bounds__(BT)
-k_deep_fix_nodes(int n, int leaf_size, TreeHeader* hdr, const KeyT* __restrict__ keys, const int* __restrict__ parent_int,
-                 NodeRec* pairs, int* pos_parent)
+k_deep_top(int n, const TreeHeader* __restrict__ hdr, const int* __restrict__ parent_int,
+           const uint16_t* __restrict__ heights, uint8_t* __restrict__ memo)
 {
     if (hdr->height + 1 < WB_MAX_DEPTH)
         return;
     const int s = blockIdx.x * BT + threadIdx.x;
     if (s >= n - 1)
         return;
-    const int left = (int)pairs[2 * (size_t)s].aux, right = (int)pairs[2 * (size_t)s + 1].aux;
-    if (wb_size_leaf<KeyT, GROUPED>(keys, leaf_size, left, right))
-        return;  // already a leaf (or below one) by the size rule
-    if (!depth_marked<KeyT, GROUPED>(keys, pairs, parent_int, n, s))
+    memo[s] = heights[s] >= DEEP_TOP_HEIGHT ? (uint8_t)depth_memo(parent_int, nullptr, n, s) : (uint8_t)0;
+}
+
+// one thread per sorted position, two roles.  Node role (internal slot s = thread index): a depth-marked node whose
+// parent is not marked becomes a visible leaf.  Position role: a visible size-leaf whose parent got marked loses its
+// entry -- with a compare-and-swap, so that a new entry written by the node role for the same position survives.
+template <class KeyT, bool GROUPED>
+__global__ void __launch_bounds__(BT)
+k_deep_fix(int n, int leaf_size, TreeHeader* hdr, const KeyT* __restrict__ keys, const int* __restrict__ parent_int,
+           uint8_t* memo, NodeRec* pairs, int* pos_parent)
+{
+    if (hdr->height + 1 < WB_MAX_DEPTH)
         return;
-    const int parent = parent_int[s];  // depth >= 32 => it has a parent
-    const int ps = parent - n;
-    if (depth_marked<KeyT, GROUPED>(keys, pairs, parent_int, n, ps))
-        return;  // muted below another depth leaf
-    NodeRec* rec = pairs + 2 * (size_t)ps + (s < ps ? 0 : 1);
-    rec->ref |= WB_LEAF;
-    pos_parent[left] = parent;
-    hdr->deep = 1;
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= n)
+        return;
+    if (i < n - 1) {
+        const int s = i;
+        const int left = (int)pairs[2 * (size_t)s].aux, right = (int)pairs[2 * (size_t)s + 1].aux;
+        // size leaves (and everything below them) are settled already
+        if (!wb_size_leaf<KeyT, GROUPED>(keys, leaf_size, left, right)) {
+            int depth = (int)__ldcg(memo + s);
+            if (depth == 0) {
+                depth = depth_memo(parent_int, memo, n, s);
+                memo[s] = (uint8_t)depth;
+            }
+            if (depth >= WB_MAX_DEPTH && node_single_group<KeyT, GROUPED>(keys, pairs, s)) {
+                const int parent = parent_int[s];  // depth >= 32 => it has a parent
+                const int ps = parent - n;
+                // the parent sits one level up: when it is marked too, this node is muted below it
+                if (!(depth - 1 >= WB_MAX_DEPTH && node_single_group<KeyT, GROUPED>(keys, pairs, ps))) {
+                    NodeRec* rec = pairs + 2 * (size_t)ps + (s < ps ? 0 : 1);
+                    rec->ref |= WB_LEAF;
+                    pos_parent[left] = parent;
+                    hdr->deep = 1;
+                }
+            }
+        }
+    }
+    const int p = *(volatile int*)(pos_parent + i);
+    if (p >= 0) {
+        const int ps = p - n;
+        int depth = (int)__ldcg(memo + ps);
+        if (depth == 0)
+            depth = depth_memo(parent_int, memo, n, ps);
+        if (depth >= WB_MAX_DEPTH && node_single_group<KeyT, GROUPED>(keys, pairs, ps))
+            atomicCAS(pos_parent + i, p, WB_NO_PARENT);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -718,11 +761,11 @@ template <class Src, class KeyT, bool GROUPED> const char* build_impl(BvhState& 
         s.plan_valid = false;
         k_merge<false, KeyT, GROUPED><<<wb_div_up(n, BP), TBM, 0, stream>>>(ma);
     }
-    // K5/K6 depth rule (early-out unless the tree is at least 32 levels deep)
-    k_deep_fix_positions<KeyT, GROUPED><<<wb_div_up(n, BT), BT, 0, stream>>>(n, s.header, keys, s.pairs, s.parent_int,
-                                                                            s.pos_parent);
-    k_deep_fix_nodes<KeyT, GROUPED><<<wb_div_up(n - 1, BT), BT, 0, stream>>>(n, s.leaf_size, s.header, keys, s.parent_int,
-                                                                            s.pairs, s.pos_parent);
+    // K5/K6 depth rule (early-out unless the tree is at least 32 levels deep); the depth table lives in the sort's
+    // spare value buffer, free until the next sort
+    k_deep_top<<<wb_div_up(n - 1, BT), BT, 0, stream>>>(n, s.header, s.parent_int, s.heights, (uint8_t*)s.prim_alt);
+    k_deep_fix<KeyT, GROUPED><<<wb_div_up(n, BT), BT, 0, stream>>>(n, s.leaf_size, s.header, keys, s.parent_int,
+                                                                  (uint8_t*)s.prim_alt, s.pairs, s.pos_parent);
     WB_CUDA_TRY(cudaGetLastError());
     return nullptr;
 }
