@@ -272,7 +272,10 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ITEMS_LARGE = 16;  // 4096-key tiles: fewer look-back words for big inputs
 constexpr int RS_ITEMS_SMALL = 8;   // 2048-key tiles: more resident warps while the input is small enough to be latency bound
-constexpr long long RS_SMALL_LIMIT = 1ll << 24;
+#ifndef WB_RS_SMALL_LIMIT
+#define WB_RS_SMALL_LIMIT (1ll << 24)
+#endif
+constexpr long long RS_SMALL_LIMIT = WB_RS_SMALL_LIMIT;
 // 64-bit keys always use the small tile (a 4096-key tile of 8-byte keys would not fit 48 KB of static shared memory)
 __host__ __device__ inline int rs_items_for(long long n, int key_bytes = 4)
 {
@@ -357,7 +360,10 @@ k_onesweep_pass(const KeyT* __restrict__ keys_in, const int* __restrict__ vals_i
         // walk back over the predecessors' words LB at a time: the loads of one batch are issued
         // back to back (one L2 round trip for the batch instead of one per tile), then consumed in
         // order; a word that is not published yet is re-polled in place
-        constexpr int LB = 16;
+#ifndef WB_RS_LB
+#define WB_RS_LB 4  // measured (1.3 M / 4 M / 10 M items, rebuild ms): 16: 0.367 / 0.88 / 2.05, 8: 0.356 / 0.85 / 1.97, 4: 0.350 / 0.83 / 1.95
+#endif
+        constexpr int LB = WB_RS_LB;
         bool found = false;
         for (int j = tile - 1; !found; j -= LB) {
             uint32_t v[LB];
