@@ -424,8 +424,16 @@ def test_sign_normal(wp, oracle_mod):
         want = oracle_mod.query_point_sign_normal(P, I, tree, Q, md, avg, eps)
         got = wp.mesh_query_point_sign_normal(m, Q, md, eps).numpy()
         assert_results_equal(got, want, fields)
+        print("sign_normal eps=%g max_dist=%g: %d sign differences vs the oracle" % (eps, md, int((got["sign"] != want["sign"]).sum())))
         assert (got["sign"] != want["sign"]).mean() <= 1e-3
         assert np.array_equal(got["sign"] == 0, want["result"] == 0)
+    # closed mesh: the normal sign is the ray-vote sign of mesh_query_point except next to the surface
+    # (test_mesh_query_point.py:320-570 asks the same of all sign methods)
+    votes = wp.mesh_query_point(m, Q[:20000], 1e6).numpy()
+    normal = wp.mesh_query_point_sign_normal(m, Q[:20000], 1e6).numpy()
+    assert (votes["face"] == normal["face"]).mean() > 0.99  # (faces may differ at shared edges: distances vs squared distances)
+    print("sign_normal vs ray votes: %d of 20000 differ" % int((votes["sign"] != normal["sign"]).sum()))
+    assert (votes["sign"] == normal["sign"]).mean() > 0.995
     # device arrays in -> device arrays out, unordered batch path (< 32768 queries) and the ordered one agree
     a = wp.mesh_query_point_sign_normal(m, wp.array(Q[:1000], dtype=wp.vec3), 1e6).numpy()
     b = wp.mesh_query_point_sign_normal(m, np.tile(Q[:1000], (40, 1)), 1e6).numpy()
