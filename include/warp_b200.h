@@ -204,6 +204,14 @@ WP_B200_API int wp_b200_mesh_eval_position(uint64_t id, const int32_t* face, con
 WP_B200_API int wp_b200_mesh_eval_velocity(uint64_t id, const int32_t* face, const float* u, const float* v,
                                            int64_t n, float* out);
 
+/* wp.mesh_eval_face_normal (mesh.h:2870-2888): out[i] = normalize(cross(q - p, r - p)) of triangle face[i], from the
+ * mesh's current points; out is n x 3 */
+WP_B200_API int wp_b200_mesh_eval_face_normal(uint64_t id, const int32_t* face, int64_t n, float* out);
+/* wp.mesh_query_furthest_point_no_sign (mesh.h:678-858): the farthest point of the mesh from each query (always a
+ * vertex: (u, v) is (1,0), (0,1) or (0,0)), result = 1 when it lies strictly beyond min_dist */
+WP_B200_API int wp_b200_mesh_query_furthest_point_no_sign(uint64_t id, const float* points, int64_t n, float min_dist,
+                                                          uint8_t* result, int32_t* face, float* u, float* v);
+
 /* the first three calls with HOST buffers: inputs are copied to the device, the query runs, results are
  * copied back, and the call returns after the results are valid (synchronous).  Work is chunked and
  * double-buffered through pinned staging so copies overlap traversal. */

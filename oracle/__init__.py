@@ -261,6 +261,27 @@ def query_point_sign_normal(points, indices, tree, queries, max_dist, average_ed
     return res
 
 
+def query_furthest_point_no_sign(points, indices, tree, queries, min_dist):
+    """mesh_query_furthest_point_no_sign restatement (mesh.h:678-858)."""
+    points, indices, targs = _tree_args(points, indices, tree)
+    q = _f32(queries, (-1, 3))
+    n = q.shape[0]
+    res = {"result": np.zeros(n, np.uint8), "face": np.zeros(n, np.int32), "u": np.zeros(n, np.float32),
+           "v": np.zeros(n, np.float32)}  # fmt: skip
+    orc().orc_query_furthest_point_no_sign(*targs, _p(q, _f32p), ctypes.c_int64(n), ctypes.c_float(min_dist),
+                                           _p(res["result"], _u8p), _p(res["face"], _i32p), _p(res["u"], _f32p),
+                                           _p(res["v"], _f32p))  # fmt: skip
+    return res
+
+
+def mesh_face_normal(points, indices, face):
+    """mesh_eval_face_normal restatement (mesh.h:2870-2888)."""
+    p, i, f = _f32(points, (-1, 3)), _i32(indices), _i32(face)
+    out = np.zeros((f.size, 3), np.float32)
+    orc().orc_mesh_face_normal(_p(p, _f32p), _p(i, _i32p), _p(f, _i32p), ctypes.c_int64(f.size), _p(out, _f32p))
+    return out
+
+
 def query_ray_anyhit(points, indices, tree, starts, dirs, max_t, roots=None):
     """mesh_query_ray_anyhit restatement (mesh.h:1893-1974)."""
     points, indices, targs = _tree_args(points, indices, tree)
@@ -445,6 +466,22 @@ class RefMesh:
                                           _p(res["face"], _i32p), _p(res["u"], _f32p), _p(res["v"], _f32p),
                                           ctypes.c_int(nthreads))  # fmt: skip
         return res
+
+    def query_furthest_point_no_sign(self, queries, min_dist, nthreads=1):
+        q = _f32(queries, (-1, 3))
+        n = q.shape[0]
+        res = {"result": np.zeros(n, np.uint8), "face": np.zeros(n, np.int32), "u": np.zeros(n, np.float32),
+               "v": np.zeros(n, np.float32)}  # fmt: skip
+        ref().ref_query_furthest_point_no_sign(ctypes.c_uint64(self.id), _p(q, _f32p), ctypes.c_int64(n),
+                                               ctypes.c_float(min_dist), _p(res["result"], _u8p), _p(res["face"], _i32p),
+                                               _p(res["u"], _f32p), _p(res["v"], _f32p), ctypes.c_int(nthreads))  # fmt: skip
+        return res
+
+    def eval_face_normal(self, face):
+        f = _i32(face)
+        out = np.zeros((f.size, 3), np.float32)
+        ref().ref_mesh_eval_face_normal(ctypes.c_uint64(self.id), _p(f, _i32p), ctypes.c_int64(f.size), _p(out, _f32p))
+        return out
 
     def query_ray_anyhit(self, starts, dirs, max_t, nthreads=1, roots=None):
         s, d = _f32(starts, (-1, 3)), _f32(dirs, (-1, 3))

@@ -1224,3 +1224,109 @@ void orc_query_point_sign_normal(const float* points, const int* indices, const 
         face[i] = ok ? f : 0, u[i] = ok ? bu : 0.f, v[i] = ok ? bv : 0.f, sign[i] = ok ? sg : 0.f;
     }
 }
+
+/* mesh_query_furthest_point_no_sign (mesh.h:678-858) with furthest_distance_to_aabb_sq (mesh.h:100-119) and
+ * furthest_point_to_triangle (intersect.h:111-125): farther child popped first, nodes culled when their farthest
+ * corner is nearer than the best so far, candidates are triangle vertices, strict '>' updates. */
+static inline float far_aabb_sq(v3 p, const orc_half* lo, const orc_half* hi)
+{
+    const float lx = fabsf(p.x - lo->x), ux = fabsf(p.x - hi->x), cx = (lx > ux) ? lx : ux;
+    const float ly = fabsf(p.y - lo->y), uy = fabsf(p.y - hi->y), cy = (ly > uy) ? ly : uy;
+    const float lz = fabsf(p.z - lo->z), uz = fabsf(p.z - hi->z), cz = (lz > uz) ? lz : uz;
+    return cx * cx + cy * cy + cz * cz;
+}
+
+static int point_furthest_one(const orc_mesh* m, v3 point, float min_dist, int* face, float* u, float* v)
+{
+    int stack[ORC_STACK];
+    int count = 1;
+    stack[0] = m->root;
+    float best = min_dist * min_dist;
+    int best_face = 0;
+    float best_v = 0.f, best_w = 0.f;
+    while (count) {
+        const int node = stack[--count];
+        const orc_half lo = m->node_lowers[node], hi = m->node_uppers[node];
+        if (far_aabb_sq(point, &lo, &hi) < best)
+            continue;
+        const int li = HALF_I(lo), ri = HALF_I(hi);
+        if (HALF_B(lo)) {
+            for (int pc = li; pc < ri; ++pc) {
+                const int prim = m->primitive_indices[pc];
+                const v3 p = v3_ld(m->points, m->indices[3 * prim + 0]);
+                const v3 q = v3_ld(m->points, m->indices[3 * prim + 1]);
+                const v3 r = v3_ld(m->points, m->indices[3 * prim + 2]);
+                const v3 e0 = v3_sub(q, p), e1 = v3_sub(r, p), e2 = v3_sub(r, q);
+                const v3 nrm = v3_cross(e0, e1);
+                if (sqrtf(nrm.x * nrm.x + nrm.y * nrm.y + nrm.z * nrm.z)
+                        / (v3_dot(e0, e0) + v3_dot(e1, e1) + v3_dot(e2, e2))
+                    < 1.e-6f)
+                    continue;
+                const v3 pa = v3_sub(point, p), pb = v3_sub(point, q), pcv = v3_sub(point, r);
+                const float da = v3_dot(pa, pa), db = v3_dot(pb, pb), dc = v3_dot(pcv, pcv);
+                float bu, bv;
+                if (da > db && da > dc)
+                    bu = 1.0f, bv = 0.0f;
+                else if (db > dc)
+                    bu = 0.0f, bv = 1.0f;
+                else
+                    bu = 0.0f, bv = 0.0f;
+                const float bw = 1.f - bu - bv;
+                const v3 c = v3_add(v3_add(v3_scale(bu, p), v3_scale(bv, q)), v3_scale(bw, r));
+                const v3 d = v3_sub(c, point);
+                const float dsq = v3_dot(d, d);
+                if (dsq > best)
+                    best = dsq, best_v = bv, best_w = bw, best_face = prim;
+            }
+        } else {
+            const orc_half llo = m->node_lowers[li], lhi = m->node_uppers[li];
+            const orc_half rlo = m->node_lowers[ri], rhi = m->node_uppers[ri];
+            const float dl = far_aabb_sq(point, &llo, &lhi), dr = far_aabb_sq(point, &rlo, &rhi);
+            int first, second;
+            float dfirst, dsecond;
+            if (dl > dr) {
+                first = ri, second = li, dfirst = dr, dsecond = dl;
+            } else {
+                first = li, second = ri, dfirst = dl, dsecond = dr;
+            }
+            if (dfirst > best)
+                stack[count++] = first;
+            if (dsecond > best)
+                stack[count++] = second;
+        }
+    }
+    if (best > min_dist * min_dist) {
+        *u = 1.0f - best_v - best_w;
+        *v = best_v;
+        *face = best_face;
+        return 1;
+    }
+    return 0;
+}
+
+void orc_query_furthest_point_no_sign(const float* points, const int* indices, const orc_half* node_lowers,
+                                      const orc_half* node_uppers, const int* primitive_indices, int root,
+                                      const float* queries, int64_t n, float min_dist, uint8_t* result, int* face, float* u,
+                                      float* v)
+{
+    const orc_mesh m = make_mesh(points, indices, node_lowers, node_uppers, primitive_indices, root);
+    for (int64_t i = 0; i < n; ++i) {
+        int f = 0;
+        float bu = 0.f, bv = 0.f;
+        const int ok = point_furthest_one(&m, v3_ld(queries, i), min_dist, &f, &bu, &bv);
+        result[i] = (uint8_t)ok;
+        face[i] = ok ? f : 0, u[i] = ok ? bu : 0.f, v[i] = ok ? bv : 0.f;
+    }
+}
+
+/* mesh_eval_face_normal (mesh.h:2870-2888) */
+void orc_mesh_face_normal(const float* points, const int* indices, const int* face, int64_t n, float* out)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        const int t = face[i];
+        const v3 p = v3_ld(points, indices[3 * t + 0]), q = v3_ld(points, indices[3 * t + 1]),
+                 r = v3_ld(points, indices[3 * t + 2]);
+        const v3 nn = v3_normalize(v3_cross(v3_sub(q, p), v3_sub(r, p)));
+        out[3 * i] = nn.x, out[3 * i + 1] = nn.y, out[3 * i + 2] = nn.z;
+    }
+}

@@ -207,6 +207,28 @@ void ref_query_point_sign_normal(
     });
 }
 
+void ref_query_furthest_point_no_sign(
+    uint64_t id, const float* pts, int64_t n, float min_dist, uint8_t* result, int* face, float* u, float* v, int nthreads
+)
+{
+    parallel_for(n, nthreads, [&](int64_t i) {
+        mesh_query_point_t q
+            = mesh_query_furthest_point_no_sign(id, vec3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), min_dist);
+        result[i] = q.result ? 1 : 0;
+        face[i] = q.face;
+        u[i] = q.u;
+        v[i] = q.v;
+    });
+}
+
+void ref_mesh_eval_face_normal(uint64_t id, const int* face, int64_t n, float* out)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        vec3 nn = mesh_eval_face_normal(id, face[i]);
+        out[3 * i + 0] = nn[0], out[3 * i + 1] = nn[1], out[3 * i + 2] = nn[2];
+    }
+}
+
 void ref_query_ray(
     uint64_t id, const float* starts, const float* dirs, int64_t n, float max_t, uint8_t* result, float* sign,
     int* face, float* t, float* u, float* v, float* normal, int nthreads, const int* roots

@@ -1,6 +1,7 @@
 """Generates tests/golden/golden_sign_normal.npz by running the UNMODIFIED reference C++
 (oracle/_ref/libwarp_ref_cpu.so) in the dev container: mesh_query_point_sign_normal
-(warp/native/mesh.h:860-1090) and Mesh.average_edge_length (mesh.cpp:140-155) on the mesh of golden_cpu.npz,
+(warp/native/mesh.h:860-1090), Mesh.average_edge_length (mesh.cpp:140-155), mesh_query_furthest_point_no_sign
+(mesh.h:678-858) and mesh_eval_face_normal (mesh.h:2870-2888) on the mesh of golden_cpu.npz,
 over the reference's own SAH tree and over the LBVH trees stored there.  Besides the box queries of golden_cpu.npz
 the query set holds points next to vertices, edge midpoints and the vertices themselves (the welding band).
 
@@ -40,6 +41,13 @@ for name in ("sah", "lbvh1", "lbvh4"):
         r = m.query_point_sign_normal(Q, md, eps)
         for k, v in r.items():
             out[f"{name}_{tag}_{k}"] = v
+
+    for tag, md in (("far0", 0.0), ("far2", 2.0)):
+        r = m.query_furthest_point_no_sign(Q, md)
+        for k, v in r.items():
+            out[f"{name}_{tag}_{k}"] = v
+out["normal_faces"] = rng.integers(0, len(T), 256).astype(np.int32)
+out["face_normals"] = ref_mesh.eval_face_normal(out["normal_faces"])
 
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "golden_sign_normal.npz"), **out)
 print(avg, {k: (v.shape, v.dtype) for k, v in out.items() if k.startswith("lbvh4")})

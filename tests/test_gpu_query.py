@@ -447,6 +447,38 @@ def test_sign_normal(wp, oracle_mod):
     assert wp.mesh_query_point_sign_normal(m2, np.zeros((0, 3), np.float32), 1.0).numpy()["face"].shape == (0,)
 
 
+def test_furthest_point_and_face_normal(wp, oracle_mod):
+    """mesh_query_furthest_point_no_sign and mesh_eval_face_normal: bit-exact against the restatement (pinned on the
+    reference C++), leaf sizes 1 / 4, several min_dist, empty batch, after a refit."""
+    P, I = mg.noisy_sphere(4, 0.05, 57)
+    Q = mg.box_queries(P, 20000, seed=58)
+    fields = ("result", "face", "u", "v")
+    for leaf in (1, 4):
+        m = gpu_mesh(wp, P, I, leaf)
+        tree = oracle_mod.mesh_lbvh_build(P, I, leaf)
+        for md in (0.0, 1.5, 2.0, 1e6):
+            want = oracle_mod.query_furthest_point_no_sign(P, I, tree, Q, md)
+            got = wp.mesh_query_furthest_point_no_sign(m, Q, md).numpy()
+            assert_results_equal(got, want, fields)
+            assert not got["sign"].any()
+    dev = wp.mesh_query_furthest_point_no_sign(m, wp.array(Q, dtype=wp.vec3), 0.0).numpy()
+    assert_results_equal(dev, oracle_mod.query_furthest_point_no_sign(P, I, tree, Q, 0.0), fields)
+    assert wp.mesh_query_furthest_point_no_sign(m, np.zeros((0, 3), np.float32), 0.0).numpy()["face"].shape == (0,)
+    f = np.arange(len(I) // 3, dtype=np.int32)
+    assert np.array_equal(wp.mesh_eval_face_normal(m, f), oracle_mod.mesh_face_normal(P, I, f))
+    # both follow the points: refit after a deformation
+    P2 = mg.renoise_sphere(P, 0.05, 59)
+    pts = wp.array(P, dtype=wp.vec3)
+    m2 = wp.Mesh(pts, wp.array(I, dtype=wp.int32), bvh_constructor="lbvh")
+    pts.assign(P2)
+    m2.refit()
+    lo2, hi2 = oracle_mod.triangle_bounds(P2, I)
+    oracle_mod.lbvh_refit(tree, lo2, hi2)
+    assert_results_equal(wp.mesh_query_furthest_point_no_sign(m2, Q, 0.0).numpy(),
+                         oracle_mod.query_furthest_point_no_sign(P2, I, tree, Q, 0.0), fields)
+    assert np.array_equal(wp.mesh_eval_face_normal(m2, wp.array(f, dtype=wp.int32)).numpy(), oracle_mod.mesh_face_normal(P2, I, f))
+
+
 def test_rooted_mesh_rays(wp, oracle_mod):
     """mesh_query_ray / _anyhit / _count_intersections restricted to a group's subtree (`root` argument of the
     reference): fixture from the reference C++, then the oracle; group roots of a grouped MESH."""

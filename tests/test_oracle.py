@@ -485,6 +485,42 @@ def test_sign_normal_live_reference(oracle_mod):
                              POINT_FIELDS)
 
 
+FAR_FIELDS = ("result", "face", "u", "v")
+
+
+def test_furthest_point_and_face_normal_restatement(oracle_mod, gold):
+    """mesh_query_furthest_point_no_sign / mesh_eval_face_normal: fixture produced by the reference C++
+    (tests/golden/make_golden_sign_normal.py), SAH and LBVH trees; then a brute-force check and the live reference."""
+    o = oracle_mod
+    sn = np.load(SIGNN_GOLD)
+    P, I, Q = gold["mesh_points"], gold["mesh_indices"], sn["queries"]
+    for name in ("sah", "lbvh1", "lbvh4"):
+        tree = {k: gold[f"{name}_tree_{k}"] for k in ("node_lowers", "node_uppers", "primitive_indices")}
+        tree["root"] = int(gold[f"{name}_tree_root"])
+        for tag, md in (("far0", 0.0), ("far2", 2.0)):
+            want = {k: sn[f"{name}_{tag}_{k}"] for k in FAR_FIELDS}
+            assert_results_equal(o.query_furthest_point_no_sign(P, I, tree, Q, md), want, FAR_FIELDS)
+    assert np.array_equal(o.mesh_face_normal(P, I, sn["normal_faces"]), sn["face_normals"])
+    # brute force: the farthest point of a mesh is its farthest vertex
+    got = o.query_furthest_point_no_sign(P, I, tree, Q[:200], 0.0)
+    T = I.reshape(-1, 3)
+    bary = np.stack([got["u"], got["v"], 1 - got["u"] - got["v"]], axis=1)
+    pos = (P[T[got["face"]]] * bary[:, :, None]).sum(axis=1)
+    d_got = np.linalg.norm(pos - Q[:200], axis=1)
+    d_max = np.sqrt(((P[None, :, :] - Q[:200, None, :]) ** 2).sum(-1)).max(axis=1)
+    assert np.allclose(d_got, d_max, rtol=1e-6)
+    if o.ref_available():
+        P2, I2 = mg.noisy_sphere(3, noise=0.1, seed=23)
+        Q2 = mg.box_queries(P2, 3000, seed=24)
+        tree2 = o.mesh_lbvh_build(P2, I2, 4)
+        rl = o.RefMesh.from_tree(P2, I2, tree2)
+        for md in (0.0, 1.5, 1e6):
+            assert_results_equal(o.query_furthest_point_no_sign(P2, I2, tree2, Q2, md), rl.query_furthest_point_no_sign(Q2, md),
+                                 FAR_FIELDS)
+        f = np.arange(len(I2) // 3, dtype=np.int32)
+        assert np.array_equal(o.mesh_face_normal(P2, I2, f), rl.eval_face_normal(f))
+
+
 def _grouped_mesh_case():
     P, I = mg.noisy_sphere(3, noise=0.05, seed=61)
     T = len(I) // 3

@@ -49,6 +49,8 @@ from .queries import (  # noqa: F401
     mesh_average_edge_length,
     mesh_eval_position,
     mesh_eval_velocity,
+    mesh_eval_face_normal,
+    mesh_query_furthest_point_no_sign,
     mesh_query_ray,
     mesh_query_ray_anyhit,
     mesh_query_ray_count_intersections,

@@ -103,6 +103,8 @@ SIGNATURES = {
     "wp_b200_mesh_query_ray_count_intersections": (_i, [_u64, _vp, _vp, _i64, _vp, _vp]),
     "wp_b200_mesh_eval_position": (_i, [_u64, _vp, _vp, _vp, _i64, _vp]),
     "wp_b200_mesh_eval_velocity": (_i, [_u64, _vp, _vp, _vp, _i64, _vp]),
+    "wp_b200_mesh_eval_face_normal": (_i, [_u64, _vp, _i64, _vp]),
+    "wp_b200_mesh_query_furthest_point_no_sign": (_i, [_u64, _vp, _i64, _f, _vp, _vp, _vp, _vp]),
     "wp_b200_mesh_query_point_no_sign_host":(_i, [_u64, _vp, _i64, _f, _vp, _vp, _vp, _vp]),
     "wp_b200_mesh_query_point_host": (_i, [_u64, _vp, _i64, _f, _vp, _vp, _vp, _vp, _vp]),
     "wp_b200_mesh_query_ray_host": (_i, [_u64, _vp, _vp, _i64, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

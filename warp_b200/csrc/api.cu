@@ -905,6 +905,45 @@ int wp_b200_mesh_eval_velocity(uint64_t id, const int32_t* face, const float* u,
     return mesh_eval(id, 1, face, u, v, n, out);
 }
 
+int wp_b200_mesh_eval_face_normal(uint64_t id, const int32_t* face, int64_t n, float* out)
+{
+    MeshState* m = query_mesh(id);
+    if (!m)
+        return 0;
+    DeviceGuard g(m->bvh.device);
+    cudaStream_t st = current_stream(m->bvh.device);
+    if (n <= 0)
+        return 1;
+    if (!m->points_data || !m->indices_data)  // mesh.h:2874-2875: vec3()
+        return check(cudaMemsetAsync(out, 0, 12 * (size_t)n, st), "memset");
+    const char* err = wb_mesh_face_normal((const float*)m->points_data, (const int*)m->indices_data, face, n, out, st);
+    if (err) {
+        set_error("Warp error: mesh face normal failed: %s", err);
+        return 0;
+    }
+    return 1;
+}
+
+int wp_b200_mesh_query_furthest_point_no_sign(uint64_t id, const float* points, int64_t n, float min_dist, uint8_t* result,
+                                              int32_t* face, float* u, float* v)
+{
+    MeshState* m = query_mesh(id);
+    if (!m)
+        return 0;
+    DeviceGuard g(m->bvh.device);
+    cudaStream_t st = current_stream(m->bvh.device);
+    if (n <= 0)
+        return 1;
+    if (m->bvh.n == 0)
+        return zero_point_outputs(n, result, nullptr, face, u, v, st);
+    const char* err = wb_query_furthest(make_view(m->bvh), points, n, min_dist, result, face, u, v, st);
+    if (err) {
+        set_error("Warp error: mesh furthest-point query failed: %s", err);
+        return 0;
+    }
+    return 1;
+}
+
 // ------------------------------------------------------------------------------------------------
 // queries (host buffers): chunked, two lanes so the copies of one chunk overlap the traversal of
 // the other.  Fully asynchronous only when the caller's buffers are pinned (wp_alloc_pinned).

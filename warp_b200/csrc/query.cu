@@ -919,6 +919,120 @@ k_query_point_sign_normal(TreeView tv, const float* __restrict__ pts, const int*
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// mesh_query_furthest_point_no_sign (mesh.h:678-858): the mirror image of the closest-point walk -- nodes are ranked
+// by the distance to their farthest corner (mesh.h:100-119), the farther child is entered first, a node is skipped when
+// even its farthest corner is nearer than the best so far, and the candidate on a triangle is its farthest VERTEX
+// (intersect.h:111-125).  Updates on strict '>', result = best > min_dist^2.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float far_aabb_sq(float3 p, float3 lo, float3 hi)
+{
+    const float lx = fabsf(p.x - lo.x), ux = fabsf(p.x - hi.x), cx = (lx > ux) ? lx : ux;
+    const float ly = fabsf(p.y - lo.y), uy = fabsf(p.y - hi.y), cy = (ly > uy) ? ly : uy;
+    const float lz = fabsf(p.z - lo.z), uz = fabsf(p.z - hi.z), cz = (lz > uz) ? lz : uz;
+    return cx * cx + cy * cy + cz * cz;
+}
+
+__global__ void __launch_bounds__(QT)
+k_query_furthest(TreeView tv, const float* __restrict__ pts, long long nq, float min_dist, uint8_t* __restrict__ result,
+                 int* __restrict__ face, float* __restrict__ u, float* __restrict__ v)
+{
+    const TreeHeader h = *tv.header;
+    for (long long qi = (long long)blockIdx.x * QT + threadIdx.x; qi < nq; qi += (long long)gridDim.x * QT) {
+        const float3 point = make_float3(__ldg(pts + 3 * qi), __ldg(pts + 3 * qi + 1), __ldg(pts + 3 * qi + 2));
+        Entry stack[WB_QUERY_STACK];
+        float stack_d[WB_QUERY_STACK];
+        int top = 0;
+        float best = min_dist * min_dist;
+        int best_face = 0;
+        float best_v = 0.f, best_w = 0.f;
+
+        Entry cur;
+        if (h.root_ref & WB_LEAF)
+            cur.a = WB_LEAF | 0u, cur.b = h.root_count;
+        else
+            cur.a = (h.root_ref & WB_IDX_MASK) - (uint32_t)tv.n, cur.b = 0;
+        float cur_d = far_aabb_sq(point, make_float3(h.lx, h.ly, h.lz), make_float3(h.hx, h.hy, h.hz));
+        bool have = true;
+        for (;;) {
+            if (!have) {
+                if (top == 0)
+                    break;
+                --top;
+                cur = stack[top];
+                cur_d = stack_d[top];
+            }
+            have = false;
+            if (cur_d < best)
+                continue;
+            if (cur.a & WB_LEAF) {
+                const uint32_t start = cur.a & WB_IDX_MASK;
+                for (uint32_t pos = start; pos < start + cur.b; ++pos) {
+                    const Tri t = load_tri(tv.tris, pos);
+                    if (t.flags & WB_TRI_SLIVER)
+                        continue;
+                    const float3 pa = wb_sub(point, t.p), pb = wb_sub(point, t.q), pc = wb_sub(point, t.r);
+                    const float da = wb_dot(pa, pa), db = wb_dot(pb, pb), dc = wb_dot(pc, pc);
+                    float bu, bv;
+                    if (da > db && da > dc)
+                        bu = 1.0f, bv = 0.0f;
+                    else if (db > dc)
+                        bu = 0.0f, bv = 1.0f;
+                    else
+                        bu = 0.0f, bv = 0.0f;
+                    const float w = 1.f - bu - bv;
+                    const float3 c = wb_add(wb_add(wb_scale(bu, t.p), wb_scale(bv, t.q)), wb_scale(w, t.r));
+                    const float3 d = wb_sub(c, point);
+                    const float dsq = wb_dot(d, d);
+                    if (dsq > best)
+                        best = dsq, best_v = bv, best_w = w, best_face = t.face;
+                }
+                continue;
+            }
+            const Pair pr = load_pair(tv.pairs, cur.a, tv.n);
+            const float dl = far_aabb_sq(point, pr.llo, pr.lhi), dr = far_aabb_sq(point, pr.rlo, pr.rhi);
+            Entry first_e, second_e;  // second is entered now (the reference pushes it last and pops it first)
+            float first_d, second_d;
+            if (dl > dr)
+                first_e = pr.right, first_d = dr, second_e = pr.left, second_d = dl;
+            else
+                first_e = pr.left, first_d = dl, second_e = pr.right, second_d = dr;
+            if (first_d > best) {
+                stack[top] = first_e;
+                stack_d[top] = first_d;
+                ++top;
+            }
+            if (second_d > best) {
+                cur = second_e;
+                cur_d = second_d;
+                have = true;
+            }
+        }
+        const bool ok = best > min_dist * min_dist;
+        result[qi] = ok ? 1 : 0;
+        face[qi] = ok ? best_face : 0;
+        u[qi] = ok ? 1.0f - best_v - best_w : 0.f;
+        v[qi] = ok ? best_v : 0.f;
+    }
+}
+
+// mesh_eval_face_normal (mesh.h:2870-2888): normalize(cross(q - p, r - p)) from the caller's arrays
+__global__ void __launch_bounds__(QT)
+k_mesh_face_normal(const float* __restrict__ points, const int* __restrict__ indices, const int* __restrict__ face, long long n,
+                   float* __restrict__ out)
+{
+    for (long long i = (long long)blockIdx.x * QT + threadIdx.x; i < n; i += (long long)gridDim.x * QT) {
+        float3 p, q, r;
+        MeshSource { points, indices }.tri(face[i], p, q, r);
+        const float3 nrm = wb_cross(wb_sub(q, p), wb_sub(r, p));
+        const float l = sqrtf(nrm.x * nrm.x + nrm.y * nrm.y + nrm.z * nrm.z);
+        const bool nz = l > 0.0f;  // vec.h:1111-1118 with kEps = 0
+        out[3 * i + 0] = nz ? nrm.x / l : 0.f;
+        out[3 * i + 1] = nz ? nrm.y / l : 0.f;
+        out[3 * i + 2] = nz ? nrm.z / l : 0.f;
+    }
+}
+
 // mesh_eval_position / mesh_eval_velocity (mesh.h:2767-2807): p*u + q*v + r*(1-u-v) from the caller's arrays
 __global__ void __launch_bounds__(QT)
 k_mesh_eval(const float* __restrict__ attr, const int* __restrict__ indices, const int* __restrict__ face,
@@ -1040,6 +1154,26 @@ const char* wb_query_point_sign_normal(const TreeView& tv, const float* mesh_poi
     if (nq > 0)
         k_query_point_sign_normal<<<query_grid(nq), QT, 0, stream>>>(tv, pts, perm, nq, max_dist, epsilon, avg_edge, result, sign,
                                                                 face, u, v);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+const char* wb_query_furthest(const TreeView& tv, const float* pts, long long nq, float min_dist, uint8_t* result, int* face,
+                              float* u, float* v, cudaStream_t stream)
+{
+    if (nq <= 0)
+        return nullptr;
+    k_query_furthest<<<query_grid(nq), QT, 0, stream>>>(tv, pts, nq, min_dist, result, face, u, v);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+const char* wb_mesh_face_normal(const float* points, const int* indices, const int* face, long long n, float* out,
+                                cudaStream_t stream)
+{
+    if (n <= 0)
+        return nullptr;
+    k_mesh_face_normal<<<query_grid(n), QT, 0, stream>>>(points, indices, face, n, out);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

@@ -38,3 +38,8 @@ const char* wb_query_point_sign_normal(const TreeView& tv, const float* mesh_poi
 // sign of mesh_query_point_sign_parity (mesh.h:2362-2392) for the queries whose `result` is set; 0 elsewhere
 const char* wb_sign_parity(const TreeView& tv, const float* pts, long long nq, int n_sample, float scale,
                            const uint8_t* result, float* sign, cudaStream_t stream);
+// mesh_query_furthest_point_no_sign (mesh.h:678-858) and mesh_eval_face_normal (mesh.h:2870-2888)
+const char* wb_query_furthest(const TreeView& tv, const float* pts, long long nq, float min_dist, uint8_t* result, int* face,
+                              float* u, float* v, cudaStream_t stream);
+const char* wb_mesh_face_normal(const float* points, const int* indices, const int* face, long long n, float* out,
+                                cudaStream_t stream);

@@ -18,7 +18,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from .types import Mesh, array, empty, float32, from_numpy, int32, uint8, vec3
+from .types import Mesh, array, empty, float32, from_numpy, int32, uint8, vec3, zeros
 
 
 class MeshQueryPoint:
@@ -292,6 +292,31 @@ def mesh_eval_position(mesh, face, u, v):
 def mesh_eval_velocity(mesh, face, u, v):
     """Same interpolation over the mesh's velocities; zeros when it has none (mesh.h:2787-2805)."""
     return _mesh_eval(mesh, face, u, v, True)
+
+
+def mesh_eval_face_normal(mesh, face):
+    """``normalize(cross(q - p, r - p))`` of triangle ``face[i]`` of the mesh's current points (mesh.h:2870-2888)."""
+    id_, dev = _mesh_id(mesh)
+    f, host = _stage(face, int32, dev, "face")
+    out = empty(len(f), vec3, dev)
+    _check(_lib.core().wp_b200_mesh_eval_face_normal(id_, _p(f), len(f), _p(out)), "mesh_eval_face_normal")
+    return out.numpy() if host else out
+
+
+def mesh_query_furthest_point_no_sign(mesh, points, min_dist: float):
+    """Farthest point of the mesh from each query (``mesh.h:678-858``; always a vertex), found when it lies strictly
+    beyond ``min_dist``.  ``sign`` stays 0.  Device array in -> device arrays out; host array in -> numpy arrays out."""
+    id_, dev = _mesh_id(mesh)
+    pts, host = _stage(points, vec3, dev, "points")
+    n = len(pts)
+    out = MeshQueryPoint(empty(n, uint8, dev), zeros(n, float32, dev), empty(n, int32, dev), empty(n, float32, dev),
+                         empty(n, float32, dev))  # fmt: skip
+    ok = _lib.core().wp_b200_mesh_query_furthest_point_no_sign(id_, _p(pts), n, float(min_dist), _p(out.result), _p(out.face),
+                                                               _p(out.u), _p(out.v))  # fmt: skip
+    _check(ok, "mesh_query_furthest_point_no_sign")
+    if host:
+        return MeshQueryPoint(*(getattr(out, k).numpy() for k in MeshQueryPoint.__slots__))
+    return out
 
 
 class query_stats:
