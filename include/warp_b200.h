@@ -269,6 +269,19 @@ WP_B200_API int wp_b200_bvh_query_ray_count(uint64_t id, const float* starts, co
                                             int64_t n, float max_dist, int32_t* counts);
 WP_B200_API int wp_b200_bvh_query_ray_fill(uint64_t id, const float* starts, const float* dirs, const int32_t* roots,
                                            int64_t n, float max_dist, const int32_t* offsets, int32_t* indices);
+/* wp.bvh_query_sphere (bvh.h:542-551, node test intersect.h:197-205): items whose AABB lies within radii[i] of
+ * centers[i]; wp.bvh_query_capsule (bvh.h:529-540, node test bvh.h:472-482): items whose AABB, inflated by radii[i],
+ * is entered by the ray starts[i] + t * dirs[i] at t <= max_dist (closed).  Negative radii count as 0.  Same count /
+ * scan / fill protocol and hit order as the AABB and ray lists. */
+WP_B200_API int wp_b200_bvh_query_sphere_count(uint64_t id, const float* centers, const float* radii, const int32_t* roots,
+                                               int64_t n, int32_t* counts);
+WP_B200_API int wp_b200_bvh_query_sphere_fill(uint64_t id, const float* centers, const float* radii, const int32_t* roots,
+                                              int64_t n, const int32_t* offsets, int32_t* indices);
+WP_B200_API int wp_b200_bvh_query_capsule_count(uint64_t id, const float* starts, const float* dirs, const float* radii,
+                                                const int32_t* roots, int64_t n, float max_dist, int32_t* counts);
+WP_B200_API int wp_b200_bvh_query_capsule_fill(uint64_t id, const float* starts, const float* dirs, const float* radii,
+                                               const int32_t* roots, int64_t n, float max_dist, const int32_t* offsets,
+                                               int32_t* indices);
 /* wp.bvh_get_group_root (bvh.h:376-390) for a batch of group ids: roots[i] = reference index of the node that holds
  * exactly the items of group_ids[i] (a leaf for a one-item group), -1 when the group does not occur.  On a tree
  * built without groups every item is in group 0. */

@@ -555,6 +555,41 @@ def bvh_query(tree, item_lowers, item_uppers, qa, qb, ray=False, max_dist=3.4028
     return offsets, indices[: int(offsets[-1])]
 
 
+_KINDS = {"aabb": 0, "ray": 1, "sphere": 2, "capsule": 3}
+
+
+def _bvh_query_kind(lib_fn, with_num_items, tree, item_lowers, item_uppers, kind, qa, qb, radii, max_dist, roots):
+    lo, hi = _f32(item_lowers, (-1, 3)), _f32(item_uppers, (-1, 3))
+    a = _f32(qa, (-1, 3))
+    b = a if qb is None else _f32(qb, (-1, 3))
+    n = a.shape[0]
+    rad = None if radii is None else np.ascontiguousarray(np.broadcast_to(np.asarray(radii, np.float32), (n,)))
+    offsets = np.zeros(n + 1, np.int32)
+    r = None if roots is None else _i32(roots)
+    args = [tree["node_lowers"].ctypes.data_as(ctypes.c_void_p), tree["node_uppers"].ctypes.data_as(ctypes.c_void_p),
+            _p(tree["primitive_indices"], _i32p), ctypes.c_int(tree["root"]), _p(lo, _f32p), _p(hi, _f32p)]
+    if with_num_items:
+        args.append(ctypes.c_int(lo.shape[0]))
+    args += [ctypes.c_int(_KINDS[kind]), _p(a, _f32p), _p(b, _f32p), _p(rad, _f32p), _p(r, _i32p), ctypes.c_int64(n),
+             ctypes.c_float(max_dist)]
+    lib_fn(*args, _p(offsets, _i32p), None)
+    indices = np.zeros(max(int(offsets[-1]), 1), np.int32)
+    lib_fn(*args, _p(offsets, _i32p), _p(indices, _i32p))
+    return offsets, indices[: int(offsets[-1])]
+
+
+def bvh_query_kind(tree, item_lowers, item_uppers, kind, qa, qb=None, radii=None, max_dist=3.4028234663852886e38, roots=None):
+    """Generic iterator restatement for any BvhQueryKind (bvh.h:420-664): "aabb" | "ray" | "sphere" (qa = centres,
+    radii) | "capsule" (qa, qb = starts, dirs; radii; closed max_dist).  Returns (offsets[n+1], indices)."""
+    return _bvh_query_kind(orc().orc_bvh_query_kind, False, tree, item_lowers, item_uppers, kind, qa, qb, radii, max_dist, roots)
+
+
+def ref_bvh_query_kind(tree, item_lowers, item_uppers, kind, qa, qb=None, radii=None, max_dist=3.4028234663852886e38,
+                       roots=None):
+    """The reference's own iterators (bvh.h:494-664, oracle/_ref) run to exhaustion per query."""
+    return _bvh_query_kind(ref().ref_bvh_query_kind, True, tree, item_lowers, item_uppers, kind, qa, qb, radii, max_dist, roots)
+
+
 def bvh_group_roots(tree, groups, group_ids):
     """bvh_get_group_root restatement (bvh.h:287-390): reference node index per queried group id, -1 if absent.
     ``groups`` = the per-item group array the tree was built with (None for an ungrouped tree)."""

@@ -347,6 +347,42 @@ void ref_bvh_query(const void* node_lowers, const void* node_uppers, const int* 
     offsets[n] = run;
 }
 
+// kind: 0 aabb, 1 ray, 2 sphere (qa = centre), 3 capsule; radii per query for kinds 2 and 3
+void ref_bvh_query_kind(const void* node_lowers, const void* node_uppers, const int* prim, int root,
+                        const float* item_lowers, const float* item_uppers, int num_items, int kind, const float* qa,
+                        const float* qb, const float* radii, const int* roots, int64_t n, float max_dist, int* offsets,
+                        int* indices)
+{
+    BVH b = make_bvh(node_lowers, node_uppers, nullptr, prim, item_lowers, item_uppers, nullptr, num_items, &root);
+    const uint64_t id = (uint64_t)&b;
+    int run = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        offsets[i] = run;
+        const vec3 a(qa[3 * i], qa[3 * i + 1], qa[3 * i + 2]);
+        const float* qbp = kind == 2 ? qa : qb;
+        const vec3 c(qbp[3 * i], qbp[3 * i + 1], qbp[3 * i + 2]);
+        const int r = roots ? roots[i] : -1;
+        const float rad = radii ? radii[i] : 0.0f;
+        bvh_query_t q = kind == 1 ? bvh_query_ray(id, a, c, r)
+            : kind == 2           ? bvh_query_sphere(id, a, rad, r)
+            : kind == 3           ? bvh_query_capsule(id, a, c, rad, r)
+                                  : bvh_query_aabb(id, a, c, r);
+        int item;
+        for (;;) {
+            const bool more = kind == 1 ? bvh_query_ray_next(q, item, max_dist)
+                : kind == 2             ? bvh_query_sphere_next(q, item, max_dist)
+                : kind == 3             ? bvh_query_capsule_next(q, item, max_dist)
+                                        : bvh_query_next(q, item, max_dist);
+            if (!more)
+                break;
+            if (indices)
+                indices[run] = item;
+            ++run;
+        }
+    }
+    offsets[n] = run;
+}
+
 void ref_bvh_group_roots(const void* node_lowers, const void* node_uppers, const int* parents, const int* prim,
                          const int* item_groups, int num_items, int root, const int* group_ids, int64_t n, int* roots)
 {

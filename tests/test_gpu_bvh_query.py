@@ -146,3 +146,58 @@ def test_group_roots_and_rooted_queries(wp, oracle_mod, leaf):
     plain = wp.Bvh(lo_d, hi_d, leaf_size=leaf)
     info_root = plain.download_tree()["root"]
     assert wp.bvh_get_group_root(plain, np.array([0, 1, -3], np.int32)).tolist() == [info_root, -1, -1]
+
+
+@pytest.mark.parametrize("leaf", [1, 2, 4])
+def test_bvh_sphere_and_capsule_queries(wp, oracle_mod, leaf):
+    """bvh_query_sphere / bvh_query_capsule: exact hit lists in iterator order against the restatement (pinned on the
+    reference C++), build -> refit -> rebuild like test_bvh.py:186-262; per-query and scalar radii, negative radii,
+    axis-aligned directions, closed max_dist, roots, empty batch."""
+    from test_oracle import _brute_sphere
+
+    lo, hi = random_boxes(3000, seed=131)
+    lo_d, hi_d = wp.array(lo, dtype=wp.vec3), wp.array(hi, dtype=wp.vec3)
+    bvh = wp.Bvh(lo_d, hi_d, constructor="lbvh", leaf_size=leaf)
+    tree = oracle_mod.lbvh_build(lo, hi, leaf)
+    rng = np.random.default_rng(132)
+    n = 1500
+    C = (rng.random((n, 3)) * 10).astype(np.float32)
+    R = (rng.random(n) * 1.5 - 0.1).astype(np.float32)
+    D = rng.standard_normal((n, 3)).astype(np.float32)
+    D[::7, 0] = 0
+    D[::11, 1] = 0
+    D[::13] = (0, 0, 1)
+    D /= np.linalg.norm(D, axis=1, keepdims=True)
+
+    def check(tree, lo, hi):
+        off, idx = wp.bvh_query_sphere(bvh, C, R).numpy()
+        woff, widx = oracle_mod.bvh_query_kind(tree, lo, hi, "sphere", C, radii=R)
+        assert np.array_equal(off, woff) and np.array_equal(idx, widx)
+        if leaf > 1:
+            for i, want in enumerate(_brute_sphere(lo, hi, C[:200], R[:200])):
+                assert sorted(idx[off[i] : off[i + 1]].tolist()) == want.tolist()
+        off, idx = wp.bvh_query_sphere(bvh, wp.array(C, dtype=wp.vec3), 0.75).numpy()
+        woff, widx = oracle_mod.bvh_query_kind(tree, lo, hi, "sphere", C, radii=0.75)
+        assert np.array_equal(off, woff) and np.array_equal(idx, widx)
+        for md in (3.4028234663852886e38, 3.0):
+            off, idx = wp.bvh_query_capsule(bvh, C, D, R, md).numpy()
+            woff, widx = oracle_mod.bvh_query_kind(tree, lo, hi, "capsule", C, D, radii=R, max_dist=md)
+            assert np.array_equal(off, woff) and np.array_equal(idx, widx)
+        roots = np.full(n, -1, np.int32)
+        roots[::2] = tree["root"]
+        off, idx = wp.bvh_query_capsule(bvh, C, D, 0.3, 2.0, roots=roots).numpy()
+        woff, widx = oracle_mod.bvh_query_kind(tree, lo, hi, "capsule", C, D, radii=0.3, max_dist=2.0, roots=roots)
+        assert np.array_equal(off, woff) and np.array_equal(idx, widx)
+
+    check(tree, lo, hi)
+    lo2, hi2 = random_boxes(3000, seed=133)
+    lo_d.assign(lo2), hi_d.assign(hi2)
+    bvh.refit()
+    oracle_mod.lbvh_refit(tree, lo2, hi2)
+    check(tree, lo2, hi2)
+    bvh.rebuild()
+    check(oracle_mod.lbvh_build(lo2, hi2, leaf), lo2, hi2)
+    z = np.zeros((0, 3), np.float32)
+    assert wp.bvh_query_sphere(bvh, z, 1.0).total == 0 and wp.bvh_query_capsule(bvh, z, z, 1.0).total == 0
+    with pytest.raises(RuntimeError):
+        wp.bvh_query_sphere(bvh, C, R[:5])

@@ -521,6 +521,49 @@ def test_furthest_point_and_face_normal_restatement(oracle_mod, gold):
         assert np.array_equal(o.mesh_face_normal(P2, I2, f), rl.eval_face_normal(f))
 
 
+def _brute_sphere(lo, hi, centers, radii):
+    r = np.maximum(radii, 0).astype(np.float32)
+    out = []
+    for c, rr in zip(centers, r):
+        d = np.maximum(np.maximum(lo - c, c - hi), np.float32(0))
+        out.append(np.flatnonzero((d * d).sum(axis=1, dtype=np.float32) <= rr * rr))
+    return out
+
+
+def test_bvh_sphere_capsule_restatement(oracle_mod):
+    """Sphere / capsule kinds of the generic iterator: fixture from the reference C++
+    (tests/golden/make_golden_bvh_kinds.py), exact lists in iterator order; sphere sets against brute force; a
+    zero-radius capsule closed at max_dist contains the plain ray's half-open list; then the live reference."""
+    o = oracle_mod
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_bvh_kinds.npz"))
+    lo, hi = random_boxes(2000, seed=int(g["seed_boxes"]))
+    C, R, D = g["centers"], g["radii"], g["dirs"]
+    for leaf in (1, 4):
+        tree = o.lbvh_build(lo, hi, leaf)
+        off, idx = o.bvh_query_kind(tree, lo, hi, "sphere", C, radii=R)
+        assert np.array_equal(off, g[f"leaf{leaf}_sphere_offsets"]) and np.array_equal(idx, g[f"leaf{leaf}_sphere_indices"])
+        if leaf == 4:  # (single-item leaves are reported on the node test alone, which is the same test here)
+            for i, want in enumerate(_brute_sphere(lo, hi, C, R)):
+                assert sorted(idx[off[i] : off[i + 1]].tolist()) == want.tolist()
+        for tag, md in (("inf", 3.4028234663852886e38), ("3", 3.0)):
+            off, idx = o.bvh_query_kind(tree, lo, hi, "capsule", C, D, radii=R, max_dist=md)
+            assert np.array_equal(off, g[f"leaf{leaf}_capsule{tag}_offsets"])
+            assert np.array_equal(idx, g[f"leaf{leaf}_capsule{tag}_indices"])
+        roff, ridx = o.bvh_query(tree, lo, hi, C, D, ray=True, max_dist=3.0)
+        coff, cidx = o.bvh_query_kind(tree, lo, hi, "capsule", C, D, radii=0.0, max_dist=3.0)
+        for i in range(len(C)):
+            assert set(ridx[roff[i] : roff[i + 1]].tolist()) <= set(cidx[coff[i] : coff[i + 1]].tolist())
+    if o.ref_available():
+        lo2, hi2 = random_boxes(5000, seed=43)
+        tree = o.lbvh_build(lo2, hi2, 2)
+        roots = np.full(len(C), -1, np.int32)
+        roots[::2] = tree["root"]
+        for kind, kw in (("sphere", dict(qa=C, radii=R)), ("capsule", dict(qa=C, qb=D, radii=0.3, max_dist=2.0)),
+                         ("capsule", dict(qa=C, qb=D, radii=R, roots=roots))):
+            a, b = o.bvh_query_kind(tree, lo2, hi2, kind, **kw), o.ref_bvh_query_kind(tree, lo2, hi2, kind, **kw)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
 def _grouped_mesh_case():
     P, I = mg.noisy_sphere(3, noise=0.05, seed=61)
     T = len(I) // 3

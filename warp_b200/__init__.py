@@ -62,6 +62,8 @@ from .bvh_queries import (  # noqa: F401,E402
     bvh_get_group_root,
     bvh_query_aabb,
     bvh_query_ray,
+    bvh_query_sphere,
+    bvh_query_capsule,
     mesh_query_aabb,
 )
 

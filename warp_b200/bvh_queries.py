@@ -10,7 +10,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from .types import Bvh, Mesh, array, empty, int32, vec3
+from .types import Bvh, Mesh, array, empty, float32, int32, vec3
 
 FLT_MAX = float(np.finfo(np.float32).max)
 
@@ -53,14 +53,28 @@ def _roots_arg(roots, n, dev):
     return roots
 
 
-def _run(bvh, qa, qb, ray, max_dist, mesh=False, roots=None):
+def _radii_arg(radii, n, dev):
+    """Per-query radii as a float32 device array; a scalar is broadcast."""
+    if isinstance(radii, array):
+        if radii.dtype != float32 or len(radii) != n:
+            raise RuntimeError("radii should be a float32 array with one entry per query")
+        return radii
+    h = np.asarray(radii, dtype=np.float32)
+    if h.ndim > 1 or (h.ndim == 1 and h.shape[0] != n):
+        raise RuntimeError("radii should be one float or a float32 array with one entry per query")
+    return array(np.ascontiguousarray(np.broadcast_to(h, (n,))), dtype=float32, device=dev)
+
+
+def _run(bvh, qa, qb, kind, max_dist, mesh=False, roots=None, radii=None):
+    """kind: "aabb" | "ray" | "sphere" | "capsule" (the reference's BvhQueryKind, bvh.h:420-427)."""
     if mesh:
         if not isinstance(bvh, Mesh) or not bvh.id:
             raise TypeError("expected a warp_b200.Mesh")
     elif not isinstance(bvh, Bvh) or not bvh.id:
         raise TypeError("expected a warp_b200.Bvh")
     dev = bvh.device
-    qa, qb = _as_dev(qa, dev, "first query array"), _as_dev(qb, dev, "second query array")
+    qa = _as_dev(qa, dev, "first query array")
+    qb = qa if qb is None else _as_dev(qb, dev, "second query array")
     if len(qa) != len(qb):
         raise RuntimeError("query arrays must have the same length")
     n = len(qa)
@@ -70,26 +84,33 @@ def _run(bvh, qa, qb, ray, max_dist, mesh=False, roots=None):
     offsets = empty(n + 1, int32, dev)
     roots = _roots_arg(roots, n, dev)
     pr = ctypes.c_void_p(roots.ptr or 0) if roots is not None else None
-    if mesh:
-        ok = c.wp_b200_mesh_query_aabb_count(bvh.id, p(qa), p(qb), n, p(counts))
-    elif ray:
-        ok = c.wp_b200_bvh_query_ray_count(bvh.id, p(qa), p(qb), pr, n, max_dist, p(counts))
-    else:
-        ok = c.wp_b200_bvh_query_aabb_count(bvh.id, p(qa), p(qb), pr, n, p(counts))
-    ok = ok and c.wp_b200_exclusive_scan_i32(p(counts), p(offsets), n)
+    rad = _radii_arg(radii, n, dev) if kind in ("sphere", "capsule") else None
+
+    def call(fill):
+        tail = (p(offsets), p(indices)) if fill else (p(counts),)
+        if mesh:
+            fn = c.wp_b200_mesh_query_aabb_fill if fill else c.wp_b200_mesh_query_aabb_count
+            return fn(bvh.id, p(qa), p(qb), n, *tail)
+        if kind == "ray":
+            fn = c.wp_b200_bvh_query_ray_fill if fill else c.wp_b200_bvh_query_ray_count
+            return fn(bvh.id, p(qa), p(qb), pr, n, max_dist, *tail)
+        if kind == "sphere":
+            fn = c.wp_b200_bvh_query_sphere_fill if fill else c.wp_b200_bvh_query_sphere_count
+            return fn(bvh.id, p(qa), p(rad), pr, n, *tail)
+        if kind == "capsule":
+            fn = c.wp_b200_bvh_query_capsule_fill if fill else c.wp_b200_bvh_query_capsule_count
+            return fn(bvh.id, p(qa), p(qb), p(rad), pr, n, max_dist, *tail)
+        fn = c.wp_b200_bvh_query_aabb_fill if fill else c.wp_b200_bvh_query_aabb_count
+        return fn(bvh.id, p(qa), p(qb), pr, n, *tail)
+
+    indices = None
+    ok = call(False) and c.wp_b200_exclusive_scan_i32(p(counts), p(offsets), n)
     if not ok:
         raise RuntimeError(f"bvh query failed: {_lib.error_string()}")
     total = int(offsets.numpy()[-1])  # the one host round trip: the hit list has to be allocated
     indices = empty(max(total, 1), int32, dev)
-    if total:
-        if mesh:
-            ok = c.wp_b200_mesh_query_aabb_fill(bvh.id, p(qa), p(qb), n, p(offsets), p(indices))
-        elif ray:
-            ok = c.wp_b200_bvh_query_ray_fill(bvh.id, p(qa), p(qb), pr, n, max_dist, p(offsets), p(indices))
-        else:
-            ok = c.wp_b200_bvh_query_aabb_fill(bvh.id, p(qa), p(qb), pr, n, p(offsets), p(indices))
-        if not ok:
-            raise RuntimeError(f"bvh query failed: {_lib.error_string()}")
+    if total and not call(True):
+        raise RuntimeError(f"bvh query failed: {_lib.error_string()}")
     return BvhQueryResult(offsets, indices, total)
 
 
@@ -97,12 +118,25 @@ def bvh_query_aabb(bvh, lowers, uppers, roots=None) -> BvhQueryResult:
     """All items whose AABB overlaps ``[lowers[i], uppers[i]]`` (closed boxes, ``intersect.h:183-192``).
     ``roots`` (optional, one int per query): start the traversal at that node -- e.g. a group's subtree from
     :func:`bvh_get_group_root` -- instead of the tree root; ``-1`` means the tree root (``bvh.h:494-518``)."""
-    return _run(bvh, lowers, uppers, False, 0.0, roots=roots)
+    return _run(bvh, lowers, uppers, "aabb", 0.0, roots=roots)
 
 
 def bvh_query_ray(bvh, starts, dirs, max_dist: float = FLT_MAX, roots=None) -> BvhQueryResult:
     """All items whose AABB the ray ``starts[i] + t * dirs[i]`` enters at ``t < max_dist`` (``bvh.h:483-487``)."""
-    return _run(bvh, starts, dirs, True, float(max_dist), roots=roots)
+    return _run(bvh, starts, dirs, "ray", float(max_dist), roots=roots)
+
+
+def bvh_query_sphere(bvh, centers, radii, roots=None) -> BvhQueryResult:
+    """All items whose AABB lies within ``radii[i]`` (an array or one float) of ``centers[i]``: the exact sphere / box
+    test of ``wp.bvh_query_sphere`` (``bvh.h:542-551``, ``intersect.h:197-205``); negative radii count as 0."""
+    return _run(bvh, centers, None, "sphere", 0.0, roots=roots, radii=radii)
+
+
+def bvh_query_capsule(bvh, starts, dirs, radii, max_dist: float = FLT_MAX, roots=None) -> BvhQueryResult:
+    """All items whose AABB, inflated by ``radii[i]``, the ray ``starts[i] + t * dirs[i]`` enters at ``t <= max_dist``
+    (closed, unlike the plain ray): ``wp.bvh_query_capsule`` + ``bvh_query_next(query, max_dist)`` (``bvh.h:472-482,
+    529-540``).  With a unit ``dir`` and ``max_dist`` = segment length this is the swept-sphere broad phase."""
+    return _run(bvh, starts, dirs, "capsule", float(max_dist), roots=roots, radii=radii)
 
 
 def bvh_get_group_root(bvh, group_ids):
@@ -125,4 +159,4 @@ def bvh_get_group_root(bvh, group_ids):
 def mesh_query_aabb(mesh, lowers, uppers) -> BvhQueryResult:
     """All faces of ``mesh`` whose AABB (as of its last build / refit) overlaps ``[lowers[i], uppers[i]]``, in the
     order the reference's ``mesh_query_aabb`` / ``mesh_query_aabb_next`` loop yields them (``mesh.h:2476-2712``)."""
-    return _run(mesh, lowers, uppers, False, 0.0, mesh=True)
+    return _run(mesh, lowers, uppers, "aabb", 0.0, mesh=True)

@@ -1055,7 +1055,8 @@ static long long* g_scan_scratch[64] = {};
 static size_t g_scan_scratch_words[64] = {};
 
 static int bvh_query_common(uint64_t id, int ray, const float* qa, const float* qb, const int32_t* roots, int64_t n,
-                            float max_dist, int32_t* counts, const int32_t* offsets, int32_t* indices, bool want_mesh = false)
+                            float max_dist, int32_t* counts, const int32_t* offsets, int32_t* indices, bool want_mesh = false,
+                            const float* radii = nullptr)
 {
     MeshState* ms = nullptr;
     BvhState* s = find_tree(id, &ms);
@@ -1073,7 +1074,7 @@ static int bvh_query_common(uint64_t id, int ray, const float* qa, const float* 
         return 1;
     }
     const char* err = wb_bvh_query(make_view(*s), want_mesh ? nullptr : s->item_lowers, want_mesh ? nullptr : s->item_uppers,
-                                   ray, qa, qb, roots, n, max_dist, counts, offsets, indices, st);
+                                   ray, qa, qb, radii, roots, n, max_dist, counts, offsets, indices, st);
     if (err) {
         set_error("Warp error: BVH query failed: %s", err);
         return 0;
@@ -1100,6 +1101,27 @@ int wp_b200_bvh_query_ray_fill(uint64_t id, const float* starts, const float* di
                                float max_dist, const int32_t* offsets, int32_t* indices)
 {
     return bvh_query_common(id, 1, starts, dirs, roots, n, max_dist, nullptr, offsets, indices);
+}
+
+int wp_b200_bvh_query_sphere_count(uint64_t id, const float* centers, const float* radii, const int32_t* roots, int64_t n,
+                                   int32_t* counts)
+{
+    return bvh_query_common(id, 2, centers, centers, roots, n, 0.f, counts, nullptr, nullptr, false, radii);
+}
+int wp_b200_bvh_query_sphere_fill(uint64_t id, const float* centers, const float* radii, const int32_t* roots, int64_t n,
+                                  const int32_t* offsets, int32_t* indices)
+{
+    return bvh_query_common(id, 2, centers, centers, roots, n, 0.f, nullptr, offsets, indices, false, radii);
+}
+int wp_b200_bvh_query_capsule_count(uint64_t id, const float* starts, const float* dirs, const float* radii,
+                                    const int32_t* roots, int64_t n, float max_dist, int32_t* counts)
+{
+    return bvh_query_common(id, 3, starts, dirs, roots, n, max_dist, counts, nullptr, nullptr, false, radii);
+}
+int wp_b200_bvh_query_capsule_fill(uint64_t id, const float* starts, const float* dirs, const float* radii,
+                                   const int32_t* roots, int64_t n, float max_dist, const int32_t* offsets, int32_t* indices)
+{
+    return bvh_query_common(id, 3, starts, dirs, roots, n, max_dist, nullptr, offsets, indices, false, radii);
 }
 
 int wp_b200_mesh_query_aabb_count(uint64_t id, const float* lowers, const float* uppers, int64_t n, int32_t* counts)

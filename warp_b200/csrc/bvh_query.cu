@@ -38,12 +38,57 @@ __device__ __forceinline__ bool ray_box(float3 pos, float3 rcp, float3 lo, float
     return hit && !(lmin >= max_dist);
 }
 
-template <bool RAY>
-__device__ __forceinline__ bool test_box(float3 qa, float3 qb, float3 lo, float3 hi, float max_dist)
+// sphere-AABB overlap (intersect.h:197-205): squared distance from the centre to the box <= radius^2
+__device__ __forceinline__ bool sphere_box(float3 c, float radius_sq, float3 lo, float3 hi)
 {
-    if (RAY)
-        return ray_box(qa, qb, lo, hi, max_dist);
-    return overlap_aabb(qa, qb, lo, hi);
+    const float dx = fmaxf(fmaxf(lo.x - c.x, c.x - hi.x), 0.0f);
+    const float dy = fmaxf(fmaxf(lo.y - c.y, c.y - hi.y), 0.0f);
+    const float dz = fmaxf(fmaxf(lo.z - c.z, c.z - hi.z), 0.0f);
+    return dx * dx + dy * dy + dz * dz <= radius_sq;
+}
+
+// capsule node test (bvh.h:472-482): the box inflated by the radius against the robust slab test (intersect.h:158-181),
+// closed at max_dist.  `dir0` is what the reference passes as the direction: 1 / (1 / dir), only compared with zero.
+__device__ __forceinline__ bool capsule_box(float3 pos, float3 rcp, float3 dir0, float radius, float3 lo, float3 hi,
+                                            float max_dist)
+{
+    float lmin = -FLT_MAX, lmax = FLT_MAX;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float d = wb_get(dir0, k), o = wb_get(pos, k), l = wb_get(lo, k) - radius, u = wb_get(hi, k) + radius;
+        if (d == 0.0f) {
+            if (o < l || o > u)
+                return false;
+        } else {
+            const float r = wb_get(rcp, k);
+            const float l1 = (l - o) * r, l2 = (u - o) * r;
+            lmin = fmaxf(fminf(l1, l2), lmin);
+            lmax = fminf(fmaxf(l1, l2), lmax);
+        }
+    }
+    const bool hit = (lmax >= 0.f) & (lmax >= lmin);
+    return hit && !(lmin > max_dist);
+}
+
+// query kinds of the generic iterator (bvh.h:420-492)
+constexpr int KIND_AABB = 0, KIND_RAY = 1, KIND_SPHERE = 2, KIND_CAPSULE = 3;
+
+struct QueryArgs {
+    float3 qa, qb;  // AABB: lower, upper; RAY / CAPSULE: start, 1 / dir; SPHERE: centre
+    float3 dir0;    // CAPSULE: 1 / (1 / dir)
+    float radius, radius_sq;
+};
+
+template <int KIND>
+__device__ __forceinline__ bool test_box(const QueryArgs& q, float3 lo, float3 hi, float max_dist)
+{
+    if (KIND == KIND_RAY)
+        return ray_box(q.qa, q.qb, lo, hi, max_dist);
+    if (KIND == KIND_SPHERE)
+        return sphere_box(q.qa, q.radius_sq, lo, hi);
+    if (KIND == KIND_CAPSULE)
+        return capsule_box(q.qa, q.qb, q.dir0, q.radius, lo, hi, max_dist);
+    return overlap_aabb(q.qa, q.qb, lo, hi);
 }
 
 __device__ __forceinline__ float3 ld3(const float* __restrict__ p, size_t i)
@@ -54,18 +99,27 @@ __device__ __forceinline__ float3 ld3(const float* __restrict__ p, size_t i)
 // RAY: (qa, qb) = (start, 1/dir);  AABB: (qa, qb) = (lower, upper).  FILL = false counts, true writes indices.
 // MESH: the tree is a wp.Mesh's (mesh_query_aabb, mesh.h:2476-2712): an item's box is its triangle's, taken from
 // the packed-triangle cache (== mesh.lowers/uppers of the last build / refit, mesh.cu:16-36)
-template <bool RAY, bool FILL, bool MESH>
+// SPHERE: (qa, radii) = (centre, radius);  CAPSULE: (qa, qb, radii) = (start, dir, radius), closed at max_dist.
+template <int KIND, bool FILL, bool MESH>
 __global__ void __launch_bounds__(BQ)
 k_bvh_query(TreeView tv, const float* __restrict__ item_lowers, const float* __restrict__ item_uppers,
-            const float* __restrict__ qa_in, const float* __restrict__ qb_in, const int* __restrict__ roots, long long nq,
-            float max_dist, int* __restrict__ counts, const int* __restrict__ offsets, int* __restrict__ indices)
+            const float* __restrict__ qa_in, const float* __restrict__ qb_in, const float* __restrict__ radii,
+            const int* __restrict__ roots, long long nq, float max_dist, int* __restrict__ counts, const int* __restrict__ offsets, int* __restrict__ indices)
 {
     const TreeHeader h = *tv.header;
     for (long long i = (long long)blockIdx.x * BQ + threadIdx.x; i < nq; i += (long long)gridDim.x * BQ) {
-        const float3 qa = ld3(qa_in, (size_t)i);
-        float3 qb = ld3(qb_in, (size_t)i);
-        if (RAY)
-            qb = make_float3(1.0f / qb.x, 1.0f / qb.y, 1.0f / qb.z);  // bvh_query_ray stores 1/dir (bvh.h:526-531)
+        QueryArgs q;
+        q.qa = ld3(qa_in, (size_t)i);
+        q.qb = KIND == KIND_SPHERE ? q.qa : ld3(qb_in, (size_t)i);
+        q.dir0 = q.qb, q.radius = 0.f, q.radius_sq = 0.f;
+        if (KIND == KIND_RAY || KIND == KIND_CAPSULE)
+            q.qb = make_float3(1.0f / q.qb.x, 1.0f / q.qb.y, 1.0f / q.qb.z);  // bvh_query_ray stores 1/dir (bvh.h:526-531)
+        if (KIND == KIND_CAPSULE)
+            q.dir0 = make_float3(1.0f / q.qb.x, 1.0f / q.qb.y, 1.0f / q.qb.z);  // bvh.h:476-478
+        if (KIND == KIND_SPHERE || KIND == KIND_CAPSULE) {
+            q.radius = fmaxf(__ldg(radii + i), 0.0f);  // bvh.h:537-538, 548-549
+            q.radius_sq = q.radius * q.radius;
+        }
         int found = 0;
         int* out = FILL ? indices + offsets[i] : nullptr;
 
@@ -94,7 +148,7 @@ k_bvh_query(TreeView tv, const float* __restrict__ item_lowers, const float* __r
         } else if (r >= tv.n) {
             wb_root_entry(tv, r, start.a, start.b, rlo, rhi);
         }
-        if (test_box<RAY>(qa, qb, rlo, rhi, max_dist))
+        if (test_box<KIND>(q, rlo, rhi, max_dist))
             stack[top++] = start;
         while (top) {
             const Entry2 cur = stack[--top];
@@ -119,7 +173,7 @@ k_bvh_query(TreeView tv, const float* __restrict__ item_lowers, const float* __r
                             ilo = ld3(item_lowers, (size_t)item);
                             ihi = ld3(item_uppers, (size_t)item);
                         }
-                        if (test_box<RAY>(qa, qb, ilo, ihi, max_dist)) {
+                        if (test_box<KIND>(q, ilo, ihi, max_dist)) {
                             if (FILL)
                                 out[found] = item;
                             ++found;
@@ -135,7 +189,7 @@ k_bvh_query(TreeView tv, const float* __restrict__ item_lowers, const float* __r
             const uint32_t rref = __float_as_uint(b0.w), raux = __float_as_uint(b1.w);
             // left is pushed first, right second => the right child is popped (reported) first (bvh.h:603-606);
             // a child whose box fails the test is simply not pushed (the reference pops and discards it)
-            if (test_box<RAY>(qa, qb, make_float3(a0.x, a0.y, a0.z), make_float3(a1.x, a1.y, a1.z), max_dist)) {
+            if (test_box<KIND>(q, make_float3(a0.x, a0.y, a0.z), make_float3(a1.x, a1.y, a1.z), max_dist)) {
                 Entry2 e;
                 if (lref & WB_LEAF)
                     e.a = laux | WB_LEAF, e.b = s - laux + 1;
@@ -143,7 +197,7 @@ k_bvh_query(TreeView tv, const float* __restrict__ item_lowers, const float* __r
                     e.a = (lref & WB_IDX_MASK) - (uint32_t)tv.n, e.b = 0;
                 stack[top++] = e;
             }
-            if (test_box<RAY>(qa, qb, make_float3(b0.x, b0.y, b0.z), make_float3(b1.x, b1.y, b1.z), max_dist)) {
+            if (test_box<KIND>(q, make_float3(b0.x, b0.y, b0.z), make_float3(b1.x, b1.y, b1.z), max_dist)) {
                 Entry2 e;
                 if (rref & WB_LEAF)
                     e.a = (s + 1) | WB_LEAF, e.b = raux - s;
@@ -311,35 +365,41 @@ int grid_for(long long nq)
 
 }  // namespace
 
-const char* wb_bvh_query(const TreeView& tv, const float* item_lowers, const float* item_uppers, int ray,
-                         const float* qa, const float* qb, const int* roots, long long nq, float max_dist, int* counts,
-                         const int* offsets, int* indices, cudaStream_t stream)
+const char* wb_bvh_query(const TreeView& tv, const float* item_lowers, const float* item_uppers, int kind,
+                         const float* qa, const float* qb, const float* radii, const int* roots, long long nq,
+                         float max_dist, int* counts, const int* offsets, int* indices, cudaStream_t stream)
 {
     if (nq <= 0)
         return nullptr;
     const int grid = grid_for(nq);
     const bool fill = offsets != nullptr;
     const bool mesh = item_lowers == nullptr;  // items are the triangles of tv.tris
-#define WB_BQ_LAUNCH(R, F, M) \
-    k_bvh_query<R, F, M><<<grid, BQ, 0, stream>>>(tv, item_lowers, item_uppers, qa, qb, roots, nq, max_dist, counts, offsets, indices)
+#define WB_BQ_LAUNCH(K, F, M) \
+    k_bvh_query<K, F, M><<<grid, BQ, 0, stream>>>(tv, item_lowers, item_uppers, qa, qb, radii, roots, nq, max_dist, counts, offsets, indices)
+#define WB_BQ_KIND(K)                    \
+    do {                                 \
+        if (fill)                        \
+            WB_BQ_LAUNCH(K, true, false);  \
+        else                             \
+            WB_BQ_LAUNCH(K, false, false); \
+    } while (0)
     if (mesh) {
-        if (ray)
-            return "ray hit lists are defined for wp.Bvh only";
+        if (kind != KIND_AABB)
+            return "only AABB hit lists are defined for a wp.Mesh";
         if (fill)
-            WB_BQ_LAUNCH(false, true, true);
+            WB_BQ_LAUNCH(KIND_AABB, true, true);
         else
-            WB_BQ_LAUNCH(false, false, true);
-    } else if (ray) {
-        if (fill)
-            WB_BQ_LAUNCH(true, true, false);
-        else
-            WB_BQ_LAUNCH(true, false, false);
+            WB_BQ_LAUNCH(KIND_AABB, false, true);
+    } else if (kind == KIND_RAY) {
+        WB_BQ_KIND(KIND_RAY);
+    } else if (kind == KIND_SPHERE) {
+        WB_BQ_KIND(KIND_SPHERE);
+    } else if (kind == KIND_CAPSULE) {
+        WB_BQ_KIND(KIND_CAPSULE);
     } else {
-        if (fill)
-            WB_BQ_LAUNCH(false, true, false);
-        else
-            WB_BQ_LAUNCH(false, false, false);
+        WB_BQ_KIND(KIND_AABB);
     }
+#undef WB_BQ_KIND
 #undef WB_BQ_LAUNCH
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);

@@ -2,12 +2,13 @@
 #pragma once
 #include "common.cuh"
 
-// generic BVH queries (bvh_query.cu): ray != 0 -> (qa, qb) = (start, dir) else (lower, upper).  offsets == NULL
+// generic BVH queries (bvh_query.cu).  kind 0: (qa, qb) = (lower, upper); 1 ray: (start, dir), half-open max_dist;
+// 2 sphere: qa = centre, radii[nq]; 3 capsule: (start, dir), radii[nq], closed max_dist (bvh.h:462-492).  offsets == NULL
 // counts hits into counts[nq]; otherwise writes the hit items of query i at indices[offsets[i]...]
 // roots: optional per-query start node (reference node index, e.g. from wb_group_roots; < 0 = the tree root)
-const char* wb_bvh_query(const TreeView& tv, const float* item_lowers, const float* item_uppers, int ray,
-                         const float* qa, const float* qb, const int* roots, long long nq, float max_dist, int* counts,
-                         const int* offsets, int* indices, cudaStream_t stream);
+const char* wb_bvh_query(const TreeView& tv, const float* item_lowers, const float* item_uppers, int kind,
+                         const float* qa, const float* qb, const float* radii, const int* roots, long long nq,
+                         float max_dist, int* counts, const int* offsets, int* indices, cudaStream_t stream);
 // bvh_get_group_root for a batch; keys = the tree's 64-bit (group << 32 | code) keys, NULL for an ungrouped tree
 const char* wb_group_roots(const TreeView& tv, const void* keys, const int* group_ids, long long nq, int* roots,
                            cudaStream_t stream);
