@@ -282,6 +282,13 @@ WP_B200_API int wp_b200_bvh_query_capsule_count(uint64_t id, const float* starts
 WP_B200_API int wp_b200_bvh_query_capsule_fill(uint64_t id, const float* starts, const float* dirs, const float* radii,
                                                const int32_t* roots, int64_t n, float max_dist, const int32_t* offsets,
                                                int32_t* indices);
+/* wp.mesh_query_sphere + the mesh_query_sphere_next loop (mesh.h:2457-2737): the faces that intersect the sphere
+ * (centers[i], radii[i]) -- exact sphere / box test on nodes and face boxes, then the closest point of the triangle
+ * within the radius -- in the iterator's order; faces are taken as of the last build / refit */
+WP_B200_API int wp_b200_mesh_query_sphere_count(uint64_t id, const float* centers, const float* radii, int64_t n,
+                                                int32_t* counts);
+WP_B200_API int wp_b200_mesh_query_sphere_fill(uint64_t id, const float* centers, const float* radii, int64_t n,
+                                               const int32_t* offsets, int32_t* indices);
 /* wp.bvh_get_group_root (bvh.h:376-390) for a batch of group ids: roots[i] = reference index of the node that holds
  * exactly the items of group_ids[i] (a leaf for a one-item group), -1 when the group does not occur.  On a tree
  * built without groups every item is in group 0. */

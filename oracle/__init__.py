@@ -282,6 +282,23 @@ def mesh_face_normal(points, indices, face):
     return out
 
 
+def mesh_query_sphere(points, indices, tree, centers, radii):
+    """mesh_query_sphere restatement (mesh.h:2457-2737): (offsets[n+1], face indices) in iterator order; the face boxes
+    of the broad phase are those of ``points`` (= mesh.lowers / uppers right after a build or refit)."""
+    points, indices, targs = _tree_args(points, indices, tree)
+    tlo, thi = triangle_bounds(points, indices)
+    tlo, thi = _f32(tlo, (-1, 3)), _f32(thi, (-1, 3))
+    c = _f32(centers, (-1, 3))
+    n = c.shape[0]
+    r = np.ascontiguousarray(np.broadcast_to(np.asarray(radii, np.float32), (n,)))
+    offsets = np.zeros(n + 1, np.int32)
+    args = (*targs, _p(tlo, _f32p), _p(thi, _f32p), _p(c, _f32p), _p(r, _f32p), ctypes.c_int64(n))
+    orc().orc_mesh_query_sphere(*args, _p(offsets, _i32p), None)
+    out = np.zeros(max(int(offsets[-1]), 1), np.int32)
+    orc().orc_mesh_query_sphere(*args, _p(offsets, _i32p), _p(out, _i32p))
+    return offsets, out[: int(offsets[-1])]
+
+
 def query_ray_anyhit(points, indices, tree, starts, dirs, max_t, roots=None):
     """mesh_query_ray_anyhit restatement (mesh.h:1893-1974)."""
     points, indices, targs = _tree_args(points, indices, tree)
@@ -511,6 +528,21 @@ class RefMesh:
         indices = np.zeros(max(int(offsets[-1]), 1), np.int32)
         ref().ref_mesh_query_aabb(ctypes.c_uint64(self.id), _p(lo, _f32p), _p(hi, _f32p), ctypes.c_int64(n), _p(offsets, _i32p),
                                   _p(indices, _i32p))
+        return offsets, indices[: int(offsets[-1])]
+
+    def query_sphere(self, centers, radii, item_bounds=None):
+        """mesh_query_sphere iterator run to exhaustion per query: (offsets[n+1], indices); see query_aabb."""
+        c = _f32(centers, (-1, 3))
+        n = c.shape[0]
+        r = np.ascontiguousarray(np.broadcast_to(np.asarray(radii, np.float32), (n,)))
+        if item_bounds is not None:
+            self._item_bounds = (_f32(item_bounds[0], (-1, 3)), _f32(item_bounds[1], (-1, 3)))
+            ref().ref_mesh_set_bounds(ctypes.c_uint64(self.id), _p(self._item_bounds[0], _f32p), _p(self._item_bounds[1], _f32p))
+        offsets = np.zeros(n + 1, np.int32)
+        ref().ref_mesh_query_sphere(ctypes.c_uint64(self.id), _p(c, _f32p), _p(r, _f32p), ctypes.c_int64(n), _p(offsets, _i32p), None)
+        indices = np.zeros(max(int(offsets[-1]), 1), np.int32)
+        ref().ref_mesh_query_sphere(ctypes.c_uint64(self.id), _p(c, _f32p), _p(r, _f32p), ctypes.c_int64(n), _p(offsets, _i32p),
+                                    _p(indices, _i32p))
         return offsets, indices[: int(offsets[-1])]
 
     def eval(self, face, u, v, velocity=False):

@@ -1330,3 +1330,85 @@ void orc_mesh_face_normal(const float* points, const int* indices, const int* fa
         out[3 * i] = nn.x, out[3 * i + 1] = nn.y, out[3 * i + 2] = nn.z;
     }
 }
+
+/* mesh_query_sphere + mesh_query_sphere_next run to exhaustion (mesh.h:2457-2737): node test = exact sphere / box
+ * (intersect.h:197-205); face test (also on single-face leaves) = the same test on the face's box (mesh.lowers /
+ * uppers of the last build / refit, passed in), then the closest point of the triangle -- of its longest edge for a
+ * zero-area face -- within the radius.  offsets[n+1]; indices may be NULL (count only). */
+static int sphere_aabb(v3 c, float radius_sq, const float* lo, const float* hi)
+{
+    const float dx = fmax_ref(fmax_ref(lo[0] - c.x, c.x - hi[0]), 0.0f);
+    const float dy = fmax_ref(fmax_ref(lo[1] - c.y, c.y - hi[1]), 0.0f);
+    const float dz = fmax_ref(fmax_ref(lo[2] - c.z, c.z - hi[2]), 0.0f);
+    return dx * dx + dy * dy + dz * dz <= radius_sq;
+}
+
+static int sphere_face(const orc_mesh* m, const float* tri_lowers, const float* tri_uppers, v3 center, float radius_sq,
+                       int prim)
+{
+    if (!sphere_aabb(center, radius_sq, tri_lowers + 3 * prim, tri_uppers + 3 * prim))
+        return 0;
+    const v3 a = v3_ld(m->points, m->indices[3 * prim + 0]), b = v3_ld(m->points, m->indices[3 * prim + 1]),
+             c = v3_ld(m->points, m->indices[3 * prim + 2]);
+    const v3 ab = v3_sub(b, a), ac = v3_sub(c, a);
+    const v3 n = v3_cross(ab, ac);
+    v3 cp;
+    if (v3_dot(n, n) == 0.0f) {
+        const v3 bc = v3_sub(c, b);
+        const float lab2 = v3_dot(ab, ab), lac2 = v3_dot(ac, ac), lbc2 = v3_dot(bc, bc);
+        v3 p, q;
+        float len2;
+        if (lab2 >= lac2 && lab2 >= lbc2)
+            p = a, q = b, len2 = lab2;
+        else if (lac2 >= lbc2)
+            p = a, q = c, len2 = lac2;
+        else
+            p = b, q = c, len2 = lbc2;
+        const v3 pq = v3_sub(q, p);
+        const float t = (len2 > 0.0f) ? fmin_ref(fmax_ref(0.0f, v3_dot(v3_sub(center, p), pq) / len2), 1.0f) : 0.0f;
+        cp = v3_add(p, v3_scale(t, pq));
+    } else {
+        float uv[2];
+        orc_closest_point_to_triangle(&a.x, &b.x, &c.x, &center.x, uv);
+        cp = v3_add(v3_add(v3_scale(uv[0], a), v3_scale(uv[1], b)), v3_scale(1.0f - uv[0] - uv[1], c));
+    }
+    const v3 d = v3_sub(cp, center);
+    return v3_dot(d, d) <= radius_sq;
+}
+
+void orc_mesh_query_sphere(const float* points, const int* indices, const orc_half* node_lowers, const orc_half* node_uppers,
+                           const int* primitive_indices, int root, const float* tri_lowers, const float* tri_uppers,
+                           const float* centers, const float* radii, int64_t n, int* offsets, int* out)
+{
+    const orc_mesh m = make_mesh(points, indices, node_lowers, node_uppers, primitive_indices, root);
+    int run = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        offsets[i] = run;
+        const v3 c = v3_ld(centers, i);
+        const float r = fmax_ref(radii[i], 0.0f);
+        const float r2 = r * r;
+        int stack[ORC_STACK * 2];
+        int count = 1;
+        stack[0] = root;
+        while (count) {
+            const int node = stack[--count];
+            const orc_half lo = node_lowers[node], hi = node_uppers[node];
+            if (!sphere_aabb(c, r2, &lo.x, &hi.x))
+                continue;
+            if (HALF_B(lo)) {
+                for (int k = HALF_I(lo); k < HALF_I(hi); ++k) {
+                    const int prim = primitive_indices[k];
+                    if (sphere_face(&m, tri_lowers, tri_uppers, c, r2, prim)) {
+                        if (out)
+                            out[run] = prim;
+                        ++run;
+                    }
+                }
+            } else {
+                stack[count++] = HALF_I(lo);
+                stack[count++] = HALF_I(hi);
+            }
+        }
+    }
+    offsets[n] = run;
+}

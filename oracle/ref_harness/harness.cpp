@@ -305,6 +305,23 @@ void ref_mesh_query_aabb(uint64_t id, const float* lowers, const float* uppers, 
     offsets[n] = run;
 }
 
+// mesh_query_sphere + mesh_query_sphere_next loop (mesh.h:2457-2737): offsets[n+1]; indices may be NULL (count only)
+void ref_mesh_query_sphere(uint64_t id, const float* centers, const float* radii, int64_t n, int* offsets, int* indices)
+{
+    int run = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        offsets[i] = run;
+        mesh_query_aabb_t q = mesh_query_sphere(id, vec3(centers[3 * i], centers[3 * i + 1], centers[3 * i + 2]), radii[i]);
+        int face;
+        while (mesh_query_sphere_next(q, face)) {
+            if (indices)
+                indices[run] = face;
+            ++run;
+        }
+    }
+    offsets[n] = run;
+}
+
 // generic wp.Bvh iterator (bvh.h:494-664) and bvh_get_group_root (bvh.h:376-390) over a caller-supplied tree in the
 // reference layout.  ray: (qa, qb) = (start, dir), else (lower, upper); roots optional (-1 / NULL = tree root).
 static BVH make_bvh(const void* node_lowers, const void* node_uppers, const int* parents, const int* prim,

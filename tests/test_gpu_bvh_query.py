@@ -201,3 +201,41 @@ def test_bvh_sphere_and_capsule_queries(wp, oracle_mod, leaf):
     assert wp.bvh_query_sphere(bvh, z, 1.0).total == 0 and wp.bvh_query_capsule(bvh, z, z, 1.0).total == 0
     with pytest.raises(RuntimeError):
         wp.bvh_query_sphere(bvh, C, R[:5])
+
+
+@pytest.mark.parametrize("leaf", [1, 4])
+def test_mesh_query_sphere(wp, oracle_mod, leaf):
+    """mesh_query_sphere: exact face lists in iterator order against the restatement (pinned on the reference C++),
+    incl. zero-area faces, scalar and per-query radii, after a refit, empty batch; fixture from the reference."""
+    import os
+
+    from warp_b200 import meshgen as mg
+
+    P, I = mg.noisy_sphere(4, 0.05, 141)
+    I = np.concatenate([I, np.array([0, 0, 5, 3, 7, 7, 10, 10, 10], np.int32)]).astype(np.int32)
+    rng = np.random.default_rng(142)
+    C = np.concatenate([mg.box_queries(P, 6000, seed=143), P[:500]]).astype(np.float32)
+    R = (rng.random(len(C)) * 0.3 - 0.01).astype(np.float32)
+    pts = wp.array(P, dtype=wp.vec3)
+    m = wp.Mesh(pts, wp.array(I, dtype=wp.int32), bvh_constructor="lbvh", bvh_leaf_size=leaf)
+    tree = oracle_mod.mesh_lbvh_build(P, I, leaf)
+    for radii in (R, 0.1):
+        off, idx = wp.mesh_query_sphere(m, C, radii).numpy()
+        woff, widx = oracle_mod.mesh_query_sphere(P, I, tree, C, radii)
+        assert int(woff[-1]) > 1000 and np.array_equal(off, woff) and np.array_equal(idx, widx)
+    P2 = mg.renoise_sphere(P, 0.05, 144)
+    pts.assign(P2)
+    m.refit()
+    lo2, hi2 = oracle_mod.triangle_bounds(P2, I)
+    oracle_mod.lbvh_refit(tree, lo2, hi2)
+    off, idx = wp.mesh_query_sphere(m, wp.array(C, dtype=wp.vec3), wp.array(R, dtype=wp.float32)).numpy()
+    woff, widx = oracle_mod.mesh_query_sphere(P2, I, tree, C, R)
+    assert np.array_equal(off, woff) and np.array_equal(idx, widx)
+    assert wp.mesh_query_sphere(m, np.zeros((0, 3), np.float32), 1.0).total == 0
+    # the reference's own answers (fixture)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_bvh_kinds.npz"))
+    gc = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_cpu.npz"))
+    gm = wp.Mesh(wp.array(gc["mesh_points"], dtype=wp.vec3), wp.array(g["mesh_indices"], dtype=wp.int32),
+                 bvh_constructor="lbvh", bvh_leaf_size=leaf)
+    off, idx = wp.mesh_query_sphere(gm, g["mesh_centers"], g["mesh_radii"]).numpy()
+    assert np.array_equal(off, g[f"mesh_leaf{leaf}_sphere_offsets"]) and np.array_equal(idx, g[f"mesh_leaf{leaf}_sphere_indices"])

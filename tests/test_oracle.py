@@ -564,6 +564,33 @@ def test_bvh_sphere_capsule_restatement(oracle_mod):
             assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 
 
+def test_mesh_query_sphere_restatement(oracle_mod, gold):
+    """mesh_query_sphere: fixture from the reference C++ (tests/golden/make_golden_bvh_kinds.py; the mesh carries three
+    zero-area faces), exact lists in iterator order, and the sets against a numpy closest-point check."""
+    o = oracle_mod
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_bvh_kinds.npz"))
+    P, I, C, R = gold["mesh_points"], g["mesh_indices"], g["mesh_centers"], g["mesh_radii"]
+    for leaf in (1, 4):
+        tree = o.mesh_lbvh_build(P, I, leaf)
+        off, idx = o.mesh_query_sphere(P, I, tree, C, R)
+        assert np.array_equal(off, g[f"mesh_leaf{leaf}_sphere_offsets"]) and np.array_equal(idx, g[f"mesh_leaf{leaf}_sphere_indices"])
+    # same faces as "closest point of the face within the radius" evaluated face by face (non-degenerate faces)
+    T = I.reshape(-1, 3)[:-3]
+    tree = o.mesh_lbvh_build(P, T.reshape(-1), 4)
+    off, idx = o.mesh_query_sphere(P, T.reshape(-1), tree, C[:60], R[:60])
+    for i in range(60):
+        got = sorted(idx[off[i] : off[i + 1]].tolist())
+        rr = max(float(R[i]), 0.0)
+        want = []
+        for f, (a, b, c) in enumerate(T):
+            uv = o.closest_point_to_triangle(P[a], P[b], P[c], C[i])
+            cp = P[a] * uv[0] + P[b] * uv[1] + P[c] * (np.float32(1) - uv[0] - uv[1])
+            d = cp - C[i]
+            if np.float32(d @ d) <= np.float32(rr * rr) * np.float32(1 + 1e-5):
+                want.append(f)
+        assert set(got) <= set(want) and len(want) - len(got) <= 1  # (one borderline face at most)
+
+
 def _grouped_mesh_case():
     P, I = mg.noisy_sphere(3, noise=0.05, seed=61)
     T = len(I) // 3

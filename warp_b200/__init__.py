@@ -63,6 +63,7 @@ from .bvh_queries import (  # noqa: F401,E402
     bvh_query_aabb,
     bvh_query_ray,
     bvh_query_sphere,
+    mesh_query_sphere,
     bvh_query_capsule,
     mesh_query_aabb,
 )

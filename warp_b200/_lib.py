@@ -120,6 +120,8 @@ SIGNATURES = {
     "wp_b200_bvh_query_aabb_fill": (_i, [_u64, _vp, _vp, _vp, _i64, _vp, _vp]),
     "wp_b200_bvh_query_ray_count": (_i, [_u64, _vp, _vp, _vp, _i64, _f, _vp]),
     "wp_b200_bvh_query_ray_fill": (_i, [_u64, _vp, _vp, _vp, _i64, _f, _vp, _vp]),
+    "wp_b200_mesh_query_sphere_count": (_i, [_u64, _vp, _vp, _i64, _vp]),
+    "wp_b200_mesh_query_sphere_fill": (_i, [_u64, _vp, _vp, _i64, _vp, _vp]),
     "wp_b200_bvh_query_sphere_count": (_i, [_u64, _vp, _vp, _vp, _i64, _vp]),
     "wp_b200_bvh_query_sphere_fill": (_i, [_u64, _vp, _vp, _vp, _i64, _vp, _vp]),
     "wp_b200_bvh_query_capsule_count": (_i, [_u64, _vp, _vp, _vp, _vp, _i64, _f, _vp]),

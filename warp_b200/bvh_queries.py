@@ -88,6 +88,9 @@ def _run(bvh, qa, qb, kind, max_dist, mesh=False, roots=None, radii=None):
 
     def call(fill):
         tail = (p(offsets), p(indices)) if fill else (p(counts),)
+        if mesh and kind == "sphere":
+            fn = c.wp_b200_mesh_query_sphere_fill if fill else c.wp_b200_mesh_query_sphere_count
+            return fn(bvh.id, p(qa), p(rad), n, *tail)
         if mesh:
             fn = c.wp_b200_mesh_query_aabb_fill if fill else c.wp_b200_mesh_query_aabb_count
             return fn(bvh.id, p(qa), p(qb), n, *tail)
@@ -160,3 +163,10 @@ def mesh_query_aabb(mesh, lowers, uppers) -> BvhQueryResult:
     """All faces of ``mesh`` whose AABB (as of its last build / refit) overlaps ``[lowers[i], uppers[i]]``, in the
     order the reference's ``mesh_query_aabb`` / ``mesh_query_aabb_next`` loop yields them (``mesh.h:2476-2712``)."""
     return _run(mesh, lowers, uppers, "aabb", 0.0, mesh=True)
+
+
+def mesh_query_sphere(mesh, centers, radii) -> BvhQueryResult:
+    """All faces of ``mesh`` (as of its last build / refit) that intersect the sphere ``(centers[i], radii[i])`` --
+    ``radii`` an array or one float -- in the order the reference's ``mesh_query_sphere`` / ``mesh_query_sphere_next``
+    loop yields them (``mesh.h:2457-2737``): exact sphere / box broad phase, closest-point narrow phase."""
+    return _run(mesh, centers, None, "sphere", 0.0, mesh=True, radii=radii)

@@ -1134,6 +1134,36 @@ int wp_b200_mesh_query_aabb_fill(uint64_t id, const float* lowers, const float* 
     return bvh_query_common(id, 0, lowers, uppers, nullptr, n, 0.f, nullptr, offsets, indices, true);
 }
 
+static int mesh_query_sphere_common(uint64_t id, const float* centers, const float* radii, int64_t n, int32_t* counts,
+                                    const int32_t* offsets, int32_t* indices)
+{
+    MeshState* m = query_mesh(id);
+    if (!m)
+        return 0;
+    DeviceGuard g(m->bvh.device);
+    cudaStream_t st = current_stream(m->bvh.device);
+    if (n <= 0)
+        return 1;
+    if (m->bvh.n == 0)
+        return offsets ? 1 : (check(cudaMemsetAsync(counts, 0, 4 * (size_t)n, st), "memset") ? 1 : 0);
+    const char* err = wb_mesh_query_sphere(make_view(m->bvh), centers, radii, n, counts, offsets, indices, st);
+    if (err) {
+        set_error("Warp error: mesh sphere query failed: %s", err);
+        return 0;
+    }
+    return 1;
+}
+
+int wp_b200_mesh_query_sphere_count(uint64_t id, const float* centers, const float* radii, int64_t n, int32_t* counts)
+{
+    return mesh_query_sphere_common(id, centers, radii, n, counts, nullptr, nullptr);
+}
+int wp_b200_mesh_query_sphere_fill(uint64_t id, const float* centers, const float* radii, int64_t n, const int32_t* offsets,
+                                   int32_t* indices)
+{
+    return mesh_query_sphere_common(id, centers, radii, n, nullptr, offsets, indices);
+}
+
 // bvh_get_group_root (bvh.h:376-390) for a batch of group ids: reference node index of the subtree that holds
 // exactly the items of the group, -1 when the group does not occur
 int wp_b200_bvh_get_group_root(uint64_t id, const int32_t* group_ids, int64_t n, int32_t* roots)

@@ -1033,6 +1033,99 @@ k_mesh_face_normal(const float* __restrict__ points, const int* __restrict__ ind
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// mesh_query_sphere + mesh_query_sphere_next (mesh.h:2457-2616, 2694-2737) for a batch: the faces that intersect the
+// sphere, in the iterator's order (children pushed left then right, leaf items in leaf order).  Node test: exact
+// sphere / box (intersect.h:197-205).  Face test, also on single-face leaves: the same test on the face's box, then the
+// closest point of the triangle -- of its longest edge when the face has zero area -- within the radius.
+// FILL = false counts, true writes the face indices at indices[offsets[i]...].
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool sphere_box_sq(float3 c, float radius_sq, float3 lo, float3 hi)
+{
+    const float dx = fmaxf(fmaxf(lo.x - c.x, c.x - hi.x), 0.0f);
+    const float dy = fmaxf(fmaxf(lo.y - c.y, c.y - hi.y), 0.0f);
+    const float dz = fmaxf(fmaxf(lo.z - c.z, c.z - hi.z), 0.0f);
+    return dx * dx + dy * dy + dz * dz <= radius_sq;
+}
+
+__device__ __forceinline__ bool sphere_face(float3 center, float radius_sq, const Tri& t)
+{
+    if (!sphere_box_sq(center, radius_sq, wb_min3(wb_min3(t.p, t.q), t.r), wb_max3(wb_max3(t.p, t.q), t.r)))
+        return false;
+    const float3 a = t.p, b = t.q, c = t.r;
+    const float3 ab = wb_sub(b, a), ac = wb_sub(c, a);
+    const float3 n = wb_cross(ab, ac);
+    float3 cp;
+    if (wb_dot(n, n) == 0.0f) {  // degenerate face: closest point of its longest edge (mesh.h:2589-2611)
+        const float3 bc = wb_sub(c, b);
+        const float lab2 = wb_dot(ab, ab), lac2 = wb_dot(ac, ac), lbc2 = wb_dot(bc, bc);
+        float3 p, q;
+        float len2;
+        if (lab2 >= lac2 && lab2 >= lbc2)
+            p = a, q = b, len2 = lab2;
+        else if (lac2 >= lbc2)
+            p = a, q = c, len2 = lac2;
+        else
+            p = b, q = c, len2 = lbc2;
+        const float3 pq = wb_sub(q, p);
+        const float tt = (len2 > 0.0f) ? fminf(fmaxf(0.0f, wb_dot(wb_sub(center, p), pq) / len2), 1.0f) : 0.0f;
+        cp = wb_add(p, wb_scale(tt, pq));
+    } else {
+        float bv, bw;
+        closest_vw(a, b, c, center, bv, bw);
+        const float bu = 1.0f - bv - bw;
+        cp = wb_add(wb_add(wb_scale(bu, a), wb_scale(bv, b)), wb_scale(1.0f - bu - bv, c));
+    }
+    const float3 d = wb_sub(cp, center);
+    return wb_dot(d, d) <= radius_sq;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(QT)
+k_mesh_query_sphere(TreeView tv, const float* __restrict__ centers, const float* __restrict__ radii, long long nq,
+                    int* __restrict__ counts, const int* __restrict__ offsets, int* __restrict__ indices)
+{
+    const TreeHeader h = *tv.header;
+    for (long long i = (long long)blockIdx.x * QT + threadIdx.x; i < nq; i += (long long)gridDim.x * QT) {
+        const float3 c = make_float3(__ldg(centers + 3 * i), __ldg(centers + 3 * i + 1), __ldg(centers + 3 * i + 2));
+        const float r = fmaxf(__ldg(radii + i), 0.0f);  // mesh.h:2525-2526
+        const float r2 = r * r;
+        int found = 0;
+        int* out = FILL ? indices + offsets[i] : nullptr;
+        Entry stack[WB_QUERY_STACK];
+        int top = 0;
+        if (sphere_box_sq(c, r2, make_float3(h.lx, h.ly, h.lz), make_float3(h.hx, h.hy, h.hz))) {
+            if (h.root_ref & WB_LEAF)
+                stack[0].a = WB_LEAF | 0u, stack[0].b = h.root_count;
+            else
+                stack[0].a = (h.root_ref & WB_IDX_MASK) - (uint32_t)tv.n, stack[0].b = 0;
+            top = 1;
+        }
+        while (top) {
+            const Entry cur = stack[--top];
+            if (cur.a & WB_LEAF) {
+                const uint32_t start = cur.a & WB_IDX_MASK;
+                for (uint32_t pos = start; pos < start + cur.b; ++pos) {
+                    const Tri t = load_tri(tv.tris, pos);
+                    if (sphere_face(c, r2, t)) {
+                        if (FILL)
+                            out[found] = t.face;
+                        ++found;
+                    }
+                }
+                continue;
+            }
+            const Pair pr = load_pair(tv.pairs, cur.a, tv.n);
+            if (sphere_box_sq(c, r2, pr.llo, pr.lhi))
+                stack[top++] = pr.left;
+            if (sphere_box_sq(c, r2, pr.rlo, pr.rhi))
+                stack[top++] = pr.right;
+        }
+        if (!FILL)
+            counts[i] = found;
+    }
+}
+
 // mesh_eval_position / mesh_eval_velocity (mesh.h:2767-2807): p*u + q*v + r*(1-u-v) from the caller's arrays
 __global__ void __launch_bounds__(QT)
 k_mesh_eval(const float* __restrict__ attr, const int* __restrict__ indices, const int* __restrict__ face,
@@ -1174,6 +1267,19 @@ const char* wb_mesh_face_normal(const float* points, const int* indices, const i
     if (n <= 0)
         return nullptr;
     k_mesh_face_normal<<<query_grid(n), QT, 0, stream>>>(points, indices, face, n, out);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+const char* wb_mesh_query_sphere(const TreeView& tv, const float* centers, const float* radii, long long nq, int* counts,
+                                 const int* offsets, int* indices, cudaStream_t stream)
+{
+    if (nq <= 0)
+        return nullptr;
+    if (offsets)
+        k_mesh_query_sphere<true><<<query_grid(nq), QT, 0, stream>>>(tv, centers, radii, nq, counts, offsets, indices);
+    else
+        k_mesh_query_sphere<false><<<query_grid(nq), QT, 0, stream>>>(tv, centers, radii, nq, counts, offsets, indices);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

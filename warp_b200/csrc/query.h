@@ -44,3 +44,6 @@ const char* wb_query_furthest(const TreeView& tv, const float* pts, long long nq
                               float* u, float* v, cudaStream_t stream);
 const char* wb_mesh_face_normal(const float* points, const int* indices, const int* face, long long n, float* out,
                                 cudaStream_t stream);
+// mesh_query_sphere hit lists (mesh.h:2457-2737): offsets == NULL counts into counts[nq], else fills indices
+const char* wb_mesh_query_sphere(const TreeView& tv, const float* centers, const float* radii, long long nq, int* counts,
+                                 const int* offsets, int* indices, cudaStream_t stream);
