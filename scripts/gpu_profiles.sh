@@ -14,7 +14,9 @@ timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'k_
 echo "build exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_refit|k_plan' -s 0 -c 12 -f -o gpurun_out/${R}_refit_wave python scripts/prof_refit_driver.py > gpurun_out/${R}_prof_r.log 2>&1
 echo "refit-wave exit $?"
-for f in ${R}_query_point ${R}_build_refit ${R}_refit_wave; do
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_query_ray' -s 2 -c 1 -f -o gpurun_out/${R}_query_ray python scripts/prof_ray_driver.py > gpurun_out/${R}_prof_ray.log 2>&1
+echo "ray exit $?"
+for f in ${R}_query_point ${R}_build_refit ${R}_refit_wave ${R}_query_ray; do
   ncu -i gpurun_out/$f.ncu-rep --page raw --csv > gpurun_out/$f.raw.csv 2>/dev/null
 done
 ls -la gpurun_out | tail -12

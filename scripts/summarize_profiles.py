@@ -98,5 +98,8 @@ table(os.path.join(G, f"{R}_refit_wave.raw.csv"), "Wavefront refit + its one-tim
       "command: `ncu --set full --clock-control none --import-source on -k regex:'k_refit|k_plan' -s 0 -c 12 python scripts/prof_refit_driver.py`. "
       "`k_plan_*` (+ 4 sort passes, not captured here) run once per build; a refit is `k_refit_leaves` + `k_refit_levels` + `k_refit_climb`.")
 
+table(os.path.join(G, f"{R}_query_ray.raw.csv"), "`k_query_ray` on C3 (9 999 392-triangle heightfield, 4096 x 4096 primary rays in row-major order)",
+      "command: `ncu --set full --clock-control none --import-source on -k regex:k_query_ray -s 2 -c 1 python scripts/prof_ray_driver.py`.")
+
 open(os.path.join(OUT, f"{R}_summary.md"), "w").write(f"# ncu summaries, round {R}\n\n" + "\n".join(lines) + "\n")
 print("wrote", os.path.join(OUT, f"{R}_summary.md"))
