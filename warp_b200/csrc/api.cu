@@ -681,7 +681,7 @@ static int query_point_on(MeshState* m, const float* points, int64_t n, float ma
     const int* perm = nullptr;
     if ((g_query_order == 1 || (g_query_order == 2 && n >= 32768)) && n < (1ll << 30)) {
         OrderScratch& ws = g_order[m->bvh.device][lane];
-        const char* oerr = wb_morton_order(ws, points, n, st);
+        const char* oerr = wb_morton_order(ws, points, n, st, !with_sign);
         if (oerr) {
             set_error("Warp error: query ordering failed: %s", oerr);
             return 0;
@@ -786,7 +786,7 @@ int wp_b200_mesh_query_point_sign_normal(uint64_t id, const float* points, int64
     const int* perm = nullptr;
     if ((g_query_order == 1 || (g_query_order == 2 && n >= 32768)) && n < (1ll << 30)) {
         OrderScratch& ws = g_order[m->bvh.device][0];
-        const char* oerr = wb_morton_order(ws, points, n, st);
+        const char* oerr = wb_morton_order(ws, points, n, st, true);
         if (oerr) {
             set_error("Warp error: query ordering failed: %s", oerr);
             return 0;

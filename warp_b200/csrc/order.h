@@ -18,8 +18,9 @@ struct OrderScratch {
     long long capacity = 0;
 };
 
-// after the call (stream-ordered) ws.idx[0..n) holds the query indices in Morton order
-const char* wb_morton_order(OrderScratch& ws, const float* pts, long long n, cudaStream_t stream);
+// after the call (stream-ordered) ws.idx[0..n) holds the query indices along a space-filling curve over the batch's
+// bounds: the 24-bit Hilbert curve (hilbert = true) or the top 24 bits of the Morton code
+const char* wb_morton_order(OrderScratch& ws, const float* pts, long long n, cudaStream_t stream, bool hilbert = false);
 // same for rays: 18 bits of origin cell (64^3 grid over the origins' bounds) above 12 bits of direction cell
 // (octahedral 64 x 64), so rays that start together and point the same way share a warp
 const char* wb_ray_order(OrderScratch& ws, const float* starts, const float* dirs, long long n, cudaStream_t stream);

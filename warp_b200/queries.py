@@ -340,9 +340,9 @@ QUERY_ORDER_INPUT, QUERY_ORDER_MORTON, QUERY_ORDER_AUTO = 0, 1, 2
 
 def set_query_order(mode: int) -> None:
     """How threads are assigned to the points of a batch: ``QUERY_ORDER_INPUT`` (thread i answers
-    point i), ``QUERY_ORDER_MORTON`` (the batch is Morton-sorted on the device first so a warp walks
-    one neighbourhood of the tree), ``QUERY_ORDER_AUTO`` (default: Morton for >= 32768 points).
-    Answers are identical in every mode."""
+    point i), ``QUERY_ORDER_MORTON`` (the batch is sorted along a space-filling curve on the device first -- the
+    24-bit Hilbert curve, or the Morton curve for the signed query -- so a warp walks one neighbourhood of the
+    tree), ``QUERY_ORDER_AUTO`` (default: sorted for >= 32768 points).  Answers are identical in every mode."""
     _lib.core().wp_b200_set_query_order(int(mode))
 
 
