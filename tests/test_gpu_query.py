@@ -383,6 +383,50 @@ def test_ray_variants_empty_inputs(wp):
         wp.mesh_query_ray_anyhit(m, np.zeros((3, 3), np.float32), np.zeros((2, 3), np.float32), 1.0)
 
 
+def test_signed_query_on_grid_aligned_probes(wp, oracle_mod):
+    """The sign probes are walked near child first, the reference walks them in a fixed order; both end on the same
+    triangle as long as equal hit distances are broken by the reference's visiting order (query.cu,
+    probe_sign_ordered).  Stress exactly that: regular meshes and query lattices aligned with them, so that the axis
+    probes run along shared edges and through shared vertices (exact ties in t, the fp64 fallback of the watertight
+    test).  Every field, sign included, must equal the reference-order restatement."""
+    def box_grid(n):  # closed box [0,1]^3, every face an n x n grid of quads split into two triangles
+        g = np.linspace(0.0, 1.0, n + 1, dtype=np.float32)
+        verts, tris = [], []
+        for axis in range(3):
+            for side in (0.0, 1.0):
+                base = len(verts)
+                for a in g:
+                    for b in g:
+                        p = [0.0, 0.0, 0.0]
+                        p[axis], p[(axis + 1) % 3], p[(axis + 2) % 3] = side, a, b
+                        verts.append(p)
+                for i in range(n):
+                    for j in range(n):
+                        v0, v1 = base + i * (n + 1) + j, base + (i + 1) * (n + 1) + j
+                        quad = (v0, v1, v1 + 1, v0 + 1)
+                        quad = quad if side == 1.0 else quad[::-1]  # outward orientation on both sides
+                        tris += [quad[0], quad[1], quad[2], quad[0], quad[2], quad[3]]
+        return np.asarray(verts, np.float32), np.asarray(tris, np.int32)
+
+    cases = []
+    P, I = box_grid(8)
+    lat = np.linspace(-0.25, 1.25, 13, dtype=np.float32)  # hits the face grid lines 0, 0.125, ... exactly
+    Q = np.stack(np.meshgrid(lat, lat, lat, indexing="ij"), axis=-1).reshape(-1, 3)
+    cases.append((P, I, Q))
+    P, I = mg.cloth(65, 3)  # open height field on a 65 x 65 vertex grid over [0,1]^2
+    gx = np.linspace(0.0, 1.0, 65, dtype=np.float32)[::4]
+    Q = np.stack(np.meshgrid(gx, gx, np.linspace(-0.1, 0.1, 9, dtype=np.float32), indexing="ij"), axis=-1).reshape(-1, 3)
+    cases.append((P, I, np.concatenate([Q, P[::7]]).astype(np.float32)))
+    for P, I, Q in cases:
+        for leaf in (1, 4):
+            m = gpu_mesh(wp, P, I, leaf)
+            tree = oracle_mod.mesh_lbvh_build(P, I, leaf)
+            want = oracle_mod.query_point(P, I, tree, Q, 1e6)
+            got = wp.mesh_query_point(m, Q, 1e6).numpy()
+            assert_results_equal(got, want, POINT_FIELDS)
+            assert (want["sign"] < 0).sum() > 10 and (want["sign"] > 0).sum() > 10
+
+
 def test_sign_parity(wp, oracle_mod):
     """mesh_query_point_sign_parity: bit-exact against the restatement in the order of the reference's device builds
     (offsets drawn x, y, z), on a closed mesh and on one with every other face removed."""

@@ -681,7 +681,10 @@ static int query_point_on(MeshState* m, const float* points, int64_t n, float ma
     const int* perm = nullptr;
     if ((g_query_order == 1 || (g_query_order == 2 && n >= 32768)) && n < (1ll << 30)) {
         OrderScratch& ws = g_order[m->bvh.device][lane];
-        const char* oerr = wb_morton_order(ws, points, n, st, !with_sign);
+#ifndef WB_SIGN_HILBERT
+#define WB_SIGN_HILBERT 0
+#endif
+        const char* oerr = wb_morton_order(ws, points, n, st, WB_SIGN_HILBERT || !with_sign);
         if (oerr) {
             set_error("Warp error: query ordering failed: %s", oerr);
             return 0;

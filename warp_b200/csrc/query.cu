@@ -409,14 +409,110 @@ __device__ __forceinline__ bool probe_sign(const TreeView& tv, const TreeHeader&
     return hit;
 }
 
+// The same probe, walked NEAR CHILD FIRST.  The reference's walk (above) visits nodes in a fixed order -- right subtree
+// before left, whatever the distance -- so its running bound tightens late.  Its ANSWER, though, does not depend on
+// that order: as long as a box is entered no later than any triangle inside it (t_entry <= t_hit), the walk ends on
+// the FIRST triangle, in its fixed order, among those with the smallest t.  That order is a function of sorted
+// positions alone -- leaves with a larger start come first, positions inside a leaf ascend -- so any traversal that
+// keeps subtrees whose entry is <= the bound (ties included) and breaks equal t by that rank returns the same
+// triangle, hence the same sign.  Near-first with early pruning reaches the hit after a few dozen nodes instead of
+// several hundred.  (-DWB_PROBE_REFERENCE_ORDER=1 builds the reference-order walk instead.)
+template <bool COUNT>
+__device__ __forceinline__ bool probe_sign_ordered(const TreeView& tv, const TreeHeader& h, float3 org, int axis,
+                                                   float& out_sign, Counters& cnt)
+{
+    const float3 dir = make_float3(axis == 0 ? 1.f : 0.f, axis == 1 ? 1.f : 0.f, axis == 2 ? 1.f : 0.f);
+    const WoopRay wr = woop_setup(dir);
+    const int a1 = axis == 0 ? 1 : 0, a2 = axis == 2 ? 1 : 2;
+    const float oa = wb_get(org, axis), o1 = wb_get(org, a1), o2 = wb_get(org, a2);
+
+    Entry stack[WB_QUERY_STACK];
+    float stack_t[WB_QUERY_STACK];
+    int top = 0;
+    float min_t = FLT_MAX;
+    uint32_t best_leaf = 0, best_pos = 0;
+    bool hit = false;
+
+    Entry cur;
+    float cur_t;
+    if (!ray_aabb_axis(oa, o1, o2, axis, a1, a2, make_float3(h.lx, h.ly, h.lz), make_float3(h.hx, h.hy, h.hz), cur_t))
+        return false;
+    if (h.root_ref & WB_LEAF)
+        cur.a = WB_LEAF | 0u, cur.b = h.root_count;
+    else
+        cur.a = (h.root_ref & WB_IDX_MASK) - (uint32_t)tv.n, cur.b = 0;
+    bool have = true;
+    for (;;) {
+        if (!have) {
+            if (top == 0)
+                break;
+            --top;
+            cur = stack[top];
+            cur_t = stack_t[top];
+        }
+        have = false;
+        if (cur_t > min_t)
+            continue;
+        if (cur.a & WB_LEAF) {
+            const uint32_t start = cur.a & WB_IDX_MASK;
+            for (uint32_t pos = start; pos < start + cur.b; ++pos) {
+                const Tri t = load_tri(tv.tris, pos);
+                if (COUNT)
+                    cnt.tris++;
+                float tt, tu, tvv, ts;
+                if (ray_tri(wr, org, t.p, t.q, t.r, tt, tu, tvv, ts) && tt >= 0.0f) {
+                    // strictly nearer, or equally near and earlier in the reference's visiting order
+                    const bool earlier = start > best_leaf || (start == best_leaf && pos < best_pos);
+                    if (tt < min_t || (hit && tt == min_t && earlier)) {
+                        min_t = tt;
+                        out_sign = ts;
+                        best_leaf = start, best_pos = pos;
+                        hit = true;
+                    }
+                }
+            }
+            continue;
+        }
+        const Pair pr = load_pair(tv.pairs, cur.a, tv.n);
+        if (COUNT)
+            cnt.pairs++;
+        float tl, tr;
+        const bool hl = ray_aabb_axis(oa, o1, o2, axis, a1, a2, pr.llo, pr.lhi, tl) && tl <= min_t;
+        const bool hr = ray_aabb_axis(oa, o1, o2, axis, a1, a2, pr.rlo, pr.rhi, tr) && tr <= min_t;
+        if (hl && hr) {
+            const bool near_left = tl < tr;
+            stack[top] = near_left ? pr.right : pr.left;
+            stack_t[top] = near_left ? tr : tl;
+            ++top;
+            cur = near_left ? pr.left : pr.right;
+            cur_t = near_left ? tl : tr;
+            have = true;
+        } else if (hl) {
+            cur = pr.left, cur_t = tl, have = true;
+        } else if (hr) {
+            cur = pr.right, cur_t = tr, have = true;
+        }
+    }
+    return hit;
+}
+
+#ifndef WB_PROBE_REFERENCE_ORDER
+#define WB_PROBE_REFERENCE_ORDER 0
+#endif
+
 #ifndef WB_QP_MIN_BLOCKS
 #define WB_QP_MIN_BLOCKS 10  // measured on C2: 9 (ptxas default, 52 registers) 653, 10: 668, 11: 617, 12: 617, 16: 464 M queries/s
 #endif
-// the signed variant (three extra probe traversals per query) runs best with 256-thread blocks at 5-6 blocks / SM:
-// 107 -> 117 M queries/s on C2; the unsigned one with 128-thread blocks
-constexpr int QT_SIGN = 256;
+// launch geometry of the signed variant (three extra probe traversals per query): see WB_QT_SIGN below
+#ifndef WB_QT_SIGN
+#define WB_QT_SIGN 128  // with the near-first probes (C2, M queries/s): 256 x 4 / 5 / 6: 194 / 208 / 186, 128 x 8 / 9 / 10 / 11 / 12:
+#endif                  // 202 / 207 / 214 / 192 / 191, 64 x 20: 214
+#ifndef WB_SIGN_MINB
+#define WB_SIGN_MINB 10
+#endif
+constexpr int QT_SIGN = WB_QT_SIGN;
 template <bool SIGN, bool COUNT>
-__global__ void __launch_bounds__(SIGN ? QT_SIGN : QT, SIGN ? 6 : WB_QP_MIN_BLOCKS)
+__global__ void __launch_bounds__(SIGN ? QT_SIGN : QT, SIGN ? WB_SIGN_MINB : WB_QP_MIN_BLOCKS)
 k_query_point(TreeView tv, const float* __restrict__ pts, const int* __restrict__ perm, long long nq, float max_dist,
               uint8_t* __restrict__ result, float* __restrict__ sign, int* __restrict__ face, float* __restrict__ u,
               float* __restrict__ v, unsigned long long* __restrict__ stats)
@@ -436,7 +532,9 @@ k_query_point(TreeView tv, const float* __restrict__ pts, const int* __restrict_
             float s = 0.f;
 #pragma unroll 1
             for (int axis = 0; axis < 3; ++axis)
-                if (probe_sign<COUNT>(tv, h, p, axis, s, cnt) && s < 0.f)
+                if ((WB_PROBE_REFERENCE_ORDER ? probe_sign<COUNT>(tv, h, p, axis, s, cnt)
+                                              : probe_sign_ordered<COUNT>(tv, h, p, axis, s, cnt))
+                    && s < 0.f)
                     votes++;
             sg = votes >= 2 ? -1.0f : 1.0f;
         }
