@@ -321,7 +321,11 @@ def main():
         "pair_fetches_per_query": st.pair_fetches / nq, "tri_fetches_per_query": st.tri_fetches / nq,
         "nodes_per_s": 2 * st.pair_fetches / (kernel_ms * 1e-3),
         "note": "bytes = 25 B/query I/O + 64 B per sibling-pair fetch + 48 B per packed-triangle fetch (counted); "
-                "most fetches hit L2 (tree 84 MB + triangles 63 MB), so DRAM traffic is far below this figure",
+                "SURVEY.md 8(d)'s traversal formula.  The tree (84 MB) and the packed triangles (63 MB) are L1 / L2 resident, "
+                "so these fetches are served on chip: `traffic` (ncu, DRAM read + write of the same launch) is ~15x smaller, and "
+                "`frac` -- fetched bytes against the HBM copy peak -- can exceed 1.  The kernel is issue bound "
+                "(profiles/r01_summary.md: issue slots 70 % busy at 12 of 32 lanes), not bandwidth bound",
+        "dram_frac": (traffic / (kernel_ms * 1e-3) / 1e9 / peak_gbs) if traffic else None,
     }  # fmt: skip
 
     # ---- end to end through the public API with pinned host buffers -------------------------------
