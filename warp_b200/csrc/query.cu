@@ -233,6 +233,10 @@ __device__ __forceinline__ bool ray_tri(const WoopRay& w, float3 org, float3 a, 
     return true;
 }
 
+#ifndef WB_LEAF_PRETEST
+#define WB_LEAF_PRETEST 8u
+#endif
+
 struct Counters {
     unsigned long long pairs = 0;  // 64-byte sibling-pair fetches
     unsigned long long tris = 0;   // 48-byte packed-triangle fetches
@@ -274,11 +278,20 @@ __device__ __forceinline__ bool closest_point(const TreeView& tv, const TreeHead
             continue;
         if (cur.a & WB_LEAF) {
             const uint32_t start = cur.a & WB_IDX_MASK;
+            // leaves made by the depth rule (bvh.cu:419-441) hold dozens of triangles -- ~100 on a 100 M-triangle mesh,
+            // where the 30-bit grid puts that many centroids in one cell.  There a triangle whose own box is already
+            // farther than the best so far is skipped before the closest-point evaluation: the same cut the walk applies
+            // to nodes (a triangle is never nearer than its box), at a quarter of the instructions.  Ordinary leaves
+            // (<= leaf_size triangles) skip the pre-test: it costs more than it saves there (-1 % on C2).
+            const bool big_leaf = cur.b > WB_LEAF_PRETEST;
             for (uint32_t pos = start; pos < start + cur.b; ++pos) {
                 const Tri t = load_tri(tv.tris, pos);
                 if (COUNT)
                     cnt.tris++;
                 if (t.flags & WB_TRI_SLIVER)
+                    continue;
+                if (big_leaf
+                    && dist_aabb_sq(point, wb_min3(wb_min3(t.p, t.q), t.r), wb_max3(wb_max3(t.p, t.q), t.r)) > best)
                     continue;
                 float bv, bw;
                 closest_vw(t.p, t.q, t.r, point, bv, bw);
