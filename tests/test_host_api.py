@@ -86,3 +86,24 @@ def test_meshgen_shapes():
     assert i.size // 3 == 2 * 16 * 16 and i.max() == p.shape[0] - 1
     s, d = mg.pinhole_rays(8, 4)
     assert s.shape == d.shape == (32, 3) and np.allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-6)
+
+
+def test_query_surface_mirrors_the_reference_builtins():
+    """Every batched query keeps the name of the Warp builtin it evaluates (warp/_src/builtins.py mesh_query_* /
+    mesh_eval_* / bvh_query_* / bvh_get_group_root) and says in its docstring which reference lines it follows."""
+    import re
+
+    import warp_b200 as wp
+
+    names = [
+        "mesh_query_point", "mesh_query_point_no_sign", "mesh_query_point_sign_normal", "mesh_query_point_sign_parity",
+        "mesh_query_furthest_point_no_sign", "mesh_query_ray", "mesh_query_ray_anyhit", "mesh_query_ray_count_intersections",
+        "mesh_query_aabb", "mesh_query_sphere", "mesh_eval_position", "mesh_eval_velocity", "mesh_eval_face_normal",
+        "bvh_query_aabb", "bvh_query_ray", "bvh_query_sphere", "bvh_query_capsule", "bvh_get_group_root",
+    ]  # fmt: skip
+    for name in names:
+        fn = getattr(wp, name)
+        assert callable(fn), name
+        assert re.search(r"(mesh|bvh|intersect)\.h:\d+", fn.__doc__ or ""), f"{name}: docstring cites no reference line"
+    # not built (DESIGN.md section 7): asking for them fails loudly instead of answering something else
+    assert not hasattr(wp, "mesh_query_point_sign_winding_number")
