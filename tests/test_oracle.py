@@ -591,6 +591,98 @@ def test_mesh_query_sphere_restatement(oracle_mod, gold):
         assert set(got) <= set(want) and len(want) - len(got) <= 1  # (one borderline face at most)
 
 
+def _topology_from_key_deltas(keys, prim, width):
+    """Parents of every node of the reference LBVH WITHOUT walking it bottom-up: the tree is the Cartesian tree of the
+    key-delta array (delta[i] = common-prefix length of keys i and i+1, bvh.cu:218-226).  The node split after sorted
+    position s covers (L, R] with L, R the nearest splits on either side whose delta is SMALLER -- two independent
+    searches per node; two equal deltas below the key width never compete, because sorted keys put a smaller delta
+    between them.  Only runs of EQUAL keys (delta == width) depend on the parity tie-break of bvh.cu:325-329 and are
+    replayed sequentially, run by run.  Groundwork for a parallel hierarchy kernel."""
+    n = len(keys)
+    k = [int(v) for v in keys]
+    delta = [width if k[i] == k[i + 1] else width - (k[i] ^ k[i + 1]).bit_length() for i in range(n - 1)]
+    par = [int(v) % 2 for v in prim]
+
+    def goes_right(l, r):  # bvh.cu:300-334, ungrouped
+        if l == 0:
+            return True
+        if r == n - 1:
+            return False
+        if delta[r] != delta[l - 1]:
+            return delta[r] > delta[l - 1]
+        return (par[l - 1] ^ par[r]) != 0
+
+    rng_l, rng_r = [0] * (n - 1), [0] * (n - 1)
+    # nearest smaller delta to the left / right (plain stack sweeps here; a kernel would search per node)
+    stack = []
+    for s in range(n - 1):
+        while stack and delta[stack[-1]] >= delta[s]:
+            stack.pop()
+        rng_l[s] = stack[-1] + 1 if stack else 0
+        stack.append(s)
+    stack = []
+    for s in range(n - 2, -1, -1):
+        while stack and delta[stack[-1]] >= delta[s]:
+            stack.pop()
+        rng_r[s] = stack[-1] if stack else n - 1
+        stack.append(s)
+    # runs of equal keys: replay the bottom-up process inside the run [p, q]
+    s = 0
+    while s < n - 1:
+        if delta[s] != width:
+            s += 1
+            continue
+        p = s
+        while s < n - 1 and delta[s] == width:
+            s += 1
+        q = s  # keys p..q are equal, splits p..q-1
+        parked = []  # nodes waiting for their right sibling: (l, r), each the left child of split r
+        for i in range(p, q + 1):
+            l, r = i, i
+            while not (l == p and r == q):
+                if goes_right(l, r):
+                    parked.append((l, r))
+                    break
+                pl, pr = parked.pop()  # left sibling: ends at l - 1
+                assert pr == l - 1
+                rng_l[pr], rng_r[pr] = pl, r
+                l = pl
+        assert not parked
+    parents = [-1] * (2 * n - 1)
+    for i in range(n):
+        parents[i] = n + (i if goes_right(i, i) else i - 1)
+    for s in range(n - 1):
+        l, r = rng_l[s], rng_r[s]
+        if l == 0 and r == n - 1:
+            root = n + s
+        else:
+            parents[n + s] = n + (r if goes_right(l, r) else l - 1)
+    return np.asarray(parents, np.int32), root
+
+
+def test_topology_is_the_cartesian_tree_of_key_deltas(oracle_mod):
+    o = oracle_mod
+    rng = np.random.default_rng(77)
+    cases = []
+    P, I = mg.noisy_sphere(4, 0.05, 71)
+    lo, hi = o.triangle_bounds(P, I)
+    cases.append((lo, hi, 30))
+    cases.append((lo, hi, 63))
+    c = (rng.random((3000, 3)) * 4).astype(np.float32)  # clustered boxes: many equal 30-bit keys
+    c = np.repeat(c[:300], 10, axis=0) + (rng.random((3000, 3)) * 1e-4).astype(np.float32)
+    cases.append((c, c + np.float32(0.01), 30))
+    same = np.tile(np.array([[1.0, 2.0, 3.0]], np.float32), (257, 1))  # one run of 257 equal keys
+    cases.append((np.concatenate([same, c[:100]]), np.concatenate([same + 1, c[:100] + 1]), 30))
+    for lo, hi, bits in cases:
+        tree = o.lbvh_build(lo, hi, 1, morton_bits=bits)
+        width = 32 if bits == 30 else 64
+        parents, root = _topology_from_key_deltas(tree["keys"], tree["primitive_indices"], width)
+        assert root == tree["root"]
+        want = tree["parents"].copy()
+        want[root] = -1
+        assert np.array_equal(parents, want)
+
+
 def _grouped_mesh_case():
     P, I = mg.noisy_sphere(3, noise=0.05, seed=61)
     T = len(I) // 3
