@@ -512,6 +512,9 @@ __device__ __forceinline__ bool probe_sign_ordered(const TreeView& tv, const Tre
 #ifndef WB_PROBE_REFERENCE_ORDER
 #define WB_PROBE_REFERENCE_ORDER 0
 #endif
+#ifndef WB_SIGN_ALL_PROBES
+#define WB_SIGN_ALL_PROBES 0
+#endif
 
 #ifndef WB_QP_MIN_BLOCKS
 #define WB_QP_MIN_BLOCKS 10  // measured on C2: 9 (ptxas default, 52 registers) 653, 10: 668, 11: 617, 12: 617, 16: 464 M queries/s
@@ -543,12 +546,17 @@ k_query_point(TreeView tv, const float* __restrict__ pts, const int* __restrict_
         if (SIGN && ok) {  // majority of three axis probes, mesh.h:2342-2359
             int votes = 0;
             float s = 0.f;
+            // the +z probe is only cast when +x and +y disagree: with 0 or 2 votes after two probes the majority is
+            // settled (the reference casts all three, mesh.h:2349-2357; same answer)
 #pragma unroll 1
-            for (int axis = 0; axis < 3; ++axis)
+            for (int axis = 0; axis < 3; ++axis) {
+                if (!WB_SIGN_ALL_PROBES && axis == 2 && votes != 1)
+                    break;
                 if ((WB_PROBE_REFERENCE_ORDER ? probe_sign<COUNT>(tv, h, p, axis, s, cnt)
                                               : probe_sign_ordered<COUNT>(tv, h, p, axis, s, cnt))
                     && s < 0.f)
                     votes++;
+            }
             sg = votes >= 2 ? -1.0f : 1.0f;
         }
         result[i] = ok ? 1 : 0;
