@@ -478,6 +478,18 @@ def test_sign_normal(wp, oracle_mod):
     assert (votes["face"] == normal["face"]).mean() > 0.99  # (faces may differ at shared edges: distances vs squared distances)
     print("sign_normal vs ray votes: %d of 20000 differ" % int((votes["sign"] != normal["sign"]).sum()))
     assert (votes["sign"] == normal["sign"]).mean() > 0.995
+    # Warp kernels read wp::Mesh::average_edge_length through the id (mesh.h:889): the field (offset 320 of the 328-byte
+    # descriptor) is refreshed with the reference-layout arrays
+    import ctypes
+
+    from warp_b200 import _lib
+
+    m.download_tree()  # -> wp_b200_bvh_sync_reference_layout
+    wp.synchronize()
+    field = np.zeros(1, np.float32)
+    assert _lib.core().wp_memcpy_d2h(None, ctypes.c_void_p(field.ctypes.data), ctypes.c_void_p(m.id + 320), 4, None)
+    wp.synchronize()
+    assert field[0] == np.float32(avg)
     # device arrays in -> device arrays out, unordered batch path (< 32768 queries) and the ordered one agree
     a = wp.mesh_query_point_sign_normal(m, wp.array(Q[:1000], dtype=wp.vec3), 1e6).numpy()
     b = wp.mesh_query_point_sign_normal(m, np.tile(Q[:1000], (40, 1)), 1e6).numpy()

@@ -1255,8 +1255,19 @@ int wp_b200_bvh_sync_reference_layout(uint64_t id)
         set_error("Warp error: reference-layout export failed: %s", err);
         return 0;
     }
-    if (first && s->n > 0)
-        return upload_desc(m, m ? nullptr : s) ? 1 : 0;
+    if (first && s->n > 0 && !upload_desc(m, m ? nullptr : s))
+        return 0;
+    if (m && s->n > 0) {
+        // a Warp kernel that calls mesh_query_point_sign_normal reads wp::Mesh::average_edge_length through the id
+        // (mesh.h:889): refresh it together with the node arrays (upload_desc above resets the field)
+        float* avg = &((wp_b200_mesh_desc*)m->dev_desc)->average_edge_length;
+        err = wb_query_point_sign_normal(make_view(*s), s->points, s->indices, nullptr, nullptr, 0, 0.f, 0.f, (double*)s->partials,
+                                         avg, nullptr, nullptr, nullptr, nullptr, nullptr, current_stream(s->device));
+        if (err) {
+            set_error("Warp error: average edge length failed: %s", err);
+            return 0;
+        }
+    }
     return 1;
 }
 
