@@ -681,6 +681,16 @@ def test_topology_is_the_cartesian_tree_of_key_deltas(oracle_mod):
         want = tree["parents"].copy()
         want[root] = -1
         assert np.array_equal(parents, want)
+    # grouped trees (key = group << 32 | code, bvh.cu:205-209): the stay-inside-the-group rule of bvh.cu:305-321 never
+    # overrides the delta comparison -- the same-group neighbour always shares the longer prefix -- so the grouped
+    # tree is the Cartesian tree of the 64-bit deltas too
+    lo, hi, _ = cases[2]
+    for groups in (rng.integers(0, 7, len(lo)).astype(np.int32), (np.arange(len(lo)) // 450).astype(np.int32)):
+        tree = o.lbvh_build(lo, hi, 1, groups=groups)
+        parents, root = _topology_from_key_deltas(tree["keys"], tree["primitive_indices"], 64)
+        want = tree["parents"].copy()
+        want[tree["root"]] = -1
+        assert root == tree["root"] and np.array_equal(parents, want)
 
 
 def _grouped_mesh_case():
