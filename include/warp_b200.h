@@ -317,6 +317,12 @@ WP_B200_API int wp_b200_bvh_sync_reference_layout(uint64_t id);
 /* host copies of the tree products (any pointer may be NULL): sorted keys [n] (key_bits / 8 bytes each),
  * primitive_indices [n], node_lowers / node_uppers [2n-1] x 16 bytes, node_parents [2n-1], root [1].
  * Calls wp_b200_bvh_sync_reference_layout first and synchronises. */
+/* EXPERIMENT, not part of the drop-in surface: parents of the n - 1 internal nodes recomputed from
+ * the sorted keys alone by a dependency-free kernel (the reference LBVH is the Cartesian tree of the key-delta array,
+ * bvh.cu:218-226, 300-334); parents_out is a device array of n - 1 int32 (reference node indices, -1 = root).  Returns
+ * the average kernel time in microseconds over `reps` launches, -1 on error, -2 when a run of equal keys exceeds what
+ * the prototype replays */
+WP_B200_API float wp_b200_experiment_parallel_topology(uint64_t id, int32_t* parents_out, int reps);
 WP_B200_API int wp_b200_bvh_download(uint64_t id, void* keys, int32_t* primitive_indices, void* node_lowers,
                                      void* node_uppers, int32_t* node_parents, int32_t* root);
 

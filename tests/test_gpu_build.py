@@ -400,3 +400,48 @@ def test_block_boundary_sizes_build_and_refit(wp, oracle_mod, refit_mode, n):
             for name in ("node_lowers", "node_uppers"):
                 for f in "xyz":
                     assert np.array_equal(got[name][f][vis], want[name][f][vis]), (n, leaf, mode, name, f)
+
+
+def test_experiment_parallel_topology(wp, oracle_mod):
+    """EXPERIMENT: parents of all internal nodes recomputed from the sorted keys by the
+    dependency-free k_topology kernel equal the parents the builder produced bottom-up -- 30-bit, 63-bit and grouped
+    keys, clustered duplicates -- and a run of equal keys longer than the prototype replays is reported, not mangled."""
+    import ctypes
+
+    from warp_b200 import _lib
+
+    fn = _lib.core().wp_b200_experiment_parallel_topology
+
+    def check(tree_obj, n, expect_ok=True):
+        got = wp.empty(n - 1, wp.int32, tree_obj.device)
+        us = fn(tree_obj.id, ctypes.c_void_p(got.ptr), 3)
+        if not expect_ok:
+            assert us == -2.0
+            return us
+        assert us > 0, us
+        want = tree_obj.download_tree()["parents"][n:].astype(np.int32)
+        assert np.array_equal(got.numpy(), want)
+        return us
+
+    P, I = mg.noisy_sphere(6, 0.02, 1)
+    for bits in (30, 63):
+        m = wp.Mesh(wp.array(P, dtype=wp.vec3), wp.array(I, dtype=wp.int32), morton_bits=bits)
+        check(m, len(I) // 3)
+    rng = np.random.default_rng(5)
+    c = (rng.random((300, 3)) * 4).astype(np.float32)
+    c = (np.repeat(c, 10, axis=0) + (rng.random((3000, 3)) * 1e-4).astype(np.float32)).astype(np.float32)
+    lo, hi = wp.array(c, dtype=wp.vec3), wp.array(c + np.float32(0.01), dtype=wp.vec3)
+    check(wp.Bvh(lo, hi, leaf_size=1), 3000)
+    groups = wp.array((np.arange(3000) // 450).astype(np.int32), dtype=wp.int32)
+    check(wp.Bvh(lo, hi, groups=groups, leaf_size=2), 3000)
+    same = np.tile(np.array([[1.0, 2.0, 3.0]], np.float32), (257, 1))
+    lo2, hi2 = wp.array(np.concatenate([same, c[:100]]), dtype=wp.vec3), wp.array(np.concatenate([same + 1, c[:100] + 1]), dtype=wp.vec3)
+    check(wp.Bvh(lo2, hi2), 357, expect_ok=False)
+    # timing at C2 size (1.31 M triangles) and on the 10 M-triangle heightfield, beside the merge kernel's 135 / 730 us
+    P, I = mg.noisy_sphere(8, 0.02, 1)
+    m = wp.Mesh(wp.array(P, dtype=wp.vec3), wp.array(I, dtype=wp.int32))
+    us_c2 = check(m, len(I) // 3)
+    P, I = mg.heightfield(2237, 4)
+    m = wp.Mesh(wp.array(P, dtype=wp.vec3), wp.array(I, dtype=wp.int32))
+    us_10m = check(m, len(I) // 3)
+    print(f"k_topology: {us_c2:.1f} us at 1.31 M triangles, {us_10m:.1f} us at 10 M")

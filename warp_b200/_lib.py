@@ -136,6 +136,7 @@ SIGNATURES = {
     "wp_b200_bvh_info": (_i, [_u64, ctypes.POINTER(bvh_info_t)]),
     "wp_b200_bvh_sync_reference_layout": (_i, [_u64]),
     "wp_b200_bvh_download": (_i, [_u64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "wp_b200_experiment_parallel_topology": (ctypes.c_float, [_u64, _vp, _i]),
     # multi-GPU
     "wp_b200_nccl_load": (_i, [ctypes.c_char_p]),
     "wp_b200_nccl_unique_id": (_i, [_vp]),

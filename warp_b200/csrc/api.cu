@@ -1271,6 +1271,37 @@ int wp_b200_bvh_sync_reference_layout(uint64_t id)
     return 1;
 }
 
+// EXPERIMENT (not used by any build): parents (reference node indices, -1 for the root) of the n - 1
+// internal nodes, recomputed from the tree's sorted keys by the dependency-free k_topology kernel, `reps` times; returns
+// the average kernel time in microseconds, -1 on error, -2 when a run of equal keys was too long for the prototype
+float wp_b200_experiment_parallel_topology(uint64_t id, int32_t* parents_out, int reps)
+{
+    BvhState* s = find_tree(id);
+    if (!s || s->n < 2 || reps < 1)
+        return -1.0f;
+    DeviceGuard g(s->device);
+    cudaStream_t st = current_stream(s->device);
+    int* fail = nullptr;
+    if (cudaMalloc(&fail, sizeof(int)) != cudaSuccess)
+        return -1.0f;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    const char* err = wb_experiment_topology(*s, parents_out, fail, st);  // warm-up
+    cudaEventRecord(e0, st);
+    for (int k = 0; k < reps && !err; ++k)
+        err = wb_experiment_topology(*s, parents_out, fail, st);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    int h_fail = 0;
+    cudaMemcpy(&h_fail, fail, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaEventDestroy(e0), cudaEventDestroy(e1), cudaFree(fail);
+    if (err)
+        return -1.0f;
+    return h_fail ? -2.0f : 1000.0f * ms / (float)reps;
+}
+
 int wp_b200_bvh_download(uint64_t id, void* keys, int32_t* primitive_indices, void* node_lowers, void* node_uppers,
                          int32_t* node_parents, int32_t* root)
 {

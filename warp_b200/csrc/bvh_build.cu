@@ -924,6 +924,124 @@ const char* wb_build(BvhState& s, cudaStream_t stream)
     return build_dispatch(s, BoxSource { s.item_lowers, s.item_uppers }, stream);
 }
 
+// ------------------------------------------------------------------------------------------------
+// EXPERIMENT (not on the build path; wp_b200_experiment_parallel_topology): the parent of every
+// internal node computed INDEPENDENTLY from the sorted keys -- the reference LBVH is the Cartesian tree of the key-delta
+// array, so the node split after position s covers (L, R] with L / R the nearest split on either side whose delta is
+// smaller: two galloping searches on clz(key[j] ^ key[s]), no atomics, no dependency chain.  Runs of equal keys, where
+// the parity tie-break of bvh.cu:325-329 decides, are replayed sequentially by the thread of the run's first split
+// (runs longer than TOPO_RUN_MAX raise `fail`: a production kernel would hand those to the merge kernel).
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int TOPO_RUN_MAX = 64;
+
+template <class KeyT>
+__device__ __forceinline__ bool topo_goes_right(const KeyT* __restrict__ keys, const int* __restrict__ prim, int n, int l, int r)
+{
+    if (l == 0)
+        return true;
+    if (r == n - 1)
+        return false;
+    const int dr = wb_clz_key((KeyT)(keys[r] ^ keys[r + 1])), dl = wb_clz_key((KeyT)(keys[l - 1] ^ keys[l]));
+    if (dr != dl)
+        return dr > dl;
+    return ((prim[l - 1] % 2) ^ (prim[r] % 2)) != 0;
+}
+
+template <class KeyT>
+__global__ void __launch_bounds__(BT)
+k_topology(int n, const KeyT* __restrict__ keys, const int* __restrict__ prim, int* __restrict__ parent_out, int* __restrict__ fail)
+{
+    const int s = blockIdx.x * BT + threadIdx.x;
+    if (s >= n - 1)
+        return;
+    const KeyT ks = keys[s], ks1 = keys[s + 1];
+    if (ks == ks1) {
+        if (s > 0 && keys[s - 1] == ks)
+            return;  // not the first split of its run
+        const int p = s;
+        int q = s + 1;
+        while (q + 1 < n && keys[q + 1] == ks)
+            ++q;
+        if (q - p + 1 > TOPO_RUN_MAX) {
+            *fail = 1;
+            return;
+        }
+        int parked[TOPO_RUN_MAX];
+        int depth = 0;
+        for (int i = p; i <= q; ++i) {
+            int l = i, split = -1;
+            const int r = i;
+            for (;;) {
+                const bool run_root = (l == p && r == q);
+                const bool whole = (l == 0 && r == n - 1);
+                const bool gr = topo_goes_right(keys, prim, n, l, r);
+                if (split >= 0)
+                    parent_out[split] = whole ? -1 : n + (gr ? r : l - 1);
+                if (run_root || gr) {
+                    if (!run_root)
+                        parked[depth++] = l;
+                    break;
+                }
+                split = l - 1;        // merges with the parked node that ends at l - 1
+                l = parked[--depth];
+            }
+        }
+        return;
+    }
+    const int d = wb_clz_key((KeyT)(ks ^ ks1));
+    // left end: smallest j <= s with clz(key[j] ^ key[s]) > d (monotone in j on sorted keys)
+    int l = s;
+    {
+        int step = 1;
+        while (s - step >= 0 && wb_clz_key((KeyT)(keys[s - step] ^ ks)) > d)
+            step <<= 1;
+        int lo = max(s - step, -1), hi = s - (step >> 1);  // key[lo] fails (or lo == -1), key[hi] passes
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (wb_clz_key((KeyT)(keys[mid] ^ ks)) > d)
+                hi = mid;
+            else
+                lo = mid;
+        }
+        l = hi;
+    }
+    int r = s + 1;
+    {
+        int step = 1;
+        while (s + 1 + step < n && wb_clz_key((KeyT)(keys[s + 1 + step] ^ ks1)) > d)
+            step <<= 1;
+        int hi = min(s + 1 + step, n), lo = s + 1 + (step >> 1);  // key[lo] passes, key[hi] fails (or hi == n)
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (wb_clz_key((KeyT)(keys[mid] ^ ks1)) > d)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        r = lo;
+    }
+    if (l == 0 && r == n - 1)
+        parent_out[s] = -1;
+    else
+        parent_out[s] = n + (topo_goes_right(keys, prim, n, l, r) ? r : l - 1);
+}
+}  // namespace
+
+const char* wb_experiment_topology(BvhState& s, int* parent_out, int* fail, cudaStream_t stream)
+{
+    if (s.n < 2)
+        return nullptr;
+    WB_CUDA_TRY(cudaMemsetAsync(fail, 0, sizeof(int), stream));
+    const int grid = wb_div_up(s.n - 1, BT);
+    if (s.key_bytes == 4)
+        k_topology<uint32_t><<<grid, BT, 0, stream>>>(s.n, (const uint32_t*)s.keys, s.prim, parent_out, fail);
+    else
+        k_topology<uint64_t><<<grid, BT, 0, stream>>>(s.n, (const uint64_t*)s.keys, s.prim, parent_out, fail);
+    WB_CUDA_TRY(cudaGetLastError());
+    return nullptr;
+}
+
 const char* wb_export_reference_layout(BvhState& s, cudaStream_t stream)
 {
     if (s.n <= 0)

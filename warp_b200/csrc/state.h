@@ -83,6 +83,8 @@ const char* wb_refit(BvhState& s, cudaStream_t stream);
 extern int g_wb_refit_mode;  // 0 auto, 1 atomic counters, 2 wavefront
 const char* wb_refit_plan(BvhState& s, cudaStream_t stream);  // (bvh_build.cu: shares the radix sort)
 const char* wb_refit_merge(BvhState& s, cudaStream_t stream);  // bottom-up pass of the refit (bvh_build.cu)
+// experiment: parents of all internal nodes from the sorted keys alone (bvh_build.cu, k_topology)
+const char* wb_experiment_topology(BvhState& s, int* parent_out, int* fail, cudaStream_t stream);
 const char* wb_export_reference_layout(BvhState& s, cudaStream_t stream);
 const char* wb_alloc_tree(BvhState& s, cudaStream_t stream);
 void wb_free_tree(BvhState& s, cudaStream_t stream);
