@@ -301,6 +301,29 @@ WP_B200_API int wp_b200_exclusive_scan_i32(const int32_t* counts, int32_t* offse
 WP_B200_API void wp_b200_set_refit_mode(int mode);
 WP_B200_API int wp_b200_get_refit_mode(void);
 
+/* Creators with the one build-time extension argument: morton_bits = 30 (the reference's 1024^3 code, bit-exact
+ * parity, bvh.cu:184-214), 63 (21 bits per axis, a quality option for meshes with far more than 2^20 occupied cells;
+ * not combinable with groups) or 0 = the process default (wp_b200_set_morton_bits).  The reference-named creators
+ * above are these with morton_bits = 0.  Everything else as wp_bvh_create_device / wp_mesh_create_device. */
+WP_B200_API uint64_t wp_b200_bvh_create_device_ex(void* context, wp_vec3* lowers, wp_vec3* uppers, int num_items,
+                                                  int constructor_type, int* groups, int leaf_size, int morton_bits);
+WP_B200_API uint64_t wp_b200_mesh_create_device_ex(void* context, wp_array_t points, wp_array_t velocities, wp_array_t tris,
+                                                   int num_points, int num_tris, int support_winding_number,
+                                                   int constructor_type, int* groups, int bvh_leaf_size, int morton_bits);
+
+/* Per-object options (thread-safe alternative to the process-wide setters, which only provide defaults):
+ * "refit_mode" 0 / 1 / 2, "query_order" 0 input / 1 curve / 2 auto, "ray_order" 0 / 1, "auto_reference_layout" 0 / 1;
+ * -1 = follow the process default.  "morton_bits" can be read, not set.  1 ok / 0 error. */
+WP_B200_API int wp_b200_bvh_set_option(uint64_t id, const char* name, int value);
+WP_B200_API int wp_b200_bvh_get_option(uint64_t id, const char* name, int* value);
+
+/* Drop-in use under the reference's Python layer: when enabled, every tree created
+ * afterwards keeps the reference-layout mirror of its descriptor (node_lowers / node_uppers / node_parents / root,
+ * Mesh::lowers / uppers, average_edge_length) current after create / refit / rebuild / set_points, so unmodified Warp
+ * kernels can traverse through `id`.  Off by default (the mirror costs one extra pass per refit). */
+WP_B200_API void wp_b200_set_auto_reference_layout(int enable);
+WP_B200_API int wp_b200_get_auto_reference_layout(void);
+
 /* in-place LBVH rebuild of a mesh's tree from the current vertices (the reference only offers this
  * for wp.Bvh, bvh.cu:819-843; here a Mesh gets it too): no allocation, same buffers. 1 ok / 0 error */
 WP_B200_API int wp_b200_mesh_rebuild_device(uint64_t id);

@@ -9,8 +9,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <map>
 #include <mutex>
+#include <utility>
 
 static_assert(sizeof(wp_array_t) == 56, "wp::array_t layout (warp/native/array.h:173-277)");
 static_assert(sizeof(wp_b200_bvh_desc) == 112, "wp::BVH layout (warp/native/bvh.h:176-207)");
@@ -26,11 +28,25 @@ std::map<uint64_t, MeshState*> g_meshes;
 cudaStream_t g_stream[64] = {};  // current stream per device (0 = legacy default stream)
 
 thread_local bool t_stats_enabled = false;
-int g_morton_bits = 30;         // Morton resolution of subsequently created trees: 30 (reference parity) or 63
-int g_query_order = 2;          // 0 input order, 1 Morton order, 2 auto (Morton for batches >= 32768 points)
+// Process-wide DEFAULTS, copied into every tree when it is created (BvhState::morton_bits / query_order / ray_order /
+// refit_mode); changing them later never touches an existing object -- wp_b200_bvh_set_option does that, per object.
+int g_morton_bits = 30;         // Morton resolution: 30 (reference parity) or 63
+int g_query_order = 2;          // 0 input order, 1 curve order, 2 auto (curve order for batches >= 32768 points)
 int g_ray_order = 0;            // 0 input order (default), 1 origin/direction order
-OrderScratch g_order[64][3];    // per device: [0] current-stream calls, [1], [2] the two host lanes
+int g_auto_reference_layout = 0;  // 1: new trees keep the reference-layout mirror current (set by the drop-in stub)
+// query-ordering scratch, one per (device, stream): two batches on different streams never share a permutation buffer,
+// and batches on the same stream are ordered by the stream itself
+std::map<std::pair<int, cudaStream_t>, OrderScratch*> g_order;
 unsigned long long* g_stats_dev = nullptr;
+
+OrderScratch& order_scratch(int device, cudaStream_t stream)
+{
+    std::lock_guard<std::mutex> g(g_lock);
+    OrderScratch*& p = g_order[std::make_pair(device, stream)];
+    if (!p)
+        p = new OrderScratch();
+    return *p;
+}
 
 void set_error(const char* fmt, ...)
 {
@@ -47,7 +63,86 @@ int current_device()
     return d;
 }
 
-int context_device(void* context) { return context ? (int)((intptr_t)context - 1) : current_device(); }
+// ---- CUcontext handling.  The reference passes a real CUcontext as `context` (warp/_src/types.py:5947-5950,
+// 6204-6205: `self.device.context`), so the handle is resolved through the driver API: libcuda.so.1 is dlopen()ed
+// lazily (the library must still load, and export its symbols, on a box without a driver).  NULL = the calling
+// thread's current device.  Values 1..64 are the ordinal + 1 tokens handed out when no driver library is present.
+typedef int (*cu_ctx_get_current_t)(void**);
+typedef int (*cu_ctx_push_t)(void*);
+typedef int (*cu_ctx_pop_t)(void**);
+typedef int (*cu_ctx_get_device_t)(int*);
+struct DriverApi {
+    bool tried = false, ok = false;
+    cu_ctx_get_current_t get_current = nullptr;
+    cu_ctx_push_t push = nullptr;
+    cu_ctx_pop_t pop = nullptr;
+    cu_ctx_get_device_t get_device = nullptr;
+};
+DriverApi g_driver;
+std::map<void*, int> g_ctx_device;  // CUcontext -> device ordinal (guarded by g_lock)
+
+const DriverApi& driver_api()
+{
+    std::lock_guard<std::mutex> g(g_lock);
+    if (!g_driver.tried) {
+        g_driver.tried = true;
+        void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (h) {
+            g_driver.get_current = (cu_ctx_get_current_t)dlsym(h, "cuCtxGetCurrent");
+            g_driver.push = (cu_ctx_push_t)dlsym(h, "cuCtxPushCurrent_v2");
+            g_driver.pop = (cu_ctx_pop_t)dlsym(h, "cuCtxPopCurrent_v2");
+            g_driver.get_device = (cu_ctx_get_device_t)dlsym(h, "cuCtxGetDevice");
+            g_driver.ok = g_driver.get_current && g_driver.push && g_driver.pop && g_driver.get_device;
+        }
+    }
+    return g_driver;
+}
+
+int context_device(void* context)
+{
+    if (!context)
+        return current_device();
+    const uintptr_t v = (uintptr_t)context;
+    if (v <= 64)
+        return (int)v - 1;
+    {
+        std::lock_guard<std::mutex> g(g_lock);
+        auto it = g_ctx_device.find(context);
+        if (it != g_ctx_device.end())
+            return it->second;
+    }
+    const DriverApi& d = driver_api();
+    int dev = current_device();
+    if (d.ok && d.push(context) == 0) {
+        int got = -1;
+        if (d.get_device(&got) == 0 && got >= 0)
+            dev = got;
+        void* popped = nullptr;
+        d.pop(&popped);
+    }
+    std::lock_guard<std::mutex> g(g_lock);
+    g_ctx_device[context] = dev;
+    return dev;
+}
+
+// the primary context of `ordinal` as the driver knows it (what Warp's Device.context holds), or the ordinal token
+void* device_primary_context(int ordinal)
+{
+    const DriverApi& d = driver_api();
+    if (!d.ok)
+        return (void*)(intptr_t)(ordinal + 1);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    void* ctx = nullptr;
+    if (cudaSetDevice(ordinal) == cudaSuccess && cudaFree(nullptr) == cudaSuccess)  // cudaFree(0) creates the primary context
+        d.get_current(&ctx);
+    cudaSetDevice(prev);
+    if (!ctx)
+        return (void*)(intptr_t)(ordinal + 1);
+    std::lock_guard<std::mutex> g(g_lock);
+    g_ctx_device[ctx] = ordinal;
+    return ctx;
+}
 
 cudaStream_t current_stream(int device) { return (device >= 0 && device < 64) ? g_stream[device] : 0; }
 
@@ -83,8 +178,9 @@ void fill_bvh_desc(const BvhState& s, wp_b200_bvh_desc& d, void* context)
     d.num_nodes = d.max_nodes;
     d.num_leaf_nodes = s.n;
     d.root = s.ref_root;
-    d.item_lowers = (wp_vec3*)s.item_lowers;
-    d.item_uppers = (wp_vec3*)s.item_uppers;
+    // a mesh's BVH items are its per-triangle bounds (mesh.cu:310-313), materialised by wb_export_reference_layout
+    d.item_lowers = (wp_vec3*)(s.is_mesh ? s.tri_lowers : s.item_lowers);
+    d.item_uppers = (wp_vec3*)(s.is_mesh ? s.tri_uppers : s.item_uppers);
     d.item_groups = (int*)s.groups;
     d.num_items = s.n;
     d.leaf_size = s.leaf_size;
@@ -107,23 +203,38 @@ BvhState* find_tree(uint64_t id, MeshState** mesh_out = nullptr)
     return nullptr;
 }
 
+// The descriptor is rewritten in stream order from a pinned staging copy owned by the object (stable address, so the
+// upload is truly asynchronous and legal under stream capture); everything up to average_edge_length is uploaded --
+// that last field is device-computed (wb_query_point_sign_normal / wp_b200_bvh_sync_reference_layout) and must
+// survive a points / velocities swap.  The staging copy is a ring of DESC_RING slots so that back-to-back updates
+// (points = A; points = B) each upload their own bytes.
+constexpr unsigned DESC_RING = 8;
 bool upload_desc(MeshState* ms, BvhState* bs)
 {
     if (ms) {
-        wp_b200_mesh_desc d;
+        if (!ms->host_desc && !check(cudaMallocHost(&ms->host_desc, DESC_RING * sizeof(wp_b200_mesh_desc)), "descriptor staging"))
+            return false;
+        wp_b200_mesh_desc& d = ((wp_b200_mesh_desc*)ms->host_desc)[ms->desc_slot++ % DESC_RING];
         memset(&d, 0, sizeof(d));
         d.points.data = ms->points_data, d.points.shape[0] = ms->points_shape0, d.points.strides[0] = 12, d.points.ndim = 1;
         d.velocities.data = ms->velocities_data, d.velocities.shape[0] = ms->velocities_shape0;
         d.velocities.strides[0] = 12, d.velocities.ndim = ms->velocities_data ? 1 : 0;
         d.indices.data = ms->indices_data, d.indices.shape[0] = ms->num_tris * 3, d.indices.strides[0] = 4, d.indices.ndim = 1;
+        d.lowers = (wp_vec3*)ms->bvh.tri_lowers, d.uppers = (wp_vec3*)ms->bvh.tri_uppers;
         d.num_points = ms->num_points, d.num_tris = ms->num_tris;
-        fill_bvh_desc(ms->bvh, d.bvh, (void*)(intptr_t)(ms->bvh.device + 1));
+        fill_bvh_desc(ms->bvh, d.bvh, ms->bvh.context);
         d.context = d.bvh.context;
-        return check(cudaMemcpy(ms->dev_desc, &d, sizeof(d), cudaMemcpyHostToDevice), "descriptor upload");
+        const size_t bytes = ms->desc_initialised ? offsetof(wp_b200_mesh_desc, average_edge_length) : sizeof(d);
+        ms->desc_initialised = true;
+        return check(cudaMemcpyAsync(ms->dev_desc, &d, bytes, cudaMemcpyHostToDevice, current_stream(ms->bvh.device)),
+                     "descriptor upload");
     }
-    wp_b200_bvh_desc d;
-    fill_bvh_desc(*bs, d, (void*)(intptr_t)(bs->device + 1));
-    return check(cudaMemcpy(bs->dev_desc, &d, sizeof(d), cudaMemcpyHostToDevice), "descriptor upload");
+    if (!bs->host_desc && !check(cudaMallocHost(&bs->host_desc, DESC_RING * sizeof(wp_b200_bvh_desc)), "descriptor staging"))
+        return false;
+    wp_b200_bvh_desc& d = ((wp_b200_bvh_desc*)bs->host_desc)[bs->desc_slot++ % DESC_RING];
+    fill_bvh_desc(*bs, d, bs->context);
+    return check(cudaMemcpyAsync(bs->dev_desc, &d, sizeof(d), cudaMemcpyHostToDevice, current_stream(bs->device)),
+                 "descriptor upload");
 }
 
 bool constructor_supported(int constructor_type)
@@ -242,8 +353,8 @@ int wp_cuda_device_get_count(void)
     return n;
 }
 
-void* wp_cuda_device_get_primary_context(int ordinal) { return (void*)(intptr_t)(ordinal + 1); }
-void* wp_cuda_context_get_current(void) { return (void*)(intptr_t)(current_device() + 1); }
+void* wp_cuda_device_get_primary_context(int ordinal) { return device_primary_context(ordinal); }
+void* wp_cuda_context_get_current(void) { return device_primary_context(current_device()); }
 void wp_cuda_context_set_current(void* context)
 {
     if (context)
@@ -298,7 +409,26 @@ int wp_cuda_graph_begin_capture(void* context, void* stream, int external, int m
 {
     if (external)
         return 1;  // the caller's own capture is already active on `stream`
-    DeviceGuard g(context_device(context));
+    const int dev = context_device(context);
+    DeviceGuard g(dev);
+    {
+        // query-ordering scratch is per (device, stream) and cannot grow inside a capture: give this stream one as large
+        // as the largest in use on the device (i.e. what the warm-up run of the loop body needed)
+        long long cap = 0;
+        {
+            std::lock_guard<std::mutex> l(g_lock);
+            for (auto& kv : g_order)
+                if (kv.first.first == dev && kv.second && kv.second->capacity > cap)
+                    cap = kv.second->capacity;
+        }
+        if (cap > 0) {
+            const char* e = wb_order_reserve(order_scratch(dev, (cudaStream_t)stream), cap, nullptr);
+            if (e) {
+                set_error("Warp error: %s", e);
+                return 0;
+            }
+        }
+    }
     return check(cudaStreamBeginCapture((cudaStream_t)stream, (cudaStreamCaptureMode)mode), "graph begin capture") ? 1 : 0;
 }
 int wp_cuda_graph_end_capture(void* context, void* stream, void** graph_ret)
@@ -423,11 +553,30 @@ int wp_b200_device_name(int ordinal, char* buf, int len)
 // ------------------------------------------------------------------------------------------------
 // Bvh
 // ------------------------------------------------------------------------------------------------
+static int sync_reference_layout(BvhState* s, MeshState* m);
+
 uint64_t wp_bvh_create_device(void* context, wp_vec3* lowers, wp_vec3* uppers, int num_items, int constructor_type,
                               int* groups, int leaf_size)
 {
+    return wp_b200_bvh_create_device_ex(context, lowers, uppers, num_items, constructor_type, groups, leaf_size, 0);
+}
+
+uint64_t wp_b200_bvh_create_device_ex(void* context, wp_vec3* lowers, wp_vec3* uppers, int num_items, int constructor_type,
+                                      int* groups, int leaf_size, int morton_bits)
+{
+    g_error[0] = 0;  // the drop-in stub reads this library's message only when the last routed call failed
     if (!constructor_supported(constructor_type))
         return 0;
+    if (morton_bits == 0)
+        morton_bits = g_morton_bits;
+    if (morton_bits != 30 && morton_bits != 63) {
+        set_error("Warp error: morton_bits must be 30 or 63 (got %d)", morton_bits);
+        return 0;
+    }
+    if (morton_bits == 63 && groups) {
+        set_error("Warp error: morton_bits=63 cannot be combined with groups (the key holds group << 32 | 30-bit code)");
+        return 0;
+    }
     if (num_items < 0 || leaf_size < 1) {
         set_error("Warp error: invalid BVH arguments (num_items=%d, leaf_size=%d)", num_items, leaf_size);
         return 0;
@@ -436,14 +585,21 @@ uint64_t wp_bvh_create_device(void* context, wp_vec3* lowers, wp_vec3* uppers, i
     DeviceGuard g(dev);
     BvhState* s = new BvhState();
     s->n = num_items, s->leaf_size = leaf_size, s->constructor_type = constructor_type, s->device = dev;
-    s->key_bytes = (groups || g_morton_bits == 63) ? 8 : 4;
+    s->context = context ? context : device_primary_context(dev);
+    s->morton_bits = morton_bits, s->auto_reference_layout = g_auto_reference_layout;
+    s->key_bytes = (groups || morton_bits == 63) ? 8 : 4;
     s->item_lowers = (const float*)lowers, s->item_uppers = (const float*)uppers, s->groups = groups;
     const char* err = num_items > 0 ? wb_alloc_tree(*s, current_stream(dev)) : nullptr;
     if (!err)
         err = wb_build(*s, current_stream(dev));
-    if (err || !check(cudaMalloc(&s->dev_desc, sizeof(wp_b200_bvh_desc)), "descriptor alloc") || !upload_desc(nullptr, s)) {
+    if (err || !check(cudaMalloc(&s->dev_desc, sizeof(wp_b200_bvh_desc)), "descriptor alloc") || !upload_desc(nullptr, s)
+        || (s->auto_reference_layout && !sync_reference_layout(s, nullptr))) {
         if (err)
             set_error("Warp error: BVH build failed: %s", err);
+        if (s->dev_desc)
+            cudaFree(s->dev_desc);
+        if (s->host_desc)
+            cudaFreeHost(s->host_desc);
         wb_free_tree(*s, current_stream(dev));
         delete s;
         return 0;
@@ -456,6 +612,7 @@ uint64_t wp_bvh_create_device(void* context, wp_vec3* lowers, wp_vec3* uppers, i
 
 void wp_bvh_destroy_device(uint64_t id)
 {
+    g_error[0] = 0;  // the drop-in stub reads this library's message only when the last routed call failed
     BvhState* s = nullptr;
     {
         std::lock_guard<std::mutex> l(g_lock);
@@ -468,12 +625,15 @@ void wp_bvh_destroy_device(uint64_t id)
     DeviceGuard g(s->device);
     cudaStreamSynchronize(current_stream(s->device));
     cudaFree(s->dev_desc);
+    if (s->host_desc)
+        cudaFreeHost(s->host_desc);
     wb_free_tree(*s, current_stream(s->device));
     delete s;
 }
 
 void wp_bvh_refit_device(uint64_t id)
 {
+    g_error[0] = 0;  // the drop-in stub reads this library's message only when the last routed call failed
     BvhState* s = find_tree(id);
     if (!s)
         return;
@@ -481,10 +641,13 @@ void wp_bvh_refit_device(uint64_t id)
     const char* err = wb_refit(*s, current_stream(s->device));
     if (err)
         set_error("Warp error: BVH refit failed: %s", err);
+    else if (s->auto_reference_layout)
+        sync_reference_layout(s, nullptr);
 }
 
 void wp_bvh_rebuild_device(uint64_t id)
 {
+    g_error[0] = 0;  // the drop-in stub reads this library's message only when the last routed call failed
     BvhState* s = find_tree(id);
     if (!s)
         return;
@@ -492,6 +655,8 @@ void wp_bvh_rebuild_device(uint64_t id)
     const char* err = wb_build(*s, current_stream(s->device));
     if (err)
         set_error("Warp error: BVH rebuild failed: %s", err);
+    else if (s->auto_reference_layout)
+        sync_reference_layout(s, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -501,8 +666,27 @@ uint64_t wp_mesh_create_device(void* context, wp_array_t points, wp_array_t velo
                                int num_tris, int support_winding_number, int constructor_type, int* groups,
                                int bvh_leaf_size)
 {
+    return wp_b200_mesh_create_device_ex(context, points, velocities, tris, num_points, num_tris, support_winding_number,
+                                         constructor_type, groups, bvh_leaf_size, 0);
+}
+
+uint64_t wp_b200_mesh_create_device_ex(void* context, wp_array_t points, wp_array_t velocities, wp_array_t tris,
+                                       int num_points, int num_tris, int support_winding_number, int constructor_type,
+                                       int* groups, int bvh_leaf_size, int morton_bits)
+{
+    g_error[0] = 0;  // the drop-in stub reads this library's message only when the last routed call failed
     if (!constructor_supported(constructor_type))
         return 0;
+    if (morton_bits == 0)
+        morton_bits = g_morton_bits;
+    if (morton_bits != 30 && morton_bits != 63) {
+        set_error("Warp error: morton_bits must be 30 or 63 (got %d)", morton_bits);
+        return 0;
+    }
+    if (morton_bits == 63 && groups) {
+        set_error("Warp error: morton_bits=63 cannot be combined with groups (the key holds group << 32 | 30-bit code)");
+        return 0;
+    }
     if (support_winding_number) {
         set_error("Warp error: support_winding_number=True is out of scope for the B200 mesh path");
         return 0;
@@ -522,16 +706,21 @@ uint64_t wp_mesh_create_device(void* context, wp_array_t points, wp_array_t velo
     s.n = num_tris, s.leaf_size = bvh_leaf_size, s.constructor_type = constructor_type, s.device = dev;
     s.is_mesh = true;
     s.groups = groups;
-    s.key_bytes = (groups || g_morton_bits == 63) ? 8 : 4;
+    s.context = context ? context : device_primary_context(dev);
+    s.morton_bits = morton_bits, s.auto_reference_layout = g_auto_reference_layout;
+    s.key_bytes = (groups || morton_bits == 63) ? 8 : 4;
     s.points = (const float*)points.data, s.indices = (const int*)tris.data, s.num_points = num_points;
     const char* err = num_tris > 0 ? wb_alloc_tree(s, current_stream(dev)) : nullptr;
     if (!err)
         err = wb_build(s, current_stream(dev));
-    if (err || !check(cudaMalloc(&m->dev_desc, sizeof(wp_b200_mesh_desc)), "descriptor alloc") || !upload_desc(m, nullptr)) {
+    if (err || !check(cudaMalloc(&m->dev_desc, sizeof(wp_b200_mesh_desc)), "descriptor alloc") || !upload_desc(m, nullptr)
+        || (s.auto_reference_layout && !sync_reference_layout(&s, m))) {
         if (err)
             set_error("Warp error: mesh build failed: %s", err);
         if (m->dev_desc)
             cudaFree(m->dev_desc);
+        if (m->host_desc)
+            cudaFreeHost(m->host_desc);
         wb_free_tree(s, current_stream(dev));
         delete m;
         return 0;
@@ -544,6 +733,7 @@ uint64_t wp_mesh_create_device(void* context, wp_array_t points, wp_array_t velo
 
 void wp_mesh_destroy_device(uint64_t id)
 {
+    g_error[0] = 0;  // the drop-in stub reads this library's message only when the last routed call failed
     MeshState* m = nullptr;
     {
         std::lock_guard<std::mutex> l(g_lock);
@@ -556,12 +746,15 @@ void wp_mesh_destroy_device(uint64_t id)
     DeviceGuard g(m->bvh.device);
     cudaStreamSynchronize(current_stream(m->bvh.device));
     cudaFree(m->dev_desc);
+    if (m->host_desc)
+        cudaFreeHost(m->host_desc);
     wb_free_tree(m->bvh, current_stream(m->bvh.device));
     delete m;
 }
 
 int wp_mesh_refit_device(uint64_t id)
 {
+    g_error[0] = 0;  // the drop-in stub reads this library's message only when the last routed call failed
     MeshState* m = nullptr;
     find_tree(id, &m);
     if (!m) {
@@ -574,11 +767,64 @@ int wp_mesh_refit_device(uint64_t id)
         set_error("Warp error: mesh refit failed: %s", err);
         return 0;
     }
+    if (m->bvh.auto_reference_layout)
+        return sync_reference_layout(&m->bvh, m);
     return 1;
 }
 
 void wp_b200_set_refit_mode(int mode) { g_wb_refit_mode = (mode == 1 || mode == 2) ? mode : 0; }
 int wp_b200_get_refit_mode(void) { return g_wb_refit_mode; }
+void wp_b200_set_auto_reference_layout(int enable) { g_auto_reference_layout = enable ? 1 : 0; }
+int wp_b200_get_auto_reference_layout(void) { return g_auto_reference_layout; }
+
+// per-object options: "refit_mode" (0 auto / 1 atomic / 2 wavefront), "query_order" (0 input / 1 curve / 2 auto),
+// "ray_order" (0 / 1), "auto_reference_layout" (0 / 1); value -1 = follow the process-wide default again.
+// "morton_bits" is read-only (fixed at creation).
+int wp_b200_bvh_set_option(uint64_t id, const char* name, int value)
+{
+    BvhState* s = find_tree(id);
+    if (!s || !name) {
+        set_error("Warp error: invalid id");
+        return 0;
+    }
+    if (!strcmp(name, "refit_mode") && value >= -1 && value <= 2)
+        s->refit_mode = value;
+    else if (!strcmp(name, "query_order") && value >= -1 && value <= 2)
+        s->query_order = value;
+    else if (!strcmp(name, "ray_order") && value >= -1 && value <= 1)
+        s->ray_order = value;
+    else if (!strcmp(name, "auto_reference_layout") && value >= 0 && value <= 1)
+        s->auto_reference_layout = value;
+    else {
+        set_error("Warp error: unknown option or value out of range: %s = %d", name, value);
+        return 0;
+    }
+    return 1;
+}
+
+int wp_b200_bvh_get_option(uint64_t id, const char* name, int* value)
+{
+    BvhState* s = find_tree(id);
+    if (!s || !name || !value) {
+        set_error("Warp error: invalid id");
+        return 0;
+    }
+    if (!strcmp(name, "refit_mode"))
+        *value = s->refit_mode;
+    else if (!strcmp(name, "query_order"))
+        *value = s->query_order;
+    else if (!strcmp(name, "ray_order"))
+        *value = s->ray_order;
+    else if (!strcmp(name, "auto_reference_layout"))
+        *value = s->auto_reference_layout;
+    else if (!strcmp(name, "morton_bits"))
+        *value = s->morton_bits;
+    else {
+        set_error("Warp error: unknown option %s", name);
+        return 0;
+    }
+    return 1;
+}
 
 int wp_b200_mesh_rebuild_device(uint64_t id)
 {
@@ -594,11 +840,14 @@ int wp_b200_mesh_rebuild_device(uint64_t id)
         set_error("Warp error: mesh rebuild failed: %s", err);
         return 0;
     }
+    if (m->bvh.auto_reference_layout)
+        return sync_reference_layout(&m->bvh, m);
     return 1;
 }
 
 int wp_mesh_set_points_device(uint64_t id, wp_array_t points)
 {
+    g_error[0] = 0;  // the drop-in stub reads this library's message only when the last routed call failed
     MeshState* m = nullptr;
     find_tree(id, &m);
     if (!m) {
@@ -619,6 +868,7 @@ int wp_mesh_set_points_device(uint64_t id, wp_array_t points)
 
 void wp_mesh_set_velocities_device(uint64_t id, wp_array_t velocities)
 {
+    g_error[0] = 0;  // the drop-in stub reads this library's message only when the last routed call failed
     MeshState* m = nullptr;
     find_tree(id, &m);
     if (!m) {
@@ -679,8 +929,9 @@ static int query_point_on(MeshState* m, const float* points, int64_t n, float ma
     if (m->bvh.n == 0)
         return zero_point_outputs(n, result, sign, face, u, v, st);
     const int* perm = nullptr;
-    if ((g_query_order == 1 || (g_query_order == 2 && n >= 32768)) && n < (1ll << 30)) {
-        OrderScratch& ws = g_order[m->bvh.device][lane];
+    const int order = m->bvh.query_order >= 0 ? m->bvh.query_order : g_query_order;
+    if ((order == 1 || (order == 2 && n >= 32768)) && n < (1ll << 30)) {
+        OrderScratch& ws = order_scratch(m->bvh.device, st);
 #ifndef WB_SIGN_HILBERT
 #define WB_SIGN_HILBERT 0
 #endif
@@ -713,8 +964,9 @@ static int query_ray_on(MeshState* m, const float* starts, const float* dirs, in
         return ok;
     }
     const int* perm = nullptr;
-    if (g_ray_order == 1 && n < (1ll << 30)) {  // opt-in: coherent batches (primary rays) gain nothing from it
-        OrderScratch& ws = g_order[m->bvh.device][lane];
+    const int order = m->bvh.ray_order >= 0 ? m->bvh.ray_order : g_ray_order;
+    if (order == 1 && n < (1ll << 30)) {  // opt-in: coherent batches (primary rays) gain nothing from it
+        OrderScratch& ws = order_scratch(m->bvh.device, st);
         const char* oerr = wb_ray_order(ws, starts, dirs, n, st);
         if (oerr) {
             set_error("Warp error: ray ordering failed: %s", oerr);
@@ -787,8 +1039,9 @@ int wp_b200_mesh_query_point_sign_normal(uint64_t id, const float* points, int64
     if (m->bvh.n == 0)
         return zero_point_outputs(n, result, sign, face, u, v, st);
     const int* perm = nullptr;
-    if ((g_query_order == 1 || (g_query_order == 2 && n >= 32768)) && n < (1ll << 30)) {
-        OrderScratch& ws = g_order[m->bvh.device][0];
+    const int order = m->bvh.query_order >= 0 ? m->bvh.query_order : g_query_order;
+    if ((order == 1 || (order == 2 && n >= 32768)) && n < (1ll << 30)) {
+        OrderScratch& ws = order_scratch(m->bvh.device, st);
         const char* oerr = wb_morton_order(ws, points, n, st, true);
         if (oerr) {
             set_error("Warp error: query ordering failed: %s", oerr);
@@ -798,7 +1051,7 @@ int wp_b200_mesh_query_point_sign_normal(uint64_t id, const float* points, int64
     }
     float* avg = &((wp_b200_mesh_desc*)m->dev_desc)->average_edge_length;
     const char* err = wb_query_point_sign_normal(make_view(m->bvh), m->bvh.points, m->bvh.indices, points, perm, n, max_dist,
-                                                 epsilon, (double*)m->bvh.partials, avg, result, sign, face, u, v, st);
+                                                 epsilon, m->bvh.edge_partials, avg, result, sign, face, u, v, st);
     if (err) {
         set_error("Warp error: mesh normal-sign query failed: %s", err);
         return 0;
@@ -818,7 +1071,7 @@ int wp_b200_mesh_average_edge_length(uint64_t id, float* out)
     if (m->bvh.n == 0)
         return 1;
     const char* err = wb_query_point_sign_normal(make_view(m->bvh), m->bvh.points, m->bvh.indices, nullptr, nullptr, 0, 0.f,
-                                                 0.f, (double*)m->bvh.partials, avg, nullptr, nullptr, nullptr, nullptr,
+                                                 0.f, m->bvh.edge_partials, avg, nullptr, nullptr, nullptr, nullptr,
                                                  nullptr, st);
     if (err) {
         set_error("Warp error: average edge length failed: %s", err);
@@ -1056,6 +1309,7 @@ int wp_b200_mesh_query_ray_host(uint64_t id, const float* starts, const float* d
 // ------------------------------------------------------------------------------------------------
 static long long* g_scan_scratch[64] = {};
 static size_t g_scan_scratch_words[64] = {};
+static std::mutex g_scan_lock;
 
 static int bvh_query_common(uint64_t id, int ray, const float* qa, const float* qb, const int32_t* roots, int64_t n,
                             float max_dist, int32_t* counts, const int32_t* offsets, int32_t* indices, bool want_mesh = false,
@@ -1193,7 +1447,20 @@ int wp_b200_bvh_get_group_root(uint64_t id, const int32_t* group_ids, int64_t n,
 
 int wp_b200_exclusive_scan_i32(const int32_t* counts, int32_t* offsets, int64_t n)
 {
-    const int dev = current_device();
+    // the scan runs where its buffers live (a Bvh on cuda:1 hands in cuda:1 pointers while the calling thread's current
+    // device may be cuda:0), on that device's current stream -- the stream the count pass was enqueued on
+    int dev = current_device();
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, counts) == cudaSuccess && attr.type == cudaMemoryTypeDevice)
+        dev = attr.device;
+    else
+        cudaGetLastError();
+    if (dev < 0 || dev >= 64) {
+        set_error("Warp error: scan buffers live on an unsupported device ordinal %d", dev);
+        return 0;
+    }
+    DeviceGuard g(dev);
+    std::lock_guard<std::mutex> scan_lock(g_scan_lock);
     const size_t words = (size_t)(n > 0 ? (n + 2047) / 2048 : 0) + 2;
     if (words > g_scan_scratch_words[dev]) {
         if (g_scan_scratch[dev])
@@ -1207,6 +1474,35 @@ int wp_b200_exclusive_scan_i32(const int32_t* counts, int32_t* offsets, int64_t 
     if (err) {
         set_error("Warp error: scan failed: %s", err);
         return 0;
+    }
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reference-layout mirror: node_lowers / node_uppers / node_parents / root (bvh.h:161-207), and for meshes the
+// per-triangle lowers / uppers (mesh.cu:279-280, 310-313) and average_edge_length -- everything an unmodified Warp
+// kernel reads through the id.  The caller holds a DeviceGuard for the tree's device.
+// ------------------------------------------------------------------------------------------------
+static int sync_reference_layout(BvhState* s, MeshState* m)
+{
+    const bool first = s->ref_lowers == nullptr;
+    const char* err = wb_export_reference_layout(*s, current_stream(s->device));
+    if (err) {
+        set_error("Warp error: reference-layout export failed: %s", err);
+        return 0;
+    }
+    if (first && s->n > 0 && !upload_desc(m, m ? nullptr : s))
+        return 0;
+    if (m && s->n > 0) {
+        // a Warp kernel that calls mesh_query_point_sign_normal reads wp::Mesh::average_edge_length through the id
+        // (mesh.h:889): refresh it together with the node arrays
+        float* avg = &((wp_b200_mesh_desc*)m->dev_desc)->average_edge_length;
+        err = wb_query_point_sign_normal(make_view(*s), s->points, s->indices, nullptr, nullptr, 0, 0.f, 0.f, s->edge_partials,
+                                         avg, nullptr, nullptr, nullptr, nullptr, nullptr, current_stream(s->device));
+        if (err) {
+            set_error("Warp error: average edge length failed: %s", err);
+            return 0;
+        }
     }
     return 1;
 }
@@ -1249,26 +1545,7 @@ int wp_b200_bvh_sync_reference_layout(uint64_t id)
         return 0;
     }
     DeviceGuard g(s->device);
-    const bool first = s->ref_lowers == nullptr;
-    const char* err = wb_export_reference_layout(*s, current_stream(s->device));
-    if (err) {
-        set_error("Warp error: reference-layout export failed: %s", err);
-        return 0;
-    }
-    if (first && s->n > 0 && !upload_desc(m, m ? nullptr : s))
-        return 0;
-    if (m && s->n > 0) {
-        // a Warp kernel that calls mesh_query_point_sign_normal reads wp::Mesh::average_edge_length through the id
-        // (mesh.h:889): refresh it together with the node arrays (upload_desc above resets the field)
-        float* avg = &((wp_b200_mesh_desc*)m->dev_desc)->average_edge_length;
-        err = wb_query_point_sign_normal(make_view(*s), s->points, s->indices, nullptr, nullptr, 0, 0.f, 0.f, (double*)s->partials,
-                                         avg, nullptr, nullptr, nullptr, nullptr, nullptr, current_stream(s->device));
-        if (err) {
-            set_error("Warp error: average edge length failed: %s", err);
-            return 0;
-        }
-    }
-    return 1;
+    return sync_reference_layout(s, m);
 }
 
 // EXPERIMENT (not used by any build): parents (reference node indices, -1 for the root) of the n - 1

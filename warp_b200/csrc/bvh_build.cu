@@ -710,6 +710,20 @@ k_export_reference_layout(int n, int leaf_size, const TreeHeader* __restrict__ h
     }
 }
 
+// per-triangle bounds in item order: wp::Mesh::lowers / uppers == BVH::item_lowers / item_uppers of a mesh
+// (compute_triangle_bounds, mesh.cu:16-36), for Warp kernels that read them through the id (mesh.h:2574, bvh.h:602)
+__global__ void __launch_bounds__(BT)
+k_export_item_bounds(MeshSource src, int n, float* __restrict__ lowers, float* __restrict__ uppers)
+{
+    const int t = blockIdx.x * BT + threadIdx.x;
+    if (t >= n)
+        return;
+    float3 lo, hi;
+    src.bounds(t, lo, hi);
+    lowers[3 * (size_t)t] = lo.x, lowers[3 * (size_t)t + 1] = lo.y, lowers[3 * (size_t)t + 2] = lo.z;
+    uppers[3 * (size_t)t] = hi.x, uppers[3 * (size_t)t + 1] = hi.y, uppers[3 * (size_t)t + 2] = hi.z;
+}
+
 // single item: the root is leaf 0 (bvh.cu:285-290 with n == 1)
 template <class Src, class KeyT, bool GROUPED>
 __global__ void k_single_item(Src src, int leaf_size, const int* groups, int* prim, KeyT* keys, int* pos_parent,
@@ -770,7 +784,8 @@ template <class Src, class KeyT, bool GROUPED> const char* build_impl(BvhState& 
     // K1 scene bounds (+ clears histograms / tickets)
     k_scene_bounds<<<s.bounds_blocks, BT, 0, stream>>>(src, n, s.partials, s.tickets, s.ghist);
     // look-back words and arrival counters start from zero
-    WB_CUDA_TRY(cudaMemsetAsync(s.tile_status, 0, sizeof(uint32_t) * 256 * PASSES * (size_t)s.num_tiles, stream));
+    const int sort_tiles = wb_div_up(n, rs_tile_for(n, (int)sizeof(KeyT)));  // what onesweep_sort will use (<= s.num_tiles)
+    WB_CUDA_TRY(cudaMemsetAsync(s.tile_status, 0, sizeof(uint32_t) * 256 * PASSES * (size_t)sort_tiles, stream));
     WB_CUDA_TRY(cudaMemsetAsync(s.counters, 0, sizeof(unsigned) * (size_t)(n - 1), stream));
     // K2 Morton keys + histograms
     k_morton_hist<Src, KeyT, GROUPED><<<s.bounds_blocks, BT, 0, stream>>>(src, n, s.partials, s.bounds_blocks, s.header,
@@ -841,12 +856,15 @@ bool pool_ready(int device)
 // streaming kernels K1/K2: four blocks per SM, each thread strides over ~n / (148*4*256) items
 int bounds_grid(long long n)
 {
-    static int sms = 0;
+    static int sm_count[64] = {};  // per device (the calling thread's current device: every caller holds a DeviceGuard)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int sms = (dev >= 0 && dev < 64) ? sm_count[dev] : 0;
     if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
             sms = 148;
+        if (dev >= 0 && dev < 64)
+            sm_count[dev] = sms;
     }
 #ifndef WB_BOUNDS_BLOCKS_PER_SM
 #define WB_BOUNDS_BLOCKS_PER_SM 4  // 2 / 4 / 8 / 16 measured within 1.5 % of each other at 1.3 M - 100 M triangles
@@ -861,7 +879,9 @@ const char* wb_alloc_tree(BvhState& s, cudaStream_t stream)
     const size_t n = (size_t)s.n;
     const size_t ni = n > 1 ? n - 1 : 1;
     const size_t kb = (size_t)s.key_bytes;
-    s.num_tiles = wb_div_up((long long)n, rs_tile_for((long long)n, s.key_bytes));
+    // look-back words are sized for the SMALL tile whatever tile the build sort picks: the refit plan sorts n - 1 keys
+    // (and may therefore fall below RS_SMALL_LIMIT when the build did not, e.g. n = 2^24) out of the same buffer
+    s.num_tiles = wb_div_up((long long)n, RS_THREADS * RS_ITEMS_SMALL);
     s.bounds_blocks = bounds_grid((long long)n);
     size_t off = 0;
     auto take = [&off](size_t bytes) {
@@ -871,6 +891,7 @@ const char* wb_alloc_tree(BvhState& s, cudaStream_t stream)
     };
     const size_t o_header = take(sizeof(TreeHeader)), o_tickets = take(sizeof(unsigned) * 16),
                  o_ghist = take(sizeof(uint32_t) * 8 * 256), o_partials = take(sizeof(float) * 6 * (size_t)s.bounds_blocks),
+                 o_edge = take(sizeof(double) * 296),
                  o_keys = take(kb * n), o_keys_alt = take(kb * n), o_prim = take(4 * n), o_prim_alt = take(4 * n),
                  o_pairs = take(sizeof(NodeRec) * 2 * ni), o_parent = take(4 * ni), o_pos = take(4 * n),
                  o_counters = take(4 * ni), o_tris = take(s.is_mesh ? sizeof(float4) * 3 * n : 0),
@@ -887,7 +908,7 @@ const char* wb_alloc_tree(BvhState& s, cudaStream_t stream)
         WB_CUDA_TRY(cudaMalloc(&s.arena, off));
     char* b = (char*)s.arena;
     s.header = (TreeHeader*)(b + o_header), s.tickets = (unsigned*)(b + o_tickets), s.ghist = (uint32_t*)(b + o_ghist);
-    s.partials = (float*)(b + o_partials), s.keys = b + o_keys, s.keys_alt = b + o_keys_alt;
+    s.partials = (float*)(b + o_partials), s.edge_partials = (double*)(b + o_edge), s.keys = b + o_keys, s.keys_alt = b + o_keys_alt;
     s.prim = (int*)(b + o_prim), s.prim_alt = (int*)(b + o_prim_alt), s.pairs = (NodeRec*)(b + o_pairs);
     s.parent_int = (int*)(b + o_parent), s.pos_parent = (int*)(b + o_pos), s.counters = (unsigned*)(b + o_counters);
     s.tris = s.is_mesh ? (float4*)(b + o_tris) : nullptr, s.tile_status = (uint32_t*)(b + o_status);
@@ -908,7 +929,7 @@ void wb_free_tree(BvhState& s, cudaStream_t stream)
         else
             cudaFree(s.arena);
     }
-    void* ptrs[] = { s.cub_temp, s.ref_lowers, s.ref_uppers, s.ref_parents, s.ref_root, s.ref_counts };
+    void* ptrs[] = { s.cub_temp, s.ref_lowers, s.ref_uppers, s.ref_parents, s.ref_root, s.ref_counts, s.tri_lowers, s.tri_uppers };
     for (void* p : ptrs)
         if (p)
             cudaFree(p);
@@ -1053,7 +1074,15 @@ const char* wb_export_reference_layout(BvhState& s, cudaStream_t stream)
         WB_CUDA_TRY(cudaMalloc(&s.ref_parents, sizeof(int) * m));
         WB_CUDA_TRY(cudaMalloc(&s.ref_counts, sizeof(int) * m));
         WB_CUDA_TRY(cudaMalloc(&s.ref_root, sizeof(int)));
+        WB_CUDA_TRY(cudaMemset(s.ref_counts, 0, sizeof(int) * m));
+        if (s.is_mesh) {
+            WB_CUDA_TRY(cudaMalloc((void**)&s.tri_lowers, 12 * (size_t)s.n));
+            WB_CUDA_TRY(cudaMalloc((void**)&s.tri_uppers, 12 * (size_t)s.n));
+        }
     }
+    if (s.is_mesh)
+        k_export_item_bounds<<<wb_div_up(s.n, BT), BT, 0, stream>>>(MeshSource { s.points, s.indices }, s.n, s.tri_lowers,
+                                                                    s.tri_uppers);
     WB_CUDA_TRY(cudaMemsetAsync(s.ref_lowers, 0, sizeof(RefHalf) * m, stream));
     WB_CUDA_TRY(cudaMemsetAsync(s.ref_uppers, 0, sizeof(RefHalf) * m, stream));
     const int grid = wb_div_up((long long)m, BT);
@@ -1252,22 +1281,8 @@ const char* wb_morton_order(OrderScratch& ws, const float* pts, long long n, cud
         return nullptr;
     if (n >= (1ll << 30))
         return "query batches are ordered in chunks of fewer than 2^30 points";
-    if (n > ws.capacity) {
-        wb_order_free(ws);
-        const size_t cap = (size_t)n;
-        const size_t tiles = (size_t)wb_div_up(n, RS_THREADS * RS_ITEMS_SMALL);
-        WB_CUDA_TRY(cudaMalloc(&ws.keys, 4 * cap));
-        WB_CUDA_TRY(cudaMalloc(&ws.keys_alt, 4 * cap));
-        WB_CUDA_TRY(cudaMalloc(&ws.idx, 4 * cap));
-        WB_CUDA_TRY(cudaMalloc(&ws.idx_alt, 4 * cap));
-        WB_CUDA_TRY(cudaMalloc(&ws.ghist, 4 * 8 * 256));
-        WB_CUDA_TRY(cudaMalloc(&ws.tile_status, 4 * 256 * 4 * tiles));
-        WB_CUDA_TRY(cudaMalloc(&ws.tickets, 4 * 16));
-        WB_CUDA_TRY(cudaMemset(ws.tickets, 0, 4 * 16));
-        WB_CUDA_TRY(cudaMalloc(&ws.partials, 4 * 6 * 4096));
-        WB_CUDA_TRY(cudaMalloc(&ws.hdr, sizeof(TreeHeader)));
-        ws.capacity = n;
-    }
+    if (const char* e = wb_order_reserve(ws, n, stream))
+        return e;
     const int ni = (int)n;
     const int tiles = wb_div_up(n, rs_tile_for(n));
     const int blocks = bounds_grid(n);
@@ -1367,10 +1382,17 @@ k_ray_key_hist(const float* __restrict__ starts, const float* __restrict__ dirs,
 
 }  // namespace
 
-static const char* order_reserve(OrderScratch& ws, long long n)
+const char* wb_order_reserve(OrderScratch& ws, long long n, cudaStream_t stream)
 {
     if (n <= ws.capacity)
         return nullptr;
+    if (stream) {  // growing allocates: not possible while the stream is being captured into a graph
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone)
+            return "the query-ordering scratch of this stream is too small and cannot grow during graph capture: run the "
+                   "query once before capturing (wp_cuda_graph_begin_capture sizes a new stream's scratch like the "
+                   "largest one in use on the device)";
+    }
     wb_order_free(ws);
     const size_t cap = (size_t)n;
     const size_t tiles = (size_t)wb_div_up(n, RS_THREADS * RS_ITEMS_SMALL);
@@ -1394,7 +1416,7 @@ const char* wb_ray_order(OrderScratch& ws, const float* starts, const float* dir
         return nullptr;
     if (n >= (1ll << 30))
         return "ray batches are ordered in chunks of fewer than 2^30 rays";
-    if (const char* e = order_reserve(ws, n))
+    if (const char* e = wb_order_reserve(ws, n, stream))
         return e;
     const int ni = (int)n;
     const int tiles = wb_div_up(n, rs_tile_for(n));

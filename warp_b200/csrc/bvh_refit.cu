@@ -227,16 +227,17 @@ k_refit_climb(MergeArgs<uint32_t> a, const uint32_t* __restrict__ top, const int
             return cudaGetErrorString(_e); \
     } while (0)
 
-int g_wb_refit_mode = 0;  // 0 auto, 1 atomic counters, 2 wavefront (wp_b200_set_refit_mode)
+int g_wb_refit_mode = 0;  // default of new trees: 0 auto, 1 atomic counters, 2 wavefront (wp_b200_set_refit_mode)
 
 const char* wb_refit(BvhState& s, cudaStream_t stream)
 {
     if (s.n <= 0)
         return nullptr;
-    // auto: wavefront from 2 M items up (see the table above); wp_b200_set_refit_mode / WARP_B200_REFIT force one
+    // auto: wavefront from 2 M items up (see the table above); wp_b200_bvh_set_option(id, "refit_mode") / WARP_B200_REFIT force one
     static const char* mode_env = getenv("WARP_B200_REFIT");
     static const int env_mode = !mode_env ? 0 : (strcmp(mode_env, "atomic") == 0 ? 1 : 2);
-    const int mode = g_wb_refit_mode ? g_wb_refit_mode : env_mode;
+    const int base_mode = s.refit_mode >= 0 ? s.refit_mode : g_wb_refit_mode;
+    const int mode = base_mode ? base_mode : env_mode;
     const bool wave = s.n >= 2 && s.n < (1 << 30) && (mode == 0 ? s.n >= (1 << 21) : mode == 2);
     if (wave && !s.plan_valid)
         if (const char* e = wb_refit_plan(s, stream))

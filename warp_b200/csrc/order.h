@@ -25,3 +25,5 @@ const char* wb_morton_order(OrderScratch& ws, const float* pts, long long n, cud
 // (octahedral 64 x 64), so rays that start together and point the same way share a warp
 const char* wb_ray_order(OrderScratch& ws, const float* starts, const float* dirs, long long n, cudaStream_t stream);
 void wb_order_free(OrderScratch& ws);
+// grow-only reservation for batches of up to n entries (allocates; fails with a message while `stream` is being captured)
+const char* wb_order_reserve(OrderScratch& ws, long long n, cudaStream_t stream);

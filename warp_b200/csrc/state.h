@@ -11,6 +11,14 @@ struct BvhState {
     int constructor_type = 2;
     bool is_mesh = false;
     int device = 0;
+    void* context = nullptr;  // the CUcontext (or ordinal token) the creator passed; echoed in the descriptor
+
+    // per-object options (wp_b200_bvh_set_option); the process-wide setters only provide the defaults at creation
+    int morton_bits = 30;   // 30 = the reference's code (parity), 63 = 21 bits per axis (fixed at creation)
+    int refit_mode = -1;    // -1 process default, 0 auto, 1 atomic counters, 2 wavefront
+    int query_order = -1;   // point batches: -1 process default, 0 input order, 1 curve order, 2 auto (>= 32768 points)
+    int ray_order = -1;     // ray batches: -1 process default, 0 input order, 1 origin / direction order
+    int auto_reference_layout = 0;  // 1: create / refit / rebuild also refresh the reference-layout mirror (drop-in use)
 
     // borrowed inputs (owned by the caller, like the reference: warp.h:105-106)
     const float* item_lowers = nullptr;
@@ -54,6 +62,7 @@ struct BvhState {
     uint32_t* tile_status = nullptr;  // 4 passes x tiles x 256 look-back words
     unsigned* tickets = nullptr;      // small block of counters (tile tickets, last-block tickets)
     float* partials = nullptr;        // per-block scene-bounds partials
+    double* edge_partials = nullptr;  // 296 doubles: per-block partial sums of the average-edge-length reduction (query.cu)
     void* cub_temp = nullptr;         // only used by the WARP_B200_SORT=cub cross-check path
     size_t cub_temp_bytes = 0;
     int num_tiles = 0;
@@ -66,7 +75,15 @@ struct BvhState {
     int* ref_root = nullptr;
     int* ref_counts = nullptr;
 
+    // per-item bounds in the reference's layout: wp::Mesh::lowers / uppers and BVH::item_lowers / item_uppers of a mesh
+    // (mesh.cu:279-280, 310-313; read by mesh_query_aabb / bvh_query_* kernels through the id).  Materialised together
+    // with the node arrays by wb_export_reference_layout.
+    float* tri_lowers = nullptr;
+    float* tri_uppers = nullptr;
+
     void* dev_desc = nullptr;  // device copy of the reference-compatible descriptor; its address is the id
+    void* host_desc = nullptr; // pinned staging ring of the descriptor (stable addresses: uploads are async and capture-safe)
+    unsigned desc_slot = 0;
 };
 
 struct MeshState {
@@ -75,12 +92,15 @@ struct MeshState {
     int num_points = 0, num_tris = 0;
     int points_shape0 = 0, velocities_shape0 = 0;
     void* dev_desc = nullptr;
+    void* host_desc = nullptr;  // pinned staging ring (see BvhState::host_desc)
+    unsigned desc_slot = 0;
+    bool desc_initialised = false;
 };
 
 // build / refit / export drivers (bvh_build.cu, bvh_refit.cu); all enqueue on `stream`
 const char* wb_build(BvhState& s, cudaStream_t stream);
 const char* wb_refit(BvhState& s, cudaStream_t stream);
-extern int g_wb_refit_mode;  // 0 auto, 1 atomic counters, 2 wavefront
+extern int g_wb_refit_mode;  // default refit mode of new trees: 0 auto, 1 atomic counters, 2 wavefront
 const char* wb_refit_plan(BvhState& s, cudaStream_t stream);  // (bvh_build.cu: shares the radix sort)
 const char* wb_refit_merge(BvhState& s, cudaStream_t stream);  // bottom-up pass of the refit (bvh_build.cu)
 // experiment: parents of all internal nodes from the sorted keys alone (bvh_build.cu, k_topology)

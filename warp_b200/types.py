@@ -71,7 +71,17 @@ class Device:
         self.is_cpu = alias == "cpu"
         self.is_cuda = not self.is_cpu
         self.ordinal = -1 if self.is_cpu else int(alias.split(":")[1])
-        self.context = None if self.is_cpu else ctypes.c_void_p(self.ordinal + 1)
+        self._context = None
+
+    @property
+    def context(self):
+        """The device's primary ``CUcontext`` (what the reference's ``Device.context`` holds and passes to the native
+        creators, ``warp/_src/types.py:5947-5950``), resolved on first use."""
+        if self.is_cpu:
+            return None
+        if self._context is None:
+            self._context = ctypes.c_void_p(_lib.core().wp_cuda_device_get_primary_context(self.ordinal))
+        return self._context
 
     def __eq__(self, other):
         return isinstance(other, Device) and other.alias == self.alias
@@ -315,32 +325,38 @@ class BvhConstructor(enum.IntEnum):
             ) from None
 
 
-class _morton_bits:
+def _check_morton_bits(bits, groups):
     """Extension (not in the reference API): ``morton_bits=63`` builds the tree on a 2 097 152^3 Morton grid
     instead of the reference's 1024^3 -- a quality option for meshes with far more than 2^20 occupied cells.
-    Only ``morton_bits=30`` (default) reproduces the reference tree bit for bit."""
+    Only ``morton_bits=30`` (default) reproduces the reference tree bit for bit.  Passed to the native creator as an
+    argument (``wp_b200_*_create_device_ex``), so it is per object and thread-safe."""
+    if bits not in (30, 63):
+        raise ValueError(f"morton_bits must be 30 or 63, current value: {bits}")
+    if bits == 63 and groups is not None:
+        raise RuntimeError("morton_bits=63 cannot be combined with groups (the key holds group << 32 | 30-bit code)")
+    return int(bits)
 
-    def __init__(self, bits, groups):
-        if bits not in (30, 63):
-            raise ValueError(f"morton_bits must be 30 or 63, current value: {bits}")
-        if bits == 63 and groups is not None:
-            raise RuntimeError("morton_bits=63 cannot be combined with groups (the key holds group << 32 | 30-bit code)")
-        self.bits = bits
 
-    def __enter__(self):
-        self.prev = _lib.core().wp_b200_get_morton_bits()
-        _lib.core().wp_b200_set_morton_bits(self.bits)
+class _Options:
+    """Per-object native options (``wp_b200_bvh_set_option``): ``refit_mode``, ``query_order``, ``ray_order``,
+    ``auto_reference_layout``; -1 = follow the process-wide default."""
 
-    def __exit__(self, *exc):
-        _lib.core().wp_b200_set_morton_bits(self.prev)
-        return False
+    def set_option(self, name: str, value: int) -> None:
+        if not _lib.core().wp_b200_bvh_set_option(self.id, name.encode(), int(value)):
+            raise RuntimeError(_lib.error_string())
+
+    def get_option(self, name: str) -> int:
+        v = ctypes.c_int(0)
+        if not _lib.core().wp_b200_bvh_get_option(self.id, name.encode(), ctypes.byref(v)):
+            raise RuntimeError(_lib.error_string())
+        return v.value
 
 
 def _void_p(arr):
     return ctypes.c_void_p(arr.ptr) if arr is not None and arr.ptr else ctypes.c_void_p(0)
 
 
-class Bvh:
+class Bvh(_Options):
     """Bounding volume hierarchy over AABBs -- ``warp/_src/types.py:5796-6078``.
 
     Only GPU trees exist here; ``constructor=None`` or ``"lbvh"`` builds with the B200 LBVH builder,
@@ -385,11 +401,10 @@ class Bvh:
         if self.device.is_cpu:
             raise RuntimeError("warp_b200.Bvh: CPU trees are not available (no CPU fallback for this path)")
 
-        with _morton_bits(morton_bits, groups):
-            self.id = _lib.core().wp_bvh_create_device(
-                self.device.context, _void_p(lowers), _void_p(uppers), len(lowers), int(constructor), _void_p(groups),
-                leaf_size,
-            )  # fmt: skip
+        self.id = _lib.core().wp_b200_bvh_create_device_ex(
+            self.device.context, _void_p(lowers), _void_p(uppers), len(lowers), int(constructor), _void_p(groups),
+            leaf_size, _check_morton_bits(morton_bits, groups),
+        )  # fmt: skip
         self._constructor = constructor
         self.leaf_size = leaf_size
         if not self.id:
@@ -429,7 +444,7 @@ class Bvh:
         return _download_tree(self.id, len(self.lowers))
 
 
-class Mesh:
+class Mesh(_Options):
     """Triangle mesh with an LBVH for closest-point and ray queries -- ``warp/_src/types.py:6081-6310``."""
 
     def __new__(cls, *args, **kwargs):
@@ -494,13 +509,12 @@ class Mesh:
             raise RuntimeError("warp_b200.Mesh: CPU meshes are not available (no CPU fallback for this path)")
 
         self.bvh_leaf_size = bvh_leaf_size
-        with _morton_bits(morton_bits, groups):
-            self.id = _lib.core().wp_mesh_create_device(
-                self.device.context, points.__ctype__(),
-                velocities.__ctype__() if velocities else _lib.array_t(), indices.__ctype__(),
-                len(points), int(indices.size // 3), int(support_winding_number), int(bvh_constructor),
-                _void_p(groups), bvh_leaf_size,
-            )  # fmt: skip
+        self.id = _lib.core().wp_b200_mesh_create_device_ex(
+            self.device.context, points.__ctype__(),
+            velocities.__ctype__() if velocities else _lib.array_t(), indices.__ctype__(),
+            len(points), int(indices.size // 3), int(support_winding_number), int(bvh_constructor),
+            _void_p(groups), bvh_leaf_size, _check_morton_bits(morton_bits, groups),
+        )  # fmt: skip
         if not self.id:
             raise RuntimeError(f"Failed to create mesh: {_lib.error_string()}")
 
