@@ -207,6 +207,10 @@ WP_B200_API int wp_b200_mesh_eval_velocity(uint64_t id, const int32_t* face, con
 /* wp.mesh_eval_face_normal (mesh.h:2870-2888): out[i] = normalize(cross(q - p, r - p)) of triangle face[i], from the
  * mesh's current points; out is n x 3 */
 WP_B200_API int wp_b200_mesh_eval_face_normal(uint64_t id, const int32_t* face, int64_t n, float* out);
+/* same with a per-entry mask: mask[i] == 0 gives the zero vector -- the `normal` field of mesh_query_ray recomputed from
+ * (result, face) alone, bit for bit (used by the sharded ray query: 12 bytes per ray that need not cross NVLink) */
+WP_B200_API int wp_b200_mesh_eval_face_normal_masked(uint64_t id, const int32_t* face, const uint8_t* mask, int64_t n,
+                                                     float* out);
 /* wp.mesh_query_furthest_point_no_sign (mesh.h:678-858): the farthest point of the mesh from each query (always a
  * vertex: (u, v) is (1,0), (0,1) or (0,0)), result = 1 when it lies strictly beyond min_dist */
 WP_B200_API int wp_b200_mesh_query_furthest_point_no_sign(uint64_t id, const float* points, int64_t n, float min_dist,
@@ -328,6 +332,18 @@ WP_B200_API int wp_b200_get_auto_reference_layout(void);
  * for wp.Bvh, bvh.cu:819-843; here a Mesh gets it too): no allocation, same buffers. 1 ok / 0 error */
 WP_B200_API int wp_b200_mesh_rebuild_device(uint64_t id);
 
+/* ---- synthetic-workload generators (bench.py / tests).  Device-side, counter-based RNG (splitmix64 of
+ * the GLOBAL index, so a shard [first_index, first_index + n) of a larger batch is reproducible on any rank), on the
+ * calling thread's current device and its current stream, capture-safe.  1 ok / 0 error.
+ * box queries: out[n] vec3 uniform in [lower, upper] (host pointers to 3 floats each).
+ * cloth: vertices of an n_side^2 grid on [0,1]^2 at frame (*frame_dev + frame_offset), z = 0.05 sin(12x + 0.05f)
+ * cos(9y + 0.03f); queries of frame f = *frame_dev: random cloth vertices at frame f - 1 + N(0, sigma) per axis. */
+WP_B200_API int wp_b200_gen_box_queries(float* out, int64_t n, int64_t first_index, uint64_t seed, const float* lower,
+                                        const float* upper);
+WP_B200_API int wp_b200_gen_cloth_points(float* points, int n_side, const int* frame_dev, int frame_offset);
+WP_B200_API int wp_b200_gen_cloth_queries(float* out, int64_t nq, int n_side, const int* frame_dev, float sigma);
+WP_B200_API int wp_b200_counter_add(int* counter_dev, int value);
+
 /* introspection for parity checks / drop-in kernels */
 typedef struct {
     int num_items, leaf_size, max_nodes, root, height, deep, key_bits;
@@ -362,6 +378,12 @@ WP_B200_API int wp_b200_nccl_allgather(const void* send, void* recv, size_t byte
  * for the current stream (the part's query), join = the current stream waits for the communication stream */
 WP_B200_API int wp_b200_nccl_allgather_part(const void* send, void* recv, size_t part_bytes, size_t shard_stride_bytes,
                                             size_t offset_bytes);
+/* several fields in one NCCL launch (group of all-gathers), on the current stream or (on_comm_stream = 1) on the
+ * library's communication stream; mark / wait_mark: per-buffer completion points on the communication stream */
+WP_B200_API int wp_b200_nccl_allgather_multi(const void* const* send, void* const* recv, const size_t* bytes_per_rank,
+                                             int count, int on_comm_stream);
+WP_B200_API int wp_b200_nccl_mark(int k);
+WP_B200_API int wp_b200_nccl_wait_mark(int k);
 WP_B200_API int wp_b200_nccl_fork(void);
 WP_B200_API int wp_b200_nccl_join(void);
 WP_B200_API int wp_b200_nccl_allreduce_max_f32(float* inout_device, size_t count);

@@ -49,3 +49,16 @@ def random_boxes(n, seed=123, extent=10.0, size=1.0):
     lo = (rng.random((n, 3)) * extent).astype(np.float32)
     hi = (lo + rng.random((n, 3)).astype(np.float32) * size).astype(np.float32)
     return lo, hi
+
+
+def visible_mask(tree):
+    """Boolean mask over nodes: reachable from the root without descending below a packed leaf.  Level-by-level and
+    vectorised, for trees too large for the Python loop of visible_nodes()."""
+    lo, hi = tree["node_lowers"]["ib"], tree["node_uppers"]["ib"]
+    mask = np.zeros(len(lo), bool)
+    frontier = np.array([tree["root"]], np.int64)
+    while frontier.size:
+        mask[frontier] = True
+        inner = frontier[(lo[frontier] >> 31) == 0]
+        frontier = np.concatenate([lo[inner] & 0x7FFFFFFF, hi[inner] & 0x7FFFFFFF]).astype(np.int64)
+    return mask

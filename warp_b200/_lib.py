@@ -104,6 +104,7 @@ SIGNATURES = {
     "wp_b200_mesh_eval_position": (_i, [_u64, _vp, _vp, _vp, _i64, _vp]),
     "wp_b200_mesh_eval_velocity": (_i, [_u64, _vp, _vp, _vp, _i64, _vp]),
     "wp_b200_mesh_eval_face_normal": (_i, [_u64, _vp, _i64, _vp]),
+    "wp_b200_mesh_eval_face_normal_masked": (_i, [_u64, _vp, _vp, _i64, _vp]),
     "wp_b200_mesh_query_furthest_point_no_sign": (_i, [_u64, _vp, _i64, _f, _vp, _vp, _vp, _vp]),
     "wp_b200_mesh_query_point_no_sign_host":(_i, [_u64, _vp, _i64, _f, _vp, _vp, _vp, _vp]),
     "wp_b200_mesh_query_point_host": (_i, [_u64, _vp, _i64, _f, _vp, _vp, _vp, _vp, _vp]),
@@ -143,12 +144,19 @@ SIGNATURES = {
     "wp_b200_bvh_sync_reference_layout": (_i, [_u64]),
     "wp_b200_bvh_download": (_i, [_u64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wp_b200_experiment_parallel_topology": (ctypes.c_float, [_u64, _vp, _i]),
+    "wp_b200_gen_box_queries": (_i, [_vp, _i64, _i64, _u64, _vp, _vp]),
+    "wp_b200_gen_cloth_points": (_i, [_vp, _i, _vp, _i]),
+    "wp_b200_gen_cloth_queries": (_i, [_vp, _i64, _i, _vp, _f]),
+    "wp_b200_counter_add": (_i, [_vp, _i]),
     # multi-GPU
     "wp_b200_nccl_load": (_i, [ctypes.c_char_p]),
     "wp_b200_nccl_unique_id": (_i, [_vp]),
     "wp_b200_nccl_init": (_i, [_vp, _i, _i]),
     "wp_b200_nccl_allgather": (_i, [_vp, _vp, _sz]),
     "wp_b200_nccl_allgather_part": (_i, [_vp, _vp, _sz, _sz, _sz]),
+    "wp_b200_nccl_allgather_multi": (_i, [_vp, _vp, _vp, _i, _i]),
+    "wp_b200_nccl_mark": (_i, [_i]),
+    "wp_b200_nccl_wait_mark": (_i, [_i]),
     "wp_b200_nccl_fork": (_i, []),
     "wp_b200_nccl_join": (_i, []),
     "wp_b200_nccl_allreduce_max_f32": (_i, [_vp, _sz]),

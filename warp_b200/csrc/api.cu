@@ -1163,6 +1163,11 @@ int wp_b200_mesh_eval_velocity(uint64_t id, const int32_t* face, const float* u,
 
 int wp_b200_mesh_eval_face_normal(uint64_t id, const int32_t* face, int64_t n, float* out)
 {
+    return wp_b200_mesh_eval_face_normal_masked(id, face, nullptr, n, out);
+}
+
+int wp_b200_mesh_eval_face_normal_masked(uint64_t id, const int32_t* face, const uint8_t* mask, int64_t n, float* out)
+{
     MeshState* m = query_mesh(id);
     if (!m)
         return 0;
@@ -1172,7 +1177,7 @@ int wp_b200_mesh_eval_face_normal(uint64_t id, const int32_t* face, int64_t n, f
         return 1;
     if (!m->points_data || !m->indices_data)  // mesh.h:2874-2875: vec3()
         return check(cudaMemsetAsync(out, 0, 12 * (size_t)n, st), "memset");
-    const char* err = wb_mesh_face_normal((const float*)m->points_data, (const int*)m->indices_data, face, n, out, st);
+    const char* err = wb_mesh_face_normal((const float*)m->points_data, (const int*)m->indices_data, face, mask, n, out, st);
     if (err) {
         set_error("Warp error: mesh face normal failed: %s", err);
         return 0;

@@ -40,6 +40,8 @@ fn_group p_group_start = nullptr, p_group_end = nullptr;
 NcclComm g_comm = nullptr;
 int g_world = 0;
 cudaEvent_t g_fork_event = nullptr, g_join_event = nullptr;
+constexpr int kMarks = 8;
+cudaEvent_t g_mark[kMarks] = {};
 cudaStream_t g_comm_stream = nullptr;
 char g_nccl_error[512] = "";
 
@@ -144,6 +146,46 @@ int wp_b200_nccl_allgather_part(const void* send, void* recv, size_t part_bytes,
     }
     const int rc2 = p_group_end();
     return (rc || rc2) ? fail("ncclSend/ncclRecv group", rc ? rc : rc2) : 1;
+}
+
+// Several fields of one result set in ONE NCCL launch (ncclGroupStart / End around the per-field all-gathers): what the
+// sharded queries gather after a traversal.  on_comm_stream = 1 enqueues on the library's communication stream (after a
+// wp_b200_nccl_fork()) so that the gather of one batch runs under the traversal of the next.
+int wp_b200_nccl_allgather_multi(const void* const* send, void* const* recv, const size_t* bytes_per_rank, int count,
+                                 int on_comm_stream)
+{
+    if (!g_comm)
+        return fail("allgather_multi (communicator not initialised)", 0);
+    if (!p_group_start || !p_group_end)
+        return fail("allgather_multi (ncclGroupStart / End not available)", 0);
+    cudaStream_t st = on_comm_stream ? g_comm_stream : (cudaStream_t)wp_cuda_context_get_stream(nullptr);
+    int rc = p_group_start();
+    for (int k = 0; k < count && !rc; ++k)
+        if (bytes_per_rank[k])
+            rc = p_all_gather(send[k], recv[k], bytes_per_rank[k], kNcclInt8, g_comm, st);
+    const int rc2 = p_group_end();
+    return (rc || rc2) ? fail("grouped ncclAllGather", rc ? rc : rc2) : 1;
+}
+
+// mark(k): remember the current tail of the communication stream; wait_mark(k): the CURRENT stream waits for that point
+// (a buffer that gather k read may be overwritten afterwards) -- finer than wp_b200_nccl_join(), which waits for everything
+int wp_b200_nccl_mark(int k)
+{
+    if (!g_comm || k < 0 || k >= kMarks)
+        return fail("mark (communicator not initialised or bad index)", 0);
+    if (!g_mark[k] && cudaEventCreateWithFlags(&g_mark[k], cudaEventDisableTiming) != cudaSuccess)
+        return 0;
+    return cudaEventRecord(g_mark[k], g_comm_stream) == cudaSuccess;
+}
+
+int wp_b200_nccl_wait_mark(int k)
+{
+    if (!g_comm || k < 0 || k >= kMarks)
+        return fail("wait_mark (communicator not initialised or bad index)", 0);
+    if (!g_mark[k])
+        return 1;  // never recorded: nothing to wait for
+    cudaStream_t st = (cudaStream_t)wp_cuda_context_get_stream(nullptr);
+    return cudaStreamWaitEvent(st, g_mark[k], 0) == cudaSuccess;
 }
 
 int wp_b200_nccl_fork(void)

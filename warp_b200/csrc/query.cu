@@ -1137,10 +1137,14 @@ k_query_furthest(TreeView tv, const float* __restrict__ pts, long long nq, float
 
 // mesh_eval_face_normal (mesh.h:2870-2888): normalize(cross(q - p, r - p)) from the caller's arrays
 __global__ void __launch_bounds__(QT)
-k_mesh_face_normal(const float* __restrict__ points, const int* __restrict__ indices, const int* __restrict__ face, long long n,
-                   float* __restrict__ out)
+k_mesh_face_normal(const float* __restrict__ points, const int* __restrict__ indices, const int* __restrict__ face,
+                   const uint8_t* __restrict__ mask, long long n, float* __restrict__ out)
 {
     for (long long i = (long long)blockIdx.x * QT + threadIdx.x; i < n; i += (long long)gridDim.x * QT) {
+        if (mask && !mask[i]) {  // a ray that missed: mesh_query_ray leaves the normal zero (mesh.h:2216-2248)
+            out[3 * i + 0] = 0.f, out[3 * i + 1] = 0.f, out[3 * i + 2] = 0.f;
+            continue;
+        }
         float3 p, q, r;
         MeshSource { points, indices }.tri(face[i], p, q, r);
         const float3 nrm = wb_cross(wb_sub(q, p), wb_sub(r, p));
@@ -1380,12 +1384,12 @@ const char* wb_query_furthest(const TreeView& tv, const float* pts, long long nq
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
-const char* wb_mesh_face_normal(const float* points, const int* indices, const int* face, long long n, float* out,
-                                cudaStream_t stream)
+const char* wb_mesh_face_normal(const float* points, const int* indices, const int* face, const uint8_t* mask, long long n,
+                                float* out, cudaStream_t stream)
 {
     if (n <= 0)
         return nullptr;
-    k_mesh_face_normal<<<query_grid(n), QT, 0, stream>>>(points, indices, face, n, out);
+    k_mesh_face_normal<<<query_grid(n), QT, 0, stream>>>(points, indices, face, mask, n, out);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

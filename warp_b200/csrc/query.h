@@ -42,8 +42,9 @@ const char* wb_sign_parity(const TreeView& tv, const float* pts, long long nq, i
 // mesh_query_furthest_point_no_sign (mesh.h:678-858) and mesh_eval_face_normal (mesh.h:2870-2888)
 const char* wb_query_furthest(const TreeView& tv, const float* pts, long long nq, float min_dist, uint8_t* result, int* face,
                               float* u, float* v, cudaStream_t stream);
-const char* wb_mesh_face_normal(const float* points, const int* indices, const int* face, long long n, float* out,
-                                cudaStream_t stream);
+// mask (optional): entries with mask[i] == 0 get the zero vector (the normal of a ray that missed)
+const char* wb_mesh_face_normal(const float* points, const int* indices, const int* face, const uint8_t* mask, long long n,
+                                float* out, cudaStream_t stream);
 // mesh_query_sphere hit lists (mesh.h:2457-2737): offsets == NULL counts into counts[nq], else fills indices
 const char* wb_mesh_query_sphere(const TreeView& tv, const float* centers, const float* radii, long long nq, int* counts,
                                  const int* offsets, int* indices, cudaStream_t stream);

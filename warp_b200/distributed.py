@@ -91,6 +91,24 @@ class NcclCommunicator:
                                                        shard_stride_bytes, offset_bytes):
             raise RuntimeError("pipelined all-gather failed")
 
+    def allgather_multi(self, fields, comm_stream: bool = False):
+        """``fields``: list of (send, recv, nbytes_per_rank) device arrays -- gathered in ONE NCCL launch (a group of
+        all-gathers), on the current stream or, with ``comm_stream=True``, on the library's communication stream."""
+        k = len(fields)
+        send = (ctypes.c_void_p * k)(*[f[0].ptr for f in fields])
+        recv = (ctypes.c_void_p * k)(*[f[1].ptr for f in fields])
+        nbytes = (ctypes.c_size_t * k)(*[int(f[2]) for f in fields])
+        if not _lib.core().wp_b200_nccl_allgather_multi(send, recv, nbytes, k, 1 if comm_stream else 0):
+            raise RuntimeError("grouped ncclAllGather failed")
+
+    def mark(self, k: int):
+        if not _lib.core().wp_b200_nccl_mark(int(k)):
+            raise RuntimeError("NCCL mark failed")
+
+    def wait_mark(self, k: int):
+        if not _lib.core().wp_b200_nccl_wait_mark(int(k)):
+            raise RuntimeError("NCCL wait_mark failed")
+
     def fork(self):
         if not _lib.core().wp_b200_nccl_fork():
             raise RuntimeError("NCCL fork failed")
@@ -184,11 +202,12 @@ def gather_fields(local: dict, plan: ShardPlan, comm, alloc):
     ``alloc(field, count)`` returns a destination buffer; ``comm.allgather(send, recv, nbytes)``
     moves the bytes.  Returns {field: gathered buffer}; callers trim to ``plan.n``.
     """
-    out = {}
-    for name, arr in local.items():
-        dst = alloc(name, plan.padded)
-        comm.allgather(arr, dst, plan.shard * FIELD_BYTES[name])
-        out[name] = dst
+    out = {name: alloc(name, plan.padded) for name in local}
+    if hasattr(comm, "allgather_multi"):  # one launch for the whole result set
+        comm.allgather_multi([(arr, out[name], plan.shard * FIELD_BYTES[name]) for name, arr in local.items()])
+    else:
+        for name, arr in local.items():
+            comm.allgather(arr, out[name], plan.shard * FIELD_BYTES[name])
     return out
 
 
@@ -266,18 +285,105 @@ def sharded_query_point(mesh, local_points, plan: ShardPlan, max_dist: float, co
     return _sharded(local, dtypes, plan, comm, mesh.device, global_out)
 
 
+RAY_WIRE_FIELDS = ("result", "sign", "face", "t", "u", "v")  # 21 bytes per ray cross NVLink; `normal` does not
+
+
+def ray_normals_from_faces(mesh, result, face, out):
+    """``normal`` of ``mesh_query_ray`` recomputed from (``result``, ``face``) on this rank's replica of the mesh:
+    ``normalize(cross(b - a, c - a))`` of the hit face (``mesh.h:1880-1886``), the zero vector for a miss -- the same
+    arithmetic on the same vertices, hence the same bits as the normal the tracing rank produced."""
+    n = len(face)
+    ok = _lib.core().wp_b200_mesh_eval_face_normal_masked(mesh.id, ctypes.c_void_p(face.ptr), ctypes.c_void_p(result.ptr), n,
+                                                           ctypes.c_void_p(out.ptr))
+    if not ok:
+        raise RuntimeError(f"ray normal evaluation failed: {_lib.error_string()}")
+    return out
+
+
 def sharded_query_ray(mesh, local_starts, local_dirs, plan: ShardPlan, max_t: float, comm, rank: int, local_out=None,
                       global_out=None):
-    """Closest ray hit (``mesh_query_ray``) for this rank's shard of a global ray batch; the seven result fields
-    are all-gathered into global ray order (``normal`` as 12-byte vec3 entries)."""
+    """Closest ray hit (``mesh_query_ray``) for this rank's shard of a global ray batch.  ``result``, ``sign``,
+    ``face``, ``t``, ``u``, ``v`` (21 bytes per ray) are all-gathered into global ray order in one NCCL launch; the
+    12-byte ``normal`` is NOT sent -- every rank holds a replica of the mesh and recomputes it from the gathered
+    (``result``, ``face``), bit for bit (:func:`ray_normals_from_faces`)."""
     from .queries import mesh_query_ray
-    from .types import float32, int32, uint8, vec3
+    from .types import empty, float32, int32, uint8, vec3
 
     res = mesh_query_ray(mesh, local_starts, local_dirs, max_t, out=local_out)
-    local = {"result": res.result, "sign": res.sign, "face": res.face, "t": res.t, "u": res.u, "v": res.v,
-             "normal": res.normal}  # fmt: skip
     dtypes = {"result": uint8, "sign": float32, "face": int32, "t": float32, "u": float32, "v": float32, "normal": vec3}
-    return _sharded(local, dtypes, plan, comm, mesh.device, global_out)
+    if comm is None:
+        return {k: getattr(res, k) for k in dtypes}, plan.n
+    if global_out is None:
+        global_out = {k: empty(plan.padded, dt, mesh.device) for k, dt in dtypes.items()}
+    local = {k: getattr(res, k) for k in RAY_WIRE_FIELDS}
+    gather_fields(local, plan, comm, lambda name, count: global_out[name])
+    ray_normals_from_faces(mesh, global_out["result"], global_out["face"], global_out["normal"])
+    return global_out, plan.n
+
+
+class QueryPipeline:
+    """Software pipeline over a stream of equally sized query batches ("pipeline in chunks of 8-16 M
+    queries so the gather of chunk k overlaps the traversal of chunk k+1"): ``submit()`` answers this rank's shard of
+    batch k on the compute stream into one of two local result sets and hands the gather of that set -- one grouped
+    NCCL launch -- to the communication stream, where it runs under the traversal of batch k + 1.  ``result(k)`` /
+    ``finish()`` order the compute stream after the gathers.  ``kind``: "point_no_sign" | "point" | "ray"."""
+
+    POINT_FIELDS = ("result", "face", "u", "v")
+
+    def __init__(self, mesh, plan: ShardPlan, comm, kind: str = "point_no_sign", max_dist: float = 1.0e6, depth: int = 2):
+        from .queries import MeshQueryPoint, MeshQueryRay
+        from .types import empty, float32, int32, uint8, vec3
+
+        self.mesh, self.plan, self.comm, self.kind, self.max_dist, self.depth = mesh, plan, comm, kind, float(max_dist), depth
+        dev, n = mesh.device, plan.shard
+        if kind == "ray":
+            self.wire = RAY_WIRE_FIELDS
+            mk = lambda cnt: MeshQueryRay(empty(cnt, uint8, dev), empty(cnt, float32, dev), empty(cnt, int32, dev),  # noqa: E731
+                                          empty(cnt, float32, dev), empty(cnt, float32, dev), empty(cnt, float32, dev),
+                                          empty(cnt, vec3, dev))
+        else:
+            self.wire = self.POINT_FIELDS + (("sign",) if kind == "point" else ())
+            mk = lambda cnt: MeshQueryPoint(empty(cnt, uint8, dev), empty(cnt, float32, dev), empty(cnt, int32, dev),  # noqa: E731
+                                            empty(cnt, float32, dev), empty(cnt, float32, dev))
+        self.local = [mk(n) for _ in range(depth)]
+        self.gathered = [mk(plan.padded) for _ in range(depth)] if comm is not None else self.local
+        self.submitted = 0
+
+    def submit(self, *inputs):
+        from .queries import mesh_query_point, mesh_query_point_no_sign, mesh_query_ray
+
+        k = self.submitted
+        slot = k % self.depth
+        if self.comm is not None and k >= self.depth:
+            self.comm.wait_mark(slot)  # the gather that last read this local set (and wrote this gathered set) is done
+        if self.kind == "ray":
+            mesh_query_ray(self.mesh, inputs[0], inputs[1], self.max_dist, out=self.local[slot])
+        elif self.kind == "point":
+            mesh_query_point(self.mesh, inputs[0], self.max_dist, out=self.local[slot])
+        else:
+            mesh_query_point_no_sign(self.mesh, inputs[0], self.max_dist, out=self.local[slot])
+        if self.comm is not None:
+            self.comm.fork()
+            self.comm.allgather_multi([(getattr(self.local[slot], f), getattr(self.gathered[slot], f),
+                                        self.plan.shard * FIELD_BYTES[f]) for f in self.wire], comm_stream=True)
+            self.comm.mark(slot)
+        self.submitted += 1
+        return k
+
+    def result(self, k: int):
+        """Result set of batch ``k`` (valid for the last ``depth`` batches), ordered after its gather on the compute
+        stream; for rays the normals of the gathered set are recomputed here."""
+        slot = k % self.depth
+        if self.comm is not None:
+            self.comm.wait_mark(slot)
+            if self.kind == "ray":
+                g = self.gathered[slot]
+                ray_normals_from_faces(self.mesh, g.result, g.face, g.normal)
+        return self.gathered[slot]
+
+    def finish(self):
+        if self.comm is not None:
+            self.comm.join()
 
 
 class GlooCommunicator:
@@ -310,6 +416,16 @@ class GlooCommunicator:
         flat = recv.view(np.uint8).reshape(-1)
         for r, b in enumerate(bufs):
             flat[r * shard_stride_bytes + offset_bytes : r * shard_stride_bytes + offset_bytes + part_bytes] = b.numpy()
+
+    def allgather_multi(self, fields, comm_stream: bool = False):
+        for send, recv, nbytes in fields:
+            self.allgather(send, recv, nbytes)
+
+    def mark(self, k: int):
+        pass
+
+    def wait_mark(self, k: int):
+        pass
 
     def fork(self):
         pass
