@@ -164,6 +164,46 @@ def timed(fn, reps, warm=2):
     return float(np.median(ts)), float(np.min(ts))
 
 
+def timing_c2_c3():
+    """The part bench.py runs in-line (`extra.reference_cuda`): C2 build / refit / closest point and C3 rays with the
+    reference's own CUDA path on the same GPU, in the same run.  Prints one JSON line."""
+    res = {"warp_version": wp.__version__, "device": wp.get_device(DEV).name, "note": "unmodified reference (NVIDIA/warp "
+           "built by its own build_lib.py --quick, sm_100 SASS), kernels of asv/benchmarks/spatial_query.py, default module options"}
+    P, I = mg.noisy_sphere(8, 0.02, 1)
+    pts = wp.array(P, dtype=wp.vec3, device=DEV)
+    idx = wp.array(I, dtype=wp.int32, device=DEV)
+    holder = {}
+
+    def build():
+        holder["m"] = wp.Mesh(pts, idx, bvh_constructor="lbvh")
+
+    res["c2_triangles"] = len(I) // 3
+    res["c2_build_ms_median"], res["c2_build_ms_min"] = timed(build, 10)
+    m = holder["m"]
+    res["c2_refit_ms_median"], res["c2_refit_ms_min"] = timed(m.refit, 20)
+    nq = 1 << 24
+    q = wp.array(mg.box_queries(P, nq, seed=2), dtype=wp.vec3, device=DEV)
+    r, f = wp.zeros(nq, dtype=wp.int32, device=DEV), wp.zeros(nq, dtype=wp.int32, device=DEV)
+    sg, u, v = (wp.zeros(nq, dtype=float, device=DEV) for _ in range(3))
+    ms, mn = timed(lambda: wp.launch(k_point_no_sign, dim=nq, inputs=[m.id, q, 1.0e6], outputs=[r, f, u, v], device=DEV), 5)
+    res["c2_point_no_sign_ms_median"], res["c2_point_no_sign_qps"] = ms, nq / (ms * 1e-3)
+    ms, mn = timed(lambda: wp.launch(k_point, dim=nq // 8, inputs=[m.id, q, 1.0e6], outputs=[r, sg, f, u, v], device=DEV), 3)
+    res["c2_point_sign_qps_on_2M_sample"] = (nq // 8) / (ms * 1e-3)
+    del m, holder, q
+    Ph, Ih = mg.heightfield(2237, 4)
+    hm = wp.Mesh(wp.array(Ph, dtype=wp.vec3, device=DEV), wp.array(Ih, dtype=wp.int32, device=DEV), bvh_constructor="lbvh")
+    S, D = mg.pinhole_rays(4096, 4096)
+    n = len(S)
+    s, d = wp.array(S, dtype=wp.vec3, device=DEV), wp.array(D, dtype=wp.vec3, device=DEV)
+    r, f = wp.zeros(n, dtype=wp.int32, device=DEV), wp.zeros(n, dtype=wp.int32, device=DEV)
+    sg, t, u, v = (wp.zeros(n, dtype=float, device=DEV) for _ in range(4))
+    nrm = wp.zeros(n, dtype=wp.vec3, device=DEV)
+    ms, mn = timed(lambda: wp.launch(k_ray, dim=n, inputs=[hm.id, s, d, 1.0e6], outputs=[r, sg, f, t, u, v, nrm], device=DEV), 5)
+    res["c3_triangles"] = len(Ih) // 3
+    res["c3_ray_ms_median"], res["c3_rays_per_s"] = ms, n / (ms * 1e-3)
+    print("REF_CUDA " + json.dumps(res), flush=True)
+
+
 def timing():
     res = {"warp_version": wp.__version__, "device": wp.get_device(DEV).name, "note": "reference built with "
            "build_lib.py --quick patched to emit sm_100 SASS only (see DESIGN.md); default module options"}
@@ -259,4 +299,4 @@ def timing():
 
 
 if __name__ == "__main__":
-    {"golden": golden, "timing": timing}[sys.argv[1]]()
+    {"golden": golden, "timing": timing, "timing_c2_c3": timing_c2_c3}[sys.argv[1]]()

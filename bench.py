@@ -8,10 +8,16 @@ against the LBVH of a 1 310 720-triangle noisy sphere (icosphere, 8 subdivisions
 configs[1].  `value` is whole-job queries/s with inputs and outputs resident in HBM; `e2e` is the same
 batch through the public API with pinned HOST buffers (H2D + D2H inside the timed region).  With
 N > 1 (launched by torchrun, one rank per GPU) the mesh and tree are replicated, every rank answers
-its own 16 M-query shard (weak scaling) and the SoA results are all-gathered with NCCL inside the
-timed region.  LBVH build / refit times, ray throughput (config C3) and their rooflines ride along
-in `extra`.  `--impl reference` times the reference's own CPU implementation (oracle/_ref, the
-unmodified reference C++; falls back to the C port) on a bounded sample of the same workload.
+its own 16 M-query shard per step (weak scaling) and the SoA results are all-gathered with NCCL inside the
+timed region: one grouped launch per batch on the communication stream, running under the traversal of the
+next batch ("pipeline in chunks of 8-16 M queries"); the K steps are timed as one region.
+
+`extra` carries the other BASELINE.json configs and the side measurements: LBVH build / refit ms with their HBM
+rooflines (C2), signed queries, rays (C3, + sharded), the 1000-frame cloth loop as one CUDA graph per frame (C4),
+the 100 M-triangle mesh with device-generated query shards at N GPUs (C5), a sampled oracle diff of the timed batch
+with a tie counter, the reference's CUDA path on the same GPU in the same run (when baseline/_ref is present) and the
+reference's CPU path on config C1 at 1 and N host threads.  `--impl reference` times the reference's own CPU
+implementation (oracle/_ref, the unmodified reference C++; falls back to the C port) on a bounded sample.
 
 No torch: device memory, streams, events and NCCL all go through libwarp_b200.so.
 """
@@ -41,12 +47,6 @@ MAX_DIST = 1.0e6
 WORKLOAD = "C2: LBVH of 1.31M-triangle noisy icosphere; 16.8M mesh_query_point_no_sign queries in 1.2x AABB per GPU"
 
 
-# pieces of the pipelined gather at N > 1 (distributed.sharded_query_point_no_sign(parts=)).  Measured at 2 GPUs:
-# 1 piece 24.9 ms/step, 4 pieces 32.6 ms -- a quarter-size batch is Morton-sorted on its own and is sparser than the
-# whole batch, which costs more than the 0.7 ms (2 GPUs) / 2.7 ms (8 GPUs) of gather it hides.  So: one piece.
-GATHER_PARTS = int(os.environ.get("BENCH_GATHER_PARTS", "1"))
-
-
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -58,7 +58,7 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -108,16 +108,14 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline
+# reference arm / cpu baselines (the only code that touches oracle/)
 # ------------------------------------------------------------------------------------------------
 
-def cpu_reference_setup():
-    """Reference CPU objects for the C2 mesh: what `wp.Mesh(..., device='cpu')` gives a user = SAH tree,
-    leaf 4 (warp/_src/types.py:6186-6191), queried by the reference's own mesh.h code."""
+def cpu_reference_setup(P, I):
+    """Reference CPU objects for a mesh: what `wp.Mesh(..., device='cpu')` gives a user = SAH tree, leaf 4
+    (warp/_src/types.py:6186-6191), queried by the reference's own mesh.h code; the C port of the LBVH otherwise."""
     import oracle
-    from warp_b200 import meshgen as mg
 
-    P, I = mg.noisy_sphere(SUBDIV, 0.02, 1)
     if oracle.ref_available():
         t0 = time.perf_counter()
         mesh = oracle.RefMesh(P, I, oracle.SAH, 4)
@@ -127,7 +125,7 @@ def cpu_reference_setup():
         def run(q, threads):
             return mesh.query_point_no_sign(q, MAX_DIST, nthreads=threads)
 
-        return P, I, run, "reference", cores, build_s
+        return run, "reference", cores, build_s
     t0 = time.perf_counter()
     tree = oracle.mesh_lbvh_build(P, I, 4)
     build_s = time.perf_counter() - t0
@@ -135,24 +133,54 @@ def cpu_reference_setup():
     def run(q, threads):
         return oracle.query_point_no_sign(P, I, tree, q, MAX_DIST)
 
-    return P, I, run, "port", 1, build_s
+    return run, "port", 1, build_s
 
 
 def cpu_baseline(sample_queries: int):
+    """C2 sample on the host: all threads (`value`) and one thread -- the reference's own device='cpu' launch is a serial
+    loop over queries (warp/_src/codegen.py:7018-7021), so the 1-thread figure is what a Warp user sees."""
     from warp_b200 import meshgen as mg
 
-    P, I, run, kind, cores, build_s = cpu_reference_setup()
+    P, I = mg.noisy_sphere(SUBDIV, 0.02, 1)
+    run, kind, cores, build_s = cpu_reference_setup(P, I)
     q = mg.box_queries(P, sample_queries, seed=2)
     run(q[:2048], cores)
     t0 = time.perf_counter()
     run(q, cores)
     dt = time.perf_counter() - t0
+    one = q[: max(sample_queries // 16, 4096)]
+    t0 = time.perf_counter()
+    run(one, 1)
+    dt1 = time.perf_counter() - t0
     return {
         "value": sample_queries / dt, "unit": UNIT, "cores": cores, "kind": kind,
+        "value_1_thread": len(one) / dt1,
         "sample": f"{sample_queries} of the {NQ} queries (seed 2) on the reference's CPU tree "
                   f"({'SAH, leaf 4, built in %.2f s' % build_s if kind == 'reference' else 'oracle LBVH, leaf 4'}), "
-                  f"{cores} host thread(s), {dt:.2f} s",
+                  f"{cores} host thread(s), {dt:.2f} s; 1 thread: {len(one)} queries, {dt1:.2f} s",
     }  # fmt: skip
+
+
+def cpu_c1():
+    """BASELINE.json configs[0] on this box's host: 81 920-triangle icosphere (SAH, leaf 4), queries uniform in
+    [-1.5, 1.5]^3 (seed 42) -- a bounded sample of the 1 M, at 1 thread (the reference's behaviour) and all threads."""
+    from warp_b200 import meshgen as mg
+
+    P, I = mg.icosphere(6)
+    run, kind, cores, build_s = cpu_reference_setup(P, I)
+    n1, nn = 1 << 15, 1 << 18
+    q = mg.cube_queries(nn, 1.5, 42)
+    run(q[:1024], cores)
+    t0 = time.perf_counter()
+    run(q[:n1], 1)
+    d1 = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    run(q, cores)
+    dn = time.perf_counter() - t0
+    return {"workload": "C1: 81 920-triangle icosphere, mesh_query_point_no_sign, queries uniform in [-1.5, 1.5]^3 (seed 42)",
+            "kind": kind, "build_s": build_s, "queries_per_s_1_thread": n1 / d1, "sample_1_thread": n1,
+            "queries_per_s_all_threads": nn / dn, "threads": cores, "sample_all_threads": nn,
+            "note": "the reference's device='cpu' launch is single-threaded (codegen.py:7018-7021): the 1-thread figure is its own"}  # fmt: skip
 
 
 def run_reference_arm(args):
@@ -161,7 +189,8 @@ def run_reference_arm(args):
         return 0
     from warp_b200 import meshgen as mg
 
-    P, I, run, kind, cores, build_s = cpu_reference_setup()
+    P, I = mg.noisy_sphere(SUBDIV, 0.02, 1)
+    run, kind, cores, build_s = cpu_reference_setup(P, I)
     sample = 1 << 18
     q = mg.box_queries(P, sample * (args.steps + args.warmup), seed=2)
     for w in range(args.warmup):
@@ -184,6 +213,27 @@ def run_reference_arm(args):
     }  # fmt: skip
     print(json.dumps(line), flush=True)
     return 0
+
+
+def reference_cuda_inline():
+    """The reference's own CUDA path (unmodified NVIDIA/warp from baseline/_ref) on this GPU, in this run: C2 build /
+    refit / closest point and C3 rays.  A subprocess, after our timed region, so the two never share the GPU."""
+    ref = os.path.join(ROOT, "baseline", "_ref", "warp_src", "warp", "bin", "warp.so")
+    if not os.path.exists(ref):
+        return "absent (baseline/_ref/warp_src is not on this box)"
+    env = dict(os.environ)
+    env.setdefault("WARP_CACHE_PATH", os.path.join(ROOT, "gpurun_out", "warp_cache"))
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "baseline", "ref_cuda.py"), "timing_c2_c3"], capture_output=True,
+                           text=True, timeout=600, env=env)  # fmt: skip
+    except subprocess.TimeoutExpired:
+        return "timed out after 600 s"
+    for ln in r.stdout.splitlines():
+        if ln.startswith("REF_CUDA "):
+            return json.loads(ln[len("REF_CUDA "):])
+    return f"failed (rc {r.returncode}): {r.stderr[-300:]}"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -218,6 +268,65 @@ def event_ms(core, fn, stream):
     return ms
 
 
+def kernel_timing(core):
+    ms, n = ctypes.c_float(0), ctypes.c_int(0)
+    core.wp_b200_kernel_timing_read(ctypes.byref(ms), ctypes.byref(n))
+    return ms.value, n.value
+
+
+def max_over_ranks(wp, comm, value, dev):
+    if comm is None:
+        return value
+    t = wp.array(np.array([value], np.float32), dtype=wp.float32, device=dev)
+    comm.allreduce_max(t)
+    return float(t.numpy()[0])
+
+
+def parity_sample(wp, P, I, Qh, out, sample=4096, seed=123):
+    """Sampled oracle diff of the TIMED batch (the outputs the timed steps wrote), with a tie counter: queries whose
+    answer has an exact-distance competitor among the faces around the answer's face (where ties live: a closest point
+    on a shared edge or vertex).  Ties are resolved in the reference's visiting order, so they must not show up as
+    mismatches."""
+    import oracle
+
+    rng = np.random.default_rng(seed)
+    sel = np.sort(rng.choice(len(Qh), sample, replace=False))
+    got = {k: getattr(out, k).numpy()[sel] for k in ("result", "face", "u", "v")}
+    tree = oracle.mesh_lbvh_build(P, I, 4)
+    want = oracle.query_point_no_sign(P, I, tree, Qh[sel], MAX_DIST)
+    mism = int(sum((np.asarray(got[k]) != np.asarray(want[k])).sum() for k in ("result", "face", "u", "v")))
+    F = I.reshape(-1, 3)
+    # faces sharing a vertex with the answer's face, via a vertex -> faces table (sorted incidence list)
+    inc_v = F.reshape(-1)
+    order = np.argsort(inc_v, kind="stable")
+    starts = np.searchsorted(inc_v[order], np.arange(len(P) + 1))
+    f32 = np.float32
+
+    def dsq(face, q):
+        a, b, c = P[F[face, 0]], P[F[face, 1]], P[F[face, 2]]
+        bu, bv = oracle.closest_point_to_triangle(a, b, c, q)
+        bu, bv = f32(bu), f32(bv)
+        w = f32(f32(f32(1.0) - bu) - bv)
+        cp = (bu * a + bv * b).astype(f32) + w * c
+        d = (cp - q).astype(f32)
+        return f32(f32(d[0] * d[0] + d[1] * d[1]) + d[2] * d[2])
+
+    ties = 0
+    for k in range(min(sample, 1024)):
+        f = int(want["face"][k])
+        q = Qh[sel[k]]
+        best = dsq(f, q)
+        nb = set()
+        for vtx in F[f]:
+            nb.update((order[starts[vtx]:starts[vtx + 1]] // 3).tolist())
+        nb.discard(f)
+        if any(dsq(g, q) == best for g in nb):
+            ties += 1
+    return {"sample": sample, "mismatches_vs_oracle": mism, "tie_sample": min(sample, 1024), "exact_distance_ties": ties,
+            "note": "oracle = oracle.query_point_no_sign on the oracle's own LBVH of the same mesh; fields result/face/u/v compared "
+                    "bit for bit; ties = sampled queries where a neighbouring face attains the same float32 squared distance"}  # fmt: skip
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -225,8 +334,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--queries", type=int, default=NQ, help="queries per GPU per step (default = config C2)")
-    ap.add_argument("--no-extra", action="store_true", help="skip the build/refit/ray side measurements")
+    ap.add_argument("--no-extra", action="store_true", help="skip the side measurements (build/refit, rays, cloth, C5, reference CUDA)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cloth-frames", type=int, default=1000)
+    ap.add_argument("--skip", default="", help="comma list of side measurements to skip: c3,c4,c5,refcuda,parity")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -243,6 +354,7 @@ def main():
     stream = core.wp_cuda_context_get_stream(None)
     peak_gbs, peak_src = measured_peaks()
     nq = args.queries
+    skip = set(x for x in args.skip.split(",") if x)
 
     # ---- workload (synthetic, generated on the host once) -----------------------------------------
     P, I = mg.noisy_sphere(SUBDIV, 0.02, 1)
@@ -256,19 +368,9 @@ def main():
     first_build_ms = 1e3 * (time.perf_counter() - t0)
     Qh = mg.box_queries(P, nq, seed=2 + rank)
     q_dev = wp.array(Qh, dtype=wp.vec3, device=dev)
-    out = wp.MeshQueryPoint(*(wp.empty(nq, dt, dev) for dt in (wp.uint8, wp.float32, wp.int32, wp.float32, wp.float32)))
     flush = wp.empty(256 << 20, wp.uint8, dev)  # L2 flush buffer (B200 L2 = 126 MB)
     plan = distributed.ShardPlan(nq * world, world)
-    gathered = None
-    if comm is not None:
-        gathered = {"result": wp.empty(plan.padded, wp.uint8, dev), "face": wp.empty(plan.padded, wp.int32, dev),
-                    "u": wp.empty(plan.padded, wp.float32, dev), "v": wp.empty(plan.padded, wp.float32, dev)}  # fmt: skip
-
-    def step():
-        # one launch of k_query_point (+ 4 NCCL all-gathers when sharded)
-        # sharded: the shard is answered in GATHER_PARTS pieces, the gather of a piece runs under the next piece's traversal
-        distributed.sharded_query_point_no_sign(mesh, q_dev, plan, MAX_DIST, comm, rank, local_out=out, global_out=gathered,
-                                                parts=GATHER_PARTS if comm is not None else 1)
+    pipe = distributed.QueryPipeline(mesh, plan, comm, "point_no_sign", MAX_DIST)
 
     def l2_flush():
         core.wp_memset_device(None, ctypes.c_void_p(flush.ptr), 0, flush.nbytes, stream)
@@ -279,34 +381,44 @@ def main():
             comm.barrier()
         core.wp_cuda_context_synchronize(None)
 
-    # ---- timed region: W warm-up steps, then exactly K steps, device-timed, L2 flushed in between -----
-    step_ms = []
+    # ---- timed region: W warm-up steps, then exactly K steps as ONE device-timed region, L2 flushed between steps --
+    # a step = order the batch (k_scene_bounds, k_morton_hist, 3 x k_onesweep_pass) + k_query_point on the compute
+    # stream; at N > 1 its grouped all-gather runs on the communication stream under the next step's traversal
     with ClockSampler(local_rank) as clocks:  # started before the warm-up so nvidia-smi is already sampling when timing starts
         for _ in range(args.warmup):
-            step()
+            pipe.submit(q_dev)
+        pipe.finish()
         barrier()
+        core.wp_b200_kernel_timing_enable(1)
+        kernel_timing(core)
         wall0 = time.perf_counter()
+        e0, e1 = core.wp_cuda_event_create(None, 0), core.wp_cuda_event_create(None, 0)
+        core.wp_cuda_event_record(e0, stream, 0)
+        last = 0
         for _ in range(args.steps):
             l2_flush()
-            step_ms.append(event_ms(core, step, stream))
+            last = pipe.submit(q_dev)
+        pipe.finish()
+        core.wp_cuda_event_record(e1, stream, 0)
+        core.wp_cuda_event_synchronize(e1)
+        total_ms = core.wp_cuda_event_elapsed_time(e0, e1)
         barrier()
         wall_ms = 1e3 * (time.perf_counter() - wall0)
-    total_ms = float(sum(step_ms))
-    if comm is not None:  # max over ranks, on the device
-        tmax = wp.array(np.array([total_ms], np.float32), dtype=wp.float32, device=dev)
-        comm.allreduce_max(tmax)
-        total_ms = float(tmax.numpy()[0])
+        kernel_ms_sum, kernel_launches = kernel_timing(core)
+        core.wp_b200_kernel_timing_enable(0)
+    total_ms = max_over_ranks(wp, comm, total_ms, dev)
     value = nq * world * args.steps / (total_ms * 1e-3)
+    timed_out = pipe.result(last)  # the result set the last timed step produced (global order at N > 1)
+    own = timed_out if comm is None else pipe.local[last % pipe.depth]
+    found = int(own.result.numpy().sum())
 
     # ---- traversal byte accounting (separate counted launch, not timed) -----------------------------
+    scratch_out = pipe.local[(last + 1) % pipe.depth]
     with wp.query_stats() as st:
-        wp.mesh_query_point_no_sign(mesh, q_dev, MAX_DIST, out=out)
+        wp.mesh_query_point_no_sign(mesh, q_dev, MAX_DIST, out=scratch_out)
         core.wp_cuda_context_synchronize(None)
     algo_bytes = nq * (12 + 13) + 64 * st.pair_fetches + 48 * st.tri_fetches
-    kernel_ms = statistics.median(step_ms) if comm is None else None
-    if comm is not None:  # kernel alone, without the gather
-        kernel_ms = statistics.median([event_ms(core, lambda: wp.mesh_query_point_no_sign(mesh, q_dev, MAX_DIST, out=out), stream)
-                                       for _ in range(3)])  # fmt: skip
+    kernel_ms = kernel_ms_sum / max(kernel_launches, 1)  # k_query_point alone, CUDA events on its stream, timed steps only
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
     traffic = None
     try:  # DRAM bytes of this kernel from the committed ncu --set full capture (same workload), scaled to this batch
@@ -317,16 +429,25 @@ def main():
     roofline = {
         "kernel": "k_query_point<no_sign>", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
         "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": kernel_ms,
+        "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": kernel_ms, "launches_timed": kernel_launches,
+        "kernel_share_of_step": kernel_ms_sum / total_ms if comm is None else None,
         "pair_fetches_per_query": st.pair_fetches / nq, "tri_fetches_per_query": st.tri_fetches / nq,
         "nodes_per_s": 2 * st.pair_fetches / (kernel_ms * 1e-3),
         "note": "bytes = 25 B/query I/O + 64 B per sibling-pair fetch + 48 B per packed-triangle fetch (counted); "
                 "SURVEY.md 8(d)'s traversal formula.  The tree (84 MB) and the packed triangles (63 MB) are L1 / L2 resident, "
-                "so these fetches are served on chip: `traffic` (ncu, DRAM read + write of the same launch) is ~15x smaller, and "
-                "`frac` -- fetched bytes against the HBM copy peak -- can exceed 1.  The kernel is issue bound "
-                "(profiles/r01_summary.md: issue slots 70 % busy at 12 of 32 lanes), not bandwidth bound",
+                "so these fetches are served on chip: `traffic` (ncu, DRAM read + write of the same launch, profiles/) is far smaller, "
+                "and `frac` -- fetched bytes against the HBM copy peak -- can exceed 1.  The kernel is issue bound, not bandwidth bound "
+                "(profiles/: issue slots ~70 % busy at ~12 of 32 lanes); `dram_frac` is the DRAM-side fraction",
         "dram_frac": (traffic / (kernel_ms * 1e-3) / 1e9 / peak_gbs) if traffic else None,
     }  # fmt: skip
+
+    # ---- sampled oracle diff of the timed batch (rank 0) --------------------------------------------
+    parity = None
+    if rank == 0 and "parity" not in skip:
+        try:
+            parity = parity_sample(wp, P, I, Qh, own)
+        except Exception as e:  # noqa: BLE001
+            parity = {"error": repr(e)}
 
     # ---- end to end through the public API with pinned host buffers -------------------------------
     hp = Pinned(core, (nq, 3), np.float32)
@@ -339,19 +460,16 @@ def main():
     for _ in range(e2e_steps):
         wp.mesh_query_point_no_sign(mesh, hp.array, MAX_DIST, out=h_out)
     core.wp_cuda_context_synchronize(None)
-    e2e_s = time.perf_counter() - t0
-    if comm is not None:
-        tmax = wp.array(np.array([e2e_s], np.float32), dtype=wp.float32, device=dev)
-        comm.allreduce_max(tmax)
-        e2e_s = float(tmax.numpy()[0])
+    e2e_s = max_over_ranks(wp, comm, time.perf_counter() - t0, dev)
     e2e = {"value": nq * world * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 12 * nq, "d2h_bytes_per_step": 13 * nq,
            "steps": e2e_steps, "api": "warp_b200.mesh_query_point_no_sign(mesh, pinned numpy, ...) -> wp_b200_mesh_query_point_no_sign_host"}  # fmt: skip
-    found = int(h_out.result.sum())
 
-    # ---- side measurements: build / refit (C2) and rays (C3) ---------------------------------------
-    extra = {"triangles": T, "first_build_ms_incl_alloc": first_build_ms, "queries_found": found}
+    # ---- side measurements ---------------------------------------------------------------------------
+    extra = {"triangles": T, "first_build_ms_incl_alloc": first_build_ms, "queries_found": found, "parity": parity}
+    del pipe, timed_out, own, scratch_out
     if not args.no_extra:
-        extra.update(side_measurements(wp, core, mg, dev, stream, mesh, pts, P, I, peak_gbs, rank, comm, world))
+        extra.update(side_measurements(wp, core, mg, dev, stream, mesh, pts, P, I, peak_gbs, rank, comm, world, args, skip))
+    del mesh
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -360,15 +478,20 @@ def main():
         "config": {"workload": WORKLOAD, "triangles": T, "queries_per_gpu": nq, "leaf_size": 4, "max_dist": MAX_DIST,
                    "l2": "256 MB memset between timed steps; query inputs (201 MB) + outputs (218 MB) exceed the 126 MB L2; "
                          "the tree is meant to stay L2-resident",
-                   "gather": ("ncclAllGather of result/face/u/v inside the step" if GATHER_PARTS == 1 else
-                              f"result/face/u/v gathered inside the step, pipelined in {GATHER_PARTS} pieces") if comm else "none (1 GPU)"},
+                   "timing": "the K steps are one CUDA-event region on the compute stream (barrier + synchronize on both sides), max over ranks",
+                   "gather": "one grouped ncclAllGather of result/face/u/v per batch on the communication stream, under the next "
+                             "batch's traversal; the region ends after the last gather" if comm else "none (1 GPU)"},
         "clocks": clocks.summary(), "e2e": e2e,
-        # per step: Morton ordering of the batch (k_scene_bounds, k_morton_hist, 4 x k_onesweep_pass) + k_query_point
-        "gpu_launches": args.steps * 7 * (GATHER_PARTS if comm is not None else 1), "roofline": roofline,
+        # per step: ordering of the batch (k_scene_bounds, k_morton_hist, 3 x k_onesweep_pass) + k_query_point
+        "gpu_launches": args.steps * 6, "roofline": roofline,
         "wall_ms_timed_region": wall_ms, "extra": extra,
     }  # fmt: skip
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(1 << 19)
+        try:
+            extra["c1_cpu"] = cpu_c1()
+        except Exception as e:  # noqa: BLE001
+            extra["c1_cpu"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     barrier()
@@ -377,28 +500,30 @@ def main():
     return 0
 
 
-def side_measurements(wp, core, mg, dev, stream, mesh, pts, P, I, peak_gbs, rank, comm=None, world=1):
-    """LBVH build + refit ms on C2 (with their HBM rooflines) and ray throughput on C3."""
+def side_measurements(wp, core, mg, dev, stream, mesh, pts, P, I, peak_gbs, rank, comm, world, args, skip):
+    """C2 build / refit / signed, C3 rays (+ sharded), C4 cloth loop, C5 (+ sharded), reference CUDA in the same run."""
+    from warp_b200 import distributed, workload
+
     T = len(I) // 3
     out = {}
-    # build: full constructor (allocations + descriptor upload + 8 launches), like timing wp.Mesh(...) on the reference
+    sync = lambda: core.wp_cuda_context_synchronize(None)  # noqa: E731
+    # build: full constructor (allocations + descriptor upload + launches), like timing wp.Mesh(...) on the reference
     idx_d = mesh.indices
     builds = []
     for _ in range(5):
-        core.wp_cuda_context_synchronize(None)
+        sync()
         t0 = time.perf_counter()
         m2 = wp.Mesh(pts, idx_d, bvh_constructor="lbvh")
-        core.wp_cuda_context_synchronize(None)
+        sync()
         builds.append(1e3 * (time.perf_counter() - t0))
         del m2
     out["build_ms_constructor"] = statistics.median(builds)
-    # build kernels only: in-place rebuild of a Bvh over the same triangle boxes shares every kernel but the gather
     # refit: vertices re-noised in place, then mesh.refit()
     P2 = mg.renoise_sphere(P, 0.02, 3)
     refits = []
     for k in range(7):
         pts.assign(P2 if k % 2 == 0 else P)
-        core.wp_cuda_context_synchronize(None)
+        sync()
         refits.append(event_ms(core, mesh.refit, stream))
     pts.assign(P)
     mesh.refit()
@@ -406,11 +531,10 @@ def side_measurements(wp, core, mg, dev, stream, mesh, pts, P, I, peak_gbs, rank
     out["refit_roofline"] = {"bound": "hbm", "algorithmic_bytes": 189 * T, "achieved": 189 * T / (out["refit_ms"] * 1e-3) / 1e9,
                              "peak": peak_gbs, "unit": "GB/s", "frac": 189 * T / (out["refit_ms"] * 1e-3) / 1e9 / peak_gbs}  # fmt: skip
     lib_build = build_kernel_ms(wp, core, stream, mesh)
-    if lib_build is not None:
-        out["build_ms_kernels"] = lib_build
-        out["build_roofline"] = {"bound": "hbm", "algorithmic_bytes": 396 * T, "achieved": 396 * T / (lib_build * 1e-3) / 1e9,
-                                 "peak": peak_gbs, "unit": "GB/s", "frac": 396 * T / (lib_build * 1e-3) / 1e9 / peak_gbs}  # fmt: skip
-    # signed closest point (mesh_query_point: + three axis-probe traversals per query) on 2 M of the C2 queries
+    out["build_ms_kernels"] = lib_build
+    out["build_roofline"] = {"bound": "hbm", "algorithmic_bytes": 396 * T, "achieved": 396 * T / (lib_build * 1e-3) / 1e9,
+                             "peak": peak_gbs, "unit": "GB/s", "frac": 396 * T / (lib_build * 1e-3) / 1e9 / peak_gbs}  # fmt: skip
+    # signed closest point (mesh_query_point: + axis-probe traversals per query) on 2 M of the C2 queries
     try:
         ns = 1 << 21
         qs = wp.array(mg.box_queries(P, ns, seed=2), dtype=wp.vec3, device=dev)
@@ -420,93 +544,220 @@ def side_measurements(wp, core, mg, dev, stream, mesh, pts, P, I, peak_gbs, rank
         ms = statistics.median([event_ms(core, run_s, stream) for _ in range(3)])
         out["signed"] = {"workload": "C2 mesh, 2 097 152 mesh_query_point (signed) queries", "queries_per_s": ns / (ms * 1e-3),
                          "ms": ms, "inside_fraction": float((s_out.sign.numpy() < 0).mean())}  # fmt: skip
-    except Exception as e:
+        del qs, s_out
+    except Exception as e:  # noqa: BLE001
         out["signed"] = {"error": repr(e)}
-    # rays: config C3 (10M-triangle heightfield, 4096 x 4096 primary rays)
-    try:
-        Ph, Ih = mg.heightfield(2237, 4)
-        hm = wp.Mesh(wp.array(Ph, dtype=wp.vec3, device=dev), wp.array(Ih, dtype=wp.int32, device=dev), bvh_constructor="lbvh")
-        S, D = mg.pinhole_rays(4096, 4096)
-        s_d, d_d = wp.array(S, dtype=wp.vec3, device=dev), wp.array(D, dtype=wp.vec3, device=dev)
-        n = S.shape[0]
-        r_out = wp.MeshQueryRay(*(wp.empty(n, dt, dev) for dt in (wp.uint8, wp.float32, wp.int32, wp.float32, wp.float32, wp.float32, wp.vec3)))
-        run = lambda: wp.mesh_query_ray(hm, s_d, d_d, 1.0e6, out=r_out)  # noqa: E731
-        run()
-        ms = statistics.median([event_ms(core, run, stream) for _ in range(3)])
-        with wp.query_stats() as st:
-            run()
-            core.wp_cuda_context_synchronize(None)
-        out["rays"] = {"workload": "C3: 9 999 392-triangle heightfield, 4096x4096 pinhole rays", "rays_per_s": n / (ms * 1e-3),
-                       "ms": ms, "hit_fraction": float(r_out.result.numpy().mean()),
-                       "pair_fetches_per_ray": st.pair_fetches / n, "tri_fetches_per_ray": st.tri_fetches / n,
-                       "bytes_fetched_GBps": (n * (24 + 37) + 64 * st.pair_fetches + 48 * st.tri_fetches) / (ms * 1e-3) / 1e9}  # fmt: skip
-        if comm is not None:
-            # rays at N GPUs (weak scaling): every rank traces its own 4096 x 4096 image of the replicated terrain
-            # (eye shifted per rank) and the seven result fields are all-gathered into global ray order
-            from warp_b200.distributed import ShardPlan, sharded_query_ray
 
-            S2, D2 = mg.pinhole_rays(4096, 4096, eye=(0.5 + 0.02 * rank, -0.6, 0.9))
-            s_d.assign(S2), d_d.assign(D2)
-            plan = ShardPlan(n * world, world)
-            dts = {"result": wp.uint8, "sign": wp.float32, "face": wp.int32, "t": wp.float32, "u": wp.float32,
-                   "v": wp.float32, "normal": wp.vec3}
-            g_out = {k: wp.empty(plan.padded, dt, dev) for k, dt in dts.items()}
-            run_n = lambda: sharded_query_ray(hm, s_d, d_d, plan, 1.0e6, comm, rank, local_out=r_out, global_out=g_out)  # noqa: E731
-            run_n()
-            comm.barrier()
-            core.wp_cuda_context_synchronize(None)
-            ms_n = statistics.median([event_ms(core, run_n, stream) for _ in range(3)])
-            tmax = wp.array(np.array([ms_n], np.float32), dtype=wp.float32, device=dev)
-            comm.allreduce_max(tmax)
-            ms_n = float(tmax.numpy()[0])
-            out["rays_sharded"] = {"workload": "C3 terrain replicated, 4096x4096 rays per GPU, 7 fields all-gathered (NCCL)",
-                                   "n_gpus": world, "rays_per_s": n * world / (ms_n * 1e-3), "ms": ms_n,
-                                   "hits_all_ranks": int(g_out["result"].numpy().sum())}  # fmt: skip
-    except Exception as e:  # the headline must not die on a side measurement
-        out["rays"] = {"error": repr(e)}
-    # collision loop: config C4 (4 M-triangle deforming cloth; per frame = refit() + 8.4 M closest-point queries within 0.05)
-    try:
+    # ---- C3: 10 M-triangle heightfield, 4096 x 4096 primary rays -------------------------------------
+    if "c3" not in skip:
         try:
+            Ph, Ih = mg.heightfield(2237, 4)
+            hm = wp.Mesh(wp.array(Ph, dtype=wp.vec3, device=dev), wp.array(Ih, dtype=wp.int32, device=dev), bvh_constructor="lbvh")
+            S, D = mg.pinhole_rays(4096, 4096, eye=(0.5 + 0.02 * rank, -0.6, 0.9))
+            s_d, d_d = wp.array(S, dtype=wp.vec3, device=dev), wp.array(D, dtype=wp.vec3, device=dev)
+            n = S.shape[0]
+            r_out = wp.MeshQueryRay(*(wp.empty(n, dt, dev) for dt in (wp.uint8, wp.float32, wp.int32, wp.float32, wp.float32, wp.float32, wp.vec3)))
+            run = lambda: wp.mesh_query_ray(hm, s_d, d_d, 1.0e6, out=r_out)  # noqa: E731
+            run()
+            ms = statistics.median([event_ms(core, run, stream) for _ in range(3)])
+            with wp.query_stats() as st:
+                run()
+                sync()
+            out["rays"] = {"workload": "C3: 9 999 392-triangle heightfield, 4096x4096 pinhole rays", "rays_per_s": n / (ms * 1e-3),
+                           "ms": ms, "hit_fraction": float(r_out.result.numpy().mean()),
+                           "pair_fetches_per_ray": st.pair_fetches / n, "tri_fetches_per_ray": st.tri_fetches / n,
+                           "bytes_fetched_GBps": (n * (24 + 37) + 64 * st.pair_fetches + 48 * st.tri_fetches) / (ms * 1e-3) / 1e9}  # fmt: skip
+            out["c3_build_refit"] = build_refit_times(wp, core, stream, hm, 9999392, peak_gbs)
+            if comm is not None:
+                # rays at N GPUs (weak scaling): every rank traces its own 4096 x 4096 image of the replicated terrain (eye
+                # shifted per rank); result / sign / face / t / u / v (21 B per ray) are all-gathered in one grouped launch on
+                # the communication stream under the next image's traversal, the 12-byte normal is recomputed from the face
+                rplan = distributed.ShardPlan(n * world, world)
+                rp = distributed.QueryPipeline(hm, rplan, comm, "ray", 1.0e6)
+                for _ in range(2):
+                    rp.submit(s_d, d_d)
+                rp.finish()
+                comm.barrier()
+                sync()
+                k_steps = 6
+                last = [0]
+
+                def run_n():
+                    for _ in range(k_steps):
+                        last[0] = rp.submit(s_d, d_d)
+                    g = rp.result(last[0])  # incl. the normals of the gathered set
+                    rp.finish()
+                    return g
+
+                ms_n = max_over_ranks(wp, comm, event_ms(core, run_n, stream) / k_steps, dev)
+                g = rp.result(last[0])
+                out["rays_sharded"] = {"workload": "C3 terrain replicated, 4096x4096 rays per GPU per step; result/sign/face/t/u/v gathered "
+                                                   "(grouped NCCL, pipelined over 6 steps), normals recomputed from the gathered faces",
+                                       "n_gpus": world, "rays_per_s": n * world / (ms_n * 1e-3), "ms_per_step": ms_n,
+                                       "nvlink_bytes_received_per_rank_per_step": 21 * n * (world - 1),
+                                       "hits_all_ranks": int(g.result.numpy().sum())}  # fmt: skip
+                del rp, g
             del hm, s_d, d_d, r_out
-        except NameError:
-            pass
-        nc, nqc = 1415, 1 << 23
-        Pc, Ic = mg.cloth(nc, 0)
-        cpts = wp.array(Pc, dtype=wp.vec3, device=dev)
-        cm = wp.Mesh(cpts, wp.array(Ic, dtype=wp.int32, device=dev), bvh_constructor="lbvh")
-        c_out = wp.MeshQueryPoint(*(wp.empty(nqc, dt, dev) for dt in (wp.uint8, wp.float32, wp.int32, wp.float32, wp.float32)))
-        frames, refits, prev = [], [], Pc
-        for f in range(1, 7):
-            Pf, _ = mg.cloth(nc, f)
-            rng = np.random.default_rng(5 + f)
-            Qc = (prev[rng.integers(0, prev.shape[0], nqc)] + rng.normal(0, 0.01, (nqc, 3))).astype(np.float32)
-            qc = wp.array(Qc, dtype=wp.vec3, device=dev)
-            cpts.assign(Pf)  # vertex update (not timed: a simulation writes the positions on the device)
-            core.wp_cuda_context_synchronize(None)
+        except Exception as e:  # the headline must not die on a side measurement
+            out["rays"] = {"error": repr(e)}
 
-            def frame():
-                cm.refit()
-                wp.mesh_query_point_no_sign(cm, qc, 0.05, out=c_out)
+    # ---- C4: cloth loop, one CUDA graph per frame ----------------------------------------------------
+    if "c4" not in skip:
+        try:
+            out["cloth"] = cloth_loop(wp, core, mg, workload, dev, stream, args.cloth_frames, peak_gbs)
+        except Exception as e:  # noqa: BLE001
+            out["cloth"] = {"error": repr(e)}
 
-            frames.append(event_ms(core, frame, stream))
-            refits.append(event_ms(core, cm.refit, stream))
-            prev = Pf
-            del qc
-        out["cloth"] = {"workload": "C4: 3 998 792-triangle cloth, per frame refit() + 8 388 608 mesh_query_point_no_sign within 0.05",
-                        "frame_ms": statistics.median(frames[1:]), "refit_ms": statistics.median(refits[1:]),
-                        "queries_per_s": nqc / (statistics.median(frames[1:]) * 1e-3), "frames": len(frames),
-                        "found_fraction": float(c_out.result.numpy().mean())}  # fmt: skip
-    except Exception as e:
-        out["cloth"] = {"error": repr(e)}
+    # ---- C5: 100 M-triangle mesh replicated, device-generated query shards, NCCL gather ---------------
+    if "c5" not in skip:
+        try:
+            out["c5"] = c5_leg(wp, core, mg, workload, distributed, dev, stream, peak_gbs, rank, comm, world)
+        except Exception as e:  # noqa: BLE001
+            out["c5"] = {"error": repr(e)}
+
+    # ---- the reference's CUDA path on this GPU, in this run ------------------------------------------
+    if rank == 0 and world == 1 and "refcuda" not in skip:
+        sync()
+        out["reference_cuda"] = reference_cuda_inline()
     return out
 
 
+def build_refit_times(wp, core, stream, mesh, T, peak_gbs):
+    b = build_kernel_ms(wp, core, stream, mesh)
+    mesh.refit()
+    core.wp_cuda_context_synchronize(None)
+    r = statistics.median([event_ms(core, mesh.refit, stream) for _ in range(5)])
+    return {"triangles": T, "build_ms_kernels": b, "build_frac_of_hbm_roofline": 396 * T / (b * 1e-3) / 1e9 / peak_gbs,
+            "refit_ms": r, "refit_frac_of_hbm_roofline": 189 * T / (r * 1e-3) / 1e9 / peak_gbs}  # fmt: skip
+
+
+def cloth_loop(wp, core, mg, workload, dev, stream, frames, peak_gbs):
+    """Config C4: 1415 x 1415 cloth (3 998 792 triangles); per frame the vertices move on the device, 8 388 608 query
+    points (previous frame's vertices + N(0, 0.01)) are generated on the device, then refit() + mesh_query_point_no_sign
+    within 0.05.  The whole frame is ONE CUDA graph, launched `frames` times; every frame is timed with events."""
+    nc, nqc = 1415, 1 << 23
+    _, Ic = mg.cloth(nc, 0)
+    cf = workload.ClothFrames(nc, dev)
+    cm = wp.Mesh(cf.points, wp.array(Ic, dtype=wp.int32, device=dev), bvh_constructor="lbvh")
+    qc = wp.empty(nqc, wp.vec3, dev)
+    c_out = wp.MeshQueryPoint(*(wp.empty(nqc, dt, dev) for dt in (wp.uint8, wp.float32, wp.int32, wp.float32, wp.float32)))
+
+    def frame():
+        cf.advance(1)
+        cf.update_points()
+        cf.queries(qc, 0.01)
+        cm.refit()
+        wp.mesh_query_point_no_sign(cm, qc, 0.05, out=c_out)
+
+    frame()  # warm-up outside the graph: refit plan, ordering scratch
+    core.wp_cuda_context_synchronize(None)
+    with wp.ScopedCapture(dev) as cap:
+        frame()
+    gstream = cap.stream.cuda_stream if cap.stream is not None else stream
+    evs = [core.wp_cuda_event_create(None, 0) for _ in range(frames + 1)]
+    with wp.ScopedStream(cap.stream) if cap.stream is not None else _Null():
+        core.wp_cuda_event_record(evs[0], gstream, 0)
+        for f in range(frames):
+            wp.capture_launch(cap.graph)
+            core.wp_cuda_event_record(evs[f + 1], gstream, 0)
+        core.wp_cuda_event_synchronize(evs[-1])
+    ms = [core.wp_cuda_event_elapsed_time(evs[f], evs[f + 1]) for f in range(frames)]
+    for e in evs:
+        core.wp_cuda_event_destroy(e)
+    refit_ms = statistics.median([event_ms(core, cm.refit, stream) for _ in range(5)])
+    T = len(Ic) // 3
+    return {"workload": "C4: 3 998 792-triangle cloth; per frame: device-side vertex update + 8 388 608 device-generated queries + refit() + "
+                        "mesh_query_point_no_sign within 0.05, one CUDA graph launch per frame",
+            "frames": frames, "frame_ms_mean": statistics.fmean(ms), "frame_ms_median": statistics.median(ms),
+            "frame_ms_first_100_mean": statistics.fmean(ms[:100]), "frame_ms_last_100_mean": statistics.fmean(ms[-100:]),
+            "frame_ms_min": min(ms), "frame_ms_max": max(ms), "queries_per_s": nqc / (statistics.median(ms) * 1e-3),
+            "refit_ms": refit_ms, "refit_frac_of_hbm_roofline": 189 * T / (refit_ms * 1e-3) / 1e9 / peak_gbs,
+            "found_fraction": float(c_out.result.numpy().mean())}  # fmt: skip
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def c5_leg(wp, core, mg, workload, distributed, dev, stream, peak_gbs, rank, comm, world):
+    """Config C5: 7072 x 7072 heightfield (99 998 082 triangles) replicated on every GPU; query shards generated ON THE
+    DEVICE from a counter RNG of the global query index (seed 6), uniform in the AABB x 1.2; 16 777 216 queries per GPU
+    per step, grouped NCCL gather pipelined under the next step.  The 1 B-query job is 1e9 / (16.8 M x N) such steps."""
+    sync = lambda: core.wp_cuda_context_synchronize(None)  # noqa: E731
+    t0 = time.perf_counter()
+    P5, I5 = mg.heightfield(7072, 4)
+    gen_s = time.perf_counter() - t0
+    T = len(I5) // 3
+    lo, hi = P5.min(0).astype(np.float64), P5.max(0).astype(np.float64)
+    c, h = 0.5 * (lo + hi), 0.6 * (hi - lo)
+    p5, i5 = wp.array(P5, dtype=wp.vec3, device=dev), wp.array(I5, dtype=wp.int32, device=dev)
+    del P5, I5
+    nq = 1 << 24
+    plan = distributed.ShardPlan(nq * world, world)
+    q = wp.empty(nq, wp.vec3, dev)
+    res = {"workload": "C5: 99 998 082-triangle heightfield replicated per GPU; 16 777 216 device-generated queries per GPU per step "
+                       "(counter RNG of the global index, seed 6, AABB x 1.2), mesh_query_point_no_sign, grouped NCCL gather",
+           "n_gpus": world, "triangles": T, "host_mesh_generation_s": gen_s, "queries_per_gpu_per_step": nq}  # fmt: skip
+    for bits in (30, 63):
+        sync()
+        t0 = time.perf_counter()
+        m = wp.Mesh(p5, i5, morton_bits=bits)
+        sync()
+        ctor_ms = 1e3 * (time.perf_counter() - t0)
+        br = build_refit_times(wp, core, stream, m, T, peak_gbs)
+        pipe = distributed.QueryPipeline(m, plan, comm, "point_no_sign", MAX_DIST)
+        step = [0]
+
+        def submit():
+            workload.box_queries(q, (step[0] * world + rank) * nq, 6, c - h, c + h)  # this step's shard of the global stream
+            step[0] += 1
+            return pipe.submit(q)
+
+        submit()
+        pipe.finish()
+        if comm is not None:
+            comm.barrier()
+        sync()
+        k_steps = 2 if bits == 30 else 3
+        core.wp_b200_kernel_timing_enable(1)
+        kernel_timing(core)
+
+        def run():
+            for _ in range(k_steps):
+                submit()
+            pipe.finish()
+
+        ms = max_over_ranks(wp, comm, event_ms(core, run, stream) / k_steps, dev)
+        kms, kl = kernel_timing(core)
+        core.wp_b200_kernel_timing_enable(0)
+        ns = 1 << 20
+        with wp.query_stats() as st:
+            wp.mesh_query_point_no_sign(m, wp.array(ptr=q.ptr, dtype=wp.vec3, shape=ns, device=dev), MAX_DIST)
+            sync()
+        own = pipe.local[(step[0] - 1) % pipe.depth]
+        r = {"constructor_ms_first": ctor_ms, **br, "queries_per_s": nq * world / (ms * 1e-3), "ms_per_step": ms,
+             "kernel_ms_per_launch": kms / max(kl, 1), "steps_timed": k_steps,
+             "pair_fetches_per_query": st.pair_fetches / ns, "tri_fetches_per_query": st.tri_fetches / ns,
+             "pair_fetches_per_s": st.pair_fetches / ns * nq / (kms / max(kl, 1) * 1e-3),
+             "tri_fetches_per_s": st.tri_fetches / ns * nq / (kms / max(kl, 1) * 1e-3),
+             "bytes_fetched_GBps": (nq * 25 + (64 * st.pair_fetches + 48 * st.tri_fetches) / ns * nq) / (kms / max(kl, 1) * 1e-3) / 1e9,
+             "found_fraction": float(own.result.numpy().mean()),
+             "seconds_for_1e9_queries_at_this_rate": 1e9 / (nq * world / (ms * 1e-3))}  # fmt: skip
+        res["parity_tree_morton30" if bits == 30 else "morton63"] = r
+        del pipe, m, own
+    res["note"] = ("a C5 query visits ~10x the sibling pairs and ~60-130x the triangles of a C2 query (queries far from a finely tessellated "
+                   "surface must open every box nearer than the answer), so the rate is bound by triangle tests per second, the same "
+                   "figure as on C2; the 30-bit parity tree additionally has ~100-triangle depth-rule leaves (bvh.cu:419-441)")
+    return res
+
+
 def build_kernel_ms(wp, core, stream, mesh):
-    """Device time of the build kernels alone (no allocation): wp_b200_mesh_rebuild_device if exported."""
-    fn = getattr(core, "wp_b200_mesh_rebuild_device", None)
-    if fn is None:
-        return None
-    fn.restype, fn.argtypes = ctypes.c_int, [ctypes.c_uint64]
+    """Device time of the build kernels alone (no allocation): in-place rebuild."""
+    fn = core.wp_b200_mesh_rebuild_device
     fn(mesh.id)
     core.wp_cuda_context_synchronize(None)
     return statistics.median([event_ms(core, lambda: fn(mesh.id), stream) for _ in range(7)])

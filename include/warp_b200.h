@@ -248,6 +248,10 @@ WP_B200_API int wp_b200_get_ray_order(void);
  * query also counts 64-byte sibling-pair fetches and 48-byte triangle fetches (slower, used for the
  * bytes-fetched / nodes-per-second report); read them back with wp_b200_query_stats_read. */
 WP_B200_API void wp_b200_query_stats_enable(int enable);
+/* live timing of the point / ray traversal kernel alone (CUDA events on the launch stream around the kernel, not the
+ * batch ordering before it): enable, run, read the summed launch durations and the launch count since the last read */
+WP_B200_API void wp_b200_kernel_timing_enable(int enable);
+WP_B200_API void wp_b200_kernel_timing_read(float* total_ms, int* launches);
 WP_B200_API void wp_b200_query_stats_read(unsigned long long* pair_fetches, unsigned long long* tri_fetches);
 
 /* wp.mesh_query_aabb (mesh.h:2476-2712): faces whose AABB (as of the last build / refit) overlaps the query box, in

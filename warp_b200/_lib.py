@@ -115,6 +115,8 @@ SIGNATURES = {
     "wp_b200_get_query_order": (_i, []),
     "wp_b200_set_ray_order": (None, [_i]),
     "wp_b200_get_ray_order": (_i, []),
+    "wp_b200_kernel_timing_enable": (None, [_i]),
+    "wp_b200_kernel_timing_read": (None, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
     "wp_b200_query_stats_enable": (None, [_i]),
     "wp_b200_query_stats_read": (None, [ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]),
     "wp_b200_bvh_query_aabb_count": (_i, [_u64, _vp, _vp, _vp, _i64, _vp]),

@@ -13,6 +13,7 @@
 #include <map>
 #include <mutex>
 #include <utility>
+#include <vector>
 
 static_assert(sizeof(wp_array_t) == 56, "wp::array_t layout (warp/native/array.h:173-277)");
 static_assert(sizeof(wp_b200_bvh_desc) == 112, "wp::BVH layout (warp/native/bvh.h:176-207)");
@@ -270,6 +271,51 @@ unsigned long long* stats_buffer()
     cudaMemsetAsync(g_stats_dev, 0, 2 * sizeof(unsigned long long), current_stream(current_device()));
     return g_stats_dev;
 }
+
+// ---- live kernel timing (bench.py roofline): CUDA events around the traversal kernel itself, on the stream it is
+// launched on, accumulated until read.  Off by default; skipped while the stream is being captured.
+struct KernelTimer {
+    bool enabled = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    std::vector<cudaEvent_t> pool;
+};
+KernelTimer g_ktimer;
+
+cudaEvent_t ktimer_event()
+{
+    if (!g_ktimer.pool.empty()) {
+        cudaEvent_t e = g_ktimer.pool.back();
+        g_ktimer.pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct KernelTimerScope {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaStream_t st;
+    explicit KernelTimerScope(cudaStream_t stream) : st(stream)
+    {
+        if (!g_ktimer.enabled)
+            return;
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (stream && cudaStreamIsCapturing(stream, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone)
+            return;
+        std::lock_guard<std::mutex> g(g_lock);
+        a = ktimer_event(), b = ktimer_event();
+        cudaEventRecord(a, st);
+    }
+    ~KernelTimerScope()
+    {
+        if (!a)
+            return;
+        cudaEventRecord(b, st);
+        std::lock_guard<std::mutex> g(g_lock);
+        g_ktimer.pending.emplace_back(a, b);
+    }
+};
 
 MeshState* query_mesh(uint64_t id)
 {
@@ -897,6 +943,41 @@ void wp_b200_set_ray_order(int mode) { g_ray_order = mode ? 1 : 0; }
 int wp_b200_get_ray_order(void) { return g_ray_order; }
 int wp_b200_get_query_order(void) { return g_query_order; }
 
+// kernel timing of the point / ray traversal kernels (see KernelTimerScope): enable, run, read = (sum of the launch
+// durations in ms, number of launches) since the last read; reading waits for the timed launches to finish
+void wp_b200_kernel_timing_enable(int enable)
+{
+    std::lock_guard<std::mutex> g(g_lock);
+    g_ktimer.enabled = enable != 0;
+}
+
+void wp_b200_kernel_timing_read(float* total_ms, int* launches)
+{
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> todo;
+    {
+        std::lock_guard<std::mutex> g(g_lock);
+        todo.swap(g_ktimer.pending);
+    }
+    float sum = 0.f;
+    int count = 0;
+    for (auto& ev : todo) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(ev.second) == cudaSuccess && cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess)
+            sum += ms, ++count;
+        else
+            cudaGetLastError();
+    }
+    {
+        std::lock_guard<std::mutex> g(g_lock);
+        for (auto& ev : todo)
+            g_ktimer.pool.push_back(ev.first), g_ktimer.pool.push_back(ev.second);
+    }
+    if (total_ms)
+        *total_ms = sum;
+    if (launches)
+        *launches = count;
+}
+
 void wp_b200_query_stats_read(unsigned long long* pair_fetches, unsigned long long* tri_fetches)
 {
     unsigned long long h[2] = { 0, 0 };
@@ -942,8 +1023,12 @@ static int query_point_on(MeshState* m, const float* points, int64_t n, float ma
         }
         perm = ws.idx;
     }
-    const char* err = wb_query_point(make_view(m->bvh), points, perm, n, max_dist, with_sign, result, sign, face, u, v,
-                                     stats_buffer(), st);
+    const char* err;
+    {
+        KernelTimerScope timed(st);
+        err = wb_query_point(make_view(m->bvh), points, perm, n, max_dist, with_sign, result, sign, face, u, v,
+                             stats_buffer(), st);
+    }
     if (err) {
         set_error("Warp error: mesh point query failed: %s", err);
         return 0;
@@ -974,8 +1059,12 @@ static int query_ray_on(MeshState* m, const float* starts, const float* dirs, in
         }
         perm = ws.idx;
     }
-    const char* err = wb_query_ray(make_view(m->bvh), starts, dirs, perm, roots, n, max_t, result, sign, face, t, u, v, normal,
-                                   stats_buffer(), st);
+    const char* err;
+    {
+        KernelTimerScope timed(st);
+        err = wb_query_ray(make_view(m->bvh), starts, dirs, perm, roots, n, max_t, result, sign, face, t, u, v, normal,
+                           stats_buffer(), st);
+    }
     if (err) {
         set_error("Warp error: mesh ray query failed: %s", err);
         return 0;

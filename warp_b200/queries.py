@@ -79,20 +79,45 @@ def _check(ok, what):
         raise RuntimeError(f"{what} failed: {_lib.error_string()}")
 
 
+_OUT_DTYPES = {"result": uint8, "sign": float32, "face": int32, "t": float32, "u": float32, "v": float32, "normal": vec3}
+
+
+def _check_out(out, n, dev, fields):
+    """A caller-supplied ``out`` is written by the kernel without further checks: refuse short, mistyped or
+    wrong-device buffers here instead of corrupting device memory."""
+    for f in fields:
+        a = getattr(out, f)
+        if isinstance(a, array):
+            if a.device != dev:
+                raise RuntimeError(f"out.{f} lives on {a.device}, the mesh on {dev}")
+            if a.dtype != _OUT_DTYPES[f] or len(a) < n:
+                raise RuntimeError(f"out.{f} must be an array of at least {n} {_OUT_DTYPES[f]} entries, got {a}")
+        else:
+            want = _OUT_DTYPES[f].np_dtype
+            shape_ok = a.shape[0] >= n and (a.ndim == 2 and a.shape[1] == 3 if f == "normal" else a.ndim == 1)
+            if a.dtype != want or not shape_ok or not a.flags["C_CONTIGUOUS"]:
+                raise RuntimeError(f"out.{f} must be a contiguous numpy array of at least {n} {want} entries")
+
+
 def _point_query(mesh, points, max_dist, with_sign, out):
     id_, dev = _mesh_id(mesh)
     c = _lib.core()
     if isinstance(points, array):
         pts = _dev_vec3(points, "points")
+        if pts.device != dev:
+            raise RuntimeError(f"points live on {pts.device}, the mesh on {dev}")
         n = len(pts)
         if out is None:
-            out = MeshQueryPoint(empty(n, uint8, dev), empty(n, float32, dev), empty(n, int32, dev),
-                                 empty(n, float32, dev), empty(n, float32, dev))  # fmt: skip
+            # `sign` of the unsigned query is 0 (mesh.h:1602-1608): zeroed once here; a caller-supplied `out` keeps
+            # whatever its sign array holds (no 4-byte-per-query memset on the per-step path)
+            out = MeshQueryPoint(empty(n, uint8, dev), empty(n, float32, dev) if with_sign else zeros(n, float32, dev),
+                                 empty(n, int32, dev), empty(n, float32, dev), empty(n, float32, dev))  # fmt: skip
+        else:
+            _check_out(out, n, dev, ("result", "face", "u", "v") + (("sign",) if with_sign else ()))
         if with_sign:
             ok = c.wp_b200_mesh_query_point(id_, _p(pts), n, max_dist, _p(out.result), _p(out.sign), _p(out.face),
                                             _p(out.u), _p(out.v))  # fmt: skip
         else:
-            out.sign.zero_()
             ok = c.wp_b200_mesh_query_point_no_sign(id_, _p(pts), n, max_dist, _p(out.result), _p(out.face),
                                                     _p(out.u), _p(out.v))  # fmt: skip
         _check(ok, "mesh_query_point")
@@ -102,6 +127,8 @@ def _point_query(mesh, points, max_dist, with_sign, out):
     if out is None:
         out = MeshQueryPoint(np.zeros(n, np.uint8), np.zeros(n, np.float32), np.zeros(n, np.int32),
                              np.zeros(n, np.float32), np.zeros(n, np.float32))  # fmt: skip
+    else:
+        _check_out(out, n, dev, ("result", "face", "u", "v") + (("sign",) if with_sign else ()))
     if with_sign:
         ok = c.wp_b200_mesh_query_point_host(id_, _p(pts), n, max_dist, _p(out.result), _p(out.sign), _p(out.face),
                                              _p(out.u), _p(out.v))  # fmt: skip
@@ -135,10 +162,14 @@ def mesh_query_ray(mesh, starts, dirs, max_t: float, out: MeshQueryRay | None = 
         if len(s) != len(d):
             raise RuntimeError("starts and dirs must have the same length")
         n = len(s)
+        if s.device != dev or d.device != dev:
+            raise RuntimeError(f"starts / dirs live on {s.device} / {d.device}, the mesh on {dev}")
         if out is None:
             out = MeshQueryRay(empty(n, uint8, dev), empty(n, float32, dev), empty(n, int32, dev),
                                empty(n, float32, dev), empty(n, float32, dev), empty(n, float32, dev),
                                empty(n, vec3, dev))  # fmt: skip
+        else:
+            _check_out(out, n, dev, MeshQueryRay.__slots__)
         r = _roots(roots, n, dev)
         ok = c.wp_b200_mesh_query_ray(id_, _p(s), _p(d), n, max_t, _p(out.result), _p(out.sign), _p(out.face),
                                       _p(out.t), _p(out.u), _p(out.v), _p(out.normal), _p(r) if r is not None else None)  # fmt: skip
@@ -154,6 +185,8 @@ def mesh_query_ray(mesh, starts, dirs, max_t: float, out: MeshQueryRay | None = 
         out = MeshQueryRay(np.zeros(n, np.uint8), np.zeros(n, np.float32), np.zeros(n, np.int32),
                            np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32),
                            np.zeros((n, 3), np.float32))  # fmt: skip
+    else:
+        _check_out(out, n, dev, MeshQueryRay.__slots__)
     ok = c.wp_b200_mesh_query_ray_host(id_, _p(s), _p(d), n, max_t, _p(out.result), _p(out.sign), _p(out.face),
                                        _p(out.t), _p(out.u), _p(out.v), _p(out.normal))  # fmt: skip
     _check(ok, "mesh_query_ray")
