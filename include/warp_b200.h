@@ -329,6 +329,9 @@ WP_B200_API int wp_b200_bvh_get_option(uint64_t id, const char* name, int* value
  * afterwards keeps the reference-layout mirror of its descriptor (node_lowers / node_uppers / node_parents / root,
  * Mesh::lowers / uppers, average_edge_length) current after create / refit / rebuild / set_points, so unmodified Warp
  * kernels can traverse through `id`.  Off by default (the mirror costs one extra pass per refit). */
+/* switches of measured-and-rejected alternatives kept as tested code paths: "small_nodes" = 1 / 0 / -1 (environment
+ * default) -- the builder's Karras-style pass over small distinct-key nodes.  1 ok / 0 unknown */
+WP_B200_API int wp_b200_set_experiment(const char* name, int value);
 WP_B200_API void wp_b200_set_auto_reference_layout(int enable);
 WP_B200_API int wp_b200_get_auto_reference_layout(void);
 

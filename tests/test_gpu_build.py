@@ -495,3 +495,45 @@ def test_refit_wavefront_at_the_sort_tile_switch(wp, oracle_mod, n):
             assert np.array_equal(got[2][name]["ib"], want[name]["ib"])
             for f in "xyz":
                 assert np.array_equal(got[2][name][f][vis], want[name][f][vis]), (name, f)
+
+
+def test_small_node_pass_builds_the_same_tree(wp, oracle_mod):
+    """The Karras-style small-node pass (k_small_nodes: ranges of small distinct-key nodes found independently from the
+    sorted keys; off by default) followed by the merge from the finished subtrees gives the oracle's
+    tree on all 2N - 1 nodes: mesh with distinct keys, mesh full of equal-key pairs, 63-bit keys, groups, leaf sizes."""
+    from warp_b200 import _lib
+
+    core = _lib.core()
+    assert core.wp_b200_set_experiment(b"small_nodes", 1)
+    try:
+        P, I = mg.noisy_sphere(6, 0.02, 3)
+        for leaf in (1, 4, 8):
+            m = wp.Mesh(wp.array(P, dtype=wp.vec3), wp.array(I, dtype=wp.int32), bvh_leaf_size=leaf)
+            assert_tree_equal(m.download_tree(), oracle_mod.mesh_lbvh_build(P, I, leaf))
+        Ph, Ih = mg.heightfield(300, 4)  # equal-key pairs everywhere (the two triangles of a quad)
+        for bits in (30, 63):
+            m = wp.Mesh(wp.array(Ph, dtype=wp.vec3), wp.array(Ih, dtype=wp.int32), morton_bits=bits)
+            assert_tree_equal(m.download_tree(), oracle_mod.mesh_lbvh_build(Ph, Ih, 4, morton_bits=bits))
+        for n in (65, 1023, 1024, 1025, 2049, 5000):
+            lo, hi = random_boxes(n, seed=n)
+            groups = (np.arange(n) % 7).astype(np.int32)
+            b = wp.Bvh(wp.array(lo, dtype=wp.vec3), wp.array(hi, dtype=wp.vec3), leaf_size=2)
+            assert_tree_equal(b.download_tree(), oracle_mod.lbvh_build(lo, hi, 2))
+            g = wp.Bvh(wp.array(lo, dtype=wp.vec3), wp.array(hi, dtype=wp.vec3), leaf_size=2, groups=wp.array(groups, dtype=wp.int32))
+            assert_tree_equal(g.download_tree(), oracle_mod.lbvh_build(lo, hi, 2, groups=groups))
+            # refit after the build (atomic and wavefront): visible boxes
+            d = np.float32(0.25)
+            lo2, hi2 = (lo + d).astype(np.float32), (hi + d).astype(np.float32)
+            want = oracle_mod.lbvh_build(lo, hi, 2)
+            oracle_mod.lbvh_refit(want, lo2, hi2)
+            b.lowers.assign(lo2), b.uppers.assign(hi2)
+            for mode in (1, 2):
+                b.set_option("refit_mode", mode)
+                b.refit()
+                got = b.download_tree()
+                vis = visible_nodes(want)
+                for name in ("node_lowers", "node_uppers"):
+                    for f in "xyz":
+                        assert np.array_equal(got[name][f][vis], want[name][f][vis]), (n, mode, name, f)
+    finally:
+        core.wp_b200_set_experiment(b"small_nodes", -1)

@@ -79,8 +79,18 @@ def test_c5_full_size_tree_refit_and_queries(wp, oracle_mod):
     off = d30 != d63
     print(f"C5: closest distance differs in the last bits for {int(off.sum())} of {nq} queries between the two trees")
     assert off.sum() <= nq // 200 and np.allclose(d30, d63, rtol=1e-5, atol=0), f"{off.sum()} queries with a different closest distance"
-    ties = int((ours30b["face"] != ours63["face"]).sum())
-    print(f"C5: {ties} of {nq} sampled queries resolve an exact distance tie differently on the 63-bit tree")
-    assert ties <= nq // 50
-    same = (ours30b["face"] == ours63["face"]) & ~off
+    # ties are the rule on this mesh, not the exception: the closest point of a far-away query is usually a grid vertex,
+    # which six triangles share (measured: ~52 % of the sample) -- where the faces differ the closest POINT must not
+    diff = ours30b["face"] != ours63["face"]
+    print(f"C5: {int(diff.sum())} of {nq} sampled queries resolve an exact distance tie differently on the 63-bit tree")
+
+    def closest(a):
+        tri = P2[I.reshape(-1, 3)[a["face"]]].astype(np.float64)
+        u, v = a["u"].astype(np.float64)[:, None], a["v"].astype(np.float64)[:, None]
+        return u * tri[:, 0] + v * tri[:, 1] + (1 - u - v) * tri[:, 2]
+
+    # (two different points can sit at float-equal distances: the handful of last-bit cases above, and rarely others)
+    err = np.abs(closest(ours30b) - closest(ours63)).max(axis=1)
+    assert (err[~off] < 1e-5).mean() > 0.999 and err.max() < 2e-3, (float((err[~off] < 1e-5).mean()), float(err.max()))
+    same = ~diff & ~off
     assert np.array_equal(ours30b["u"][same], ours63["u"][same]) and np.array_equal(ours30b["v"][same], ours63["v"][same])

@@ -28,6 +28,9 @@ std::map<uint64_t, BvhState*> g_bvhs;
 std::map<uint64_t, MeshState*> g_meshes;
 cudaStream_t g_stream[64] = {};  // current stream per device (0 = legacy default stream)
 
+#ifndef WB_L2_PERSIST_DEFAULT
+#define WB_L2_PERSIST_DEFAULT 0
+#endif
 thread_local bool t_stats_enabled = false;
 // Process-wide DEFAULTS, copied into every tree when it is created (BvhState::morton_bits / query_order / ray_order /
 // refit_mode); changing them later never touches an existing object -- wp_b200_bvh_set_option does that, per object.
@@ -314,6 +317,80 @@ struct KernelTimerScope {
         cudaEventRecord(b, st);
         std::lock_guard<std::mutex> g(g_lock);
         g_ktimer.pending.emplace_back(a, b);
+    }
+};
+
+// memory-side variant of the unsigned closest-point kernel (query.cu QM_* bits); WARP_B200_QMODE overrides the default
+#ifndef WB_QMODE_DEFAULT
+#define WB_QMODE_DEFAULT 6  // QM_STREAM | QM_PACKED: measured best on C2 / C4 (scripts/qmode_ab.py)
+#endif
+int query_mode()
+{
+    static const int mode = [] {
+        const char* e = getenv("WARP_B200_QMODE");
+        return e ? atoi(e) : WB_QMODE_DEFAULT;
+    }();
+    return mode;
+}
+
+// L2 residency of the tree (BASELINE north_star: "node layout kept L2-resident"): while a traversal kernel runs, the
+// sibling-pair array is covered by a PERSISTING access-policy window on the launch stream, sized to the device's
+// persisting-L2 carve-out (hit ratio = carve-out / array size when the array is larger), everything else on the stream
+// being streaming-class traffic.  WARP_B200_L2_PERSIST=0 turns it off (A/B).
+struct L2PersistScope {
+    cudaStream_t st;
+    bool active = false;
+    static int enabled()
+    {
+        static const int on = [] {
+            const char* e = getenv("WARP_B200_L2_PERSIST");
+            return e ? atoi(e) : WB_L2_PERSIST_DEFAULT;
+        }();
+        return on;
+    }
+    L2PersistScope(const BvhState& s, cudaStream_t stream) : st(stream)
+    {
+        if (!enabled() || s.n < 2)
+            return;
+        static size_t carve[64] = {};
+        static int max_window[64] = {};
+        const int d = s.device;
+        if (d < 0 || d >= 64)
+            return;
+        if (!max_window[d]) {
+            int persist_max = 0, win = 0;
+            cudaDeviceGetAttribute(&persist_max, cudaDevAttrMaxPersistingL2CacheSize, d);
+            cudaDeviceGetAttribute(&win, cudaDevAttrMaxAccessPolicyWindowSize, d);
+            if (persist_max <= 0 || win <= 0) {
+                max_window[d] = -1;
+                return;
+            }
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist_max);
+            carve[d] = (size_t)persist_max, max_window[d] = win;
+        }
+        if (max_window[d] < 0)
+            return;
+        const size_t bytes = sizeof(NodeRec) * 2 * (size_t)(s.n - 1);
+        cudaStreamAttrValue v;
+        memset(&v, 0, sizeof(v));
+        v.accessPolicyWindow.base_ptr = (void*)s.pairs;
+        v.accessPolicyWindow.num_bytes = bytes < (size_t)max_window[d] ? bytes : (size_t)max_window[d];
+        const double ratio = (double)carve[d] / (double)v.accessPolicyWindow.num_bytes;
+        v.accessPolicyWindow.hitRatio = ratio >= 1.0 ? 1.0f : (float)ratio;
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        active = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) == cudaSuccess;
+        if (!active)
+            cudaGetLastError();
+    }
+    ~L2PersistScope()
+    {
+        if (!active)
+            return;
+        cudaStreamAttrValue v;
+        memset(&v, 0, sizeof(v));
+        v.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
     }
 };
 
@@ -820,6 +897,18 @@ int wp_mesh_refit_device(uint64_t id)
 
 void wp_b200_set_refit_mode(int mode) { g_wb_refit_mode = (mode == 1 || mode == 2) ? mode : 0; }
 int wp_b200_get_refit_mode(void) { return g_wb_refit_mode; }
+// process-wide switches of measured-and-rejected alternatives that stay in the library as tested code paths:
+// "small_nodes" (builder: Karras-style pass for small distinct-key nodes before the merge; -1 = environment default)
+int wp_b200_set_experiment(const char* name, int value)
+{
+    if (name && !strcmp(name, "small_nodes")) {
+        g_wb_small_nodes = value < 0 ? -1 : (value ? 1 : 0);
+        return 1;
+    }
+    set_error("Warp error: unknown experiment %s", name ? name : "(null)");
+    return 0;
+}
+
 void wp_b200_set_auto_reference_layout(int enable) { g_auto_reference_layout = enable ? 1 : 0; }
 int wp_b200_get_auto_reference_layout(void) { return g_auto_reference_layout; }
 
@@ -1010,6 +1099,8 @@ static int query_point_on(MeshState* m, const float* points, int64_t n, float ma
     if (m->bvh.n == 0)
         return zero_point_outputs(n, result, sign, face, u, v, st);
     const int* perm = nullptr;
+    uint4* packed = nullptr;
+    float* sorted_pts = nullptr;
     const int order = m->bvh.query_order >= 0 ? m->bvh.query_order : g_query_order;
     if ((order == 1 || (order == 2 && n >= 32768)) && n < (1ll << 30)) {
         OrderScratch& ws = order_scratch(m->bvh.device, st);
@@ -1021,13 +1112,14 @@ static int query_point_on(MeshState* m, const float* points, int64_t n, float ma
             set_error("Warp error: query ordering failed: %s", oerr);
             return 0;
         }
-        perm = ws.idx;
+        perm = ws.idx, packed = ws.packed, sorted_pts = ws.sorted_pts;
     }
     const char* err;
     {
         KernelTimerScope timed(st);
+        L2PersistScope l2(m->bvh, st);
         err = wb_query_point(make_view(m->bvh), points, perm, n, max_dist, with_sign, result, sign, face, u, v,
-                             stats_buffer(), st);
+                             stats_buffer(), st, query_mode(), packed, sorted_pts);
     }
     if (err) {
         set_error("Warp error: mesh point query failed: %s", err);
@@ -1062,6 +1154,7 @@ static int query_ray_on(MeshState* m, const float* starts, const float* dirs, in
     const char* err;
     {
         KernelTimerScope timed(st);
+        L2PersistScope l2(m->bvh, st);
         err = wb_query_ray(make_view(m->bvh), starts, dirs, perm, roots, n, max_t, result, sign, face, t, u, v, normal,
                            stats_buffer(), st);
     }

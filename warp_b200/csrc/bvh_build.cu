@@ -539,6 +539,155 @@ k_leaves(Src src, int n, const KeyT* __restrict__ keys, const int* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// K4b: small nodes, Karras style -- one thread per split position, no atomics, no dependency chain.
+// The reference LBVH is the Cartesian tree of the key deltas (common-prefix lengths of neighbouring sorted keys,
+// bvh.cu:218-226) wherever keys are distinct: the node split after position s covers [L, R], L / R being the nearest
+// split on either side whose delta is smaller (a smaller delta = a shorter common prefix = a higher node).  A node
+// whose range holds at most WB_SMALL_MAX positions, all with distinct keys, is therefore found by looking at no more
+// than WB_SMALL_MAX - 1 deltas around s, and everything about it follows locally: its box (union of its <= 8 leaf
+// records), its parent (the reference's own rule, wb_goes_right_k, on [L, R]), the packed-leaf flags of its children,
+// its height (longest chain of successive delta minima).  About 80 % of the internal nodes of a mesh are of this kind.
+// What is left -- nodes over more than 8 positions, and everything inside runs of EQUAL keys, where the reference
+// breaks ties by primitive parity (bvh.cu:325-329) and the tree is not a Cartesian tree -- is merged bottom-up by
+// k_merge<build>, which starts from the tops of the finished subtrees (unit[], merge.cuh) instead of the leaves.
+// ---------------------------------------------------------------------------------------------
+constexpr int SN_BP = 1024;   // splits per block
+constexpr int SN_T = 256;
+constexpr int SN_HALO = 16;   // keys staged on either side of the block's positions
+
+// range [L, R] of the node split after s if it is a "small distinct" node; false otherwise (equal keys at s or inside
+// the range, more than WB_SMALL_MAX positions, or the tree root)
+template <bool GROUPED, class K> __device__ __forceinline__ bool small_range(const K& k, int n, int s, int& L, int& R)
+{
+    constexpr int W = 8 * (int)sizeof(decltype(k.key(0)));
+    const int d = wb_key_delta_k(k, s);
+    if (d == W)
+        return false;
+    int a = 0, b = 0;
+    for (;; ++a) {
+        const int j = s - 1 - a;
+        if (j < 0)
+            break;
+        const int dj = wb_key_delta_k(k, j);
+        if (dj < d)
+            break;
+        if (dj == W || dj == d || a + 2 > WB_SMALL_MAX - 1)
+            return false;
+    }
+    for (;; ++b) {
+        const int j = s + 1 + b;
+        if (j > n - 2)
+            break;
+        const int dj = wb_key_delta_k(k, j);
+        if (dj < d)
+            break;
+        if (dj == W || dj == d || a + b + 2 > WB_SMALL_MAX - 1)
+            return false;
+    }
+    L = s - a, R = s + 1 + b;
+    return !(L == 0 && R == n - 1);
+}
+
+template <class KeyT, bool GROUPED>
+__global__ void __launch_bounds__(SN_T)
+k_small_nodes(int n, int leaf_size, const KeyT* __restrict__ keys, const int* __restrict__ prim, NodeRec* pairs,
+              int* __restrict__ parent_int, int* __restrict__ pos_parent, uint16_t* __restrict__ heights, int* __restrict__ unit)
+{
+    constexpr int WIN = SN_BP + 2 * SN_HALO + 2;
+    __shared__ KeyT skeys[WIN];
+    __shared__ unsigned char spar[WIN];
+    __shared__ unsigned char sinfo[SN_BP + 1];  // split b0 - 1 + k: 0x80 | a | b << 3 when it is a small node
+    const int tid = threadIdx.x;
+    const int b0 = blockIdx.x * SN_BP;
+    const int b1 = min(b0 + SN_BP - 1, n - 2);  // last split of the block
+    const int base = b0 - SN_HALO - 1;
+    for (int k = tid; k < WIN; k += SN_T) {
+        const long long g = (long long)base + k;
+        if (g >= 0 && g < n) {
+            skeys[k] = __ldg(keys + g);
+            spar[k] = (unsigned char)(__ldg(prim + g) % 2);
+        }
+    }
+    __syncthreads();
+    const BlockKeys<KeyT> bk { skeys, spar, base };
+    for (int k = tid; k < SN_BP + 1; k += SN_T) {
+        const int s = b0 - 1 + k;
+        unsigned char info = 0;
+        int L, R;
+        if (s >= 0 && s <= b1 && small_range<GROUPED>(bk, n, s, L, R))
+            info = (unsigned char)(0x80 | (s - L) | ((R - s - 1) << 3));
+        sinfo[k] = info;
+    }
+    __syncthreads();
+    for (int k = tid; k < SN_BP; k += SN_T) {
+        const int s = b0 + k;
+        if (s > b1)
+            break;
+        const unsigned char info = sinfo[k + 1];
+        const bool left_done = (sinfo[k] & 0x80) != 0;
+        if (!(info & 0x80)) {
+            // position s is a plain leaf unless the split on its left is a small node (which then covers it)
+            if (!left_done)
+                unit[s] = WB_UNIT_LEAF;
+            if (s == n - 2)
+                unit[n - 1] = WB_UNIT_LEAF;  // nothing to the right of the last position
+            continue;
+        }
+        const int L = s - (info & 7), R = s + 1 + ((info >> 3) & 7);
+        // deltas of the range, 7 bits each (at most 7 of them)
+        unsigned long long dd = 0;
+        for (int j = L; j < R; ++j)
+            dd |= (unsigned long long)wb_key_delta_k(bk, j) << (7 * (j - L));
+        // box: union of the leaf records the leaf pass wrote (each into its own parent's pair)
+        float3 lo = make_float3(FLT_MAX, FLT_MAX, FLT_MAX), hi = make_float3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+        int height = 0;
+        for (int i = L; i <= R; ++i) {
+            const bool gr = wb_goes_right_k<GROUPED>(bk, n, i, i);
+            const float4* r4 = reinterpret_cast<const float4*>(pairs + 2 * (size_t)(gr ? i : i - 1) + (gr ? 0 : 1));
+            const float4 r0 = r4[0], r1 = r4[1];
+            lo = wb_min3(lo, make_float3(r0.x, r0.y, r0.z));
+            hi = wb_max3(hi, make_float3(r1.x, r1.y, r1.z));
+            // depth of leaf i below this node = number of successive delta minima walking away from it, both ways
+            int depth = 0, run = 128;
+            for (int j = i - 1; j >= L; --j) {
+                const int dj = (int)((dd >> (7 * (j - L))) & 127u);
+                if (dj < run)
+                    run = dj, ++depth;
+            }
+            run = 128;
+            for (int j = i; j < R; ++j) {
+                const int dj = (int)((dd >> (7 * (j - L))) & 127u);
+                if (dj < run)
+                    run = dj, ++depth;
+            }
+            height = max(height, depth);
+        }
+        // packed leaves among the children (wb_absorb's rule)
+        if (!wb_size_leaf_k<GROUPED>(bk, leaf_size, L, R)) {
+            if (wb_size_leaf_k<GROUPED>(bk, leaf_size, L, s))
+                pos_parent[L] = n + s;
+            if (wb_size_leaf_k<GROUPED>(bk, leaf_size, s + 1, R))
+                pos_parent[s + 1] = n + s;
+        }
+        heights[s] = wb_pack_height((unsigned)height, R - L + 1);
+        // parent choice and record, exactly as the merge does for a node in hand
+        const bool go_right = wb_goes_right_k<GROUPED>(bk, n, L, R);
+        const int ps = go_right ? R : L - 1;
+        parent_int[s] = n + ps;
+        wb_store_rec(pairs + 2 * (size_t)ps + (go_right ? 0 : 1), lo, hi,
+                     (uint32_t)(n + s) | (wb_size_leaf_k<GROUPED>(bk, leaf_size, L, R) ? WB_LEAF : 0u),
+                     (uint32_t)(go_right ? L : R));
+        // top of a finished subtree (its parent is not a small node): the merge pass starts from here
+        int pL, pR;
+        if (!small_range<GROUPED>(bk, n, ps, pL, pR)) {
+            unit[L] = WB_UNIT_TOP | (s - L) | ((R - L) << 3) | (height << 6);
+            for (int i = L + 1; i <= R; ++i)
+                unit[i] = WB_UNIT_COVERED;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K5/K6: depth rule (bvh.cu:419-441): a single-group node at depth >= 32 (root = 1) becomes a
 // packed leaf whatever its size.  Only trees taller than 30 edges can contain such a node;
 // everything else returns after one header read.
@@ -608,27 +757,32 @@ k_deep_top(int n, const TreeHeader* __restrict__ hdr, const int* __restrict__ pa
     const int s = blockIdx.x * BT + threadIdx.x;
     if (s >= n - 1)
         return;
-    memo[s] = heights[s] >= DEEP_TOP_HEIGHT ? (uint8_t)depth_memo(parent_int, nullptr, n, s) : (uint8_t)0;
+    memo[s] = (heights[s] & WB_HEIGHT_MASK) >= DEEP_TOP_HEIGHT ? (uint8_t)depth_memo(parent_int, nullptr, n, s) : (uint8_t)0;
 }
 
-// one thread per sorted position, two roles.  Node role (internal slot s = thread index): a depth-marked node whose
-// parent is not marked becomes a visible leaf.  Position role: a visible size-leaf whose parent got marked loses its
-// entry -- with a compare-and-swap, so that a new entry written by the node role for the same position survives.
+// one thread per internal node.  A node that holds at most leaf_size positions is a size leaf or lies below one: settled
+// (decided from the range length packed into heights[], two coalesced bytes, for the usual leaf sizes; from the pair
+// record otherwise).  Every other node gets its depth -- memoised, or by walking to the first ancestor whose depth is
+// known -- and, when it is the TOPMOST node at depth >= 32 of its group, becomes a visible leaf: flag in its record,
+// pos_parent[] of its first position set, the entries of the size leaves it swallows cleared.
 template <class KeyT, bool GROUPED>
 __global__ void __launch_bounds__(BT)
 k_deep_fix(int n, int leaf_size, TreeHeader* hdr, const KeyT* __restrict__ keys, const int* __restrict__ parent_int,
-           uint8_t* memo, NodeRec* pairs, int* pos_parent)
+           const uint16_t* __restrict__ heights, uint8_t* memo, NodeRec* pairs, int* pos_parent)
 {
     if (hdr->height + 1 < WB_MAX_DEPTH)
         return;
-    const int i = blockIdx.x * BT + threadIdx.x;
-    if (i >= n)
-        return;
-    if (i < n - 1) {
-        const int s = i;
-        const int left = (int)pairs[2 * (size_t)s].aux, right = (int)pairs[2 * (size_t)s + 1].aux;
-        // size leaves (and everything below them) are settled already
-        if (!wb_size_leaf<KeyT, GROUPED>(keys, leaf_size, left, right)) {
+    const int s = blockIdx.x * BT + threadIdx.x;
+    bool mark = false;  // this node is the topmost one at depth >= 32 of its group
+    int left = 0, right = 0;
+    if (s < n - 1) {
+        bool settled;
+        if (!GROUPED && leaf_size <= 16) {
+            settled = (int)(__ldg(heights + s) >> 12) + 2 <= leaf_size;
+        } else {
+            settled = wb_size_leaf<KeyT, GROUPED>(keys, leaf_size, (int)pairs[2 * (size_t)s].aux, (int)pairs[2 * (size_t)s + 1].aux);
+        }
+        if (!settled) {
             int depth = (int)__ldcg(memo + s);
             if (depth == 0) {
                 depth = depth_memo(parent_int, memo, n, s);
@@ -639,22 +793,26 @@ k_deep_fix(int n, int leaf_size, TreeHeader* hdr, const KeyT* __restrict__ keys,
                 const int ps = parent - n;
                 // the parent sits one level up: when it is marked too, this node is muted below it
                 if (!(depth - 1 >= WB_MAX_DEPTH && node_single_group<KeyT, GROUPED>(keys, pairs, ps))) {
+                    left = (int)pairs[2 * (size_t)s].aux, right = (int)pairs[2 * (size_t)s + 1].aux;
                     NodeRec* rec = pairs + 2 * (size_t)ps + (s < ps ? 0 : 1);
                     rec->ref |= WB_LEAF;
                     pos_parent[left] = parent;
                     hdr->deep = 1;
+                    mark = true;
                 }
             }
         }
     }
-    const int p = *(volatile int*)(pos_parent + i);
-    if (p >= 0) {
-        const int ps = p - n;
-        int depth = (int)__ldcg(memo + ps);
-        if (depth == 0)
-            depth = depth_memo(parent_int, memo, n, ps);
-        if (depth >= WB_MAX_DEPTH && node_single_group<KeyT, GROUPED>(keys, pairs, ps))
-            atomicCAS(pos_parent + i, p, WB_NO_PARENT);
+    // the size leaves a marked node swallows are no longer visible: their pos_parent[] entries are cleared by the whole
+    // warp, 32 consecutive positions per step (a depth-rule leaf of a 100 M-triangle mesh holds ~100 positions)
+    unsigned todo = __ballot_sync(0xffffffffu, mark);
+    const int lane = (int)(threadIdx.x & 31);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int l = __shfl_sync(0xffffffffu, left, src), r = __shfl_sync(0xffffffffu, right, src);
+        for (int p = l + 1 + lane; p <= r; p += 32)
+            pos_parent[p] = WB_NO_PARENT;
     }
 }
 
@@ -762,6 +920,20 @@ __global__ void k_single_item(Src src, int leaf_size, const int* groups, int* pr
                                       (cz - lo.z) * hdr->inv_edges[2], groups, 0);
 }
 
+// WARP_B200_SMALL_NODES=1 turns the Karras-style small-node pass on.  OFF by default: measured on B200 it costs more than it
+// saves (rebuild ms, off / on: C2 sphere 0.370 / 0.451, 10 M heightfield 30-bit 1.95 / 2.07 and 63-bit 2.49 / 2.87, 4 M cloth
+// 0.83 / 0.91).  k_small_nodes takes 97 us at C2 while k_merge only drops from 144 to 129 us although ~80 % of its node
+// merges are gone: the merge is bound by the latency of its dependent chain (chunk -> block counters -> global counters
+// up the spine), not by the bulk of small merges.  Kept as a tested alternative (tests/test_gpu_build.py runs both).
+bool small_nodes_enabled()
+{
+    static const bool env_on = [] {
+        const char* v = getenv("WARP_B200_SMALL_NODES");
+        return v && atoi(v) != 0;
+    }();
+    return g_wb_small_nodes >= 0 ? g_wb_small_nodes != 0 : env_on;
+}
+
 bool use_cub_sort()
 {
     const char* v = getenv("WARP_B200_SORT");
@@ -813,15 +985,23 @@ template <class Src, class KeyT, bool GROUPED> const char* build_impl(BvhState& 
     // K4a leaves, K4b chunked bottom-up merge
     k_leaves<Src, KeyT, GROUPED><<<wb_div_up(n, BT), BT, 0, stream>>>(src, n, keys, s.prim, s.pairs, s.pos_parent, s.tris);
     {
-        const MergeArgs<KeyT> ma { n, s.leaf_size, keys, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters, s.header, s.heights };
+        // K4b small distinct-key nodes, one thread per split (unit[] lives in the sort's spare value buffer, free until the
+        // depth pass reuses it); K4c merges what is left, starting from the tops of the finished subtrees
+        int* unit = nullptr;
+        if (small_nodes_enabled() && n > 64) {
+            unit = s.prim_alt;
+            k_small_nodes<KeyT, GROUPED><<<wb_div_up(n - 1, SN_BP), SN_T, 0, stream>>>(n, s.leaf_size, keys, s.prim, s.pairs, s.parent_int,
+                                                                                     s.pos_parent, s.heights, unit);
+        }
+        const MergeArgs<KeyT> ma { n, s.leaf_size, keys, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters, s.header, s.heights, unit };
         s.plan_valid = false;
         k_merge<false, KeyT, GROUPED><<<wb_div_up(n, BP), TBM, 0, stream>>>(ma);
     }
     // K5/K6 depth rule (early-out unless the tree is at least 32 levels deep); the depth table lives in the sort's
     // spare value buffer, free until the next sort
     k_deep_top<<<wb_div_up(n - 1, BT), BT, 0, stream>>>(n, s.header, s.parent_int, s.heights, (uint8_t*)s.prim_alt);
-    k_deep_fix<KeyT, GROUPED><<<wb_div_up(n, BT), BT, 0, stream>>>(n, s.leaf_size, s.header, keys, s.parent_int,
-                                                                  (uint8_t*)s.prim_alt, s.pairs, s.pos_parent);
+    k_deep_fix<KeyT, GROUPED><<<wb_div_up(n - 1, BT), BT, 0, stream>>>(n, s.leaf_size, s.header, keys, s.parent_int, s.heights,
+                                                                      (uint8_t*)s.prim_alt, s.pairs, s.pos_parent);
     WB_CUDA_TRY(cudaGetLastError());
     return nullptr;
 }
@@ -873,6 +1053,8 @@ int bounds_grid(long long n)
 }
 
 }  // namespace
+
+int g_wb_small_nodes = -1;  // -1: follow WARP_B200_SMALL_NODES (default off); 0 / 1: wp_b200_set_experiment("small_nodes", v)
 
 const char* wb_alloc_tree(BvhState& s, cudaStream_t stream)
 {
@@ -1108,10 +1290,10 @@ const char* wb_refit_merge(BvhState& s, cudaStream_t stream)
         return nullptr;
     const int grid = wb_div_up(s.n, BP);
     if (s.key_bytes == 4) {
-        const MergeArgs<uint32_t> ma { s.n, s.leaf_size, (const uint32_t*)s.keys, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters, s.header };
+        const MergeArgs<uint32_t> ma { s.n, s.leaf_size, (const uint32_t*)s.keys, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters, s.header, nullptr, nullptr };
         k_merge<true, uint32_t, false><<<grid, TBM, 0, stream>>>(ma);
     } else {
-        const MergeArgs<uint64_t> ma { s.n, s.leaf_size, (const uint64_t*)s.keys, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters, s.header };
+        const MergeArgs<uint64_t> ma { s.n, s.leaf_size, (const uint64_t*)s.keys, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters, s.header, nullptr, nullptr };
         k_merge<true, uint64_t, false><<<grid, TBM, 0, stream>>>(ma);  // the static-tree replay never consults groups
     }
     WB_CUDA_TRY(cudaGetLastError());
@@ -1170,7 +1352,7 @@ k_plan_keys(int n, const NodeRec* __restrict__ pairs, const int* __restrict__ pa
             else if (l / WB_WAVE_BP != r / WB_WAVE_BP)
                 key = WB_PLAN_TOP;
             else
-                key = ((uint32_t)(l / WB_WAVE_BP) << WB_PLAN_HEIGHT_BITS) | min((uint32_t)__ldg(heights + s), (1u << WB_PLAN_HEIGHT_BITS) - 1u);
+                key = ((uint32_t)(l / WB_WAVE_BP) << WB_PLAN_HEIGHT_BITS) | min((uint32_t)__ldg(heights + s) & WB_HEIGHT_MASK, (1u << WB_PLAN_HEIGHT_BITS) - 1u);
             keys[s] = key;
         }
 #pragma unroll
@@ -1268,7 +1450,8 @@ const char* wb_refit_plan(BvhState& s, cudaStream_t stream)
 // ------------------------------------------------------------------------------------------------
 void wb_order_free(OrderScratch& ws)
 {
-    void* ptrs[] = { ws.keys, ws.keys_alt, ws.idx, ws.idx_alt, ws.ghist, ws.tile_status, ws.tickets, ws.partials, ws.hdr };
+    void* ptrs[] = { ws.keys, ws.keys_alt, ws.idx, ws.idx_alt, ws.ghist, ws.tile_status, ws.tickets, ws.partials, ws.hdr,
+                     ws.packed, ws.sorted_pts };
     for (void* p : ptrs)
         if (p)
             cudaFree(p);
@@ -1406,6 +1589,8 @@ const char* wb_order_reserve(OrderScratch& ws, long long n, cudaStream_t stream)
     WB_CUDA_TRY(cudaMemset(ws.tickets, 0, 4 * 16));
     WB_CUDA_TRY(cudaMalloc(&ws.partials, 4 * 6 * 4096));
     WB_CUDA_TRY(cudaMalloc(&ws.hdr, sizeof(TreeHeader)));
+    WB_CUDA_TRY(cudaMalloc((void**)&ws.packed, 16 * cap));
+    WB_CUDA_TRY(cudaMalloc((void**)&ws.sorted_pts, 12 * cap + 16));
     ws.capacity = n;
     return nullptr;
 }

@@ -253,7 +253,7 @@ const char* wb_refit(BvhState& s, cudaStream_t stream)
     if (!wave)
         return wb_refit_merge(s, stream);
     const MergeArgs<uint32_t> ma { s.n, s.leaf_size, nullptr, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters, s.header,
-                                   nullptr };
+                                   nullptr, nullptr };
     k_refit_levels<<<wb_div_up(s.n, WB_WAVE_BP), WT, 0, stream>>>(ma, s.unit_flags, s.plan_keys, s.plan_nodes, s.plan_dst,
                                                                   s.plan_begin, s.plan_end);
     int sms = 148;

@@ -24,6 +24,10 @@
 #define WB_QUERY_STACK 32        // BVH_QUERY_STACK_SIZE, warp/native/bvh.h:18
 #define WB_MAX_DEPTH 32          // packed-leaf depth rule, warp/native/bvh.cu:437
 #define WB_HEIGHT_CAP 0xffffu
+// heights[] entry of an internal node: height in the low 12 bits (capped), min(range length - 2, 15) in the high 4 --
+// enough to decide "does this node hold at most leaf_size positions" for leaf_size <= 16 from two coalesced bytes
+// instead of its 64-byte pair record (depth pass, bvh_build.cu)
+#define WB_HEIGHT_MASK 0x0fffu
 
 // one node record = two float4: (lo.xyz, ref) (hi.xyz, aux)
 struct __align__(16) NodeRec {
@@ -70,6 +74,12 @@ struct TreeView {
 #define WB_PLAN_DST_ROOT 0xFFFFFFFFu
 
 __host__ __device__ inline int wb_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+__host__ __device__ inline uint16_t wb_pack_height(unsigned height, int range_len)
+{
+    const unsigned h = height < WB_HEIGHT_MASK ? height : WB_HEIGHT_MASK;
+    const unsigned r = range_len - 2 < 15 ? (unsigned)(range_len - 2) : 15u;
+    return (uint16_t)(h | (r << 12));
+}
 
 #ifdef __CUDACC__
 

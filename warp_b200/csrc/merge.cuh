@@ -31,7 +31,16 @@ template <class KeyT> struct MergeArgs {
     unsigned* counters;
     TreeHeader* hdr;
     uint16_t* heights;  // builder: height of every internal node, for the refit plan
+    const int* unit;    // builder: per sorted position, what k_small_nodes left there (WB_UNIT_*); nullptr = all plain leaves
 };
+
+// unit[] values (k_small_nodes -> k_merge<build>): a position is a plain leaf, lies inside a subtree that starts further
+// left, or starts a finished subtree whose top node is n + (pos + (u & 7)), covering [pos, pos + ((u >> 3) & 7)], of
+// height (u >> 6) & 7
+#define WB_UNIT_LEAF 0
+#define WB_UNIT_COVERED (-1)
+#define WB_UNIT_TOP 0x200
+#define WB_SMALL_MAX 8  // largest key range (sorted positions) of a node that k_small_nodes builds
 
 __device__ __forceinline__ int wb_clz_key(uint32_t x) { return __clz((int)x); }
 __device__ __forceinline__ int wb_clz_key(uint64_t x) { return __clzll((long long)x); }
@@ -183,7 +192,7 @@ __device__ __forceinline__ void wb_absorb(const MergeArgs<KeyT>& a, const K& kv,
                 a.pos_parent[s + 1] = a.n + s;
         }
         xh = max(xh, other_h) + 1u;
-        a.heights[s] = (uint16_t)min(xh, 0xffffu);
+        a.heights[s] = wb_pack_height(xh, new_right - new_left + 1);
     }
     lo = wb_min3(lo, make_float3(s0.x, s0.y, s0.z));
     hi = wb_max3(hi, make_float3(s1.x, s1.y, s1.z));
@@ -269,10 +278,12 @@ k_merge(MergeArgs<KeyT> a)
     for (int k = tid; k < BP; k += TBM)
         scount[k] = 0u;
     // builder: the block's keys (one halo key each side) and primitive parities, loaded once, coalesced
-    __shared__ KeyT skeys[REFIT ? 1 : BP + 2];
-    __shared__ unsigned char spar[REFIT ? 1 : BP + 2];
+    // (halo: one key to the left, WB_SMALL_MAX + 1 to the right -- a unit from k_small_nodes that starts in the block
+    // may end up to WB_SMALL_MAX - 1 positions past it, and its parent choice looks one key further)
+    __shared__ KeyT skeys[REFIT ? 1 : BP + 2 + WB_SMALL_MAX];
+    __shared__ unsigned char spar[REFIT ? 1 : BP + 2 + WB_SMALL_MAX];
     if (!REFIT) {
-        for (int k = tid; k < BP + 2; k += TBM) {
+        for (int k = tid; k < BP + 2 + WB_SMALL_MAX; k += TBM) {
             const long long g = (long long)b0 - 1 + k;
             if (g >= 0 && g < n) {
                 skeys[k] = __ldg(a.keys + g);
@@ -355,15 +366,22 @@ k_merge(MergeArgs<KeyT> a)
                     pos = xr + 1;
                     have = true, fresh = true;
                 } else {
-                    // next original leaf (its record was written by the leaf pass)
-                    const bool gr = wb_goes_right_k<GROUPED>(bk, n, pos, pos);
-                    const NodeRec* rec = a.pairs + 2 * (size_t)(gr ? pos : pos - 1) + (gr ? 0 : 1);
-                    xl = xr = pos;
+                    // next unit: an original leaf (its record was written by the leaf pass), or the top of a subtree
+                    // that k_small_nodes already finished (its record sits in ITS parent's pair, like a leaf's)
+                    const int uw = a.unit ? a.unit[pos] : WB_UNIT_LEAF;
+                    if (uw == WB_UNIT_COVERED) {
+                        ++pos;
+                        continue;
+                    }
+                    xl = pos;
+                    xr = pos + ((uw >> 3) & 7);
+                    xnode = uw == WB_UNIT_LEAF ? (uint32_t)pos : (uint32_t)(n + pos + (uw & 7));
+                    xh = (unsigned)((uw >> 6) & 7);
+                    const bool gr = wb_goes_right_k<GROUPED>(bk, n, xl, xr);
+                    const NodeRec* rec = a.pairs + 2 * (size_t)(gr ? xr : xl - 1) + (gr ? 0 : 1);
                     lo = make_float3(rec->lx, rec->ly, rec->lz);
                     hi = make_float3(rec->hx, rec->hy, rec->hz);
-                    xnode = (uint32_t)pos;
-                    xh = 0;
-                    ++pos;
+                    pos = xr + 1;
                     have = true, fresh = true;
                 }
             }

@@ -15,6 +15,8 @@ struct OrderScratch {
     unsigned* tickets = nullptr;
     float* partials = nullptr;
     TreeHeader* hdr = nullptr;
+    uint4* packed = nullptr;      // capacity records: results of an ordered batch before the unpack pass (query.cu QM_PACKED)
+    float* sorted_pts = nullptr;  // 12 * capacity + 16 bytes: the batch in curve order (query.cu QM_STAGED)
     long long capacity = 0;
 };
 

@@ -245,12 +245,17 @@ struct Counters {
 // ------------------------------------------------------------------------------------------------
 // closest point, mesh.h:501-676
 // ------------------------------------------------------------------------------------------------
-template <bool COUNT>
+// STACK16: one 16-byte local-memory word {a, b, distance} per stack entry (one STL.128 / LDL.128 per push / pop) instead of
+// three 4-byte words in two arrays -- the stack is ~40 % of the kernel's L1 transactions (126 pair fetches x 4 LDG.128 +
+// 23 triangle fetches x 3 against ~60 pushes and pops x 3 per query)
+template <bool COUNT, bool STACK16 = false, bool STACK8 = false>
 __device__ __forceinline__ bool closest_point(const TreeView& tv, const TreeHeader& h, float3 point, float max_dist,
                                               int& face, float& u, float& v, Counters& cnt)
 {
-    Entry stack[WB_QUERY_STACK];
-    float stack_d[WB_QUERY_STACK];
+    Entry stack[(STACK16 || STACK8) ? 1 : WB_QUERY_STACK];
+    float stack_d[(STACK16 || STACK8) ? 1 : WB_QUERY_STACK];
+    uint4 stack16[STACK16 ? WB_QUERY_STACK : 1];
+    uint2 stack8[STACK8 ? WB_QUERY_STACK : 1];  // TIMING EXPERIMENT ONLY: leaf count (<= 8) rides in the low 3 distance bits
     int top = 0;
 
     float best = max_dist * max_dist;
@@ -270,8 +275,16 @@ __device__ __forceinline__ bool closest_point(const TreeView& tv, const TreeHead
             if (top == 0)
                 break;
             --top;
-            cur = stack[top];
-            cur_d = stack_d[top];
+            if (STACK8) {
+                const uint2 e = stack8[top];
+                cur.a = e.x, cur.b = (e.x & WB_LEAF) ? (e.y & 7u) + 1u : 0u, cur_d = __uint_as_float(e.y & ~7u);
+            } else if (STACK16) {
+                const uint4 e = stack16[top];
+                cur.a = e.x, cur.b = e.y, cur_d = __uint_as_float(e.z);
+            } else {
+                cur = stack[top];
+                cur_d = stack_d[top];
+            }
         }
         have = false;
         if (cur_d > best)
@@ -320,8 +333,14 @@ __device__ __forceinline__ bool closest_point(const TreeView& tv, const TreeHead
         else
             far_e = pr.left, far_d = dl, near_e = pr.right, near_d = dr;
         if (far_d < best) {
-            stack[top] = far_e;
-            stack_d[top] = far_d;
+            if (STACK8) {
+                stack8[top] = make_uint2(far_e.a, (__float_as_uint(far_d) & ~7u) | ((far_e.a & WB_LEAF) ? ((far_e.b - 1u) & 7u) : 0u));
+            } else if (STACK16) {
+                stack16[top] = make_uint4(far_e.a, far_e.b, __float_as_uint(far_d), 0u);
+            } else {
+                stack[top] = far_e;
+                stack_d[top] = far_d;
+            }
             ++top;
         }
         if (near_d < best) {
@@ -527,22 +546,78 @@ __device__ __forceinline__ bool probe_sign_ordered(const TreeView& tv, const Tre
 #define WB_SIGN_MINB 10
 #endif
 constexpr int QT_SIGN = WB_QT_SIGN;
-template <bool SIGN, bool COUNT>
+// MODE bits (A/B-measured variants of the memory side of the kernel):
+//   1 QM_STACK16  16-byte stack entries (see closest_point)
+//   2 QM_STREAM   evict-first loads of the permutation / points and streaming stores of the results (ld.global.cs /
+//                 st.global.cs): 419 MB of once-touched I/O per batch should not displace the 147 MB tree from the 126 MB L2
+//   4 QM_PACKED   ordered batches write ONE 16-byte {face, u, v, result} record per query at packed[perm[slot]] instead of
+//                 four 4-byte scatters (sector-granular: 330 B of DRAM writes per query); k_unpack_results then streams the
+//                 records into the caller's SoA arrays
+//   8 QM_STAGED   the batch is gathered into curve order once (k_gather_points) and every block stages its 128 points
+//                 (1536 contiguous bytes) into shared memory with ONE TMA bulk copy (cp.async.bulk + mbarrier)
+#define QM_STACK16 1
+#define QM_STREAM 2
+#define QM_PACKED 4
+#define QM_STAGED 8
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool SIGN, bool COUNT, int MODE = 0>
 __global__ void __launch_bounds__(SIGN ? QT_SIGN : QT, SIGN ? WB_SIGN_MINB : WB_QP_MIN_BLOCKS)
 k_query_point(TreeView tv, const float* __restrict__ pts, const int* __restrict__ perm, long long nq, float max_dist,
               uint8_t* __restrict__ result, float* __restrict__ sign, int* __restrict__ face, float* __restrict__ u,
-              float* __restrict__ v, unsigned long long* __restrict__ stats)
+              float* __restrict__ v, unsigned long long* __restrict__ stats, uint4* __restrict__ packed = nullptr,
+              const float* __restrict__ sorted_pts = nullptr)
 {
     const TreeHeader h = *tv.header;
     Counters cnt;
     constexpr int T = SIGN ? QT_SIGN : QT;
-    for (long long slot = (long long)blockIdx.x * T + threadIdx.x; slot < nq; slot += (long long)gridDim.x * T) {
+    constexpr bool STAGED = (MODE & QM_STAGED) != 0;
+    __shared__ __align__(16) float s_pts[STAGED ? 3 * T : 4];
+    __shared__ __align__(8) unsigned long long s_bar[1];
+    uint32_t phase = 0;
+    if (STAGED) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_bar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    for (long long base = (long long)blockIdx.x * T; base < nq; base += (long long)gridDim.x * T) {
+        const long long slot = base + threadIdx.x;
+        if (STAGED) {
+            // one elected thread issues the bulk copy of this block's 12 * T contiguous bytes (16-byte aligned: T % 4 == 0)
+            const long long count = (nq - base < T) ? nq - base : T;
+            const uint32_t bytes = (uint32_t)((12 * count + 15) & ~15ll);  // the staging buffer of the batch is padded to 16 B
+            if (threadIdx.x == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(s_bar)), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(s_pts)),
+                             "l"(sorted_pts + 3 * base), "r"(bytes), "r"(smem_u32(s_bar))
+                             : "memory");
+            }
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done)
+                             : "r"(smem_u32(s_bar)), "r"(phase)
+                             : "memory");
+            }
+            phase ^= 1u;
+        }
+        if (slot < nq) {
         // `perm` (optional) is a Morton ordering of the batch: thread `slot` answers query perm[slot]
-        const long long i = perm ? (long long)__ldg(perm + slot) : slot;
-        const float3 p = make_float3(__ldg(pts + 3 * i), __ldg(pts + 3 * i + 1), __ldg(pts + 3 * i + 2));
+        const long long i = perm ? (long long)((MODE & QM_STREAM) ? __ldcs(perm + slot) : __ldg(perm + slot)) : slot;
+        float3 p;
+        if (STAGED)
+            p = make_float3(s_pts[3 * threadIdx.x], s_pts[3 * threadIdx.x + 1], s_pts[3 * threadIdx.x + 2]);
+        else if (MODE & QM_STREAM)
+            p = make_float3(__ldcs(pts + 3 * i), __ldcs(pts + 3 * i + 1), __ldcs(pts + 3 * i + 2));
+        else
+            p = make_float3(__ldg(pts + 3 * i), __ldg(pts + 3 * i + 1), __ldg(pts + 3 * i + 2));
         int f = 0;
         float bu = 0.f, bv = 0.f, sg = 0.f;
-        const bool ok = closest_point<COUNT>(tv, h, p, max_dist, f, bu, bv, cnt);
+        const bool ok = closest_point<COUNT, (MODE & QM_STACK16) != 0, (MODE & 16) != 0>(tv, h, p, max_dist, f, bu, bv, cnt);
         if (SIGN && ok) {  // majority of three axis probes, mesh.h:2342-2359
             int votes = 0;
             float s = 0.f;
@@ -559,17 +634,62 @@ k_query_point(TreeView tv, const float* __restrict__ pts, const int* __restrict_
             }
             sg = votes >= 2 ? -1.0f : 1.0f;
         }
-        result[i] = ok ? 1 : 0;
-        face[i] = ok ? f : 0;
-        u[i] = ok ? bu : 0.f;
-        v[i] = ok ? bv : 0.f;
-        if (sign)
-            sign[i] = sg;
+        if ((MODE & QM_PACKED) && packed) {
+            const uint4 rec = make_uint4(ok ? (uint32_t)f : 0u, __float_as_uint(ok ? bu : 0.f), __float_as_uint(ok ? bv : 0.f),
+                                         (ok ? 1u : 0u) | (SIGN ? (__float_as_uint(sg) & 0x80000000u) | (ok ? 2u : 0u) : 0u));
+            __stcs(packed + i, rec);
+        } else if (MODE & QM_STREAM) {
+            __stcs(result + i, (uint8_t)(ok ? 1 : 0));
+            __stcs(face + i, ok ? f : 0);
+            __stcs(u + i, ok ? bu : 0.f);
+            __stcs(v + i, ok ? bv : 0.f);
+            if (sign)
+                __stcs(sign + i, sg);
+        } else {
+            result[i] = ok ? 1 : 0;
+            face[i] = ok ? f : 0;
+            u[i] = ok ? bu : 0.f;
+            v[i] = ok ? bv : 0.f;
+            if (sign)
+                sign[i] = sg;
+        }
+        }
+        if (STAGED)
+            __syncthreads();  // everyone has read its point before the next bulk copy overwrites the buffer
     }
     if (COUNT) {
         atomicAdd(stats + 0, cnt.pairs);
         atomicAdd(stats + 1, cnt.tris);
     }
+}
+
+// QM_PACKED: records in ORIGINAL query order -> the caller's SoA arrays (coalesced reads and writes)
+__global__ void __launch_bounds__(256)
+k_unpack_results(const uint4* __restrict__ packed, long long nq, uint8_t* __restrict__ result, int* __restrict__ face,
+                 float* __restrict__ u, float* __restrict__ v)
+{
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= nq)
+        return;
+    const uint4 r = __ldcs(packed + i);
+    __stcs(result + i, (uint8_t)(r.w & 1u));
+    __stcs(face + i, (int)r.x);
+    __stcs(u + i, __uint_as_float(r.y));
+    __stcs(v + i, __uint_as_float(r.z));
+}
+
+// QM_STAGED: the batch in curve order (12 B per point; the buffer is padded so that every block's slice may be read in
+// whole 16-byte units)
+__global__ void __launch_bounds__(256)
+k_gather_points(const float* __restrict__ pts, const int* __restrict__ perm, long long nq, float* __restrict__ sorted)
+{
+    const long long s = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (s >= nq)
+        return;
+    const long long i = __ldcs(perm + s);
+    sorted[3 * s + 0] = __ldcs(pts + 3 * i);
+    sorted[3 * s + 1] = __ldcs(pts + 3 * i + 1);
+    sorted[3 * s + 2] = __ldcs(pts + 3 * i + 2);
 }
 
 // start entry of a ray traversal: the tree root, or the caller's root node (mesh_query_ray(..., root), mesh.h:1768)
@@ -1281,13 +1401,53 @@ int query_grid(long long nq, int threads = QT)
 
 }  // namespace
 
+namespace {
+template <int MODE>
+void launch_point_mode(const TreeView& tv, const float* pts, const int* perm, long long nq, float max_dist, uint8_t* result,
+                       int* face, float* u, float* v, uint4* packed, float* sorted_pts, cudaStream_t stream)
+{
+    const int grid = query_grid(nq);
+    if ((MODE & QM_STAGED) && perm && sorted_pts)
+        k_gather_points<<<(unsigned)((nq + 255) / 256), 256, 0, stream>>>(pts, perm, nq, sorted_pts);
+    const bool pack = (MODE & QM_PACKED) && perm && packed;
+    k_query_point<false, false, MODE><<<grid, QT, 0, stream>>>(tv, pts, perm, nq, max_dist, result, nullptr, face, u, v, nullptr,
+                                                              pack ? packed : nullptr, sorted_pts);
+    if (pack)
+        k_unpack_results<<<(unsigned)((nq + 255) / 256), 256, 0, stream>>>(packed, nq, result, face, u, v);
+}
+}  // namespace
+
 const char* wb_query_point(const TreeView& tv, const float* pts, const int* perm, long long nq, float max_dist,
                            int with_sign, uint8_t* result, float* sign, int* face, float* u, float* v,
-                           unsigned long long* stats, cudaStream_t stream)
+                           unsigned long long* stats, cudaStream_t stream, int mode, uint4* packed, float* sorted_pts)
 {
     if (nq <= 0)
         return nullptr;
     const int grid = query_grid(nq);
+    if (!with_sign && !stats && mode) {
+        // the staged variant needs the ordered copy of the batch; without an ordering it reads the caller's points in place
+        if ((mode & QM_STAGED) && !(perm && sorted_pts))
+            mode &= ~QM_STAGED;
+        if (mode == 22) {  // timing experiment (QM_STREAM | QM_PACKED | 8-byte stack entries); not a product path
+            launch_point_mode<22>(tv, pts, perm, nq, max_dist, result, face, u, v, packed, sorted_pts, stream);
+            cudaError_t e22 = cudaGetLastError();
+            return e22 == cudaSuccess ? nullptr : cudaGetErrorString(e22);
+        }
+        switch (mode & 15) {
+#define WB_MODE_CASE(M)                                                                                                       \
+    case M:                                                                                                                   \
+        launch_point_mode<M>(tv, pts, perm, nq, max_dist, result, face, u, v, packed, sorted_pts, stream);                  \
+        break;
+            WB_MODE_CASE(1) WB_MODE_CASE(2) WB_MODE_CASE(3) WB_MODE_CASE(4) WB_MODE_CASE(5) WB_MODE_CASE(6) WB_MODE_CASE(7)
+            WB_MODE_CASE(8) WB_MODE_CASE(9) WB_MODE_CASE(10) WB_MODE_CASE(11) WB_MODE_CASE(12) WB_MODE_CASE(13)
+            WB_MODE_CASE(14) WB_MODE_CASE(15)
+#undef WB_MODE_CASE
+        default:
+            k_query_point<false, false><<<grid, QT, 0, stream>>>(tv, pts, perm, nq, max_dist, result, sign, face, u, v, stats);
+        }
+        cudaError_t e = cudaGetLastError();
+        return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+    }
     if (with_sign) {
         const int sgrid = query_grid(nq, QT_SIGN);
         if (stats)

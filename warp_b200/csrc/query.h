@@ -16,9 +16,13 @@ const char* wb_group_roots(const TreeView& tv, const void* keys, const int* grou
 const char* wb_exclusive_scan(const int* counts, int* offsets, long long n, long long* scratch, cudaStream_t stream);
 
 // perm: optional permutation (thread slot -> query index), e.g. from wb_morton_order
+// mode: memory-side variant bits of the unsigned kernel (query.cu QM_*: 1 16-byte stack entries, 2 streaming I/O hints,
+// 4 packed 16-byte result records through `packed` (nq entries) + unpack pass, 8 curve-ordered copy of the batch in
+// `sorted_pts` (12 * nq + 16 bytes) staged per block with one TMA bulk copy); 0 = the plain kernel
 const char* wb_query_point(const TreeView& tv, const float* pts, const int* perm, long long nq, float max_dist,
                            int with_sign, uint8_t* result, float* sign, int* face, float* u, float* v,
-                           unsigned long long* stats, cudaStream_t stream);
+                           unsigned long long* stats, cudaStream_t stream, int mode = 0, uint4* packed = nullptr,
+                           float* sorted_pts = nullptr);
 // roots: optional per-ray start node (reference node index; < 0 or NULL = the tree root)
 const char* wb_query_ray(const TreeView& tv, const float* starts, const float* dirs, const int* perm, const int* roots,
                          long long nq, float max_t, uint8_t* result, float* sign, int* face, float* t, float* u, float* v,

@@ -100,6 +100,7 @@ struct MeshState {
 // build / refit / export drivers (bvh_build.cu, bvh_refit.cu); all enqueue on `stream`
 const char* wb_build(BvhState& s, cudaStream_t stream);
 const char* wb_refit(BvhState& s, cudaStream_t stream);
+extern int g_wb_small_nodes;  // experiment switch of the builder's Karras-style small-node pass (bvh_build.cu)
 extern int g_wb_refit_mode;  // default refit mode of new trees: 0 auto, 1 atomic counters, 2 wavefront
 const char* wb_refit_plan(BvhState& s, cudaStream_t stream);  // (bvh_build.cu: shares the radix sort)
 const char* wb_refit_merge(BvhState& s, cudaStream_t stream);  // bottom-up pass of the refit (bvh_build.cu)
