@@ -182,8 +182,14 @@ def load(path: str | None = None) -> ctypes.CDLL:
             "(needs nvcc).  There is no CPU fallback for this path."
         )
     core = ctypes.CDLL(p)  # ctypes.CDLL releases the GIL around calls, like the reference (context.py:8452-8454)
+    variant = p != LIB_PATH  # an A/B build of an older revision may lack newer entry points; the product library may not
     for name, (restype, argtypes) in SIGNATURES.items():
-        fn = getattr(core, name)  # AttributeError here == the .so does not export a declared symbol
+        try:
+            fn = getattr(core, name)  # AttributeError here == the .so does not export a declared symbol
+        except AttributeError:
+            if variant:
+                continue
+            raise
         fn.restype = restype
         fn.argtypes = argtypes
     if path is None:

@@ -259,6 +259,7 @@ TreeView make_view(const BvhState& s)
     tv.tris = s.tris;
     tv.prim = s.prim;
     tv.parent_int = s.parent_int;
+    tv.pos_parent = s.pos_parent;
     tv.n = s.n;
     return tv;
 }
@@ -322,7 +323,7 @@ struct KernelTimerScope {
 
 // memory-side variant of the unsigned closest-point kernel (query.cu QM_* bits); WARP_B200_QMODE overrides the default
 #ifndef WB_QMODE_DEFAULT
-#define WB_QMODE_DEFAULT 6  // QM_STREAM | QM_PACKED: measured best on C2 / C4 (scripts/qmode_ab.py)
+#define WB_QMODE_DEFAULT 22  // QM_STREAM | QM_PACKED | QM_STACK8: measured best on C2 / C4 (scripts/qmode_ab.py)
 #endif
 int query_mode()
 {
@@ -1118,8 +1119,11 @@ static int query_point_on(MeshState* m, const float* points, int64_t n, float ma
     {
         KernelTimerScope timed(st);
         L2PersistScope l2(m->bvh, st);
+        // the host-buffer lanes keep the direct SoA stores: with packed records + unpack pass the pinned-buffer pipeline
+        // measured 533 instead of 572 M queries/s end to end (the device-resident batch gains 1.5 % from them)
+        const int mode = lane ? (query_mode() & ~4) : query_mode();
         err = wb_query_point(make_view(m->bvh), points, perm, n, max_dist, with_sign, result, sign, face, u, v,
-                             stats_buffer(), st, query_mode(), packed, sorted_pts);
+                             stats_buffer(), st, mode, packed, sorted_pts);
     }
     if (err) {
         set_error("Warp error: mesh point query failed: %s", err);

@@ -61,6 +61,7 @@ struct TreeView {
     const float4* tris;          // 3 float4 per sorted position (mesh only): p, q, r, face, flags
     const int* prim;             // primitive_indices (sorted position -> item)
     const int* parent_int;       // parent (reference index) of internal node n+s, WB_NO_PARENT for the root
+    const int* pos_parent;       // parent of the visible leaf that starts at a sorted position (state.h)
     int n;
 };
 

@@ -245,6 +245,40 @@ struct Counters {
 // ------------------------------------------------------------------------------------------------
 // closest point, mesh.h:501-676
 // ------------------------------------------------------------------------------------------------
+// STACK8 (the default for trees below 2^28 items): a stack entry is ONE 8-byte word {entry, distance}.  A leaf entry packs
+// its first position and its item count into 31 bits -- start << 3 | count - 1 for counts up to 7; the code 7 stands for
+// "8 or more" (depth-rule leaves) and sends the pop to the leaf's parent record for the count.  256 B of local memory per
+// thread instead of 384 B, one STL.64 / LDL.64 per push / pop instead of three 4-byte accesses: -2.7 % on C2.
+__device__ __forceinline__ uint32_t pack_entry(Entry e)
+{
+    if (!(e.a & WB_LEAF))
+        return e.a;
+    return WB_LEAF | ((e.a & WB_IDX_MASK) << 3) | (e.b - 1u < 7u ? e.b - 1u : 7u);
+}
+
+__device__ __forceinline__ Entry unpack_entry(const TreeView& tv, uint32_t w)
+{
+    Entry e;
+    if (!(w & WB_LEAF)) {
+        e.a = w, e.b = 0;
+        return e;
+    }
+    const uint32_t start = (w & WB_IDX_MASK) >> 3, c = w & 7u;
+    e.a = start | WB_LEAF;
+    if (c < 7u) {
+        e.b = c + 1u;
+    } else {  // a large leaf: its range is in its record inside the parent's pair
+        const int p = __ldg(tv.pos_parent + start);
+        if (p == WB_ROOT_PARENT) {
+            e.b = (uint32_t)tv.n;
+        } else {
+            const uint32_t ps = (uint32_t)(p - tv.n);
+            e.b = start <= ps ? ps - start + 1u : tv.pairs[2 * (size_t)ps + 1].aux - ps;
+        }
+    }
+    return e;
+}
+
 // STACK16: one 16-byte local-memory word {a, b, distance} per stack entry (one STL.128 / LDL.128 per push / pop) instead of
 // three 4-byte words in two arrays -- the stack is ~40 % of the kernel's L1 transactions (126 pair fetches x 4 LDG.128 +
 // 23 triangle fetches x 3 against ~60 pushes and pops x 3 per query)
@@ -255,7 +289,7 @@ __device__ __forceinline__ bool closest_point(const TreeView& tv, const TreeHead
     Entry stack[(STACK16 || STACK8) ? 1 : WB_QUERY_STACK];
     float stack_d[(STACK16 || STACK8) ? 1 : WB_QUERY_STACK];
     uint4 stack16[STACK16 ? WB_QUERY_STACK : 1];
-    uint2 stack8[STACK8 ? WB_QUERY_STACK : 1];  // TIMING EXPERIMENT ONLY: leaf count (<= 8) rides in the low 3 distance bits
+    uint2 stack8[STACK8 ? WB_QUERY_STACK : 1];  // {packed entry, distance}: see pack_entry
     int top = 0;
 
     float best = max_dist * max_dist;
@@ -277,7 +311,7 @@ __device__ __forceinline__ bool closest_point(const TreeView& tv, const TreeHead
             --top;
             if (STACK8) {
                 const uint2 e = stack8[top];
-                cur.a = e.x, cur.b = (e.x & WB_LEAF) ? (e.y & 7u) + 1u : 0u, cur_d = __uint_as_float(e.y & ~7u);
+                cur = unpack_entry(tv, e.x), cur_d = __uint_as_float(e.y);
             } else if (STACK16) {
                 const uint4 e = stack16[top];
                 cur.a = e.x, cur.b = e.y, cur_d = __uint_as_float(e.z);
@@ -334,7 +368,7 @@ __device__ __forceinline__ bool closest_point(const TreeView& tv, const TreeHead
             far_e = pr.left, far_d = dl, near_e = pr.right, near_d = dr;
         if (far_d < best) {
             if (STACK8) {
-                stack8[top] = make_uint2(far_e.a, (__float_as_uint(far_d) & ~7u) | ((far_e.a & WB_LEAF) ? ((far_e.b - 1u) & 7u) : 0u));
+                stack8[top] = make_uint2(pack_entry(far_e), __float_as_uint(far_d));
             } else if (STACK16) {
                 stack16[top] = make_uint4(far_e.a, far_e.b, __float_as_uint(far_d), 0u);
             } else {
@@ -553,6 +587,7 @@ constexpr int QT_SIGN = WB_QT_SIGN;
 //   4 QM_PACKED   ordered batches write ONE 16-byte {face, u, v, result} record per query at packed[perm[slot]] instead of
 //                 four 4-byte scatters (sector-granular: 330 B of DRAM writes per query); k_unpack_results then streams the
 //                 records into the caller's SoA arrays
+//  16 QM_STACK8   8-byte stack entries (see pack_entry); combined with 0, 2 or 6 only
 //   8 QM_STAGED   the batch is gathered into curve order once (k_gather_points) and every block stages its 128 points
 //                 (1536 contiguous bytes) into shared memory with ONE TMA bulk copy (cp.async.bulk + mbarrier)
 #define QM_STACK16 1
@@ -719,7 +754,8 @@ __device__ __forceinline__ Entry ray_start_entry(const TreeView& tv, const TreeH
 #ifndef WB_QR_MIN_BLOCKS
 #define WB_QR_MIN_BLOCKS 10  // measured on C3: unhinted 2.98, (QT, 1) 2.88, 8: 2.86, 10: 3.01, 12: 2.83 G rays/s
 #endif
-template <bool COUNT>
+// PACK: 4-byte stack entries (pack_entry) for trees below 2^28 items -- 128 B of local memory per ray instead of 256 B
+template <bool COUNT, bool PACK>
 __global__ void __launch_bounds__(QT, WB_QR_MIN_BLOCKS)
 k_query_ray(TreeView tv, const float* __restrict__ starts, const float* __restrict__ dirs, const int* __restrict__ perm,
             const int* __restrict__ roots, long long nq, float max_t, uint8_t* __restrict__ result, float* __restrict__ sign, int* __restrict__ face,
@@ -744,7 +780,8 @@ k_query_ray(TreeView tv, const float* __restrict__ starts, const float* __restri
         const bool fast = dir.x != 0.0f && dir.y != 0.0f && dir.z != 0.0f;
         const WoopRay wr = woop_setup(dir);
 
-        Entry stack[WB_QUERY_STACK];
+        Entry stack[PACK ? 1 : WB_QUERY_STACK];
+        uint32_t stack4[PACK ? WB_QUERY_STACK : 1];
         int top = 0;
         float3 start_lo, start_hi;  // the start node's box is not tested (mesh.h:1779)
         Entry cur = ray_start_entry(tv, h, roots, i, start_lo, start_hi);
@@ -771,7 +808,8 @@ k_query_ray(TreeView tv, const float* __restrict__ starts, const float* __restri
                 }
                 if (top == 0)
                     break;
-                cur = stack[--top];
+                --top;
+                cur = PACK ? unpack_entry(tv, stack4[top]) : stack[top];
                 continue;
             }
             const Pair pr = load_pair(tv.pairs, cur.a, tv.n);
@@ -788,7 +826,10 @@ k_query_ray(TreeView tv, const float* __restrict__ starts, const float* __restri
                 const bool near_left = t0 < t1;
                 if (top >= WB_QUERY_STACK)
                     break;  // mesh.h:1860-1861
-                stack[top++] = near_left ? pr.right : pr.left;
+                if (PACK)
+                    stack4[top++] = pack_entry(near_left ? pr.right : pr.left);
+                else
+                    stack[top++] = near_left ? pr.right : pr.left;
                 cur = near_left ? pr.left : pr.right;
             } else if (h0) {
                 cur = pr.left;
@@ -797,7 +838,8 @@ k_query_ray(TreeView tv, const float* __restrict__ starts, const float* __restri
             } else {
                 if (top == 0)
                     break;
-                cur = stack[--top];
+                --top;
+                cur = PACK ? unpack_entry(tv, stack4[top]) : stack[top];
             }
         }
 
@@ -1428,8 +1470,15 @@ const char* wb_query_point(const TreeView& tv, const float* pts, const int* perm
         // the staged variant needs the ordered copy of the batch; without an ordering it reads the caller's points in place
         if ((mode & QM_STAGED) && !(perm && sorted_pts))
             mode &= ~QM_STAGED;
-        if (mode == 22) {  // timing experiment (QM_STREAM | QM_PACKED | 8-byte stack entries); not a product path
-            launch_point_mode<22>(tv, pts, perm, nq, max_dist, result, face, u, v, packed, sorted_pts, stream);
+        if ((mode & 16) && tv.n >= (1 << 28))
+            mode &= ~16;  // packed stack entries hold 28 bits of position
+        if ((mode & ~15) == 16 && ((mode & 15) == 6 || (mode & 15) == 2 || (mode & 15) == 0)) {  // 8-byte stack entries (+ I/O bits)
+            if ((mode & 15) == 6)
+                launch_point_mode<22>(tv, pts, perm, nq, max_dist, result, face, u, v, packed, sorted_pts, stream);
+            else if ((mode & 15) == 2)
+                launch_point_mode<18>(tv, pts, perm, nq, max_dist, result, face, u, v, packed, sorted_pts, stream);
+            else
+                launch_point_mode<16>(tv, pts, perm, nq, max_dist, result, face, u, v, packed, sorted_pts, stream);
             cudaError_t e22 = cudaGetLastError();
             return e22 == cudaSuccess ? nullptr : cudaGetErrorString(e22);
         }
@@ -1471,10 +1520,19 @@ const char* wb_query_ray(const TreeView& tv, const float* starts, const float* d
     if (nq <= 0)
         return nullptr;
     const int grid = query_grid(nq);
+    // 4-byte packed stack entries for rays: measured SLOWER on C3 (2.96 vs 3.08 G primary rays/s: a primary ray's stack is
+    // shallow, the unpack on every pop costs more than the smaller footprint saves) -- off unless WARP_B200_RAY_PACK=1
+    static const bool pack_env = [] {
+        const char* e = getenv("WARP_B200_RAY_PACK");
+        return e && atoi(e) != 0;
+    }();
+    const bool pack = pack_env && tv.n < (1 << 28);
     if (stats)
-        k_query_ray<true><<<grid, QT, 0, stream>>>(tv, starts, dirs, perm, roots, nq, max_t, result, sign, face, t, u, v, normal, stats);
+        k_query_ray<true, false><<<grid, QT, 0, stream>>>(tv, starts, dirs, perm, roots, nq, max_t, result, sign, face, t, u, v, normal, stats);
+    else if (pack)
+        k_query_ray<false, true><<<grid, QT, 0, stream>>>(tv, starts, dirs, perm, roots, nq, max_t, result, sign, face, t, u, v, normal, stats);
     else
-        k_query_ray<false><<<grid, QT, 0, stream>>>(tv, starts, dirs, perm, roots, nq, max_t, result, sign, face, t, u, v, normal, stats);
+        k_query_ray<false, false><<<grid, QT, 0, stream>>>(tv, starts, dirs, perm, roots, nq, max_t, result, sign, face, t, u, v, normal, stats);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
