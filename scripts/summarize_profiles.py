@@ -88,12 +88,15 @@ def table(raw, title, note):
     lines.append("")
 
 table(os.path.join(G, f"{R}_query_point.raw.csv"), "`k_query_point` at bench size (16 777 216 queries, C2 mesh, Morton-ordered batch)",
-      "command: `ncu --set full --clock-control none --import-source on -k regex:k_query_point -s 1 -c 1 python scripts/prof_driver.py` "
-      "(PROF_NQ=2^24).  `DRAM read + write` of this launch is the `roofline.traffic` figure bench.py reports.")
+      "command: `ncu --set full --clock-control none --import-source on -k regex:'k_query_point|k_unpack_results' -s 2 -c 2 python scripts/prof_driver.py` "
+      "(PROF_NQ=2^24).  `DRAM read + write` of the traversal launch plus its unpack pass is the `roofline.traffic` figure bench.py reports.")
 table(os.path.join(G, f"{R}_build_refit.raw.csv"), "Build / refit / ray kernels at C2 size (1 310 720 triangles; rays: 1 M random rays)",
       "command: `ncu --set full --clock-control none --import-source on -k regex:'k_scene|k_morton|k_onesweep|k_leaves|k_merge|k_refit|k_deep|k_query_ray' "
       "-s 12 -c 16 python scripts/prof_driver.py`.")
 
+table(os.path.join(G, f"{R}_build10m.raw.csv"), "Build kernels at C3 size (9 999 392-triangle heightfield, 30-bit keys)",
+      "command: `ncu --set full --clock-control none --import-source on -k regex:'k_onesweep|k_merge|k_leaves|k_scene|k_morton|k_deep' -s 11 -c 11 "
+      "python scripts/prof_build_big.py` (taken before the depth pass was reworked: `k_deep_fix` reads packed range lengths since).")
 table(os.path.join(G, f"{R}_refit_wave.raw.csv"), "Wavefront refit + its one-time plan at C4 size (3 998 792-triangle cloth)",
       "command: `ncu --set full --clock-control none --import-source on -k regex:'k_refit|k_plan' -s 0 -c 12 python scripts/prof_refit_driver.py`. "
       "`k_plan_*` (+ 4 sort passes, not captured here) run once per build; a refit is `k_refit_leaves` + `k_refit_levels` + `k_refit_climb`.")

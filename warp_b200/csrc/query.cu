@@ -1501,6 +1501,8 @@ const char* wb_query_point(const TreeView& tv, const float* pts, const int* perm
         const int sgrid = query_grid(nq, QT_SIGN);
         if (stats)
             k_query_point<true, true><<<sgrid, QT_SIGN, 0, stream>>>(tv, pts, perm, nq, max_dist, result, sign, face, u, v, stats);
+        else if ((mode & 16) && tv.n < (1 << 28))  // 8-byte stack entries for the closest-point part
+            k_query_point<true, false, 16><<<sgrid, QT_SIGN, 0, stream>>>(tv, pts, perm, nq, max_dist, result, sign, face, u, v, stats);
         else
             k_query_point<true, false><<<sgrid, QT_SIGN, 0, stream>>>(tv, pts, perm, nq, max_dist, result, sign, face, u, v, stats);
     } else {
