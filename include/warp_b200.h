@@ -389,6 +389,13 @@ WP_B200_API int wp_b200_nccl_allgather_part(const void* send, void* recv, size_t
  * library's communication stream; mark / wait_mark: per-buffer completion points on the communication stream */
 WP_B200_API int wp_b200_nccl_allgather_multi(const void* const* send, void* const* recv, const size_t* bytes_per_rank,
                                              int count, int on_comm_stream);
+/* peer-memory gather over NVLink: CUDA IPC mapping of a peer's result buffers, then every rank pushes its shard into
+ * every peer's buffer with copy-engine memcpys on the communication stream, fenced by two 4-byte NCCL all-reduces */
+WP_B200_API int wp_b200_ipc_get_handle(void* device_ptr, void* handle72);   /* 64-byte IPC handle + 8-byte offset */
+WP_B200_API void* wp_b200_ipc_open_handle(const void* handle72);
+WP_B200_API void wp_b200_ipc_close_handle(void* peer_ptr, const void* handle72);
+WP_B200_API int wp_b200_p2p_allgather_multi(const void* const* send, void* const* own_recv, void* const* peer_recv,
+                                            const size_t* bytes_per_rank, int count, int rank);
 WP_B200_API int wp_b200_nccl_mark(int k);
 WP_B200_API int wp_b200_nccl_wait_mark(int k);
 WP_B200_API int wp_b200_nccl_fork(void);

@@ -31,6 +31,32 @@ if rank == 0:
         a, b = plan.range(r)
         for k in ("result", "face", "u", "v"):
             assert np.array_equal(ref[k][r * plan.shard : r * plan.shard + (b - a)], whole[k][a:b]), (r, k)
+# QueryPipeline (cross-batch pipelining of the gather) over both transports: peer-memory pushes and grouped NCCL
+S, D = mg.random_rays(P, plan.shard, seed=20 + rank)
+s_d, d_d = wp.array(S, dtype=wp.vec3, device=dev), wp.array(D, dtype=wp.vec3, device=dev)
+ray_ref, _ = distributed.sharded_query_ray(mesh, s_d, d_d, plan, 1e6, comm, rank)
+ray_ref = {k: v.numpy().copy() for k, v in ray_ref.items()}
+for transport in ("p2p", "nccl"):
+    os.environ["WARP_B200_GATHER"] = transport
+    pipe = distributed.QueryPipeline(mesh, plan, comm, "point_no_sign", 1e6)
+    assert pipe.transport == transport, (pipe.transport, transport)
+    for step in range(5):
+        k = pipe.submit(q_dev)
+    g = pipe.result(k)
+    pipe.finish()
+    wp.synchronize()
+    for f in ("result", "face", "u", "v"):
+        assert np.array_equal(getattr(g, f).numpy(), ref[f]), (rank, transport, f)
+    rp = distributed.QueryPipeline(mesh, plan, comm, "ray", 1e6)
+    for step in range(4):
+        k = rp.submit(s_d, d_d)
+    g = rp.result(k)
+    rp.finish()
+    wp.synchronize()
+    for f in ("result", "sign", "face", "t", "u", "v", "normal"):
+        assert np.array_equal(getattr(g, f).numpy(), ray_ref[f]), (rank, transport, f)
+    del pipe, rp, g
+    comm.barrier()
 comm.barrier()
 print("sharded OK", rank, flush=True)
 comm.close()

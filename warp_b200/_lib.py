@@ -158,6 +158,10 @@ SIGNATURES = {
     "wp_b200_nccl_allgather": (_i, [_vp, _vp, _sz]),
     "wp_b200_nccl_allgather_part": (_i, [_vp, _vp, _sz, _sz, _sz]),
     "wp_b200_nccl_allgather_multi": (_i, [_vp, _vp, _vp, _i, _i]),
+    "wp_b200_ipc_get_handle": (_i, [_vp, _vp]),
+    "wp_b200_ipc_open_handle": (_vp, [_vp]),
+    "wp_b200_ipc_close_handle": (None, [_vp, _vp]),
+    "wp_b200_p2p_allgather_multi": (_i, [_vp, _vp, _vp, _vp, _i, _i]),
     "wp_b200_nccl_mark": (_i, [_i]),
     "wp_b200_nccl_wait_mark": (_i, [_i]),
     "wp_b200_nccl_fork": (_i, []),

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 
@@ -186,6 +187,110 @@ int wp_b200_nccl_wait_mark(int k)
         return 1;  // never recorded: nothing to wait for
     cudaStream_t st = (cudaStream_t)wp_cuda_context_get_stream(nullptr);
     return cudaStreamWaitEvent(st, g_mark[k], 0) == cudaSuccess;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Peer-memory all-gather: every rank PUSHES its shard straight into every peer's result buffer with
+// cudaMemcpyAsync over NVLink (copy engines, no SM), instead of an SM-driven NCCL kernel that competes with the
+// traversal it is supposed to hide under.  One process per GPU, so peer buffers are reached through CUDA IPC handles
+// (exchanged once per buffer set by the caller, with NCCL).  Ordering across ranks uses two 4-byte NCCL all-reduces on
+// the communication stream: the first ("everyone has forked") keeps a fast rank from overwriting a buffer a slow rank
+// is still reading, the second ("everyone has pushed") tells each rank that all its incoming shards have landed.
+// ------------------------------------------------------------------------------------------------
+// handle72 = the 64-byte cudaIpcMemHandle_t of the allocation that holds device_ptr + the 8-byte offset of device_ptr
+// inside it (the runtime may carve small buffers out of a larger block; an IPC handle always maps the whole block)
+int wp_b200_ipc_get_handle(void* device_ptr, void* handle72)
+{
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, device_ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t");
+    unsigned long long offset = 0;
+    typedef int (*fn_range)(unsigned long long*, size_t*, unsigned long long);
+    static fn_range get_range = [] {
+        void* lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        return lib ? (fn_range)dlsym(lib, "cuMemGetAddressRange_v2") : (fn_range) nullptr;
+    }();
+    if (get_range) {
+        unsigned long long base = 0;
+        size_t size = 0;
+        if (get_range(&base, &size, (unsigned long long)(uintptr_t)device_ptr) == 0 && base)
+            offset = (unsigned long long)(uintptr_t)device_ptr - base;
+    }
+    memcpy(handle72, &h, sizeof(h));
+    memcpy((char*)handle72 + 64, &offset, 8);
+    return 1;
+}
+
+// maps a peer's allocation into this process; returns the peer buffer's address here (base + offset), NULL on failure
+void* wp_b200_ipc_open_handle(const void* handle72)
+{
+    cudaIpcMemHandle_t h;
+    unsigned long long offset = 0;
+    memcpy(&h, handle72, sizeof(h));
+    memcpy(&offset, (const char*)handle72 + 64, 8);
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return (char*)p + offset;
+}
+
+// takes what wp_b200_ipc_open_handle returned and the same handle (for the offset)
+void wp_b200_ipc_close_handle(void* peer_ptr, const void* handle72)
+{
+    if (!peer_ptr)
+        return;
+    unsigned long long offset = 0;
+    memcpy(&offset, (const char*)handle72 + 64, 8);
+    cudaIpcCloseMemHandle((char*)peer_ptr - offset);
+}
+
+// peer_recv[r * count + k] = field k of rank r's gathered buffer as mapped into this process (NULL for r == own rank:
+// the own shard is copied locally into own_recv[k]); send[k] = this rank's shard of field k, bytes_per_rank[k] bytes.
+// Enqueued on the communication stream (after a wp_b200_nccl_fork()).
+int wp_b200_p2p_allgather_multi(const void* const* send, void* const* own_recv, void* const* peer_recv,
+                                const size_t* bytes_per_rank, int count, int rank)
+{
+    if (!g_comm)
+        return fail("p2p_allgather (communicator not initialised)", 0);
+    static float* token = nullptr;
+    if (!token) {
+        cudaMalloc(&token, 2 * sizeof(float));
+        cudaMemset(token, 0, 2 * sizeof(float));
+    }
+    int rc = p_all_reduce(token, token, 1, kNcclFloat32, kNcclMax, g_comm, g_comm_stream);  // everyone has forked
+    if (rc)
+        return fail("ncclAllReduce (p2p pre-sync)", rc);
+    bool ok = true;
+    for (int k = 0; k < count && ok; ++k) {
+        if (!bytes_per_rank[k])
+            continue;
+        ok = cudaMemcpyAsync((char*)own_recv[k] + (size_t)rank * bytes_per_rank[k], send[k], bytes_per_rank[k],
+                             cudaMemcpyDeviceToDevice, g_comm_stream) == cudaSuccess;
+    }
+    // peers in a rotated order, so that at any moment every rank is mostly receiving from a different sender
+    for (int step = 1; step < g_world && ok; ++step) {
+        const int r = (rank + step) % g_world;
+        for (int k = 0; k < count && ok; ++k) {
+            if (!bytes_per_rank[k])
+                continue;
+            char* dst = (char*)peer_recv[(size_t)r * count + k];
+            if (!dst)
+                return fail("p2p_allgather (peer buffer not mapped)", 0);
+            ok = cudaMemcpyAsync(dst + (size_t)rank * bytes_per_rank[k], send[k], bytes_per_rank[k], cudaMemcpyDeviceToDevice,
+                                 g_comm_stream) == cudaSuccess;
+        }
+    }
+    if (!ok) {
+        cudaGetLastError();
+        return fail("p2p_allgather (cudaMemcpyAsync to a peer)", 0);
+    }
+    rc = p_all_reduce(token + 1, token + 1, 1, kNcclFloat32, kNcclMax, g_comm, g_comm_stream);  // everyone has pushed
+    return rc ? fail("ncclAllReduce (p2p post-sync)", rc) : 1;
 }
 
 int wp_b200_nccl_fork(void)

@@ -101,6 +101,44 @@ class NcclCommunicator:
         if not _lib.core().wp_b200_nccl_allgather_multi(send, recv, nbytes, k, 1 if comm_stream else 0):
             raise RuntimeError("grouped ncclAllGather failed")
 
+    def map_peers(self, buffers):
+        """CUDA IPC mapping of every rank's ``buffers`` (a list of device arrays, same order on every rank) into this
+        process: returns a :class:`PeerMap` for :meth:`p2p_allgather_multi`.  Collective (one NCCL all-gather of the
+        72-byte handles)."""
+        from .types import array, uint8
+
+        c = _lib.core()
+        k = len(buffers)
+        mine = np.zeros((k, 72), np.uint8)
+        for i, b in enumerate(buffers):
+            if not c.wp_b200_ipc_get_handle(ctypes.c_void_p(b.ptr), mine[i].ctypes.data):
+                raise RuntimeError("cudaIpcGetMemHandle failed")
+        send = array(mine.reshape(-1), dtype=uint8, device=buffers[0].device)
+        recv = array(np.zeros(self.world * k * 72, np.uint8), dtype=uint8, device=buffers[0].device)
+        self.allgather(send, recv, k * 72)
+        c.wp_cuda_stream_synchronize(c.wp_cuda_context_get_stream(None))
+        handles = recv.numpy().reshape(self.world, k, 72).copy()
+        table = (ctypes.c_void_p * (self.world * k))()
+        for r in range(self.world):
+            for i in range(k):
+                if r == self.rank:
+                    continue
+                p = c.wp_b200_ipc_open_handle(handles[r, i].ctypes.data)
+                if not p:
+                    raise RuntimeError(f"cudaIpcOpenMemHandle failed for rank {r}'s buffer {i}")
+                table[r * k + i] = p
+        return PeerMap(self, buffers, handles, table)
+
+    def p2p_allgather_multi(self, sends, peer_map, nbytes):
+        """Every rank pushes its shard of each field into every rank's buffer (copy engines over NVLink), on the
+        communication stream; ``sends[i]`` / ``nbytes[i]`` per field, ``peer_map`` from :meth:`map_peers`."""
+        k = len(sends)
+        send = (ctypes.c_void_p * k)(*[a.ptr for a in sends])
+        own = (ctypes.c_void_p * k)(*[b.ptr for b in peer_map.buffers])
+        nb = (ctypes.c_size_t * k)(*[int(x) for x in nbytes])
+        if not _lib.core().wp_b200_p2p_allgather_multi(send, own, peer_map.table, nb, k, self.rank):
+            raise RuntimeError("peer-memory all-gather failed")
+
     def mark(self, k: int):
         if not _lib.core().wp_b200_nccl_mark(int(k)):
             raise RuntimeError("NCCL mark failed")
@@ -127,6 +165,29 @@ class NcclCommunicator:
 
     def close(self):
         _lib.core().wp_b200_nccl_destroy()
+
+
+class PeerMap:
+    """Peers' buffers mapped into this process (CUDA IPC); unmapped when the object goes away."""
+
+    def __init__(self, comm, buffers, handles, table):
+        self.comm, self.buffers, self.handles, self.table = comm, buffers, handles, table
+
+    def close(self):
+        c = _lib.core()
+        k = len(self.buffers)
+        for r in range(self.comm.world):
+            for i in range(k):
+                p = self.table[r * k + i]
+                if p:
+                    c.wp_b200_ipc_close_handle(ctypes.c_void_p(p), self.handles[r, i].ctypes.data)
+                    self.table[r * k + i] = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def exchange_unique_id(rank: int, world: int, make_id, addr: str | None = None, port: int | None = None,
@@ -348,6 +409,15 @@ class QueryPipeline:
         self.local = [mk(n) for _ in range(depth)]
         self.gathered = [mk(plan.padded) for _ in range(depth)] if comm is not None else self.local
         self.submitted = 0
+        # transport of the gather: "p2p" = every rank pushes its shard into the peers' buffers with copy-engine memcpys
+        # over NVLink (no SM taken from the traversal it runs under), "nccl" = one grouped ncclAllGather launch
+        self.transport = os.environ.get("WARP_B200_GATHER", "p2p") if (comm is not None and hasattr(comm, "map_peers")) else "nccl"
+        self.peers = None
+        if comm is not None and self.transport == "p2p":
+            try:
+                self.peers = [comm.map_peers([getattr(g, f) for f in self.wire]) for g in self.gathered]
+            except RuntimeError:
+                self.transport, self.peers = "nccl", None
 
     def submit(self, *inputs):
         from .queries import mesh_query_point, mesh_query_point_no_sign, mesh_query_ray
@@ -364,8 +434,12 @@ class QueryPipeline:
             mesh_query_point_no_sign(self.mesh, inputs[0], self.max_dist, out=self.local[slot])
         if self.comm is not None:
             self.comm.fork()
-            self.comm.allgather_multi([(getattr(self.local[slot], f), getattr(self.gathered[slot], f),
-                                        self.plan.shard * FIELD_BYTES[f]) for f in self.wire], comm_stream=True)
+            if self.peers is not None:
+                self.comm.p2p_allgather_multi([getattr(self.local[slot], f) for f in self.wire], self.peers[slot],
+                                              [self.plan.shard * FIELD_BYTES[f] for f in self.wire])
+            else:
+                self.comm.allgather_multi([(getattr(self.local[slot], f), getattr(self.gathered[slot], f),
+                                            self.plan.shard * FIELD_BYTES[f]) for f in self.wire], comm_stream=True)
             self.comm.mark(slot)
         self.submitted += 1
         return k
