@@ -396,6 +396,7 @@ WP_B200_API void* wp_b200_ipc_open_handle(const void* handle72);
 WP_B200_API void wp_b200_ipc_close_handle(void* peer_ptr, const void* handle72);
 WP_B200_API int wp_b200_p2p_allgather_multi(const void* const* send, void* const* own_recv, void* const* peer_recv,
                                             const size_t* bytes_per_rank, int count, int rank);
+WP_B200_API void* wp_b200_nccl_comm_stream(void);
 WP_B200_API int wp_b200_nccl_mark(int k);
 WP_B200_API int wp_b200_nccl_wait_mark(int k);
 WP_B200_API int wp_b200_nccl_fork(void);

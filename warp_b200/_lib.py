@@ -162,6 +162,7 @@ SIGNATURES = {
     "wp_b200_ipc_open_handle": (_vp, [_vp]),
     "wp_b200_ipc_close_handle": (None, [_vp, _vp]),
     "wp_b200_p2p_allgather_multi": (_i, [_vp, _vp, _vp, _vp, _i, _i]),
+    "wp_b200_nccl_comm_stream": (_vp, []),
     "wp_b200_nccl_mark": (_i, [_i]),
     "wp_b200_nccl_wait_mark": (_i, [_i]),
     "wp_b200_nccl_fork": (_i, []),

@@ -106,8 +106,15 @@ int wp_b200_nccl_init(const void* id128, int world_size, int rank)
     if (rc)
         return fail("ncclCommInitRank", rc);
     g_world = world_size;
-    if (!g_comm_stream)
-        cudaStreamCreateWithFlags(&g_comm_stream, cudaStreamNonBlocking);
+    if (!g_comm_stream) {
+        // HIGHEST priority: a kernel on this stream (NCCL's, the 4-byte fences of the peer-memory gather, the ray normals)
+        // must get SM slots while a traversal grid of 131 072 blocks is still being dispatched on the compute stream --
+        // at equal priority the block scheduler serves the earlier launch first and the "overlapped" gather of batch k
+        // only starts in the tail of traversal k + 1 (measured: step = traversal + gather instead of their maximum)
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        cudaStreamCreateWithPriority(&g_comm_stream, cudaStreamNonBlocking, hi);
+    }
     if (!g_fork_event) {
         cudaEventCreateWithFlags(&g_fork_event, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&g_join_event, cudaEventDisableTiming);
@@ -265,7 +272,15 @@ int wp_b200_p2p_allgather_multi(const void* const* send, void* const* own_recv, 
     int rc = p_all_reduce(token, token, 1, kNcclFloat32, kNcclMax, g_comm, g_comm_stream);  // everyone has forked
     if (rc)
         return fail("ncclAllReduce (p2p pre-sync)", rc);
-    bool ok = true;
+    // one stream per peer, so that the pushes to different peers run on different copy engines at the same time
+    // (a single stream serialises them: measured 270 GB/s of NVLink egress per rank instead of what the links allow)
+    constexpr int kPeerStreams = 16;
+    static cudaStream_t peer_stream[kPeerStreams] = {};
+    static cudaEvent_t peer_done[kPeerStreams] = {};
+    static cudaEvent_t go = nullptr;
+    if (!go)
+        cudaEventCreateWithFlags(&go, cudaEventDisableTiming);
+    bool ok = cudaEventRecord(go, g_comm_stream) == cudaSuccess;
     for (int k = 0; k < count && ok; ++k) {
         if (!bytes_per_rank[k])
             continue;
@@ -275,6 +290,14 @@ int wp_b200_p2p_allgather_multi(const void* const* send, void* const* own_recv, 
     // peers in a rotated order, so that at any moment every rank is mostly receiving from a different sender
     for (int step = 1; step < g_world && ok; ++step) {
         const int r = (rank + step) % g_world;
+        const int lane = (step - 1) % kPeerStreams;
+        if (!peer_stream[lane]) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            cudaStreamCreateWithPriority(&peer_stream[lane], cudaStreamNonBlocking, hi);
+            cudaEventCreateWithFlags(&peer_done[lane], cudaEventDisableTiming);
+        }
+        ok = cudaStreamWaitEvent(peer_stream[lane], go, 0) == cudaSuccess;
         for (int k = 0; k < count && ok; ++k) {
             if (!bytes_per_rank[k])
                 continue;
@@ -282,8 +305,10 @@ int wp_b200_p2p_allgather_multi(const void* const* send, void* const* own_recv, 
             if (!dst)
                 return fail("p2p_allgather (peer buffer not mapped)", 0);
             ok = cudaMemcpyAsync(dst + (size_t)rank * bytes_per_rank[k], send[k], bytes_per_rank[k], cudaMemcpyDeviceToDevice,
-                                 g_comm_stream) == cudaSuccess;
+                                 peer_stream[lane]) == cudaSuccess;
         }
+        ok = ok && cudaEventRecord(peer_done[lane], peer_stream[lane]) == cudaSuccess
+            && cudaStreamWaitEvent(g_comm_stream, peer_done[lane], 0) == cudaSuccess;
     }
     if (!ok) {
         cudaGetLastError();
@@ -292,6 +317,10 @@ int wp_b200_p2p_allgather_multi(const void* const* send, void* const* own_recv, 
     rc = p_all_reduce(token + 1, token + 1, 1, kNcclFloat32, kNcclMax, g_comm, g_comm_stream);  // everyone has pushed
     return rc ? fail("ncclAllReduce (p2p post-sync)", rc) : 1;
 }
+
+// the library's communication stream (created by wp_b200_nccl_init): callers that want a kernel of theirs to run in
+// communication order (e.g. the ray normals recomputed from gathered faces) make it current around the launch
+void* wp_b200_nccl_comm_stream(void) { return g_comm_stream; }
 
 int wp_b200_nccl_fork(void)
 {

@@ -139,6 +139,10 @@ class NcclCommunicator:
         if not _lib.core().wp_b200_p2p_allgather_multi(send, own, peer_map.table, nb, k, self.rank):
             raise RuntimeError("peer-memory all-gather failed")
 
+    def on_comm_stream(self):
+        """Context manager: the library's communication stream is the device's current stream inside the block."""
+        return _CommStreamScope()
+
     def mark(self, k: int):
         if not _lib.core().wp_b200_nccl_mark(int(k)):
             raise RuntimeError("NCCL mark failed")
@@ -165,6 +169,18 @@ class NcclCommunicator:
 
     def close(self):
         _lib.core().wp_b200_nccl_destroy()
+
+
+class _CommStreamScope:
+    def __enter__(self):
+        c = _lib.core()
+        self.saved = c.wp_cuda_context_get_stream(None)
+        c.wp_cuda_context_set_stream(None, c.wp_b200_nccl_comm_stream(), 0)
+        return self
+
+    def __exit__(self, *exc):
+        _lib.core().wp_cuda_context_set_stream(None, self.saved, 0)
+        return False
 
 
 class PeerMap:
@@ -397,8 +413,14 @@ class QueryPipeline:
 
         self.mesh, self.plan, self.comm, self.kind, self.max_dist, self.depth = mesh, plan, comm, kind, float(max_dist), depth
         dev, n = mesh.device, plan.shard
+        transport = os.environ.get("WARP_B200_GATHER", "p2p") if (comm is not None and hasattr(comm, "map_peers")) else "nccl"
         if kind == "ray":
-            self.wire = RAY_WIRE_FIELDS
+            # the 12-byte normal: sent with the other fields when the gather runs on copy engines (peer-memory pushes cost
+            # no SM time; measured at 8 GPUs: recomputing 134 M normals per step takes ~5 ms of SM / HBM time on every rank,
+            # sending them 2 ms more of NVLink time that hides under the traversal), recomputed from the gathered
+            # (result, face) when the gather is an SM-driven NCCL launch.  WARP_B200_RAY_WIRE=all / faces overrides.
+            wire = os.environ.get("WARP_B200_RAY_WIRE", "all" if transport == "p2p" else "faces")
+            self.wire = RAY_WIRE_FIELDS + (("normal",) if wire == "all" else ())
             mk = lambda cnt: MeshQueryRay(empty(cnt, uint8, dev), empty(cnt, float32, dev), empty(cnt, int32, dev),  # noqa: E731
                                           empty(cnt, float32, dev), empty(cnt, float32, dev), empty(cnt, float32, dev),
                                           empty(cnt, vec3, dev))
@@ -411,7 +433,7 @@ class QueryPipeline:
         self.submitted = 0
         # transport of the gather: "p2p" = every rank pushes its shard into the peers' buffers with copy-engine memcpys
         # over NVLink (no SM taken from the traversal it runs under), "nccl" = one grouped ncclAllGather launch
-        self.transport = os.environ.get("WARP_B200_GATHER", "p2p") if (comm is not None and hasattr(comm, "map_peers")) else "nccl"
+        self.transport = transport
         self.peers = None
         if comm is not None and self.transport == "p2p":
             try:
@@ -440,17 +462,23 @@ class QueryPipeline:
             else:
                 self.comm.allgather_multi([(getattr(self.local[slot], f), getattr(self.gathered[slot], f),
                                             self.plan.shard * FIELD_BYTES[f]) for f in self.wire], comm_stream=True)
+            if self.kind == "ray" and "normal" not in self.wire and hasattr(self.comm, "on_comm_stream"):
+                # the normals of ALL ranks' rays, recomputed from the gathered (result, face) on this rank's replica --
+                # in communication order, so that they too run under the next batch's traversal
+                g = self.gathered[slot]
+                with self.comm.on_comm_stream():
+                    ray_normals_from_faces(self.mesh, g.result, g.face, g.normal)
             self.comm.mark(slot)
         self.submitted += 1
         return k
 
     def result(self, k: int):
-        """Result set of batch ``k`` (valid for the last ``depth`` batches), ordered after its gather on the compute
-        stream; for rays the normals of the gathered set are recomputed here."""
+        """Result set of batch ``k`` (valid for the last ``depth`` batches), ordered after its gather (and, for rays, the
+        recomputation of the normals) on the compute stream."""
         slot = k % self.depth
         if self.comm is not None:
             self.comm.wait_mark(slot)
-            if self.kind == "ray":
+            if self.kind == "ray" and "normal" not in self.wire and not hasattr(self.comm, "on_comm_stream"):
                 g = self.gathered[slot]
                 ray_normals_from_faces(self.mesh, g.result, g.face, g.normal)
         return self.gathered[slot]
