@@ -337,7 +337,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the side measurements (build/refit, rays, cloth, C5, reference CUDA)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cloth-frames", type=int, default=1000)
-    ap.add_argument("--skip", default="", help="comma list of side measurements to skip: c3,c4,c5,refcuda,parity")
+    ap.add_argument("--skip", default="", help="comma list of side measurements to skip: c3,c4,c5,refcuda,parity,quality")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -551,6 +551,35 @@ def side_measurements(wp, core, mg, dev, stream, mesh, pts, P, I, peak_gbs, rank
         del qs, s_out
     except Exception as e:  # noqa: BLE001
         out["signed"] = {"error": repr(e)}
+
+    # ---- tree quality: the same C2 queries on a SAH / median tree of the same mesh (host constructors) ---
+    if "quality" not in skip:
+        try:
+            nqq = 1 << 22
+            qq = wp.array(mg.box_queries(P, nqq, seed=2), dtype=wp.vec3, device=dev)
+            q_out = wp.MeshQueryPoint(*(wp.empty(nqq, dt, dev) for dt in (wp.uint8, wp.float32, wp.int32, wp.float32, wp.float32)))
+            tq = {"workload": "C2 mesh, 4 194 304 of the C2 queries; constructors sah / median build on the host and upload (bvh.cpp:216-572)"}
+            for ctor in ("lbvh", "sah", "median"):
+                sync()
+                t0 = time.perf_counter()
+                mq = mesh if ctor == "lbvh" else wp.Mesh(pts, idx_d, bvh_constructor=ctor)
+                sync()
+                build_ms = 1e3 * (time.perf_counter() - t0)
+                run_q = lambda: wp.mesh_query_point_no_sign(mq, qq, MAX_DIST, out=q_out)  # noqa: E731
+                run_q()
+                ms = statistics.median([event_ms(core, run_q, stream) for _ in range(3)])
+                with wp.query_stats() as st:
+                    run_q()
+                    sync()
+                tq[ctor] = {"queries_per_s": nqq / (ms * 1e-3), "pair_fetches_per_query": st.pair_fetches / nqq,
+                            "tri_fetches_per_query": st.tri_fetches / nqq,
+                            "constructor_ms": out["build_ms_constructor"] if ctor == "lbvh" else build_ms}  # fmt: skip
+                if ctor != "lbvh":
+                    del mq
+            out["tree_quality"] = tq
+            del qq, q_out
+        except Exception as e:  # noqa: BLE001
+            out["tree_quality"] = {"error": repr(e)}
 
     # ---- C3: 10 M-triangle heightfield, 4096 x 4096 primary rays -------------------------------------
     if "c3" not in skip:

@@ -177,10 +177,12 @@ def test_native_failure_raises_with_error_string(wp):
     """warp/tests/geometry/test_mesh.py:443-485: id 0 -> RuntimeError carrying wp_get_error_string()."""
     P, I = mg.CUBE_POINTS, mg.CUBE_INDICES_RH
     with pytest.raises(RuntimeError, match="Failed to create mesh: .*constructor"):
-        gpu_mesh_sah = wp.Mesh(wp.array(P, dtype=wp.vec3), wp.array(I, dtype=wp.int32), bvh_constructor="sah")  # noqa: F841
+        gpu_mesh_cubql = wp.Mesh(wp.array(P, dtype=wp.vec3), wp.array(I, dtype=wp.int32), bvh_constructor="cubql")  # noqa: F841
     lo, hi = random_boxes(4)
     with pytest.raises(RuntimeError, match="Failed to create BVH"):
-        wp.Bvh(wp.array(lo, dtype=wp.vec3), wp.array(hi, dtype=wp.vec3), constructor="median")
+        wp.Bvh(wp.array(lo, dtype=wp.vec3), wp.array(hi, dtype=wp.vec3), constructor="cubql")
+    with pytest.raises(RuntimeError, match="Failed to create BVH: .*grouped"):  # host constructors take ungrouped items only
+        wp.Bvh(wp.array(lo, dtype=wp.vec3), wp.array(hi, dtype=wp.vec3), constructor="median", groups=wp.array(np.zeros(4, np.int32), dtype=wp.int32))
 
 
 REF_GOLD = os.path.join(os.path.dirname(__file__), "golden", "golden_ref_lbvh.npz")

@@ -21,7 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libwarp_b200.so")
-SOURCES = ["api.cu", "bvh_build.cu", "bvh_refit.cu", "query.cu", "bvh_query.cu", "nccl_gather.cu", "workload.cu"]
+SOURCES = ["api.cu", "bvh_build.cu", "bvh_refit.cu", "query.cu", "bvh_query.cu", "nccl_gather.cu", "workload.cu", "host_build.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v", "--expt-relaxed-constexpr",

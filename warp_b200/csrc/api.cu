@@ -241,14 +241,25 @@ bool upload_desc(MeshState* ms, BvhState* bs)
                  "descriptor upload");
 }
 
-bool constructor_supported(int constructor_type)
+bool constructor_supported(int constructor_type, const int* groups)
 {
     if (constructor_type == WP_BVH_CONSTRUCTOR_LBVH)
         return true;
-    set_error("Warp error: BVH constructor %d is not available in the B200 library: it builds on the GPU only "
-              "(constructor 'lbvh' = %d); the reference's host builders (sah/median) and cuBQL are out of scope",
-              constructor_type, WP_BVH_CONSTRUCTOR_LBVH);
+    if (constructor_type == 0 || constructor_type == 1) {  // sah / median: built on the host, uploaded (host_build.cu)
+        if (!groups)
+            return true;
+        set_error("Warp error: grouped trees are built with constructor 'lbvh' (%d) in the B200 library; the host "
+                  "constructors (sah / median) take ungrouped items only", WP_BVH_CONSTRUCTOR_LBVH);
+        return false;
+    }
+    set_error("Warp error: BVH constructor %d is not available in the B200 library (lbvh = %d, sah = 0, median = 1; "
+              "cuBQL is out of scope)", constructor_type, WP_BVH_CONSTRUCTOR_LBVH);
     return false;
+}
+
+const char* build_tree(BvhState& s, cudaStream_t stream)
+{
+    return s.constructor_type == WP_BVH_CONSTRUCTOR_LBVH ? wb_build(s, stream) : wb_build_host(s, stream);
 }
 
 TreeView make_view(const BvhState& s)
@@ -689,7 +700,7 @@ uint64_t wp_b200_bvh_create_device_ex(void* context, wp_vec3* lowers, wp_vec3* u
                                       int* groups, int leaf_size, int morton_bits)
 {
     g_error[0] = 0;  // the drop-in stub reads this library's message only when the last routed call failed
-    if (!constructor_supported(constructor_type))
+    if (!constructor_supported(constructor_type, groups))
         return 0;
     if (morton_bits == 0)
         morton_bits = g_morton_bits;
@@ -710,12 +721,13 @@ uint64_t wp_b200_bvh_create_device_ex(void* context, wp_vec3* lowers, wp_vec3* u
     BvhState* s = new BvhState();
     s->n = num_items, s->leaf_size = leaf_size, s->constructor_type = constructor_type, s->device = dev;
     s->context = context ? context : device_primary_context(dev);
-    s->morton_bits = morton_bits, s->auto_reference_layout = g_auto_reference_layout;
+    s->morton_bits = morton_bits;
+    s->auto_reference_layout = constructor_type == WP_BVH_CONSTRUCTOR_LBVH ? g_auto_reference_layout : 0;  // no mirror of host-built trees
     s->key_bytes = (groups || morton_bits == 63) ? 8 : 4;
     s->item_lowers = (const float*)lowers, s->item_uppers = (const float*)uppers, s->groups = groups;
     const char* err = num_items > 0 ? wb_alloc_tree(*s, current_stream(dev)) : nullptr;
     if (!err)
-        err = wb_build(*s, current_stream(dev));
+        err = build_tree(*s, current_stream(dev));
     if (err || !check(cudaMalloc(&s->dev_desc, sizeof(wp_b200_bvh_desc)), "descriptor alloc") || !upload_desc(nullptr, s)
         || (s->auto_reference_layout && !sync_reference_layout(s, nullptr))) {
         if (err)
@@ -799,7 +811,7 @@ uint64_t wp_b200_mesh_create_device_ex(void* context, wp_array_t points, wp_arra
                                        int* groups, int bvh_leaf_size, int morton_bits)
 {
     g_error[0] = 0;  // the drop-in stub reads this library's message only when the last routed call failed
-    if (!constructor_supported(constructor_type))
+    if (!constructor_supported(constructor_type, groups))
         return 0;
     if (morton_bits == 0)
         morton_bits = g_morton_bits;
@@ -831,12 +843,13 @@ uint64_t wp_b200_mesh_create_device_ex(void* context, wp_array_t points, wp_arra
     s.is_mesh = true;
     s.groups = groups;
     s.context = context ? context : device_primary_context(dev);
-    s.morton_bits = morton_bits, s.auto_reference_layout = g_auto_reference_layout;
+    s.morton_bits = morton_bits;
+    s.auto_reference_layout = constructor_type == WP_BVH_CONSTRUCTOR_LBVH ? g_auto_reference_layout : 0;  // no mirror of host-built trees
     s.key_bytes = (groups || morton_bits == 63) ? 8 : 4;
     s.points = (const float*)points.data, s.indices = (const int*)tris.data, s.num_points = num_points;
     const char* err = num_tris > 0 ? wb_alloc_tree(s, current_stream(dev)) : nullptr;
     if (!err)
-        err = wb_build(s, current_stream(dev));
+        err = build_tree(s, current_stream(dev));
     if (err || !check(cudaMalloc(&m->dev_desc, sizeof(wp_b200_mesh_desc)), "descriptor alloc") || !upload_desc(m, nullptr)
         || (s.auto_reference_layout && !sync_reference_layout(&s, m))) {
         if (err)
@@ -1676,6 +1689,11 @@ int wp_b200_exclusive_scan_i32(const int32_t* counts, int32_t* offsets, int64_t 
 // ------------------------------------------------------------------------------------------------
 static int sync_reference_layout(BvhState* s, MeshState* m)
 {
+    if (s->host_built) {
+        set_error("Warp error: the reference-layout mirror is not available for trees of the host constructors (sah / median): "
+                  "their nodes are not numbered like the reference's (host_build.cu)");
+        return 0;
+    }
     const bool first = s->ref_lowers == nullptr;
     const char* err = wb_export_reference_layout(*s, current_stream(s->device));
     if (err) {
@@ -1773,9 +1791,14 @@ float wp_b200_experiment_parallel_topology(uint64_t id, int32_t* parents_out, in
 int wp_b200_bvh_download(uint64_t id, void* keys, int32_t* primitive_indices, void* node_lowers, void* node_uppers,
                          int32_t* node_parents, int32_t* root)
 {
-    if (!wp_b200_bvh_sync_reference_layout(id))
+    const bool want_nodes = node_lowers || node_uppers || node_parents || root;
+    if (want_nodes && !wp_b200_bvh_sync_reference_layout(id))  // (keys / primitive_indices alone need no mirror)
         return 0;
     BvhState* s = find_tree(id);
+    if (!s) {
+        set_error("Warp error: invalid id");
+        return 0;
+    }
     if (s->n == 0)
         return 1;
     DeviceGuard g(s->device);

@@ -1122,6 +1122,7 @@ const char* wb_build(BvhState& s, cudaStream_t stream)
 {
     if (s.n <= 0)
         return nullptr;
+    s.host_built = false;  // an in-place rebuild is always an LBVH (bvh.cu:819-843), whatever built the tree first
     if (s.is_mesh)
         return build_dispatch(s, MeshSource { s.points, s.indices }, stream);
     return build_dispatch(s, BoxSource { s.item_lowers, s.item_uppers }, stream);

@@ -238,7 +238,8 @@ const char* wb_refit(BvhState& s, cudaStream_t stream)
     static const int env_mode = !mode_env ? 0 : (strcmp(mode_env, "atomic") == 0 ? 1 : 2);
     const int base_mode = s.refit_mode >= 0 ? s.refit_mode : g_wb_refit_mode;
     const int mode = base_mode ? base_mode : env_mode;
-    const bool wave = s.n >= 2 && s.n < (1 << 30) && (mode == 0 ? s.n >= (1 << 21) : mode == 2);
+    // (a host-built tree has no heights / key ranges for the plan: it always takes the counter climb)
+    const bool wave = !s.host_built && s.n >= 2 && s.n < (1 << 30) && (mode == 0 ? s.n >= (1 << 21) : mode == 2);
     if (wave && !s.plan_valid)
         if (const char* e = wb_refit_plan(s, stream))
             return e;

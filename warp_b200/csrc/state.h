@@ -10,6 +10,7 @@ struct BvhState {
     int leaf_size = 1;
     int constructor_type = 2;
     bool is_mesh = false;
+    bool host_built = false;  // topology from a host constructor (host_build.cu): no keys, no reference numbering, no refit plan
     int device = 0;
     void* context = nullptr;  // the CUcontext (or ordinal token) the creator passed; echoed in the descriptor
 
@@ -99,6 +100,7 @@ struct MeshState {
 
 // build / refit / export drivers (bvh_build.cu, bvh_refit.cu); all enqueue on `stream`
 const char* wb_build(BvhState& s, cudaStream_t stream);
+const char* wb_build_host(BvhState& s, cudaStream_t stream);  // constructor_type 0 (sah) / 1 (median), host_build.cu
 const char* wb_refit(BvhState& s, cudaStream_t stream);
 extern int g_wb_small_nodes;  // experiment switch of the builder's Karras-style small-node pass (bvh_build.cu)
 extern int g_wb_refit_mode;  // default refit mode of new trees: 0 auto, 1 atomic counters, 2 wavefront

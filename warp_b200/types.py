@@ -580,6 +580,14 @@ class Mesh(_Options):
     def download_tree(self):
         return _download_tree(self.id, int(self.indices.size // 3))
 
+    def download_primitive_indices(self):
+        """``bvh.primitive_indices`` (sorted position -> face); also available for sah / median trees."""
+        n = int(self.indices.size // 3)
+        out = np.zeros(n, np.int32)
+        if n and not _lib.core().wp_b200_bvh_download(self.id, None, out.ctypes.data, None, None, None, None):
+            raise RuntimeError(_lib.error_string())
+        return out
+
 
 HALF_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("ib", "<u4")])
 
