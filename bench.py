@@ -745,7 +745,8 @@ def cloth_loop(wp, core, mg, workload, dev, stream, frames, peak_gbs):
             "refit_ms": refit_ms, "refit_frac_of_hbm_roofline": 189 * T / (refit_ms * 1e-3) / 1e9 / peak_gbs,
             "found_fraction": found_fraction, "with_periodic_rebuild": rebuilt,
             "note": "refit-only frames slow down as the cloth leaves the pose the tree was built in (frame 1 ~41 ms, plateau ~54 ms): "
-                    "the Morton order of frame 0 no longer matches the geometry; an in-place rebuild (0.85 ms) every 32 frames restores it"}  # fmt: skip
+                    "the Morton order of frame 0 no longer matches the geometry; frame time also varies with the wave's phase. "
+                    "with_periodic_rebuild = the same loop with an in-place rebuild (0.85 ms) every 32 frames"}  # fmt: skip
 
 
 class _Null:

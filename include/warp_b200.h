@@ -154,6 +154,7 @@ WP_B200_API int wp_memcpy_d2d(void* context, void* dest, void* src, size_t n, vo
 WP_B200_API int wp_memset_device(void* context, void* dest, int value, size_t n, void* stream);
 /* device-wide query used by bench.py (L2 size, SM count, clocks, free memory) */
 WP_B200_API int wp_b200_device_attr(int ordinal, const char* name, long long* value);
+WP_B200_API int wp_b200_pointer_device(const void* ptr, long long* ordinal); /* which device owns a device pointer */
 WP_B200_API int wp_b200_device_name(int ordinal, char* buf, int len);
 
 /* ---------------------------------------------------------------------------------------------

@@ -91,6 +91,7 @@ SIGNATURES = {
     "wp_memcpy_d2d": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "wp_memset_device": (_i, [_vp, _vp, _i, _sz, _vp]),
     "wp_b200_device_attr": (_i, [_i, ctypes.c_char_p, ctypes.POINTER(ctypes.c_longlong)]),
+    "wp_b200_pointer_device": (_i, [_vp, ctypes.POINTER(ctypes.c_longlong)]),
     "wp_b200_device_name": (_i, [_i, ctypes.c_char_p, _i]),
     # part 3: batched queries
     "wp_b200_mesh_query_point_no_sign": (_i, [_u64, _vp, _i64, _f, _vp, _vp, _vp, _vp]),

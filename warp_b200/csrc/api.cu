@@ -676,6 +676,18 @@ int wp_b200_device_attr(int ordinal, const char* name, long long* value)
     return check(e, "device attribute");
 }
 
+// device ordinal that owns a device pointer (cudaPointerGetAttributes); 0 when the pointer is not device memory
+int wp_b200_pointer_device(const void* ptr, long long* ordinal)
+{
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess || (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)) {
+        cudaGetLastError();
+        return 0;
+    }
+    *ordinal = attr.device;
+    return 1;
+}
+
 int wp_b200_device_name(int ordinal, char* buf, int len)
 {
     cudaDeviceProp p;

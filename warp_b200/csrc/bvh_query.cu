@@ -338,7 +338,10 @@ k_group_roots(TreeView tv, const uint64_t* __restrict__ keys, const int* __restr
             // parent of leaf `first`: the same rule the builder applied (merge.cuh)
             const bool gr = keys ? wb_goes_right<uint64_t, true>(keys, tv.prim, n, first, first) : true;
             int s = gr ? first : first - 1;
-            for (int guard = 0; guard < 4096; ++guard) {
+            // (bounded by the tree height -- the climb ends at the root at the latest; a tall subtree of many equal keys
+            // is a legitimate input, so no constant cap)
+            const int max_hops = h.height >= (int)WB_HEIGHT_CAP ? n : h.height + 1;  // a capped height says nothing: n bounds any climb
+            for (int guard = 0; guard <= max_hops; ++guard) {
                 const int l = (int)tv.pairs[2 * (size_t)s].aux, r = (int)tv.pairs[2 * (size_t)s + 1].aux;
                 if (l <= first && r >= last) {
                     root = n + s;

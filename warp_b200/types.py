@@ -149,8 +149,13 @@ class array:
                     raise RuntimeError(f"cannot view shape {shp} {npdt} as {dt}")
                 shp = shp[:-1]
             self.dtype, self.shape = dt, shp
-            self.device = get_device(device)
             self.ptr = int(cai["data"][0])
+            if device is None and self.ptr:
+                # the buffer says where it lives; labelling a cuda:1 pointer cuda:0 would send kernels to the wrong device
+                ordinal = ctypes.c_longlong(-1)
+                if _lib.core().wp_b200_pointer_device(ctypes.c_void_p(self.ptr), ctypes.byref(ordinal)) and ordinal.value >= 0:
+                    device = f"cuda:{ordinal.value}"
+            self.device = get_device(device)
             self.owner = data
             return
         self.device = get_device(device)
