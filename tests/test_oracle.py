@@ -234,7 +234,10 @@ def test_queries_vs_reference_cuda_kernels(oracle_mod, ref_gold, name):
         assert np.allclose(a["u"][same], r["u"][same], rtol=0, atol=1e-5)
         assert np.allclose(a["v"][same], r["v"][same], rtol=0, atol=1e-5)
         ties = int((~same).sum())
-        assert ties <= len(Q) // 8, ties
+        # measured on these fixtures (256 queries each): cube 0 / 0, ico2 19 / 19, height33 15 / 21 for leaf 1 / 4 -- the
+        # counts are a property of the fixtures and of the two builds' rounding, so they are pinned, with a margin of 2
+        measured = {("cube", 1): 0, ("cube", 4): 0, ("ico2", 1): 19, ("ico2", 4): 19, ("height33", 1): 15, ("height33", 4): 21}
+        assert ties <= measured[(name, leaf)] + 2, (name, leaf, ties)
         pa, pr = pos(a["face"], a["u"], a["v"]), pos(r["face"], r["u"], r["v"])
         assert np.abs(pa - pr).max() < 1e-5, "differing faces must still be the same closest point"
         b = oracle_mod.query_ray(P, I, t, S, D, 1e6)
