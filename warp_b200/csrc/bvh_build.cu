@@ -727,6 +727,9 @@ __device__ __forceinline__ bool depth_marked(const KeyT* __restrict__ keys, cons
 // known -- a tall node is at most DEEP_TOP_HEIGHT hops away -- and records its own result for the walks below it.
 // Racing readers see either 0 or the final value, so the outcome does not depend on timing.
 constexpr int DEEP_TOP_HEIGHT = 6;
+#ifndef WB_DEEP_BFS_MIN
+#define WB_DEEP_BFS_MIN (1 << 24)
+#endif
 
 __device__ __forceinline__ int depth_memo(const int* __restrict__ parent_int, const uint8_t* memo, int n, int slot)
 {
@@ -813,6 +816,78 @@ k_deep_fix(int n, int leaf_size, TreeHeader* hdr, const KeyT* __restrict__ keys,
         const int l = __shfl_sync(0xffffffffu, left, src), r = __shfl_sync(0xffffffffu, right, src);
         for (int p = l + 1 + lane; p <= r; p += 32)
             pos_parent[p] = WB_NO_PARENT;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5': the same rule for LARGE ungrouped trees, top-down.  The memoised walks above touch every node; on a 100 M-triangle
+// mesh with 30-bit keys (1 M runs of ~100 equal keys, each a comb ~50 deep) that is 10 ms of a 27 ms build.  But only nodes
+// at depth <= 32 matter: the node that becomes a depth-rule leaf is exactly a non-leaf node AT depth 32 (its parent, at
+// depth 31, is unmarked), and nothing below it is ever looked at.  So: a breadth-first sweep from the root, one launch
+// per level, 31 levels, each reading the 64-byte pair record of the frontier's nodes and appending their non-leaf
+// children; at level 32 the children are marked instead.  Nodes deeper than 32 are never touched.  Queues: the sort's
+// two spare buffers.  (Grouped trees keep the walks: a node that spans groups is not marked whatever its depth, so the
+// topmost marked node can sit below depth 32.)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_bfs_start(int n, const TreeHeader* __restrict__ hdr, int* __restrict__ queue, int* __restrict__ counts)
+{
+    // counts[d] = number of nodes at depth d in the frontier (depth 1 = the root)
+    for (int k = threadIdx.x; k < 40; k += blockDim.x)
+        counts[k] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0 && hdr->height + 1 >= WB_MAX_DEPTH && !(hdr->root_ref & WB_LEAF)) {
+        queue[0] = (int)(hdr->root_ref & WB_IDX_MASK) - n;
+        counts[1] = 1;
+    }
+}
+
+// frontier of depth `depth` (slots in `in`) -> its non-leaf children at depth + 1 (slots in `out`), or, when the
+// children sit at depth 32, the depth-rule leaves
+__global__ void __launch_bounds__(BT)
+k_bfs_level(int n, int depth, TreeHeader* hdr, const int* __restrict__ in, int* __restrict__ out, int* __restrict__ counts,
+            NodeRec* pairs, int* pos_parent)
+{
+    const int m = counts[depth];
+    const int lane = (int)(threadIdx.x & 31);
+    const bool last = depth + 1 >= WB_MAX_DEPTH;
+    for (int base = blockIdx.x * BT; base < m; base += gridDim.x * BT) {
+        const int i = base + (int)threadIdx.x;
+        int clear_from[2] = { 0, 0 }, clear_to[2] = { -1, -1 };
+        if (i < m) {
+            const int s = in[i];
+            const float4* p4 = reinterpret_cast<const float4*>(pairs + 2 * (size_t)s);
+            const uint32_t lref = __float_as_uint(p4[0].w), laux = __float_as_uint(p4[1].w);
+            const uint32_t rref = __float_as_uint(p4[2].w), raux = __float_as_uint(p4[3].w);
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                const uint32_t ref = side ? rref : lref;
+                if ((ref & WB_LEAF) || (int)ref < n)
+                    continue;  // a packed leaf (by size) or an original leaf: settled
+                if (!last) {
+                    out[atomicAdd(&counts[depth + 1], 1)] = (int)ref - n;
+                } else {
+                    // depth 32: this child becomes a visible leaf over its whole range
+                    const int left = side ? s + 1 : (int)laux, right = side ? (int)raux : s;
+                    pairs[2 * (size_t)s + side].ref = ref | WB_LEAF;
+                    pos_parent[left] = n + s;
+                    clear_from[side] = left + 1, clear_to[side] = right;
+                    hdr->deep = 1;
+                }
+            }
+        }
+        if (last) {  // the size leaves a marked node swallows lose their entries, 32 positions per step
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                unsigned todo = __ballot_sync(0xffffffffu, clear_to[side] >= clear_from[side] && clear_to[side] >= 0);
+                while (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int a = __shfl_sync(0xffffffffu, clear_from[side], src), b = __shfl_sync(0xffffffffu, clear_to[side], src);
+                    for (int p = a + lane; p <= b; p += 32)
+                        pos_parent[p] = WB_NO_PARENT;
+                }
+            }
+        }
     }
 }
 
@@ -934,6 +1009,17 @@ bool small_nodes_enabled()
     return g_wb_small_nodes >= 0 ? g_wb_small_nodes != 0 : env_on;
 }
 
+// item count from which the depth rule is applied by the top-down sweep (k_bfs_level) instead of the memoised walks;
+// WARP_B200_DEEP_BFS_MIN overrides (0 = always, a huge value = never)
+int deep_bfs_threshold()
+{
+    static const long long t = [] {
+        const char* v = getenv("WARP_B200_DEEP_BFS_MIN");
+        return v ? atoll(v) : (long long)WB_DEEP_BFS_MIN;
+    }();
+    return t > 0x7fffffffll ? 0x7fffffff : (int)t;
+}
+
 bool use_cub_sort()
 {
     const char* v = getenv("WARP_B200_SORT");
@@ -999,6 +1085,19 @@ template <class Src, class KeyT, bool GROUPED> const char* build_impl(BvhState& 
     }
     // K5/K6 depth rule (early-out unless the tree is at least 32 levels deep); the depth table lives in the sort's
     // spare value buffer, free until the next sort
+    if (!GROUPED && n >= deep_bfs_threshold()) {
+        // large ungrouped trees: top-down sweep over the nodes of depth <= 32 only (see k_bfs_level)
+        int* q0 = (int*)keys_alt;
+        int* q1 = s.prim_alt;
+        int* counts = (int*)s.bfs_counts;
+        k_bfs_start<<<1, 64, 0, stream>>>(n, s.header, q0, counts);
+        const int grid = min(148 * 8, wb_div_up(n, BT));  // grid-stride over the frontier
+        for (int depth = 1; depth < WB_MAX_DEPTH; ++depth)
+            k_bfs_level<<<grid, BT, 0, stream>>>(n, depth, s.header, (depth & 1) ? q0 : q1, (depth & 1) ? q1 : q0, counts, s.pairs,
+                                                 s.pos_parent);
+        WB_CUDA_TRY(cudaGetLastError());
+        return nullptr;
+    }
     k_deep_top<<<wb_div_up(n - 1, BT), BT, 0, stream>>>(n, s.header, s.parent_int, s.heights, (uint8_t*)s.prim_alt);
     k_deep_fix<KeyT, GROUPED><<<wb_div_up(n - 1, BT), BT, 0, stream>>>(n, s.leaf_size, s.header, keys, s.parent_int, s.heights,
                                                                       (uint8_t*)s.prim_alt, s.pairs, s.pos_parent);
@@ -1073,7 +1172,7 @@ const char* wb_alloc_tree(BvhState& s, cudaStream_t stream)
     };
     const size_t o_header = take(sizeof(TreeHeader)), o_tickets = take(sizeof(unsigned) * 16),
                  o_ghist = take(sizeof(uint32_t) * 8 * 256), o_partials = take(sizeof(float) * 6 * (size_t)s.bounds_blocks),
-                 o_edge = take(sizeof(double) * 296),
+                 o_edge = take(sizeof(double) * 296), o_bfs = take(sizeof(int) * 64),
                  o_keys = take(kb * n), o_keys_alt = take(kb * n), o_prim = take(4 * n), o_prim_alt = take(4 * n),
                  o_pairs = take(sizeof(NodeRec) * 2 * ni), o_parent = take(4 * ni), o_pos = take(4 * n),
                  o_counters = take(4 * ni), o_tris = take(s.is_mesh ? sizeof(float4) * 3 * n : 0),
@@ -1090,7 +1189,7 @@ const char* wb_alloc_tree(BvhState& s, cudaStream_t stream)
         WB_CUDA_TRY(cudaMalloc(&s.arena, off));
     char* b = (char*)s.arena;
     s.header = (TreeHeader*)(b + o_header), s.tickets = (unsigned*)(b + o_tickets), s.ghist = (uint32_t*)(b + o_ghist);
-    s.partials = (float*)(b + o_partials), s.edge_partials = (double*)(b + o_edge), s.keys = b + o_keys, s.keys_alt = b + o_keys_alt;
+    s.partials = (float*)(b + o_partials), s.edge_partials = (double*)(b + o_edge), s.bfs_counts = (int*)(b + o_bfs), s.keys = b + o_keys, s.keys_alt = b + o_keys_alt;
     s.prim = (int*)(b + o_prim), s.prim_alt = (int*)(b + o_prim_alt), s.pairs = (NodeRec*)(b + o_pairs);
     s.parent_int = (int*)(b + o_parent), s.pos_parent = (int*)(b + o_pos), s.counters = (unsigned*)(b + o_counters);
     s.tris = s.is_mesh ? (float4*)(b + o_tris) : nullptr, s.tile_status = (uint32_t*)(b + o_status);

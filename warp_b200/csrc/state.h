@@ -63,6 +63,7 @@ struct BvhState {
     uint32_t* tile_status = nullptr;  // 4 passes x tiles x 256 look-back words
     unsigned* tickets = nullptr;      // small block of counters (tile tickets, last-block tickets)
     float* partials = nullptr;        // per-block scene-bounds partials
+    int* bfs_counts = nullptr;        // 64 ints: frontier sizes of the top-down depth sweep (bvh_build.cu k_bfs_level)
     double* edge_partials = nullptr;  // 296 doubles: per-block partial sums of the average-edge-length reduction (query.cu)
     void* cub_temp = nullptr;         // only used by the WARP_B200_SORT=cub cross-check path
     size_t cub_temp_bytes = 0;
