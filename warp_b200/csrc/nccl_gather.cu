@@ -8,6 +8,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace {
@@ -113,7 +114,8 @@ int wp_b200_nccl_init(const void* id128, int world_size, int rank)
         // only starts in the tail of traversal k + 1 (measured: step = traversal + gather instead of their maximum)
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        cudaStreamCreateWithPriority(&g_comm_stream, cudaStreamNonBlocking, hi);
+        const char* e = getenv("WARP_B200_COMM_PRIORITY");  // 0 = default priority (A/B)
+        cudaStreamCreateWithPriority(&g_comm_stream, cudaStreamNonBlocking, (e && atoi(e) == 0) ? lo : hi);
     }
     if (!g_fork_event) {
         cudaEventCreateWithFlags(&g_fork_event, cudaEventDisableTiming);
@@ -294,7 +296,8 @@ int wp_b200_p2p_allgather_multi(const void* const* send, void* const* own_recv, 
         if (!peer_stream[lane]) {
             int lo = 0, hi = 0;
             cudaDeviceGetStreamPriorityRange(&lo, &hi);
-            cudaStreamCreateWithPriority(&peer_stream[lane], cudaStreamNonBlocking, hi);
+            const char* e = getenv("WARP_B200_COMM_PRIORITY");
+            cudaStreamCreateWithPriority(&peer_stream[lane], cudaStreamNonBlocking, (e && atoi(e) == 0) ? lo : hi);
             cudaEventCreateWithFlags(&peer_done[lane], cudaEventDisableTiming);
         }
         ok = cudaStreamWaitEvent(peer_stream[lane], go, 0) == cudaSuccess;
