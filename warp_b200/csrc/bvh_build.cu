@@ -88,9 +88,13 @@ __device__ __forceinline__ void block_minmax(float3& lo, float3& hi, float (*sm)
 template <class Src>
 __global__ void __launch_bounds__(BT)
 k_scene_bounds(Src src, int n, float* __restrict__ partials, unsigned* __restrict__ tickets,
-               uint32_t* __restrict__ ghist)
+               uint32_t* __restrict__ ghist, uint4* __restrict__ clear = nullptr, size_t clear_words4 = 0)
 {
     __shared__ float sm[BT / 32][6];
+
+    // the sort's look-back words start from zero: cleared here by all blocks (16 bytes per store) instead of a memset launch
+    for (size_t k = (size_t)blockIdx.x * BT + threadIdx.x; k < clear_words4; k += (size_t)gridDim.x * BT)
+        clear[k] = make_uint4(0u, 0u, 0u, 0u);
 
     if (blockIdx.x == 0) {
         for (int k = threadIdx.x; k < 8 * 256; k += BT)
@@ -508,11 +512,13 @@ void onesweep_sort(KeyT* keys, KeyT* keys_alt, int* vals, int* vals_alt, int n, 
 template <class Src, class KeyT, bool GROUPED>
 __global__ void __launch_bounds__(BT)
 k_leaves(Src src, int n, const KeyT* __restrict__ keys, const int* __restrict__ prim, NodeRec* __restrict__ pairs,
-         int* __restrict__ pos_parent, float4* __restrict__ tris)
+         int* __restrict__ pos_parent, float4* __restrict__ tris, unsigned* __restrict__ counters)
 {
     const int i = blockIdx.x * BT + threadIdx.x;
     if (i >= n)
         return;
+    if (i < n - 1)
+        counters[i] = 0u;  // arrival counter of internal node n + i (merge.cuh)
     const int item = __ldg(prim + i);
     float3 lo, hi;
     if constexpr (Src::kIsMesh) {
@@ -757,10 +763,8 @@ k_deep_top(int n, const TreeHeader* __restrict__ hdr, const int* __restrict__ pa
 {
     if (hdr->height + 1 < WB_MAX_DEPTH)
         return;
-    const int s = blockIdx.x * BT + threadIdx.x;
-    if (s >= n - 1)
-        return;
-    memo[s] = (heights[s] & WB_HEIGHT_MASK) >= DEEP_TOP_HEIGHT ? (uint8_t)depth_memo(parent_int, nullptr, n, s) : (uint8_t)0;
+    for (int s = blockIdx.x * BT + threadIdx.x; s < n - 1; s += gridDim.x * BT)
+        memo[s] = (heights[s] & WB_HEIGHT_MASK) >= DEEP_TOP_HEIGHT ? (uint8_t)depth_memo(parent_int, nullptr, n, s) : (uint8_t)0;
 }
 
 // one thread per internal node.  A node that holds at most leaf_size positions is a size leaf or lies below one: settled
@@ -775,7 +779,8 @@ k_deep_fix(int n, int leaf_size, TreeHeader* hdr, const KeyT* __restrict__ keys,
 {
     if (hdr->height + 1 < WB_MAX_DEPTH)
         return;
-    const int s = blockIdx.x * BT + threadIdx.x;
+    for (int base = blockIdx.x * BT; base < n - 1; base += gridDim.x * BT) {
+    const int s = base + (int)threadIdx.x;
     bool mark = false;  // this node is the topmost one at depth >= 32 of its group
     int left = 0, right = 0;
     if (s < n - 1) {
@@ -817,6 +822,7 @@ k_deep_fix(int n, int leaf_size, TreeHeader* hdr, const KeyT* __restrict__ keys,
         for (int p = l + 1 + lane; p <= r; p += 32)
             pos_parent[p] = WB_NO_PARENT;
     }
+    }  // grid-stride
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1039,12 +1045,11 @@ template <class Src, class KeyT, bool GROUPED> const char* build_impl(BvhState& 
         return nullptr;
     }
 
-    // K1 scene bounds (+ clears histograms / tickets)
-    k_scene_bounds<<<s.bounds_blocks, BT, 0, stream>>>(src, n, s.partials, s.tickets, s.ghist);
-    // look-back words and arrival counters start from zero
+    // K1 scene bounds (+ clears histograms / tickets and the sort's look-back words; the arrival counters are cleared by
+    // the leaf pass -- two memset launches less)
     const int sort_tiles = wb_div_up(n, rs_tile_for(n, (int)sizeof(KeyT)));  // what onesweep_sort will use (<= s.num_tiles)
-    WB_CUDA_TRY(cudaMemsetAsync(s.tile_status, 0, sizeof(uint32_t) * 256 * PASSES * (size_t)sort_tiles, stream));
-    WB_CUDA_TRY(cudaMemsetAsync(s.counters, 0, sizeof(unsigned) * (size_t)(n - 1), stream));
+    k_scene_bounds<<<s.bounds_blocks, BT, 0, stream>>>(src, n, s.partials, s.tickets, s.ghist, (uint4*)s.tile_status,
+                                                       (size_t)64 * PASSES * (size_t)sort_tiles);
     // K2 Morton keys + histograms
     k_morton_hist<Src, KeyT, GROUPED><<<s.bounds_blocks, BT, 0, stream>>>(src, n, s.partials, s.bounds_blocks, s.header,
                                                                          s.groups, keys, s.ghist);
@@ -1069,7 +1074,7 @@ template <class Src, class KeyT, bool GROUPED> const char* build_impl(BvhState& 
     }
 
     // K4a leaves, K4b chunked bottom-up merge
-    k_leaves<Src, KeyT, GROUPED><<<wb_div_up(n, BT), BT, 0, stream>>>(src, n, keys, s.prim, s.pairs, s.pos_parent, s.tris);
+    k_leaves<Src, KeyT, GROUPED><<<wb_div_up(n, BT), BT, 0, stream>>>(src, n, keys, s.prim, s.pairs, s.pos_parent, s.tris, s.counters);
     {
         // K4b small distinct-key nodes, one thread per split (unit[] lives in the sort's spare value buffer, free until the
         // depth pass reuses it); K4c merges what is left, starting from the tops of the finished subtrees
@@ -1099,9 +1104,10 @@ template <class Src, class KeyT, bool GROUPED> const char* build_impl(BvhState& 
         WB_CUDA_TRY(cudaGetLastError());
         return nullptr;
     }
-    k_deep_top<<<wb_div_up(n - 1, BT), BT, 0, stream>>>(n, s.header, s.parent_int, s.heights, (uint8_t*)s.prim_alt);
-    k_deep_fix<KeyT, GROUPED><<<wb_div_up(n - 1, BT), BT, 0, stream>>>(n, s.leaf_size, s.header, keys, s.parent_int, s.heights,
-                                                                      (uint8_t*)s.prim_alt, s.pairs, s.pos_parent);
+    const int deep_grid = min(148 * 8, wb_div_up(n - 1, BT));  // grid-stride: the usual early-out costs ~1000 blocks, not n / 256
+    k_deep_top<<<deep_grid, BT, 0, stream>>>(n, s.header, s.parent_int, s.heights, (uint8_t*)s.prim_alt);
+    k_deep_fix<KeyT, GROUPED><<<deep_grid, BT, 0, stream>>>(n, s.leaf_size, s.header, keys, s.parent_int, s.heights,
+                                                            (uint8_t*)s.prim_alt, s.pairs, s.pos_parent);
     wb_chunk_boxes(s, stream);
     WB_CUDA_TRY(cudaGetLastError());
     return nullptr;
