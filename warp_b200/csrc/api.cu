@@ -271,7 +271,6 @@ TreeView make_view(const BvhState& s)
     tv.prim = s.prim;
     tv.parent_int = s.parent_int;
     tv.pos_parent = s.pos_parent;
-    tv.chunks = s.chunks;
     tv.n = s.n;
     return tv;
 }

@@ -1100,7 +1100,6 @@ template <class Src, class KeyT, bool GROUPED> const char* build_impl(BvhState& 
         for (int depth = 1; depth < WB_MAX_DEPTH; ++depth)
             k_bfs_level<<<grid, BT, 0, stream>>>(n, depth, s.header, (depth & 1) ? q0 : q1, (depth & 1) ? q1 : q0, counts, s.pairs,
                                                  s.pos_parent);
-        wb_chunk_boxes(s, stream);
         WB_CUDA_TRY(cudaGetLastError());
         return nullptr;
     }
@@ -1108,7 +1107,6 @@ template <class Src, class KeyT, bool GROUPED> const char* build_impl(BvhState& 
     k_deep_top<<<deep_grid, BT, 0, stream>>>(n, s.header, s.parent_int, s.heights, (uint8_t*)s.prim_alt);
     k_deep_fix<KeyT, GROUPED><<<deep_grid, BT, 0, stream>>>(n, s.leaf_size, s.header, keys, s.parent_int, s.heights,
                                                             (uint8_t*)s.prim_alt, s.pairs, s.pos_parent);
-    wb_chunk_boxes(s, stream);
     WB_CUDA_TRY(cudaGetLastError());
     return nullptr;
 }
@@ -1184,7 +1182,6 @@ const char* wb_alloc_tree(BvhState& s, cudaStream_t stream)
                  o_keys = take(kb * n), o_keys_alt = take(kb * n), o_prim = take(4 * n), o_prim_alt = take(4 * n),
                  o_pairs = take(sizeof(NodeRec) * 2 * ni), o_parent = take(4 * ni), o_pos = take(4 * n),
                  o_counters = take(4 * ni), o_tris = take(s.is_mesh ? sizeof(float4) * 3 * n : 0),
-                 o_chunks = take(s.is_mesh ? sizeof(float4) * 2 * (n / 4 + 2) : 0),
                  o_status = take(sizeof(uint32_t) * 256 * kb * (size_t)s.num_tiles), o_heights = take(2 * ni),
                  o_pkeys = take(4 * ni), o_pnodes = take(4 * ni), o_pdst = take(4 * ni),
                  o_pbegin = take(4 * (size_t)wb_div_up((long long)n, WB_WAVE_BP)),
@@ -1202,7 +1199,6 @@ const char* wb_alloc_tree(BvhState& s, cudaStream_t stream)
     s.prim = (int*)(b + o_prim), s.prim_alt = (int*)(b + o_prim_alt), s.pairs = (NodeRec*)(b + o_pairs);
     s.parent_int = (int*)(b + o_parent), s.pos_parent = (int*)(b + o_pos), s.counters = (unsigned*)(b + o_counters);
     s.tris = s.is_mesh ? (float4*)(b + o_tris) : nullptr, s.tile_status = (uint32_t*)(b + o_status);
-    s.chunks = s.is_mesh ? (float4*)(b + o_chunks) : nullptr;
     s.heights = (uint16_t*)(b + o_heights), s.plan_keys = (uint32_t*)(b + o_pkeys), s.plan_nodes = (int*)(b + o_pnodes);
     s.plan_dst = (uint32_t*)(b + o_pdst), s.plan_begin = (int*)(b + o_pbegin), s.plan_end = (int*)(b + o_pend);
     s.unit_flags = (uint8_t*)(b + o_uflags), s.plan_top = (uint32_t*)(b + o_ptop), s.plan_ntop = (int*)(b + o_pntop);

@@ -218,59 +218,7 @@ k_refit_climb(MergeArgs<uint32_t> a, const uint32_t* __restrict__ top, const int
     }
 }
 
-// chunk boxes of the large visible leaves (common.cuh WB_BIG_LEAF), from the packed triangles the leaf pass just wrote.
-// One thread per position finds the large leaves that start there; each of them is then worked on by the whole warp,
-// one lane per chunk.  Nothing to do -- one header read per block -- for trees without such leaves.
-__global__ void __launch_bounds__(BT)
-k_chunk_boxes(int n, const TreeHeader* __restrict__ hdr, const int* __restrict__ pos_parent, const NodeRec* __restrict__ pairs,
-              const float4* __restrict__ tris, float4* __restrict__ chunks)
-{
-    if (!hdr->deep && (unsigned)hdr->leaf_size <= WB_BIG_LEAF)
-        return;
-    const int lane = (int)(threadIdx.x & 31);
-    for (int base = blockIdx.x * BT; base < n; base += gridDim.x * BT) {
-        const int p = base + (int)threadIdx.x;
-        int count = 0;
-        if (p < n) {
-            const int parent = __ldg(pos_parent + p);
-            if (parent == WB_ROOT_PARENT) {
-                count = n;
-            } else if (parent >= 0) {
-                const int ps = parent - n;
-                count = p <= ps ? ps - p + 1 : (int)pairs[2 * (size_t)ps + 1].aux - ps;
-            }
-        }
-        unsigned todo = __ballot_sync(0xffffffffu, (unsigned)count > WB_BIG_LEAF);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int start = __shfl_sync(0xffffffffu, p, src), cnt = __shfl_sync(0xffffffffu, count, src);
-            const int nchunks = cnt / 4;
-            for (int c = lane; c < nchunks; c += 32) {
-                const int first = start + 4 * c, last = (c == nchunks - 1) ? start + cnt - 1 : first + 3;
-                float3 lo = make_float3(FLT_MAX, FLT_MAX, FLT_MAX), hi = make_float3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
-                for (int q = first; q <= last; ++q) {
-                    const float4 t0 = tris[3 * (size_t)q], t1 = tris[3 * (size_t)q + 1], t2 = tris[3 * (size_t)q + 2];
-                    const float3 a = make_float3(t0.x, t0.y, t0.z), b = make_float3(t0.w, t1.x, t1.y), c3 = make_float3(t1.z, t1.w, t2.x);
-                    lo = wb_min3(lo, wb_min3(wb_min3(a, b), c3));
-                    hi = wb_max3(hi, wb_max3(wb_max3(a, b), c3));
-                }
-                chunks[2 * (size_t)(first >> 2)] = make_float4(lo.x, lo.y, lo.z, 0.f);
-                chunks[2 * (size_t)(first >> 2) + 1] = make_float4(hi.x, hi.y, hi.z, 0.f);
-            }
-        }
-    }
-}
-
 }  // namespace
-
-void wb_chunk_boxes(BvhState& s, cudaStream_t stream)
-{
-    if (!s.is_mesh || s.n <= (int)WB_BIG_LEAF || !s.chunks)
-        return;
-    const int grid = min(148 * 4, wb_div_up(s.n, BT));
-    k_chunk_boxes<<<grid, BT, 0, stream>>>(s.n, s.header, s.pos_parent, s.pairs, s.tris, s.chunks);
-}
 
 #define WB_CUDA_TRY(expr)                  \
     do {                                   \
@@ -303,7 +251,6 @@ const char* wb_refit(BvhState& s, cudaStream_t stream)
         k_refit_leaves<<<grid, BT, 0, stream>>>(BoxSource { s.item_lowers, s.item_uppers }, s.n, s.prim, s.pos_parent,
                                                 s.pairs, s.tris, s.header);
     WB_CUDA_TRY(cudaGetLastError());
-    wb_chunk_boxes(s, stream);  // large leaves: chunk boxes from the refreshed triangles
     if (!wave)
         return wb_refit_merge(s, stream);
     const MergeArgs<uint32_t> ma { s.n, s.leaf_size, nullptr, s.prim, s.pairs, s.parent_int, s.pos_parent, s.counters, s.header,

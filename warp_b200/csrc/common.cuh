@@ -62,15 +62,8 @@ struct TreeView {
     const int* prim;             // primitive_indices (sorted position -> item)
     const int* parent_int;       // parent (reference index) of internal node n+s, WB_NO_PARENT for the root
     const int* pos_parent;       // parent of the visible leaf that starts at a sorted position (state.h)
-    const float4* chunks;        // boxes of 4-position chunks of LARGE visible leaves (> WB_BIG_LEAF items), 2 float4 per slot
     int n;
 };
-
-// A visible leaf of more than WB_BIG_LEAF items (depth-rule leaves: ~100 triangles on a 100 M-triangle mesh; or a leaf size
-// above 8) is cut into chunks of 4 consecutive positions -- the last chunk takes the remainder, 4..7 positions -- and the box
-// of the chunk that starts at position f is kept at chunks[2 * (f >> 2)]: distinct chunks never share a slot because every
-// chunk covers at least 4 positions.  The closest-point walk tests a chunk's box before touching its triangles.
-#define WB_BIG_LEAF 8u
 
 #define WB_TRI_SLIVER 1u
 

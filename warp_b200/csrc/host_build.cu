@@ -239,8 +239,7 @@ const char* wb_build_host(BvhState& s, cudaStream_t stream)
 
     TreeHeader h;
     memset(&h, 0, sizeof(h));
-    h.root_ref = t.root_ref, h.root_count = (uint32_t)n, h.height = t.depth, h.n = n, h.leaf_size = s.leaf_size;
-    h.deep = t.depth >= WB_QUERY_STACK ? 1 : 0;  // depth-forced leaves may hold more than leaf_size items (chunk boxes, bvh_refit.cu)
+    h.root_ref = t.root_ref, h.root_count = (uint32_t)n, h.height = t.depth, h.deep = 0, h.n = n, h.leaf_size = s.leaf_size;
     WB_TRY(cudaMemcpyAsync(s.header, &h, sizeof(h), cudaMemcpyHostToDevice, stream));
     WB_TRY(cudaMemcpyAsync(s.prim, t.order.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, stream));
     WB_TRY(cudaMemcpyAsync(s.pos_parent, t.pos_parent.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, stream));

@@ -331,26 +331,7 @@ __device__ __forceinline__ bool closest_point(const TreeView& tv, const TreeHead
             // to nodes (a triangle is never nearer than its box), at a quarter of the instructions.  Ordinary leaves
             // (<= leaf_size triangles) skip the pre-test: it costs more than it saves there (-1 % on C2).
             const bool big_leaf = cur.b > WB_LEAF_PRETEST;
-            const uint32_t end = start + cur.b;
-            const uint32_t nchunks = (big_leaf && tv.chunks) ? cur.b / 4u : 0u;  // WB_LEAF_PRETEST == WB_BIG_LEAF
-            uint32_t chunk_end = nchunks ? start : end;  // positions below chunk_end belong to a chunk whose box passed
-            for (uint32_t pos = start; pos < end; ++pos) {
-                if (pos == chunk_end && nchunks) {
-                    // entering the next chunk of a large leaf: its box first (one 32-byte fetch instead of 4..7 triangles);
-                    // a chunk whose box is farther than the best so far cannot hold a nearer triangle, nor an equally near
-                    // one that would win -- updates need strictly smaller distances
-                    const uint32_t c = (pos - start) / 4u;
-                    const uint32_t last = (c == nchunks - 1u) ? end : pos + 4u;
-                    const float4 c0 = __ldg(tv.chunks + 2 * (size_t)(pos >> 2)), c1 = __ldg(tv.chunks + 2 * (size_t)(pos >> 2) + 1);
-                    if (COUNT)
-                        cnt.pairs++;  // counted with the node fetches (half a pair: 32 bytes)
-                    if (dist_aabb_sq(point, make_float3(c0.x, c0.y, c0.z), make_float3(c1.x, c1.y, c1.z)) > best) {
-                        pos = last - 1u;  // skip the chunk
-                        chunk_end = last;
-                        continue;
-                    }
-                    chunk_end = last;
-                }
+            for (uint32_t pos = start; pos < start + cur.b; ++pos) {
                 const Tri t = load_tri(tv.tris, pos);
                 if (COUNT)
                     cnt.tris++;

@@ -41,7 +41,6 @@ struct BvhState {
     int* pos_parent = nullptr;    // n: parent of the visible leaf starting at sorted position i, else -1
     unsigned* counters = nullptr; // n-1 arrival counters (build: count | height<<8; refit: parity)
     float4* tris = nullptr;       // 3n packed triangles in sorted order (mesh only)
-    float4* chunks = nullptr;     // 2 (n / 4 + 2) float4: chunk boxes of large visible leaves (mesh only; common.cuh WB_BIG_LEAF)
     TreeHeader* header = nullptr;
     uint16_t* heights = nullptr;  // n-1: height of internal node n+s (original leaves = 0), capped at 0xffff
 
@@ -104,7 +103,6 @@ struct MeshState {
 const char* wb_build(BvhState& s, cudaStream_t stream);
 const char* wb_build_host(BvhState& s, cudaStream_t stream);  // constructor_type 0 (sah) / 1 (median), host_build.cu
 const char* wb_refit(BvhState& s, cudaStream_t stream);
-void wb_chunk_boxes(BvhState& s, cudaStream_t stream);  // (bvh_refit.cu) refresh BvhState::chunks from the packed triangles
 extern int g_wb_small_nodes;  // experiment switch of the builder's Karras-style small-node pass (bvh_build.cu)
 extern int g_wb_refit_mode;  // default refit mode of new trees: 0 auto, 1 atomic counters, 2 wavefront
 const char* wb_refit_plan(BvhState& s, cudaStream_t stream);  // (bvh_build.cu: shares the radix sort)
