@@ -106,7 +106,11 @@ def capture_end(device=None, stream: Stream | None = None) -> Graph:
     if not c.wp_cuda_graph_create_exec(dev.context, s, graph, ctypes.byref(graph_exec)):
         c.wp_cuda_graph_destroy(dev.context, graph)
         raise RuntimeError(f"Failed to instantiate the captured graph: {_lib.error_string()}")
-    return Graph(dev, graph, graph_exec)
+    g = Graph(dev, graph, graph_exec)
+    # the captured kernels point into the capture stream's grow-only scratch (query ordering), which is released when the
+    # stream is destroyed: the graph keeps the stream alive
+    g._captured_on = stream
+    return g
 
 
 def capture_launch(graph: Graph, stream: Stream | None = None) -> None:

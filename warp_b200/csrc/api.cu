@@ -518,7 +518,32 @@ void* wp_cuda_stream_create(void* context, int priority)
         return nullptr;
     return s;
 }
-void wp_cuda_stream_destroy(void*, void* stream) { cudaStreamDestroy((cudaStream_t)stream); }
+void wp_cuda_stream_destroy(void*, void* stream)
+{
+    // the stream's query-ordering scratch (per (device, stream), up to ~45 bytes per query of the largest batch) goes with
+    // it: a program that creates a stream per captured graph would otherwise keep every scratch forever
+    std::vector<OrderScratch*> gone;
+    {
+        std::lock_guard<std::mutex> g(g_lock);
+        for (auto it = g_order.begin(); it != g_order.end();) {
+            if (it->first.second == (cudaStream_t)stream) {
+                gone.push_back(it->second);
+                it = g_order.erase(it);
+            } else {
+                ++it;
+            }
+        }
+    }
+    if (!gone.empty())
+        cudaStreamSynchronize((cudaStream_t)stream);  // nothing on the stream may still read the scratch
+    for (OrderScratch* ws : gone) {
+        if (ws) {
+            wb_order_free(*ws);
+            delete ws;
+        }
+    }
+    cudaStreamDestroy((cudaStream_t)stream);
+}
 void wp_cuda_stream_synchronize(void* stream) { check(cudaStreamSynchronize((cudaStream_t)stream), "stream synchronize"); }
 void* wp_cuda_event_create(void* context, unsigned flags)
 {
