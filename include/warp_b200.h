@@ -330,6 +330,12 @@ WP_B200_API int wp_b200_bvh_get_option(uint64_t id, const char* name, int* value
  * afterwards keeps the reference-layout mirror of its descriptor (node_lowers / node_uppers / node_parents / root,
  * Mesh::lowers / uppers, average_edge_length) current after create / refit / rebuild / set_points, so unmodified Warp
  * kernels can traverse through `id`.  Off by default (the mirror costs one extra pass per refit). */
+/* host-only (needs no device): item order (primitive_indices) and leaf starts of the sah (0) / median (1) tree the library
+ * builds for these boxes (csrc/host_build.cu, restating warp/native/bvh.cpp:216-572); returns the tree depth, -1 on bad
+ * arguments.  For CPU-side parity checks against the reference's host builder. */
+WP_B200_API int wp_b200_host_build_order(const float* lowers, const float* uppers, int n, int leaf_size, int constructor_type,
+                                         int* order_out, unsigned char* leaf_start_out);
+
 /* switches of measured-and-rejected alternatives kept as tested code paths: "small_nodes" = 1 / 0 / -1 (environment
  * default) -- the builder's Karras-style pass over small distinct-key nodes.  1 ok / 0 unknown */
 WP_B200_API int wp_b200_set_experiment(const char* name, int value);

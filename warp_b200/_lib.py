@@ -141,6 +141,7 @@ SIGNATURES = {
     "wp_b200_mesh_create_device_ex": (_u64, [_vp, array_t, array_t, array_t, _i, _i, _i, _i, _vp, _i, _i]),
     "wp_b200_bvh_set_option": (_i, [_u64, ctypes.c_char_p, _i]),
     "wp_b200_bvh_get_option": (_i, [_u64, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int)]),
+    "wp_b200_host_build_order": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "wp_b200_set_experiment": (_i, [ctypes.c_char_p, _i]),
     "wp_b200_set_auto_reference_layout": (None, [_i]),
     "wp_b200_get_auto_reference_layout": (_i, []),

@@ -209,6 +209,25 @@ __global__ void k_triangle_bounds(const float* __restrict__ points, const int* _
 
 }  // namespace
 
+// Host-only entry point (no device needed): the item order and the visible leaves of the sah / median tree over the given
+// boxes -- what tests/test_host_builders_cpu.py pins against the reference's own host builder on every CPU-only run.
+// order_out[n] = primitive_indices; leaf_start_out[n] = 1 where a leaf starts at that sorted position.  Returns the depth.
+extern "C" __attribute__((visibility("default"))) int wp_b200_host_build_order(const float* lowers, const float* uppers, int n,
+                                                                               int leaf_size, int constructor_type,
+                                                                               int* order_out, unsigned char* leaf_start_out)
+{
+    if (n <= 0 || leaf_size < 1 || (constructor_type != 0 && constructor_type != 1))
+        return -1;
+    HostTree t;
+    build_top_down(Items { lowers, uppers }, n, leaf_size, constructor_type, t);
+    for (int i = 0; i < n; ++i) {
+        order_out[i] = t.order[i];
+        if (leaf_start_out)
+            leaf_start_out[i] = t.pos_parent[i] != WB_NO_PARENT ? 1 : 0;
+    }
+    return t.depth;
+}
+
 // Builds the tree of an allocated BvhState (wb_alloc_tree) with the host constructor s.constructor_type (0 sah, 1 median),
 // uploads it and refits it.  Synchronises `stream` (the item bounds have to reach the host first, as in the reference).
 const char* wb_build_host(BvhState& s, cudaStream_t stream)
